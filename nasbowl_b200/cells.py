@@ -1,0 +1,193 @@
+"""Packed cell batches: the HBM data layout of the WL hot path.
+
+A *cell* is a small labelled DAG (NAS-Bench-101: <=7 nodes, NAS-Bench-201: <=8, DARTS: <=15;
+reference generators bayesopt/generate_test_graphs.py:543-641, darts/utils.py:11-98).  The
+reference hands cells around as ``networkx.DiGraph`` objects with an ``op_name`` node
+attribute and converts them one at a time into GraKeL's ``[{(u,v):1}, {node:label}, None]``
+triple (kernels/weisfilerlehman.py:134-136).  Here a batch of N cells is ONE contiguous array
+of fixed-stride records, so a sub-warp reads a whole cell with one coalesced vector load:
+
+    n_max = 8  : 16-byte record  = labels[8]  u8 | succ[8]  u8   (one 128-bit load)
+    n_max = 16 : 48-byte record  = labels[16] u8 | succ[16] u16  (three 128-bit loads)
+
+``labels[v]`` is the op code of node v (0xFF = no node); ``succ[v]`` is the bitmask of v's
+successors (bit j set <=> edge v->j): a bit-packed CSR row, the neighbourhood the reference's
+WL aggregates over (weisfeiler_lehman.py:266-267, Assumption A1 of SURVEY.md).  Nodes are
+renumbered 0..k-1 in ascending order of their original ids (NB201/DARTS cells delete nodes
+without renumbering: generate_test_graphs.py:155,168).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Iterable, List, Optional, Sequence
+
+import numpy as np
+
+NO_NODE = 0xFF
+MAX_OPS = 255
+
+
+class OpVocab:
+    """Append-only map op-name -> u8 op code shared by every batch fed to one kernel object."""
+
+    def __init__(self, names: Optional[Sequence[str]] = None):
+        self.names: List[str] = []
+        self._code = {}
+        for n in names or ():
+            self.code(n)
+
+    def code(self, name) -> int:
+        c = self._code.get(name)
+        if c is None:
+            c = len(self.names)
+            if c >= MAX_OPS:
+                raise ValueError("more than %d distinct op names" % MAX_OPS)
+            self._code[name] = c
+            self.names.append(name)
+        return c
+
+    def __len__(self):
+        return len(self.names)
+
+    def __getstate__(self):
+        return {"names": list(self.names)}
+
+    def __setstate__(self, st):
+        self.__init__(st["names"])
+
+
+def record_stride(n_max: int) -> int:
+    if n_max == 8:
+        return 16
+    if n_max == 16:
+        return 48
+    raise ValueError("n_max must be 8 or 16, got %r" % (n_max,))
+
+
+@dataclass
+class CellBatch:
+    """N packed cells. ``labels``: (N, n_max) u8, ``succ``: (N, n_max) u16 (host-side view)."""
+    n_max: int
+    labels: np.ndarray
+    succ: np.ndarray
+
+    def __post_init__(self):
+        record_stride(self.n_max)
+        self.labels = np.ascontiguousarray(self.labels, dtype=np.uint8)
+        self.succ = np.ascontiguousarray(self.succ, dtype=np.uint16)
+        assert self.labels.shape == self.succ.shape and self.labels.shape[1] == self.n_max
+
+    def __len__(self):
+        return self.labels.shape[0]
+
+    @property
+    def n_nodes(self) -> np.ndarray:
+        return (self.labels != NO_NODE).sum(axis=1)
+
+    @property
+    def n_edges(self) -> np.ndarray:
+        s = self.succ.astype(np.uint32)
+        cnt = np.zeros(s.shape, dtype=np.uint32)
+        for j in range(self.n_max):
+            cnt += (s >> j) & 1
+        return cnt.sum(axis=1)
+
+    def to_records(self) -> np.ndarray:
+        """Device layout: (N, stride) u8."""
+        n = len(self)
+        rec = np.empty((n, record_stride(self.n_max)), dtype=np.uint8)
+        rec[:, :self.n_max] = self.labels
+        if self.n_max == 8:
+            rec[:, 8:16] = self.succ.astype(np.uint8)
+        else:
+            rec[:, 16:48] = self.succ.astype("<u2").view(np.uint8).reshape(n, 32)
+        return rec
+
+    @staticmethod
+    def from_records(rec: np.ndarray, n_max: int) -> "CellBatch":
+        rec = np.ascontiguousarray(rec, dtype=np.uint8).reshape(-1, record_stride(n_max))
+        labels = rec[:, :n_max].copy()
+        if n_max == 8:
+            succ = rec[:, 8:16].astype(np.uint16)
+        else:
+            succ = rec[:, 16:48].copy().view("<u2").astype(np.uint16)
+        return CellBatch(n_max, labels, succ)
+
+    def __getitem__(self, idx) -> "CellBatch":
+        if isinstance(idx, (int, np.integer)):
+            idx = slice(idx, idx + 1)
+        return CellBatch(self.n_max, self.labels[idx], self.succ[idx])
+
+    @staticmethod
+    def concat(batches: Iterable["CellBatch"]) -> "CellBatch":
+        batches = list(batches)
+        n_max = max(b.n_max for b in batches)
+        batches = [b.widen(n_max) for b in batches]
+        return CellBatch(n_max, np.concatenate([b.labels for b in batches]),
+                         np.concatenate([b.succ for b in batches]))
+
+    def widen(self, n_max: int) -> "CellBatch":
+        if n_max == self.n_max:
+            return self
+        assert n_max > self.n_max
+        n = len(self)
+        labels = np.full((n, n_max), NO_NODE, dtype=np.uint8)
+        succ = np.zeros((n, n_max), dtype=np.uint16)
+        labels[:, :self.n_max] = self.labels
+        succ[:, :self.n_max] = self.succ
+        return CellBatch(n_max, labels, succ)
+
+    def to_undirected(self) -> "CellBatch":
+        """Symmetrise adjacency (reference kernels/utils.py:511-521 via `undirected=True`)."""
+        s = self.succ.astype(np.uint32)
+        pred = np.zeros_like(s)
+        for u in range(self.n_max):
+            for v in range(self.n_max):
+                pred[:, v] |= ((s[:, u] >> v) & 1) << u
+        return CellBatch(self.n_max, self.labels, (s | pred).astype(np.uint16))
+
+    def to_networkx(self, vocab: OpVocab, node_label: str = "op_name"):
+        import networkx as nx
+        out = []
+        for i in range(len(self)):
+            g = nx.DiGraph()
+            for v in range(self.n_max):
+                if self.labels[i, v] != NO_NODE:
+                    g.add_node(v, **{node_label: vocab.names[self.labels[i, v]]})
+            for v in range(self.n_max):
+                m = int(self.succ[i, v])
+                for j in range(self.n_max):
+                    if (m >> j) & 1:
+                        g.add_edge(v, j)
+            out.append(g)
+        return out
+
+
+def pack_networkx(graphs, vocab: OpVocab, node_label: str = "op_name",
+                  undirected: bool = False, n_max: Optional[int] = None) -> CellBatch:
+    """list[nx.DiGraph] -> CellBatch (the conversion the reference does with
+    grakel.utils.graph_from_networkx, kernels/weisfilerlehman.py:134-136)."""
+    graphs = list(graphs)
+    need = max((g.number_of_nodes() for g in graphs), default=0)
+    if n_max is None:
+        n_max = 8 if need <= 8 else 16
+    if need > n_max or n_max not in (8, 16):
+        raise ValueError("cells with more than 16 nodes are not supported (got %d)" % need)
+    n = len(graphs)
+    labels = np.full((n, n_max), NO_NODE, dtype=np.uint8)
+    succ = np.zeros((n, n_max), dtype=np.uint16)
+    for i, g in enumerate(graphs):
+        order = sorted(g.nodes())
+        pos = {v: k for k, v in enumerate(order)}
+        for v in order:
+            try:
+                name = g.nodes[v][node_label]
+            except KeyError:
+                raise ValueError("node %r of graph %d has no %r attribute" % (v, i, node_label))
+            labels[i, pos[v]] = vocab.code(name)
+        directed = g.is_directed()
+        for u, v in g.edges():
+            succ[i, pos[u]] |= np.uint16(1 << pos[v])
+            if undirected or not directed:
+                succ[i, pos[v]] |= np.uint16(1 << pos[u])
+    return CellBatch(n_max, labels, succ)

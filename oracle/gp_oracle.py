@@ -1,0 +1,242 @@
+"""TEST INFRASTRUCTURE — fp64 CPU restatement of the reference's GP surrogate and acquisitions.
+
+Not part of the product (see oracle/wl_oracle.py header).  Follows, formula by formula:
+
+* y normalisation              bayesopt/utils.py:72-85
+* Cholesky inverse + "logDetK" bayesopt/utils.py:120-140   (sign quirk; jitter retry Q7)
+* marginal likelihood          bayesopt/utils.py:102-117
+* WL-depth grid search         bayesopt/gp.py:493-538       (un-normalised Gram, strict <, Q5)
+* cosine normalisation         kernels/combine_kernels.py:36-56
+* noise optimisation (Adam)    bayesopt/gp.py:179-219       (Q9)
+* posterior                    bayesopt/gp.py:240-283       (Q11)
+* EI / AEI / UCB, incumbent    bayesopt/acquisitions.py:59-92,130-138 (Q12-Q14)
+* top-n distinct by value      bayesopt/acquisitions.py:94-113 (Q15)
+
+The reference evaluates the GP in fp32 (Q8); this restatement evaluates the same formulas in
+fp64 and is validated against the reference at fp32 tolerance (tests/test_oracle_golden.py).
+Quantities that the reference *stores* in fp32 and feeds back (the noise lambda) are rounded
+to fp32 here too so that h*, lambda and the clamp threshold agree exactly.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import wl_oracle
+
+_LOG_2PI = math.log(2.0 * math.pi)
+
+
+def f32(x) -> float:
+    return float(np.float32(x))
+
+
+def normalize_y(y):
+    """(y - mean) / std with the unbiased std of torch.std (utils.py:72-76)."""
+    y = np.asarray(y, dtype=np.float64)
+    mean = y.mean()
+    std = y.std(ddof=1)
+    return (y - mean) / std, mean, std
+
+
+def pd_inverse(K: np.ndarray, jitter: float):
+    """compute_pd_inverse (utils.py:120-140): Cholesky of K + jitter*10^k*I, k = 0,1,2;
+    logDetK := -2*sum(log(diag(L))) i.e. MINUS log|K| (the reference's sign quirk)."""
+    n = K.shape[0]
+    L = None
+    for k in range(3):
+        try:
+            L = np.linalg.cholesky(K + jitter * (10 ** k) * np.eye(n))
+            break
+        except np.linalg.LinAlgError:
+            continue
+    if L is None:
+        raise RuntimeError("Gram matrix not positive definite despite of jitter")
+    logdet_quirk = -2.0 * np.log(np.diag(L)).sum()
+    Linv = np.linalg.solve(L, np.eye(n))
+    K_i = Linv.T @ Linv
+    return K_i, logdet_quirk, L
+
+
+def nlml_prime(K_i, logdet_quirk, y) -> float:
+    """-compute_log_marginal_likelihood(...) (utils.py:102-117), the quantity the reference
+    minimises: (1/2 y^T K^-1 y + 1/2 logDetK_quirk + n/2 log 2pi) / n."""
+    n = y.shape[0]
+    lml = -0.5 * float(y @ K_i @ y) - 0.5 * logdet_quirk - n / 2.0 * _LOG_2PI
+    return -lml / n
+
+
+def grid_search_h(K_levels: np.ndarray, y_norm, lik: float, candidates: Sequence[int]):
+    """_grid_search_wl_kernel (gp.py:493-538).  K_levels[l] = integer Gram of WL level l, so
+    K_raw(h) = sum_{l<=h} K_levels[l].  Returns (h*, [nlml'(h) for h in candidates])."""
+    best, best_h, vals = math.inf, None, []
+    csum = np.cumsum(K_levels.astype(np.float64), axis=0)
+    for hc in candidates:
+        K_i, ld, _ = pd_inverse(csum[hc], lik)
+        v = nlml_prime(K_i, ld, y_norm)
+        vals.append(v)
+        if v < best:
+            best, best_h = v, hc
+    return best_h, vals
+
+
+def normalize_gram(K_raw: np.ndarray) -> np.ndarray:
+    """K / sqrt(diag ⊗ diag) (combine_kernels.py:54-56)."""
+    d = np.sqrt(np.diag(K_raw).astype(np.float64))
+    return K_raw.astype(np.float64) / np.outer(d, d)
+
+
+def optimise_noise(K: np.ndarray, y_norm, lik0: float, iters: int = 20, lr: float = 0.1,
+                   max_lik: float = 0.01):
+    """The Adam loop of GraphGP.fit on the scalar noise lambda (gp.py:179-210), fp32 state.
+
+    d nlml'/d lambda = -(1/2 |K_l^-1 y|^2 + 1/2 tr K_l^-1) / n  (always negative because of
+    the Q6 sign quirk).  Returns (lambda_final, nlml' of the last loop iteration)."""
+    lam = np.float32(lik0)
+    m = np.float32(0.0)
+    v = np.float32(0.0)
+    b1, b2, eps = np.float32(0.9), np.float32(0.999), np.float32(1e-8)
+    n = y_norm.shape[0]
+    last = None
+    for t in range(1, iters + 1):
+        K_i, ld, _ = pd_inverse(K, float(lam))
+        last = nlml_prime(K_i, ld, y_norm)
+        alpha = K_i @ y_norm
+        g = np.float32(-(0.5 * float(alpha @ alpha) + 0.5 * float(np.trace(K_i))) / n)
+        m = b1 * m + (np.float32(1) - b1) * g
+        v = b2 * v + (np.float32(1) - b2) * g * g
+        bc1 = np.float32(1.0 - 0.9 ** t)
+        bc2 = np.float32(1.0 - 0.999 ** t)
+        denom = np.float32(np.sqrt(v) / np.sqrt(bc2)) + eps
+        lam = np.float32(lam - (np.float32(lr) / bc1) * (m / denom))
+        lam = np.float32(min(max(lam, np.float32(1e-5)), np.float32(max_lik)))
+    return float(lam), last
+
+
+@dataclass
+class GPState:
+    """What GraphGP holds after fit() (gp.py:212-219) plus what predict() needs."""
+    h: int
+    oa: bool
+    lik: float
+    y_mean: float
+    y_std: float
+    y_norm: np.ndarray
+    y_raw: np.ndarray
+    K: np.ndarray            # normalised training Gram
+    K_i: np.ndarray          # (K + lik I)^-1
+    logDetK: float           # quirk sign
+    L: np.ndarray
+    diag_raw: np.ndarray     # K_raw(x_i, x_i)
+    nlml: Optional[float] = None
+    nlml_grid: list = field(default_factory=list)
+
+
+def gp_fit(train, y, h_candidates: Sequence[int] = tuple(range(5)), oa: bool = False,
+           likelihood: float = 1e-3, optimize_lik: bool = True, max_lik: float = 0.01,
+           iters: int = 20, h_fixed: Optional[int] = None) -> GPState:
+    """GraphGP(...).fit(...) for a single WL kernel (gp.py:107-238)."""
+    y = np.asarray(y, dtype=np.float64)
+    y_norm, y_mean, y_std = normalize_y(y)
+    lik = f32(likelihood)
+    grid = []
+    if len(h_candidates):
+        hmax = max(h_candidates)
+        K_levels = wl_oracle.gram_raw_levels(train, hmax, oa)
+        h_star, grid = grid_search_h(K_levels, y_norm, lik, h_candidates)
+        K_raw = K_levels[:h_star + 1].sum(axis=0)
+    else:
+        h_star = h_fixed
+        K_raw = wl_oracle.gram_raw(train, h_star, oa)
+    K = normalize_gram(K_raw)
+    nlml = None
+    if optimize_lik:
+        lik, nlml = optimise_noise(K, y_norm, lik, iters=iters, max_lik=max_lik)
+    K_i, ld, L = pd_inverse(K, lik)
+    return GPState(h=h_star, oa=oa, lik=lik, y_mean=float(y_mean), y_std=float(y_std),
+                   y_norm=y_norm, y_raw=y, K=K, K_i=K_i, logDetK=ld, L=L,
+                   diag_raw=np.diag(K_raw).astype(np.float64), nlml=nlml, nlml_grid=grid)
+
+
+def gp_predict_diag(st: GPState, train, pool, chunk: int = 4096):
+    """Posterior mean and marginal variance over a pool (gp.py:240-283, diagonal only):
+    mu = (K_s^T K_i y)*y_std + y_mean ; var = clamp(1 + lik - k_s^T K_i k_s, lik) * y_std^2."""
+    M = len(pool)
+    mu = np.empty(M)
+    var = np.empty(M)
+    a = st.K_i @ st.y_norm
+    for s in range(0, M, chunk):
+        sub = pool[s:s + chunk]
+        K_s_raw, kss, ktt = wl_oracle.pool_features(train, sub, st.h, st.oa)
+        K_s = K_s_raw / np.sqrt(np.outer(ktt, kss))
+        mu[s:s + chunk] = (K_s.T @ a) * st.y_std + st.y_mean
+        q = np.einsum("ij,ij->j", K_s, st.K_i @ K_s)
+        cov = np.maximum(1.0 + st.lik - q, st.lik)
+        var[s:s + chunk] = (np.sqrt(cov) * st.y_std) ** 2
+    return mu, var
+
+
+def gp_predict_full(st: GPState, train, pool):
+    """(mu [M], cov [M, M]) exactly as GraphGP.predict returns them, incl. the element-wise
+    clamp of the full covariance (gp.py:276)."""
+    n, M = len(train), len(pool)
+    from nasbowl_b200.cells import CellBatch
+    joint = CellBatch.concat([train, pool])
+    K_full = normalize_gram(wl_oracle.gram_raw(joint, st.h, st.oa))
+    K_s = K_full[:n, n:]
+    K_ss = K_full[n:, n:] + st.lik * np.eye(M)
+    mu = (K_s.T @ st.K_i @ st.y_norm) * st.y_std + st.y_mean
+    cov = np.maximum(K_ss - K_s.T @ st.K_i @ K_s, st.lik)
+    cov = (np.sqrt(cov) * st.y_std) ** 2
+    return mu, cov
+
+
+def incumbent(st: GPState) -> float:
+    """_get_incumbent (acquisitions.py:82-92): `in_fill == 'max'` is never true (Q13), so the
+    incumbent is y_raw[argmax of the posterior mean at the training points]."""
+    mu_train = st.K @ (st.K_i @ st.y_norm)
+    return float(st.y_raw[int(np.argmax(mu_train))])
+
+
+def _phi(u):
+    return np.exp(-0.5 * u * u) / math.sqrt(2.0 * math.pi)
+
+
+def _Phi(u):
+    from scipy.special import erfc
+    return 0.5 * erfc(-u / math.sqrt(2.0))
+
+
+def expected_improvement(mu, var, mu_star: float, xi: float = 0.0, augmented: bool = False,
+                         lik: float = 0.0):
+    """EI = std*pdf(u) + (mu - mu* - xi)*cdf(u), u = (mu - mu* - xi)/std (acquisitions.py:68-74);
+    AEI factor 1 - sqrt(lik)/sqrt(lik + var) (:75-77)."""
+    std = np.sqrt(var)
+    d = mu - mu_star - xi
+    u = d / std
+    ei = std * _phi(u) + d * _Phi(u)
+    if augmented:
+        ei = ei * (1.0 - math.sqrt(lik) / np.sqrt(lik + var))
+    return ei
+
+
+def ucb_beta(iters: int) -> float:
+    """3*sqrt(0.5*log(2*iters+1)) (acquisitions.py:133-135)."""
+    return 3.0 * math.sqrt(0.5 * math.log(2.0 * iters + 1.0))
+
+
+def upper_confidence_bound(mu, var, beta: float):
+    return mu + beta * np.sqrt(var)
+
+
+def top_n_distinct(scores: np.ndarray, top_n: int) -> np.ndarray:
+    """propose_location's selection (acquisitions.py:101-105): first index of each distinct
+    score value, then the top_n largest distinct values.  Order unspecified -> returns the
+    indices sorted by descending score (compare as sets against the reference)."""
+    vals, first = np.unique(np.asarray(scores).reshape(-1), return_index=True)
+    take = min(top_n, vals.shape[0])
+    sel = np.argsort(-vals, kind="stable")[:take]
+    return first[sel]

@@ -1,0 +1,43 @@
+"""TEST INFRASTRUCTURE — loads the *unmodified* reference from /root/reference under import shims.
+
+Only usable in the build container (the reference tree does not travel to the GPU box).
+Used by oracle/make_golden.py to generate tests/golden/*.npz and by the optional
+`tests/test_oracle_vs_reference.py` differential tests (skipped when the tree is absent).
+"""
+import collections
+import collections.abc
+import os
+import sys
+import warnings
+
+REFERENCE_ROOT = os.environ.get("NASBOWL_REFERENCE", "/root/reference")
+_SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_shims")
+
+
+def reference_available() -> bool:
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "grakel_replace"))
+
+
+def load_reference():
+    """Return a namespace with the reference's hot-path classes (imports are cached)."""
+    if not reference_available():
+        raise RuntimeError("reference tree not found at " + REFERENCE_ROOT)
+    # py3.10+ removed the alias the vendored grakel code imports (vertex_histogram.py:4)
+    if not hasattr(collections, "Iterable"):
+        collections.Iterable = collections.abc.Iterable
+    for p in (_SHIMS, REFERENCE_ROOT):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    warnings.filterwarnings("ignore")
+    import types
+    import kernels as ref_kernels                      # noqa: E402
+    import bayesopt as ref_bayesopt                    # noqa: E402
+    from bayesopt import generate_test_graphs as gtg   # noqa: E402
+    ns = types.SimpleNamespace(
+        kernels=ref_kernels, bayesopt=ref_bayesopt, gtg=gtg,
+        WeisfilerLehman=ref_kernels.WeisfilerLehman, SumKernel=ref_kernels.SumKernel,
+        GraphGP=ref_bayesopt.GraphGP,
+        GraphExpectedImprovement=ref_bayesopt.GraphExpectedImprovement,
+        GraphUpperConfidentBound=ref_bayesopt.GraphUpperConfidentBound,
+    )
+    return ns
