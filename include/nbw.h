@@ -1,0 +1,243 @@
+/*
+ * nbw.h — C-ABI of the B200-native NAS-BOWL surrogate-scoring path (libnbw.so).
+ *
+ * The reference (xingchenwan/nasbowl) is pure Python and has no FFI; the entry points below
+ * are what a maintainer would bind (ctypes) to replace, one for one, the
+ * Python functions of the hot path.  Each entry cites the reference interface it replaces.
+ *
+ * Conventions
+ *   - every function returns an nbw_status (0 = OK) and never throws; nbw_last_error() gives
+ *     the message of the last failure on that context;
+ *   - pointers are DEVICE pointers unless the name ends in _h (host);
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued on it and, unless stated
+ *     ("syncs"), the call returns without waiting;
+ *   - one nbw_ctx per GPU / rank, used from the thread that owns the CUDA context; the
+ *     context owns a scratch arena that grows on demand (nbw_reserve pre-sizes it);
+ *   - cells are packed records (nasbowl_b200/cells.py): n_max = 8 -> 16-byte record
+ *     labels[8] u8 | succ[8] u8, n_max = 16 -> 48-byte record labels[16] u8 | succ[16] u16;
+ *     label 0xFF = no node; succ[v] bit j = edge v->j (successor neighbourhood,
+ *     grakel_replace/weisfeiler_lehman.py:266-267).
+ */
+#ifndef NBW_H_
+#define NBW_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nbw_ctx nbw_ctx;
+
+typedef enum {
+  NBW_OK = 0,
+  NBW_ERR_INVALID = 1,        /* bad argument (AssertionError / TypeError in the reference) */
+  NBW_ERR_CUDA = 2,           /* CUDA runtime / driver failure */
+  NBW_ERR_NOT_PD = 3,         /* Cholesky pivot <= 0 (RuntimeError in bayesopt/utils.py:127-137) */
+  NBW_ERR_HASH_COLLISION = 4, /* two distinct WL credentials share a 64-bit key: re-run with another seed */
+  NBW_ERR_CAPACITY = 5,       /* caller-provided output buffer too small */
+  NBW_ERR_UNSUPPORTED = 6
+} nbw_status;
+
+#define NBW_MAX_LEVELS 8       /* WL depth h <= 7 */
+#define NBW_INVALID_ID 0xFFFFFFFFu
+#define NBW_INVALID_KEY 0xFFFFFFFFFFFFFFFFull
+
+int nbw_version(void);
+int nbw_create(nbw_ctx** out, int device);
+int nbw_destroy(nbw_ctx* ctx);
+const char* nbw_last_error(const nbw_ctx* ctx);
+int nbw_reserve(nbw_ctx* ctx, uint64_t scratch_bytes);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t nbw_launch_count(const nbw_ctx* ctx);
+
+/* ---------------------------------------------------------------------------------------
+ * (1) WL relabelling — replaces the credential loop of WeisfeilerLehman.parse_input,
+ *     grakel_replace/weisfeiler_lehman.py:258-296.
+ * Level 0 (ids_prev == NULL): key = op code of each node, chk = 0.
+ * Level l >= 1: key/chk = two independent 64-bit multiset hashes of
+ *     (ids_prev[v], {ids_prev[s] : s in successors(v)}), salted by (seed, level);
+ *     nodes that are not an endpoint of any edge get NBW_INVALID_KEY.
+ * keys/chks: [N * n_max] u64.  ids_prev: [N * n_max] u32 (NBW_INVALID_ID = not counted).
+ */
+int nbw_wl_signatures(nbw_ctx* ctx, const void* cells, int64_t n_cells, int n_max,
+                      const uint32_t* ids_prev, int level, uint64_t seed,
+                      uint64_t* keys, uint64_t* chks, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (2) Dictionary build: global radix sort + unique that compacts keys into dense label ids —
+ *     replaces `sorted(list(label_set))` + id assignment, weisfeiler_lehman.py:226-229,271-274.
+ * ids[i] = rank of keys[i] among the distinct valid keys (NBW_INVALID_ID for invalid keys);
+ * uniq_keys/uniq_chks[0..D) = the dictionary in ascending key order (capacity `uniq_cap`).
+ * key_bits: number of significant low key bits (8 for level 0, 64 otherwise).
+ * Verifies that equal keys carry equal chks, and (when cells != NULL) that nodes sharing a
+ * key have identical (own id, successor-id multiset) tuples — the partition is then exact,
+ * not probabilistic.  Syncs the stream; writes the dictionary size to *n_unique_h.
+ */
+int nbw_dict_build(nbw_ctx* ctx, const uint64_t* keys, const uint64_t* chks, int64_t n_keys,
+                   int key_bits, const void* cells, int n_max, const uint32_t* ids_prev,
+                   uint32_t* ids, uint64_t* uniq_keys, uint64_t* uniq_chks, int64_t uniq_cap,
+                   int64_t* n_unique_h, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (3) Vertex histograms — replaces VertexHistogram.parse_input,
+ *     grakel_replace/vertex_histogram.py:98-209 (dense Phi of small integer counts).
+ * ids: [n_levels][N * n_max] u32 stacked level-major.  Level l occupies columns
+ * [col_off_h[l], col_off_h[l+1]) of the row-major int8 matrix phi [N x ld_phi]
+ * (col_off_h and label_off_h have n_levels + 1 entries; label_off_h is only read when oa != 0);
+ * every byte of phi[:, col_off_h[0] .. col_off_h[n_levels]) is written (pad columns = 0).
+ *   oa == 0: phi[g, col_off[l] + id] = count of id in cell g at level l.
+ *   oa != 0: thermometer code of the same counts (min(a,b) = sum_t [a>=t][b>=t]), so that
+ *            Phi Phi^T equals the histogram-intersection kernel of vertex_histogram.py:233-249;
+ *            thermo_base[l-stacked id] gives the first column of each label.
+ * self_sim[g] (i32) = K_raw(g, g) = sum of squared counts (oa: number of counted nodes).
+ */
+int nbw_hist_dense_i8(nbw_ctx* ctx, const uint32_t* ids, int64_t n_cells, int n_max,
+                      int n_levels, const int64_t* col_off_h, const int64_t* label_off_h,
+                      const uint32_t* thermo_base, int oa, int8_t* phi, int64_t ld_phi,
+                      int32_t* self_sim, void* stream);
+
+/* OA support: per-label maximum count over the batch -> thermometer column bases.
+ * level_off_h[l] = first stacked label index of level l (level_off_h[n_levels] = total labels).
+ * thermo_base[i] (u32, i < total) = exclusive prefix sum of max counts *within its level*;
+ * level_width_h[l] = sum of max counts of level l.  Syncs. */
+int nbw_oa_thermo_layout(nbw_ctx* ctx, const uint32_t* ids, int64_t n_cells, int n_max,
+                         int n_levels, const int64_t* level_off_h, uint32_t* thermo_base,
+                         uint8_t* max_count, int64_t* level_width_h, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (4) Integer Gram — replaces VertexHistogram._calculate_kernel_matrix
+ *     (vertex_histogram.py:211-259) and the level sum of weisfeiler_lehman.py:316-327.
+ * C[i, j] = sum_{k in [k0, k1)} A[i, k] * B[j, k], int8 x int8 -> int32, exact.
+ * A: [m x lda] int8 row-major, B: [n x ldb] int8 row-major, C: [m x ldc] int32 row-major.
+ * tcgen05.mma kind::i8 with TMA-fed operands and TMEM accumulators; k0, k1, lda, ldb must be
+ * multiples of 128 and A, B 128-byte aligned.  impl: 0 = tcgen05 (product), 1 = SIMT dp4a
+ * cross-check kernel (test use).
+ */
+int nbw_gram_i8(nbw_ctx* ctx, const int8_t* A, int64_t m, int64_t lda, const int8_t* B,
+                int64_t n, int64_t ldb, int64_t k0, int64_t k1, int32_t* C, int64_t ldc,
+                int impl, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (5) GP linear algebra in fp64 — replaces kernels/combine_kernels.py:36-56 (weighted sum +
+ *     cosine normalisation), bayesopt/utils.py:120-140 (compute_pd_inverse) and the matrix
+ *     products of GraphGP.fit / predict (bayesopt/gp.py:173-219, 271-276).
+ * All matrices are row-major fp64 with explicit leading dimensions.
+ */
+/* out[i,j] = beta*out[i,j] + w * K[i,j] (int32 -> fp64 accumulate) */
+int nbw_gram_accumulate(nbw_ctx* ctx, const int32_t* K, int64_t ldk, int64_t m, int64_t n,
+                        double w, double beta, double* out, int64_t ldo, void* stream);
+/* Y = a*X + b*Y on m x n fp64 blocks (weighted kernel sum, combine_kernels.py:40) */
+int nbw_axpby_f64(nbw_ctx* ctx, const double* X, int64_t ldx, int64_t m, int64_t n, double a,
+                  double b, double* Y, int64_t ldy, void* stream);
+/* s[i] = 1/sqrt(K[i,i]);  K[i,j] *= s[i]*s[j]   (combine_kernels.py:54-56) */
+int nbw_gram_normalize(nbw_ctx* ctx, double* K, int64_t ld, int64_t n, double* inv_sqrt_diag,
+                       void* stream);
+/* Factor A + shift*I = L L^T (lower, in `L`, upper part zeroed).  *info_h = 0 on success,
+ * k+1 if pivot k is not positive.  Writes log|A + shift I| to *logdet_h.  Syncs. */
+int nbw_chol_f64(nbw_ctx* ctx, const double* A, int64_t lda, int64_t n, double shift,
+                 double* L, int64_t ldl, double* logdet_h, int* info_h, void* stream);
+/* Everything GraphGP.fit needs from one factorisation of K + lik*I (compute_pd_inverse,
+ * bayesopt/utils.py:120-140, plus the terms of the marginal likelihood :102-117 and of its
+ * gradient w.r.t. lik): L (lower), Linv = L^-1, alpha = (K + lik I)^-1 y and
+ *   stats_h[0] = log|K + lik I|,  stats_h[1] = y^T (K + lik I)^-1 y,  stats_h[2] = tr (K + lik I)^-1,
+ *   stats_h[3] = |alpha|^2   (stats_h has 4 entries).
+ * Syncs.  Returns NBW_ERR_NOT_PD (and *info_h = failing pivot + 1) when the factorisation breaks
+ * down; the caller retries with 10x the jitter like utils.py:127-133. */
+int nbw_gp_factor(nbw_ctx* ctx, const double* K, int64_t ldk, int64_t n, double lik,
+                  const double* y, double* L, int64_t ldl, double* Linv, int64_t ldi,
+                  double* alpha, double* stats_h, int* info_h, void* stream);
+/* Linv = L^-1 (lower triangular) */
+int nbw_trtri_lower_f64(nbw_ctx* ctx, const double* L, int64_t ldl, int64_t n, double* Linv,
+                        int64_t ldi, void* stream);
+/* C = alpha * op(A) op(B) + beta * C;  op(X) = X or X^T; C is m x n, inner dimension k */
+int nbw_gemm_f64(nbw_ctx* ctx, int trans_a, int trans_b, int64_t m, int64_t n, int64_t k,
+                 double alpha, const double* A, int64_t lda, const double* B, int64_t ldb,
+                 double beta, double* C, int64_t ldc, void* stream);
+/* B[i, j] = s[i] * sqrt_w * phi[i, k0 + j]  (int8 -> fp64), j < k1-k0 */
+int nbw_scale_features(nbw_ctx* ctx, const int8_t* phi, int64_t ld_phi, int64_t n, int64_t k0,
+                       int64_t k1, const double* s, double sqrt_w, double* B, int64_t ldb,
+                       void* stream);
+/* cov[i,j] = (sqrt(max(Kss[i,j] + (i==j)*lik - Q[i,j], lik)) * y_std)^2   (gp.py:272-280) */
+int nbw_posterior_cov_finish(nbw_ctx* ctx, const double* Kss, int64_t ldk, const double* Q,
+                             int64_t ldq, int64_t m, double lik, double y_std, double* cov,
+                             int64_t ldc, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (6) Fused pool scoring — replaces GraphGP.predict (bayesopt/gp.py:240-283, diagonal) +
+ *     GraphExpectedImprovement.eval / GraphUpperConfidentBound.eval
+ *     (bayesopt/acquisitions.py:59-80, 130-138) for a whole candidate pool in one launch.
+ *
+ * The fitted surrogate is handed over as a flat model descriptor (all device pointers):
+ * per WL level a dictionary (open-addressing table of 16-byte slots built by
+ * nbw_model_build_table), the feature-space posterior operators
+ *     w_mu = B^T alpha          [D]
+ *     G    = B^T K_lam^-1 B     [D x D]      with B = diag(1/sqrt(K_raw,ii)) Phi_train
+ * and the scalars of the posterior / acquisition.  For a candidate c with (restricted)
+ * feature vector phi_c and self-similarity k_cc over ALL its labels:
+ *     mu  = (phi_c . w_mu / sqrt(k_cc)) * y_std + y_mean
+ *     var = (sqrt(max(1 + lik - phi_c^T G phi_c / k_cc, lik)) * y_std)^2
+ */
+typedef enum { NBW_ACQ_EI = 0, NBW_ACQ_AEI = 1, NBW_ACQ_UCB = 2, NBW_ACQ_MEAN = 3 } nbw_acq;
+
+typedef struct {
+  int32_t n_max;                         /* 8 or 16 */
+  int32_t h;                             /* WL depth: levels 0..h */
+  int32_t oa;                            /* 0 linear, 1 histogram intersection */
+  int32_t acq;                           /* nbw_acq */
+  uint64_t seed;                         /* the seed the dictionary was built with */
+  const uint16_t* level0_table;          /* [256] op code -> dense level-0 id, 0xFFFF = unseen */
+  const void* table[NBW_MAX_LEVELS];     /* level l>=1: slots {u64 key; u32 chk_lo; u32 id} */
+  uint32_t table_mask[NBW_MAX_LEVELS];   /* capacity-1 (capacity is a power of two) */
+  int32_t col_off[NBW_MAX_LEVELS];       /* first feature column of level l (oa==0: + id) */
+  int32_t label_off[NBW_MAX_LEVELS];     /* first stacked label index of level l */
+  const uint32_t* thermo_base;           /* oa: stacked label -> first column within level */
+  const uint8_t* max_count;              /* oa: stacked label -> max training count */
+  int32_t n_features;                    /* D (columns of G) */
+  int32_t ld_g;
+  const double* G;                       /* [D x ld_g] */
+  const double* w_mu;                    /* [D] */
+  double lik, y_mean, y_std, incumbent, xi, beta;
+} nbw_model;
+
+/* Build one level's lookup table from the sorted dictionary of nbw_dict_build.
+ * table: capacity slots of 16 bytes, capacity = power of two >= 2 * n_unique. */
+int nbw_model_build_table(nbw_ctx* ctx, const uint64_t* uniq_keys, const uint64_t* uniq_chks,
+                          int64_t n_unique, void* table, int64_t capacity, void* stream);
+
+/* scores: [M] f32 (required).  mu64/var64/score64: optional [M] f64 outputs (NULL to skip). */
+int nbw_score_pool(nbw_ctx* ctx, const nbw_model* model_h, const void* cells, int64_t n_cells,
+                   float* scores, double* mu64, double* var64, double* score64, void* stream);
+
+/* Pool-side features only (test/diagnostic use): restricted dense feature rows
+ * phi [M x ld_phi] int8 (columns < n_features) and self-similarity k_cc [M] i32. */
+int nbw_pool_features(nbw_ctx* ctx, const nbw_model* model_h, const void* cells,
+                      int64_t n_cells, int8_t* phi, int64_t ld_phi, int32_t* self_sim,
+                      void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Top-n selection — replaces propose_location's np.unique + np.argpartition
+ * (bayesopt/acquisitions.py:101-105): the k largest DISTINCT score values, each with the
+ * first (lowest) index at which it occurs; NaN scores are ignored.  Results are sorted by
+ * descending value; *n_found_h <= k.  index_base is added to the indices (pool shard offset).
+ * distinct == 0 gives plain top-k (ties by lowest index).  Syncs.
+ */
+int nbw_topk(nbw_ctx* ctx, const float* scores, int64_t n, int k, int distinct,
+             int64_t index_base, float* top_val_h, int64_t* top_idx_h, int* n_found_h,
+             void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Synthetic pools shaped like the reference's samplers, generated on device
+ * (bayesopt/generate_test_graphs.py:543-641; darts/darts_objectives.py:159-198 +
+ * darts/utils.py:11-98).  family: 0 = NAS-Bench-101 (n_max 8), 1 = NAS-Bench-201 (n_max 8),
+ * 2 = DARTS (n_max 16).  Cell i depends only on (seed, first_index + i): shards generated on
+ * different GPUs concatenate to the single-GPU pool.  Op codes are the fixed family
+ * vocabularies listed in nasbowl_b200/synth.py.
+ */
+int nbw_generate_cells(nbw_ctx* ctx, int family, uint64_t seed, int64_t first_index,
+                       int64_t n_cells, void* cells, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NBW_H_ */

@@ -1,0 +1,112 @@
+"""EI / augmented EI / UCB over a candidate pool, fused with the GP posterior on the GPU
+(reference bayesopt/acquisitions.py:9-138).
+
+The reference scores one candidate per call (`eval`), re-running WL on train ∪ {candidate}
+and on train ∪ train (for the incumbent) every time; here `propose_location` packs the whole
+pool, scores it with ONE launch of the fused kernel (csrc/score_pool.cu) and selects the
+top-n distinct values on the device (csrc/topk.cu).  Values agree with the reference's
+per-candidate path because batched and per-candidate posteriors are mathematically identical
+(SURVEY Q11).
+"""
+from abc import ABC
+
+import numpy as np
+import torch
+
+from ..cells import CellBatch
+
+
+class BaseAcquisition(ABC):
+    def __init__(self, gp):
+        self.gp = gp
+        self.iters = 0
+        self.next_location = None
+        self.next_acq_value = None
+
+    def propose_location(self, *args):
+        raise NotImplementedError
+
+    def optimize(self):
+        raise NotImplementedError
+
+    def eval(self, x):
+        raise NotImplementedError
+
+    def __call__(self, *args, **kwargs):
+        return self.eval(*args, **kwargs)
+
+
+class GraphExpectedImprovement(BaseAcquisition):
+    def __init__(self, surrogate_model, augmented_ei=False, xi: float = 0.0, in_fill: str = 'best',
+                 strict: bool = True):
+        """strict=False restores the reference's habit of returning -1 on any error inside eval
+        (acquisitions.py:64-67); by default errors propagate."""
+        super().__init__(surrogate_model)
+        assert in_fill in ['best', 'posterior']
+        self.in_fill = in_fill
+        self.augmented_ei = augmented_ei
+        self.xi = xi
+        self.strict = strict
+
+    # -- model configuration ------------------------------------------------------------
+    def _model(self):
+        if self.in_fill == 'max':                      # never true (assert above): SURVEY Q13
+            inc = float(torch.max(self.gp.y_))
+        else:
+            inc = None                                 # posterior-mean incumbent (acquisitions.py:89-92)
+        return self.gp.pool_model("AEI" if self.augmented_ei else "EI", xi=self.xi, incumbent=inc)
+
+    def _get_incumbent(self):
+        if self.in_fill == 'max':
+            return torch.max(self.gp.y_)
+        return self.gp.y_[self.gp._score_state()['incumbent_idx']]
+
+    def score_pool(self, candidates, want64=False):
+        """Acquisition values of a whole pool: (scores f32 device tensor [M], mu, var, score64)."""
+        cells, M = self.gp.upload_pool(candidates)
+        eng = self.gp._dev['eng']
+        return eng.score_pool(self._model(), cells, M, want64=want64)
+
+    # -- reference API --------------------------------------------------------------------
+    def eval(self, x, asscalar=False):
+        single = not isinstance(x, (list, tuple, CellBatch))
+        try:
+            _, _, _, sc = self.score_pool([x] if single else x, want64=True)
+        except Exception:
+            if self.strict:
+                raise
+            return -1.
+        ei = sc.cpu()
+        if asscalar:
+            return ei.numpy().item()
+        return ei
+
+    def propose_location(self, candidates, top_n=5, return_distinct=True):
+        """top_n: return the top n candidates wrt the acquisition function (acquisitions.py:94-113)."""
+        self.iters += 1
+        scores, _, _, _ = self.score_pool(candidates)
+        eng = self.gp._dev['eng']
+        vals, indices = eng.topk(scores, top_n, distinct=bool(return_distinct))
+        if return_distinct and len(indices) < top_n:
+            # fewer than top_n distinct values: the reference falls back to plain top-k (:106-108)
+            vals, indices = eng.topk(scores, top_n, distinct=False)
+        eis = scores.cpu().numpy().reshape(-1, 1)
+        if isinstance(candidates, (CellBatch, torch.Tensor)):
+            xs = tuple(int(i) for i in indices)
+        else:
+            xs = tuple([candidates[int(i)] for i in indices])
+        return xs, eis, indices
+
+    def optimize(self):
+        raise ValueError("The kernel invoked does not have hyperparameters to optimse over!")
+
+
+class GraphUpperConfidentBound(GraphExpectedImprovement):
+    def __init__(self, surrogate_model, beta=None, strict: bool = True):
+        super().__init__(surrogate_model, strict=strict)
+        self.beta = beta
+
+    def _model(self):
+        if self.beta is None:                          # acquisitions.py:133-135
+            self.beta = 3. * torch.sqrt(0.5 * torch.log(torch.tensor(2. * self.iters + 1.)))
+        return self.gp.pool_model("UCB", beta=float(self.beta))

@@ -1,0 +1,371 @@
+"""GraphGP — the reference's GP surrogate (bayesopt/gp.py:27-294) with every numerical step
+on the GPU through libnbw's C-ABI.  Host logic (what is looped over, in which order, with which
+clamp) mirrors the reference line by line so that h*, lambda, the incumbent and the selected
+architectures agree; see SURVEY.md Appendix A for the quirks that are reproduced on purpose.
+
+Differences a caller can observe:
+  * results are computed in fp64 (the reference mixes fp64 and fp32, Q8) and returned as
+    CPU float64 tensors;
+  * WL features of the training set are computed ONCE per fit instead of once per grid
+    candidate and once per Adam iteration (the Gram does not depend on lambda);
+  * `predict_diag` / the acquisition classes score a whole pool with one fused kernel instead
+    of re-fitting WL on train ∪ {candidate} per candidate.
+"""
+from __future__ import annotations
+
+import logging
+import math
+from copy import deepcopy
+from typing import List, Optional, Sequence
+
+import networkx as nx
+import numpy as np
+import torch
+
+from .. import _lib
+from ..cells import CellBatch
+from ..kernels import GraphKernels, SumKernel, WeisfilerLehman
+
+_LOG_2PI = math.log(2.0 * math.pi)
+
+
+def normalize_y(y: torch.Tensor):
+    """bayesopt/utils.py:72-76 (torch.std is the unbiased estimator)."""
+    y_mean = torch.mean(y) if isinstance(y, torch.Tensor) else np.mean(y)
+    y_std = torch.std(y) if isinstance(y, torch.Tensor) else np.std(y)
+    y = (y - y_mean) / y_std
+    return y, y_mean, y_std
+
+
+def _as_f64(y):
+    """The GPU path evaluates the GP in fp64: normalise the targets in fp64 as well."""
+    return y.detach().double() if isinstance(y, torch.Tensor) else torch.as_tensor(np.asarray(y, dtype=np.float64))
+
+
+def unnormalize_y(y, y_mean, y_std, scale_std=False):
+    """bayesopt/utils.py:79-85."""
+    if not scale_std:
+        return y * y_std + y_mean
+    return y * y_std
+
+
+def _nlml_from_stats(logdet: float, yKy: float, n: int) -> float:
+    """-compute_log_marginal_likelihood (bayesopt/utils.py:102-117) with the reference's
+    logDetK = -log|K| (utils.py:138): (yKy/2 - log|K|/2 + n/2 log 2pi) / n."""
+    return (0.5 * yKy - 0.5 * logdet + 0.5 * n * _LOG_2PI) / n
+
+
+def _wl_model(eng, fit, h, acq="MEAN"):
+    """nbw_model descriptor for one fitted WL kernel (dictionary side only).  Returns
+    (model, keepalive) — keepalive holds the device tensors the struct points into."""
+    import ctypes as C
+    level0, tables, masks = eng.build_tables(fit, h)
+    m = _lib.Model()
+    m.n_max, m.h, m.oa, m.acq = fit.n_max, h, int(fit.oa), 3 if acq == "MEAN" else acq
+    m.seed = fit.seed & 0xFFFFFFFFFFFFFFFF
+    m.level0_table = level0.data_ptr()
+    for l in range(h + 1):
+        m.col_off[l] = fit.col_off[l]
+        m.label_off[l] = fit.label_off[l]
+        if l >= 1:
+            m.table[l] = tables[l].data_ptr()
+            m.table_mask[l] = masks[l]
+    if fit.oa:
+        m.thermo_base = fit.thermo_base.data_ptr()
+        m.max_count = fit.max_count.data_ptr()
+    m.n_features = fit.k_end(h)
+    return m, (level0, tables)
+
+
+class GraphGP:
+    def __init__(self, train_x, train_y, kernels: list, vectorial_features: list = None, likelihood=1e-3,
+                 weights=None, vector_theta_bounds: tuple = (1e-5, 0.1), graph_theta_bounds: tuple = (1e-1, 1.e1),
+                 verbose=False, n_max=None):
+        assert len(train_x) == train_y.shape[0], 'mismatch of length between train and test GP'
+        if not isinstance(train_x, CellBatch):
+            assert all([isinstance(x, nx.Graph) for x in train_x]), \
+                'each of the training example in train_x needs to be a networkX graph!'
+        self.likelihood = likelihood
+        self.kernels = kernels
+        self.n_kernels = len(kernels)
+        self.n_graph_kernels = len([i for i in kernels if isinstance(i, GraphKernels)])
+        self.n_vector_kernels = self.n_kernels - self.n_graph_kernels
+        if self.n_vector_kernels > 0 or vectorial_features:
+            raise NotImplementedError("vectorial kernels / hand-crafted features are outside the GPU hot path")
+        self.x = train_x[:]
+        self.feature_d = None
+        self.vectorial_feactures = vectorial_features
+        self.x_features, self.x_features_min, self.x_features_max = [None] * 3
+        self.n = len(self.x)
+        self.y_ = deepcopy(train_y)
+        self.y, self.y_mean, self.y_std = normalize_y(_as_f64(train_y))
+        if weights is not None:
+            self.fixed_weights = True
+            assert len(weights) == len(kernels), \
+                "the weights vector, if supplied, needs to have the same length as the number of kernels!"
+            self.weights = weights if isinstance(weights, torch.Tensor) else torch.tensor(weights).flatten()
+        else:
+            self.fixed_weights = False
+            self.weights = torch.tensor([1. / len(kernels)] * len(kernels), )
+        self.sum_kernels = SumKernel(*kernels, weights=self.weights)
+        self.vector_theta_bounds = vector_theta_bounds
+        self.graph_theta_bounds = graph_theta_bounds
+        self.verbose = verbose
+        self.n_max = n_max         # force 16-node records when pools may hold larger cells than train
+        self.theta_vector = None
+        self.layer_weights = None
+        self.nlml = None
+        self.nlml_grid = {}
+        self.logDetK = None
+        self._fitted = False
+        self._dev = None           # device state of the last fit (not pickled)
+
+    # ------------------------------------------------------------------ device helpers
+    def _engine(self):
+        from ..engine import Engine
+        return Engine.get()
+
+    def _pack(self, gr) -> CellBatch:
+        return self.kernels[0].pack(gr)
+
+    def _like_train(self, batch: CellBatch) -> CellBatch:
+        """Bring a pool batch to the record width the GP was fitted with."""
+        n_max = self._dev['n_max']
+        if batch.n_max > n_max:
+            raise ValueError("pool cells have up to %d nodes but the GP was fitted on %d-node records; "
+                             "construct the GP with n_max=16" % (batch.n_max, n_max))
+        return batch.widen(n_max)
+
+    def _y_device(self, eng):
+        return torch.as_tensor(np.asarray(self.y.detach().cpu().numpy(), dtype=np.float64)).to(eng.device)
+
+    # ------------------------------------------------------------------ grid search over h
+    def _grid_search_wl_kernel(self, k: WeisfilerLehman, fit, subtree_candidates, y_dev, lik):
+        """bayesopt/gp.py:493-538: for each candidate h, marginal likelihood of the
+        UN-normalised Gram + lik*I; strict '<' keeps the smallest h on ties."""
+        eng = self._engine()
+        best_nlml, best_h = math.inf, None
+        grid = {}
+        for hc in subtree_candidates:
+            K = k.gram_device(fit, hc)
+            _, _, _, logdet, yKy, _, _ = eng.pd_inverse(K, float(lik), y_dev)
+            nlml = _nlml_from_stats(logdet, yKy, self.n)
+            grid[int(hc)] = nlml
+            if nlml < best_nlml:
+                best_nlml, best_h = nlml, hc
+        k.change_kernel_params({'h': best_h})
+        self.nlml_grid[id(k)] = grid
+        return best_h
+
+    # ------------------------------------------------------------------ fit
+    def fit(self, iters=20, optimizer='adam', wl_subtree_candidates: tuple = tuple(range(5)),
+            wl_lengthscales=tuple([np.e ** i for i in range(-2, 3)]), optimize_lik=True, max_lik=0.01,
+            optimize_wl_layer_weights=False, optimizer_kwargs=None):
+        if optimizer_kwargs is None:
+            optimizer_kwargs = {'lr': 0.1}
+        if optimize_wl_layer_weights:
+            raise NotImplementedError("optimize_wl_layer_weights is outside the GPU hot path")
+        eng = self._engine()
+        batch = self._pack(self.x)
+        if self.n_max is not None:
+            batch = batch.widen(self.n_max)
+        cells = eng.upload_cells(batch)
+        y_dev = self._y_device(eng)
+        self.nlml_grid = {}
+
+        # 1. WL features once per kernel, deep enough for every candidate; h by marginal likelihood
+        fits = []
+        for k in self.sum_kernels.kernels:
+            if not isinstance(k, WeisfilerLehman):
+                logging.warning('Graph kernel optimisation for ' + str(k) + " not implemented yet.")
+                raise NotImplementedError("only WeisfilerLehman kernels run on the GPU path")
+            cands = [int(c) for c in wl_subtree_candidates]
+            h_fit = max(cands + [k.h])
+            fit = k.fit_device(cells, batch.n_max, h=h_fit)
+            if len(cands):
+                self._grid_search_wl_kernel(k, fit, cands, y_dev, self.likelihood)
+            fits.append(fit)
+
+        # 2. K = sum_i w_i K_raw,i, cosine-normalised (combine_kernels.py:36-56)
+        weights = self.weights.clone()
+        if (not self.fixed_weights) and len(self.kernels) > 1:
+            raise NotImplementedError("trainable kernel weights (gp.py:141-142) are not implemented on the "
+                                      "GPU path; pass weights=[...] to fix them")
+        grams = [k.gram_device(f) for k, f in zip(self.sum_kernels.kernels, fits)]
+        K, inv_sqrt_diag = self.sum_kernels.combine_device(weights, grams, normalize=True)
+
+        # 3. noise: Adam / SGD on the scalar lambda with the reference's clamp (gp.py:153-210)
+        likelihood = torch.tensor(self.likelihood, )
+        nlml = None
+        if optimize_lik:
+            likelihood.requires_grad_(True)
+            assert optimizer.lower() in ['adam', 'sgd']
+            optim = (torch.optim.Adam if optimizer.lower() == 'adam' else torch.optim.SGD)([likelihood],
+                                                                                         **optimizer_kwargs)
+            for i in range(iters):
+                optim.zero_grad()
+                _, _, _, logdet, yKy, trKinv, alpha_sq = eng.pd_inverse(K, float(likelihood.item()), y_dev)
+                nlml = _nlml_from_stats(logdet, yKy, self.n)
+                # d nlml / d lambda = -(|K_l^-1 y|^2 + tr K_l^-1) / (2n): always negative (Q9)
+                likelihood.grad = torch.tensor(-(0.5 * alpha_sq + 0.5 * trKinv) / self.n, dtype=likelihood.dtype)
+                if self.verbose and i % 10 == 0:
+                    print('Iteration:', i, "/", iters, 'Negative log-marginal likelihood:', nlml, weights, likelihood)
+                optim.step()
+                with torch.no_grad():
+                    likelihood.clamp_(1e-5, max_lik)
+        lik = float(likelihood.item())
+        L, Linv, alpha, logdet, yKy, _, _ = eng.pd_inverse(K, lik, y_dev)
+
+        # 4. state (gp.py:212-219)
+        self.weights = weights.clone() / torch.sum(weights)
+        self.likelihood = lik
+        self.logDetK = torch.tensor(-logdet, dtype=torch.float64)
+        self.nlml = torch.tensor(nlml, dtype=torch.float64) if nlml is not None else None
+        self.sum_kernels.weights = weights.clone()
+        self._fitted = True
+        self._dev = dict(eng=eng, fits=fits, hs=[k.h for k in self.sum_kernels.kernels], K=K, L=L, Linv=Linv,
+                         alpha=alpha, s=inv_sqrt_diag, y=y_dev, n_max=batch.n_max, cells=cells,
+                         weights=[float(w) for w in weights], score=None, K_host=None, Ki_host=None)
+        if self.verbose:
+            print('Optimisation summary: ')
+            print('Optimal NLML: ', nlml)
+            print('Optimal h: ', [k.h for k in self.kernels])
+            print('Weights: ', self.weights)
+            print('Lik:', self.likelihood)
+
+    # ------------------------------------------------------------------ reference attributes
+    @property
+    def K(self):
+        if not self._fitted or self._dev is None:
+            return None
+        if self._dev['K_host'] is None:
+            self._dev['K_host'] = self._dev['K'].cpu()
+        return self._dev['K_host']
+
+    @property
+    def K_i(self):
+        """(K + lambda I)^-1 = Linv^T Linv (torch.cholesky_inverse in utils.py:139)."""
+        if not self._fitted or self._dev is None:
+            return None
+        if self._dev['Ki_host'] is None:
+            eng, Linv, n = self._dev['eng'], self._dev['Linv'], self.n
+            Ki = eng.empty((n, n), torch.float64)
+            eng.gemm(True, False, n, n, n, 1.0, Linv, n, Linv, n, 0.0, Ki, n)
+            self._dev['Ki_host'] = Ki.cpu()
+        return self._dev['Ki_host']
+
+    def _require_fit(self):
+        if not self._fitted or self._dev is None:
+            raise ValueError("Inverse of Gram matrix is not instantiated. Please call the optimize function to "
+                             "fit on the training data first!")
+
+    # ------------------------------------------------------------------ predict (reference path)
+    def predict(self, X_s, preserve_comp_graph=False):
+        """Kriging predictions (mu [M], cov [M, M]) exactly as bayesopt/gp.py:240-283: joint WL
+        on train ∪ test, full M x M covariance with the element-wise clamp."""
+        if not isinstance(X_s, (list, CellBatch)):
+            X_s = [X_s]
+        self._require_fit()
+        d = self._dev
+        eng = d['eng']
+        n, M = self.n, len(X_s)
+        test = self._like_train(self._pack(X_s))
+        cells_all = torch.cat([d['cells'], eng.upload_cells(test)], dim=0).contiguous()
+        grams = []
+        for k, h in zip(self.sum_kernels.kernels, d['hs']):
+            fit = eng.wl_fit(cells_all, d['n_max'], h, k.oa)
+            k._fit = fit          # the reference leaves the kernel fitted on train ∪ test (Q19)
+            grams.append(k.gram_device(fit, h))
+        K_full, _ = self.sum_kernels.combine_device(d['weights'], grams, normalize=True)
+        N = n + M
+        K_s = K_full[:n, n:]                     # views: explicit leading dimension N below
+        K_ss = K_full[n:, n:]
+        W = eng.empty((n, M), torch.float64)     # W = L^-1 K_s
+        eng.gemm(False, False, n, M, n, 1.0, d['Linv'], n, K_s, N, 0.0, W, M)
+        Q = eng.empty((M, M), torch.float64)     # K_s^T K_i K_s = W^T W
+        eng.gemm(True, False, M, M, n, 1.0, W, M, W, M, 0.0, Q, M)
+        mu = eng.empty((M,), torch.float64)      # K_s^T K_i y
+        eng.gemm(True, False, M, 1, n, 1.0, K_s, N, d['alpha'], 1, 0.0, mu, 1)
+        cov = eng.posterior_cov_finish(K_ss, N, Q, M, self.likelihood, float(self.y_std))
+        mu_s = unnormalize_y(mu.cpu(), float(self.y_mean), float(self.y_std))
+        return mu_s, cov.cpu()
+
+    # ------------------------------------------------------------------ fused pool path
+    def _score_state(self):
+        """Feature-space posterior operators (see csrc/score_pool.cu): w_mu = B^T alpha,
+        G = (L^-1 B)^T (L^-1 B) with B = diag(1/sqrt(K_raw,ii)) sqrt(w) Phi_train."""
+        self._require_fit()
+        d = self._dev
+        if d['score'] is not None:
+            return d['score']
+        if len(self.sum_kernels.kernels) != 1:
+            raise NotImplementedError("the fused pool path handles a single WL kernel; use predict()")
+        eng, n = d['eng'], self.n
+        fit, h, w = d['fits'][0], d['hs'][0], d['weights'][0]
+        D = fit.k_end(h)
+        # the normalisation of K uses diag(w * K_raw): s already contains 1/sqrt(w K_raw,ii)
+        B = eng.empty((n, D), torch.float64)
+        eng.scale_features(fit.phi, 0, D, d['s'], math.sqrt(w), B, D)
+        Wt = eng.empty((n, D), torch.float64)
+        eng.gemm(False, False, n, D, n, 1.0, d['Linv'], n, B, D, 0.0, Wt, D)
+        G = eng.empty((D, D), torch.float64)
+        eng.gemm(True, False, D, D, n, 1.0, Wt, D, Wt, D, 0.0, G, D)
+        w_mu = eng.empty((D,), torch.float64)
+        eng.gemm(True, False, D, 1, n, 1.0, B, D, d['alpha'], 1, 0.0, w_mu, 1)
+        # incumbent: y_raw[argmax of the posterior mean at the training points] (acquisitions.py:82-92)
+        mu_train = eng.empty((n,), torch.float64)
+        eng.gemm(False, False, n, 1, n, 1.0, d['K'], n, d['alpha'], 1, 0.0, mu_train, 1)
+        inc_idx = int(np.argmax(mu_train.cpu().numpy()))
+        model, keep = _wl_model(eng, fit, h)
+        model.G, model.ld_g, model.w_mu = G.data_ptr(), D, w_mu.data_ptr()
+        model.lik, model.y_mean, model.y_std = float(self.likelihood), float(self.y_mean), float(self.y_std)
+        d['score'] = dict(model=model, keep=(keep, G, w_mu), incumbent_idx=inc_idx,
+                          incumbent=float(self.y_[inc_idx]))
+        return d['score']
+
+    def pool_model(self, acq="MEAN", xi=0.0, beta=0.0, incumbent=None):
+        """A copy of the nbw_model descriptor configured for one acquisition."""
+        from ..engine import ACQ
+        st = self._score_state()
+        import ctypes as C
+        m = _lib.Model()
+        C.memmove(C.byref(m), C.byref(st['model']), C.sizeof(m))
+        m.acq = ACQ[acq]
+        m.xi, m.beta = float(xi), float(beta)
+        m.incumbent = float(st['incumbent'] if incumbent is None else incumbent)
+        return m
+
+    def upload_pool(self, X):
+        """list[nx.DiGraph] | CellBatch | device records -> (device records, n_cells)."""
+        d = self._dev
+        if isinstance(X, torch.Tensor):
+            return X, X.shape[0]
+        batch = self._like_train(self._pack(X))
+        return d['eng'].upload_cells(batch), len(batch)
+
+    def predict_diag(self, X_s):
+        """(mu [M], var [M]) — the diagonal of predict() — through the fused pool kernel."""
+        self._require_fit()
+        eng = self._dev['eng']
+        cells, M = self.upload_pool(X_s)
+        _, mu, var, _ = eng.score_pool(self.pool_model("MEAN"), cells, M, want64=True)
+        return mu.cpu(), var.cpu()
+
+    def reset_XY(self, train_x, train_y):
+        """bayesopt/gp.py:285-294."""
+        self.x = train_x
+        self.n = len(self.x)
+        self.y_ = train_y
+        self.y, self.y_mean, self.y_std = normalize_y(_as_f64(train_y))
+        self.logDetK = None
+        self._fitted = False
+        self._dev = None
+
+    def dmu_dphi(self, *a, **k):
+        raise NotImplementedError("interpretability gradients (gp.py:296-424) are outside the GPU hot path")
+
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st['_dev'] = None
+        st['_fitted'] = False      # device state does not travel; call fit() after unpickling
+        return st

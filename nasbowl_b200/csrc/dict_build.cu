@@ -1,0 +1,340 @@
+// Dictionary build: global LSD radix sort of 64-bit WL keys + unique + dense id assignment.
+// Replaces `sorted(list(label_set))` and the running id counter of
+// grakel_replace/weisfeiler_lehman.py:226-229,271-274 (ids here are local to the level and
+// ordered by key; only the partition of nodes into label classes enters the kernel value).
+//
+// Sort: 8-bit digits, stable, three kernels per pass (per-tile digit counts -> exclusive scan
+// of the digit-major count matrix -> ranked scatter).  A tile is 4096 keys: 8 warps x 16
+// rounds x 32 lanes; ranks inside a round come from __match_any_sync, so there are no
+// shared-memory atomics and the order of equal digits is preserved.
+#include "nbw_common.cuh"
+
+namespace {
+
+constexpr int kSortThreads = 256;
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kRounds = 16;
+constexpr int kTile = kSortWarps * kRounds * 32;   // 4096
+
+// ---------------------------------------------------------------- exclusive scan (u32)
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;   // 2048
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* smem_warp, uint32_t& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) smem_warp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = lane < (kScanThreads / 32) ? smem_warp[lane] : 0;
+    uint32_t winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    if (lane < (kScanThreads / 32)) smem_warp[lane] = winc - w;
+    if (lane == 31) smem_warp[32] = winc;
+  }
+  __syncthreads();
+  total = smem_warp[32];
+  uint32_t r = smem_warp[warp] + inc - v;
+  __syncthreads();
+  return r;
+}
+
+// pass 1: per-tile sums
+__global__ void __launch_bounds__(kScanThreads)
+scan_reduce_kernel(const uint32_t* __restrict__ in, int64_t n, uint32_t* __restrict__ tile_sums) {
+  __shared__ uint32_t sw[33];
+  const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+  uint32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i)
+    if (base + i < n) s += in[base + i];
+  uint32_t total;
+  block_exclusive_scan(s, sw, total);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+// pass 3 (or the only pass when one tile): scan inside the tile, add tile offset
+__global__ void __launch_bounds__(kScanThreads)
+scan_apply_kernel(const uint32_t* in, uint32_t* out, int64_t n,   // in may alias out
+                  const uint32_t* tile_offsets) {
+  __shared__ uint32_t sw[33];
+  const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+  uint32_t v[kScanItems];
+  uint32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) {
+    v[i] = (base + i < n) ? in[base + i] : 0;
+    s += v[i];
+  }
+  uint32_t total;
+  uint32_t ex = block_exclusive_scan(s, sw, total);
+  ex += tile_offsets ? tile_offsets[blockIdx.x] : 0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) {
+    if (base + i < n) out[base + i] = ex;
+    ex += v[i];
+  }
+}
+
+size_t scan_scratch_elems(int64_t n) {
+  size_t total = 0;
+  while (n > kScanTile) {
+    n = (n + kScanTile - 1) / kScanTile;
+    total += (size_t)n + 64;
+  }
+  return total + 64;
+}
+
+// Exclusive scan of n u32 (in-place allowed); tmp has scan_scratch_elems(n) elements.
+int device_exclusive_scan(nbw_ctx* ctx, const uint32_t* in, uint32_t* out, int64_t n,
+                          uint32_t* tmp, cudaStream_t st) {
+  if (n <= 0) return NBW_OK;
+  const int64_t tiles = (n + kScanTile - 1) / kScanTile;
+  if (tiles == 1) {
+    scan_apply_kernel<<<1, kScanThreads, 0, st>>>(in, out, n, nullptr);
+    NBW_CHECK_LAUNCH(ctx);
+    return NBW_OK;
+  }
+  uint32_t* sums = tmp;
+  scan_reduce_kernel<<<(unsigned)tiles, kScanThreads, 0, st>>>(in, n, sums);
+  NBW_CHECK_LAUNCH(ctx);
+  int rc = device_exclusive_scan(ctx, sums, sums, tiles, tmp + tiles + 64, st);
+  if (rc) return rc;
+  scan_apply_kernel<<<(unsigned)tiles, kScanThreads, 0, st>>>(in, out, n, sums);
+  NBW_CHECK_LAUNCH(ctx);
+  return NBW_OK;
+}
+
+// ---------------------------------------------------------------- radix sort passes
+// Per-warp digit counts of the warp's strip of the tile -> cnt[warp][digit].
+__device__ __forceinline__ void strip_digit_counts(const uint64_t* __restrict__ keys, int64_t n,
+                                                   int shift, uint32_t (*cnt)[256]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int d = lane; d < 256; d += 32) cnt[warp][d] = 0;
+  __syncwarp();
+  const int64_t strip = (int64_t)blockIdx.x * kTile + (int64_t)warp * (kRounds * 32);
+  for (int r = 0; r < kRounds; ++r) {
+    const int64_t i = strip + r * 32 + lane;
+    const uint32_t digit = (i < n) ? (uint32_t)((keys[i] >> shift) & 0xFFu) : 256u;
+    const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+    if (digit < 256u && (peers & ((1u << lane) - 1u)) == 0u) cnt[warp][digit] += __popc(peers);
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(kSortThreads)
+radix_count_kernel(const uint64_t* __restrict__ keys, int64_t n, int shift, int n_tiles,
+                   uint32_t* __restrict__ counts /* [256][n_tiles] */) {
+  __shared__ uint32_t cnt[kSortWarps][256];
+  strip_digit_counts(keys, n, shift, cnt);
+  __syncthreads();
+  uint32_t s = 0;
+#pragma unroll
+  for (int w = 0; w < kSortWarps; ++w) s += cnt[w][threadIdx.x];
+  counts[(size_t)threadIdx.x * n_tiles + blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(kSortThreads)
+radix_scatter_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                     uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n,
+                     int shift, int n_tiles, const uint32_t* __restrict__ offsets) {
+  __shared__ uint32_t cnt[kSortWarps][256];
+  strip_digit_counts(keys_in, n, shift, cnt);
+  __syncthreads();
+  {
+    uint32_t base = offsets[(size_t)threadIdx.x * n_tiles + blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) {
+      const uint32_t c = cnt[w][threadIdx.x];
+      cnt[w][threadIdx.x] = base;
+      base += c;
+    }
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t strip = (int64_t)blockIdx.x * kTile + (int64_t)warp * (kRounds * 32);
+  for (int r = 0; r < kRounds; ++r) {
+    const int64_t i = strip + r * 32 + lane;
+    const bool valid = i < n;
+    const uint64_t key = valid ? keys_in[i] : 0;
+    const uint32_t digit = valid ? (uint32_t)((key >> shift) & 0xFFu) : 256u;
+    const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+    const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+    if (valid) {
+      const uint32_t pos = cnt[warp][digit] + rank;
+      keys_out[pos] = key;
+      vals_out[pos] = vals_in ? vals_in[i] : (uint32_t)i;
+    }
+    __syncwarp();
+    if (valid && rank == 0) cnt[warp][digit] += __popc(peers);
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------- unique / ids / verification
+__global__ void mark_heads_kernel(const uint64_t* __restrict__ sk, int64_t n, uint32_t* __restrict__ flags) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint64_t k = sk[i];
+    flags[i] = (k != NBW_INVALID_KEY && (i == 0 || sk[i - 1] != k)) ? 1u : 0u;
+  }
+}
+
+// Exact comparison of two credentials (own id, multiset of successor ids).
+template <int NMAX>
+__device__ bool same_credential(const uint8_t* cells, const uint32_t* ids_prev, uint32_t a, uint32_t b) {
+  if (ids_prev[a] != ids_prev[b]) return false;
+  uint32_t la[NMAX], lb[NMAX];
+  int na = 0, nb = 0;
+  {
+    const int64_t g = a / NMAX;
+    const uint32_t m = CellTraits<NMAX>::succ(cells, g, a % NMAX);
+    for (int j = 0; j < NMAX; ++j)
+      if ((m >> j) & 1u) {
+        uint32_t v = ids_prev[g * NMAX + j];
+        int p = na++;
+        while (p > 0 && la[p - 1] > v) { la[p] = la[p - 1]; --p; }
+        la[p] = v;
+      }
+  }
+  {
+    const int64_t g = b / NMAX;
+    const uint32_t m = CellTraits<NMAX>::succ(cells, g, b % NMAX);
+    for (int j = 0; j < NMAX; ++j)
+      if ((m >> j) & 1u) {
+        uint32_t v = ids_prev[g * NMAX + j];
+        int p = nb++;
+        while (p > 0 && lb[p - 1] > v) { lb[p] = lb[p - 1]; --p; }
+        lb[p] = v;
+      }
+  }
+  if (na != nb) return false;
+  for (int j = 0; j < na; ++j)
+    if (la[j] != lb[j]) return false;
+  return true;
+}
+
+struct DictCounters {
+  uint32_t n_unique;
+  uint32_t collision;
+};
+
+__global__ void assign_ids_kernel(const uint64_t* __restrict__ sk, const uint32_t* __restrict__ sv,
+                                  const uint64_t* __restrict__ chks, const uint32_t* __restrict__ flags,
+                                  const uint32_t* __restrict__ rank, int64_t n,
+                                  const uint8_t* __restrict__ cells, int n_max,
+                                  const uint32_t* __restrict__ ids_prev,
+                                  uint32_t* __restrict__ ids, uint64_t* __restrict__ uniq_keys,
+                                  uint64_t* __restrict__ uniq_chks, int64_t cap,
+                                  DictCounters* __restrict__ counters) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint64_t k = sk[i];
+    const uint32_t src = sv[i];
+    if (i == n - 1) counters->n_unique = rank[i] + flags[i];
+    if (k == NBW_INVALID_KEY) {
+      ids[src] = NBW_INVALID_ID;
+      continue;
+    }
+    const uint32_t head = flags[i];
+    const uint32_t id = rank[i] + head - 1u;
+    ids[src] = id;
+    if (head) {
+      if ((int64_t)id < cap) {
+        uniq_keys[id] = k;
+        uniq_chks[id] = chks[src];
+      }
+    } else {
+      const uint32_t prev = sv[i - 1];
+      bool ok = chks[src] == chks[prev];
+      if (ok && cells != nullptr && ids_prev != nullptr) {
+        ok = (n_max == 8) ? same_credential<8>(cells, ids_prev, prev, src)
+                          : same_credential<16>(cells, ids_prev, prev, src);
+      }
+      if (!ok) atomicOr(&counters->collision, 1u);
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int nbw_dict_build(nbw_ctx* ctx, const uint64_t* keys, const uint64_t* chks, int64_t n_keys,
+                              int key_bits, const void* cells, int n_max, const uint32_t* ids_prev,
+                              uint32_t* ids, uint64_t* uniq_keys, uint64_t* uniq_chks,
+                              int64_t uniq_cap, int64_t* n_unique_h, void* stream) {
+  if (!ctx) return NBW_ERR_INVALID;
+  NBW_REQUIRE(ctx, n_keys >= 0 && n_keys < (int64_t)1 << 31, "n_keys out of range");
+  NBW_REQUIRE(ctx, key_bits >= 8 && key_bits <= 64 && key_bits % 8 == 0, "key_bits must be a multiple of 8 in [8,64]");
+  NBW_REQUIRE(ctx, n_unique_h != nullptr, "n_unique_h is NULL");
+  NBW_REQUIRE(ctx, cells == nullptr || n_max == 8 || n_max == 16, "n_max must be 8 or 16");
+  *n_unique_h = 0;
+  if (n_keys == 0) return NBW_OK;
+  NBW_REQUIRE(ctx, keys && chks && ids && uniq_keys && uniq_chks, "null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  const int n_tiles = (int)((n_keys + kTile - 1) / kTile);
+  const size_t n_counts = (size_t)256 * n_tiles;
+  const size_t scan_tmp = scan_scratch_elems((int64_t)(n_counts > (size_t)n_keys ? n_counts : (size_t)n_keys));
+  size_t need = 0;
+  need += Carver::pad(sizeof(uint64_t) * n_keys) * 2;   // key ping-pong
+  need += Carver::pad(sizeof(uint32_t) * n_keys) * 2;   // value ping-pong
+  need += Carver::pad(sizeof(uint32_t) * n_counts);
+  need += Carver::pad(sizeof(uint32_t) * n_keys) * 2;   // flags, rank
+  need += Carver::pad(sizeof(uint32_t) * scan_tmp);
+  need += Carver::pad(sizeof(DictCounters)) + 4096;
+  int rc = nbw_scratch_ensure(ctx, need, st);
+  if (rc) return rc;
+  Carver cv(ctx->scratch);
+  uint64_t* kbuf[2] = {cv.take<uint64_t>(n_keys), cv.take<uint64_t>(n_keys)};
+  uint32_t* vbuf[2] = {cv.take<uint32_t>(n_keys), cv.take<uint32_t>(n_keys)};
+  uint32_t* counts = cv.take<uint32_t>(n_counts);
+  uint32_t* flags = cv.take<uint32_t>(n_keys);
+  uint32_t* rank = cv.take<uint32_t>(n_keys);
+  uint32_t* stmp = cv.take<uint32_t>(scan_tmp);
+  DictCounters* counters = cv.take<DictCounters>(1);
+
+  const uint64_t* kin = keys;
+  const uint32_t* vin = nullptr;
+  int cur = 0;
+  for (int shift = 0; shift < key_bits; shift += 8) {
+    radix_count_kernel<<<n_tiles, kSortThreads, 0, st>>>(kin, n_keys, shift, n_tiles, counts);
+    NBW_CHECK_LAUNCH(ctx);
+    rc = device_exclusive_scan(ctx, counts, counts, (int64_t)n_counts, stmp, st);
+    if (rc) return rc;
+    radix_scatter_kernel<<<n_tiles, kSortThreads, 0, st>>>(kin, vin, kbuf[cur], vbuf[cur], n_keys, shift,
+                                                          n_tiles, counts);
+    NBW_CHECK_LAUNCH(ctx);
+    kin = kbuf[cur];
+    vin = vbuf[cur];
+    cur ^= 1;
+  }
+  const int grid = nbw_grid_for(ctx, n_keys, 256);
+  mark_heads_kernel<<<grid, 256, 0, st>>>(kin, n_keys, flags);
+  NBW_CHECK_LAUNCH(ctx);
+  rc = device_exclusive_scan(ctx, flags, rank, n_keys, stmp, st);
+  if (rc) return rc;
+  NBW_CUDA(ctx, cudaMemsetAsync(counters, 0, sizeof(DictCounters), st));
+  assign_ids_kernel<<<grid, 256, 0, st>>>(kin, vin, chks, flags, rank, n_keys,
+                                         static_cast<const uint8_t*>(cells), n_max, ids_prev, ids,
+                                         uniq_keys, uniq_chks, uniq_cap, counters);
+  NBW_CHECK_LAUNCH(ctx);
+  DictCounters host;
+  NBW_CUDA(ctx, cudaMemcpyAsync(&host, counters, sizeof(host), cudaMemcpyDeviceToHost, st));
+  NBW_CUDA(ctx, cudaStreamSynchronize(st));
+  *n_unique_h = host.n_unique;
+  if (host.collision)
+    NBW_FAIL(ctx, NBW_ERR_HASH_COLLISION, "two distinct WL credentials share a key; retry with another seed");
+  if ((int64_t)host.n_unique > uniq_cap)
+    NBW_FAIL(ctx, NBW_ERR_CAPACITY, "dictionary has %u entries, capacity %lld", host.n_unique, (long long)uniq_cap);
+  return NBW_OK;
+}

@@ -1,0 +1,320 @@
+// Exact integer Gram matrix  C[i,j] = sum_k A[i,k] * B[j,k]  (int8 x int8 -> int32).
+// Replaces VertexHistogram._calculate_kernel_matrix (grakel_replace/vertex_histogram.py:211-259,
+// a float64 BLAS dgemm over integer-valued histograms) and the per-level sum of
+// weisfeiler_lehman.py:316-327: WL levels are contiguous column blocks of Phi, so the sum over
+// levels 0..h is ONE GEMM over the K-range [0, col_off[h+1]).
+//
+// Product path (impl 0): tcgen05.mma kind::i8, cta_group::1, 128x128 accumulator tile in TMEM
+// (128 lanes x 128 columns of s32), both operands K-major, staged by TMA into 128B-swizzled
+// shared memory (one 128-byte K-block per row per stage), 3-stage mbarrier pipeline:
+//   warp 0 lane 0 : TMA producer          (cp.async.bulk.tensor.2d -> full barrier)
+//   warp 1 lane 0 : MMA issuer            (4 x UMMA_K=32 per stage, tcgen05.commit -> empty barrier)
+//   warps 0..3    : epilogue              (tcgen05.ld 32x32b.x32 -> 128-byte row segments to HBM)
+// Two CTAs fit per SM (97 KB smem, 128 TMEM columns each) so one tile's epilogue overlaps the
+// other's main loop.  int32 accumulation of int8 products is exact.
+//
+// Cross-check path (impl 1): plain dp4a kernel, used by the tests to validate impl 0.
+#include "nbw_common.cuh"
+
+#include <cuda.h>
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 128;   // BK in bytes == int8 elements == one swizzle row
+constexpr int UMMA_K = 32;
+constexpr int STAGES = 3;
+constexpr int TILE_BYTES = BM * BK;            // 16 KB per operand per stage
+constexpr int TMEM_COLS = 128;
+constexpr uint32_t SPIN_LIMIT = 1u << 26;
+
+struct __align__(8) PipeBarriers {
+  uint64_t full[STAGES];
+  uint64_t empty[STAGES];
+  uint64_t tmem_full;
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * 2 * TILE_BYTES + sizeof(PipeBarriers);
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0, spins = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (!done && ++spins > SPIN_LIMIT) __trap();   // a broken pipeline must fault, not hang the GPU
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int32_t x, int32_t y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y)
+      : "memory");
+}
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row swizzle atoms 1024 B apart.
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);   // start address       [0,14)
+  d |= (uint64_t)1 << 16;                        // leading byte offset [16,30) (unused for SW128 K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset  [32,46)
+  d |= (uint64_t)1 << 46;                        // descriptor version  [46,48) = 1 on sm_100
+  d |= (uint64_t)2 << 61;                        // layout type         [61,64) = SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_c), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_load_32cols(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// instruction descriptor: D = s32, A = B = signed 8-bit, both K-major, M = 128, N = 128
+constexpr uint32_t kIdescI8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                              ((uint32_t)(BM >> 4) << 24);
+
+__global__ void __launch_bounds__(128)
+gram_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                       int32_t* __restrict__ C, int64_t ldc, int64_t m, int64_t n, int32_t kblk0, int32_t k_blocks) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* tile_a = smem;                                   // [STAGES][128 rows][128 B]
+  uint8_t* tile_b = smem + (size_t)STAGES * TILE_BYTES;
+  PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(smem + (size_t)STAGES * 2 * TILE_BYTES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int32_t row0 = blockIdx.y * BM, col0 = blockIdx.x * BN;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->empty[s], 1);
+    }
+    mbar_init(&bars->tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_acc = bars->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer
+      uint32_t stage = 0, phase = 0;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&bars->empty[stage], phase ^ 1u);
+        mbar_expect_tx(&bars->full[stage], 2u * TILE_BYTES);
+        const int32_t kx = (kblk0 + kb) * BK;
+        tma_load_2d(&map_a, &bars->full[stage], tile_a + (size_t)stage * TILE_BYTES, kx, row0);
+        tma_load_2d(&map_b, &bars->full[stage], tile_b + (size_t)stage * TILE_BYTES, kx, col0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer
+      uint32_t stage = 0, phase = 0;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&bars->full[stage], phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_addr = smem_u32(tile_a + (size_t)stage * TILE_BYTES);
+        const uint32_t b_addr = smem_u32(tile_b + (size_t)stage * TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint64_t da = umma_smem_desc(a_addr + k * UMMA_K);
+          const uint64_t db = umma_smem_desc(b_addr + k * UMMA_K);
+          umma_i8(tmem_acc, da, db, kIdescI8, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&bars->empty[stage]);   // frees the smem slot once these MMAs have read it
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(&bars->tmem_full);        // accumulator complete
+    }
+    __syncwarp();
+  }
+
+  // ---------------- epilogue: warp w owns TMEM lanes [32w, 32w+32) = output rows row0 + 32w + lane
+  mbar_wait(&bars->tmem_full, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const int64_t r = (int64_t)row0 + warp * 32 + lane;
+  const bool vec_ok = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    uint32_t v[32];
+    tmem_load_32cols(tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), v);
+    if (r < m) {
+      const int64_t cbase = (int64_t)col0 + c * 32;
+      int32_t* dst = C + r * ldc + cbase;
+      if (vec_ok && cbase + 32 <= n) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<int4*>(dst + 4 * q) =
+              make_int4((int)v[4 * q], (int)v[4 * q + 1], (int)v[4 * q + 2], (int)v[4 * q + 3]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 32; ++q)
+          if (cbase + q < n) dst[q] = (int32_t)v[q];
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ dp4a cross-check kernel
+__global__ void __launch_bounds__(256)
+gram_i8_simt_kernel(const int8_t* __restrict__ A, int64_t m, int64_t lda, const int8_t* __restrict__ B, int64_t n,
+                    int64_t ldb, int64_t k0, int64_t k1, int32_t* __restrict__ C, int64_t ldc) {
+  __shared__ uint32_t As[64][17];
+  __shared__ uint32_t Bs[64][17];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int64_t row0 = (int64_t)blockIdx.y * 64, col0 = (int64_t)blockIdx.x * 64;
+  int acc[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0;
+  for (int64_t kk = k0; kk < k1; kk += 64) {
+    {
+      const int r = threadIdx.x >> 2, q = threadIdx.x & 3;   // 64 rows x 4 uint4
+      uint4 va = make_uint4(0, 0, 0, 0), vb = make_uint4(0, 0, 0, 0);
+      if (row0 + r < m) va = *reinterpret_cast<const uint4*>(A + (row0 + r) * lda + kk + q * 16);
+      if (col0 + r < n) vb = *reinterpret_cast<const uint4*>(B + (col0 + r) * ldb + kk + q * 16);
+      As[r][q * 4 + 0] = va.x; As[r][q * 4 + 1] = va.y; As[r][q * 4 + 2] = va.z; As[r][q * 4 + 3] = va.w;
+      Bs[r][q * 4 + 0] = vb.x; Bs[r][q * 4 + 1] = vb.y; Bs[r][q * 4 + 2] = vb.z; Bs[r][q * 4 + 3] = vb.w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < 16; ++w) {
+      int a[4], b[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) a[r] = (int)As[ty * 4 + r][w];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) b[c] = (int)Bs[tx * 4 + c][w];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = __dp4a(a[r], b[c], acc[r][c]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int64_t gi = row0 + ty * 4 + r, gj = col0 + tx * 4 + c;
+      if (gi < m && gj < n) C[gi * ldc + gj] = acc[r][c];
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_operand_map(nbw_ctx* ctx, CUtensorMap* map, const int8_t* base, int64_t rows, int64_t ld) {
+  if (!ctx->encode_tiled) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    NBW_CUDA(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) NBW_FAIL(ctx, NBW_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    ctx->encode_tiled = fn;
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld};
+  const cuuint32_t box[2] = {BK, BM};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled)(
+      map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int8_t*>(base), dims, strides, box, estr,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) NBW_FAIL(ctx, NBW_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return NBW_OK;
+}
+
+}  // namespace
+
+extern "C" int nbw_gram_i8(nbw_ctx* ctx, const int8_t* A, int64_t m, int64_t lda, const int8_t* B, int64_t n,
+                           int64_t ldb, int64_t k0, int64_t k1, int32_t* C, int64_t ldc, int impl, void* stream) {
+  if (!ctx) return NBW_ERR_INVALID;
+  NBW_REQUIRE(ctx, m >= 0 && n >= 0 && ldc >= n, "bad shape");
+  NBW_REQUIRE(ctx, k0 >= 0 && k1 > k0 && k0 % 128 == 0 && k1 % 128 == 0, "k0, k1 must be multiples of 128 with k1 > k0");
+  NBW_REQUIRE(ctx, lda % 128 == 0 && ldb % 128 == 0 && lda >= k1 && ldb >= k1, "lda/ldb must be multiples of 128 and >= k1");
+  if (m == 0 || n == 0) return NBW_OK;
+  NBW_REQUIRE(ctx, A && B && C, "null pointer");
+  NBW_REQUIRE(ctx, ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 127) == 0,
+              "A and B must be 128-byte aligned");
+  NBW_REQUIRE(ctx, m < ((int64_t)1 << 31) && n < ((int64_t)1 << 31) && lda < ((int64_t)1 << 31) && ldb < ((int64_t)1 << 31),
+              "dimension too large");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (impl == 1) {
+    dim3 grid((unsigned)((n + 63) / 64), (unsigned)((m + 63) / 64));
+    NBW_REQUIRE(ctx, grid.y <= 65535, "simt gram: m too large");
+    gram_i8_simt_kernel<<<grid, 256, 0, st>>>(A, m, lda, B, n, ldb, k0, k1, C, ldc);
+    NBW_CHECK_LAUNCH(ctx);
+    return NBW_OK;
+  }
+  NBW_REQUIRE(ctx, impl == 0, "unknown impl %d", impl);
+  CUtensorMap map_a, map_b;
+  int rc = make_operand_map(ctx, &map_a, A, m, lda);
+  if (rc) return rc;
+  rc = make_operand_map(ctx, &map_b, B, n, ldb);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NBW_CUDA(ctx, cudaFuncSetAttribute(gram_i8_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)((n + BN - 1) / BN), (unsigned)((m + BM - 1) / BM));
+  NBW_REQUIRE(ctx, grid.y <= 65535, "gram: m too large for one launch (tile the rows)");
+  gram_i8_tcgen05_kernel<<<grid, 128, SMEM_BYTES, st>>>(map_a, map_b, C, ldc, m, n, (int32_t)(k0 / BK),
+                                                       (int32_t)((k1 - k0) / BK));
+  NBW_CHECK_LAUNCH(ctx);
+  return NBW_OK;
+}

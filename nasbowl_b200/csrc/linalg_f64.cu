@@ -1,0 +1,512 @@
+// fp64 GP linear algebra on device: weighted Gram accumulation + cosine normalisation
+// (kernels/combine_kernels.py:36-56), blocked Cholesky with pivot check + log-determinant,
+// triangular inverse (bayesopt/utils.py:120-140, compute_pd_inverse) and the GEMMs of the GP
+// posterior (bayesopt/gp.py:271-276).  Training sets are n <= a few thousand, so these are
+// small, latency-bound problems: plain shared-memory tiling, no tensor cores (the reference
+// evaluates them in fp32; fp64 here is what lets the posterior meet the 1e-6 parity target).
+#include "nbw_common.cuh"
+
+#include <math.h>
+
+namespace {
+
+constexpr int NB = 32;   // Cholesky / trtri block size
+
+// ------------------------------------------------------------------ element-wise kernels
+__global__ void gram_accumulate_kernel(const int32_t* __restrict__ K, int64_t ldk, int64_t m, int64_t n,
+                                       double w, double beta, double* __restrict__ out, int64_t ldo) {
+  const int64_t total = m * n, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const int64_t i = t / n, j = t % n;
+    const double v = w * (double)K[i * ldk + j];
+    out[i * ldo + j] = (beta == 0.0) ? v : beta * out[i * ldo + j] + v;
+  }
+}
+
+__global__ void axpby_kernel(const double* __restrict__ X, int64_t ldx, int64_t m, int64_t n, double a, double b,
+                             double* __restrict__ Y, int64_t ldy) {
+  const int64_t total = m * n, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const int64_t i = t / n, j = t % n;
+    const double v = a * X[i * ldx + j];
+    Y[i * ldy + j] = (b == 0.0) ? v : b * Y[i * ldy + j] + v;
+  }
+}
+
+__global__ void inv_sqrt_diag_kernel(const double* __restrict__ K, int64_t ld, int64_t n, double* __restrict__ s) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) s[i] = 1.0 / sqrt(K[i * ld + i]);
+}
+
+__global__ void scale_sym_kernel(double* __restrict__ K, int64_t ld, int64_t n, const double* __restrict__ s) {
+  const int64_t total = n * n, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const int64_t i = t / n, j = t % n;
+    K[i * ld + j] = K[i * ld + j] * s[i] * s[j];
+  }
+}
+
+__global__ void scale_features_kernel(const int8_t* __restrict__ phi, int64_t ld_phi, int64_t n, int64_t k0,
+                                      int64_t width, const double* __restrict__ s, double sqrt_w,
+                                      double* __restrict__ B, int64_t ldb) {
+  const int64_t total = n * width, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const int64_t i = t / width, j = t % width;
+    B[i * ldb + j] = s[i] * sqrt_w * (double)phi[i * ld_phi + k0 + j];
+  }
+}
+
+__global__ void posterior_cov_kernel(const double* __restrict__ Kss, int64_t ldk, const double* __restrict__ Q,
+                                     int64_t ldq, int64_t m, double lik, double y_std,
+                                     double* __restrict__ cov, int64_t ldc) {
+  const int64_t total = m * m, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const int64_t i = t / m, j = t % m;
+    double c = Kss[i * ldk + j] + (i == j ? lik : 0.0) - Q[i * ldq + j];
+    c = fmax(c, lik);                     // torch.clamp(cov_s, likelihood, inf), gp.py:276
+    const double sd = sqrt(c) * y_std;    // gp.py:278-279
+    cov[i * ldc + j] = sd * sd;           // gp.py:280
+  }
+}
+
+// sum of squares of an m x n block -> *out (double, atomically accumulated; caller zeroes)
+__global__ void sumsq_kernel(const double* __restrict__ X, int64_t ld, int64_t m, int64_t n, double* out) {
+  const int64_t total = m * n, stride = (int64_t)gridDim.x * blockDim.x;
+  double acc = 0.0;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const double v = X[(t / n) * ld + (t % n)];
+    acc += v * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ double ws[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) ws[warp] = acc;
+  __syncthreads();
+  if (warp == 0) {
+    acc = lane < (blockDim.x >> 5) ? ws[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) atomicAdd(out, acc);
+  }
+}
+
+// ------------------------------------------------------------------ GEMM
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256)
+gemm_f64_kernel(int64_t m, int64_t n, int64_t k, double alpha, const double* __restrict__ A, int64_t lda,
+                const double* __restrict__ B, int64_t ldb, double beta, double* __restrict__ C, int64_t ldc) {
+  constexpr int BM = 64, BN = 64, BK = 16;
+  __shared__ double As[BK][BM + 2];
+  __shared__ double Bs[BK][BN + 2];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int64_t row0 = (int64_t)blockIdx.y * BM, col0 = (int64_t)blockIdx.x * BN;
+  double acc[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
+
+  for (int64_t k0 = 0; k0 < k; k0 += BK) {
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const int idx = threadIdx.x + s * 256;
+      {
+        int i, kk;
+        if (TA) { i = idx % BM; kk = idx / BM; } else { kk = idx % BK; i = idx / BK; }
+        const int64_t gi = row0 + i, gk = k0 + kk;
+        double v = 0.0;
+        if (gi < m && gk < k) v = TA ? A[gk * lda + gi] : A[gi * lda + gk];
+        As[kk][i] = v;
+      }
+      {
+        int j, kk;
+        if (TB) { kk = idx % BK; j = idx / BK; } else { j = idx % BN; kk = idx / BN; }
+        const int64_t gj = col0 + j, gk = k0 + kk;
+        double v = 0.0;
+        if (gj < n && gk < k) v = TB ? B[gj * ldb + gk] : B[gk * ldb + gj];
+        Bs[kk][j] = v;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      double a[4], b[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) a[r] = As[kk][ty * 4 + r];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) b[c] = Bs[kk][tx * 4 + c];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = fma(a[r], b[c], acc[r][c]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int64_t gi = row0 + ty * 4 + r;
+    if (gi >= m) continue;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int64_t gj = col0 + tx * 4 + c;
+      if (gj >= n) continue;
+      const double v = alpha * acc[r][c];
+      C[gi * ldc + gj] = (beta == 0.0) ? v : beta * C[gi * ldc + gj] + v;
+    }
+  }
+}
+
+int gemm_enqueue(nbw_ctx* ctx, int ta, int tb, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
+                 int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, cudaStream_t st) {
+  if (m <= 0 || n <= 0) return NBW_OK;
+  dim3 grid((unsigned)((n + 63) / 64), (unsigned)((m + 63) / 64));
+  NBW_REQUIRE(ctx, grid.y <= 65535, "gemm: m too large");
+  if (!ta && !tb) gemm_f64_kernel<false, false><<<grid, 256, 0, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+  else if (ta && !tb) gemm_f64_kernel<true, false><<<grid, 256, 0, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+  else if (!ta && tb) gemm_f64_kernel<false, true><<<grid, 256, 0, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+  else gemm_f64_kernel<true, true><<<grid, 256, 0, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+  NBW_CHECK_LAUNCH(ctx);
+  return NBW_OK;
+}
+
+// ------------------------------------------------------------------ Cholesky (lower, blocked)
+__global__ void chol_init_kernel(const double* __restrict__ A, int64_t lda, int64_t n, double shift,
+                                 double* __restrict__ L, int64_t ldl) {
+  const int64_t total = n * n, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const int64_t i = t / n, j = t % n;
+    L[i * ldl + j] = (j > i) ? 0.0 : A[i * lda + j] + (i == j ? shift : 0.0);
+  }
+}
+
+// Unblocked factorisation of the nb x nb diagonal block at (k0, k0); 32 x 32 threads.
+__global__ void __launch_bounds__(NB * NB)
+potrf_diag_kernel(double* __restrict__ L, int64_t ldl, int64_t k0, int nb, int* __restrict__ info) {
+  __shared__ double a[NB][NB + 1];
+  const int c = threadIdx.x % NB, r = threadIdx.x / NB;
+  const bool in = r < nb && c < nb;
+  a[r][c] = (in && c <= r) ? L[(k0 + r) * ldl + k0 + c] : 0.0;
+  __syncthreads();
+  for (int j = 0; j < nb; ++j) {
+    if (r == j && c == j) {
+      const double d = a[j][j];
+      if (!(d > 0.0)) atomicCAS(info, 0, (int)(k0 + j + 1));
+      a[j][j] = sqrt(d);
+    }
+    __syncthreads();
+    if (c == j && r > j && r < nb) a[r][j] /= a[j][j];
+    __syncthreads();
+    if (c > j && r >= c && r < nb) a[r][c] -= a[r][j] * a[c][j];
+    __syncthreads();
+  }
+  if (in && c <= r) L[(k0 + r) * ldl + k0 + c] = a[r][c];
+}
+
+// Rows below the diagonal block: X = A21 * L11^-T (one thread per row).
+__global__ void __launch_bounds__(128)
+trsm_panel_kernel(double* __restrict__ L, int64_t ldl, int64_t k0, int nb, int64_t n) {
+  __shared__ double l11[NB][NB + 1];
+  for (int t = threadIdx.x; t < NB * NB; t += blockDim.x) {
+    const int r = t / NB, c = t % NB;
+    l11[r][c] = (r < nb && c <= r) ? L[(k0 + r) * ldl + k0 + c] : 0.0;
+  }
+  __syncthreads();
+  const int64_t i = k0 + nb + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double x[NB];
+  double* row = L + i * ldl + k0;
+#pragma unroll
+  for (int j = 0; j < NB; ++j) x[j] = (j < nb) ? row[j] : 0.0;
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    if (j < nb) {
+      double v = x[j];
+#pragma unroll
+      for (int t = 0; t < NB; ++t)
+        if (t < j) v -= x[t] * l11[j][t];
+      x[j] = v / l11[j][j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NB; ++j)
+    if (j < nb) row[j] = x[j];
+}
+
+// Trailing update A22 -= P P^T on the lower triangle, P = L[k0+nb:, k0:k0+nb].
+__global__ void __launch_bounds__(256)
+syrk_update_kernel(double* __restrict__ L, int64_t ldl, int64_t k0, int nb, int64_t n) {
+  const int64_t base = k0 + nb;
+  const int64_t i0 = base + (int64_t)blockIdx.y * 64, j0 = base + (int64_t)blockIdx.x * 64;
+  if (j0 > i0 + 63) return;   // tile strictly above the diagonal
+  __shared__ double Pi[NB][64 + 2];
+  __shared__ double Pj[NB][64 + 2];
+  for (int t = threadIdx.x; t < 64 * NB; t += 256) {
+    const int kk = t % NB, r = t / NB;
+    const int64_t gi = i0 + r, gj = j0 + r;
+    Pi[kk][r] = (gi < n && kk < nb) ? L[gi * ldl + k0 + kk] : 0.0;
+    Pj[kk][r] = (gj < n && kk < nb) ? L[gj * ldl + k0 + kk] : 0.0;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  double acc[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
+#pragma unroll 8
+  for (int kk = 0; kk < NB; ++kk) {
+    double a[4], b[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) a[r] = Pi[kk][ty * 4 + r];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) b[c] = Pj[kk][tx * 4 + c];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[r][c] = fma(a[r], b[c], acc[r][c]);
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int64_t gi = i0 + ty * 4 + r;
+    if (gi >= n) continue;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int64_t gj = j0 + tx * 4 + c;
+      if (gj <= gi) L[gi * ldl + gj] -= acc[r][c];
+    }
+  }
+}
+
+__global__ void logdet_kernel(const double* __restrict__ L, int64_t ldl, int64_t n, double* __restrict__ out) {
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) acc += log(L[i * ldl + i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ double ws[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) ws[warp] = acc;
+  __syncthreads();
+  if (warp == 0) {
+    acc = lane < (blockDim.x >> 5) ? ws[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) *out = 2.0 * acc;
+  }
+}
+
+int chol_enqueue(nbw_ctx* ctx, const double* A, int64_t lda, int64_t n, double shift, double* L, int64_t ldl,
+                 double* d_logdet, int* d_info, cudaStream_t st) {
+  NBW_CUDA(ctx, cudaMemsetAsync(d_info, 0, sizeof(int), st));
+  chol_init_kernel<<<nbw_grid_for(ctx, n * n, 256), 256, 0, st>>>(A, lda, n, shift, L, ldl);
+  NBW_CHECK_LAUNCH(ctx);
+  for (int64_t k0 = 0; k0 < n; k0 += NB) {
+    const int nb = (int)((n - k0) < NB ? (n - k0) : NB);
+    potrf_diag_kernel<<<1, NB * NB, 0, st>>>(L, ldl, k0, nb, d_info);
+    NBW_CHECK_LAUNCH(ctx);
+    const int64_t rest = n - k0 - nb;
+    if (rest > 0) {
+      trsm_panel_kernel<<<(unsigned)((rest + 127) / 128), 128, 0, st>>>(L, ldl, k0, nb, n);
+      NBW_CHECK_LAUNCH(ctx);
+      const unsigned tiles = (unsigned)((rest + 63) / 64);
+      syrk_update_kernel<<<dim3(tiles, tiles), 256, 0, st>>>(L, ldl, k0, nb, n);
+      NBW_CHECK_LAUNCH(ctx);
+    }
+  }
+  logdet_kernel<<<1, 256, 0, st>>>(L, ldl, n, d_logdet);
+  NBW_CHECK_LAUNCH(ctx);
+  return NBW_OK;
+}
+
+// ------------------------------------------------------------------ triangular inverse
+// One CTA per 32-wide block column c of X = L^-1; rows are produced top to bottom:
+//   X[r,c] = L[r,r]^-1 * ( [r==c] I - sum_{c <= t < r} L[r,t] X[t,c] )
+__global__ void __launch_bounds__(NB * NB)
+trtri_lower_kernel(const double* __restrict__ L, int64_t ldl, int64_t n, double* X, int64_t ldx) {
+  __shared__ double Ls[NB][NB + 1];
+  __shared__ double Xs[NB][NB + 1];
+  const int j = threadIdx.x % NB, i = threadIdx.x / NB;
+  const int64_t nblk = (n + NB - 1) / NB;
+  const int64_t c = blockIdx.x, c0 = c * NB;
+  for (int64_t r = c; r < nblk; ++r) {
+    const int64_t r0 = r * NB;
+    double acc = 0.0;
+    for (int64_t t = c; t < r; ++t) {
+      const int64_t t0 = t * NB;
+      Ls[i][j] = (r0 + i < n && t0 + j < n) ? L[(r0 + i) * ldl + t0 + j] : 0.0;
+      Xs[i][j] = (t0 + i < n && c0 + j < n) ? X[(t0 + i) * ldx + c0 + j] : 0.0;
+      __syncthreads();
+#pragma unroll 8
+      for (int p = 0; p < NB; ++p) acc = fma(Ls[i][p], Xs[p][j], acc);
+      __syncthreads();
+    }
+    // right-hand side and the diagonal block
+    Xs[i][j] = (r == c) ? ((i == j) ? 1.0 : 0.0) : -acc;
+    Ls[i][j] = (r0 + i < n && r0 + j < n && j <= i) ? L[(r0 + i) * ldl + r0 + j]
+                                                   : ((i == j) ? 1.0 : 0.0);
+    __syncthreads();
+    if (i == 0) {   // lane j forward-substitutes column j
+      for (int p = 0; p < NB; ++p) {
+        double v = Xs[p][j];
+        for (int q = 0; q < p; ++q) v -= Ls[p][q] * Xs[q][j];
+        Xs[p][j] = v / Ls[p][p];
+      }
+    }
+    __syncthreads();
+    if (r0 + i < n && c0 + j < n) X[(r0 + i) * ldx + c0 + j] = Xs[i][j];
+    __syncthreads();
+  }
+}
+
+int trtri_enqueue(nbw_ctx* ctx, const double* L, int64_t ldl, int64_t n, double* X, int64_t ldx, cudaStream_t st) {
+  NBW_CUDA(ctx, cudaMemset2DAsync(X, ldx * sizeof(double), 0, n * sizeof(double), n, st));
+  trtri_lower_kernel<<<(unsigned)((n + NB - 1) / NB), NB * NB, 0, st>>>(L, ldl, n, X, ldx);
+  NBW_CHECK_LAUNCH(ctx);
+  return NBW_OK;
+}
+
+}  // namespace
+
+// ====================================================================== C-ABI
+extern "C" int nbw_gram_accumulate(nbw_ctx* ctx, const int32_t* K, int64_t ldk, int64_t m, int64_t n,
+                                   double w, double beta, double* out, int64_t ldo, void* stream) {
+  if (!ctx) return NBW_ERR_INVALID;
+  NBW_REQUIRE(ctx, m >= 0 && n >= 0 && ldk >= n && ldo >= n, "bad shape");
+  if (m == 0 || n == 0) return NBW_OK;
+  NBW_REQUIRE(ctx, K && out, "null pointer");
+  gram_accumulate_kernel<<<nbw_grid_for(ctx, m * n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      K, ldk, m, n, w, beta, out, ldo);
+  NBW_CHECK_LAUNCH(ctx);
+  return NBW_OK;
+}
+
+extern "C" int nbw_axpby_f64(nbw_ctx* ctx, const double* X, int64_t ldx, int64_t m, int64_t n, double a, double b,
+                             double* Y, int64_t ldy, void* stream) {
+  if (!ctx) return NBW_ERR_INVALID;
+  NBW_REQUIRE(ctx, m >= 0 && n >= 0 && ldx >= n && ldy >= n, "bad shape");
+  if (m == 0 || n == 0) return NBW_OK;
+  NBW_REQUIRE(ctx, X && Y, "null pointer");
+  axpby_kernel<<<nbw_grid_for(ctx, m * n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(X, ldx, m, n, a, b, Y, ldy);
+  NBW_CHECK_LAUNCH(ctx);
+  return NBW_OK;
+}
+
+extern "C" int nbw_gram_normalize(nbw_ctx* ctx, double* K, int64_t ld, int64_t n, double* inv_sqrt_diag,
+                                  void* stream) {
+  if (!ctx) return NBW_ERR_INVALID;
+  NBW_REQUIRE(ctx, n >= 0 && ld >= n, "bad shape");
+  if (n == 0) return NBW_OK;
+  NBW_REQUIRE(ctx, K && inv_sqrt_diag, "null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  inv_sqrt_diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(K, ld, n, inv_sqrt_diag);
+  NBW_CHECK_LAUNCH(ctx);
+  scale_sym_kernel<<<nbw_grid_for(ctx, n * n, 256), 256, 0, st>>>(K, ld, n, inv_sqrt_diag);
+  NBW_CHECK_LAUNCH(ctx);
+  return NBW_OK;
+}
+
+extern "C" int nbw_scale_features(nbw_ctx* ctx, const int8_t* phi, int64_t ld_phi, int64_t n, int64_t k0,
+                                  int64_t k1, const double* s, double sqrt_w, double* B, int64_t ldb,
+                                  void* stream) {
+  if (!ctx) return NBW_ERR_INVALID;
+  NBW_REQUIRE(ctx, n >= 0 && k1 >= k0 && k0 >= 0 && ld_phi >= k1 && ldb >= k1 - k0, "bad shape");
+  if (n == 0 || k1 == k0) return NBW_OK;
+  NBW_REQUIRE(ctx, phi && s && B, "null pointer");
+  scale_features_kernel<<<nbw_grid_for(ctx, n * (k1 - k0), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      phi, ld_phi, n, k0, k1 - k0, s, sqrt_w, B, ldb);
+  NBW_CHECK_LAUNCH(ctx);
+  return NBW_OK;
+}
+
+extern "C" int nbw_posterior_cov_finish(nbw_ctx* ctx, const double* Kss, int64_t ldk, const double* Q,
+                                        int64_t ldq, int64_t m, double lik, double y_std, double* cov,
+                                        int64_t ldc, void* stream) {
+  if (!ctx) return NBW_ERR_INVALID;
+  NBW_REQUIRE(ctx, m >= 0 && ldk >= m && ldq >= m && ldc >= m, "bad shape");
+  if (m == 0) return NBW_OK;
+  NBW_REQUIRE(ctx, Kss && Q && cov, "null pointer");
+  posterior_cov_kernel<<<nbw_grid_for(ctx, m * m, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      Kss, ldk, Q, ldq, m, lik, y_std, cov, ldc);
+  NBW_CHECK_LAUNCH(ctx);
+  return NBW_OK;
+}
+
+extern "C" int nbw_gemm_f64(nbw_ctx* ctx, int trans_a, int trans_b, int64_t m, int64_t n, int64_t k,
+                            double alpha, const double* A, int64_t lda, const double* B, int64_t ldb,
+                            double beta, double* C, int64_t ldc, void* stream) {
+  if (!ctx) return NBW_ERR_INVALID;
+  NBW_REQUIRE(ctx, m >= 0 && n >= 0 && k >= 0 && ldc >= n, "bad shape");
+  NBW_REQUIRE(ctx, lda >= (trans_a ? m : k) && ldb >= (trans_b ? k : n), "bad leading dimension");
+  NBW_REQUIRE(ctx, (m == 0 || n == 0) || (A && B && C) || k == 0, "null pointer");
+  return gemm_enqueue(ctx, trans_a, trans_b, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc,
+                      static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int nbw_chol_f64(nbw_ctx* ctx, const double* A, int64_t lda, int64_t n, double shift, double* L,
+                            int64_t ldl, double* logdet_h, int* info_h, void* stream) {
+  if (!ctx) return NBW_ERR_INVALID;
+  NBW_REQUIRE(ctx, n > 0 && lda >= n && ldl >= n && A && L && info_h, "bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = nbw_scratch_ensure(ctx, 1024, st);
+  if (rc) return rc;
+  Carver cv(ctx->scratch);
+  double* d_logdet = cv.take<double>(1);
+  int* d_info = cv.take<int>(1);
+  rc = chol_enqueue(ctx, A, lda, n, shift, L, ldl, d_logdet, d_info, st);
+  if (rc) return rc;
+  double ld = 0.0;
+  NBW_CUDA(ctx, cudaMemcpyAsync(&ld, d_logdet, sizeof(double), cudaMemcpyDeviceToHost, st));
+  NBW_CUDA(ctx, cudaMemcpyAsync(info_h, d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
+  NBW_CUDA(ctx, cudaStreamSynchronize(st));
+  if (logdet_h) *logdet_h = ld;
+  if (*info_h != 0) NBW_FAIL(ctx, NBW_ERR_NOT_PD, "matrix not positive definite at pivot %d", *info_h - 1);
+  return NBW_OK;
+}
+
+extern "C" int nbw_trtri_lower_f64(nbw_ctx* ctx, const double* L, int64_t ldl, int64_t n, double* Linv,
+                                   int64_t ldi, void* stream) {
+  if (!ctx) return NBW_ERR_INVALID;
+  NBW_REQUIRE(ctx, n > 0 && ldl >= n && ldi >= n && L && Linv, "bad argument");
+  return trtri_enqueue(ctx, L, ldl, n, Linv, ldi, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int nbw_gp_factor(nbw_ctx* ctx, const double* K, int64_t ldk, int64_t n, double lik,
+                             const double* y, double* L, int64_t ldl, double* Linv, int64_t ldi,
+                             double* alpha, double* stats_h, int* info_h, void* stream) {
+  if (!ctx) return NBW_ERR_INVALID;
+  NBW_REQUIRE(ctx, n > 0 && ldk >= n && ldl >= n && ldi >= n, "bad shape");
+  NBW_REQUIRE(ctx, K && y && L && Linv && alpha && stats_h && info_h, "null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = nbw_scratch_ensure(ctx, Carver::pad(sizeof(double) * n) + 4096, st);
+  if (rc) return rc;
+  Carver cv(ctx->scratch);
+  double* d_stats = cv.take<double>(4);   // logdet, yKy, trKinv, |alpha|^2
+  int* d_info = cv.take<int>(1);
+  double* z = cv.take<double>(n);
+  NBW_CUDA(ctx, cudaMemsetAsync(d_stats, 0, sizeof(double) * 4, st));
+  rc = chol_enqueue(ctx, K, ldk, n, lik, L, ldl, d_stats + 0, d_info, st);
+  if (rc) return rc;
+  rc = trtri_enqueue(ctx, L, ldl, n, Linv, ldi, st);
+  if (rc) return rc;
+  // z = Linv y ; alpha = Linv^T z
+  rc = gemm_enqueue(ctx, 0, 0, n, 1, n, 1.0, Linv, ldi, y, 1, 0.0, z, 1, st);
+  if (rc) return rc;
+  rc = gemm_enqueue(ctx, 1, 0, n, 1, n, 1.0, Linv, ldi, z, 1, 0.0, alpha, 1, st);
+  if (rc) return rc;
+  sumsq_kernel<<<1, 256, 0, st>>>(z, 1, n, 1, d_stats + 1);
+  NBW_CHECK_LAUNCH(ctx);
+  sumsq_kernel<<<nbw_grid_for(ctx, n * n, 256, 2), 256, 0, st>>>(Linv, ldi, n, n, d_stats + 2);
+  NBW_CHECK_LAUNCH(ctx);
+  sumsq_kernel<<<1, 256, 0, st>>>(alpha, 1, n, 1, d_stats + 3);
+  NBW_CHECK_LAUNCH(ctx);
+  double hs[4];
+  NBW_CUDA(ctx, cudaMemcpyAsync(hs, d_stats, sizeof(hs), cudaMemcpyDeviceToHost, st));
+  NBW_CUDA(ctx, cudaMemcpyAsync(info_h, d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
+  NBW_CUDA(ctx, cudaStreamSynchronize(st));
+  stats_h[0] = hs[0];
+  stats_h[1] = hs[1];
+  stats_h[2] = hs[2];
+  stats_h[3] = hs[3];
+  if (*info_h != 0) NBW_FAIL(ctx, NBW_ERR_NOT_PD, "matrix not positive definite at pivot %d", *info_h - 1);
+  return NBW_OK;
+}

@@ -1,0 +1,178 @@
+// Shared device/host helpers for libnbw (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "nbw.h"
+
+struct nbw_ctx {
+  int device;
+  int sm_count;
+  char err[512];
+  void* scratch;
+  size_t scratch_bytes;
+  uint64_t launches;
+  void* encode_tiled;   // cuTensorMapEncodeTiled, resolved lazily (gram_i8.cu)
+};
+
+#define NBW_FAIL(ctx, code, ...)                                  \
+  do {                                                            \
+    if (ctx) snprintf((ctx)->err, sizeof((ctx)->err), __VA_ARGS__); \
+    return (code);                                                \
+  } while (0)
+
+#define NBW_CUDA(ctx, expr)                                                          \
+  do {                                                                               \
+    cudaError_t e__ = (expr);                                                        \
+    if (e__ != cudaSuccess)                                                          \
+      NBW_FAIL(ctx, NBW_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+               __FILE__, __LINE__);                                                  \
+  } while (0)
+
+#define NBW_CHECK_LAUNCH(ctx)          \
+  do {                                 \
+    (ctx)->launches++;                 \
+    NBW_CUDA(ctx, cudaGetLastError()); \
+  } while (0)
+
+#define NBW_REQUIRE(ctx, cond, ...) \
+  do {                              \
+    if (!(cond)) NBW_FAIL(ctx, NBW_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+// Scratch arena: grows on demand (syncs the stream before releasing the old block).
+int nbw_scratch_ensure(nbw_ctx* ctx, size_t bytes, cudaStream_t stream);
+
+struct Carver {
+  char* base;
+  size_t off;
+  explicit Carver(void* p) : base(static_cast<char*>(p)), off(0) {}
+  template <typename T>
+  T* take(size_t count) {
+    off = (off + 255) & ~size_t(255);
+    T* p = reinterpret_cast<T*>(base + off);
+    off += count * sizeof(T);
+    return p;
+  }
+  static size_t pad(size_t bytes) { return (bytes + 255) & ~size_t(255); }
+};
+
+static inline int nbw_grid_for(const nbw_ctx* ctx, int64_t work_items, int per_block, int waves = 8) {
+  int64_t need = (work_items + per_block - 1) / per_block;
+  int64_t cap = (int64_t)ctx->sm_count * waves;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+// ---------------------------------------------------------------------------------------
+// Hashing of WL credentials.
+// A credential is (own id, multiset of successor ids).  Both signatures are of the form
+//   fin( h_own(own) + sum_s h_nbr(id_s) )   (sum mod 2^64: order-independent, so no sort)
+// with independent mixers for key and chk.  Ids are 64-bit: a dense dictionary id (< 2^32)
+// for labels known to the dictionary, or UNSEEN_BIT | key for labels outside it.
+// ---------------------------------------------------------------------------------------
+#define NBW_UNSEEN_BIT 0x8000000000000000ull
+#define NBW_OWN_TWEAK 0x5851f42d4c957f2dull
+
+__host__ __device__ __forceinline__ uint64_t nbw_mix_a(uint64_t x) {   // splitmix64 finaliser
+  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+  x ^= x >> 27; x *= 0x94d049bb133111ebull;
+  x ^= x >> 31;
+  return x;
+}
+__host__ __device__ __forceinline__ uint64_t nbw_mix_b(uint64_t x) {   // murmur3 fmix64
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdull;
+  x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull;
+  x ^= x >> 33;
+  return x;
+}
+
+struct LevelSalt {
+  uint64_t a_own, a_nbr, b_own, b_nbr;
+};
+__host__ __device__ __forceinline__ LevelSalt nbw_level_salt(uint64_t seed, int level) {
+  uint64_t s = nbw_mix_a(seed + 0x9e3779b97f4a7c15ull * (uint64_t)(level + 1));
+  LevelSalt t;
+  t.a_own = nbw_mix_a(s ^ 0x01);
+  t.a_nbr = nbw_mix_a(s ^ 0x02);
+  t.b_own = nbw_mix_b(s ^ 0x03);
+  t.b_nbr = nbw_mix_b(s ^ 0x04);
+  return t;
+}
+__host__ __device__ __forceinline__ uint64_t nbw_key_finish(uint64_t acc) {
+  uint64_t k = nbw_mix_a(acc);
+  return k == NBW_INVALID_KEY ? k - 1 : k;
+}
+__host__ __device__ __forceinline__ uint64_t nbw_chk_finish(uint64_t acc) { return nbw_mix_b(acc); }
+
+// ---------------------------------------------------------------------------------------
+// Cell records: lane `node` of a sub-warp reads its own label and successor mask.
+// The 32 lanes of a warp touch 32/NMAX consecutive records = one contiguous span.
+// ---------------------------------------------------------------------------------------
+template <int NMAX>
+struct CellTraits;
+template <>
+struct CellTraits<8> {
+  static constexpr int kStride = 16;
+  static __device__ __forceinline__ uint32_t label(const uint8_t* cells, int64_t g, int node) {
+    return __ldg(cells + g * 16 + node);
+  }
+  static __device__ __forceinline__ uint32_t succ(const uint8_t* cells, int64_t g, int node) {
+    return __ldg(cells + g * 16 + 8 + node);
+  }
+};
+template <>
+struct CellTraits<16> {
+  static constexpr int kStride = 48;
+  static __device__ __forceinline__ uint32_t label(const uint8_t* cells, int64_t g, int node) {
+    return __ldg(cells + g * 48 + node);
+  }
+  static __device__ __forceinline__ uint32_t succ(const uint8_t* cells, int64_t g, int node) {
+    return __ldg(reinterpret_cast<const uint16_t*>(cells + g * 48 + 16) + node);
+  }
+};
+
+// OR-reduce / sum-reduce over the NMAX lanes of a sub-warp (all 32 lanes must call).
+template <int NMAX>
+__device__ __forceinline__ uint32_t subwarp_or(uint32_t v) {
+#pragma unroll
+  for (int o = NMAX / 2; o > 0; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <int NMAX>
+__device__ __forceinline__ int subwarp_sum(int v) {
+#pragma unroll
+  for (int o = NMAX / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <int NMAX>
+__device__ __forceinline__ double subwarp_sum(double v) {
+#pragma unroll
+  for (int o = NMAX / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
+  uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src);
+  uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src);
+  return ((uint64_t)hi << 32) | lo;
+}
+
+// Sum over successors of two per-lane 64-bit values (multiset hash accumulation).
+template <int NMAX>
+__device__ __forceinline__ void successor_sums(uint32_t succ, int sub_base, uint64_t va, uint64_t vb,
+                                               uint64_t& sum_a, uint64_t& sum_b) {
+  sum_a = 0;
+  sum_b = 0;
+#pragma unroll
+  for (int j = 0; j < NMAX; ++j) {
+    uint64_t oa = shfl64(va, sub_base + j);
+    uint64_t ob = shfl64(vb, sub_base + j);
+    if ((succ >> j) & 1u) {
+      sum_a += oa;
+      sum_b += ob;
+    }
+  }
+}

@@ -1,0 +1,306 @@
+// Fused pool scoring: WL relabelling -> dictionary lookup -> GP posterior -> acquisition,
+// one launch for the whole candidate pool.  Replaces, per candidate, GraphGP.predict
+// (bayesopt/gp.py:240-283: a full WL refit on train ∪ {candidate} and an (n+1)^2 Gram) and
+// GraphExpectedImprovement.eval / GraphUpperConfidentBound.eval
+// (bayesopt/acquisitions.py:59-80,130-138).
+//
+// Structure used: the posterior of a candidate c depends only on its
+// histogram restricted to the training vocabulary, phi_c, and on its own self-similarity
+// k_cc over ALL its labels.  With B = diag(K_raw,ii^-1/2) Phi_train the cross-covariance is
+// k_s = B phi_c / sqrt(k_cc), hence
+//     mu_c  = phi_c . (B^T alpha) / sqrt(k_cc)
+//     q_c   = k_s^T K_lam^-1 k_s = phi_c^T (B^T K_lam^-1 B) phi_c / k_cc = phi_c^T G phi_c / k_cc
+// phi_c has at most n_nodes * (h+1) non-zeros, so q_c is a sum of <= (n_nodes (h+1))^2
+// entries of the L2-resident D x D matrix G — no O(n D) or O(n^2) work per candidate.
+//
+// One sub-warp (n_max lanes) per cell, lane = node; successor labels travel by shuffles;
+// the pool is read once (16 / 48 B per cell) and 4 B per cell are written.
+#include "nbw_common.cuh"
+
+#include <math.h>
+
+namespace {
+
+constexpr int kScoreThreads = 256;
+
+__host__ __device__ __forceinline__ uint32_t slot_of(uint64_t key) { return (uint32_t)(key >> 17); }
+
+// ---------------------------------------------------------------- lookup table build
+__global__ void table_insert_kernel(const uint64_t* __restrict__ uniq_keys, const uint64_t* __restrict__ uniq_chks,
+                                    int64_t n_unique, uint4* table, uint32_t mask) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_unique) return;
+  const uint64_t key = uniq_keys[i];
+  uint32_t slot = slot_of(key) & mask;
+  for (uint32_t it = 0; it <= mask; ++it) {
+    unsigned long long* kp = reinterpret_cast<unsigned long long*>(table + slot);
+    const unsigned long long old = atomicCAS(kp, (unsigned long long)NBW_INVALID_KEY, (unsigned long long)key);
+    if (old == (unsigned long long)NBW_INVALID_KEY) {
+      uint32_t* w = reinterpret_cast<uint32_t*>(table + slot);
+      w[2] = (uint32_t)uniq_chks[i];
+      w[3] = (uint32_t)i;
+      return;
+    }
+    slot = (slot + 1) & mask;
+  }
+}
+
+__device__ __forceinline__ bool table_probe(const uint4* __restrict__ table, uint32_t mask, uint64_t key,
+                                            uint32_t chk, uint32_t& id) {
+  uint32_t slot = slot_of(key) & mask;
+  for (uint32_t it = 0; it <= mask; ++it) {
+    const uint4 s = __ldg(table + slot);
+    const uint64_t k = ((uint64_t)s.y << 32) | s.x;
+    if (k == key) {
+      // dictionary keys are unique, so a key hit with a different check word is a label
+      // outside the dictionary
+      if (s.z == chk) { id = s.w; return true; }
+      return false;
+    }
+    if (k == NBW_INVALID_KEY) return false;
+    slot = (slot + 1) & mask;
+  }
+  return false;
+}
+
+// count / rank of a node's 64-bit label within its cell (see histogram.cu)
+template <int NMAX>
+__device__ __forceinline__ void class_count_rank64(uint64_t id, bool valid, int node, int sub_base,
+                                                   int& count, int& rank) {
+  count = 0;
+  rank = 0;
+#pragma unroll
+  for (int j = 0; j < NMAX; ++j) {
+    const uint64_t other = shfl64(id, sub_base + j);
+    const bool ov = __shfl_sync(0xffffffffu, (int)valid, sub_base + j) != 0;
+    const bool same = valid && ov && other == id;
+    count += same ? 1 : 0;
+    rank += (same && j < node) ? 1 : 0;
+  }
+}
+
+__device__ __forceinline__ int effective_column(const nbw_model& M, int l, bool seen, uint32_t dense, int rank) {
+  if (!seen) return -1;
+  if (!M.oa) return M.col_off[l] + (int)dense;
+  const int sl = M.label_off[l] + (int)dense;
+  const int mc = (int)__ldg(M.max_count + sl);
+  return rank < mc ? M.col_off[l] + (int)__ldg(M.thermo_base + sl) + rank : -1;
+}
+
+template <int NMAX, int NL, bool FEATURES_ONLY>
+__global__ void __launch_bounds__(kScoreThreads)
+score_pool_kernel(const nbw_model M, const uint8_t* __restrict__ cells, int64_t n_cells,
+                  float* __restrict__ scores, double* __restrict__ mu64, double* __restrict__ var64,
+                  double* __restrict__ score64, int8_t* __restrict__ phi, int64_t ld_phi,
+                  int32_t* __restrict__ self_sim) {
+  constexpr int GPW = 32 / NMAX;
+  const int lane = threadIdx.x & 31;
+  const int node = lane % NMAX;
+  const int sub = lane / NMAX;
+  const int sub_base = sub * NMAX;
+  const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+
+  for (int64_t g0 = warp_id * GPW; g0 < n_cells; g0 += n_warps * GPW) {
+    const int64_t g = g0 + sub;
+    const bool in_range = g < n_cells;
+    const uint32_t label = in_range ? CellTraits<NMAX>::label(cells, g, node) : 0xFFu;
+    const bool present = label != 0xFFu;
+    const uint32_t succ = (in_range && present) ? CellTraits<NMAX>::succ(cells, g, node) : 0u;
+    const uint32_t incoming = subwarp_or<NMAX>(succ);
+    const bool endpoint = present && (succ != 0u || ((incoming >> node) & 1u));
+
+    int col[NL];
+    int cnt[NL];   // class size of the node's label at level l (FEATURES_ONLY / linear self-sim)
+    int rk[NL];
+    int kss = 0;
+
+    // ---- level 0: op code -> dense id (weisfeiler_lehman.py:430-441 in transform form)
+    uint64_t id64;
+    {
+      const uint32_t d0 = present ? (uint32_t)__ldg(M.level0_table + label) : 0xFFFFu;
+      const bool seen = present && d0 != 0xFFFFu;
+      id64 = seen ? (uint64_t)d0 : (NBW_UNSEEN_BIT | (uint64_t)label);
+      class_count_rank64<NMAX>(id64, present, node, sub_base, cnt[0], rk[0]);
+      col[0] = effective_column(M, 0, seen, d0, rk[0]);
+      if (present) kss += M.oa ? 1 : cnt[0];
+    }
+    // ---- levels 1..h
+#pragma unroll
+    for (int l = 1; l < NL; ++l) {
+      const LevelSalt salt = nbw_level_salt(M.seed, l);
+      const uint64_t a_nbr = nbw_mix_a(id64 + salt.a_nbr);
+      const uint64_t b_nbr = nbw_mix_b(id64 + salt.b_nbr);
+      uint64_t sum_a, sum_b;
+      successor_sums<NMAX>(succ, sub_base, a_nbr, b_nbr, sum_a, sum_b);
+      const uint64_t key = nbw_key_finish(nbw_mix_a((id64 ^ NBW_OWN_TWEAK) + salt.a_own) + sum_a);
+      const uint64_t chk = nbw_chk_finish(nbw_mix_b((id64 ^ NBW_OWN_TWEAK) + salt.b_own) + sum_b);
+      uint32_t dense = 0;
+      bool seen = false;
+      if (endpoint) seen = table_probe(static_cast<const uint4*>(M.table[l]), M.table_mask[l], key, (uint32_t)chk, dense);
+      id64 = seen ? (uint64_t)dense : (NBW_UNSEEN_BIT | key);
+      class_count_rank64<NMAX>(id64, endpoint, node, sub_base, cnt[l], rk[l]);
+      col[l] = endpoint ? effective_column(M, l, seen, dense, rk[l]) : -1;
+      if (endpoint) kss += M.oa ? 1 : cnt[l];
+    }
+    const int kcc_i = subwarp_sum<NMAX>(kss);
+
+    if (FEATURES_ONLY) {
+      if (in_range) {
+#pragma unroll
+        for (int l = 0; l < NL; ++l) {
+          if (col[l] >= 0) {
+            if (M.oa) phi[g * ld_phi + col[l]] = 1;
+            else if (rk[l] == 0) phi[g * ld_phi + col[l]] = (int8_t)cnt[l];
+          }
+        }
+        if (node == 0 && self_sim) self_sim[g] = kcc_i;
+      }
+      continue;
+    }
+
+    // ---- posterior: mean and quadratic form in feature space
+    double mu_acc = 0.0, q_acc = 0.0;
+#pragma unroll
+    for (int l = 0; l < NL; ++l)
+      if (col[l] >= 0) mu_acc += __ldg(M.w_mu + col[l]);
+#pragma unroll
+    for (int r = 0; r <= NMAX / 2; ++r) {
+      const int partner = sub_base + ((node + r) % NMAX);
+      const double weight = (r == 0 || r == NMAX / 2) ? 1.0 : 2.0;
+      double part = 0.0;
+#pragma unroll
+      for (int lb = 0; lb < NL; ++lb) {
+        const int pc = __shfl_sync(0xffffffffu, col[lb], partner);
+#pragma unroll
+        for (int la = 0; la < NL; ++la)
+          if (col[la] >= 0 && pc >= 0) part += __ldg(M.G + (int64_t)col[la] * M.ld_g + pc);
+      }
+      q_acc += weight * part;
+    }
+    mu_acc = subwarp_sum<NMAX>(mu_acc);
+    q_acc = subwarp_sum<NMAX>(q_acc);
+
+    if (in_range && node == 0) {
+      const double inv_kcc = 1.0 / (double)kcc_i;
+      const double mu_n = mu_acc * sqrt(inv_kcc);
+      const double q = q_acc * inv_kcc;
+      const double var_n = fmax(1.0 + M.lik - q, M.lik);    // gp.py:272-276 (diagonal)
+      const double sd = sqrt(var_n) * M.y_std;              // gp.py:278-279
+      const double var = sd * sd;                           // gp.py:280
+      const double mu = mu_n * M.y_std + M.y_mean;          // gp.py:277
+      double score;
+      if (M.acq == NBW_ACQ_UCB) {
+        score = mu + M.beta * sd;                           // acquisitions.py:136
+      } else if (M.acq == NBW_ACQ_MEAN) {
+        score = mu;
+      } else {
+        const double d = mu - M.incumbent - M.xi;           // acquisitions.py:71-74
+        const double u = d / sd;
+        const double pdf = exp(-0.5 * u * u) * 0.3989422804014327;
+        const double cdf = 0.5 * erfc(-u * 0.7071067811865476);
+        score = sd * pdf + d * cdf;
+        if (M.acq == NBW_ACQ_AEI) score *= 1.0 - sqrt(M.lik) / sqrt(M.lik + var);   // :75-77
+      }
+      scores[g] = (float)score;
+      if (mu64) mu64[g] = mu;
+      if (var64) var64[g] = var;
+      if (score64) score64[g] = score;
+    }
+  }
+}
+
+template <int NMAX, bool FO>
+int launch_levels(nbw_ctx* ctx, const nbw_model& M, const uint8_t* cells, int64_t n, float* scores,
+                  double* mu64, double* var64, double* score64, int8_t* phi, int64_t ld_phi,
+                  int32_t* self_sim, cudaStream_t st) {
+  const int grid = nbw_grid_for(ctx, n, kScoreThreads / NMAX, 16);
+#define NBW_LAUNCH_NL(NLV)                                                                         \
+  case NLV:                                                                                         \
+    score_pool_kernel<NMAX, NLV, FO><<<grid, kScoreThreads, 0, st>>>(M, cells, n, scores, mu64, var64, \
+                                                                    score64, phi, ld_phi, self_sim); \
+    break;
+  switch (M.h + 1) {
+    NBW_LAUNCH_NL(1)
+    NBW_LAUNCH_NL(2)
+    NBW_LAUNCH_NL(3)
+    NBW_LAUNCH_NL(4)
+    NBW_LAUNCH_NL(5)
+    NBW_LAUNCH_NL(6)
+    NBW_LAUNCH_NL(7)
+    NBW_LAUNCH_NL(8)
+    default:
+      NBW_FAIL(ctx, NBW_ERR_INVALID, "h out of range");
+  }
+#undef NBW_LAUNCH_NL
+  NBW_CHECK_LAUNCH(ctx);
+  return NBW_OK;
+}
+
+int check_model(nbw_ctx* ctx, const nbw_model* M, bool need_posterior) {
+  NBW_REQUIRE(ctx, M != nullptr, "model is NULL");
+  NBW_REQUIRE(ctx, M->n_max == 8 || M->n_max == 16, "model.n_max must be 8 or 16");
+  NBW_REQUIRE(ctx, M->h >= 0 && M->h < NBW_MAX_LEVELS, "model.h out of range");
+  NBW_REQUIRE(ctx, M->level0_table != nullptr, "model.level0_table is NULL");
+  for (int l = 1; l <= M->h; ++l) {
+    NBW_REQUIRE(ctx, M->table[l] != nullptr, "model.table[%d] is NULL", l);
+    NBW_REQUIRE(ctx, ((M->table_mask[l] + 1) & M->table_mask[l]) == 0, "table capacity must be a power of two");
+  }
+  NBW_REQUIRE(ctx, !M->oa || (M->thermo_base && M->max_count), "oa model needs thermo_base/max_count");
+  NBW_REQUIRE(ctx, M->n_features > 0, "model.n_features must be positive");
+  if (need_posterior) {
+    NBW_REQUIRE(ctx, M->G && M->w_mu && M->ld_g >= M->n_features, "model.G / w_mu missing");
+    NBW_REQUIRE(ctx, M->acq >= NBW_ACQ_EI && M->acq <= NBW_ACQ_MEAN, "unknown acquisition");
+  }
+  return NBW_OK;
+}
+
+}  // namespace
+
+extern "C" int nbw_model_build_table(nbw_ctx* ctx, const uint64_t* uniq_keys, const uint64_t* uniq_chks,
+                                     int64_t n_unique, void* table, int64_t capacity, void* stream) {
+  if (!ctx) return NBW_ERR_INVALID;
+  NBW_REQUIRE(ctx, capacity > 0 && (capacity & (capacity - 1)) == 0, "capacity must be a power of two");
+  NBW_REQUIRE(ctx, n_unique >= 0 && capacity >= 2 * n_unique && capacity <= ((int64_t)1 << 31),
+              "capacity must be >= 2 * n_unique");
+  NBW_REQUIRE(ctx, table != nullptr, "table is NULL");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  NBW_CUDA(ctx, cudaMemsetAsync(table, 0xFF, (size_t)capacity * 16, st));
+  if (n_unique == 0) return NBW_OK;
+  NBW_REQUIRE(ctx, uniq_keys && uniq_chks, "null pointer");
+  table_insert_kernel<<<(unsigned)((n_unique + 255) / 256), 256, 0, st>>>(
+      uniq_keys, uniq_chks, n_unique, static_cast<uint4*>(table), (uint32_t)(capacity - 1));
+  NBW_CHECK_LAUNCH(ctx);
+  return NBW_OK;
+}
+
+extern "C" int nbw_score_pool(nbw_ctx* ctx, const nbw_model* model_h, const void* cells, int64_t n_cells,
+                              float* scores, double* mu64, double* var64, double* score64, void* stream) {
+  if (!ctx) return NBW_ERR_INVALID;
+  int rc = check_model(ctx, model_h, true);
+  if (rc) return rc;
+  NBW_REQUIRE(ctx, n_cells >= 0, "n_cells negative");
+  if (n_cells == 0) return NBW_OK;
+  NBW_REQUIRE(ctx, cells && scores, "null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const uint8_t* c = static_cast<const uint8_t*>(cells);
+  if (model_h->n_max == 8)
+    return launch_levels<8, false>(ctx, *model_h, c, n_cells, scores, mu64, var64, score64, nullptr, 0, nullptr, st);
+  return launch_levels<16, false>(ctx, *model_h, c, n_cells, scores, mu64, var64, score64, nullptr, 0, nullptr, st);
+}
+
+extern "C" int nbw_pool_features(nbw_ctx* ctx, const nbw_model* model_h, const void* cells, int64_t n_cells,
+                                 int8_t* phi, int64_t ld_phi, int32_t* self_sim, void* stream) {
+  if (!ctx) return NBW_ERR_INVALID;
+  int rc = check_model(ctx, model_h, false);
+  if (rc) return rc;
+  NBW_REQUIRE(ctx, n_cells >= 0 && ld_phi >= model_h->n_features, "bad shape");
+  if (n_cells == 0) return NBW_OK;
+  NBW_REQUIRE(ctx, cells && phi, "null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  NBW_CUDA(ctx, cudaMemsetAsync(phi, 0, (size_t)n_cells * ld_phi, st));
+  const uint8_t* c = static_cast<const uint8_t*>(cells);
+  if (model_h->n_max == 8)
+    return launch_levels<8, true>(ctx, *model_h, c, n_cells, nullptr, nullptr, nullptr, nullptr, phi, ld_phi, self_sim, st);
+  return launch_levels<16, true>(ctx, *model_h, c, n_cells, nullptr, nullptr, nullptr, nullptr, phi, ld_phi, self_sim, st);
+}

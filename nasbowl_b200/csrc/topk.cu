@@ -1,0 +1,162 @@
+// Top-n selection over the acquisition scores of a pool shard.
+// Replaces propose_location's  np.unique(eis, return_index=True) + np.argpartition
+// (bayesopt/acquisitions.py:101-105): the k largest DISTINCT values, each reported with the
+// first index at which it occurs.  Selection is a tournament: every CTA extracts the top k of
+// its 4096-score chunk by k rounds of (value desc, index asc) arg-max, the per-CTA lists are
+// merged by the same kernel until one list is left.  "Distinct" merging is associative: a
+// partial list always keeps the lowest index of each value it contains.
+#include "nbw_common.cuh"
+
+#include <math.h>
+#include <stdlib.h>
+
+namespace {
+
+constexpr int kTopThreads = 256;
+constexpr int kTopItems = 16;
+constexpr int kTopChunk = kTopThreads * kTopItems;
+
+struct Cand {
+  float v;
+  int32_t pad;
+  int64_t idx;   // -1 = empty
+};
+
+__device__ __forceinline__ bool better(float v, int64_t i, float bv, int64_t bi) {
+  // (v, i) beats (bv, bi): larger value, or equal value and lower index; empty loses
+  if (i < 0) return false;
+  if (bi < 0) return true;
+  return v > bv || (v == bv && i < bi);
+}
+
+template <bool FROM_CANDS>
+__global__ void __launch_bounds__(kTopThreads)
+topk_round_kernel(const float* __restrict__ scores, const Cand* __restrict__ cands, int64_t n, int k,
+                  int distinct, int64_t index_base, Cand* __restrict__ out) {
+  __shared__ float sv[kTopThreads / 32];
+  __shared__ int64_t si[kTopThreads / 32];
+  __shared__ float best_v_s;
+  __shared__ int64_t best_i_s;
+  float v[kTopItems];
+  int64_t ix[kTopItems];
+  const int64_t base = (int64_t)blockIdx.x * kTopChunk;
+#pragma unroll
+  for (int t = 0; t < kTopItems; ++t) {
+    const int64_t p = base + (int64_t)t * kTopThreads + threadIdx.x;
+    v[t] = 0.f;
+    ix[t] = -1;
+    if (p < n) {
+      if (FROM_CANDS) {
+        v[t] = cands[p].v;
+        ix[t] = cands[p].idx;
+      } else {
+        v[t] = scores[p];
+        ix[t] = index_base + p;
+      }
+      if (v[t] != v[t]) ix[t] = -1;   // NaN scores never win
+    }
+  }
+  float last_v = 0.f;
+  int64_t last_i = -1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int round = 0; round < k; ++round) {
+    float bv = 0.f;
+    int64_t bi = -1;
+#pragma unroll
+    for (int t = 0; t < kTopItems; ++t) {
+      bool eligible = ix[t] >= 0;
+      if (eligible && last_i >= 0)
+        eligible = distinct ? (v[t] < last_v) : (v[t] < last_v || (v[t] == last_v && ix[t] > last_i));
+      if (eligible && better(v[t], ix[t], bv, bi)) { bv = v[t]; bi = ix[t]; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { sv[warp] = bv; si[warp] = bi; }
+    __syncthreads();
+    if (warp == 0) {
+      bv = lane < kTopThreads / 32 ? sv[lane] : 0.f;
+      bi = lane < kTopThreads / 32 ? si[lane] : -1;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+      }
+      if (lane == 0) {
+        best_v_s = bv;
+        best_i_s = bi;
+        Cand c;
+        c.v = bv; c.pad = 0; c.idx = bi;
+        out[(int64_t)blockIdx.x * k + round] = c;
+      }
+    }
+    __syncthreads();
+    last_v = best_v_s;
+    last_i = best_i_s;
+    __syncthreads();
+    if (last_i < 0) {   // chunk exhausted: pad the rest of the list with empties
+      for (int r = round + 1 + threadIdx.x; r < k; r += kTopThreads) {
+        Cand c;
+        c.v = 0.f; c.pad = 0; c.idx = -1;
+        out[(int64_t)blockIdx.x * k + r] = c;
+      }
+      break;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int nbw_topk(nbw_ctx* ctx, const float* scores, int64_t n, int k, int distinct, int64_t index_base,
+                        float* top_val_h, int64_t* top_idx_h, int* n_found_h, void* stream) {
+  if (!ctx) return NBW_ERR_INVALID;
+  NBW_REQUIRE(ctx, k >= 1 && k <= 1024, "k must be in [1, 1024]");
+  NBW_REQUIRE(ctx, n >= 0 && top_val_h && top_idx_h && n_found_h, "bad argument");
+  *n_found_h = 0;
+  if (n == 0) return NBW_OK;
+  NBW_REQUIRE(ctx, scores != nullptr, "scores is NULL");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int64_t blocks = (n + kTopChunk - 1) / kTopChunk;
+  // two ping-pong candidate lists
+  const size_t list0 = (size_t)blocks * k;
+  const size_t blocks1 = (list0 + kTopChunk - 1) / kTopChunk;
+  const size_t list1 = blocks1 * (size_t)k;
+  int rc = nbw_scratch_ensure(ctx, Carver::pad(sizeof(Cand) * list0) + Carver::pad(sizeof(Cand) * list1) + 1024, st);
+  if (rc) return rc;
+  Carver cv(ctx->scratch);
+  Cand* buf[2] = {cv.take<Cand>(list0), cv.take<Cand>(list1)};
+  topk_round_kernel<false><<<(unsigned)blocks, kTopThreads, 0, st>>>(scores, nullptr, n, k, distinct, index_base, buf[0]);
+  NBW_CHECK_LAUNCH(ctx);
+  int cur = 0;
+  int64_t count = blocks * k;
+  while (blocks > 1) {
+    const int64_t nb = (count + kTopChunk - 1) / kTopChunk;
+    topk_round_kernel<true><<<(unsigned)nb, kTopThreads, 0, st>>>(nullptr, buf[cur], count, k, distinct, 0, buf[cur ^ 1]);
+    NBW_CHECK_LAUNCH(ctx);
+    cur ^= 1;
+    blocks = nb;
+    count = nb * k;
+  }
+  Cand* host = static_cast<Cand*>(malloc(sizeof(Cand) * k));
+  if (!host) NBW_FAIL(ctx, NBW_ERR_INVALID, "host allocation failed");
+  cudaError_t e = cudaMemcpyAsync(host, buf[cur], sizeof(Cand) * k, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) {
+    free(host);
+    NBW_FAIL(ctx, NBW_ERR_CUDA, "top-k readback failed: %s", cudaGetErrorString(e));
+  }
+  int found = 0;
+  for (int i = 0; i < k; ++i) {
+    if (host[i].idx < 0) break;
+    top_val_h[found] = host[i].v;
+    top_idx_h[found] = host[i].idx;
+    ++found;
+  }
+  free(host);
+  *n_found_h = found;
+  return NBW_OK;
+}

@@ -1,0 +1,328 @@
+"""Device engine: drives libnbw's C-ABI (include/nbw.h) with torch-owned device memory.
+
+PyTorch is used here only as plumbing — allocation, streams, host<->device copies and (in
+parallel.py) torch.distributed.  Every arithmetic step is a hand-written sm_100a kernel
+behind the C-ABI; nothing in this module computes on the CPU or with torch operators.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .cells import CellBatch, record_stride
+
+ACQ = {"EI": 0, "AEI": 1, "UCB": 2, "MEAN": 3}
+DEFAULT_SEED = 0x5EEDB200
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def _pow2_at_least(x: int) -> int:
+    p = 1
+    while p < x:
+        p *= 2
+    return p
+
+
+@dataclass
+class WLFit:
+    """A fitted WL vocabulary over a batch of cells plus the batch's dense features."""
+    n_cells: int
+    n_max: int
+    h: int
+    oa: bool
+    seed: int
+    ids: torch.Tensor                  # int32 storage [h+1, n_cells * n_max] (u32 values)
+    dims: List[int]                    # D_l: distinct labels per level
+    uniq_keys: List[torch.Tensor]      # per level, int64 storage (u64) sorted ascending
+    uniq_chks: List[torch.Tensor]
+    label_off: List[int]               # stacked label offsets, len h+2
+    widths: List[int]                  # feature columns per level (D_l, or thermometer width)
+    col_off: List[int]                 # feature column offsets (levels padded to 128), len h+2
+    phi: torch.Tensor                  # int8 [n_cells, ld_phi]
+    self_sim: torch.Tensor             # int32 [n_cells]  = K_raw(g, g) at depth h
+    thermo_base: Optional[torch.Tensor] = None   # int32 [total labels] (oa)
+    max_count: Optional[torch.Tensor] = None     # uint8 [total labels] (oa)
+    op_codes: Optional[np.ndarray] = None        # sorted op codes present (level-0 dictionary)
+
+    @property
+    def ld_phi(self) -> int:
+        return self.phi.shape[1]
+
+    def k_end(self, h: int) -> int:
+        """Feature columns [0, k_end(h)) hold WL levels 0..h."""
+        return self.col_off[h + 1]
+
+
+class Engine:
+    """One per process / GPU (the C-ABI context is bound to the current CUDA device)."""
+    _instances = {}
+
+    @classmethod
+    def get(cls, device: Optional[int] = None) -> "Engine":
+        if not torch.cuda.is_available():
+            raise RuntimeError("nasbowl_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+        if device is None:
+            device = torch.cuda.current_device()
+        eng = cls._instances.get(device)
+        if eng is None:
+            eng = cls(device)
+            cls._instances[device] = eng
+        return eng
+
+    def __init__(self, device: int):
+        self.lib = _lib.load()
+        self.device_index = int(device)
+        self.device = torch.device("cuda", self.device_index)
+        torch.cuda.set_device(self.device)
+        torch.zeros(1, device=self.device)          # make sure the primary context exists
+        ctx = C.c_void_p()
+        rc = self.lib.nbw_create(C.byref(ctx), self.device_index)
+        if rc != 0:
+            raise _lib.NbwError(rc, "nbw_create failed on device %d" % self.device_index)
+        self.ctx = ctx
+
+    # ------------------------------------------------------------------ helpers
+    def _check(self, rc: int):
+        if rc == 0:
+            return
+        msg = self.lib.nbw_last_error(self.ctx).decode("utf-8", "replace")
+        if rc == 3:
+            raise _lib.NotPositiveDefinite(rc, msg)
+        if rc == 4:
+            raise _lib.HashCollision(rc, msg)
+        raise _lib.NbwError(rc, msg)
+
+    @property
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.nbw_launch_count(self.ctx))
+
+    @staticmethod
+    def _p(t: Optional[torch.Tensor]):
+        return None if t is None else C.c_void_p(t.data_ptr())
+
+    def empty(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def upload_cells(self, batch: CellBatch) -> torch.Tensor:
+        rec = torch.from_numpy(batch.to_records())
+        return rec.to(self.device, non_blocking=False)
+
+    # ------------------------------------------------------------------ WL fit (train side)
+    def wl_fit(self, cells: torch.Tensor, n_max: int, h: int, oa: bool = False,
+               seed: int = DEFAULT_SEED, build_features: bool = True) -> WLFit:
+        """WL relabelling + dictionary build + dense features for a batch of cells.
+        Mirrors WeisfeilerLehman.parse_input (grakel_replace/weisfeiler_lehman.py:140-328)."""
+        assert cells.dtype == torch.uint8 and cells.is_cuda and cells.is_contiguous()
+        stride = record_stride(n_max)
+        n = cells.numel() // stride
+        if n == 0:
+            raise ValueError("parsed input is empty")          # weisfeiler_lehman.py:205-206
+        if not (0 <= h < _lib.NBW_MAX_LEVELS):
+            raise TypeError("'h' must be a non-negative integer below %d. Got h%s" % (_lib.NBW_MAX_LEVELS, h))
+        for attempt in range(4):
+            try:
+                return self._wl_fit_once(cells, n, n_max, h, oa, seed + attempt * 0x9E3779B1, build_features)
+            except _lib.HashCollision:
+                continue
+        raise RuntimeError("WL hashing collided for 4 different seeds")
+
+    def _wl_fit_once(self, cells, n, n_max, h, oa, seed, build_features) -> WLFit:
+        lib, ctx, st = self.lib, self.ctx, self.stream
+        n_keys = n * n_max
+        ids = self.empty((h + 1, n_keys), torch.int32)
+        keys = self.empty((n_keys,), torch.int64)
+        chks = self.empty((n_keys,), torch.int64)
+        uk = self.empty((n_keys,), torch.int64)
+        uc = self.empty((n_keys,), torch.int64)
+        dims, ukeys, uchks = [], [], []
+        for l in range(h + 1):
+            prev = ids[l - 1] if l > 0 else None
+            self._check(lib.nbw_wl_signatures(ctx, self._p(cells), n, n_max, self._p(prev), l,
+                                              C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), self._p(keys),
+                                              self._p(chks), st))
+            d = C.c_int64(0)
+            self._check(lib.nbw_dict_build(ctx, self._p(keys), self._p(chks), n_keys, 8 if l == 0 else 64,
+                                           self._p(cells), n_max, self._p(prev), self._p(ids[l]),
+                                           self._p(uk), self._p(uc), n_keys, C.byref(d), st))
+            dims.append(int(d.value))
+            ukeys.append(uk[:d.value].clone())
+            uchks.append(uc[:d.value].clone())
+        label_off = [0]
+        for d in dims:
+            label_off.append(label_off[-1] + d)
+        thermo_base = max_count = None
+        widths = list(dims)
+        if oa:
+            total = label_off[-1]
+            thermo_base = self.empty((max(total, 1),), torch.int32)
+            max_count = self.empty((max(total, 1),), torch.uint8)
+            lo = (C.c_int64 * (h + 2))(*label_off)
+            wd = (C.c_int64 * (h + 1))()
+            self._check(lib.nbw_oa_thermo_layout(ctx, self._p(ids), n, n_max, h + 1, lo, self._p(thermo_base),
+                                                 self._p(max_count), wd, st))
+            widths = [int(w) for w in wd]
+        col_off = [0]
+        for w in widths:
+            col_off.append(col_off[-1] + _round_up(max(w, 1), 128))
+        op_codes = ukeys[0].cpu().numpy().astype(np.int64)
+        fit = WLFit(n_cells=n, n_max=n_max, h=h, oa=bool(oa), seed=seed, ids=ids, dims=dims,
+                    uniq_keys=ukeys, uniq_chks=uchks, label_off=label_off, widths=widths,
+                    col_off=col_off, phi=None, self_sim=None, thermo_base=thermo_base,
+                    max_count=max_count, op_codes=op_codes)
+        if build_features:
+            self.build_features(fit)
+        return fit
+
+    def build_features(self, fit: WLFit):
+        """Dense int8 histogram rows (VertexHistogram.parse_input, vertex_histogram.py:98-209)."""
+        n, h = fit.n_cells, fit.h
+        ld = fit.col_off[-1]
+        fit.phi = self.empty((n, ld), torch.int8)
+        fit.self_sim = self.empty((n,), torch.int32)
+        co = (C.c_int64 * (h + 2))(*fit.col_off)
+        lo = (C.c_int64 * (h + 2))(*fit.label_off)
+        self._check(self.lib.nbw_hist_dense_i8(self.ctx, self._p(fit.ids), n, fit.n_max, h + 1, co, lo,
+                                               self._p(fit.thermo_base), int(fit.oa), self._p(fit.phi), ld,
+                                               self._p(fit.self_sim), self.stream))
+
+    # ------------------------------------------------------------------ integer Gram
+    def gram(self, A: torch.Tensor, B: torch.Tensor, k0: int, k1: int, impl: int = 0,
+             out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """int32 [m, n] = A[:, k0:k1] @ B[:, k0:k1].T  (exact)."""
+        assert A.dtype == torch.int8 and B.dtype == torch.int8
+        m, n = A.shape[0], B.shape[0]
+        if out is None:
+            out = self.empty((m, _round_up(n, 4)), torch.int32)
+        self._check(self.lib.nbw_gram_i8(self.ctx, self._p(A), m, A.stride(0), self._p(B), n, B.stride(0),
+                                         k0, k1, self._p(out), out.stride(0), impl, self.stream))
+        return out[:, :n]
+
+    # ------------------------------------------------------------------ fp64 linear algebra
+    def gram_accumulate(self, K: torch.Tensor, w: float, beta: float, out: torch.Tensor):
+        m, n = K.shape
+        self._check(self.lib.nbw_gram_accumulate(self.ctx, self._p(K), K.stride(0), m, n, float(w), float(beta),
+                                                 self._p(out), out.stride(0), self.stream))
+
+    def axpby(self, X: torch.Tensor, a: float, b: float, Y: torch.Tensor):
+        m, n = X.shape
+        self._check(self.lib.nbw_axpby_f64(self.ctx, self._p(X), X.stride(0), m, n, float(a), float(b),
+                                           self._p(Y), Y.stride(0), self.stream))
+
+    def gram_normalize(self, K: torch.Tensor) -> torch.Tensor:
+        n = K.shape[0]
+        s = self.empty((n,), torch.float64)
+        self._check(self.lib.nbw_gram_normalize(self.ctx, self._p(K), K.stride(0), n, self._p(s), self.stream))
+        return s
+
+    def gemm(self, ta: bool, tb: bool, m: int, n: int, k: int, alpha: float, A: torch.Tensor, lda: int,
+             B: torch.Tensor, ldb: int, beta: float, Cm: torch.Tensor, ldc: int):
+        self._check(self.lib.nbw_gemm_f64(self.ctx, int(ta), int(tb), m, n, k, float(alpha), self._p(A), lda,
+                                          self._p(B), ldb, float(beta), self._p(Cm), ldc, self.stream))
+
+    def gp_factor(self, K: torch.Tensor, lik: float, y: torch.Tensor):
+        """One attempt of compute_pd_inverse (bayesopt/utils.py:127-140) at jitter `lik`.
+        Returns (L, Linv, alpha, logdet, yKy, trKinv, |alpha|^2); raises NotPositiveDefinite."""
+        n = K.shape[0]
+        L = self.empty((n, n), torch.float64)
+        Linv = self.empty((n, n), torch.float64)
+        alpha = self.empty((n,), torch.float64)
+        stats = (C.c_double * 4)()
+        info = C.c_int(0)
+        self._check(self.lib.nbw_gp_factor(self.ctx, self._p(K), K.stride(0), n, float(lik), self._p(y),
+                                           self._p(L), n, self._p(Linv), n, self._p(alpha), stats,
+                                           C.byref(info), self.stream))
+        return L, Linv, alpha, float(stats[0]), float(stats[1]), float(stats[2]), float(stats[3])
+
+    def pd_inverse(self, K: torch.Tensor, jitter: float, y: torch.Tensor):
+        """compute_pd_inverse with its jitter retry (x10, x100) — bayesopt/utils.py:120-140."""
+        last = None
+        for fail in range(3):
+            try:
+                return self.gp_factor(K, jitter * (10 ** fail), y)
+            except _lib.NotPositiveDefinite as e:
+                last = e
+        raise RuntimeError("Gram matrix not positive definite despite of jitter") from last
+
+    def scale_features(self, phi: torch.Tensor, k0: int, k1: int, s: torch.Tensor, sqrt_w: float,
+                       out: torch.Tensor, ldo: int):
+        n = phi.shape[0]
+        self._check(self.lib.nbw_scale_features(self.ctx, self._p(phi), phi.stride(0), n, k0, k1, self._p(s),
+                                                float(sqrt_w), self._p(out), ldo, self.stream))
+
+    def posterior_cov_finish(self, Kss: torch.Tensor, ldk: int, Q: torch.Tensor, m: int, lik: float,
+                             y_std: float) -> torch.Tensor:
+        cov = self.empty((m, m), torch.float64)
+        self._check(self.lib.nbw_posterior_cov_finish(self.ctx, self._p(Kss), ldk, self._p(Q), Q.stride(0), m,
+                                                      float(lik), float(y_std), self._p(cov), m, self.stream))
+        return cov
+
+    # ------------------------------------------------------------------ lookup tables / model
+    def build_tables(self, fit: WLFit, h: int):
+        """Per-level open-addressing tables for pool-side lookups (levels 1..h) and the
+        level-0 op-code table."""
+        tables, masks = [None], [0]
+        for l in range(1, h + 1):
+            d = fit.dims[l]
+            cap = _pow2_at_least(max(2 * d, 16))
+            t = self.empty((cap * 16,), torch.uint8)
+            self._check(self.lib.nbw_model_build_table(self.ctx, self._p(fit.uniq_keys[l]),
+                                                       self._p(fit.uniq_chks[l]), d, self._p(t), cap,
+                                                       self.stream))
+            tables.append(t)
+            masks.append(cap - 1)
+        l0 = np.full(256, 0xFFFF, dtype=np.uint16)
+        for rank, code in enumerate(fit.op_codes):
+            l0[int(code)] = rank
+        level0 = torch.from_numpy(l0.view(np.int16)).to(self.device)
+        return level0, tables, masks
+
+    # ------------------------------------------------------------------ pool scoring
+    def score_pool(self, model: "_lib.Model", cells: torch.Tensor, n_cells: int,
+                   scores: Optional[torch.Tensor] = None, want64: bool = False):
+        if scores is None:
+            scores = self.empty((n_cells,), torch.float32)
+        mu = var = sc = None
+        if want64:
+            mu = self.empty((n_cells,), torch.float64)
+            var = self.empty((n_cells,), torch.float64)
+            sc = self.empty((n_cells,), torch.float64)
+        self._check(self.lib.nbw_score_pool(self.ctx, C.byref(model), self._p(cells), n_cells, self._p(scores),
+                                            self._p(mu), self._p(var), self._p(sc), self.stream))
+        return scores, mu, var, sc
+
+    def pool_features(self, model: "_lib.Model", cells: torch.Tensor, n_cells: int):
+        ld = _round_up(model.n_features, 16)
+        phi = self.empty((n_cells, ld), torch.int8)
+        ss = self.empty((n_cells,), torch.int32)
+        self._check(self.lib.nbw_pool_features(self.ctx, C.byref(model), self._p(cells), n_cells, self._p(phi),
+                                               ld, self._p(ss), self.stream))
+        return phi, ss
+
+    def topk(self, scores: torch.Tensor, k: int, distinct: bool = True, index_base: int = 0):
+        n = scores.numel()
+        vals = (C.c_float * k)()
+        idx = (C.c_int64 * k)()
+        found = C.c_int(0)
+        self._check(self.lib.nbw_topk(self.ctx, self._p(scores), n, k, int(distinct), index_base, vals, idx,
+                                      C.byref(found), self.stream))
+        f = found.value
+        return np.array(vals[:f], dtype=np.float32), np.array(idx[:f], dtype=np.int64)
+
+    def generate_cells(self, family: int, seed: int, first_index: int, n_cells: int) -> torch.Tensor:
+        stride = 48 if family == 2 else 16
+        cells = self.empty((n_cells, stride), torch.uint8)
+        self._check(self.lib.nbw_generate_cells(self.ctx, family, C.c_uint64(seed), first_index, n_cells,
+                                                self._p(cells), self.stream))
+        return cells

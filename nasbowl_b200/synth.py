@@ -1,0 +1,235 @@
+"""Synthetic cell pools shaped like the reference's samplers (host side).
+
+Same construction rules as the reference, driven by a counter-based RNG so that cell i depends
+only on (seed, i) and the CUDA generator (csrc/cellgen.cu, ``nbw_generate_cells``) produces
+bit-identical records:
+
+* family 0 — NAS-Bench-101: bayesopt/generate_test_graphs.py:559-603 (7x7 upper-triangular
+  adjacency, each of 21 edges ~ Bernoulli(1/2); 5 interior ops uniform over 3; `prune`
+  :26-78; reject if no path input->output, 0 edges or > 9 edges).
+* family 1 — NAS-Bench-201: :95-177 + :605-624 (6 ops uniform over 5 on the fixed 8-node
+  template; `none` nodes deleted, `skip_connect` nodes bypassed; one sweep of dangling-node
+  removal; reject empty / edge-less graphs).
+* family 2 — DARTS: darts/darts_objectives.py:159-198 (4 towers x 2 ops uniform over 7, two
+  distinct inputs among earlier states, both cell inputs used) + darts/utils.py:11-98
+  (`add` nodes, skip_connect contraction, removal sweep).
+
+Not reproduced: the reference samplers also drop *duplicates within one pool* (two-node NB101
+cells, repeated NB201 op strings), which is a global operation on a host list.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .cells import NO_NODE, CellBatch
+
+NB101_OPS = ["input", "output", "conv1x1-bn-relu", "conv3x3-bn-relu", "maxpool3x3"]
+NB201_OPS = ["input", "output", "nor_conv_3x3", "nor_conv_1x1", "avg_pool_3x3"]
+DARTS_OPS = ["input1", "input2", "output", "add", "max_pool_3x3", "avg_pool_3x3", "skip_connect",
+             "sep_conv_3x3", "sep_conv_5x5", "dil_conv_3x3", "dil_conv_5x5"]
+FAMILY_OPS = {0: NB101_OPS, 1: NB201_OPS, 2: DARTS_OPS}
+FAMILY_NMAX = {0: 8, 1: 8, 2: 16}
+FAMILY_ID = {"nasbench101": 0, "nasbench201": 1, "darts": 2}
+
+_M64 = (1 << 64) - 1
+_GOLD = 0x9E3779B97F4A7C15
+_GOLD2 = 0xD1B54A32D192ED03
+
+
+def _mix_a(x):
+    x &= _M64
+    x ^= x >> 30
+    x = (x * 0xBF58476D1CE4E5B9) & _M64
+    x ^= x >> 27
+    x = (x * 0x94D049BB133111EB) & _M64
+    x ^= x >> 31
+    return x
+
+
+def _mix_b(x):
+    x &= _M64
+    x ^= x >> 33
+    x = (x * 0xFF51AFD7ED558CCD) & _M64
+    x ^= x >> 33
+    x = (x * 0xC4CEB9FE1A85EC53) & _M64
+    x ^= x >> 33
+    return x
+
+
+def draw(seed: int, index: int, attempt: int, t: int) -> int:
+    """64 random bits for (seed, cell index, rejection attempt, draw number)."""
+    s = _mix_a(seed + _GOLD * (index + 1))
+    return _mix_b(s + _GOLD2 * (attempt * 64 + t + 1))
+
+
+def _below(x: int, n: int, field: int) -> int:
+    """(near-)uniform integer in [0, n) from byte `field` (0..7) of x."""
+    return (((x >> (8 * field)) & 0xFF) * n) >> 8
+
+
+# ------------------------------------------------------------------------------- NB101
+_TRIU = [(r, c) for r in range(7) for c in range(r + 1, 7)]
+
+
+def _nb101_cell(seed, idx):
+    attempt = 0
+    while True:
+        x = draw(seed, idx, attempt, 0)
+        y = draw(seed, idx, attempt, 1)
+        attempt += 1
+        succ = [0] * 7
+        for e, (r, c) in enumerate(_TRIU):
+            if (x >> e) & 1:
+                succ[r] |= 1 << c
+        ops = [0] + [2 + _below(y, 3, i) for i in range(5)] + [1]
+        fwd = 1
+        for v in range(1, 7):
+            if any((fwd >> u) & 1 and (succ[u] >> v) & 1 for u in range(v)):
+                fwd |= 1 << v
+        bwd = 1 << 6
+        for v in range(5, -1, -1):
+            if succ[v] & bwd:
+                bwd |= 1 << v
+        keep = fwd & bwd
+        if keep == 0:
+            continue
+        n_edges = sum(bin(succ[v] & keep).count("1") for v in range(7) if (keep >> v) & 1)
+        if n_edges == 0 or n_edges > 9:
+            continue
+        return _compact(ops, succ, keep, 7)
+
+
+def _compact(ops, succ, keep, n):
+    """Renumber the kept nodes 0..k-1 in ascending order of their ids."""
+    pos, k = {}, 0
+    for v in range(n):
+        if (keep >> v) & 1:
+            pos[v] = k
+            k += 1
+    labels, masks = [NO_NODE] * 16, [0] * 16
+    for v, p in pos.items():
+        labels[p] = ops[v]
+        m = 0
+        for j in range(n):
+            if (succ[v] >> j) & 1 and (keep >> j) & 1:
+                m |= 1 << pos[j]
+        masks[p] = m
+    return labels, masks
+
+
+# ------------------------------------------------------------------------------- NB201
+_T201 = [(0, 1), (0, 2), (0, 4), (1, 3), (1, 5), (2, 6), (3, 6), (4, 7), (5, 7), (6, 7)]
+
+
+def _nb201_cell(seed, idx):
+    attempt = 0
+    while True:
+        x = draw(seed, idx, attempt, 0)
+        attempt += 1
+        choice = [_below(x, 5, i) for i in range(6)]       # 0..2 real ops, 3 skip_connect, 4 none
+        succ0 = [0] * 8
+        pred0 = [0] * 8
+        for u, v in _T201:
+            succ0[u] |= 1 << v
+            pred0[v] |= 1 << u
+        succ = list(succ0)
+        removed = 0
+        for i in range(1, 7):
+            c = choice[i - 1]
+            if c >= 3:
+                removed |= 1 << i
+                if c == 3:       # bypass: original predecessors x original successors (:151-153)
+                    for u in range(8):
+                        if (pred0[i] >> u) & 1:
+                            succ[u] |= succ0[i]
+        keep = 0xFF & ~removed
+        succ = [(succ[v] & keep) if (keep >> v) & 1 else 0 for v in range(8)]
+        indeg = [sum((succ[u] >> v) & 1 for u in range(8)) for v in range(8)]
+        drop = 0
+        for v in range(8):
+            if not (keep >> v) & 1:
+                continue
+            if v != 0 and indeg[v] == 0:
+                drop |= 1 << v
+            elif v != 7 and succ[v] == 0:
+                drop |= 1 << v
+        keep &= ~drop
+        succ = [(succ[v] & keep) if (keep >> v) & 1 else 0 for v in range(8)]
+        if keep == 0 or not any(succ):
+            continue
+        ops = [0] + [2 + min(c, 2) for c in choice] + [1]
+        return _compact(ops, succ, keep, 8)
+
+
+# ------------------------------------------------------------------------------- DARTS
+def _darts_cell(seed, idx):
+    attempt = 0
+    while True:
+        x = draw(seed, idx, attempt, 0)      # 8 op choices
+        y = draw(seed, idx, attempt, 1)      # 8 input choices
+        attempt += 1
+        cell = []
+        for i in range(4):
+            a = (((y >> (16 * i)) & 0xFF) * (i + 2)) >> 8
+            b = (((y >> (16 * i + 8)) & 0xFF) * (i + 1)) >> 8
+            if b >= a:
+                b += 1
+            cell.append((_below(x, 7, 2 * i), a))
+            cell.append((_below(x, 7, 2 * i + 1), b))
+        conns = [c[1] for c in cell]
+        if 0 not in conns or 1 not in conns:          # is_valid_darts (darts/utils.py:148-153)
+            continue
+        n = 15
+        ops = [NO_NODE] * n
+        ops[0], ops[1], ops[14] = 0, 1, 2
+        succ = [0] * n
+        for i in range(4):
+            ops[3 * i + 2] = 4 + cell[2 * i][0]
+            ops[3 * i + 3] = 4 + cell[2 * i + 1][0]
+            ops[3 * i + 4] = 3
+            succ[3 * i + 2] |= 1 << (3 * i + 4)
+            succ[3 * i + 3] |= 1 << (3 * i + 4)
+        for i in range(4):
+            for off in range(2):
+                k = cell[2 * i + off][1]
+                src = k if k <= 1 else (k - 2) * 3 + 4
+                succ[src] |= 1 << (3 * i + 2 + off)
+        for i in range(4):
+            succ[3 * i + 4] |= 1 << 14
+        keep = (1 << n) - 1
+        skip = 4 + 2
+        for j in range(n):                             # skip_connect contraction (:53-64)
+            if (keep >> j) & 1 and ops[j] == skip:
+                out = (succ[j] & -succ[j]).bit_length() - 1
+                for u in range(n):
+                    if (keep >> u) & 1 and (succ[u] >> j) & 1:
+                        succ[u] = (succ[u] | (1 << out)) & ~(1 << j)
+                succ[j] = 0
+                keep &= ~(1 << j)
+        for j in range(n):                             # removal sweep, sequential (:67-86)
+            if not (keep >> j) & 1:
+                continue
+            if ops[j] not in (0, 1):
+                if not any((keep >> u) & 1 and (succ[u] >> j) & 1 for u in range(n)):
+                    keep &= ~(1 << j)
+                    succ[j] = 0
+            else:
+                if succ[j] & keep == 0:
+                    keep &= ~(1 << j)
+        return _compact(ops, succ, keep, n)
+
+
+_GEN = {0: _nb101_cell, 1: _nb201_cell, 2: _darts_cell}
+
+
+def generate_cells_host(family: int, seed: int, first_index: int, n_cells: int) -> CellBatch:
+    """Host restatement of nbw_generate_cells (bit-identical records)."""
+    n_max = FAMILY_NMAX[family]
+    labels = np.full((n_cells, n_max), NO_NODE, dtype=np.uint8)
+    succ = np.zeros((n_cells, n_max), dtype=np.uint16)
+    gen = _GEN[family]
+    for i in range(n_cells):
+        l, m = gen(seed, first_index + i)
+        labels[i] = l[:n_max]
+        succ[i] = m[:n_max]
+    return CellBatch(n_max, labels, succ)

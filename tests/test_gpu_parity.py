@@ -1,0 +1,422 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle and the golden
+vectors of the unmodified reference.  Integer / index work is compared bit-exactly; floating
+point against the fp64 oracle at 1e-6 relative (fp64 outputs) and 1e-4 (fp32 scores), the
+tolerances BASELINE.json's north_star states."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from nasbowl_b200 import synth
+from nasbowl_b200.cells import NO_NODE, CellBatch
+from oracle import gp_oracle, wl_oracle
+
+pytestmark = pytest.mark.gpu
+
+RTOL64 = 1e-6
+RTOL32 = 1e-4
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from nasbowl_b200.engine import Engine
+    return Engine.get()
+
+
+def _sorted_columns(phi):
+    phi = np.asarray(phi)
+    cols = [tuple(c) for c in phi.T.tolist() if any(c)]
+    return sorted(cols)
+
+
+# ---------------------------------------------------------------------------- WL + Gram
+@pytest.mark.parametrize("oa", [False, True])
+@pytest.mark.parametrize("h", [0, 1, 2, 3, 5])
+def test_raw_gram_bit_exact_vs_reference(eng, family, h, oa):
+    _, z, train, _ = family
+    fit = eng.wl_fit(eng.upload_cells(train), train.n_max, h, oa)
+    _, dims = wl_oracle.wl_labels_fast(train, h)
+    assert fit.dims == dims                                  # vocabulary sizes per level
+    K = eng.gram(fit.phi, fit.phi, 0, fit.k_end(h)).cpu().numpy()
+    assert np.array_equal(K, z["Kraw_h%d_oa%d" % (h, int(oa))])     # golden, from the reference
+    K_simt = eng.gram(fit.phi, fit.phi, 0, fit.k_end(h), impl=1).cpu().numpy()
+    assert np.array_equal(K, K_simt)
+    assert np.array_equal(fit.self_sim.cpu().numpy(), np.diag(K))
+    # prefix property: one fit at depth h serves every shallower depth (used by the h grid search)
+    for hh in range(h):
+        Kh = eng.gram(fit.phi, fit.phi, 0, fit.k_end(hh)).cpu().numpy()
+        assert np.array_equal(Kh, wl_oracle.gram_raw(train, hh, oa))
+
+
+def test_histograms_match_oracle_up_to_column_order(eng, family):
+    _, z, train, _ = family
+    fit = eng.wl_fit(eng.upload_cells(train), train.n_max, 3, False)
+    phi = fit.phi.cpu().numpy()
+    ref = wl_oracle.wl_features(train, 3)
+    for l in range(4):
+        block = phi[:, fit.col_off[l]:fit.col_off[l + 1]]
+        assert _sorted_columns(block) == _sorted_columns(ref[l])
+        assert not block[:, fit.widths[l]:].any()            # pad columns are zero
+
+
+def test_joint_gram_and_pool_features(eng, family):
+    _, z, train, pool = family
+    n = len(train)
+    from nasbowl_b200.bayesopt.gp import _wl_model
+    for oa in (False, True):
+        ref = z["Kraw_joint_h2_oa%d" % int(oa)]
+        joint = CellBatch.concat([train, pool])
+        fitj = eng.wl_fit(eng.upload_cells(joint), joint.n_max, 2, oa)
+        assert np.array_equal(eng.gram(fitj.phi, fitj.phi, 0, fitj.k_end(2)).cpu().numpy(), ref)
+        # pool side: features restricted to the training vocabulary + self-similarity over all labels
+        fit = eng.wl_fit(eng.upload_cells(train), train.n_max, 2, oa)
+        model, keep = _wl_model(eng, fit, 2)
+        phi_p, ss = eng.pool_features(model, eng.upload_cells(pool), len(pool))
+        D = fit.k_end(2)
+        K_s = fit.phi.cpu().numpy()[:, :D].astype(np.int64) @ phi_p.cpu().numpy()[:, :D].astype(np.int64).T
+        assert np.array_equal(K_s, ref[:n, n:])
+        assert np.array_equal(ss.cpu().numpy(), np.diag(ref)[n:])
+        # the training cells themselves must map onto their own rows
+        phi_t, ss_t = eng.pool_features(model, eng.upload_cells(train), n)
+        assert np.array_equal(phi_t.cpu().numpy()[:, :D], fit.phi.cpu().numpy()[:, :D])
+        assert np.array_equal(ss_t.cpu().numpy(), np.diag(ref)[:n])
+
+
+def test_gram_tcgen05_random_shapes(eng):
+    rng = np.random.RandomState(0)
+    for (m, n, k) in [(1, 1, 128), (50, 70, 256), (128, 128, 128), (129, 257, 384), (300, 40, 1280), (513, 515, 640)]:
+        A = torch.from_numpy(rng.randint(-128, 128, size=(m, k)).astype(np.int8)).cuda()
+        B = torch.from_numpy(rng.randint(-128, 128, size=(n, k)).astype(np.int8)).cuda()
+        ref = A.cpu().numpy().astype(np.int64) @ B.cpu().numpy().astype(np.int64).T
+        for k0, k1 in [(0, k), (128 * ((k // 128) // 2), k)]:
+            r = A.cpu().numpy().astype(np.int64)[:, k0:k1] @ B.cpu().numpy().astype(np.int64)[:, k0:k1].T
+            assert np.array_equal(eng.gram(A, B, k0, k1, impl=0).cpu().numpy(), r), (m, n, k, k0)
+            assert np.array_equal(eng.gram(A, B, k0, k1, impl=1).cpu().numpy(), r), (m, n, k, k0)
+        assert np.array_equal(eng.gram(A, B, 0, k).cpu().numpy(), ref)
+
+
+# ---------------------------------------------------------------------------- dictionary build
+def test_sort_unique_large(eng):
+    import ctypes as C
+    rng = np.random.RandomState(1)
+    for n, distinct in [(1, 1), (37, 5), (4096, 100), (4097, 4097), (300000, 20000)]:
+        pool = rng.randint(0, 2 ** 63 - 1, size=distinct, dtype=np.int64)
+        keys = pool[rng.randint(0, distinct, size=n)]
+        invalid = rng.rand(n) < 0.1
+        keys_u = keys.astype(np.uint64)
+        keys_u[invalid] = np.uint64(0xFFFFFFFFFFFFFFFF)
+        chks = (keys_u * np.uint64(3)) ^ np.uint64(0x1234)
+        dk = torch.from_numpy(keys_u.view(np.int64)).cuda()
+        dc = torch.from_numpy(chks.view(np.int64)).cuda()
+        ids = torch.empty(n, dtype=torch.int32, device="cuda")
+        uk = torch.empty(n, dtype=torch.int64, device="cuda")
+        uc = torch.empty(n, dtype=torch.int64, device="cuda")
+        d = C.c_int64(0)
+        eng._check(eng.lib.nbw_dict_build(eng.ctx, eng._p(dk), eng._p(dc), n, 64, None, 8, None, eng._p(ids),
+                                          eng._p(uk), eng._p(uc), n, C.byref(d), eng.stream))
+        valid = ~invalid
+        uniq, inv = np.unique(keys_u[valid], return_inverse=True)
+        assert d.value == len(uniq)
+        got = ids.cpu().numpy().view(np.uint32)
+        assert np.all(got[invalid] == 0xFFFFFFFF)
+        assert np.array_equal(got[valid].astype(np.int64), inv.reshape(-1))
+        assert np.array_equal(uk.cpu().numpy()[:d.value].view(np.uint64), uniq)
+
+
+def test_hash_collision_is_detected(eng):
+    """Equal keys with different check words must be reported, not merged."""
+    import ctypes as C
+    from nasbowl_b200 import _lib
+    keys = torch.tensor([5, 9, 5, 7], dtype=torch.int64, device="cuda")
+    chks = torch.tensor([1, 2, 3, 4], dtype=torch.int64, device="cuda")
+    ids = torch.empty(4, dtype=torch.int32, device="cuda")
+    uk = torch.empty(4, dtype=torch.int64, device="cuda")
+    uc = torch.empty(4, dtype=torch.int64, device="cuda")
+    d = C.c_int64(0)
+    rc = eng.lib.nbw_dict_build(eng.ctx, eng._p(keys), eng._p(chks), 4, 64, None, 8, None, eng._p(ids),
+                                eng._p(uk), eng._p(uc), 4, C.byref(d), eng.stream)
+    assert rc == 4
+    with pytest.raises(_lib.HashCollision):
+        eng._check(rc)
+
+
+# ---------------------------------------------------------------------------- linear algebra
+@pytest.mark.parametrize("n", [1, 5, 32, 33, 100, 257, 600])
+def test_cholesky_inverse_gemm(eng, n):
+    rng = np.random.RandomState(n)
+    A = rng.randn(n, n)
+    K = A @ A.T / n + 0.5 * np.eye(n)
+    y = rng.randn(n)
+    Kd = torch.from_numpy(K).cuda()
+    yd = torch.from_numpy(y).cuda()
+    L, Linv, alpha, logdet, yKy, trKinv, a2 = eng.gp_factor(Kd, 0.01, yd)
+    Kl = K + 0.01 * np.eye(n)
+    Lr = np.linalg.cholesky(Kl)
+    np.testing.assert_allclose(L.cpu().numpy(), Lr, rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(Linv.cpu().numpy(), np.linalg.inv(Lr), rtol=1e-8, atol=1e-10)
+    Ki = np.linalg.inv(Kl)
+    np.testing.assert_allclose(alpha.cpu().numpy(), Ki @ y, rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(logdet, np.linalg.slogdet(Kl)[1], rtol=1e-10)
+    np.testing.assert_allclose(yKy, y @ Ki @ y, rtol=1e-9)
+    np.testing.assert_allclose(trKinv, np.trace(Ki), rtol=1e-9)
+    np.testing.assert_allclose(a2, (Ki @ y) @ (Ki @ y), rtol=1e-8)
+    # GEMM in all four transpose modes
+    m, k = 70, 45
+    X, Y = rng.randn(m, k), rng.randn(k, n)
+    for ta in (False, True):
+        for tb in (False, True):
+            Xa = torch.from_numpy(np.ascontiguousarray(X.T if ta else X)).cuda()
+            Yb = torch.from_numpy(np.ascontiguousarray(Y.T if tb else Y)).cuda()
+            Cd = torch.from_numpy(np.ones((m, n))).cuda()
+            eng.gemm(ta, tb, m, n, k, 2.0, Xa, Xa.shape[1], Yb, Yb.shape[1], 0.5, Cd, n)
+            np.testing.assert_allclose(Cd.cpu().numpy(), 2.0 * X @ Y + 0.5, rtol=1e-12, atol=1e-12)
+
+
+def test_not_positive_definite_is_reported(eng):
+    from nasbowl_b200 import _lib
+    K = torch.from_numpy(np.array([[1.0, 2.0], [2.0, 1.0]])).cuda()
+    y = torch.zeros(2, dtype=torch.float64, device="cuda")
+    with pytest.raises(_lib.NotPositiveDefinite):
+        eng.gp_factor(K, 0.0, y)
+    with pytest.raises(RuntimeError, match="not positive definite despite of jitter"):
+        eng.pd_inverse(K, 1e-3, y)        # utils.py:135-137
+
+
+# ---------------------------------------------------------------------------- GP + acquisitions
+def _fit_both(train, y, cands, oa, opt):
+    from nasbowl_b200.bayesopt import GraphGP
+    from nasbowl_b200.kernels import WeisfilerLehman
+    gp = GraphGP(train, torch.tensor(y), [WeisfilerLehman(h=2, oa=oa)])
+    gp.fit(wl_subtree_candidates=cands, optimize_lik=opt, max_lik=0.01)
+    st = gp_oracle.gp_fit(train, y.astype(np.float64), h_candidates=cands, oa=oa, optimize_lik=opt, max_lik=0.01)
+    return gp, st
+
+
+@pytest.mark.parametrize("opt", [False, True])
+@pytest.mark.parametrize("oa", [False, True])
+def test_gp_fit_predict_acquisitions(family, oa, opt):
+    from nasbowl_b200.bayesopt import GraphExpectedImprovement, GraphUpperConfidentBound
+    _, z, train, pool = family
+    tag = "oa%d_opt%d" % (int(oa), int(opt))
+    cands = tuple(int(c) for c in z["gp_cands_" + tag])
+    gp, st = _fit_both(train, z["y"], cands, oa, opt)
+    k = gp.kernels[0]
+    # --- fit: exact discrete quantities, fp64 tolerance elsewhere
+    assert k.h == st.h == int(z["gp_h_" + tag])
+    assert np.float32(gp.likelihood) == np.float32(st.lik) == np.float32(z["gp_lik_" + tag])
+    grid = [gp.nlml_grid[id(k)][c] for c in cands]
+    np.testing.assert_allclose(grid, st.nlml_grid, rtol=1e-9)
+    np.testing.assert_allclose(grid, z["gp_grid_" + tag], rtol=2e-5)          # fp32 reference
+    np.testing.assert_allclose(gp.K.numpy(), st.K, rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(gp.K_i.numpy(), st.K_i, rtol=RTOL64, atol=1e-8)
+    np.testing.assert_allclose(float(gp.logDetK), st.logDetK, rtol=1e-10)
+    if opt:
+        np.testing.assert_allclose(float(gp.nlml), st.nlml, rtol=1e-9)
+    # --- posterior: fused pool path and reference-shaped dense path vs the fp64 oracle
+    mu_o, var_o = gp_oracle.gp_predict_diag(st, train, pool)
+    mu_d, var_d = gp.predict_diag(pool)
+    np.testing.assert_allclose(mu_d.numpy(), mu_o, rtol=RTOL64, atol=1e-9)
+    np.testing.assert_allclose(var_d.numpy(), var_o, rtol=RTOL64, atol=1e-12)
+    mu_f, cov_f = gp.predict(pool)
+    mu_fo, cov_fo = gp_oracle.gp_predict_full(st, train, pool)
+    np.testing.assert_allclose(mu_f.numpy(), mu_fo, rtol=RTOL64, atol=1e-9)
+    np.testing.assert_allclose(cov_f.numpy(), cov_fo, rtol=RTOL64, atol=1e-12)
+    np.testing.assert_allclose(mu_f.numpy(), z["gp_mu_" + tag], rtol=2e-3, atol=2e-3)     # fp32 reference
+    # --- acquisitions
+    inc = gp_oracle.incumbent(st)
+    ei_o = gp_oracle.expected_improvement(mu_o, var_o, inc)
+    acq = GraphExpectedImprovement(gp)
+    assert float(acq._get_incumbent()) == pytest.approx(inc, rel=1e-7) == pytest.approx(float(z["incumbent_" + tag]), rel=1e-6)
+    np.testing.assert_allclose(acq.eval(pool).numpy(), ei_o, rtol=RTOL64, atol=1e-12)
+    np.testing.assert_allclose(acq.eval(pool).numpy(), z["ei_" + tag], rtol=5e-2, atol=2e-3)
+    xs, eis, idx = acq.propose_location(pool, top_n=5)
+    np.testing.assert_allclose(eis.reshape(-1), ei_o, rtol=RTOL32, atol=1e-9)
+    assert eis.dtype == np.float32 and eis.shape == (len(pool), 1)
+    assert set(int(i) for i in idx) == set(int(i) for i in gp_oracle.top_n_distinct(eis.reshape(-1), 5))
+    if opt:
+        aei = GraphExpectedImprovement(gp, augmented_ei=True, in_fill='posterior')
+        np.testing.assert_allclose(aei.eval(pool).numpy(),
+                                   gp_oracle.expected_improvement(mu_o, var_o, inc, augmented=True, lik=st.lik),
+                                   rtol=RTOL64, atol=1e-12)
+        ucb = GraphUpperConfidentBound(gp)
+        ucb.iters = 1
+        np.testing.assert_allclose(ucb.eval(pool).numpy(),
+                                   gp_oracle.upper_confidence_bound(mu_o, var_o, gp_oracle.ucb_beta(1)),
+                                   rtol=RTOL64)
+        np.testing.assert_allclose(ucb.eval(pool).numpy(), z["ucb_" + tag], rtol=5e-3, atol=5e-3)
+        ref_top = set(int(i) for i in z["top5_" + tag])
+        got = set(int(i) for i in idx)
+        if got != ref_top:       # only candidates the fp32 reference cannot tell apart may swap
+            vals = [z["ei_" + tag][i] for i in got ^ ref_top]
+            assert max(vals) - min(vals) < 1e-4 * max(1.0, abs(max(vals)))
+
+
+def test_networkx_entry_points_match_packed(family):
+    """list[nx.DiGraph] in, the reference's call shapes out (gp.py:240-283, acquisitions.py:59-113)."""
+    from nasbowl_b200 import OpVocab
+    from nasbowl_b200.bayesopt import GraphExpectedImprovement, GraphGP
+    from nasbowl_b200.kernels import SumKernel, WeisfilerLehman
+    name, z, train, pool = family
+    vocab = OpVocab(list(z["op_names"]))
+    g_train, g_pool = train.to_networkx(vocab), pool.to_networkx(vocab)
+    k = WeisfilerLehman(h=2)
+    K = k.fit_transform(g_train, rebuild_model=True)
+    assert K.dtype == torch.float64 and np.array_equal(K.numpy(), z["Kraw_h2_oa0"])
+    Kn = SumKernel(WeisfilerLehman(h=2)).fit_transform([1.0], g_train)
+    np.testing.assert_allclose(Kn.numpy(), gp_oracle.normalize_gram(z["Kraw_h2_oa0"]), rtol=1e-13)
+    y = torch.tensor(z["y"])
+    gp = GraphGP(g_train, y, [WeisfilerLehman(h=2)])
+    with pytest.raises(ValueError):
+        gp.predict(g_pool)                                   # predict before fit (gp.py:245-247)
+    gp.fit(wl_subtree_candidates=(1, 2, 3), optimize_lik=False)
+    mu, cov = gp.predict(g_pool)
+    assert mu.shape == (len(pool),) and cov.shape == (len(pool), len(pool))
+    mu1, cov1 = gp.predict(g_pool[4])                        # single graph (gp.py:242-244)
+    np.testing.assert_allclose(mu1.numpy(), mu.numpy()[4:5], rtol=1e-9)
+    np.testing.assert_allclose(cov1.numpy()[0, 0], cov.numpy()[4, 4], rtol=1e-9)
+    acq = GraphExpectedImprovement(gp)
+    e = acq.eval(g_pool[4])
+    xs, eis, idx = acq.propose_location(g_pool, top_n=3)
+    assert len(xs) == 3 and all(x is g_pool[int(i)] for x, i in zip(xs, idx))
+    np.testing.assert_allclose(float(e), eis[4, 0], rtol=1e-5)
+    gp.reset_XY(g_train[:20], y[:20])
+    assert gp.K_i is None
+    with pytest.raises(ValueError):
+        gp.predict(g_pool)
+    gp.fit(wl_subtree_candidates=(0, 1), optimize_lik=True)
+    assert gp.K.shape == (20, 20)
+
+
+def test_appendix_b_known_answer():
+    from nasbowl_b200.bayesopt import GraphExpectedImprovement, GraphGP, GraphUpperConfidentBound
+    from nasbowl_b200.kernels import WeisfilerLehman
+    z, batch = load_golden("appendix_b")
+    train, test = batch[:4], batch[4:]
+    gp = GraphGP(train, torch.tensor(z["y"]), [WeisfilerLehman(h=2)])
+    gp.fit(optimize_lik=False, wl_subtree_candidates=(0, 1, 2))
+    assert gp.kernels[0].h == 2 and np.float32(gp.likelihood) == np.float32(1e-3)
+    np.testing.assert_allclose(gp.K.numpy(), z["gp_K"], rtol=2e-6)
+    np.testing.assert_allclose(gp.K_i.numpy(), z["gp_Ki"], rtol=2e-4)
+    np.testing.assert_allclose(float(gp.logDetK), z["gp_logDetK"], rtol=1e-5)
+    mu, cov = gp.predict(test)
+    np.testing.assert_allclose(mu.numpy(), z["gp_mu"], rtol=1e-4)
+    np.testing.assert_allclose(cov.numpy(), z["gp_cov"], rtol=2e-3, atol=1e-6)
+    np.testing.assert_allclose(GraphExpectedImprovement(gp).eval(test).numpy(), z["ei"], rtol=5e-3, atol=1e-7)
+    ucb = GraphUpperConfidentBound(gp)
+    ucb.iters = 1
+    np.testing.assert_allclose(ucb.eval(test).numpy(), z["ucb"], rtol=1e-4)
+
+
+# ---------------------------------------------------------------------------- top-k
+def test_topk_distinct_and_plain(eng):
+    rng = np.random.RandomState(3)
+    for n in [1, 5, 4096, 4097, 100000, 1 << 20]:
+        s = np.round(rng.randn(n), 2).astype(np.float32)      # many duplicates
+        s[rng.rand(n) < 0.01] = np.nan
+        d = torch.from_numpy(s).cuda()
+        for k in [1, 5, 64]:
+            vals, idx = eng.topk(d, k, distinct=True, index_base=7)
+            ok = ~np.isnan(s)
+            uniq, first = np.unique(s[ok], return_index=True)
+            first = np.nonzero(ok)[0][first]
+            order = np.argsort(-uniq, kind="stable")[:k]
+            assert np.array_equal(vals, uniq[order])
+            assert np.array_equal(idx, first[order] + 7)
+            vals, idx = eng.topk(d, k, distinct=False)
+            cand = np.nonzero(ok)[0]
+            order = cand[np.lexsort((cand, -s[cand]))][:k]
+            assert np.array_equal(idx, order) and np.array_equal(vals, s[order])
+
+
+# ---------------------------------------------------------------------------- synthetic pools
+@pytest.mark.parametrize("fam", [0, 1, 2])
+def test_device_generator_matches_host(eng, fam):
+    host = synth.generate_cells_host(fam, 99, 12345, 3000)
+    dev = eng.generate_cells(fam, 99, 12345, 3000).cpu().numpy()
+    assert np.array_equal(dev, host.to_records())
+    # shards concatenate to the whole
+    a = eng.generate_cells(fam, 99, 12345, 1000).cpu().numpy()
+    b = eng.generate_cells(fam, 99, 13345, 2000).cpu().numpy()
+    assert np.array_equal(np.concatenate([a, b]), dev)
+
+
+# ---------------------------------------------------------------------------- edge cases
+def test_edge_cases(eng):
+    from nasbowl_b200.bayesopt import GraphGP
+    from nasbowl_b200.kernels import WeisfilerLehman
+    train = synth.generate_cells_host(0, 5, 0, 24)
+    y = np.random.RandomState(0).randn(24)
+    gp = GraphGP(train, torch.tensor(y), [WeisfilerLehman(h=2)])
+    gp.fit(wl_subtree_candidates=(2,), optimize_lik=False)
+    st = gp_oracle.gp_fit(train, y, h_candidates=(2,), optimize_lik=False)
+    lab = np.full((5, 8), NO_NODE, np.uint8)
+    suc = np.zeros((5, 8), np.uint16)
+    lab[0, :2] = [0, 1]; suc[0, 0] = 2                        # input -> output (smallest legal cell)
+    lab[1, :3] = [0, 200, 1]; suc[1, 0] = 0b110; suc[1, 1] = 0b100   # op code never seen in training
+    lab[2, :3] = [0, 3, 1]; suc[2, 0] = 0b100                 # node 1 is isolated: counted at level 0 only (Q4)
+    lab[3, :1] = [2]                                          # a single node, no edge
+    lab[4] = train.labels[0]; suc[4] = train.succ[0]          # a training cell: variance at the clamp
+    pool = CellBatch(8, lab, suc)
+    mu, var = gp.predict_diag(pool)
+    mu_o, var_o = gp_oracle.gp_predict_diag(st, train, pool)
+    np.testing.assert_allclose(mu.numpy(), mu_o, rtol=RTOL64, atol=1e-9)
+    np.testing.assert_allclose(var.numpy(), var_o, rtol=RTOL64, atol=1e-12)
+    assert var.numpy()[4] == pytest.approx(st.lik * st.y_std ** 2, rel=1e-9)
+    # empty pool
+    scores, _, _, _ = eng.score_pool(gp.pool_model("EI"), torch.empty((0, 16), dtype=torch.uint8, device="cuda"), 0)
+    assert scores.numel() == 0
+    with pytest.raises(ValueError):
+        eng.wl_fit(torch.empty((0, 16), dtype=torch.uint8, device="cuda"), 8, 2)
+    with pytest.raises(TypeError):
+        WeisfilerLehman(h=-1)
+
+
+# ---------------------------------------------------------------------------- full-size properties
+def test_million_candidate_pool_properties(eng):
+    """BASELINE config 2 size (NB201-shaped, n_train=150, 1M candidates): size-independent
+    properties instead of an oracle pass — shard invariance, invariance under renumbering of a
+    cell's nodes, duplicates of training cells sit at the variance clamp, top-k is consistent."""
+    from nasbowl_b200.bayesopt import GraphExpectedImprovement, GraphGP
+    from nasbowl_b200.kernels import WeisfilerLehman
+    n, M = 150, 1_000_000
+    train = CellBatch.from_records(eng.generate_cells(1, 0, 0, n).cpu().numpy(), 8)
+    y = torch.randn(n, generator=torch.Generator().manual_seed(0))
+    gp = GraphGP(train, y, [WeisfilerLehman(h=2)])
+    gp.fit(wl_subtree_candidates=tuple(range(6)), optimize_lik=True, max_lik=0.01)
+    pool = eng.generate_cells(1, 1234, 10_000, M)
+    acq = GraphExpectedImprovement(gp)
+    scores, mu, var, sc = acq.score_pool(pool, want64=True)
+    s = scores.cpu().numpy()
+    assert np.isfinite(s).all() and (s >= 0).all()
+    # (1) shard invariance: bitwise equal scores whichever way the pool is split
+    cut = 333_337
+    a, _, _, _ = acq.score_pool(pool[:cut].contiguous())
+    b, _, _, _ = acq.score_pool(pool[cut:].contiguous())
+    assert torch.equal(torch.cat([a, b]), scores)
+    # (2) node renumbering: reverse the node order of every cell
+    sub = CellBatch.from_records(pool[:20000].cpu().numpy(), 8)
+    k = sub.n_nodes
+    lab = np.full_like(sub.labels, NO_NODE)
+    suc = np.zeros_like(sub.succ)
+    for v in range(8):
+        src = k - 1 - v
+        okv = src >= 0
+        lab[okv, v] = sub.labels[okv, src[okv]]
+        m = sub.succ[okv, src[okv]].astype(np.uint32)
+        out = np.zeros_like(m)
+        for j in range(8):
+            tgt = k[okv] - 1 - j
+            bit = (m >> j) & 1
+            out |= np.where(tgt >= 0, bit << np.maximum(tgt, 0), 0).astype(np.uint32)
+        suc[okv, v] = out
+    perm, _, _, _ = acq.score_pool(CellBatch(8, lab, suc))
+    np.testing.assert_allclose(perm.cpu().numpy(), s[:20000], rtol=1e-5, atol=1e-9)
+    # (3) against the oracle on a slice the CPU finishes in seconds
+    st = gp_oracle.gp_fit(train, y.numpy().astype(np.float64), h_candidates=tuple(range(6)), optimize_lik=True)
+    assert st.h == gp.kernels[0].h
+    mu_o, var_o = gp_oracle.gp_predict_diag(st, train, sub[:4000])
+    np.testing.assert_allclose(mu.cpu().numpy()[:4000], mu_o, rtol=RTOL64, atol=1e-9)
+    np.testing.assert_allclose(var.cpu().numpy()[:4000], var_o, rtol=RTOL64, atol=1e-12)
+    # (4) top-5 distinct agrees with numpy on the full score vector
+    _, _, idx = acq.propose_location(pool, top_n=5)
+    assert set(int(i) for i in idx) == set(int(i) for i in gp_oracle.top_n_distinct(s, 5))
