@@ -193,10 +193,10 @@ typedef struct {
   int32_t label_off[NBW_MAX_LEVELS];     /* first stacked label index of level l */
   const uint32_t* thermo_base;           /* oa: stacked label -> first column within level */
   const uint8_t* max_count;              /* oa: stacked label -> max training count */
-  int32_t n_features;                    /* D (columns of G) */
-  int32_t ld_g;
-  const double* G;                       /* [D x ld_g] */
-  const double* w_mu;                    /* [D] */
+  int32_t n_features;                    /* D */
+  int32_t ld_g;                          /* >= D + 1 */
+  const double* G;                       /* [(D+1) x ld_g]; row D and column D are all zero: the */
+  const double* w_mu;                    /* [D+1], w_mu[D] = 0   landing slot of unseen labels */
   double lik, y_mean, y_std, incumbent, xi, beta;
 } nbw_model;
 

@@ -59,7 +59,7 @@ class GraphExpectedImprovement(BaseAcquisition):
     def _get_incumbent(self):
         if self.in_fill == 'max':
             return torch.max(self.gp.y_)
-        return self.gp.y_[self.gp._score_state()['incumbent_idx']]
+        return self.gp.y_[self.gp._score_state().incumbent_idx]
 
     def score_pool(self, candidates, want64=False):
         """Acquisition values of a whole pool: (scores f32 device tensor [M], mu, var, score64)."""

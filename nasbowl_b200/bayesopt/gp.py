@@ -25,6 +25,7 @@ import torch
 from .. import _lib
 from ..cells import CellBatch
 from ..kernels import GraphKernels, SumKernel, WeisfilerLehman
+from ..pool_model import PoolModel
 
 _LOG_2PI = math.log(2.0 * math.pi)
 
@@ -53,28 +54,6 @@ def _nlml_from_stats(logdet: float, yKy: float, n: int) -> float:
     """-compute_log_marginal_likelihood (bayesopt/utils.py:102-117) with the reference's
     logDetK = -log|K| (utils.py:138): (yKy/2 - log|K|/2 + n/2 log 2pi) / n."""
     return (0.5 * yKy - 0.5 * logdet + 0.5 * n * _LOG_2PI) / n
-
-
-def _wl_model(eng, fit, h, acq="MEAN"):
-    """nbw_model descriptor for one fitted WL kernel (dictionary side only).  Returns
-    (model, keepalive) — keepalive holds the device tensors the struct points into."""
-    import ctypes as C
-    level0, tables, masks = eng.build_tables(fit, h)
-    m = _lib.Model()
-    m.n_max, m.h, m.oa, m.acq = fit.n_max, h, int(fit.oa), 3 if acq == "MEAN" else acq
-    m.seed = fit.seed & 0xFFFFFFFFFFFFFFFF
-    m.level0_table = level0.data_ptr()
-    for l in range(h + 1):
-        m.col_off[l] = fit.col_off[l]
-        m.label_off[l] = fit.label_off[l]
-        if l >= 1:
-            m.table[l] = tables[l].data_ptr()
-            m.table_mask[l] = masks[l]
-    if fit.oa:
-        m.thermo_base = fit.thermo_base.data_ptr()
-        m.max_count = fit.max_count.data_ptr()
-    m.n_features = fit.k_end(h)
-    return m, (level0, tables)
 
 
 class GraphGP:
@@ -146,6 +125,9 @@ class GraphGP:
         eng = self._engine()
         best_nlml, best_h = math.inf, None
         grid = {}
+        # the reference builds the jitter as `lik * torch.eye(n)` in fp32 (utils.py:129): the value
+        # that reaches the fp64 Gram is fp32(lik); near-singular K_raw(h=0) makes that visible
+        lik = float(np.float32(lik))
         for hc in subtree_candidates:
             K = k.gram_device(fit, hc)
             _, _, _, logdet, yKy, _, _ = eng.pd_inverse(K, float(lik), y_dev)
@@ -296,7 +278,7 @@ class GraphGP:
         G = (L^-1 B)^T (L^-1 B) with B = diag(1/sqrt(K_raw,ii)) sqrt(w) Phi_train."""
         self._require_fit()
         d = self._dev
-        if d['score'] is not None:
+        if d.get('score') is not None:
             return d['score']
         if len(self.sum_kernels.kernels) != 1:
             raise NotImplementedError("the fused pool path handles a single WL kernel; use predict()")
@@ -308,32 +290,32 @@ class GraphGP:
         eng.scale_features(fit.phi, 0, D, d['s'], math.sqrt(w), B, D)
         Wt = eng.empty((n, D), torch.float64)
         eng.gemm(False, False, n, D, n, 1.0, d['Linv'], n, B, D, 0.0, Wt, D)
-        G = eng.empty((D, D), torch.float64)
-        eng.gemm(True, False, D, D, n, 1.0, Wt, D, Wt, D, 0.0, G, D)
-        w_mu = eng.empty((D,), torch.float64)
+        # one extra all-zero row/column: the landing slot of labels outside the dictionary
+        G = torch.zeros((D + 1, D + 1), dtype=torch.float64, device=eng.device)
+        eng.gemm(True, False, D, D, n, 1.0, Wt, D, Wt, D, 0.0, G, D + 1)
+        w_mu = torch.zeros((D + 1,), dtype=torch.float64, device=eng.device)
         eng.gemm(True, False, D, 1, n, 1.0, B, D, d['alpha'], 1, 0.0, w_mu, 1)
         # incumbent: y_raw[argmax of the posterior mean at the training points] (acquisitions.py:82-92)
         mu_train = eng.empty((n,), torch.float64)
         eng.gemm(False, False, n, 1, n, 1.0, d['K'], n, d['alpha'], 1, 0.0, mu_train, 1)
         inc_idx = int(np.argmax(mu_train.cpu().numpy()))
-        model, keep = _wl_model(eng, fit, h)
-        model.G, model.ld_g, model.w_mu = G.data_ptr(), D, w_mu.data_ptr()
-        model.lik, model.y_mean, model.y_std = float(self.likelihood), float(self.y_mean), float(self.y_std)
-        d['score'] = dict(model=model, keep=(keep, G, w_mu), incumbent_idx=inc_idx,
-                          incumbent=float(self.y_[inc_idx]))
-        return d['score']
+        pm = PoolModel.from_fit(eng, fit, h)
+        pm.G, pm.w_mu = G, w_mu
+        pm.lik, pm.y_mean, pm.y_std = float(self.likelihood), float(self.y_mean), float(self.y_std)
+        pm.incumbent_idx, pm.incumbent = inc_idx, float(self.y_[inc_idx])
+        d['score'] = pm
+        return pm
+
+    def set_pool_model(self, pm: "PoolModel"):
+        """Install a pool model received from another rank (parallel.broadcast_pool_model)."""
+        from ..engine import Engine
+        self._fitted = True
+        self._dev = dict(eng=Engine.get(), n_max=pm.n_max, score=pm)
+        self.likelihood = pm.lik
 
     def pool_model(self, acq="MEAN", xi=0.0, beta=0.0, incumbent=None):
-        """A copy of the nbw_model descriptor configured for one acquisition."""
-        from ..engine import ACQ
-        st = self._score_state()
-        import ctypes as C
-        m = _lib.Model()
-        C.memmove(C.byref(m), C.byref(st['model']), C.sizeof(m))
-        m.acq = ACQ[acq]
-        m.xi, m.beta = float(xi), float(beta)
-        m.incumbent = float(st['incumbent'] if incumbent is None else incumbent)
-        return m
+        """nbw_model descriptor of the fitted surrogate configured for one acquisition."""
+        return self._score_state().descriptor(acq, xi=xi, beta=beta, incumbent=incumbent)
 
     def upload_pool(self, X):
         """list[nx.DiGraph] | CellBatch | device records -> (device records, n_cells)."""

@@ -159,24 +159,53 @@ score_pool_kernel(const nbw_model M, const uint8_t* __restrict__ cells, int64_t 
       continue;
     }
 
-    // ---- posterior: mean and quadratic form in feature space
+    // ---- posterior: mean and quadratic form in feature space.
+    // Labels outside the dictionary (and absent nodes) are mapped to the all-zero row/column
+    // n_features of G and w_mu, so every gather below is unconditional.
+    const int zero_col = M.n_features;
+    const double* __restrict__ Gp = M.G;
+    const int ldg = M.ld_g;
+    int pcol[NL];
+    const double* grow[NL];
     double mu_acc = 0.0, q_acc = 0.0;
 #pragma unroll
-    for (int l = 0; l < NL; ++l)
-      if (col[l] >= 0) mu_acc += __ldg(M.w_mu + col[l]);
+    for (int l = 0; l < NL; ++l) {
+      pcol[l] = col[l] >= 0 ? col[l] : zero_col;
+      grow[l] = Gp + (int64_t)pcol[l] * ldg;
+      mu_acc += __ldg(M.w_mu + pcol[l]);
+    }
+    {
+      // r = 0: the node with itself; G is symmetric, so off-diagonal level pairs count twice
+      double part[NL];
 #pragma unroll
-    for (int r = 0; r <= NMAX / 2; ++r) {
+      for (int la = 0; la < NL; ++la) part[la] = 0.0;
+#pragma unroll
+      for (int lb = 0; lb < NL; ++lb)
+#pragma unroll
+        for (int la = 0; la <= lb; ++la) {
+          const double g = __ldg(grow[la] + pcol[lb]);
+          part[la] += (la == lb) ? g : 2.0 * g;
+        }
+#pragma unroll
+      for (int la = 0; la < NL; ++la) q_acc += part[la];
+    }
+#pragma unroll
+    for (int r = 1; r <= NMAX / 2; ++r) {
+      // ordered pairs (node, node + r): r < NMAX/2 also stands for (node + r, node)
       const int partner = sub_base + ((node + r) % NMAX);
-      const double weight = (r == 0 || r == NMAX / 2) ? 1.0 : 2.0;
-      double part = 0.0;
+      double part[NL];
+#pragma unroll
+      for (int la = 0; la < NL; ++la) part[la] = 0.0;
 #pragma unroll
       for (int lb = 0; lb < NL; ++lb) {
-        const int pc = __shfl_sync(0xffffffffu, col[lb], partner);
+        const int pc = __shfl_sync(0xffffffffu, pcol[lb], partner);
 #pragma unroll
-        for (int la = 0; la < NL; ++la)
-          if (col[la] >= 0 && pc >= 0) part += __ldg(M.G + (int64_t)col[la] * M.ld_g + pc);
+        for (int la = 0; la < NL; ++la) part[la] += __ldg(grow[la] + pc);
       }
-      q_acc += weight * part;
+      double sum = 0.0;
+#pragma unroll
+      for (int la = 0; la < NL; ++la) sum += part[la];
+      q_acc += (r == NMAX / 2) ? sum : 2.0 * sum;
     }
     mu_acc = subwarp_sum<NMAX>(mu_acc);
     q_acc = subwarp_sum<NMAX>(q_acc);
@@ -249,7 +278,7 @@ int check_model(nbw_ctx* ctx, const nbw_model* M, bool need_posterior) {
   NBW_REQUIRE(ctx, !M->oa || (M->thermo_base && M->max_count), "oa model needs thermo_base/max_count");
   NBW_REQUIRE(ctx, M->n_features > 0, "model.n_features must be positive");
   if (need_posterior) {
-    NBW_REQUIRE(ctx, M->G && M->w_mu && M->ld_g >= M->n_features, "model.G / w_mu missing");
+    NBW_REQUIRE(ctx, M->G && M->w_mu && M->ld_g >= M->n_features + 1, "model.G / w_mu missing or ld_g < n_features + 1");
     NBW_REQUIRE(ctx, M->acq >= NBW_ACQ_EI && M->acq <= NBW_ACQ_MEAN, "unknown acquisition");
   }
   return NBW_OK;

@@ -157,13 +157,12 @@ class WeisfilerLehman(GraphKernels):
         if self._fit is None:
             raise ValueError("The kernel has not been fitted. Call fit_transform first.")
         from ..engine import Engine
-        from ..bayesopt.gp import _wl_model
+        from ..pool_model import PoolModel
         eng = Engine.get()
         batch = self.pack(gr).widen(self._fit.n_max)
-        model, keep = _wl_model(eng, self._fit, self.h)
-        phi, ss = eng.pool_features(model, eng.upload_cells(batch), len(batch))
-        del keep
-        return phi.cpu().numpy()[:, :model.n_features], ss.cpu().numpy()
+        pm = PoolModel.from_fit(eng, self._fit, self.h)
+        phi, ss = eng.pool_features(pm.descriptor(), eng.upload_cells(batch), len(batch))
+        return phi.cpu().numpy()[:, :pm.n_features], ss.cpu().numpy()
 
     def forward_t(self, gr2, gr1=None):
         raise NotImplementedError("kernel gradients (interpretability, gp.py:296-424) are outside the GPU hot path")

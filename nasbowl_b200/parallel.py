@@ -1,0 +1,106 @@
+"""Multi-GPU pool scoring: one process per GPU, torch.distributed (NCCL over NVLink on the GPU
+box, gloo in CPU tests) for the two small exchanges the path has:
+
+  1. the fitted surrogate (PoolModel: dictionaries, G, w_mu, scalars; a few MB) is broadcast
+     once from the rank that fitted it;
+  2. every rank scores its own contiguous shard of the candidate pool — no data-path
+     collective — and the per-rank top-n lists (n x (value, global index)) are all-gathered and
+     merged with the reference's distinct-by-value rule (bayesopt/acquisitions.py:101-105).
+
+Because each candidate is scored by exactly one rank from identical replicated state, scores
+are bitwise independent of the number of ranks.
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .pool_model import PoolModel
+
+
+def init_distributed(backend: Optional[str] = None) -> Tuple[int, int, int]:
+    """Initialise from torchrun's environment; returns (rank, world_size, local_rank)."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous index range [lo, hi) of `rank` ([r*M/R, (r+1)*M/R))."""
+    return (rank * n_items) // world, ((rank + 1) * n_items) // world
+
+
+def merge_topk(vals: np.ndarray, idx: np.ndarray, k: int, distinct: bool = True):
+    """Merge candidate (value, global index) pairs into the global top-k: k largest DISTINCT
+    values, each with the lowest index at which it occurs (np.unique(return_index=True) +
+    argpartition in the reference); distinct=False gives plain top-k with ties by lowest index.
+    Entries with idx < 0 or NaN values are ignored.  Sorted by descending value."""
+    vals = np.asarray(vals, dtype=np.float32).reshape(-1)
+    idx = np.asarray(idx, dtype=np.int64).reshape(-1)
+    ok = (idx >= 0) & ~np.isnan(vals)
+    vals, idx = vals[ok], idx[ok]
+    order = np.lexsort((idx, -vals))                 # value desc, index asc
+    vals, idx = vals[order], idx[order]
+    if distinct and len(vals):
+        keep = np.concatenate([[True], vals[1:] != vals[:-1]])
+        vals, idx = vals[keep], idx[keep]
+    return vals[:k], idx[:k]
+
+
+def allgather_topk(vals: np.ndarray, idx: np.ndarray, k: int, distinct: bool = True, device=None):
+    """All-gather every rank's local top-k list and merge; every rank returns the same result."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return merge_topk(vals, idx, k, distinct)
+    world = dist.get_world_size()
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else "cpu"
+    v = torch.full((k,), float("nan"), dtype=torch.float32)
+    i = torch.full((k,), -1, dtype=torch.int64)
+    v[:len(vals)] = torch.from_numpy(np.asarray(vals, dtype=np.float32))
+    i[:len(idx)] = torch.from_numpy(np.asarray(idx, dtype=np.int64))
+    v, i = v.to(device), i.to(device)
+    gv = [torch.empty_like(v) for _ in range(world)]
+    gi = [torch.empty_like(i) for _ in range(world)]
+    dist.all_gather(gv, v)
+    dist.all_gather(gi, i)
+    return merge_topk(torch.cat(gv).cpu().numpy(), torch.cat(gi).cpu().numpy(), k, distinct)
+
+
+def broadcast_pool_model(pm: Optional[PoolModel], src: int = 0, device=None) -> PoolModel:
+    """Broadcast the fitted surrogate from `src` to every rank (NCCL: over NVLink)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return pm
+    rank = dist.get_rank()
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else "cpu"
+    box = [pm.meta() if rank == src else None]
+    dist.broadcast_object_list(box, src=src)
+    if rank != src:
+        pm = PoolModel.empty_from_meta(box[0], device)
+    for t in pm.tensors():
+        dist.broadcast(t, src=src)
+    return pm
+
+
+def propose_location_sharded(acq, pool_shard, index_base: int, top_n: int = 5, return_distinct: bool = True):
+    """Score this rank's shard (device records) and agree on the global top-n.
+    Returns (top values, global indices, local scores device tensor)."""
+    acq.iters += 1
+    scores, _, _, _ = acq.score_pool(pool_shard)
+    eng = acq.gp._dev['eng']
+    vals, idx = eng.topk(scores, top_n, distinct=bool(return_distinct), index_base=index_base)
+    vals, idx = allgather_topk(vals, idx, top_n, return_distinct)
+    return vals, idx, scores

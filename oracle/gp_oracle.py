@@ -224,8 +224,10 @@ def expected_improvement(mu, var, mu_star: float, xi: float = 0.0, augmented: bo
 
 
 def ucb_beta(iters: int) -> float:
-    """3*sqrt(0.5*log(2*iters+1)) (acquisitions.py:133-135)."""
-    return 3.0 * math.sqrt(0.5 * math.log(2.0 * iters + 1.0))
+    """3*sqrt(0.5*log(2*iters+1)) (acquisitions.py:133-135) — evaluated, like the reference,
+    with fp32 torch scalars."""
+    import torch
+    return float(3. * torch.sqrt(0.5 * torch.log(torch.tensor(2. * iters + 1.))))
 
 
 def upper_confidence_bound(mu, var, beta: float):
