@@ -158,6 +158,18 @@ int nbw_gemm_f64(nbw_ctx* ctx, int trans_a, int trans_b, int64_t m, int64_t n, i
 int nbw_scale_features(nbw_ctx* ctx, const int8_t* phi, int64_t ld_phi, int64_t n, int64_t k0,
                        int64_t k1, const double* s, double sqrt_w, double* B, int64_t ldb,
                        void* stream);
+/* Ancestor map of one WL level: parent[ids_cur[i]] = ids_prev[i] for every counted node i
+ * (all nodes sharing a label share the ancestor, weisfeiler_lehman.py:266-267). */
+int nbw_label_parents(nbw_ctx* ctx, const uint32_t* ids_prev, const uint32_t* ids_cur,
+                      int64_t n_keys, uint32_t* parent, void* stream);
+/* Prefix-summed features over ancestor chains (see nbw_model.H):
+ *   Bp[i, label_off[0] + z]  = B[i, col_off[0] + z]
+ *   Bp[i, label_off[l] + z]  = Bp[i, label_off[l-1] + parent[label_off[l] + z]] + B[i, col_off[l] + z]
+ * B: [n x ldb] fp64 (feature-column layout), Bp: [n x ldp] fp64 (stacked-label layout);
+ * parent: stacked u32 array (entries of level 0 unused); offsets have n_levels + 1 entries. */
+int nbw_prefix_features(nbw_ctx* ctx, const double* B, int64_t ldb, int64_t n, int n_levels,
+                        const int64_t* col_off_h, const int64_t* label_off_h,
+                        const uint32_t* parent, double* Bp, int64_t ldp, void* stream);
 /* cov[i,j] = (sqrt(max(Kss[i,j] + (i==j)*lik - Q[i,j], lik)) * y_std)^2   (gp.py:272-280) */
 int nbw_posterior_cov_finish(nbw_ctx* ctx, const double* Kss, int64_t ldk, const double* Q,
                              int64_t ldq, int64_t m, double lik, double y_std, double* cov,
@@ -197,6 +209,16 @@ typedef struct {
   int32_t ld_g;                          /* >= D + 1 */
   const double* G;                       /* [(D+1) x ld_g]; row D and column D are all zero: the */
   const double* w_mu;                    /* [D+1], w_mu[D] = 0   landing slot of unseen labels */
+  /* Prefix form (oa == 0 only, optional: H == NULL selects the general G path).  A WL label of
+   * level l determines its ancestors at levels < l, and a label can only be in the dictionary if
+   * its ancestor is, so a node is fully described by its DEEPEST dictionary label s (stacked
+   * label index).  H and w_mu_prefix are G and w_mu summed over the ancestor chains:
+   *   H[s, s'] = sum_{a in chain(s), b in chain(s')} G[col(a), col(b)],
+   * which turns phi^T G phi into a sum over node PAIRS instead of (node, level) pairs. */
+  int32_t n_labels;                      /* T = total stacked labels of levels 0..h */
+  int32_t ld_h;                          /* >= T + 1 */
+  const double* H;                       /* [(T+1) x ld_h], row/column T all zero */
+  const double* w_mu_prefix;             /* [T+1], entry T = 0 */
   double lik, y_mean, y_std, incumbent, xi, beta;
 } nbw_model;
 

@@ -49,6 +49,8 @@ class Model(C.Structure):
         ("max_count", C.c_void_p),
         ("n_features", C.c_int32), ("ld_g", C.c_int32),
         ("G", C.c_void_p), ("w_mu", C.c_void_p),
+        ("n_labels", C.c_int32), ("ld_h", C.c_int32),
+        ("H", C.c_void_p), ("w_mu_prefix", C.c_void_p),
         ("lik", C.c_double), ("y_mean", C.c_double), ("y_std", C.c_double),
         ("incumbent", C.c_double), ("xi", C.c_double), ("beta", C.c_double),
     ]
@@ -80,6 +82,9 @@ _PROTOTYPES = {
     "nbw_gemm_f64": (C.c_int, [_vp, _i32, _i32, _i64, _i64, _i64, _f64, _vp, _i64, _vp, _i64, _f64, _vp,
                                _i64, _vp]),
     "nbw_scale_features": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _f64, _vp, _i64, _vp]),
+    "nbw_label_parents": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    "nbw_prefix_features": (C.c_int, [_vp, _vp, _i64, _i64, _i32, C.POINTER(_i64), C.POINTER(_i64), _vp, _vp,
+                                      _i64, _vp]),
     "nbw_posterior_cov_finish": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _f64, _f64, _vp, _i64, _vp]),
     "nbw_model_build_table": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i64, _vp]),
     "nbw_score_pool": (C.c_int, [_vp, C.POINTER(Model), _vp, _i64, _vp, _vp, _vp, _vp, _vp]),

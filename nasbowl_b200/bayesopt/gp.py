@@ -301,6 +301,17 @@ class GraphGP:
         inc_idx = int(np.argmax(mu_train.cpu().numpy()))
         pm = PoolModel.from_fit(eng, fit, h)
         pm.G, pm.w_mu = G, w_mu
+        if not fit.oa:
+            # prefix form (nbw_model.H): the same operators summed over ancestor chains of labels
+            T = fit.label_off[h + 1]
+            Bp = eng.prefix_features(B, fit, h)                       # [n, T+1], last column zero
+            Wp = eng.empty((n, T + 1), torch.float64)
+            eng.gemm(False, False, n, T + 1, n, 1.0, d['Linv'], n, Bp, T + 1, 0.0, Wp, T + 1)
+            H = eng.empty((T + 1, T + 1), torch.float64)
+            eng.gemm(True, False, T + 1, T + 1, n, 1.0, Wp, T + 1, Wp, T + 1, 0.0, H, T + 1)
+            w_mu_p = eng.empty((T + 1,), torch.float64)
+            eng.gemm(True, False, T + 1, 1, n, 1.0, Bp, T + 1, d['alpha'], 1, 0.0, w_mu_p, 1)
+            pm.H, pm.w_mu_prefix = H, w_mu_p
         pm.lik, pm.y_mean, pm.y_std = float(self.likelihood), float(self.y_mean), float(self.y_std)
         pm.incumbent_idx, pm.incumbent = inc_idx, float(self.y_[inc_idx])
         d['score'] = pm

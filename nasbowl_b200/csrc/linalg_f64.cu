@@ -510,3 +510,60 @@ extern "C" int nbw_gp_factor(nbw_ctx* ctx, const double* K, int64_t ldk, int64_t
   if (*info_h != 0) NBW_FAIL(ctx, NBW_ERR_NOT_PD, "matrix not positive definite at pivot %d", *info_h - 1);
   return NBW_OK;
 }
+
+// ====================================================================== prefix form of the pool model
+namespace {
+
+__global__ void label_parents_kernel(const uint32_t* __restrict__ ids_prev, const uint32_t* __restrict__ ids_cur,
+                                     int64_t n_keys, uint32_t* __restrict__ parent) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_keys; i += stride) {
+    const uint32_t c = ids_cur[i];
+    if (c != NBW_INVALID_ID) parent[c] = ids_prev[i];   // every writer of a slot writes the same value
+  }
+}
+
+__global__ void prefix_level_kernel(const double* __restrict__ B, int64_t ldb, int64_t n, int64_t col0,
+                                    int64_t lab0, int64_t lab_prev0, int64_t width,
+                                    const uint32_t* __restrict__ parent, double* Bp, int64_t ldp, int level) {
+  const int64_t total = n * width, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const int64_t i = t / width, z = t % width;
+    double v = B[i * ldb + col0 + z];
+    if (level > 0) v += Bp[i * ldp + lab_prev0 + parent[lab0 + z]];
+    Bp[i * ldp + lab0 + z] = v;
+  }
+}
+
+}  // namespace
+
+extern "C" int nbw_label_parents(nbw_ctx* ctx, const uint32_t* ids_prev, const uint32_t* ids_cur, int64_t n_keys,
+                                 uint32_t* parent, void* stream) {
+  if (!ctx) return NBW_ERR_INVALID;
+  NBW_REQUIRE(ctx, n_keys >= 0, "n_keys negative");
+  if (n_keys == 0) return NBW_OK;
+  NBW_REQUIRE(ctx, ids_prev && ids_cur && parent, "null pointer");
+  label_parents_kernel<<<nbw_grid_for(ctx, n_keys, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      ids_prev, ids_cur, n_keys, parent);
+  NBW_CHECK_LAUNCH(ctx);
+  return NBW_OK;
+}
+
+extern "C" int nbw_prefix_features(nbw_ctx* ctx, const double* B, int64_t ldb, int64_t n, int n_levels,
+                                   const int64_t* col_off_h, const int64_t* label_off_h, const uint32_t* parent,
+                                   double* Bp, int64_t ldp, void* stream) {
+  if (!ctx) return NBW_ERR_INVALID;
+  NBW_REQUIRE(ctx, n_levels >= 1 && n_levels <= NBW_MAX_LEVELS && col_off_h && label_off_h, "bad levels");
+  NBW_REQUIRE(ctx, n >= 0 && ldp >= label_off_h[n_levels] && ldb >= col_off_h[n_levels - 1], "bad shape");
+  if (n == 0) return NBW_OK;
+  NBW_REQUIRE(ctx, B && Bp && (n_levels == 1 || parent), "null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int l = 0; l < n_levels; ++l) {
+    const int64_t width = label_off_h[l + 1] - label_off_h[l];
+    if (width <= 0) continue;
+    prefix_level_kernel<<<nbw_grid_for(ctx, n * width, 256), 256, 0, st>>>(
+        B, ldb, n, col_off_h[l], label_off_h[l], l > 0 ? label_off_h[l - 1] : 0, width, parent, Bp, ldp, l);
+    NBW_CHECK_LAUNCH(ctx);
+  }
+  return NBW_OK;
+}

@@ -87,7 +87,10 @@ __device__ __forceinline__ int effective_column(const nbw_model& M, int l, bool 
   return rank < mc ? M.col_off[l] + (int)__ldg(M.thermo_base + sl) + rank : -1;
 }
 
-template <int NMAX, int NL, bool FEATURES_ONLY>
+// MODE 0: general path (G over (node, level) pairs; required for oa)
+// MODE 1: features only (nbw_pool_features)
+// MODE 2: prefix path (H over node pairs; linear kernel only)
+template <int NMAX, int NL, int MODE>
 __global__ void __launch_bounds__(kScoreThreads)
 score_pool_kernel(const nbw_model M, const uint8_t* __restrict__ cells, int64_t n_cells,
                   float* __restrict__ scores, double* __restrict__ mu64, double* __restrict__ var64,
@@ -110,10 +113,13 @@ score_pool_kernel(const nbw_model M, const uint8_t* __restrict__ cells, int64_t 
     const uint32_t incoming = subwarp_or<NMAX>(succ);
     const bool endpoint = present && (succ != 0u || ((incoming >> node) & 1u));
 
+    constexpr bool FEATURES_ONLY = MODE == 1;
+    constexpr bool PREFIX = MODE == 2;
     int col[NL];
     int cnt[NL];   // class size of the node's label at level l (FEATURES_ONLY / linear self-sim)
     int rk[NL];
     int kss = 0;
+    int deep = M.n_labels;   // PREFIX: stacked index of the deepest dictionary label (zero slot if none)
 
     // ---- level 0: op code -> dense id (weisfeiler_lehman.py:430-441 in transform form)
     uint64_t id64;
@@ -122,7 +128,8 @@ score_pool_kernel(const nbw_model M, const uint8_t* __restrict__ cells, int64_t 
       const bool seen = present && d0 != 0xFFFFu;
       id64 = seen ? (uint64_t)d0 : (NBW_UNSEEN_BIT | (uint64_t)label);
       class_count_rank64<NMAX>(id64, present, node, sub_base, cnt[0], rk[0]);
-      col[0] = effective_column(M, 0, seen, d0, rk[0]);
+      if (PREFIX) { if (seen) deep = M.label_off[0] + (int)d0; }
+      else col[0] = effective_column(M, 0, seen, d0, rk[0]);
       if (present) kss += M.oa ? 1 : cnt[0];
     }
     // ---- levels 1..h
@@ -140,7 +147,8 @@ score_pool_kernel(const nbw_model M, const uint8_t* __restrict__ cells, int64_t 
       if (endpoint) seen = table_probe(static_cast<const uint4*>(M.table[l]), M.table_mask[l], key, (uint32_t)chk, dense);
       id64 = seen ? (uint64_t)dense : (NBW_UNSEEN_BIT | key);
       class_count_rank64<NMAX>(id64, endpoint, node, sub_base, cnt[l], rk[l]);
-      col[l] = endpoint ? effective_column(M, l, seen, dense, rk[l]) : -1;
+      if (PREFIX) { if (endpoint && seen) deep = M.label_off[l] + (int)dense; }
+      else col[l] = endpoint ? effective_column(M, l, seen, dense, rk[l]) : -1;
       if (endpoint) kss += M.oa ? 1 : cnt[l];
     }
     const int kcc_i = subwarp_sum<NMAX>(kss);
@@ -159,6 +167,25 @@ score_pool_kernel(const nbw_model M, const uint8_t* __restrict__ cells, int64_t 
       continue;
     }
 
+    double mu_acc = 0.0, q_acc = 0.0;
+    if (PREFIX) {
+      // ---- posterior, prefix form: one gather per node pair against H (see nbw_model.H)
+      const int zero_slot = M.n_labels;
+      const double* __restrict__ hrow = M.H + (int64_t)deep * M.ld_h;
+      const bool own = deep != zero_slot;
+      if (own) {
+        mu_acc = __ldg(M.w_mu_prefix + deep);
+        q_acc = __ldg(hrow + deep);
+      }
+#pragma unroll
+      for (int r = 1; r <= NMAX / 2; ++r) {
+        const int pd = __shfl_sync(0xffffffffu, deep, sub_base + ((node + r) % NMAX));
+        if (own && pd != zero_slot) {
+          const double g = __ldg(hrow + pd);
+          q_acc += (r == NMAX / 2) ? g : 2.0 * g;
+        }
+      }
+    } else {
     // ---- posterior: mean and quadratic form in feature space.
     // Labels outside the dictionary (and absent nodes) are mapped to the all-zero row/column
     // n_features of G and w_mu, so every gather below is unconditional.
@@ -167,7 +194,6 @@ score_pool_kernel(const nbw_model M, const uint8_t* __restrict__ cells, int64_t 
     const int ldg = M.ld_g;
     int pcol[NL];
     const double* grow[NL];
-    double mu_acc = 0.0, q_acc = 0.0;
 #pragma unroll
     for (int l = 0; l < NL; ++l) {
       pcol[l] = col[l] >= 0 ? col[l] : zero_col;
@@ -207,6 +233,7 @@ score_pool_kernel(const nbw_model M, const uint8_t* __restrict__ cells, int64_t 
       for (int la = 0; la < NL; ++la) sum += part[la];
       q_acc += (r == NMAX / 2) ? sum : 2.0 * sum;
     }
+    }
     mu_acc = subwarp_sum<NMAX>(mu_acc);
     q_acc = subwarp_sum<NMAX>(q_acc);
 
@@ -239,14 +266,14 @@ score_pool_kernel(const nbw_model M, const uint8_t* __restrict__ cells, int64_t 
   }
 }
 
-template <int NMAX, bool FO>
+template <int NMAX, int MODE>
 int launch_levels(nbw_ctx* ctx, const nbw_model& M, const uint8_t* cells, int64_t n, float* scores,
                   double* mu64, double* var64, double* score64, int8_t* phi, int64_t ld_phi,
                   int32_t* self_sim, cudaStream_t st) {
   const int grid = nbw_grid_for(ctx, n, kScoreThreads / NMAX, 16);
 #define NBW_LAUNCH_NL(NLV)                                                                         \
   case NLV:                                                                                         \
-    score_pool_kernel<NMAX, NLV, FO><<<grid, kScoreThreads, 0, st>>>(M, cells, n, scores, mu64, var64, \
+    score_pool_kernel<NMAX, NLV, MODE><<<grid, kScoreThreads, 0, st>>>(M, cells, n, scores, mu64, var64, \
                                                                     score64, phi, ld_phi, self_sim); \
     break;
   switch (M.h + 1) {
@@ -277,10 +304,10 @@ int check_model(nbw_ctx* ctx, const nbw_model* M, bool need_posterior) {
   }
   NBW_REQUIRE(ctx, !M->oa || (M->thermo_base && M->max_count), "oa model needs thermo_base/max_count");
   NBW_REQUIRE(ctx, M->n_features > 0, "model.n_features must be positive");
-  if (need_posterior) {
+  if (need_posterior && !(M->H != nullptr && !M->oa)) {
     NBW_REQUIRE(ctx, M->G && M->w_mu && M->ld_g >= M->n_features + 1, "model.G / w_mu missing or ld_g < n_features + 1");
-    NBW_REQUIRE(ctx, M->acq >= NBW_ACQ_EI && M->acq <= NBW_ACQ_MEAN, "unknown acquisition");
   }
+  if (need_posterior) NBW_REQUIRE(ctx, M->acq >= NBW_ACQ_EI && M->acq <= NBW_ACQ_MEAN, "unknown acquisition");
   return NBW_OK;
 }
 
@@ -313,9 +340,16 @@ extern "C" int nbw_score_pool(nbw_ctx* ctx, const nbw_model* model_h, const void
   NBW_REQUIRE(ctx, cells && scores, "null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const uint8_t* c = static_cast<const uint8_t*>(cells);
-  if (model_h->n_max == 8)
-    return launch_levels<8, false>(ctx, *model_h, c, n_cells, scores, mu64, var64, score64, nullptr, 0, nullptr, st);
-  return launch_levels<16, false>(ctx, *model_h, c, n_cells, scores, mu64, var64, score64, nullptr, 0, nullptr, st);
+  const bool prefix = model_h->H != nullptr && !model_h->oa;
+  if (prefix)
+    NBW_REQUIRE(ctx, model_h->w_mu_prefix && model_h->n_labels > 0 && model_h->ld_h >= model_h->n_labels + 1,
+                "model.H needs w_mu_prefix, n_labels and ld_h >= n_labels + 1");
+  if (model_h->n_max == 8) {
+    if (prefix) return launch_levels<8, 2>(ctx, *model_h, c, n_cells, scores, mu64, var64, score64, nullptr, 0, nullptr, st);
+    return launch_levels<8, 0>(ctx, *model_h, c, n_cells, scores, mu64, var64, score64, nullptr, 0, nullptr, st);
+  }
+  if (prefix) return launch_levels<16, 2>(ctx, *model_h, c, n_cells, scores, mu64, var64, score64, nullptr, 0, nullptr, st);
+  return launch_levels<16, 0>(ctx, *model_h, c, n_cells, scores, mu64, var64, score64, nullptr, 0, nullptr, st);
 }
 
 extern "C" int nbw_pool_features(nbw_ctx* ctx, const nbw_model* model_h, const void* cells, int64_t n_cells,
@@ -330,6 +364,6 @@ extern "C" int nbw_pool_features(nbw_ctx* ctx, const nbw_model* model_h, const v
   NBW_CUDA(ctx, cudaMemsetAsync(phi, 0, (size_t)n_cells * ld_phi, st));
   const uint8_t* c = static_cast<const uint8_t*>(cells);
   if (model_h->n_max == 8)
-    return launch_levels<8, true>(ctx, *model_h, c, n_cells, nullptr, nullptr, nullptr, nullptr, phi, ld_phi, self_sim, st);
-  return launch_levels<16, true>(ctx, *model_h, c, n_cells, nullptr, nullptr, nullptr, nullptr, phi, ld_phi, self_sim, st);
+    return launch_levels<8, 1>(ctx, *model_h, c, n_cells, nullptr, nullptr, nullptr, nullptr, phi, ld_phi, self_sim, st);
+  return launch_levels<16, 1>(ctx, *model_h, c, n_cells, nullptr, nullptr, nullptr, nullptr, phi, ld_phi, self_sim, st);
 }

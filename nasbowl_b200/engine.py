@@ -51,6 +51,7 @@ class WLFit:
     thermo_base: Optional[torch.Tensor] = None   # int32 [total labels] (oa)
     max_count: Optional[torch.Tensor] = None     # uint8 [total labels] (oa)
     op_codes: Optional[np.ndarray] = None        # sorted op codes present (level-0 dictionary)
+    parents: Optional[torch.Tensor] = None       # int32 [total labels]: ancestor (level l-1 id) of each label
 
     @property
     def ld_phi(self) -> int:
@@ -162,6 +163,12 @@ class Engine:
         label_off = [0]
         for d in dims:
             label_off.append(label_off[-1] + d)
+        # ancestor map: the level l-1 label every level-l label refines
+        parents = torch.zeros((max(label_off[-1], 1),), dtype=torch.int32, device=self.device)
+        for l in range(1, h + 1):
+            if dims[l] > 0:
+                self._check(lib.nbw_label_parents(ctx, self._p(ids[l - 1]), self._p(ids[l]), n_keys,
+                                                  self._p(parents[label_off[l]:]), st))
         thermo_base = max_count = None
         widths = list(dims)
         if oa:
@@ -180,7 +187,7 @@ class Engine:
         fit = WLFit(n_cells=n, n_max=n_max, h=h, oa=bool(oa), seed=seed, ids=ids, dims=dims,
                     uniq_keys=ukeys, uniq_chks=uchks, label_off=label_off, widths=widths,
                     col_off=col_off, phi=None, self_sim=None, thermo_base=thermo_base,
-                    max_count=max_count, op_codes=op_codes)
+                    max_count=max_count, op_codes=op_codes, parents=parents)
         if build_features:
             self.build_features(fit)
         return fit
@@ -260,6 +267,18 @@ class Engine:
         n = phi.shape[0]
         self._check(self.lib.nbw_scale_features(self.ctx, self._p(phi), phi.stride(0), n, k0, k1, self._p(s),
                                                 float(sqrt_w), self._p(out), ldo, self.stream))
+
+    def prefix_features(self, B: torch.Tensor, fit: "WLFit", h: int) -> torch.Tensor:
+        """Bp [n, T+1]: features summed over ancestor chains (nbw_prefix_features); the extra
+        last column stays zero."""
+        n = B.shape[0]
+        T = fit.label_off[h + 1]
+        Bp = torch.zeros((n, T + 1), dtype=torch.float64, device=self.device)
+        co = (C.c_int64 * (h + 2))(*fit.col_off[:h + 2])
+        lo = (C.c_int64 * (h + 2))(*fit.label_off[:h + 2])
+        self._check(self.lib.nbw_prefix_features(self.ctx, self._p(B), B.stride(0), n, h + 1, co, lo,
+                                                 self._p(fit.parents), self._p(Bp), Bp.stride(0), self.stream))
+        return Bp
 
     def posterior_cov_finish(self, Kss: torch.Tensor, ldk: int, Q: torch.Tensor, m: int, lik: float,
                              y_std: float) -> torch.Tensor:

@@ -15,7 +15,7 @@ ACQ = {"EI": 0, "AEI": 1, "UCB": 2, "MEAN": 3}
 
 
 class PoolModel:
-    TENSOR_FIELDS = ("level0", "thermo_base", "max_count", "G", "w_mu")
+    TENSOR_FIELDS = ("level0", "thermo_base", "max_count", "G", "w_mu", "H", "w_mu_prefix")
 
     def __init__(self):
         self.n_max = 8
@@ -31,7 +31,11 @@ class PoolModel:
         self.max_count: Optional[torch.Tensor] = None
         self.n_features = 0
         self.G: Optional[torch.Tensor] = None                # fp64 [D, D]
-        self.w_mu: Optional[torch.Tensor] = None             # fp64 [D]
+        self.w_mu: Optional[torch.Tensor] = None             # fp64 [D + 1]
+        self.n_labels = 0
+        self.H: Optional[torch.Tensor] = None                # fp64 [T + 1, T + 1] (linear kernel only)
+        self.w_mu_prefix: Optional[torch.Tensor] = None      # fp64 [T + 1]
+        self.use_prefix = True                               # False forces the general G path
         self.lik = 0.0
         self.y_mean = 0.0
         self.y_std = 1.0
@@ -49,6 +53,7 @@ class PoolModel:
         m.label_off = list(fit.label_off[:h + 2])
         m.thermo_base, m.max_count = fit.thermo_base, fit.max_count
         m.n_features = fit.k_end(h)
+        m.n_labels = fit.label_off[h + 1]
         return m
 
     # ------------------------------------------------------------------ C descriptor
@@ -70,6 +75,9 @@ class PoolModel:
         d.n_features = self.n_features
         if self.G is not None:
             d.G, d.ld_g, d.w_mu = self.G.data_ptr(), self.G.stride(0), self.w_mu.data_ptr()
+        d.n_labels = self.n_labels
+        if self.H is not None and self.use_prefix and not self.oa:
+            d.H, d.ld_h, d.w_mu_prefix = self.H.data_ptr(), self.H.stride(0), self.w_mu_prefix.data_ptr()
         d.lik, d.y_mean, d.y_std = float(self.lik), float(self.y_mean), float(self.y_std)
         d.incumbent = float(self.incumbent if incumbent is None else incumbent)
         d.xi, d.beta = float(xi), float(beta)
@@ -81,6 +89,7 @@ class PoolModel:
                   for f in self.TENSOR_FIELDS}
         return dict(n_max=self.n_max, h=self.h, oa=self.oa, seed=self.seed, masks=list(self.masks),
                     col_off=list(self.col_off), label_off=list(self.label_off), n_features=self.n_features,
+                    n_labels=self.n_labels,
                     lik=self.lik, y_mean=self.y_mean, y_std=self.y_std, incumbent=self.incumbent,
                     incumbent_idx=self.incumbent_idx, shapes=shapes,
                     table_sizes=[0 if t is None else int(t.numel()) for t in self.tables])
@@ -93,7 +102,7 @@ class PoolModel:
     @classmethod
     def empty_from_meta(cls, meta: dict, device) -> "PoolModel":
         m = cls()
-        for k in ("n_max", "h", "oa", "seed", "masks", "col_off", "label_off", "n_features", "lik", "y_mean",
+        for k in ("n_max", "h", "oa", "seed", "masks", "col_off", "label_off", "n_features", "n_labels", "lik", "y_mean",
                   "y_std", "incumbent", "incumbent_idx"):
             setattr(m, k, meta[k])
         for f, sd in meta["shapes"].items():

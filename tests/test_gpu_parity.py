@@ -218,6 +218,16 @@ def test_gp_fit_predict_acquisitions(family, oa, opt):
     mu_d, var_d = gp.predict_diag(pool)
     np.testing.assert_allclose(mu_d.numpy(), mu_o, rtol=RTOL64, atol=1e-9)
     np.testing.assert_allclose(var_d.numpy(), var_o, rtol=RTOL64, atol=1e-12)
+    # the prefix form (H over node pairs, linear kernel) and the general form (G over
+    # (node, level) pairs) are two evaluation orders of the same quadratic form
+    pm = gp._score_state()
+    assert (pm.H is not None) == (not oa)
+    pm.use_prefix = False
+    mu_g, var_g = gp.predict_diag(pool)
+    pm.use_prefix = True
+    np.testing.assert_allclose(mu_g.numpy(), mu_d.numpy(), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(var_g.numpy(), var_d.numpy(), rtol=1e-8, atol=1e-13)
+    np.testing.assert_allclose(var_g.numpy(), var_o, rtol=RTOL64, atol=1e-12)
     mu_f, cov_f = gp.predict(pool)
     mu_fo, cov_fo = gp_oracle.gp_predict_full(st, train, pool)
     np.testing.assert_allclose(mu_f.numpy(), mu_fo, rtol=RTOL64, atol=1e-9)
