@@ -20,22 +20,6 @@ struct HistLevels {
   int64_t label_off[NBW_MAX_LEVELS + 1];
 };
 
-// count = number of lanes of the sub-warp with the same valid id; rank = how many of them
-// sit at lower lanes.
-template <int NMAX>
-__device__ __forceinline__ void class_count_rank(uint32_t id, bool valid, int node, int sub_base,
-                                                 int& count, int& rank) {
-  count = 0;
-  rank = 0;
-#pragma unroll
-  for (int j = 0; j < NMAX; ++j) {
-    const uint32_t other = __shfl_sync(0xffffffffu, id, sub_base + j);
-    const bool same = valid && other == id;   // invalid ids are NBW_INVALID_ID on both sides
-    count += same ? 1 : 0;
-    rank += (same && j < node) ? 1 : 0;
-  }
-}
-
 template <int NMAX>
 __global__ void __launch_bounds__(kHistThreads)
 hist_dense_kernel(const uint32_t* __restrict__ ids, int64_t n_cells, HistLevels lv,
@@ -64,7 +48,7 @@ hist_dense_kernel(const uint32_t* __restrict__ ids, int64_t n_cells, HistLevels 
     const uint32_t id = in_range ? ids[(int64_t)l * n_cells * NMAX + g * NMAX + node] : NBW_INVALID_ID;
     const bool valid = id != NBW_INVALID_ID;
     int count, rank;
-    class_count_rank<NMAX>(id, valid, node, sub_base, count, rank);
+    class_count_rank<NMAX>((uint64_t)id, valid, lane, sub_base, count, rank);
     if (valid) {
       if (!oa) {
         self_acc += count;   // sum over nodes of class size = sum over classes of size^2
@@ -114,7 +98,7 @@ max_count_kernel(const uint32_t* __restrict__ ids, int64_t n_cells, HistLevels l
       const uint32_t id = in_range ? ids[(int64_t)l * n_cells * NMAX + g * NMAX + node] : NBW_INVALID_ID;
       const bool valid = id != NBW_INVALID_ID;
       int count, rank;
-      class_count_rank<NMAX>(id, valid, node, sub_base, count, rank);
+      class_count_rank<NMAX>((uint64_t)id, valid, lane, sub_base, count, rank);
       if (valid && rank == 0) atomicMax(&max_count[lv.label_off[l] + id], (uint32_t)count);
     }
   }

@@ -69,13 +69,17 @@ static inline int nbw_grid_for(const nbw_ctx* ctx, int64_t work_items, int per_b
 
 // ---------------------------------------------------------------------------------------
 // Hashing of WL credentials.
-// A credential is (own id, multiset of successor ids).  Both signatures are of the form
-//   fin( h_own(own) + sum_s h_nbr(id_s) )   (sum mod 2^64: order-independent, so no sort)
-// with independent mixers for key and chk.  Ids are 64-bit: a dense dictionary id (< 2^32)
-// for labels known to the dictionary, or UNSEEN_BIT | key for labels outside it.
+// A credential is (own id, multiset of successor ids).  Every node hashes its id once into a
+// 64-bit value ha and a 32-bit value hb (independent mixers, salted per level); the signature is
+//   key   = fin64( own64(ha_v) + sum_{s in succ(v)} ha_s )      (sums mod 2^64 / 2^32:
+//   chk32 = fin32( own32(hb_v) + sum_{s in succ(v)} hb_s )       order-independent, so no sort)
+// where own64/own32 are cheap bijections (rotate + odd multiply) that keep "v with successor s"
+// apart from "s with successor v".  Ids are 64-bit: a dense dictionary id (< 2^32) for labels
+// known to the dictionary, UNSEEN_BIT | key for labels outside it.  96 signature bits decide
+// pool-side membership; the training-side partition is verified exactly (dict_build.cu).
 // ---------------------------------------------------------------------------------------
 #define NBW_UNSEEN_BIT 0x8000000000000000ull
-#define NBW_OWN_TWEAK 0x5851f42d4c957f2dull
+#define NBW_NOCLASS_BIT 0x4000000000000000ull   // | lane: a class id no other lane can have
 
 __host__ __device__ __forceinline__ uint64_t nbw_mix_a(uint64_t x) {   // splitmix64 finaliser
   x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
@@ -89,24 +93,44 @@ __host__ __device__ __forceinline__ uint64_t nbw_mix_b(uint64_t x) {   // murmur
   x ^= x >> 33;
   return x;
 }
+__host__ __device__ __forceinline__ uint32_t nbw_mix32(uint32_t x) {   // murmur3 fmix32
+  x ^= x >> 16; x *= 0x85ebca6bu;
+  x ^= x >> 13; x *= 0xc2b2ae35u;
+  x ^= x >> 16;
+  return x;
+}
 
 struct LevelSalt {
-  uint64_t a_own, a_nbr, b_own, b_nbr;
+  uint64_t a_nbr, a_own;
+  uint32_t b_nbr, b_own;
 };
 __host__ __device__ __forceinline__ LevelSalt nbw_level_salt(uint64_t seed, int level) {
   uint64_t s = nbw_mix_a(seed + 0x9e3779b97f4a7c15ull * (uint64_t)(level + 1));
   LevelSalt t;
-  t.a_own = nbw_mix_a(s ^ 0x01);
-  t.a_nbr = nbw_mix_a(s ^ 0x02);
-  t.b_own = nbw_mix_b(s ^ 0x03);
-  t.b_nbr = nbw_mix_b(s ^ 0x04);
+  t.a_nbr = nbw_mix_a(s ^ 0x01);
+  t.a_own = nbw_mix_a(s ^ 0x02);
+  const uint64_t b = nbw_mix_b(s ^ 0x03);
+  t.b_nbr = (uint32_t)b;
+  t.b_own = (uint32_t)(b >> 32);
   return t;
 }
-__host__ __device__ __forceinline__ uint64_t nbw_key_finish(uint64_t acc) {
-  uint64_t k = nbw_mix_a(acc);
+// per-node hashes of an id
+__host__ __device__ __forceinline__ uint64_t nbw_hash_a(uint64_t id64, const LevelSalt& s) {
+  return nbw_mix_a(id64 + s.a_nbr);
+}
+__host__ __device__ __forceinline__ uint32_t nbw_hash_b(uint64_t id64, const LevelSalt& s) {
+  return nbw_mix32(((uint32_t)id64 * 0x9e3779b1u) ^ ((uint32_t)(id64 >> 32) * 0x85ebca77u) ^ s.b_nbr);
+}
+// signature from the node's own hashes and the sums over its successors
+__host__ __device__ __forceinline__ uint64_t nbw_key_from(uint64_t ha_own, uint64_t sum_a, const LevelSalt& s) {
+  const uint64_t own = ((ha_own << 27) | (ha_own >> 37)) * 0x9e3779b97f4a7c15ull + s.a_own;
+  const uint64_t k = nbw_mix_a(own + sum_a);
   return k == NBW_INVALID_KEY ? k - 1 : k;
 }
-__host__ __device__ __forceinline__ uint64_t nbw_chk_finish(uint64_t acc) { return nbw_mix_b(acc); }
+__host__ __device__ __forceinline__ uint32_t nbw_chk_from(uint32_t hb_own, uint32_t sum_b, const LevelSalt& s) {
+  const uint32_t own = ((hb_own << 13) | (hb_own >> 19)) * 0xcc9e2d51u + s.b_own;
+  return nbw_mix32(own + sum_b);
+}
 
 // ---------------------------------------------------------------------------------------
 // Cell records: lane `node` of a sub-warp reads its own label and successor mask.
@@ -160,19 +184,36 @@ __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
   return ((uint64_t)hi << 32) | lo;
 }
 
-// Sum over successors of two per-lane 64-bit values (multiset hash accumulation).
+// Sums of the successors' hashes.  Each round every lane fetches ITS next successor (per-lane
+// source lane), so the trip count is the largest out-degree in the warp, not n_max.
 template <int NMAX>
-__device__ __forceinline__ void successor_sums(uint32_t succ, int sub_base, uint64_t va, uint64_t vb,
-                                               uint64_t& sum_a, uint64_t& sum_b) {
+__device__ __forceinline__ void successor_sums(uint32_t succ, int sub_base, int node, uint64_t ha, uint32_t hb,
+                                               uint64_t& sum_a, uint32_t& sum_b) {
   sum_a = 0;
   sum_b = 0;
-#pragma unroll
-  for (int j = 0; j < NMAX; ++j) {
-    uint64_t oa = shfl64(va, sub_base + j);
-    uint64_t ob = shfl64(vb, sub_base + j);
-    if ((succ >> j) & 1u) {
+  uint32_t m = succ;
+#pragma unroll 1
+  for (int t = 0; t < NMAX; ++t) {
+    if (!__any_sync(0xffffffffu, m != 0u)) break;
+    const int j = m ? (__ffs(m) - 1) : node;
+    const uint64_t oa = shfl64(ha, sub_base + j);
+    const uint32_t ob = __shfl_sync(0xffffffffu, hb, sub_base + j);
+    if (m) {
       sum_a += oa;
       sum_b += ob;
+      m &= m - 1u;
     }
   }
+}
+
+// Size of the node's label class inside its cell and its rank in it, from ONE warp match:
+// lanes without a counted label get a class id no other lane can hold.
+template <int NMAX>
+__device__ __forceinline__ void class_count_rank(uint64_t id64, bool valid, int lane, int sub_base,
+                                                 int& count, int& rank) {
+  const unsigned long long cid = valid ? (unsigned long long)id64 : (NBW_NOCLASS_BIT | (unsigned long long)lane);
+  const uint32_t sub_mask = (NMAX == 32 ? 0xffffffffu : ((1u << NMAX) - 1u)) << sub_base;
+  const uint32_t peers = __match_any_sync(0xffffffffu, cid) & sub_mask;
+  count = valid ? __popc(peers) : 0;
+  rank = __popc(peers & ((1u << lane) - 1u));
 }

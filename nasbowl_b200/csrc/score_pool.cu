@@ -63,22 +63,6 @@ __device__ __forceinline__ bool table_probe(const uint4* __restrict__ table, uin
   return false;
 }
 
-// count / rank of a node's 64-bit label within its cell (see histogram.cu)
-template <int NMAX>
-__device__ __forceinline__ void class_count_rank64(uint64_t id, bool valid, int node, int sub_base,
-                                                   int& count, int& rank) {
-  count = 0;
-  rank = 0;
-#pragma unroll
-  for (int j = 0; j < NMAX; ++j) {
-    const uint64_t other = shfl64(id, sub_base + j);
-    const bool ov = __shfl_sync(0xffffffffu, (int)valid, sub_base + j) != 0;
-    const bool same = valid && ov && other == id;
-    count += same ? 1 : 0;
-    rank += (same && j < node) ? 1 : 0;
-  }
-}
-
 __device__ __forceinline__ int effective_column(const nbw_model& M, int l, bool seen, uint32_t dense, int rank) {
   if (!seen) return -1;
   if (!M.oa) return M.col_off[l] + (int)dense;
@@ -87,16 +71,22 @@ __device__ __forceinline__ int effective_column(const nbw_model& M, int l, bool 
   return rank < mc ? M.col_off[l] + (int)__ldg(M.thermo_base + sl) + rank : -1;
 }
 
+struct ScoreParams {
+  nbw_model M;
+  LevelSalt salt[NBW_MAX_LEVELS];   // per-level hash salts, derived from M.seed on the host
+};
+
 // MODE 0: general path (G over (node, level) pairs; required for oa)
 // MODE 1: features only (nbw_pool_features)
 // MODE 2: prefix path (H over node pairs; linear kernel only)
 template <int NMAX, int NL, int MODE>
 __global__ void __launch_bounds__(kScoreThreads)
-score_pool_kernel(const nbw_model M, const uint8_t* __restrict__ cells, int64_t n_cells,
+score_pool_kernel(const ScoreParams P, const uint8_t* __restrict__ cells, int64_t n_cells,
                   float* __restrict__ scores, double* __restrict__ mu64, double* __restrict__ var64,
                   double* __restrict__ score64, int8_t* __restrict__ phi, int64_t ld_phi,
                   int32_t* __restrict__ self_sim) {
   constexpr int GPW = 32 / NMAX;
+  const nbw_model& M = P.M;
   const int lane = threadIdx.x & 31;
   const int node = lane % NMAX;
   const int sub = lane / NMAX;
@@ -127,7 +117,7 @@ score_pool_kernel(const nbw_model M, const uint8_t* __restrict__ cells, int64_t 
       const uint32_t d0 = present ? (uint32_t)__ldg(M.level0_table + label) : 0xFFFFu;
       const bool seen = present && d0 != 0xFFFFu;
       id64 = seen ? (uint64_t)d0 : (NBW_UNSEEN_BIT | (uint64_t)label);
-      class_count_rank64<NMAX>(id64, present, node, sub_base, cnt[0], rk[0]);
+      class_count_rank<NMAX>(id64, present, lane, sub_base, cnt[0], rk[0]);
       if (PREFIX) { if (seen) deep = M.label_off[0] + (int)d0; }
       else col[0] = effective_column(M, 0, seen, d0, rk[0]);
       if (present) kss += M.oa ? 1 : cnt[0];
@@ -135,18 +125,19 @@ score_pool_kernel(const nbw_model M, const uint8_t* __restrict__ cells, int64_t 
     // ---- levels 1..h
 #pragma unroll
     for (int l = 1; l < NL; ++l) {
-      const LevelSalt salt = nbw_level_salt(M.seed, l);
-      const uint64_t a_nbr = nbw_mix_a(id64 + salt.a_nbr);
-      const uint64_t b_nbr = nbw_mix_b(id64 + salt.b_nbr);
-      uint64_t sum_a, sum_b;
-      successor_sums<NMAX>(succ, sub_base, a_nbr, b_nbr, sum_a, sum_b);
-      const uint64_t key = nbw_key_finish(nbw_mix_a((id64 ^ NBW_OWN_TWEAK) + salt.a_own) + sum_a);
-      const uint64_t chk = nbw_chk_finish(nbw_mix_b((id64 ^ NBW_OWN_TWEAK) + salt.b_own) + sum_b);
+      const LevelSalt salt = P.salt[l];
+      const uint64_t ha = nbw_hash_a(id64, salt);
+      const uint32_t hb = nbw_hash_b(id64, salt);
+      uint64_t sum_a;
+      uint32_t sum_b;
+      successor_sums<NMAX>(succ, sub_base, node, ha, hb, sum_a, sum_b);
+      const uint64_t key = nbw_key_from(ha, sum_a, salt);
+      const uint32_t chk = nbw_chk_from(hb, sum_b, salt);
       uint32_t dense = 0;
       bool seen = false;
-      if (endpoint) seen = table_probe(static_cast<const uint4*>(M.table[l]), M.table_mask[l], key, (uint32_t)chk, dense);
+      if (endpoint) seen = table_probe(static_cast<const uint4*>(M.table[l]), M.table_mask[l], key, chk, dense);
       id64 = seen ? (uint64_t)dense : (NBW_UNSEEN_BIT | key);
-      class_count_rank64<NMAX>(id64, endpoint, node, sub_base, cnt[l], rk[l]);
+      class_count_rank<NMAX>(id64, endpoint, lane, sub_base, cnt[l], rk[l]);
       if (PREFIX) { if (endpoint && seen) deep = M.label_off[l] + (int)dense; }
       else col[l] = endpoint ? effective_column(M, l, seen, dense, rk[l]) : -1;
       if (endpoint) kss += M.oa ? 1 : cnt[l];
@@ -271,9 +262,12 @@ int launch_levels(nbw_ctx* ctx, const nbw_model& M, const uint8_t* cells, int64_
                   double* mu64, double* var64, double* score64, int8_t* phi, int64_t ld_phi,
                   int32_t* self_sim, cudaStream_t st) {
   const int grid = nbw_grid_for(ctx, n, kScoreThreads / NMAX, 16);
+  ScoreParams P;
+  P.M = M;
+  for (int l = 0; l < NBW_MAX_LEVELS; ++l) P.salt[l] = nbw_level_salt(M.seed, l);
 #define NBW_LAUNCH_NL(NLV)                                                                         \
   case NLV:                                                                                         \
-    score_pool_kernel<NMAX, NLV, MODE><<<grid, kScoreThreads, 0, st>>>(M, cells, n, scores, mu64, var64, \
+    score_pool_kernel<NMAX, NLV, MODE><<<grid, kScoreThreads, 0, st>>>(P, cells, n, scores, mu64, var64, \
                                                                     score64, phi, ld_phi, self_sim); \
     break;
   switch (M.h + 1) {

@@ -36,14 +36,14 @@ wl_signature_kernel(const uint8_t* __restrict__ cells, int64_t n_cells,
       const bool endpoint = present && (succ != 0u || ((incoming >> node) & 1u));
       const uint32_t idp = in_range ? ids_prev[g * NMAX + node] : NBW_INVALID_ID;
       const uint64_t id64 = idp;
-      const uint64_t a_nbr = nbw_mix_a(id64 + salt.a_nbr);
-      const uint64_t b_nbr = nbw_mix_b(id64 + salt.b_nbr);
-      uint64_t sum_a, sum_b;
-      successor_sums<NMAX>(succ, sub_base, a_nbr, b_nbr, sum_a, sum_b);
+      const uint64_t ha = nbw_hash_a(id64, salt);
+      const uint32_t hb = nbw_hash_b(id64, salt);
+      uint64_t sum_a;
+      uint32_t sum_b;
+      successor_sums<NMAX>(succ, sub_base, node, ha, hb, sum_a, sum_b);
       const bool counted = endpoint && idp != NBW_INVALID_ID;
-      key = counted ? nbw_key_finish(nbw_mix_a((id64 ^ NBW_OWN_TWEAK) + salt.a_own) + sum_a)
-                    : NBW_INVALID_KEY;
-      chk = counted ? nbw_chk_finish(nbw_mix_b((id64 ^ NBW_OWN_TWEAK) + salt.b_own) + sum_b) : 0;
+      key = counted ? nbw_key_from(ha, sum_a, salt) : NBW_INVALID_KEY;
+      chk = counted ? (uint64_t)nbw_chk_from(hb, sum_b, salt) : 0;
     }
     if (in_range) {
       keys[g * NMAX + node] = key;
