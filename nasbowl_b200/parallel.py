@@ -91,7 +91,7 @@ def broadcast_pool_model(pm: Optional[PoolModel], src: int = 0, device=None) -> 
     if rank != src:
         pm = PoolModel.empty_from_meta(box[0], device)
     for t in pm.tensors():
-        dist.broadcast(t, src=src)
+        dist.broadcast(t.view(torch.uint8), src=src)      # raw bytes: every backend moves uint8
     return pm
 
 

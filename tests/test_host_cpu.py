@@ -1,0 +1,284 @@
+"""CPU-only tests: the C-ABI library loads and exports every symbol include/nbw.h declares (no
+compute calls without a GPU), the packed cell format, the synthetic generators against the
+reference's samplers, and the multi-rank host logic (gloo, world_size 2)."""
+import os
+import re
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+from nasbowl_b200 import _lib, synth
+from nasbowl_b200.cells import NO_NODE, CellBatch, OpVocab, pack_networkx
+from oracle import wl_oracle
+
+
+# ---------------------------------------------------------------------------- C-ABI surface
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "nbw.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(nbw_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__
+    __graft_entry__.build()
+    lib = _lib.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(lib, name), name
+    # ... and the ctypes prototypes cover the header exactly
+    assert sorted(_lib.EXPORTED) == declared
+    assert lib.nbw_version() >= 100
+    assert lib.nbw_last_error(None) == b"null context"
+    assert lib.nbw_launch_count(None) == 0
+
+
+def test_model_struct_layout_matches_header():
+    """ctypes mirror of nbw_model: field order from the header, natural alignment."""
+    text = open(os.path.join(ROOT, "include", "nbw.h")).read()
+    body = text[text.index("typedef struct {"):text.index("} nbw_model;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = re.findall(r"\b([a-zA-Z_][a-zA-Z0-9_]*)\s*(?:\[[A-Z_]+\])?\s*[;,]", body)
+    names = [n for n in names if n not in ("NBW_MAX_LEVELS",)]
+    assert names == [f[0] for f in _lib.Model._fields_]
+    assert _lib.Model.G.offset % 8 == 0 and _lib.Model.H.offset % 8 == 0 and _lib.Model.lik.offset % 8 == 0
+
+
+def test_no_cpu_fallback_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("needs a CUDA-less host")
+    from nasbowl_b200.engine import Engine
+    from nasbowl_b200.kernels import WeisfilerLehman
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        Engine.get()
+    z, batch = load_golden("appendix_b")
+    with pytest.raises(RuntimeError):
+        WeisfilerLehman(h=1).fit_transform(batch)
+
+
+# ---------------------------------------------------------------------------- cell records
+def test_pack_roundtrip_and_node_renumbering():
+    import networkx as nx
+    g = nx.DiGraph()
+    for n, op in [(0, "input"), (3, "conv"), (7, "output")]:      # non-contiguous ids (NB201/DARTS)
+        g.add_node(n, op_name=op)
+    g.add_edges_from([(0, 3), (3, 7), (0, 7)])
+    vocab = OpVocab()
+    b = pack_networkx([g], vocab)
+    assert b.n_max == 8 and list(b.labels[0, :3]) == [0, 1, 2] and b.labels[0, 3] == NO_NODE
+    assert list(b.succ[0, :3]) == [0b110, 0b100, 0]
+    assert int(b.n_nodes[0]) == 3 and int(b.n_edges[0]) == 3
+    rec = b.to_records()
+    assert rec.shape == (1, 16)
+    b2 = CellBatch.from_records(rec, 8)
+    assert np.array_equal(b2.labels, b.labels) and np.array_equal(b2.succ, b.succ)
+    w = b.widen(16)
+    assert w.to_records().shape == (1, 48)
+    w2 = CellBatch.from_records(w.to_records(), 16)
+    assert np.array_equal(w2.labels[:, :8], b.labels) and np.array_equal(w2.succ[:, :8], b.succ)
+    u = b.to_undirected()
+    assert list(u.succ[0, :3]) == [0b110, 0b101, 0b011]
+    g2 = b.to_networkx(vocab)[0]
+    assert sorted(g2.edges()) == [(0, 1), (0, 2), (1, 2)]
+    with pytest.raises(ValueError):
+        pack_networkx([nx.path_graph(20, create_using=nx.DiGraph)], vocab, node_label="missing")
+    g.nodes[3].pop("op_name")
+    with pytest.raises(ValueError):
+        pack_networkx([g], vocab)
+    # widening a batch does not change its WL features
+    z, batch = load_golden("nasbench101")
+    assert np.array_equal(wl_oracle.gram_raw(batch, 2), wl_oracle.gram_raw(batch.widen(16), 2))
+
+
+def test_vocab_pickles():
+    import pickle
+    v = OpVocab(["a", "b"])
+    v2 = pickle.loads(pickle.dumps(v))
+    assert v2.names == ["a", "b"] and v2.code("b") == 1 and v2.code("c") == 2
+
+
+# ---------------------------------------------------------------------------- synthetic pools
+
+
+def test_synthetic_generators_are_deterministic_and_well_formed():
+    for fam in (0, 1, 2):
+        a = synth.generate_cells_host(fam, 7, 100, 300)
+        b = synth.generate_cells_host(fam, 7, 100, 300)
+        c = synth.generate_cells_host(fam, 7, 250, 50)
+        assert np.array_equal(a.to_records(), b.to_records())
+        assert np.array_equal(a.to_records()[150:200], c.to_records())       # index-addressable
+        k = a.n_nodes
+        assert k.min() >= 2 and k.max() <= (15 if fam == 2 else 8 if fam == 1 else 7)
+        # successor masks only reference existing nodes, no isolated nodes, first label is an input
+        for i in range(len(a)):
+            present = (1 << int(k[i])) - 1
+            assert all(int(m) & ~present == 0 for m in a.succ[i])
+            inc = 0
+            for m in a.succ[i]:
+                inc |= int(m)
+            assert all(((int(a.succ[i, v]) != 0) or ((inc >> v) & 1)) for v in range(int(k[i])))
+        assert len(synth.FAMILY_OPS[fam]) > int(a.labels[a.labels != NO_NODE].max())
+
+
+def test_synthetic_construction_matches_reference_samplers():
+    """Same choices in -> same cell out, for the reference's own construction code
+    (generate_test_graphs.py prune / create_nasbench201_graph, darts/utils.py darts2graph)."""
+    from oracle.ref_import import load_reference, reference_available
+    if not reference_available():
+        pytest.skip("reference tree not present on this machine")
+    import random
+    import networkx as nx
+    R = load_reference()
+    from darts.cnn.genotypes import Genotype
+    from darts.utils import darts2graph, is_valid_darts
+    rng = random.Random(5)
+
+    def field(c, n):
+        f = (c * 256 + n - 1) // n
+        while (f * n) >> 8 < c:
+            f += 1
+        return f
+
+    def run(gen, x, y):
+        orig = synth.draw
+
+        def fake(seed, idx, attempt, t):
+            if attempt > 0:
+                raise StopIteration
+            return x if t == 0 else y
+        synth.draw = fake
+        try:
+            return gen(0, 0)
+        except StopIteration:
+            return None
+        finally:
+            synth.draw = orig
+    ops201 = ['nor_conv_3x3', 'nor_conv_1x1', 'avg_pool_3x3', 'skip_connect', 'none']
+    for _ in range(400):
+        # NB201
+        choice = [rng.randrange(5) for _ in range(6)]
+        x = sum(field(c, 5) << (8 * i) for i, c in enumerate(choice))
+        g = R.gtg.create_nasbench201_graph([ops201[c] for c in choice])
+        mine = run(synth._nb201_cell, x, 0)
+        if len(g) == 0 or g.number_of_edges() == 0:
+            assert mine is None
+        else:
+            rb = pack_networkx([g], OpVocab(synth.NB201_OPS))
+            assert list(rb.labels[0]) == mine[0][:8] and list(rb.succ[0]) == mine[1][:8]
+        # NB101
+        x = rng.getrandbits(21)
+        ops = [rng.randrange(3) for _ in range(5)]
+        y = sum(field(c, 3) << (8 * i) for i, c in enumerate(ops))
+        adj = np.zeros((7, 7), dtype=np.int8)
+        for e, (r, c) in enumerate(synth._TRIU):
+            adj[r, c] = (x >> e) & 1
+        res = R.gtg.prune(adj, ['input'] + [synth.NB101_OPS[2 + o] for o in ops] + ['output'])
+        mine = run(synth._nb101_cell, x, y)
+        if res is None or not (0 < res[0].sum() <= 9):
+            assert mine is None
+        else:
+            G = nx.from_numpy_array(res[0], create_using=nx.DiGraph)
+            for i, n in enumerate(res[1]):
+                G.nodes[i]['op_name'] = n
+            rb = pack_networkx([G], OpVocab(synth.NB101_OPS))
+            assert list(rb.labels[0]) == mine[0][:8] and list(rb.succ[0]) == mine[1][:8]
+        # DARTS
+        x = y = 0
+        normal = []
+        dops = synth.DARTS_OPS[4:]
+        for i in range(4):
+            a, b = rng.randrange(i + 2), rng.randrange(i + 1)
+            y |= field(a, i + 2) << (16 * i) | field(b, i + 1) << (16 * i + 8)
+            o0, o1 = rng.randrange(7), rng.randrange(7)
+            x |= field(o0, 7) << (16 * i) | field(o1, 7) << (16 * i + 8)
+            normal += [(dops[o0], a), (dops[o1], b + 1 if b >= a else b)]
+        gt = Genotype(normal=normal, normal_concat=range(2, 6), reduce=normal, reduce_concat=range(2, 6))
+        mine = run(synth._darts_cell, x, y)
+        if not is_valid_darts(gt):
+            assert mine is None
+        else:
+            rb = pack_networkx([darts2graph(gt)[0]], OpVocab(synth.DARTS_OPS), n_max=16)
+            assert list(rb.labels[0]) == mine[0] and list(rb.succ[0]) == mine[1]
+
+
+# ---------------------------------------------------------------------------- multi-rank host logic
+def test_merge_topk_matches_reference_rule():
+    from nasbowl_b200 import parallel
+    from oracle import gp_oracle
+    rng = np.random.RandomState(0)
+    s = np.round(rng.randn(5000), 1).astype(np.float32)
+    s[::97] = np.nan
+    for world in (1, 2, 3, 8):
+        vals, idx = [], []
+        for r in range(world):
+            lo, hi = parallel.shard_range(len(s), r, world)
+            v, i = parallel.merge_topk(s[lo:hi], np.arange(lo, hi), 5, True)     # local distinct top-5
+            vals.append(v)
+            idx.append(i)
+        v, i = parallel.merge_topk(np.concatenate(vals), np.concatenate(idx), 5, True)
+        ok = ~np.isnan(s)
+        ref = gp_oracle.top_n_distinct(np.where(ok, s, -np.inf), 5)
+        assert list(i) == list(ref) and np.array_equal(v, s[ref])
+    assert parallel.shard_range(10, 0, 3) == (0, 3) and parallel.shard_range(10, 2, 3) == (6, 10)
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, %r)
+import numpy as np, torch, torch.distributed as dist
+from nasbowl_b200 import parallel
+from nasbowl_b200.pool_model import PoolModel
+rank, world, _ = parallel.init_distributed("gloo")
+# 1. pool-model broadcast
+pm = None
+if rank == 0:
+    pm = PoolModel()
+    pm.n_max, pm.h, pm.oa, pm.seed = 8, 2, False, 77
+    pm.level0 = torch.arange(256, dtype=torch.int16)
+    pm.tables = [None, torch.full((64,), 3, dtype=torch.uint8), torch.full((128,), 5, dtype=torch.uint8)]
+    pm.masks, pm.col_off, pm.label_off = [0, 3, 7], [0, 128, 256, 384], [0, 5, 20, 60]
+    pm.n_features, pm.n_labels = 384, 60
+    pm.G = torch.arange(385 * 385, dtype=torch.float64).reshape(385, 385)
+    pm.w_mu = torch.ones(385, dtype=torch.float64)
+    pm.H = torch.full((61, 61), 2.5, dtype=torch.float64)
+    pm.w_mu_prefix = torch.zeros(61, dtype=torch.float64)
+    pm.lik, pm.y_mean, pm.y_std, pm.incumbent, pm.incumbent_idx = 0.01, 0.5, 2.0, 1.25, 9
+pm = parallel.broadcast_pool_model(pm, src=0, device="cpu")
+assert pm.h == 2 and pm.seed == 77 and pm.masks == [0, 3, 7] and pm.incumbent == 1.25
+assert pm.tables[0] is None and int(pm.tables[2].sum()) == 5 * 128 and float(pm.G[384, 384]) == 385 * 385 - 1
+assert float(pm.H.sum()) == 2.5 * 61 * 61 and pm.level0[255] == 255
+# 2. sharded top-k agrees on every rank with the single-rank answer
+rng = np.random.RandomState(3)
+s = np.round(rng.randn(4001), 1).astype(np.float32)
+lo, hi = parallel.shard_range(len(s), rank, world)
+v, i = parallel.merge_topk(s[lo:hi], np.arange(lo, hi), 5, True)
+gv, gi = parallel.allgather_topk(v, i, 5, True, device="cpu")
+rv, ri = parallel.merge_topk(s, np.arange(len(s)), 5, True)
+assert list(gi) == list(ri) and np.array_equal(gv, rv), (gi, ri)
+dist.barrier()
+print("rank", rank, "ok")
+"""
+
+
+def test_two_rank_gloo_broadcast_and_topk(tmp_path):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER % ROOT)
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port), CUDA_VISIBLE_DEVICES="")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+    assert "rank 0 ok" in outs[0] and "rank 1 ok" in outs[1]
