@@ -246,11 +246,13 @@ def run_b200(args):
         scores, _, _, _ = eng.score_pool(model, cells, M, scores=score_buf)
         if ev is not None:
             ev[1].record()
-        vals, idx = eng.topk(scores, TOP_N, distinct=True, index_base=first)
-        return parallel.allgather_topk(vals, idx, TOP_N, True)
+        local = eng.topk_device(scores, TOP_N, distinct=True, index_base=first, out=cand_buf)
+        return parallel.allgather_topk_device(eng, local, TOP_N, True, gathered=gather_buf)
 
     model = acq._model()
     score_buf = eng.empty((M,), torch.float32)
+    cand_buf = eng.empty((TOP_N * 16,), torch.uint8)
+    gather_buf = eng.empty((world * TOP_N * 16,), torch.uint8)
     for i in range(args.warmup):
         step(i)
     if world > 1:

@@ -248,6 +248,16 @@ int nbw_topk(nbw_ctx* ctx, const float* scores, int64_t n, int k, int distinct,
              int64_t index_base, float* top_val_h, int64_t* top_idx_h, int* n_found_h,
              void* stream);
 
+/* The same selection with the result left on the device (no sync): out_cands[k] 16-byte entries
+ * {f32 value; i32 pad; i64 index}, index -1 = empty.  This is what each rank contributes to the
+ * top-n all-gather. */
+int nbw_topk_device(nbw_ctx* ctx, const float* scores, int64_t n, int k, int distinct,
+                    int64_t index_base, void* out_cands, void* stream);
+/* Merge `count` such entries (e.g. the all-gathered lists of every rank) into the global top k:
+ * same distinct-by-value rule, ties to the lowest index.  Syncs. */
+int nbw_topk_merge(nbw_ctx* ctx, const void* cands, int64_t count, int k, int distinct,
+                   float* top_val_h, int64_t* top_idx_h, int* n_found_h, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Synthetic pools shaped like the reference's samplers, generated on device
  * (bayesopt/generate_test_graphs.py:543-641; darts/darts_objectives.py:159-198 +

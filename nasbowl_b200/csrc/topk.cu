@@ -111,17 +111,11 @@ topk_round_kernel(const float* __restrict__ scores, const Cand* __restrict__ can
 
 }  // namespace
 
-extern "C" int nbw_topk(nbw_ctx* ctx, const float* scores, int64_t n, int k, int distinct, int64_t index_base,
-                        float* top_val_h, int64_t* top_idx_h, int* n_found_h, void* stream) {
-  if (!ctx) return NBW_ERR_INVALID;
-  NBW_REQUIRE(ctx, k >= 1 && k <= 1024, "k must be in [1, 1024]");
-  NBW_REQUIRE(ctx, n >= 0 && top_val_h && top_idx_h && n_found_h, "bad argument");
-  *n_found_h = 0;
-  if (n == 0) return NBW_OK;
-  NBW_REQUIRE(ctx, scores != nullptr, "scores is NULL");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+// Tournament over `n` scores (or, when scores == NULL, over `n` candidates in `cands`); the
+// final k-entry list ends up in *result (scratch memory, valid until the next scratch user).
+static int topk_enqueue(nbw_ctx* ctx, const float* scores, const Cand* cands, int64_t n, int k, int distinct,
+                        int64_t index_base, Cand** result, cudaStream_t st) {
   int64_t blocks = (n + kTopChunk - 1) / kTopChunk;
-  // two ping-pong candidate lists
   const size_t list0 = (size_t)blocks * k;
   const size_t blocks1 = (list0 + kTopChunk - 1) / kTopChunk;
   const size_t list1 = blocks1 * (size_t)k;
@@ -129,7 +123,10 @@ extern "C" int nbw_topk(nbw_ctx* ctx, const float* scores, int64_t n, int k, int
   if (rc) return rc;
   Carver cv(ctx->scratch);
   Cand* buf[2] = {cv.take<Cand>(list0), cv.take<Cand>(list1)};
-  topk_round_kernel<false><<<(unsigned)blocks, kTopThreads, 0, st>>>(scores, nullptr, n, k, distinct, index_base, buf[0]);
+  if (scores)
+    topk_round_kernel<false><<<(unsigned)blocks, kTopThreads, 0, st>>>(scores, nullptr, n, k, distinct, index_base, buf[0]);
+  else
+    topk_round_kernel<true><<<(unsigned)blocks, kTopThreads, 0, st>>>(nullptr, cands, n, k, distinct, 0, buf[0]);
   NBW_CHECK_LAUNCH(ctx);
   int cur = 0;
   int64_t count = blocks * k;
@@ -141,9 +138,15 @@ extern "C" int nbw_topk(nbw_ctx* ctx, const float* scores, int64_t n, int k, int
     blocks = nb;
     count = nb * k;
   }
+  *result = buf[cur];
+  return NBW_OK;
+}
+
+static int topk_readback(nbw_ctx* ctx, const Cand* dev, int k, float* top_val_h, int64_t* top_idx_h, int* n_found_h,
+                         cudaStream_t st) {
   Cand* host = static_cast<Cand*>(malloc(sizeof(Cand) * k));
   if (!host) NBW_FAIL(ctx, NBW_ERR_INVALID, "host allocation failed");
-  cudaError_t e = cudaMemcpyAsync(host, buf[cur], sizeof(Cand) * k, cudaMemcpyDeviceToHost, st);
+  cudaError_t e = cudaMemcpyAsync(host, dev, sizeof(Cand) * k, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) {
     free(host);
@@ -159,4 +162,52 @@ extern "C" int nbw_topk(nbw_ctx* ctx, const float* scores, int64_t n, int k, int
   free(host);
   *n_found_h = found;
   return NBW_OK;
+}
+
+extern "C" int nbw_topk(nbw_ctx* ctx, const float* scores, int64_t n, int k, int distinct, int64_t index_base,
+                        float* top_val_h, int64_t* top_idx_h, int* n_found_h, void* stream) {
+  if (!ctx) return NBW_ERR_INVALID;
+  NBW_REQUIRE(ctx, k >= 1 && k <= 1024, "k must be in [1, 1024]");
+  NBW_REQUIRE(ctx, n >= 0 && top_val_h && top_idx_h && n_found_h, "bad argument");
+  *n_found_h = 0;
+  if (n == 0) return NBW_OK;
+  NBW_REQUIRE(ctx, scores != nullptr, "scores is NULL");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Cand* res = nullptr;
+  int rc = topk_enqueue(ctx, scores, nullptr, n, k, distinct, index_base, &res, st);
+  if (rc) return rc;
+  return topk_readback(ctx, res, k, top_val_h, top_idx_h, n_found_h, st);
+}
+
+extern "C" int nbw_topk_device(nbw_ctx* ctx, const float* scores, int64_t n, int k, int distinct,
+                               int64_t index_base, void* out_cands, void* stream) {
+  if (!ctx) return NBW_ERR_INVALID;
+  NBW_REQUIRE(ctx, k >= 1 && k <= 1024, "k must be in [1, 1024]");
+  NBW_REQUIRE(ctx, n >= 0 && out_cands, "bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n == 0) {   // an empty shard contributes k empty entries (index -1)
+    NBW_CUDA(ctx, cudaMemsetAsync(out_cands, 0xFF, sizeof(Cand) * k, st));
+    return NBW_OK;
+  }
+  NBW_REQUIRE(ctx, scores != nullptr, "scores is NULL");
+  Cand* res = nullptr;
+  int rc = topk_enqueue(ctx, scores, nullptr, n, k, distinct, index_base, &res, st);
+  if (rc) return rc;
+  NBW_CUDA(ctx, cudaMemcpyAsync(out_cands, res, sizeof(Cand) * k, cudaMemcpyDeviceToDevice, st));
+  return NBW_OK;
+}
+
+extern "C" int nbw_topk_merge(nbw_ctx* ctx, const void* cands, int64_t count, int k, int distinct,
+                              float* top_val_h, int64_t* top_idx_h, int* n_found_h, void* stream) {
+  if (!ctx) return NBW_ERR_INVALID;
+  NBW_REQUIRE(ctx, k >= 1 && k <= 1024, "k must be in [1, 1024]");
+  NBW_REQUIRE(ctx, count >= 0 && top_val_h && top_idx_h && n_found_h, "bad argument");
+  *n_found_h = 0;
+  if (count == 0) return NBW_OK;
+  NBW_REQUIRE(ctx, cands != nullptr, "cands is NULL");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Cand* res = nullptr;
+  int rc = topk_enqueue(ctx, nullptr, static_cast<const Cand*>(cands), count, k, distinct, 0, &res, st);
+  if (rc) return rc;
+  return topk_readback(ctx, res, k, top_val_h, top_idx_h, n_found_h, st);
 }

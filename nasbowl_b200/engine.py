@@ -339,6 +339,25 @@ class Engine:
         f = found.value
         return np.array(vals[:f], dtype=np.float32), np.array(idx[:f], dtype=np.int64)
 
+    def topk_device(self, scores: torch.Tensor, k: int, distinct: bool = True, index_base: int = 0,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Local top-k left on the device: uint8 [k * 16] ({f32 value, i32 pad, i64 index} entries)."""
+        if out is None:
+            out = self.empty((k * 16,), torch.uint8)
+        self._check(self.lib.nbw_topk_device(self.ctx, self._p(scores), scores.numel(), k, int(distinct),
+                                             index_base, self._p(out), self.stream))
+        return out
+
+    def topk_merge(self, cands: torch.Tensor, k: int, distinct: bool = True):
+        count = cands.numel() // 16
+        vals = (C.c_float * k)()
+        idx = (C.c_int64 * k)()
+        found = C.c_int(0)
+        self._check(self.lib.nbw_topk_merge(self.ctx, self._p(cands), count, k, int(distinct), vals, idx,
+                                            C.byref(found), self.stream))
+        f = found.value
+        return np.array(vals[:f], dtype=np.float32), np.array(idx[:f], dtype=np.int64)
+
     def generate_cells(self, family: int, seed: int, first_index: int, n_cells: int) -> torch.Tensor:
         stride = 48 if family == 2 else 16
         cells = self.empty((n_cells, stride), torch.uint8)

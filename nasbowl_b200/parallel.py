@@ -34,7 +34,10 @@ def init_distributed(backend: Optional[str] = None) -> Tuple[int, int, int]:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
             torch.cuda.set_device(local)
-        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+            dist.init_process_group(backend=backend, rank=rank, world_size=world,
+                                    device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend=backend, rank=rank, world_size=world)
     return rank, world, local
 
 
@@ -79,6 +82,19 @@ def allgather_topk(vals: np.ndarray, idx: np.ndarray, k: int, distinct: bool = T
     return merge_topk(torch.cat(gv).cpu().numpy(), torch.cat(gi).cpu().numpy(), k, distinct)
 
 
+def allgather_topk_device(eng, local_cands: torch.Tensor, k: int, distinct: bool = True,
+                          gathered: Optional[torch.Tensor] = None):
+    """Device-resident variant used on the GPU path: one all-gather of k 16-byte entries per rank
+    (NCCL over NVLink), merged by the same tournament kernel; a single host sync per pool."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return eng.topk_merge(local_cands, k, distinct)
+    world = dist.get_world_size()
+    if gathered is None:
+        gathered = torch.empty((world * local_cands.numel(),), dtype=torch.uint8, device=local_cands.device)
+    dist.all_gather_into_tensor(gathered, local_cands)
+    return eng.topk_merge(gathered, k, distinct)
+
+
 def broadcast_pool_model(pm: Optional[PoolModel], src: int = 0, device=None) -> PoolModel:
     """Broadcast the fitted surrogate from `src` to every rank (NCCL: over NVLink)."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
@@ -101,6 +117,6 @@ def propose_location_sharded(acq, pool_shard, index_base: int, top_n: int = 5, r
     acq.iters += 1
     scores, _, _, _ = acq.score_pool(pool_shard)
     eng = acq.gp._dev['eng']
-    vals, idx = eng.topk(scores, top_n, distinct=bool(return_distinct), index_base=index_base)
-    vals, idx = allgather_topk(vals, idx, top_n, return_distinct)
+    local = eng.topk_device(scores, top_n, distinct=bool(return_distinct), index_base=index_base)
+    vals, idx = allgather_topk_device(eng, local, top_n, return_distinct)
     return vals, idx, scores

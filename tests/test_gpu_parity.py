@@ -435,3 +435,25 @@ def test_million_candidate_pool_properties(eng):
     # (4) top-5 distinct agrees with numpy on the full score vector
     _, _, idx = acq.propose_location(pool, top_n=5)
     assert set(int(i) for i in idx) == set(int(i) for i in gp_oracle.top_n_distinct(s, 5))
+
+
+def test_sharded_topk_device_merge_equals_global(eng):
+    """The multi-GPU selection path on one GPU: per-shard device top-k lists, concatenated the
+    way the all-gather delivers them, merged by nbw_topk_merge == top-k of the whole pool."""
+    from nasbowl_b200 import parallel
+    rng = np.random.RandomState(11)
+    s = np.round(rng.randn(300_000), 2).astype(np.float32)
+    s[::1013] = np.nan
+    d = torch.from_numpy(s).cuda()
+    for distinct in (True, False):
+        ref_v, ref_i = eng.topk(d, 5, distinct=distinct)
+        for world in (1, 2, 3, 8):
+            parts = []
+            for r in range(world):
+                lo, hi = parallel.shard_range(len(s), r, world)
+                parts.append(eng.topk_device(d[lo:hi], 5, distinct=distinct, index_base=lo).clone())
+            parts.append(eng.topk_device(d[:0], 5, distinct=distinct))          # an empty shard
+            v, i = eng.topk_merge(torch.cat(parts), 5, distinct=distinct)
+            assert np.array_equal(i, ref_i) and np.array_equal(v, ref_v)
+            hv, hi_ = parallel.merge_topk(s, np.arange(len(s)), 5, distinct)     # host restatement
+            assert np.array_equal(i, hi_) and np.array_equal(v, hv)
