@@ -307,6 +307,13 @@ def run_b200(args):
     if rank != 0:
         return
     peak, peak_src = load_peaks()
+    traffic = None
+    try:       # DRAM bytes per launch from the committed ncu capture of the same kernel / pool size
+        tr = json.load(open(os.path.join(ROOT, "profiles", "score_traffic.json")))
+        if tr["pool"] == M and tr["h"] == h_star:
+            traffic = tr["traffic_bytes_per_launch"]
+    except Exception:
+        pass
     value = world * M * args.steps / (elapsed_ms / 1e3)
     achieved = SURVEY_BYTES_PER_CANDIDATE * M / (kernel_ms / 1e3) / 1e9
     line = {
@@ -319,7 +326,7 @@ def run_b200(args):
                    "l2": "inputs larger than L2: %d rotating pools x %.0f MB per GPU" % (ROTATING_POOLS, M * 16 / 1e6),
                    "fit_ms": fit_ms, "broadcast_ms": bcast_ms, "model_bytes": pm.nbytes()},
         "roofline": {"bound": "hbm", "kernel": "score_pool_kernel", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "kernel_ms": kernel_ms, "bytes_per_unit": SURVEY_BYTES_PER_CANDIDATE,
                      "layout_bytes_per_unit": LAYOUT_BYTES_PER_CANDIDATE,
                      "kernel_share_of_step": kernel_ms / (elapsed_ms / args.steps)},
