@@ -36,6 +36,7 @@ SURVEY_BYTES_PER_CANDIDATE = 36  # 32 B padded CSR record in +
 LAYOUT_BYTES_PER_CANDIDATE = 20  # this build: 16 B bit-CSR record in + 4 B EI out
 ROTATING_POOLS = 16
 METRIC = "candidate archs scored/sec (WL + GP posterior + EI + top-5)"
+WORKLOAD_DESC = ""
 
 
 def load_peaks():
@@ -159,12 +160,12 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = S * args.steps / dt
     threads = blas_threads()
-    sample_desc = "%d NB201-shaped candidates per step (of the 1M-candidate pool), n_train=%d, h*=%d" % (S, N_TRAIN, st.h)
+    sample_desc = "%d candidates per step (of the pool), n_train=%d, h*=%d" % (S, N_TRAIN, st.h)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "candidates/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "NB201-shaped cells, n_train=150, h in {0..5} by marginal likelihood, EI pool scoring",
+        "config": {"workload": WORKLOAD_DESC + ", EI pool scoring",
                    "h_star": st.h, "sample_per_step": S, "host": "CPU only"},
         "cpu_baseline": {"value": value, "unit": "candidates/s", "cores": threads, "kind": "port", "sample": sample_desc},
         "e2e": {"value": value, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -190,6 +191,7 @@ def run_b200(args):
         sampler.start()
     M = args.pool
     train, y = make_training_set()
+    n_max, stride = train.n_max, (48 if train.n_max == 16 else 16)
 
     # ---- fit on rank 0, broadcast the pool model
     gp = GraphGP(train, y, [WeisfilerLehman(h=2)])
@@ -230,7 +232,7 @@ def run_b200(args):
     cpu_baseline, parity = None, None
     if rank == 0 and world == 1 and not args.skip_cpu:
         S = args.cpu_sample
-        sample = CellBatch.from_records(pools[0][0][:S].cpu().numpy(), 8)
+        sample = CellBatch.from_records(pools[0][0][:S].cpu().numpy(), n_max)
         rate, st, ei_ref, top_ref = cpu_port_rate(train, y, sample)
         sc, _, _, sc64 = acq.score_pool(pools[0][0][:S].contiguous(), want64=True)
         err = float(np.max(np.abs(sc64.cpu().numpy() - ei_ref) / (np.abs(ei_ref) + 1e-12)))
@@ -276,9 +278,9 @@ def run_b200(args):
     kernel_ms = sum(a.elapsed_time(b) for a, b in kernel_events) / args.steps
 
     # ---- end to end through the public API with HOST buffers (pinned): H2D pool, score, top-5, D2H scores
-    host_pool = torch.empty((M, 16), dtype=torch.uint8).pin_memory()
+    host_pool = torch.empty((M, stride), dtype=torch.uint8).pin_memory()
     host_pool.copy_(pools[0][0].cpu())
-    dev_pool = eng.empty((M, 16), torch.uint8)
+    dev_pool = eng.empty((M, stride), torch.uint8)
 
     def e2e_step():
         dev_pool.copy_(host_pool, non_blocking=True)
@@ -310,7 +312,7 @@ def run_b200(args):
     traffic = None
     try:       # DRAM bytes per launch from the committed ncu capture of the same kernel / pool size
         tr = json.load(open(os.path.join(ROOT, "profiles", "score_traffic.json")))
-        if tr["pool"] == M and tr["h"] == h_star:
+        if tr["pool"] == M and tr["h"] == h_star and args.workload == "cfg2":
             traffic = tr["traffic_bytes_per_launch"]
     except Exception:
         pass
@@ -320,19 +322,18 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": "candidates/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "NB201-shaped cells (8 nodes, 5 ops), n_train=150, h in {0..5} by marginal "
-                               "likelihood, %d-candidate EI pool per GPU, top-5" % M,
+        "config": {"workload": WORKLOAD_DESC + ", %d-candidate EI pool per GPU, top-5" % M,
                    "h_star": h_star, "n_features": pm.n_features, "pool_per_gpu": M,
-                   "l2": "inputs larger than L2: %d rotating pools x %.0f MB per GPU" % (ROTATING_POOLS, M * 16 / 1e6),
+                   "l2": "inputs larger than L2: %d rotating pools x %.0f MB per GPU" % (ROTATING_POOLS, M * stride / 1e6),
                    "fit_ms": fit_ms, "broadcast_ms": bcast_ms, "model_bytes": pm.nbytes()},
-        "roofline": {"bound": "hbm", "kernel": "score_pool_kernel", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": "score_pool_kernel<%d,%d,prefix>" % (n_max, h_star + 1), "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "kernel_ms": kernel_ms, "bytes_per_unit": SURVEY_BYTES_PER_CANDIDATE,
                      "layout_bytes_per_unit": LAYOUT_BYTES_PER_CANDIDATE,
                      "kernel_share_of_step": kernel_ms / (elapsed_ms / args.steps)},
         "cpu_baseline": cpu_baseline,
         "e2e": {"value": world * M * e_steps / (e2e_ms / 1e3), "unit": "candidates/s",
-                "h2d_bytes_per_step": M * 16, "d2h_bytes_per_step": M * 4 + TOP_N * 12, "steps": e_steps,
+                "h2d_bytes_per_step": M * stride, "d2h_bytes_per_step": M * 4 + TOP_N * 12, "steps": e_steps,
                 "api": "GraphExpectedImprovement.propose_location on pinned host records"},
         "gpu_launches": launches,
         "clocks": clocks,
@@ -341,17 +342,39 @@ def run_b200(args):
     print(json.dumps(line))
 
 
+WORKLOADS = {
+    # BASELINE.json configs[1] (the headline), configs[2] and configs[3] per-GPU shards
+    "cfg2": dict(family=1, n_train=150, h_grid=tuple(range(6)), pool=1_000_000, bytes=36,
+                 desc="NB201-shaped cells (8 nodes, 5 ops), n_train=150, h in {0..5} by marginal likelihood"),
+    "cfg3": dict(family=0, n_train=500, h_grid=(2,), pool=1_250_000, bytes=36,
+                 desc="NB101-shaped cells (<=7 nodes, 5 ops), n_train=500, WL h=2 (1/8 of the 10M pool per GPU)"),
+    "cfg4": dict(family=2, n_train=1000, h_grid=(2,), pool=1_250_000, bytes=68,
+                 desc="DARTS-shaped cells (<=15 nodes, 11 ops), n_train=1000, WL h=2 (1/8 of the 10M pool per GPU)"),
+}
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--pool", type=int, default=1_000_000)
-    ap.add_argument("--cpu-sample", type=int, default=16000)
+    ap.add_argument("--pool", type=int, default=None)
+    ap.add_argument("--cpu-sample", type=int, default=None)
     ap.add_argument("--ref-sample", type=int, default=1000)
     ap.add_argument("--skip-cpu", action="store_true")
     args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    g = globals()
+    g["FAMILY"], g["N_TRAIN"], g["H_GRID"] = w["family"], w["n_train"], w["h_grid"]
+    g["SURVEY_BYTES_PER_CANDIDATE"] = w["bytes"]
+    g["LAYOUT_BYTES_PER_CANDIDATE"] = (48 if w["family"] == 2 else 16) + 4
+    g["WORKLOAD_DESC"] = w["desc"]
+    if args.pool is None:
+        args.pool = w["pool"]
+    if args.cpu_sample is None:
+        args.cpu_sample = {"cfg2": 16000, "cfg3": 8000, "cfg4": 4000}[args.workload]
     if args.impl == "reference":
         run_reference(args)
     else:
