@@ -84,13 +84,21 @@ class GraphExpectedImprovement(BaseAcquisition):
     def propose_location(self, candidates, top_n=5, return_distinct=True):
         """top_n: return the top n candidates wrt the acquisition function (acquisitions.py:94-113)."""
         self.iters += 1
-        scores, _, _, _ = self.score_pool(candidates)
         eng = self.gp._dev['eng']
-        vals, indices = eng.topk(scores, top_n, distinct=bool(return_distinct))
+        host_scores = None
+        if isinstance(candidates, torch.Tensor) and not candidates.is_cuda:
+            # packed records in host memory: H2D, kernel and D2H of the scores are pipelined
+            scores, host_scores = eng.score_host_pool(self._model(), candidates)
+        else:
+            scores, _, _, _ = self.score_pool(candidates)
+        vals, indices = eng.topk(scores, top_n, distinct=bool(return_distinct))      # syncs
         if return_distinct and len(indices) < top_n:
             # fewer than top_n distinct values: the reference falls back to plain top-k (:106-108)
             vals, indices = eng.topk(scores, top_n, distinct=False)
-        eis = scores.cpu().numpy().reshape(-1, 1)
+        if host_scores is not None:
+            eis = host_scores.numpy().reshape(-1, 1).copy()
+        else:
+            eis = scores.cpu().numpy().reshape(-1, 1)
         if isinstance(candidates, (CellBatch, torch.Tensor)):
             xs = tuple(int(i) for i in indices)
         else:

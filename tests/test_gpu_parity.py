@@ -457,3 +457,23 @@ def test_sharded_topk_device_merge_equals_global(eng):
             assert np.array_equal(i, ref_i) and np.array_equal(v, ref_v)
             hv, hi_ = parallel.merge_topk(s, np.arange(len(s)), 5, distinct)     # host restatement
             assert np.array_equal(i, hi_) and np.array_equal(v, hv)
+
+
+def test_host_pool_pipeline_matches_resident_path(eng):
+    """propose_location on packed records in HOST memory (chunked H2D / kernel / D2H pipeline)
+    returns the same scores and selection as the resident-pool path."""
+    from nasbowl_b200.bayesopt import GraphExpectedImprovement, GraphGP
+    from nasbowl_b200.kernels import WeisfilerLehman
+    train = synth.generate_cells_host(0, 3, 0, 60)
+    gp = GraphGP(train, torch.randn(60, generator=torch.Generator().manual_seed(1)), [WeisfilerLehman(h=2)])
+    gp.fit(wl_subtree_candidates=(1, 2), optimize_lik=True)
+    acq = GraphExpectedImprovement(gp)
+    for M in (5, 1000, 100_003):
+        dev = eng.generate_cells(0, 9, 500, M)
+        host = dev.cpu()
+        xs_d, eis_d, idx_d = acq.propose_location(dev, top_n=5)
+        xs_h, eis_h, idx_h = acq.propose_location(host, top_n=5)
+        xs_p, eis_p, idx_p = acq.propose_location(host.pin_memory(), top_n=5)
+        assert np.array_equal(eis_d, eis_h) and np.array_equal(eis_d, eis_p)
+        assert np.array_equal(idx_d, idx_h) and np.array_equal(idx_d, idx_p)
+        assert eis_h.shape == (M, 1) and eis_h.dtype == np.float32
