@@ -305,6 +305,9 @@ def run_b200(args):
         lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
         dist.all_reduce(lt, op=dist.ReduceOp.SUM)
         launches = int(lt.item())
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     peak, peak_src = load_peaks()

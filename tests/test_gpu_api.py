@@ -1,0 +1,116 @@
+"""GPU tests of the reference-shaped API corners: undirected WL, per-level weights, several WL
+kernels with fixed weights (dense predict path), embeddings, pickling, mixed record widths."""
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from nasbowl_b200.cells import CellBatch
+from oracle import gp_oracle, wl_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def test_undirected_and_layer_weights(family):
+    from nasbowl_b200.kernels import WeisfilerLehman
+    _, z, train, _ = family
+    und = train.to_undirected()
+    K = WeisfilerLehman(h=2, undirected=True).fit_transform(train, rebuild_model=True)
+    assert np.array_equal(K.numpy(), wl_oracle.gram_raw(und, 2))
+    assert not np.array_equal(K.numpy(), z["Kraw_h2_oa0"])
+    lw = np.array([1.0, 0.5, 2.0])
+    Kw = WeisfilerLehman(h=2, layer_weights=lw).fit_transform(train, rebuild_model=True)
+    levels = wl_oracle.gram_raw_levels(train, 2)
+    np.testing.assert_allclose(Kw.numpy(), (levels * lw[:, None, None]).sum(0), rtol=1e-14)
+    # weights of the wrong length are reset to ones (weisfeiler_lehman.py:126-127)
+    K1 = WeisfilerLehman(h=1, layer_weights=lw).fit_transform(train, rebuild_model=True)
+    assert np.array_equal(K1.numpy(), z["Kraw_h1_oa0"])
+    # cached Gram is returned unless rebuild_model (weisfilerlehman.py:125-126)
+    k = WeisfilerLehman(h=2)
+    a = k.fit_transform(train, rebuild_model=True)
+    assert k.fit_transform(train[:5]) is k._gram and np.array_equal(a.numpy(), k._gram.numpy())
+
+
+def test_embeddings_restricted_to_fitted_vocabulary(family):
+    from nasbowl_b200.kernels import WeisfilerLehman
+    _, z, train, pool = family
+    k = WeisfilerLehman(h=2)
+    k.fit_transform(train, rebuild_model=True)
+    emb = k.transform(pool)
+    assert len(emb) == 3 and all(e.shape[0] == len(pool) for e in emb)
+    phi_train = [e.numpy().astype(np.int64) for e in k.transform(train)]
+    K_s = sum(pt @ e.numpy().astype(np.int64).T for pt, e in zip(phi_train, emb))
+    assert np.array_equal(K_s, wl_oracle.pool_features(train, pool, 2)[0])
+
+
+def test_two_kernels_fixed_weights_dense_predict(family):
+    """SumKernel of two WL kernels with fixed weights (combine_kernels.py:36-56) through
+    GraphGP.predict: K = normalise(w1 K1 + w2 K2) on train ∪ test."""
+    from nasbowl_b200.bayesopt import GraphGP
+    from nasbowl_b200.kernels import WeisfilerLehman
+    _, z, train, pool = family
+    y = z["y"].astype(np.float64)
+    w = [0.3, 0.7]
+    gp = GraphGP(train, torch.tensor(y), [WeisfilerLehman(h=1), WeisfilerLehman(h=2, oa=True)], weights=w)
+    gp.fit(wl_subtree_candidates=(), optimize_lik=False)
+    n, M = len(train), len(pool)
+    joint = CellBatch.concat([train, pool])
+    wf = [gp_oracle.f32(v) for v in w]      # the reference keeps kernel weights as an fp32 tensor (gp.py:66)
+    Kj = gp_oracle.normalize_gram(wf[0] * wl_oracle.gram_raw(joint, 1) + wf[1] * wl_oracle.gram_raw(joint, 2, oa=True))
+    yn, ym, ys = gp_oracle.normalize_y(y)
+    lik = gp_oracle.f32(1e-3)
+    K_i, _, _ = gp_oracle.pd_inverse(Kj[:n, :n], lik)
+    K_s = Kj[:n, n:]
+    mu_o = (K_s.T @ K_i @ yn) * ys + ym
+    cov_o = (np.sqrt(np.maximum(Kj[n:, n:] + lik * np.eye(M) - K_s.T @ K_i @ K_s, lik)) * ys) ** 2
+    mu, cov = gp.predict(pool)
+    np.testing.assert_allclose(gp.K.numpy(), Kj[:n, :n], rtol=1e-12)
+    np.testing.assert_allclose(mu.numpy(), mu_o, rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(cov.numpy(), cov_o, rtol=1e-6, atol=1e-12)
+    assert torch.allclose(gp.weights.double(), torch.tensor(w, dtype=torch.float64))
+    with pytest.raises(NotImplementedError):
+        gp.predict_diag(pool)                  # the fused pool path is single-kernel
+    with pytest.raises(NotImplementedError):   # trainable kernel weights are not on the GPU path
+        GraphGP(train, torch.tensor(y), [WeisfilerLehman(h=1), WeisfilerLehman(h=2)]).fit(wl_subtree_candidates=())
+
+
+def test_pickle_roundtrip_and_refit(family):
+    from nasbowl_b200.bayesopt import GraphExpectedImprovement, GraphGP
+    from nasbowl_b200.kernels import WeisfilerLehman
+    _, z, train, pool = family
+    gp = GraphGP(train, torch.tensor(z["y"]), [WeisfilerLehman(h=2, oa=True)])
+    gp.fit(wl_subtree_candidates=(1, 2), optimize_lik=True)
+    mu0, var0 = gp.predict_diag(pool)
+    gp2 = pickle.loads(pickle.dumps({"gp": gp, "x": train}))["gp"]        # run_darts.py:110-125
+    assert gp2.kernels[0].h == gp.kernels[0].h and gp2.likelihood == gp.likelihood
+    with pytest.raises(ValueError):
+        gp2.predict_diag(pool)                                              # device state does not travel
+    gp2.reset_XY(train, torch.tensor(z["y"]))
+    gp2.fit(wl_subtree_candidates=(1, 2), optimize_lik=True)               # what the resume path does
+    mu1, var1 = gp2.predict_diag(pool)
+    np.testing.assert_allclose(mu1.numpy(), mu0.numpy(), rtol=1e-12)
+    np.testing.assert_allclose(var1.numpy(), var0.numpy(), rtol=1e-12)
+    assert GraphExpectedImprovement(gp2).propose_location(pool, top_n=3)[2].shape == (3,)
+
+
+def test_small_cells_scored_by_a_gp_fitted_on_wide_records():
+    """NB cells (8-node records) scored by a surrogate fitted on 16-node records, and the
+    reverse request is refused with a clear message."""
+    from nasbowl_b200.bayesopt import GraphGP
+    from nasbowl_b200.kernels import WeisfilerLehman
+    z, batch = load_golden("nasbench101")
+    train, pool = batch[:40], batch[40:]
+    y = torch.tensor(z["y"])
+    g8 = GraphGP(train, y, [WeisfilerLehman(h=2)])
+    g8.fit(wl_subtree_candidates=(2,), optimize_lik=False)
+    g16 = GraphGP(train, y, [WeisfilerLehman(h=2)], n_max=16)
+    g16.fit(wl_subtree_candidates=(2,), optimize_lik=False)
+    a, b = g8.predict_diag(pool), g16.predict_diag(pool)
+    np.testing.assert_allclose(a[0].numpy(), b[0].numpy(), rtol=1e-12)
+    np.testing.assert_allclose(a[1].numpy(), b[1].numpy(), rtol=1e-12)
+    zd, darts = load_golden("darts")
+    with pytest.raises(ValueError, match="n_max=16"):
+        g8.predict_diag(darts[:4])
+    assert g16.predict_diag(darts[:4])[0].shape == (4,)
