@@ -71,6 +71,37 @@ __device__ __forceinline__ int effective_column(const nbw_model& M, int l, bool 
   return rank < mc ? M.col_off[l] + (int)__ldg(M.thermo_base + sl) + rank : -1;
 }
 
+// Posterior scaling + acquisition for one candidate (fp64): gp.py:272-280, acquisitions.py:68-77,136.
+__device__ __forceinline__ void finish_candidate(const nbw_model& M, double mu_acc, double q_acc, int kcc_i, int64_t g,
+                                                 float* __restrict__ scores, double* __restrict__ mu64,
+                                                 double* __restrict__ var64, double* __restrict__ score64) {
+  if (g < 0) return;
+  const double inv_kcc = 1.0 / (double)kcc_i;
+  const double mu_n = mu_acc * sqrt(inv_kcc);
+  const double q = q_acc * inv_kcc;
+  const double var_n = fmax(1.0 + M.lik - q, M.lik);    // gp.py:272-276 (diagonal)
+  const double sd = sqrt(var_n) * M.y_std;              // gp.py:278-279
+  const double var = sd * sd;                           // gp.py:280
+  const double mu = mu_n * M.y_std + M.y_mean;          // gp.py:277
+  double score;
+  if (M.acq == NBW_ACQ_UCB) {
+    score = mu + M.beta * sd;                           // acquisitions.py:136
+  } else if (M.acq == NBW_ACQ_MEAN) {
+    score = mu;
+  } else {
+    const double d = mu - M.incumbent - M.xi;           // acquisitions.py:71-74
+    const double u = d / sd;
+    const double pdf = exp(-0.5 * u * u) * 0.3989422804014327;
+    const double cdf = 0.5 * erfc(-u * 0.7071067811865476);
+    score = sd * pdf + d * cdf;
+    if (M.acq == NBW_ACQ_AEI) score *= 1.0 - sqrt(M.lik) / sqrt(M.lik + var);   // :75-77
+  }
+  scores[g] = (float)score;
+  if (mu64) mu64[g] = mu;
+  if (var64) var64[g] = var;
+  if (score64) score64[g] = score;
+}
+
 struct ScoreParams {
   nbw_model M;
   LevelSalt salt[NBW_MAX_LEVELS];   // per-level hash salts, derived from M.seed on the host
@@ -93,6 +124,10 @@ score_pool_kernel(const ScoreParams P, const uint8_t* __restrict__ cells, int64_
   const int sub_base = sub * NMAX;
   const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  // staging area of the batched epilogue: 32 / GPW = NMAX rounds fill all 32 lanes
+  double st_mu = 0.0, st_q = 0.0;
+  int st_k = 1, staged = 0;
+  int64_t st_g = -1;
 
   for (int64_t g0 = warp_id * GPW; g0 < n_cells; g0 += n_warps * GPW) {
     const int64_t g = g0 + sub;
@@ -228,33 +263,29 @@ score_pool_kernel(const ScoreParams P, const uint8_t* __restrict__ cells, int64_
     mu_acc = subwarp_sum<NMAX>(mu_acc);
     q_acc = subwarp_sum<NMAX>(q_acc);
 
-    if (in_range && node == 0) {
-      const double inv_kcc = 1.0 / (double)kcc_i;
-      const double mu_n = mu_acc * sqrt(inv_kcc);
-      const double q = q_acc * inv_kcc;
-      const double var_n = fmax(1.0 + M.lik - q, M.lik);    // gp.py:272-276 (diagonal)
-      const double sd = sqrt(var_n) * M.y_std;              // gp.py:278-279
-      const double var = sd * sd;                           // gp.py:280
-      const double mu = mu_n * M.y_std + M.y_mean;          // gp.py:277
-      double score;
-      if (M.acq == NBW_ACQ_UCB) {
-        score = mu + M.beta * sd;                           // acquisitions.py:136
-      } else if (M.acq == NBW_ACQ_MEAN) {
-        score = mu;
-      } else {
-        const double d = mu - M.incumbent - M.xi;           // acquisitions.py:71-74
-        const double u = d / sd;
-        const double pdf = exp(-0.5 * u * u) * 0.3989422804014327;
-        const double cdf = 0.5 * erfc(-u * 0.7071067811865476);
-        score = sd * pdf + d * cdf;
-        if (M.acq == NBW_ACQ_AEI) score *= 1.0 - sqrt(M.lik) / sqrt(M.lik + var);   // :75-77
+    // ---- stage (mu, q, k_cc) of this round's GPW cells on lanes [slot*GPW, slot*GPW + GPW):
+    // the fp64 acquisition epilogue (sqrt, exp, erfc, divisions) then runs once per 32 cells
+    // with every lane busy instead of once per round with GPW lanes busy.
+    {
+      const int src = (lane % GPW) * NMAX;   // any lane of sub-warp (lane % GPW) holds its totals
+      const double s_mu = __shfl_sync(0xffffffffu, mu_acc, src);
+      const double s_q = __shfl_sync(0xffffffffu, q_acc, src);
+      const int s_k = __shfl_sync(0xffffffffu, kcc_i, src);
+      if (lane / GPW == staged) {
+        const int64_t gs = g0 + (lane % GPW);
+        st_mu = s_mu;
+        st_q = s_q;
+        st_k = s_k;
+        st_g = gs < n_cells ? gs : -1;
       }
-      scores[g] = (float)score;
-      if (mu64) mu64[g] = mu;
-      if (var64) var64[g] = var;
-      if (score64) score64[g] = score;
+    }
+    if (++staged == NMAX) {
+      finish_candidate(M, st_mu, st_q, st_k, st_g, scores, mu64, var64, score64);
+      st_g = -1;
+      staged = 0;
     }
   }
+  if (MODE != 1 && staged > 0) finish_candidate(M, st_mu, st_q, st_k, st_g, scores, mu64, var64, score64);
 }
 
 template <int NMAX, int MODE>
