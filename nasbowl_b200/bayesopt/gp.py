@@ -163,7 +163,7 @@ class GraphGP:
                 raise NotImplementedError("only WeisfilerLehman kernels run on the GPU path")
             cands = [int(c) for c in wl_subtree_candidates]
             h_fit = max(cands + [k.h])
-            fit = k.fit_device(cells, batch.n_max, h=h_fit)
+            fit = k.fit_device(cells, batch.n_max, h=h_fit, batch=batch)
             if len(cands):
                 self._grid_search_wl_kernel(k, fit, cands, y_dev, self.likelihood)
             fits.append(fit)
@@ -206,7 +206,7 @@ class GraphGP:
         self.sum_kernels.weights = weights.clone()
         self._fitted = True
         self._dev = dict(eng=eng, fits=fits, hs=[k.h for k in self.sum_kernels.kernels], K=K, L=L, Linv=Linv,
-                         alpha=alpha, s=inv_sqrt_diag, y=y_dev, n_max=batch.n_max, cells=cells,
+                         alpha=alpha, s=inv_sqrt_diag, y=y_dev, n_max=batch.n_max, cells=cells, batch=batch,
                          weights=[float(w) for w in weights], score=None, K_host=None, Ki_host=None)
         if self.verbose:
             print('Optimisation summary: ')
@@ -257,6 +257,7 @@ class GraphGP:
         for k, h in zip(self.sum_kernels.kernels, d['hs']):
             fit = eng.wl_fit(cells_all, d['n_max'], h, k.oa)
             k._fit = fit          # the reference leaves the kernel fitted on train ∪ test (Q19)
+            k._fit_batch, k._ref_cache = CellBatch.concat([d['batch'], test]), None
             grams.append(k.gram_device(fit, h))
         K_full, _ = self.sum_kernels.combine_device(d['weights'], grams, normalize=True)
         N = n + M

@@ -57,7 +57,7 @@ class CombineKernel:
             if rebuild_model or k._fit is None:
                 if rebuild_model:
                     k._train = gr1[:] if not isinstance(gr1, CellBatch) else gr1
-                k.fit_device(cells, batch.n_max)
+                k.fit_device(cells, batch.n_max, batch=batch)
             grams.append(k.gram_device(k._fit))
         K, _ = self.combine_device(weights, grams, normalize)
         K = K.cpu()

@@ -62,6 +62,8 @@ class WeisfilerLehman(GraphKernels):
         self._gram = None
         self._train, self._train_transformed = None, None
         self._fit = None                          # engine.WLFit of the last fit (device state)
+        self._fit_batch = None                    # the packed cells it was fitted on (host)
+        self._ref_cache = None
         self.__name__ = 'WeisfeilerLehman'
 
     # ------------------------------------------------------------------ reference API
@@ -98,11 +100,12 @@ class WeisfilerLehman(GraphKernels):
             return None
         return None if np.all(lw == 1.0) else lw
 
-    def fit_device(self, cells: torch.Tensor, n_max: int, h: Optional[int] = None):
+    def fit_device(self, cells: torch.Tensor, n_max: int, h: Optional[int] = None, batch: Optional[CellBatch] = None):
         """Fit on packed device records; returns the engine's WLFit (features stay on device)."""
         from ..engine import Engine
         eng = Engine.get()
         self._fit = eng.wl_fit(cells, n_max, self.h if h is None else h, self.oa)
+        self._fit_batch = batch
         return self._fit
 
     def gram_device(self, fit, h: Optional[int] = None) -> torch.Tensor:
@@ -135,7 +138,7 @@ class WeisfilerLehman(GraphKernels):
             self._train_transformed = batch
         if layer_weights is not None and layer_weights is not self.layer_weights:
             self.change_kernel_params({'layer_weights': layer_weights})
-        fit = self.fit_device(eng.upload_cells(batch), batch.n_max)
+        fit = self.fit_device(eng.upload_cells(batch), batch.n_max, batch=batch)
         K = self.gram_device(fit).cpu()
         if not self.return_tensor:
             K = K.numpy()
@@ -167,14 +170,101 @@ class WeisfilerLehman(GraphKernels):
     def forward_t(self, gr2, gr1=None):
         raise NotImplementedError("kernel gradients (interpretability, gp.py:296-424) are outside the GPU hot path")
 
+    # ------------------------------------------------------------------ motif strings (row f3)
+    def _reference_labels(self):
+        """Number the device's label classes exactly like the reference and name them.
+
+        The reference numbers the labels of level l by the rank of their credential STRING
+        `str(own) + "," + str(sorted(successor ids))` among the level's distinct credentials,
+        continuing one counter over the levels (weisfeiler_lehman.py:226-229,266-274), and names
+        them "root~leaf~leaf" in terms of the previous level's names (translate_label, :577-599).
+        Only the partition is computed on the GPU; this assembles the strings on the host from
+        one representative node per label class.  Returns (ref_id, names): per level, an array
+        device id -> reference id, and a dict reference id -> motif string."""
+        fit, batch = self._fit, self._fit_batch
+        if fit is None or batch is None:
+            return None
+        if getattr(self, '_ref_cache', None) is not None and self._ref_cache[0] is fit:
+            return self._ref_cache[1]
+        h, n_max = self.h, fit.n_max
+        ids = fit.ids[:h + 1].cpu().numpy().view(np.uint32).reshape(h + 1, fit.n_cells, n_max)
+        succ = batch.succ
+        names0 = {}
+        codes = [int(c) for c in fit.op_codes]
+        order = sorted(codes, key=lambda c: self.vocab.names[c])
+        ref_of_code = {c: i for i, c in enumerate(order)}
+        ref_id = [np.array([ref_of_code[c] for c in codes], dtype=np.int64)]
+        names = [{ref_of_code[c]: str(self.vocab.names[c]) for c in codes}]
+        counter = len(codes)
+        for l in range(1, h + 1):
+            D = fit.dims[l]
+            flat = ids[l].reshape(-1)
+            valid = np.nonzero(flat != 0xFFFFFFFF)[0]
+            rep = np.full(D, -1, dtype=np.int64)
+            rep[flat[valid][::-1]] = valid[::-1]              # first node carrying each label
+            creds = []
+            for z in range(D):
+                g, v = divmod(int(rep[z]), n_max)
+                own = int(ref_id[l - 1][ids[l - 1][g, v]])
+                nb = sorted(int(ref_id[l - 1][ids[l - 1][g, j]]) for j in range(n_max) if (int(succ[g, v]) >> j) & 1)
+                creds.append((str(own) + "," + str(nb), own, nb))
+            rank = sorted(range(D), key=lambda z: creds[z][0])
+            rid = np.empty(D, dtype=np.int64)
+            nm = {}
+            for r, z in enumerate(rank):
+                rid[z] = counter + r
+                _, own, nb = creds[z]
+                nm[counter + r] = "~".join([names[l - 1][own]] + [names[l - 1][i] for i in nb])
+            counter += D
+            ref_id.append(rid)
+            names.append(nm)
+        self._ref_cache = (fit, (ref_id, names))
+        return ref_id, names
+
     def feature_map(self, flatten=True):
-        raise NotImplementedError("feature_map (motif strings) is not part of the scoring hot path yet")
+        """{feature index: motif string}, layered by WL level unless `flatten`
+        (reference kernels/weisfilerlehman.py:219-242)."""
+        if self._gram is None and self._fit is None:
+            return None
+        ref = self._reference_labels()
+        if ref is None:
+            return None
+        _, names = ref
+        if not flatten:
+            return {l: dict(sorted(nm.items())) for l, nm in enumerate(names)}
+        res = {}
+        for nm in names:
+            res.update(dict(sorted(nm.items())))
+        return res
 
     def feature_value(self, X_s):
-        raise NotImplementedError("feature_value is not part of the scoring hot path yet")
+        """WL embedding of X_s over the fitted features, columns in feature_map order, plus the
+        list of motif strings (reference kernels/weisfilerlehman.py:244-266)."""
+        ref = self._reference_labels()
+        if ref is None:
+            raise ValueError("The kernel has not been fitted. Call fit_transform first.")
+        ref_id, _ = ref
+        fit = self._fit
+        phi, _ = self.feature_matrix(X_s)
+        total = sum(fit.dims[:self.h + 1])
+        emb = np.zeros((phi.shape[0], total), dtype=np.float64)
+        tb = fit.thermo_base.cpu().numpy() if fit.oa else None
+        mc = fit.max_count.cpu().numpy() if fit.oa else None
+        for l in range(self.h + 1):
+            for z in range(fit.dims[l]):
+                if fit.oa:      # thermometer columns of one label add up to its (capped) count
+                    sl = fit.label_off[l] + z
+                    c0 = fit.col_off[l] + int(tb[sl])
+                    col = phi[:, c0:c0 + int(mc[sl])].sum(axis=1)
+                else:
+                    col = phi[:, fit.col_off[l] + z]
+                emb[:, ref_id[l][z]] = col
+        return torch.tensor(emb), list(self.feature_map(flatten=True).values())
 
     # device state does not travel through pickle (run_darts.py:110-125 pickles the GP)
     def __getstate__(self):
         st = dict(self.__dict__)
         st['_fit'] = None
+        st['_fit_batch'] = None
+        st['_ref_cache'] = None
         return st

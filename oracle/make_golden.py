@@ -75,6 +75,13 @@ def family_case(R, family, seed, n_train=40, n_pool=30):
             out["Kraw_h%d_oa%d" % (h, int(oa))] = np.rint(K).astype(np.int64)
             if h == 3 and not oa:
                 out["feature_dims_h3"] = np.array(dims, dtype=np.int64)
+                kk = R.WeisfilerLehman(h=3, oa=False, requires_grad=True)
+                kk.fit_transform(train, rebuild_model=True)
+                fm = kk.feature_map(flatten=True)
+                out["featmap_h3_ids"] = np.array(list(fm.keys()), dtype=np.int64)
+                out["featmap_h3_names"] = np.array(list(fm.values()))
+                emb, names = kk.feature_value(pool)
+                out["featval_h3_pool"] = np.rint(emb.numpy()).astype(np.int16)
                 for l, p in enumerate(phis):
                     out["phi_h3_l%d" % l] = np.rint(p).astype(np.int16)
         # joint (train ∪ pool) Gram at h=2: pins pool-side features incl. unseen labels

@@ -114,3 +114,38 @@ def test_small_cells_scored_by_a_gp_fitted_on_wide_records():
     with pytest.raises(ValueError, match="n_max=16"):
         g8.predict_diag(darts[:4])
     assert g16.predict_diag(darts[:4])[0].shape == (4,)
+
+
+def test_feature_map_and_feature_value_match_reference(family):
+    """Interpretability accessors (row f3): the motif strings and their numbering, and the
+    embedding of unseen cells over them, exactly as the reference produces them
+    (kernels/weisfilerlehman.py:219-266, weisfeiler_lehman.py:577-599)."""
+    from nasbowl_b200 import OpVocab
+    from nasbowl_b200.kernels import WeisfilerLehman
+    _, z, train, pool = family
+    for as_graphs in (False, True):
+        k = WeisfilerLehman(h=3, requires_grad=True)
+        if as_graphs:
+            vocab = OpVocab(list(z["op_names"]))
+            train_in, pool_in = train.to_networkx(vocab), pool.to_networkx(vocab)
+        else:
+            k.vocab = OpVocab(list(z["op_names"]))      # packed records carry the fixture's op codes
+            train_in, pool_in = train, pool
+        k.fit_transform(train_in, rebuild_model=True)
+        emb, names = k.feature_value(pool_in)
+        fm = k.feature_map(flatten=True)
+        assert list(fm.keys()) == list(z["featmap_h3_ids"])
+        assert list(fm.values()) == list(z["featmap_h3_names"]) == names
+        layered = k.feature_map(flatten=False)
+        assert [len(layered[l]) for l in range(4)] == list(np.diff(z["feature_dims_h3"]))
+        assert np.array_equal(emb.numpy().astype(np.int64), z["featval_h3_pool"].astype(np.int64))
+        # the training embedding reproduces the reference's ordered histograms column for column
+        emb_t, _ = k.feature_value(train_in)
+        ref = np.concatenate([z["phi_h3_l%d" % l][:, :w] for l, w in enumerate(np.diff(z["feature_dims_h3"]))], axis=1)
+        assert np.array_equal(emb_t.numpy().astype(np.int64), ref.astype(np.int64))
+    # oa: same counts (the base kernel changes the Gram, not the histogram)
+    k = WeisfilerLehman(h=3, oa=True)
+    k.vocab = OpVocab(list(z["op_names"]))
+    k.fit_transform(train, rebuild_model=True)
+    emb_oa, _ = k.feature_value(train)
+    assert np.array_equal(emb_oa.numpy().astype(np.int64), ref.astype(np.int64))
