@@ -149,3 +149,24 @@ def test_feature_map_and_feature_value_match_reference(family):
     k.fit_transform(train, rebuild_model=True)
     emb_oa, _ = k.feature_value(train)
     assert np.array_equal(emb_oa.numpy().astype(np.int64), ref.astype(np.int64))
+
+
+def test_bo_loop_matches_oracle_every_iteration():
+    """The reference's outer loop (nasbench_optimisation.py:153-216) on the GPU path: at every
+    iteration the fitted depth, the noise and the proposed batch agree with the CPU oracle."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples"))
+    import bo_loop
+
+    def check(gp, x, y, pool, eis, idx):
+        st = gp_oracle.gp_fit(x, y.numpy(), h_candidates=(1, 2, 3), optimize_lik=True, max_lik=0.01)
+        assert st.h == gp.kernels[0].h and np.float32(st.lik) == np.float32(gp.likelihood)
+        sub = CellBatch.from_records(pool.cpu().numpy(), 8)
+        mu, var = gp_oracle.gp_predict_diag(st, x, sub)
+        ei = gp_oracle.expected_improvement(mu, var, gp_oracle.incumbent(st))
+        np.testing.assert_allclose(eis.reshape(-1), ei, rtol=1e-4, atol=1e-9)
+        assert set(int(i) for i in idx) == set(int(i) for i in gp_oracle.top_n_distinct(eis.reshape(-1), 5))
+
+    best, x, y = bo_loop.run(iters=4, pool_size=3000, batch_size=5, n_init=20, verbose=False, check=check)
+    assert len(x) == 40 and best[-1] >= best[0]
