@@ -4,37 +4,40 @@
 // weisfeiler_lehman.py:316-327: WL levels are contiguous column blocks of Phi, so the sum over
 // levels 0..h is ONE GEMM over the K-range [0, col_off[h+1]).
 //
-// Product path (impl 0): tcgen05.mma kind::i8, cta_group::1, 128x128 accumulator tile in TMEM
-// (128 lanes x 128 columns of s32), both operands K-major, staged by TMA into 128B-swizzled
-// shared memory (one 128-byte K-block per row per stage), 3-stage mbarrier pipeline:
+// Product path (impl 0): tcgen05.mma kind::i8, cta_group::1, M = 128, N = 256 accumulator tiles
+// in TMEM (128 lanes x 256 columns of s32, two buffers), both operands K-major, staged by TMA
+// into 128B-swizzled shared memory (one 128-byte K-block per row per stage), 4-stage mbarrier
+// pipeline, persistent CTAs (one per SM) walking the tiles in a grouped order:
 //   warp 0 lane 0 : TMA producer          (cp.async.bulk.tensor.2d -> full barrier)
 //   warp 1 lane 0 : MMA issuer            (4 x UMMA_K=32 per stage, tcgen05.commit -> empty barrier)
-//   warps 0..3    : epilogue              (tcgen05.ld 32x32b.x32 -> 128-byte row segments to HBM)
-// Two CTAs fit per SM (97 KB smem, 128 TMEM columns each) so one tile's epilogue overlaps the
-// other's main loop.  int32 accumulation of int8 products is exact.
+//   warps 2..5    : epilogue              (tcgen05.ld 32x32b.x32 -> 128-byte row segments to HBM)
+// int32 accumulation of int8 products is exact.
 //
 // Cross-check path (impl 1): plain dp4a kernel, used by the tests to validate impl 0.
 #include "nbw_common.cuh"
 
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 128;   // BK in bytes == int8 elements == one swizzle row
+constexpr int BM = 128, BK = 128;   // BK in bytes == int8 elements == one swizzle row
 constexpr int UMMA_K = 32;
-constexpr int STAGES = 3;
-constexpr int TILE_BYTES = BM * BK;            // 16 KB per operand per stage
-constexpr int TMEM_COLS = 128;
+constexpr int MAX_STAGES = 8;
+constexpr int A_TILE_BYTES = BM * BK;          // 16 KB of A per stage
 constexpr uint32_t SPIN_LIMIT = 1u << 26;
 
 struct __align__(8) PipeBarriers {
-  uint64_t full[STAGES];
-  uint64_t empty[STAGES];
+  uint64_t full[MAX_STAGES];
+  uint64_t empty[MAX_STAGES];
   uint64_t tmem_full;
   uint32_t tmem_base;
   uint32_t pad;
 };
-constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * 2 * TILE_BYTES + sizeof(PipeBarriers);
+template <int BN, int STAGES>
+constexpr size_t gram_smem_bytes() {
+  return 1024 /*align slack*/ + (size_t)STAGES * (A_TILE_BYTES + BN * BK) + sizeof(PipeBarriers);
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -103,21 +106,44 @@ __device__ __forceinline__ void tmem_load_32cols(uint32_t taddr, uint32_t (&r)[3
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// instruction descriptor: D = s32, A = B = signed 8-bit, both K-major, M = 128, N = 128
-constexpr uint32_t kIdescI8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
-                              ((uint32_t)(BM >> 4) << 24);
+// instruction descriptor: D = s32, A = B = signed 8-bit, both K-major, M = 128, N = BN
+// Grouped tile order: consecutive tile indices sweep GROUP_M row-tiles before moving to the next
+// column-tile, so CTAs that run at the same time share both their A and their B tiles in L2
+// (with a plain row-major order every row-tile re-streams all of B from HBM).
+constexpr int GROUP_M = 16;
+__device__ __forceinline__ void tile_coords(int64_t t, int32_t m_tiles, int32_t n_tiles, int32_t& mt, int32_t& nt) {
+  const int64_t per_group = (int64_t)GROUP_M * n_tiles;
+  const int32_t first_m = (int32_t)(t / per_group) * GROUP_M;
+  const int32_t gsize = (m_tiles - first_m) < GROUP_M ? (m_tiles - first_m) : GROUP_M;
+  const int64_t in_group = t % per_group;
+  mt = first_m + (int32_t)(in_group % gsize);
+  nt = (int32_t)(in_group / gsize);
+}
 
+template <int BN>
+struct IdescI8 {
+  static constexpr uint32_t value =
+      (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+};
+
+template <int BN, int STAGES>
 __global__ void __launch_bounds__(128)
 gram_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                       int32_t* __restrict__ C, int64_t ldc, int64_t m, int64_t n, int32_t kblk0, int32_t k_blocks) {
+                       int32_t* __restrict__ C, int64_t ldc, int64_t m, int64_t n, int32_t kblk0, int32_t k_blocks,
+                       int32_t m_tiles, int32_t n_tiles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int B_TILE_BYTES = BN * BK;
+  constexpr int TMEM_COLS = BN;
+  constexpr uint32_t kIdescI8 = IdescI8<BN>::value;
   uint8_t* tile_a = smem;                                   // [STAGES][128 rows][128 B]
-  uint8_t* tile_b = smem + (size_t)STAGES * TILE_BYTES;
-  PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(smem + (size_t)STAGES * 2 * TILE_BYTES);
+  uint8_t* tile_b = smem + (size_t)STAGES * A_TILE_BYTES;   // [STAGES][BN rows][128 B]
+  PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(smem + (size_t)STAGES * (A_TILE_BYTES + B_TILE_BYTES));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int32_t row0 = blockIdx.y * BM, col0 = blockIdx.x * BN;
+  int32_t mt, nt;
+  tile_coords(blockIdx.x, m_tiles, n_tiles, mt, nt);
+  const int32_t row0 = mt * BM, col0 = nt * BN;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -145,10 +171,10 @@ gram_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
       uint32_t stage = 0, phase = 0;
       for (int kb = 0; kb < k_blocks; ++kb) {
         mbar_wait(&bars->empty[stage], phase ^ 1u);
-        mbar_expect_tx(&bars->full[stage], 2u * TILE_BYTES);
+        mbar_expect_tx(&bars->full[stage], (uint32_t)(A_TILE_BYTES + B_TILE_BYTES));
         const int32_t kx = (kblk0 + kb) * BK;
-        tma_load_2d(&map_a, &bars->full[stage], tile_a + (size_t)stage * TILE_BYTES, kx, row0);
-        tma_load_2d(&map_b, &bars->full[stage], tile_b + (size_t)stage * TILE_BYTES, kx, col0);
+        tma_load_2d(&map_a, &bars->full[stage], tile_a + (size_t)stage * A_TILE_BYTES, kx, row0);
+        tma_load_2d(&map_b, &bars->full[stage], tile_b + (size_t)stage * B_TILE_BYTES, kx, col0);
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
@@ -160,8 +186,8 @@ gram_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
       for (int kb = 0; kb < k_blocks; ++kb) {
         mbar_wait(&bars->full[stage], phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_addr = smem_u32(tile_a + (size_t)stage * TILE_BYTES);
-        const uint32_t b_addr = smem_u32(tile_b + (size_t)stage * TILE_BYTES);
+        const uint32_t a_addr = smem_u32(tile_a + (size_t)stage * A_TILE_BYTES);
+        const uint32_t b_addr = smem_u32(tile_b + (size_t)stage * B_TILE_BYTES);
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k) {
           const uint64_t da = umma_smem_desc(a_addr + k * UMMA_K);
@@ -204,6 +230,154 @@ gram_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ persistent variant
+// One CTA per SM walks the output tiles (128 x BN) in row-major tile order.  Six warps:
+//   warp 0      : TMA producer over (tile, k-block)
+//   warp 1      : MMA issuer; owns the TMEM allocation: two accumulator buffers of BN columns
+//   warps 2..5  : epilogue of tile i (tcgen05.ld -> HBM) while warp 1 already accumulates tile i+1
+// so neither the epilogue nor the TMEM/barrier set-up sits on the tensor pipe's critical path.
+struct __align__(8) PersistBarriers {
+  uint64_t full[MAX_STAGES];
+  uint64_t empty[MAX_STAGES];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+template <int BN, int STAGES>
+constexpr size_t gram_persist_smem_bytes() {
+  return 1024 + (size_t)STAGES * (A_TILE_BYTES + BN * BK) + sizeof(PersistBarriers);
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+gram_i8_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                          int32_t* __restrict__ C, int64_t ldc, int64_t m, int64_t n, int32_t kblk0, int32_t k_blocks,
+                          int32_t m_tiles, int32_t n_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int B_TILE_BYTES = BN * BK;
+  constexpr uint32_t kIdesc = IdescI8<BN>::value;
+  static_assert(2 * BN <= 512, "two accumulator buffers must fit the 512 TMEM columns");
+  uint8_t* tile_a = smem;
+  uint8_t* tile_b = smem + (size_t)STAGES * A_TILE_BYTES;
+  PersistBarriers* bars = reinterpret_cast<PersistBarriers*>(smem + (size_t)STAGES * (A_TILE_BYTES + B_TILE_BYTES));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t total_tiles = (int64_t)m_tiles * n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bars->tmem_full[b], 1);
+      mbar_init(&bars->tmem_empty[b], 4);   // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
+                 "r"((uint32_t)(2 * BN))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int32_t mt, nt;
+        tile_coords(t, m_tiles, n_tiles, mt, nt);
+        const int32_t row0 = mt * BM, col0 = nt * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&bars->empty[stage], phase ^ 1u);
+          mbar_expect_tx(&bars->full[stage], (uint32_t)(A_TILE_BYTES + B_TILE_BYTES));
+          const int32_t kx = (kblk0 + kb) * BK;
+          tma_load_2d(&map_a, &bars->full[stage], tile_a + (size_t)stage * A_TILE_BYTES, kx, row0);
+          tma_load_2d(&map_b, &bars->full[stage], tile_b + (size_t)stage * B_TILE_BYTES, kx, col0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1u);        // epilogue has drained this buffer
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tmem_acc = tmem_base + acc * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&bars->full[stage], phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_addr = smem_u32(tile_a + (size_t)stage * A_TILE_BYTES);
+          const uint32_t b_addr = smem_u32(tile_b + (size_t)stage * B_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_i8(tmem_acc, umma_smem_desc(a_addr + k * UMMA_K), umma_smem_desc(b_addr + k * UMMA_K), kIdesc,
+                    (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&bars->empty[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&bars->tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // epilogue warps 2..5: warp w may touch TMEM lanes [32 (w % 4), 32 (w % 4) + 32)
+    const int quarter = warp & 3;
+    const bool vec_ok = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+    uint32_t acc = 0, acc_phase = 0;
+    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int32_t mt, nt;
+      tile_coords(t, m_tiles, n_tiles, mt, nt);
+      const int64_t row0 = (int64_t)mt * BM, col0 = (int64_t)nt * BN;
+      mbar_wait(&bars->tmem_full[acc], acc_phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int64_t r = row0 + quarter * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_load_32cols(tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), v);
+        if (r < m) {
+          const int64_t cbase = col0 + c * 32;
+          int32_t* dst = C + r * ldc + cbase;
+          if (vec_ok && cbase + 32 <= n) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<int4*>(dst + 4 * q) =
+                  make_int4((int)v[4 * q], (int)v[4 * q + 1], (int)v[4 * q + 2], (int)v[4 * q + 3]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 32; ++q)
+              if (cbase + q < n) dst[q] = (int32_t)v[q];
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN))
                  : "memory");
   }
 }
@@ -258,7 +432,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_operand_map(nbw_ctx* ctx, CUtensorMap* map, const int8_t* base, int64_t rows, int64_t ld) {
+int make_operand_map(nbw_ctx* ctx, CUtensorMap* map, const int8_t* base, int64_t rows, int64_t ld, int box_rows) {
   if (!ctx->encode_tiled) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult q;
@@ -268,7 +442,7 @@ int make_operand_map(nbw_ctx* ctx, CUtensorMap* map, const int8_t* base, int64_t
   }
   const cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)ld};
-  const cuuint32_t box[2] = {BK, BM};
+  const cuuint32_t box[2] = {BK, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled)(
       map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int8_t*>(base), dims, strides, box, estr,
@@ -301,20 +475,57 @@ extern "C" int nbw_gram_i8(nbw_ctx* ctx, const int8_t* A, int64_t m, int64_t lda
     return NBW_OK;
   }
   NBW_REQUIRE(ctx, impl == 0, "unknown impl %d", impl);
+  // Default: the persistent kernel (variant 4): 128 x 256 tiles, one CTA per SM, epilogue of tile i
+  // overlapped with the main loop of tile i+1 through two TMEM accumulator buffers, grouped tile
+  // order for L2 reuse.  Measured int8 throughput: 2.89 Pop/s at 16384^2 x 8192, 3.48 Pop/s on the
+  // 200k x 200k x 33792 stress (profiles/).  NBW_GRAM_VARIANT selects the simpler one-tile-per-CTA
+  // variants for experiments: 0 = 128x128 3-stage, 1 = 128x256 4-stage, 2 = 128x128 6-stage,
+  // 3 = 128x256 2-stage (two CTAs per SM).
+  int variant = 4;
+  if (const char* v = getenv("NBW_GRAM_VARIANT")) variant = atoi(v);
+  const int bn = (variant == 0 || variant == 2) ? 128 : 256;   // variants 1, 3, 4 use 256-wide tiles
   CUtensorMap map_a, map_b;
-  int rc = make_operand_map(ctx, &map_a, A, m, lda);
+  int rc = make_operand_map(ctx, &map_a, A, m, lda, BM);
   if (rc) return rc;
-  rc = make_operand_map(ctx, &map_b, B, n, ldb);
+  rc = make_operand_map(ctx, &map_b, B, n, ldb, bn);
   if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    NBW_CUDA(ctx, cudaFuncSetAttribute(gram_i8_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    attr_set = true;
+  const int32_t mt_all = (int32_t)((m + BM - 1) / BM), nt_all = (int32_t)((n + bn - 1) / bn);
+  NBW_REQUIRE(ctx, (int64_t)mt_all * nt_all < ((int64_t)1 << 31), "gram: too many tiles for one launch");
+  const unsigned grid = (unsigned)((int64_t)mt_all * nt_all);
+  const int32_t kb0 = (int32_t)(k0 / BK), nkb = (int32_t)((k1 - k0) / BK);
+#define NBW_GRAM_LAUNCH(BN_, ST_)                                                                          \
+  do {                                                                                                     \
+    static bool attr_set = false;                                                                          \
+    if (!attr_set) {                                                                                       \
+      NBW_CUDA(ctx, cudaFuncSetAttribute(gram_i8_tcgen05_kernel<BN_, ST_>,                                  \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,                      \
+                                         (int)gram_smem_bytes<BN_, ST_>()));                                \
+      attr_set = true;                                                                                     \
+    }                                                                                                      \
+    gram_i8_tcgen05_kernel<BN_, ST_><<<grid, 128, gram_smem_bytes<BN_, ST_>(), st>>>(map_a, map_b, C, ldc, m, n, \
+                                                                                   kb0, nkb, mt_all, nt_all); \
+  } while (0)
+  switch (variant) {
+    case 0: NBW_GRAM_LAUNCH(128, 3); break;   // 97 KB: two CTAs per SM
+    case 1: NBW_GRAM_LAUNCH(256, 4); break;   // 193 KB: one CTA per SM, 256 TMEM columns
+    case 2: NBW_GRAM_LAUNCH(128, 6); break;   // experiment: deeper pipeline, one CTA per SM
+    case 3: NBW_GRAM_LAUNCH(256, 2); break;   // experiment: 97 KB, two CTAs per SM x 256 columns
+    case 4: {                                 // persistent, epilogue overlapped through two TMEM buffers
+      static bool attr4 = false;
+      constexpr size_t kBytes = gram_persist_smem_bytes<256, 4>();
+      if (!attr4) {
+        NBW_CUDA(ctx, cudaFuncSetAttribute(gram_i8_persistent_kernel<256, 4>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBytes));
+        attr4 = true;
+      }
+      const int64_t tiles = (int64_t)mt_all * nt_all;
+      const unsigned ctas = (unsigned)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
+      gram_i8_persistent_kernel<256, 4><<<ctas, 192, kBytes, st>>>(map_a, map_b, C, ldc, m, n, kb0, nkb, mt_all, nt_all);
+      break;
+    }
+    default: NBW_FAIL(ctx, NBW_ERR_INVALID, "unknown NBW_GRAM_VARIANT %d", variant);
   }
-  dim3 grid((unsigned)((n + BN - 1) / BN), (unsigned)((m + BM - 1) / BM));
-  NBW_REQUIRE(ctx, grid.y <= 65535, "gram: m too large for one launch (tile the rows)");
-  gram_i8_tcgen05_kernel<<<grid, 128, SMEM_BYTES, st>>>(map_a, map_b, C, ldc, m, n, (int32_t)(k0 / BK),
-                                                       (int32_t)((k1 - k0) / BK));
+#undef NBW_GRAM_LAUNCH
   NBW_CHECK_LAUNCH(ctx);
   return NBW_OK;
 }
