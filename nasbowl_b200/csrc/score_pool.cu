@@ -111,7 +111,7 @@ struct ScoreParams {
 // MODE 1: features only (nbw_pool_features)
 // MODE 2: prefix path (H over node pairs; linear kernel only)
 template <int NMAX, int NL, int MODE>
-__global__ void __launch_bounds__(kScoreThreads)
+__global__ void __launch_bounds__(kScoreThreads, MODE == 2 ? 5 : 3)
 score_pool_kernel(const ScoreParams P, const uint8_t* __restrict__ cells, int64_t n_cells,
                   float* __restrict__ scores, double* __restrict__ mu64, double* __restrict__ var64,
                   double* __restrict__ score64, int8_t* __restrict__ phi, int64_t ld_phi,

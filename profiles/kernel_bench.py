@@ -51,6 +51,11 @@ def main():
     flush = torch.zeros(128 * 1024 * 1024, dtype=torch.float32, device="cuda")
     out = {"hbm_peak_gbs": hbm, "int8_peak_tops_assumed_2x_bf16": i8_peak, "kernels": {}}
     lib, ctx, st = eng.lib, eng.ctx, eng.stream
+    # context for write-dominated kernels: a pure store stream (cudaMemset of 2 GiB) on this GPU
+    big = torch.empty(2 * 1024 ** 3, dtype=torch.uint8, device="cuda")
+    ms = timed(lambda: big.zero_(), flush, reps=5)
+    out["write_only_stream_gbs (memset 2 GiB)"] = big.numel() / ms / 1e6
+    del big
 
     if not args.only or "wl" in args.only:
         N, n_max, h = args.cells, (16 if args.family == 2 else 8), args.h
