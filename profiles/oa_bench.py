@@ -1,0 +1,52 @@
+#!/usr/bin/env python
+"""Pool-scoring throughput of the histogram-intersection (oa=True) kernel, the default base kernel of
+the reference's NB101 / DARTS drivers: general G path (thermometer features)."""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+from nasbowl_b200 import synth  # noqa: E402
+from nasbowl_b200.bayesopt import GraphExpectedImprovement, GraphGP  # noqa: E402
+from nasbowl_b200.cells import CellBatch  # noqa: E402
+from nasbowl_b200.engine import Engine  # noqa: E402
+from nasbowl_b200.kernels import WeisfilerLehman  # noqa: E402
+from oracle import gp_oracle  # noqa: E402
+
+eng = Engine.get()
+out = {}
+for fam, n, M in ((0, 500, 1_000_000), (2, 1000, 500_000)):
+    for oa in (False, True):
+        train = synth.generate_cells_host(fam, 0, 0, n)
+        y = torch.randn(n, generator=torch.Generator().manual_seed(0))
+        gp = GraphGP(train, y, [WeisfilerLehman(h=2, oa=oa)])
+        gp.fit(wl_subtree_candidates=(2,), optimize_lik=True)
+        acq = GraphExpectedImprovement(gp)
+        pool = eng.generate_cells(fam, 5, 10_000, M)
+        model = acq._model()
+        buf = eng.empty((M,), torch.float32)
+        for _ in range(3):
+            eng.score_pool(model, pool, M, scores=buf)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            eng.score_pool(model, pool, M, scores=buf)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 10
+        # parity on a slice
+        S = 2000
+        st = gp_oracle.gp_fit(train, y.numpy().astype(np.float64), h_candidates=(2,), oa=oa, optimize_lik=True)
+        sub = CellBatch.from_records(pool[:S].cpu().numpy(), train.n_max)
+        mu, var = gp_oracle.gp_predict_diag(st, train, sub)
+        ei = gp_oracle.expected_improvement(mu, var, gp_oracle.incumbent(st))
+        _, _, _, sc = eng.score_pool(model, pool[:S].contiguous(), S, want64=True)
+        err = float(np.max(np.abs(sc.cpu().numpy() - ei) / (np.abs(ei) + 1e-12)))
+        out["family%d_n%d_oa%d" % (fam, n, int(oa))] = {"ms": ms, "cand_per_s": M / ms * 1e3, "n_features": model.n_features,
+                                                      "max_rel_err_ei": err}
+print(json.dumps(out))
