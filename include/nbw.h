@@ -231,6 +231,16 @@ int nbw_model_build_table(nbw_ctx* ctx, const uint64_t* uniq_keys, const uint64_
 int nbw_score_pool(nbw_ctx* ctx, const nbw_model* model_h, const void* cells, int64_t n_cells,
                    float* scores, double* mu64, double* var64, double* score64, void* stream);
 
+/* Host-buffer form of nbw_score_pool — the call a host-side plugin makes: `cells_h` are packed
+ * records in HOST memory (pinned memory gives full overlap), `scores_h` (optional) receives the
+ * acquisition values in host memory, `scores_dev` [M] keeps them on the device for nbw_topk.  The
+ * pool is cut into `chunks` pieces; the H2D copy of piece i+1, the kernel on piece i and the D2H copy
+ * of piece i-1 overlap on internal streams.  Enqueues only: `stream` is made to wait for the last
+ * D2H copy, so a following call that syncs (nbw_topk) also completes scores_h. */
+int nbw_score_pool_host(nbw_ctx* ctx, const nbw_model* model_h, const void* cells_h,
+                        int64_t n_cells, float* scores_h, float* scores_dev, int chunks,
+                        void* stream);
+
 /* Pool-side features only (test/diagnostic use): restricted dense feature rows
  * phi [M x ld_phi] int8 (columns < n_features) and self-similarity k_cc [M] i32. */
 int nbw_pool_features(nbw_ctx* ctx, const nbw_model* model_h, const void* cells,

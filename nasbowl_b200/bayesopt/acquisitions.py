@@ -96,7 +96,7 @@ class GraphExpectedImprovement(BaseAcquisition):
             # fewer than top_n distinct values: the reference falls back to plain top-k (:106-108)
             vals, indices = eng.topk(scores, top_n, distinct=False)
         if host_scores is not None:
-            eis = host_scores.numpy().reshape(-1, 1).copy()
+            eis = host_scores.numpy().reshape(-1, 1)       # view of a pinned block owned by this result
         else:
             eis = scores.cpu().numpy().reshape(-1, 1)
         if isinstance(candidates, (CellBatch, torch.Tensor)):

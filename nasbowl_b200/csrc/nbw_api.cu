@@ -35,6 +35,16 @@ extern "C" int nbw_create(nbw_ctx** out, int device) {
 extern "C" int nbw_destroy(nbw_ctx* ctx) {
   if (!ctx) return NBW_OK;
   if (ctx->scratch) cudaFree(ctx->scratch);
+  if (ctx->pipe_ready) {
+    cudaStreamDestroy(ctx->s_in);
+    cudaStreamDestroy(ctx->s_out);
+    for (int i = 0; i < 2; ++i) {
+      cudaEventDestroy(ctx->ev_ready[i]);
+      cudaEventDestroy(ctx->ev_free[i]);
+      cudaEventDestroy(ctx->ev_done[i]);
+      if (ctx->stage[i]) cudaFree(ctx->stage[i]);
+    }
+  }
   delete ctx;
   return NBW_OK;
 }

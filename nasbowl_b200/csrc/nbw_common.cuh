@@ -16,6 +16,12 @@ struct nbw_ctx {
   size_t scratch_bytes;
   uint64_t launches;
   void* encode_tiled;   // cuTensorMapEncodeTiled, resolved lazily (gram_i8.cu)
+  // host-buffer pipeline of nbw_score_pool_host (score_pool.cu), created on first use
+  cudaStream_t s_in, s_out;
+  cudaEvent_t ev_ready[2], ev_free[2], ev_done[2];
+  void* stage[2];
+  size_t stage_bytes;
+  int pipe_ready;
 };
 
 #define NBW_FAIL(ctx, code, ...)                                  \

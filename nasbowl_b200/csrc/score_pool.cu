@@ -392,3 +392,75 @@ extern "C" int nbw_pool_features(nbw_ctx* ctx, const nbw_model* model_h, const v
     return launch_levels<8, 1>(ctx, *model_h, c, n_cells, nullptr, nullptr, nullptr, nullptr, phi, ld_phi, self_sim, st);
   return launch_levels<16, 1>(ctx, *model_h, c, n_cells, nullptr, nullptr, nullptr, nullptr, phi, ld_phi, self_sim, st);
 }
+
+// Host-buffer form: the pool lives in host memory (pinned for full overlap).  Chunk i+1's H2D copy,
+// chunk i's kernel and chunk i-1's D2H copy of the scores run on three streams.
+extern "C" int nbw_score_pool_host(nbw_ctx* ctx, const nbw_model* model_h, const void* cells_h, int64_t n_cells,
+                                   float* scores_h, float* scores_dev, int chunks, void* stream) {
+  if (!ctx) return NBW_ERR_INVALID;
+  int rc = check_model(ctx, model_h, true);
+  if (rc) return rc;
+  NBW_REQUIRE(ctx, n_cells >= 0 && chunks >= 1 && chunks <= 64, "bad n_cells / chunks");
+  if (n_cells == 0) return NBW_OK;
+  NBW_REQUIRE(ctx, cells_h && scores_dev, "null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t rec = model_h->n_max == 8 ? 16 : 48;
+  if (!ctx->pipe_ready) {
+    NBW_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+    NBW_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      NBW_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_ready[i], cudaEventDisableTiming));
+      NBW_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming));
+      NBW_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
+      ctx->stage[i] = nullptr;
+    }
+    ctx->stage_bytes = 0;
+    ctx->pipe_ready = 1;
+  }
+  const int64_t per = (n_cells + chunks - 1) / chunks;
+  const size_t need = (size_t)per * rec;
+  if (need > ctx->stage_bytes) {
+    NBW_CUDA(ctx, cudaDeviceSynchronize());
+    for (int i = 0; i < 2; ++i) {
+      if (ctx->stage[i]) NBW_CUDA(ctx, cudaFree(ctx->stage[i]));
+      NBW_CUDA(ctx, cudaMalloc(&ctx->stage[i], need));
+    }
+    ctx->stage_bytes = need;
+  }
+  // the side streams start after whatever the caller queued on `stream`
+  NBW_CUDA(ctx, cudaEventRecord(ctx->ev_done[0], st));
+  NBW_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_done[0], 0));
+  NBW_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_done[0], 0));
+  const uint8_t* src = static_cast<const uint8_t*>(cells_h);
+  for (int c = 0; c < chunks; ++c) {
+    const int64_t lo = (int64_t)c * per, hi = (lo + per < n_cells) ? lo + per : n_cells;
+    if (lo >= hi) break;
+    const int b = c & 1;
+    if (c >= 2) NBW_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_free[b], 0));   // kernel of chunk c-2 has read it
+    NBW_CUDA(ctx, cudaMemcpyAsync(ctx->stage[b], src + lo * rec, (size_t)(hi - lo) * rec, cudaMemcpyHostToDevice, ctx->s_in));
+    NBW_CUDA(ctx, cudaEventRecord(ctx->ev_ready[b], ctx->s_in));
+    NBW_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_ready[b], 0));
+    const uint8_t* dev = static_cast<const uint8_t*>(ctx->stage[b]);
+    if (model_h->n_max == 8) {
+      const bool prefix = model_h->H != nullptr && !model_h->oa;
+      rc = prefix ? launch_levels<8, 2>(ctx, *model_h, dev, hi - lo, scores_dev + lo, nullptr, nullptr, nullptr, nullptr, 0, nullptr, st)
+                  : launch_levels<8, 0>(ctx, *model_h, dev, hi - lo, scores_dev + lo, nullptr, nullptr, nullptr, nullptr, 0, nullptr, st);
+    } else {
+      const bool prefix = model_h->H != nullptr && !model_h->oa;
+      rc = prefix ? launch_levels<16, 2>(ctx, *model_h, dev, hi - lo, scores_dev + lo, nullptr, nullptr, nullptr, nullptr, 0, nullptr, st)
+                  : launch_levels<16, 0>(ctx, *model_h, dev, hi - lo, scores_dev + lo, nullptr, nullptr, nullptr, nullptr, 0, nullptr, st);
+    }
+    if (rc) return rc;
+    NBW_CUDA(ctx, cudaEventRecord(ctx->ev_free[b], st));
+    if (scores_h) {
+      NBW_CUDA(ctx, cudaEventRecord(ctx->ev_done[b], st));
+      NBW_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_done[b], 0));
+      NBW_CUDA(ctx, cudaMemcpyAsync(scores_h + lo, scores_dev + lo, (size_t)(hi - lo) * sizeof(float),
+                                    cudaMemcpyDeviceToHost, ctx->s_out));
+    }
+  }
+  // the caller's stream continues (e.g. nbw_topk on scores_dev) once the D2H copies are done
+  NBW_CUDA(ctx, cudaEventRecord(ctx->ev_done[0], ctx->s_out));
+  NBW_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_done[0], 0));
+  return NBW_OK;
+}

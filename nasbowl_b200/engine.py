@@ -322,49 +322,23 @@ class Engine:
         return scores, mu, var, sc
 
     def score_host_pool(self, model: "_lib.Model", host_cells: torch.Tensor, chunks: int = 8):
-        """Score a pool that lives in HOST memory: the H2D copy of chunk i+1, the kernel on chunk i
-        and the D2H copy of chunk i-1's scores overlap on three streams.  Returns (scores on the
-        device [M] f32, scores on the host (pinned) [M] f32); the caller synchronises."""
+        """Score a pool that lives in HOST memory through nbw_score_pool_host: the H2D copy of
+        chunk i+1, the kernel on chunk i and the D2H copy of chunk i-1's scores overlap.  Returns
+        (scores on the device [M] f32, scores in pinned host memory [M] f32); the host copy is
+        complete after the next call that syncs the stream (e.g. topk)."""
         assert not host_cells.is_cuda and host_cells.dtype == torch.uint8 and host_cells.dim() == 2
-        M, stride = host_cells.shape
-        if not host_cells.is_pinned():
-            host_cells = host_cells.pin_memory()
+        host_cells = host_cells.contiguous()
+        M = host_cells.shape[0]
         st = self._host_state = getattr(self, "_host_state", None) or {}
-        key = (M, stride, chunks)
-        if st.get("key") != key:
-            per = (M + chunks - 1) // chunks
-            st.update(key=key, per=per, s_in=torch.cuda.Stream(self.device), s_out=torch.cuda.Stream(self.device),
-                      bufs=[self.empty((per, stride), torch.uint8) for _ in range(2)],
-                      scores=self.empty((M,), torch.float32),
-                      host_scores=torch.empty((M,), dtype=torch.float32).pin_memory(),
-                      free=[torch.cuda.Event(), torch.cuda.Event()])
-        per, s_in, s_out, bufs, scores, host_scores = (st["per"], st["s_in"], st["s_out"], st["bufs"], st["scores"],
-                                                       st["host_scores"])
-        s_c = torch.cuda.current_stream(self.device)
-        s_in.wait_stream(s_c)
-        s_out.wait_stream(s_c)
-        for c in range(chunks):
-            lo, hi = c * per, min(M, (c + 1) * per)
-            if lo >= hi:
-                break
-            buf = bufs[c % 2]
-            with torch.cuda.stream(s_in):
-                if c >= 2:
-                    s_in.wait_event(st["free"][c % 2])          # the kernel that read this buffer is done
-                buf[:hi - lo].copy_(host_cells[lo:hi], non_blocking=True)
-                ready = torch.cuda.Event()
-                ready.record(s_in)
-            s_c.wait_event(ready)
-            self._check(self.lib.nbw_score_pool(self.ctx, C.byref(model), self._p(buf), hi - lo,
-                                                self._p(scores[lo:hi]), None, None, None, self.stream))
-            st["free"][c % 2].record(s_c)
-            done = torch.cuda.Event()
-            done.record(s_c)
-            with torch.cuda.stream(s_out):
-                s_out.wait_event(done)
-                host_scores[lo:hi].copy_(scores[lo:hi], non_blocking=True)
-        s_c.wait_stream(s_out)
-        return scores, host_scores
+        if st.get("M") != M:
+            st.update(M=M, scores=self.empty((M,), torch.float32))
+        # a fresh pinned block per call (torch's caching host allocator recycles them): the caller
+        # owns the returned scores, nothing is overwritten by the next pool
+        host_scores = torch.empty((M,), dtype=torch.float32, pin_memory=True)
+        self._check(self.lib.nbw_score_pool_host(self.ctx, C.byref(model), C.c_void_p(host_cells.data_ptr()), M,
+                                                 C.c_void_p(host_scores.data_ptr()), self._p(st["scores"]),
+                                                 max(1, min(chunks, M)), self.stream))
+        return st["scores"], host_scores
 
     def pool_features(self, model: "_lib.Model", cells: torch.Tensor, n_cells: int):
         ld = _round_up(model.n_features, 16)
