@@ -279,6 +279,14 @@ int nbw_topk_merge(nbw_ctx* ctx, const void* cands, int64_t count, int k, int di
 int nbw_generate_cells(nbw_ctx* ctx, int family, uint64_t seed, int64_t first_index,
                        int64_t n_cells, void* cells, void* stream);
 
+/* BANANAS-style mutation pool (bayesopt/generate_test_graphs.py:393-539, NB101 branch): child i is
+ * an edit of parents[(first_index + i) % n_parents] — every possible edge flips with probability
+ * ~1/vertice, every interior op changes with probability ~1/(vertice-2), then `prune`; children with
+ * <= 3 nodes or > 9 edges are re-drawn (64 attempts, then a random cell).  The reference's
+ * isomorphism de-duplication (a host-side graph search) is not reproduced.  family must be 0. */
+int nbw_mutate_cells(nbw_ctx* ctx, int family, const void* parents, int64_t n_parents, uint64_t seed,
+                     int64_t first_index, int64_t n_children, void* cells, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -96,6 +96,7 @@ _PROTOTYPES = {
     "nbw_topk_merge": (C.c_int, [_vp, _vp, _i64, _i32, _i32, C.POINTER(C.c_float), C.POINTER(_i64),
                                  C.POINTER(_i32), _vp]),
     "nbw_generate_cells": (C.c_int, [_vp, _i32, _u64, _i64, _i64, _vp, _vp]),
+    "nbw_mutate_cells": (C.c_int, [_vp, _i32, _vp, _i64, _u64, _i64, _i64, _vp, _vp]),
 }
 EXPORTED = tuple(_PROTOTYPES)
 

@@ -189,6 +189,75 @@ __device__ void gen_darts(uint64_t state, uint8_t* rec) {
   }
 }
 
+// BANANAS-style mutation of pruned NB101 cells (generate_test_graphs.py:437-456, 486-492):
+// every possible edge flips with probability ~1/vertice, every interior op changes with
+// probability ~1/(vertice-2); prune; reject <= 3 nodes or > 9 edges; after 64 failed attempts
+// fall back to a random cell.  Bit-identical to synth.mutate_cells_host.
+__global__ void __launch_bounds__(256)
+mutate_nb101_kernel(const uint8_t* __restrict__ parents, int64_t n_parents, uint64_t seed, int64_t first_index,
+                    int64_t n_children, uint8_t* __restrict__ cells) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_children; i += stride) {
+    const int64_t idx = first_index + i;
+    const uint8_t* par = parents + (idx % n_parents) * 16;
+    uint8_t p_ops[8];
+    uint32_t p_succ[8];
+    int vertice = 0;
+    for (int v = 0; v < 8; ++v) {
+      p_ops[v] = par[v];
+      p_succ[v] = par[8 + v];
+      if (par[v] != 0xFF) ++vertice;
+    }
+    __align__(16) uint8_t rec[16];
+    bool done = false;
+    if (vertice > 2) {
+      const uint64_t state = nbw_mix_a((seed ^ 0x6D75746174650000ull) + kGold * (uint64_t)(idx + 1));
+      for (uint32_t attempt = 0; attempt < 64 && !done; ++attempt) {
+        uint64_t d[5];
+        for (int t = 0; t < 5; ++t) d[t] = gen_draw(state, attempt, t);
+        uint32_t succ[8];
+        uint8_t ops[8];
+        for (int v = 0; v < 8; ++v) { succ[v] = p_succ[v]; ops[v] = p_ops[v]; }
+        int e = 0;
+        for (int src = 0; src < vertice - 1; ++src)
+          for (int dst = src + 1; dst < vertice; ++dst, ++e)
+            if (below(d[e >> 3], (uint32_t)vertice, e & 7) == 0) succ[src] ^= 1u << dst;
+        for (int ind = 1; ind < vertice - 1; ++ind) {
+          if (below(d[3], (uint32_t)(vertice - 2), ind - 1) == 0) {
+            const uint32_t pick = below(d[4], 2, ind - 1);
+            uint8_t avail[2];
+            int na = 0;
+            for (uint8_t o = 2; o <= 4; ++o)
+              if (o != p_ops[ind]) avail[na++] = o;
+            ops[ind] = avail[pick];
+          }
+        }
+        const int out = vertice - 1;
+        uint32_t fwd = 1u;
+        for (int v = 1; v < vertice; ++v) {
+          bool hit = false;
+          for (int u = 0; u < v; ++u) hit |= ((fwd >> u) & 1u) && ((succ[u] >> v) & 1u);
+          if (hit) fwd |= 1u << v;
+        }
+        uint32_t bwd = 1u << out;
+        for (int v = out - 1; v >= 0; --v)
+          if (succ[v] & bwd) bwd |= 1u << v;
+        const uint32_t keep = fwd & bwd;
+        if (keep == 0) continue;
+        int n_edges = 0;
+        for (int v = 0; v < vertice; ++v)
+          if ((keep >> v) & 1u) n_edges += __popc(succ[v] & keep);
+        if (__popc(keep) <= 3 || n_edges > 9) continue;
+        write_compact<8>(rec, ops, succ, keep, vertice);
+        done = true;
+      }
+    }
+    if (!done) gen_nb101(nbw_mix_a((seed ^ 0x66616C6C6261636Bull) + kGold * (uint64_t)(idx + 1)), rec);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(rec);
+    *reinterpret_cast<uint4*>(cells + i * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 generate_cells_kernel(int family, uint64_t seed, int64_t first_index, int64_t n_cells, uint8_t* __restrict__ cells) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -217,6 +286,19 @@ extern "C" int nbw_generate_cells(nbw_ctx* ctx, int family, uint64_t seed, int64
   NBW_REQUIRE(ctx, cells != nullptr && (reinterpret_cast<uintptr_t>(cells) & 15) == 0, "cells must be 16-byte aligned");
   generate_cells_kernel<<<nbw_grid_for(ctx, n_cells, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       family, seed, first_index, n_cells, static_cast<uint8_t*>(cells));
+  NBW_CHECK_LAUNCH(ctx);
+  return NBW_OK;
+}
+
+extern "C" int nbw_mutate_cells(nbw_ctx* ctx, int family, const void* parents, int64_t n_parents, uint64_t seed,
+                                int64_t first_index, int64_t n_children, void* cells, void* stream) {
+  if (!ctx) return NBW_ERR_INVALID;
+  NBW_REQUIRE(ctx, family == 0, "mutation is implemented for NAS-Bench-101 cells (NB201 / DARTS need the unpruned encoding)");
+  NBW_REQUIRE(ctx, n_parents > 0 && n_children >= 0 && first_index >= 0, "bad range");
+  if (n_children == 0) return NBW_OK;
+  NBW_REQUIRE(ctx, parents && cells && (reinterpret_cast<uintptr_t>(cells) & 15) == 0, "null / misaligned pointer");
+  mutate_nb101_kernel<<<nbw_grid_for(ctx, n_children, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint8_t*>(parents), n_parents, seed, first_index, n_children, static_cast<uint8_t*>(cells));
   NBW_CHECK_LAUNCH(ctx);
   return NBW_OK;
 }

@@ -383,3 +383,10 @@ class Engine:
         self._check(self.lib.nbw_generate_cells(self.ctx, family, C.c_uint64(seed), first_index, n_cells,
                                                 self._p(cells), self.stream))
         return cells
+
+    def mutate_cells(self, family: int, parents: torch.Tensor, seed: int, first_index: int, n_children: int) -> torch.Tensor:
+        """BANANAS-style mutation pool on the device (nbw_mutate_cells); parents are device records."""
+        cells = self.empty((n_children, 16), torch.uint8)
+        self._check(self.lib.nbw_mutate_cells(self.ctx, family, self._p(parents), parents.shape[0], C.c_uint64(seed),
+                                              first_index, n_children, self._p(cells), self.stream))
+        return cells

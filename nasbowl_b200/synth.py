@@ -219,6 +219,83 @@ def _darts_cell(seed, idx):
         return _compact(ops, succ, keep, n)
 
 
+# ------------------------------------------------------------------------------- NB101 mutation
+MUTATION_ATTEMPTS = 64
+
+
+def apply_mutation_nb101(ops, succ, vertice, flip_mask, new_ops):
+    """One BANANAS-style edit of a pruned NB101 cell (generate_test_graphs.py:437-456): XOR the
+    upper-triangular adjacency with `flip_mask` (bit e = e-th (src<dst) pair in row-major order),
+    replace interior ops by `new_ops` (dict node -> op code), prune.  Returns the packed child
+    (labels, masks) or None when input and output are disconnected."""
+    succ = list(succ[:vertice])
+    ops = list(ops[:vertice])
+    e = 0
+    for src in range(vertice - 1):
+        for dst in range(src + 1, vertice):
+            if (flip_mask >> e) & 1:
+                succ[src] ^= 1 << dst
+            e += 1
+    for v, o in new_ops.items():
+        ops[v] = o
+    out = vertice - 1
+    fwd = 1
+    for v in range(1, vertice):
+        if any((fwd >> u) & 1 and (succ[u] >> v) & 1 for u in range(v)):
+            fwd |= 1 << v
+    bwd = 1 << out
+    for v in range(out - 1, -1, -1):
+        if succ[v] & bwd:
+            bwd |= 1 << v
+    keep = fwd & bwd
+    if keep == 0:
+        return None
+    return _compact(ops, succ, keep, vertice)
+
+
+def _mutate_nb101_cell(seed, idx, p_labels, p_succ):
+    vertice = sum(1 for l in p_labels if l != NO_NODE)
+    if vertice > 2:
+        for attempt in range(MUTATION_ATTEMPTS):
+            d = [draw(seed ^ 0x6D75746174650000, idx, attempt, t) for t in range(5)]
+            flip = 0
+            n_pairs = vertice * (vertice - 1) // 2
+            for e in range(n_pairs):                       # each possible edge flips w.p. ~1/vertice
+                if _below(d[e // 8], vertice, e % 8) == 0:
+                    flip |= 1 << e
+            new_ops = {}
+            for ind in range(1, vertice - 1):              # each interior op mutates w.p. ~1/(vertice-2)
+                if _below(d[3], vertice - 2, ind - 1) == 0:
+                    avail = [o for o in (2, 3, 4) if o != p_labels[ind]]
+                    new_ops[ind] = avail[_below(d[4], 2, ind - 1)]
+            child = apply_mutation_nb101(p_labels, p_succ, vertice, flip, new_ops)
+            if child is None:
+                continue
+            labels, masks = child
+            n_nodes = sum(1 for l in labels if l != NO_NODE)
+            n_edges = sum(bin(m).count("1") for m in masks)
+            if n_nodes <= 3 or n_edges > 9:                # generate_test_graphs.py:486-492
+                continue
+            return labels, masks
+    return _nb101_cell(seed ^ 0x66616C6C6261636B, idx)     # patience exhausted: a random cell (:529-535)
+
+
+def mutate_cells_host(family: int, parents: CellBatch, seed: int, first_index: int, n_children: int) -> CellBatch:
+    """Host twin of nbw_mutate_cells: child i is an edit of parent i % n_parents."""
+    if family != 0:
+        raise NotImplementedError("mutation needs the unpruned encoding for NB201 / DARTS cells")
+    labels = np.full((n_children, 8), NO_NODE, dtype=np.uint8)
+    succ = np.zeros((n_children, 8), dtype=np.uint16)
+    npar = len(parents)
+    for i in range(n_children):
+        p = (first_index + i) % npar
+        l, m = _mutate_nb101_cell(seed, first_index + i, [int(x) for x in parents.labels[p]],
+                                  [int(x) for x in parents.succ[p]])
+        labels[i] = l[:8]
+        succ[i] = m[:8]
+    return CellBatch(8, labels, succ)
+
+
 _GEN = {0: _nb101_cell, 1: _nb201_cell, 2: _darts_cell}
 
 

@@ -477,3 +477,14 @@ def test_host_pool_pipeline_matches_resident_path(eng):
         assert np.array_equal(eis_d, eis_h) and np.array_equal(eis_d, eis_p)
         assert np.array_equal(idx_d, idx_h) and np.array_equal(idx_d, idx_p)
         assert eis_h.shape == (M, 1) and eis_h.dtype == np.float32
+
+
+def test_device_mutation_pool_matches_host(eng):
+    par = synth.generate_cells_host(0, 3, 0, 12)
+    dev_par = eng.upload_cells(par)
+    host = synth.mutate_cells_host(0, par, 7, 500, 3000)
+    dev = eng.mutate_cells(0, dev_par, 7, 500, 3000).cpu().numpy()
+    assert np.array_equal(dev, host.to_records())
+    a = eng.mutate_cells(0, dev_par, 7, 500, 1000).cpu().numpy()
+    b = eng.mutate_cells(0, dev_par, 7, 1500, 2000).cpu().numpy()
+    assert np.array_equal(np.concatenate([a, b]), dev)

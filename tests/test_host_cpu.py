@@ -282,3 +282,51 @@ def test_two_rank_gloo_broadcast_and_topk(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
     assert "rank 0 ok" in outs[0] and "rank 1 ok" in outs[1]
+
+
+def test_mutation_pool_host_twin():
+    """BANANAS-style NB101 mutation: children are valid cells, the edit+prune step agrees with
+    the reference's `prune` (generate_test_graphs.py:26-78,437-456) for arbitrary edits."""
+    import random
+    par = synth.generate_cells_host(0, 3, 0, 12)
+    ch = synth.mutate_cells_host(0, par, 7, 100, 400)
+    again = synth.mutate_cells_host(0, par, 7, 100, 400)
+    assert np.array_equal(ch.to_records(), again.to_records())
+    assert ch.n_edges.max() <= 9 and ch.n_edges.min() >= 1 and ch.n_nodes.max() <= 7
+    assert (ch.n_nodes >= 4).mean() > 0.9                     # the rest are random fall-back cells
+    assert not np.array_equal(ch.to_records()[:12], par.to_records())
+    with pytest.raises(NotImplementedError):
+        synth.mutate_cells_host(1, par, 7, 0, 4)
+    from oracle.ref_import import load_reference, reference_available
+    if not reference_available():
+        return
+    import networkx as nx
+    R = load_reference()
+    rng = random.Random(0)
+    for _ in range(300):
+        p = rng.randrange(len(par))
+        labels, succ = [int(x) for x in par.labels[p]], [int(x) for x in par.succ[p]]
+        v = sum(1 for l in labels if l != NO_NODE)
+        if v <= 2:
+            continue
+        pairs = v * (v - 1) // 2
+        flip = rng.getrandbits(pairs) & rng.getrandbits(pairs)
+        new_ops = {i: rng.choice([o for o in (2, 3, 4) if o != labels[i]]) for i in range(1, v - 1) if rng.random() < 0.4}
+        mine = synth.apply_mutation_nb101(labels, succ, v, flip, new_ops)
+        adj = np.array([[(succ[s] >> d) & 1 for d in range(v)] for s in range(v)], dtype=np.int8)
+        e = 0
+        for s in range(v - 1):
+            for d in range(s + 1, v):
+                if (flip >> e) & 1:
+                    adj[s, d] = 1 - adj[s, d]
+                e += 1
+        ops = [synth.NB101_OPS[new_ops.get(i, labels[i])] for i in range(v)]
+        res = R.gtg.prune(adj, ops)
+        if res is None:
+            assert mine is None
+        else:
+            G = nx.from_numpy_array(res[0], create_using=nx.DiGraph)
+            for i, nm in enumerate(res[1]):
+                G.nodes[i]['op_name'] = nm
+            rb = pack_networkx([G], OpVocab(synth.NB101_OPS))
+            assert mine is not None and list(rb.labels[0]) == mine[0][:8] and list(rb.succ[0]) == mine[1][:8]
