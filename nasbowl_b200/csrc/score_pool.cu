@@ -148,9 +148,11 @@ score_pool_kernel(const ScoreParams P, const uint8_t* __restrict__ cells, int64_
 
     // ---- level 0: op code -> dense id (weisfeiler_lehman.py:430-441 in transform form)
     uint64_t id64;
+    bool in_dict;   // label of the previous level is in the dictionary: only then can the next one be
     {
       const uint32_t d0 = present ? (uint32_t)__ldg(M.level0_table + label) : 0xFFFFu;
       const bool seen = present && d0 != 0xFFFFu;
+      in_dict = seen;
       id64 = seen ? (uint64_t)d0 : (NBW_UNSEEN_BIT | (uint64_t)label);
       class_count_rank<NMAX>(id64, present, lane, sub_base, cnt[0], rk[0]);
       if (PREFIX) { if (seen) deep = M.label_off[0] + (int)d0; }
@@ -170,7 +172,9 @@ score_pool_kernel(const ScoreParams P, const uint8_t* __restrict__ cells, int64_
       const uint32_t chk = nbw_chk_from(hb, sum_b, salt);
       uint32_t dense = 0;
       bool seen = false;
-      if (endpoint) seen = table_probe(static_cast<const uint4*>(M.table[l]), M.table_mask[l], key, chk, dense);
+      if (endpoint && in_dict)
+        seen = table_probe(static_cast<const uint4*>(M.table[l]), M.table_mask[l], key, chk, dense);
+      in_dict = seen;
       id64 = seen ? (uint64_t)dense : (NBW_UNSEEN_BIT | key);
       class_count_rank<NMAX>(id64, endpoint, lane, sub_base, cnt[l], rk[l]);
       if (PREFIX) { if (endpoint && seen) deep = M.label_off[l] + (int)dense; }

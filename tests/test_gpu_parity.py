@@ -488,3 +488,46 @@ def test_device_mutation_pool_matches_host(eng):
     a = eng.mutate_cells(0, dev_par, 7, 500, 1000).cpu().numpy()
     b = eng.mutate_cells(0, dev_par, 7, 1500, 2000).cpu().numpy()
     assert np.array_equal(np.concatenate([a, b]), dev)
+
+
+def _random_dags(rng, n_cells, n_max, n_ops, p_edge, allow_isolated=True):
+    """Arbitrary labelled DAGs (not sampler-shaped): random sizes, dense / sparse adjacency,
+    isolated nodes, duplicate cells — the edge cases of the WL relabelling rules."""
+    lab = np.full((n_cells, n_max), NO_NODE, np.uint8)
+    suc = np.zeros((n_cells, n_max), np.uint16)
+    for i in range(n_cells):
+        k = rng.randint(1, n_max + 1)
+        lab[i, :k] = rng.randint(0, n_ops, size=k)
+        perm = rng.permutation(k)                  # edges follow a hidden topological order
+        for a in range(k):
+            for b in range(a + 1, k):
+                if rng.rand() < p_edge:
+                    suc[i, perm[a]] |= np.uint16(1 << perm[b])
+        if not allow_isolated:
+            continue
+    return CellBatch(n_max, lab, suc)
+
+
+@pytest.mark.parametrize("n_max,p_edge", [(8, 0.15), (8, 0.6), (8, 1.0), (16, 0.1), (16, 0.45)])
+def test_random_dags_exact_wl_and_posterior(eng, n_max, p_edge):
+    from nasbowl_b200.bayesopt import GraphGP
+    from nasbowl_b200.kernels import WeisfilerLehman
+    rng = np.random.RandomState(int(n_max * 100 + p_edge * 10))
+    train = _random_dags(rng, 120, n_max, 6, p_edge)
+    pool = CellBatch.concat([_random_dags(rng, 400, n_max, 7, p_edge), train[:20]])   # op 6 is unseen in training
+    for oa in (False, True):
+        for h in (1, 4, 7):
+            fit = eng.wl_fit(eng.upload_cells(train), n_max, h, oa)
+            _, dims = wl_oracle.wl_labels_fast(train, h)
+            assert fit.dims == dims
+            K = eng.gram(fit.phi, fit.phi, 0, fit.k_end(h)).cpu().numpy()
+            assert np.array_equal(K, wl_oracle.gram_raw(train, h, oa))
+        y = rng.randn(len(train))
+        gp = GraphGP(train, torch.tensor(y), [WeisfilerLehman(h=2, oa=oa)])
+        gp.fit(wl_subtree_candidates=(0, 1, 2, 3, 4), optimize_lik=True)
+        st = gp_oracle.gp_fit(train, y, h_candidates=(0, 1, 2, 3, 4), oa=oa, optimize_lik=True)
+        assert gp.kernels[0].h == st.h
+        mu, var = gp.predict_diag(pool)
+        mu_o, var_o = gp_oracle.gp_predict_diag(st, train, pool)
+        np.testing.assert_allclose(mu.numpy(), mu_o, rtol=RTOL64, atol=1e-9)
+        np.testing.assert_allclose(var.numpy(), var_o, rtol=RTOL64, atol=1e-12)
