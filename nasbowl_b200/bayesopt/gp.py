@@ -289,19 +289,27 @@ class GraphGP:
         # the normalisation of K uses diag(w * K_raw): s already contains 1/sqrt(w K_raw,ii)
         B = eng.empty((n, D), torch.float64)
         eng.scale_features(fit.phi, 0, D, d['s'], math.sqrt(w), B, D)
-        Wt = eng.empty((n, D), torch.float64)
-        eng.gemm(False, False, n, D, n, 1.0, d['Linv'], n, B, D, 0.0, Wt, D)
-        # one extra all-zero row/column: the landing slot of labels outside the dictionary
-        G = torch.zeros((D + 1, D + 1), dtype=torch.float64, device=eng.device)
-        eng.gemm(True, False, D, D, n, 1.0, Wt, D, Wt, D, 0.0, G, D + 1)
-        w_mu = torch.zeros((D + 1,), dtype=torch.float64, device=eng.device)
-        eng.gemm(True, False, D, 1, n, 1.0, B, D, d['alpha'], 1, 0.0, w_mu, 1)
+        Linv, alpha = d['Linv'], d['alpha']
+
+        def build_general():
+            """G and w_mu over feature columns: needed by the oa kernel and by the general path of
+            the linear kernel; the prefix form below does not use them, so they are built lazily."""
+            Wt = eng.empty((n, D), torch.float64)
+            eng.gemm(False, False, n, D, n, 1.0, Linv, n, B, D, 0.0, Wt, D)
+            # one extra all-zero row/column: the landing slot of labels outside the dictionary
+            G = torch.zeros((D + 1, D + 1), dtype=torch.float64, device=eng.device)
+            eng.gemm(True, False, D, D, n, 1.0, Wt, D, Wt, D, 0.0, G, D + 1)
+            w_mu = torch.zeros((D + 1,), dtype=torch.float64, device=eng.device)
+            eng.gemm(True, False, D, 1, n, 1.0, B, D, alpha, 1, 0.0, w_mu, 1)
+            return G, w_mu
         # incumbent: y_raw[argmax of the posterior mean at the training points] (acquisitions.py:82-92)
         mu_train = eng.empty((n,), torch.float64)
         eng.gemm(False, False, n, 1, n, 1.0, d['K'], n, d['alpha'], 1, 0.0, mu_train, 1)
         inc_idx = int(np.argmax(mu_train.cpu().numpy()))
         pm = PoolModel.from_fit(eng, fit, h)
-        pm.G, pm.w_mu = G, w_mu
+        pm.general_builder = build_general
+        if fit.oa:
+            pm.G, pm.w_mu = build_general()
         if not fit.oa:
             # prefix form (nbw_model.H): the same operators summed over ancestor chains of labels
             T = fit.label_off[h + 1]

@@ -36,6 +36,7 @@ class PoolModel:
         self.H: Optional[torch.Tensor] = None                # fp64 [T + 1, T + 1] (linear kernel only)
         self.w_mu_prefix: Optional[torch.Tensor] = None      # fp64 [T + 1]
         self.use_prefix = True                               # False forces the general G path
+        self.general_builder = None                          # builds (G, w_mu) on demand (fitting rank only)
         self.lik = 0.0
         self.y_mean = 0.0
         self.y_std = 1.0
@@ -73,10 +74,17 @@ class PoolModel:
             d.thermo_base = self.thermo_base.data_ptr()
             d.max_count = self.max_count.data_ptr()
         d.n_features = self.n_features
+        prefix = self.H is not None and self.use_prefix and not self.oa
+        if self.G is None and not prefix and not (self.H is None and self.general_builder is None):
+            # (a model with neither G, H nor a builder is dictionary-only: nbw_pool_features)
+            if self.general_builder is None:
+                raise RuntimeError("this pool model carries only the prefix operators (H); the general "
+                                   "path needs G, which only the rank that fitted the GP can build")
+            self.G, self.w_mu = self.general_builder()
         if self.G is not None:
             d.G, d.ld_g, d.w_mu = self.G.data_ptr(), self.G.stride(0), self.w_mu.data_ptr()
         d.n_labels = self.n_labels
-        if self.H is not None and self.use_prefix and not self.oa:
+        if prefix:
             d.H, d.ld_h, d.w_mu_prefix = self.H.data_ptr(), self.H.stride(0), self.w_mu_prefix.data_ptr()
         d.lik, d.y_mean, d.y_std = float(self.lik), float(self.y_mean), float(self.y_std)
         d.incumbent = float(self.incumbent if incumbent is None else incumbent)
