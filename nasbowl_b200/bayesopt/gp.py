@@ -179,6 +179,14 @@ class GraphGP:
         # 3. noise: Adam / SGD on the scalar lambda with the reference's clamp (gp.py:153-210)
         likelihood = torch.tensor(self.likelihood, )
         nlml = None
+        factor_cache = {}
+
+        def factor(lam: float):
+            """K does not depend on lambda and, with the reference's sign quirk, lambda sits at
+            max_lik from the second iteration on: identical lambdas are factored once."""
+            if lam not in factor_cache:
+                factor_cache[lam] = eng.pd_inverse(K, lam, y_dev)
+            return factor_cache[lam]
         if optimize_lik:
             likelihood.requires_grad_(True)
             assert optimizer.lower() in ['adam', 'sgd']
@@ -186,7 +194,7 @@ class GraphGP:
                                                                                          **optimizer_kwargs)
             for i in range(iters):
                 optim.zero_grad()
-                _, _, _, logdet, yKy, trKinv, alpha_sq = eng.pd_inverse(K, float(likelihood.item()), y_dev)
+                _, _, _, logdet, yKy, trKinv, alpha_sq = factor(float(likelihood.item()))
                 nlml = _nlml_from_stats(logdet, yKy, self.n)
                 # d nlml / d lambda = -(|K_l^-1 y|^2 + tr K_l^-1) / (2n): always negative (Q9)
                 likelihood.grad = torch.tensor(-(0.5 * alpha_sq + 0.5 * trKinv) / self.n, dtype=likelihood.dtype)
@@ -196,7 +204,7 @@ class GraphGP:
                 with torch.no_grad():
                     likelihood.clamp_(1e-5, max_lik)
         lik = float(likelihood.item())
-        L, Linv, alpha, logdet, yKy, _, _ = eng.pd_inverse(K, lik, y_dev)
+        L, Linv, alpha, logdet, yKy, _, _ = factor(lik)
 
         # 4. state (gp.py:212-219)
         self.weights = weights.clone() / torch.sum(weights)
