@@ -176,10 +176,41 @@ def appendix_b(R):
     return out
 
 
+def cfg1_case(R, seed=11, n_train=50, n_test=400):
+    """BASELINE.json configs[0]: nas_regression.py:78-83 on NB101-shaped cells from the reference's
+    own random_sampling — fit(optimize_lik=True) with the default h grid 0..4, predict on 400 test
+    cells, plus EI of every test cell and the proposed top-5."""
+    seed_all(seed)
+    graphs = sample_cells(R, "nasbench101", n_train + n_test)
+    vocab = OpVocab()
+    batch = pack_networkx(graphs, vocab)
+    train, test = graphs[:n_train], graphs[n_train:]
+    y = torch.randn(n_train)
+    gp = R.GraphGP(train, y.clone(), [R.WeisfilerLehman(h=2, oa=False)])
+    gp.fit(optimize_lik=True)
+    out = {"records": batch.to_records(), "n_max": np.int64(batch.n_max), "op_names": np.array(vocab.names),
+           "n_train": np.int64(n_train), "y": y.numpy().astype(np.float32)}
+    with torch.no_grad():
+        mu, cov = gp.predict(test)
+        out["gp_h"], out["gp_lik"] = np.int64(gp.kernels[0].h), np.float64(gp.likelihood)
+        out["gp_nlml"] = np.float64(gp.nlml)
+        out["gp_mu"], out["gp_var"] = mu.numpy(), np.diag(cov.numpy()).copy()
+        mu_t, cov_t = gp.predict(train)
+        out["gp_mu_train"] = mu_t.numpy()
+        ei = R.GraphExpectedImprovement(gp)
+        out["ei"] = np.array([float(ei.eval(c)) for c in test])
+        out["incumbent"] = np.float64(ei._get_incumbent())
+        _, _, idx = R.GraphExpectedImprovement(gp).propose_location(test, top_n=5)
+        out["top5"] = np.array(sorted(int(i) for i in idx), dtype=np.int64)
+    return out
+
+
+
 def main():
     R = load_reference()
     os.makedirs(OUT, exist_ok=True)
     np.savez_compressed(os.path.join(OUT, "appendix_b.npz"), **appendix_b(R))
+    np.savez_compressed(os.path.join(OUT, "cfg1_nb101.npz"), **cfg1_case(R))
     for family, seed in (("nasbench101", 101), ("nasbench201", 201), ("darts", 301)):
         case = family_case(R, family, seed)
         np.savez_compressed(os.path.join(OUT, family + ".npz"), **case)

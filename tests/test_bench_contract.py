@@ -1,0 +1,53 @@
+"""bench.py's reference arm (CPU only) honours the JSON contract; the B200 arm needs a GPU and is
+covered by the gpu-marked test below."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+REQUIRED = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+            "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"]
+
+
+def _run(args, env=None):
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + args, capture_output=True, text=True,
+                       timeout=900, env=env)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, p.stdout
+    return json.loads(lines[0])
+
+
+def test_reference_arm_json_line():
+    d = _run(["--impl", "reference", "--gpus", "1", "--steps", "2", "--warmup", "1", "--ref-sample", "300"],
+             env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    for k in REQUIRED:
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["unit"] == "candidates/s"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0 and d["vs_baseline"] is None and "workload" in d["config"]
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                       capture_output=True, text=True, timeout=120,
+                       env=dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1", CUDA_VISIBLE_DEVICES=""))
+    assert p.returncode == 0 and p.stdout.strip() == ""
+
+
+@pytest.mark.gpu
+def test_b200_arm_json_line():
+    d = _run(["--gpus", "1", "--steps", "5", "--warmup", "3", "--pool", "200000", "--cpu-sample", "1000"])
+    for k in REQUIRED + ["roofline", "clocks", "parity"]:
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["steps"] == 5 and d["value"] > 1e7 and d["gpu_launches"] >= 5
+    r = d["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 200000 * 16 and d["e2e"]["d2h_bytes_per_step"] >= 200000 * 4
+    assert d["parity"]["max_rel_err_ei_fp64"] < 1e-6 and d["parity"]["h_star_equal"]

@@ -531,3 +531,34 @@ def test_random_dags_exact_wl_and_posterior(eng, n_max, p_edge):
         mu_o, var_o = gp_oracle.gp_predict_diag(st, train, pool)
         np.testing.assert_allclose(mu.numpy(), mu_o, rtol=RTOL64, atol=1e-9)
         np.testing.assert_allclose(var.numpy(), var_o, rtol=RTOL64, atol=1e-12)
+
+
+def test_cfg1_regression_case():
+    """BASELINE.json configs[0]: GraphGP(...).fit(optimize_lik=True); predict(400 test cells)."""
+    from nasbowl_b200.bayesopt import GraphExpectedImprovement, GraphGP
+    from nasbowl_b200.kernels import WeisfilerLehman
+    z, batch = load_golden("cfg1_nb101")
+    n = int(z["n_train"])
+    train, test = batch[:n], batch[n:]
+    gp = GraphGP(train, torch.tensor(z["y"]), [WeisfilerLehman(h=2)])
+    gp.fit(optimize_lik=True)                                      # defaults: h in range(5), 20 Adam iterations
+    st = gp_oracle.gp_fit(train, z["y"].astype(np.float64), h_candidates=tuple(range(5)), optimize_lik=True)
+    assert gp.kernels[0].h == st.h == int(z["gp_h"])
+    assert np.float32(gp.likelihood) == np.float32(z["gp_lik"])
+    np.testing.assert_allclose(float(gp.nlml), st.nlml, rtol=1e-9)
+    mu, cov = gp.predict(test)                                      # reference-shaped: full 400 x 400 covariance
+    mu_o, var_o = gp_oracle.gp_predict_diag(st, train, test)
+    np.testing.assert_allclose(mu.numpy(), mu_o, rtol=RTOL64, atol=1e-9)
+    np.testing.assert_allclose(np.diag(cov.numpy()), var_o, rtol=RTOL64, atol=1e-12)
+    np.testing.assert_allclose(mu.numpy(), z["gp_mu"], rtol=2e-3, atol=2e-3)          # fp32 reference
+    mu_t, _ = gp.predict(train)
+    np.testing.assert_allclose(mu_t.numpy(), z["gp_mu_train"], rtol=2e-3, atol=2e-3)
+    acq = GraphExpectedImprovement(gp)
+    _, eis, idx = acq.propose_location(test, top_n=5)
+    np.testing.assert_allclose(eis.reshape(-1), gp_oracle.expected_improvement(mu_o, var_o, gp_oracle.incumbent(st)),
+                               rtol=RTOL32, atol=1e-9)
+    np.testing.assert_allclose(eis.reshape(-1), z["ei"], rtol=5e-2, atol=2e-3)
+    got, ref_top = set(int(i) for i in idx), set(int(i) for i in z["top5"])
+    if got != ref_top:
+        vals = [z["ei"][i] for i in got ^ ref_top]
+        assert max(vals) - min(vals) < 1e-4 * max(1.0, abs(max(vals)))

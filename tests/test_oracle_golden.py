@@ -124,3 +124,26 @@ def test_gp_fit_predict_acquisitions(family, oa, opt):
             diff = set(int(i) for i in top) ^ ref_top
             vals = [ref_ei[i] for i in diff]
             assert max(vals) - min(vals) < 1e-4 * max(1.0, abs(max(vals)))
+
+
+def test_cfg1_regression_case():
+    """BASELINE.json configs[0] (nas_regression.py:78-83): n_train=50, 400 test cells, default h grid,
+    optimize_lik=True — oracle vs the unmodified reference."""
+    z, batch = load_golden("cfg1_nb101")
+    n = int(z["n_train"])
+    train, test = batch[:n], batch[n:]
+    st = gp_oracle.gp_fit(train, z["y"].astype(np.float64), h_candidates=tuple(range(5)), optimize_lik=True)
+    assert st.h == int(z["gp_h"]) and st.lik == float(z["gp_lik"])
+    np.testing.assert_allclose(st.nlml, z["gp_nlml"], rtol=1e-4)
+    mu, var = gp_oracle.gp_predict_diag(st, train, test)
+    np.testing.assert_allclose(mu, z["gp_mu"], rtol=2e-3, atol=2e-3)
+    np.testing.assert_allclose(var, z["gp_var"], rtol=5e-2, atol=1e-3)
+    inc = gp_oracle.incumbent(st)
+    assert inc == pytest.approx(float(z["incumbent"]), rel=1e-6)
+    ei = gp_oracle.expected_improvement(mu, var, inc)
+    np.testing.assert_allclose(ei, z["ei"], rtol=5e-2, atol=2e-3)
+    top = set(int(i) for i in gp_oracle.top_n_distinct(ei, 5))
+    ref_top = set(int(i) for i in z["top5"])
+    if top != ref_top:
+        vals = [z["ei"][i] for i in top ^ ref_top]
+        assert max(vals) - min(vals) < 1e-4 * max(1.0, abs(max(vals)))
