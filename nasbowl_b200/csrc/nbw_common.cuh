@@ -191,24 +191,35 @@ __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
 }
 
 // Sums of the successors' hashes.  Each round every lane fetches ITS next successor (per-lane
-// source lane), so the trip count is the largest out-degree in the warp, not n_max.
+// source lane).  The first four rounds are unrolled without any vote or branch — the cells of
+// all three search spaces rarely exceed out-degree 4 — so their twelve shuffles are independent
+// and overlap; higher degrees fall through to a voted loop.
 template <int NMAX>
 __device__ __forceinline__ void successor_sums(uint32_t succ, int sub_base, int node, uint64_t ha, uint32_t hb,
                                                uint64_t& sum_a, uint32_t& sum_b) {
   sum_a = 0;
   sum_b = 0;
   uint32_t m = succ;
-#pragma unroll 1
-  for (int t = 0; t < NMAX; ++t) {
-    if (!__any_sync(0xffffffffu, m != 0u)) break;
-    const int j = m ? (__ffs(m) - 1) : node;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const bool has = m != 0u;
+    const int j = has ? (__ffs(m) - 1) : node;
     const uint64_t oa = shfl64(ha, sub_base + j);
     const uint32_t ob = __shfl_sync(0xffffffffu, hb, sub_base + j);
-    if (m) {
-      sum_a += oa;
-      sum_b += ob;
-      m &= m - 1u;
-    }
+    sum_a += has ? oa : 0ull;
+    sum_b += has ? ob : 0u;
+    m &= m - 1u;      // 0 stays 0
+  }
+#pragma unroll 1
+  for (int t = 4; t < NMAX; ++t) {
+    if (!__any_sync(0xffffffffu, m != 0u)) break;
+    const bool has = m != 0u;
+    const int j = has ? (__ffs(m) - 1) : node;
+    const uint64_t oa = shfl64(ha, sub_base + j);
+    const uint32_t ob = __shfl_sync(0xffffffffu, hb, sub_base + j);
+    sum_a += has ? oa : 0ull;
+    sum_b += has ? ob : 0u;
+    m &= m - 1u;
   }
 }
 

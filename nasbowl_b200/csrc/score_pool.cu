@@ -48,19 +48,54 @@ __global__ void table_insert_kernel(const uint64_t* __restrict__ uniq_keys, cons
 __device__ __forceinline__ bool table_probe(const uint4* __restrict__ table, uint32_t mask, uint64_t key,
                                             uint32_t chk, uint32_t& id) {
   uint32_t slot = slot_of(key) & mask;
-  for (uint32_t it = 0; it <= mask; ++it) {
-    const uint4 s = __ldg(table + slot);
-    const uint64_t k = ((uint64_t)s.y << 32) | s.x;
-    if (k == key) {
-      // dictionary keys are unique, so a key hit with a different check word is a label
-      // outside the dictionary
-      if (s.z == chk) { id = s.w; return true; }
-      return false;
+  // first probe without a loop: at load factor <= 1/2 it almost always decides
+  uint4 s = __ldg(table + slot);
+  uint64_t k = ((uint64_t)s.y << 32) | s.x;
+  if (k != key && k != NBW_INVALID_KEY) {
+    for (uint32_t it = 0; it < mask; ++it) {
+      slot = (slot + 1) & mask;
+      s = __ldg(table + slot);
+      k = ((uint64_t)s.y << 32) | s.x;
+      if (k == key || k == NBW_INVALID_KEY) break;
     }
-    if (k == NBW_INVALID_KEY) return false;
-    slot = (slot + 1) & mask;
   }
-  return false;
+  // dictionary keys are unique, so a key hit with a different check word is a label outside it
+  id = s.w;
+  return k == key && s.z == chk;
+}
+
+// Label classes inside a cell, tracked level by level.  WL labels refine: two nodes can share a
+// level-l label only if they shared the level-(l-1) label, so after level 0 (one shuffle sweep over
+// the op codes) each node compares itself only with the members of its previous class — usually
+// none.  (__match_any_sync on the 64-bit ids gives the same answer but costs ~40 % of this kernel.)
+// `cls` is a bitmask over the sub-warp's lanes (bit j = node j shares my label), 0 for uncounted nodes.
+template <int NMAX>
+__device__ __forceinline__ uint32_t classes_level0(uint32_t label, bool valid, int node, int sub_base) {
+  uint32_t cls = 0;
+  const uint32_t mine = valid ? label : (0x100u + (uint32_t)node);   // uncounted nodes match nobody
+#pragma unroll
+  for (int j = 0; j < NMAX; ++j) {
+    const uint32_t other = __shfl_sync(0xffffffffu, mine, sub_base + j);
+    cls |= (valid && other == mine) ? (1u << j) : 0u;
+  }
+  return cls;
+}
+template <int NMAX>
+__device__ __forceinline__ uint32_t classes_refine(uint32_t cls_prev, uint64_t id64, bool valid, int node, int lane,
+                                                   int sub_base) {
+  const uint64_t cid = valid ? id64 : (NBW_NOCLASS_BIT | (uint64_t)lane);
+  uint32_t rem = valid ? (cls_prev & ~(1u << node)) : 0u;
+  uint32_t cls = valid ? (1u << node) : 0u;
+#pragma unroll 1
+  for (int t = 0; t < NMAX; ++t) {
+    if (!__any_sync(0xffffffffu, rem != 0u)) break;
+    const bool has = rem != 0u;
+    const int j = has ? (__ffs(rem) - 1) : node;
+    const uint64_t other = shfl64(cid, sub_base + j);
+    cls |= (has && other == cid) ? (1u << j) : 0u;
+    rem &= rem - 1u;
+  }
+  return cls;
 }
 
 __device__ __forceinline__ int effective_column(const nbw_model& M, int l, bool seen, uint32_t dense, int rank) {
@@ -148,13 +183,16 @@ score_pool_kernel(const ScoreParams P, const uint8_t* __restrict__ cells, int64_
 
     // ---- level 0: op code -> dense id (weisfeiler_lehman.py:430-441 in transform form)
     uint64_t id64;
+    uint32_t cls;   // lanes of the sub-warp that share this node's label at the current level
     bool in_dict;   // label of the previous level is in the dictionary: only then can the next one be
     {
       const uint32_t d0 = present ? (uint32_t)__ldg(M.level0_table + label) : 0xFFFFu;
       const bool seen = present && d0 != 0xFFFFu;
       in_dict = seen;
       id64 = seen ? (uint64_t)d0 : (NBW_UNSEEN_BIT | (uint64_t)label);
-      class_count_rank<NMAX>(id64, present, lane, sub_base, cnt[0], rk[0]);
+      cls = classes_level0<NMAX>(label, present, node, sub_base);
+      cnt[0] = __popc(cls);
+      rk[0] = __popc(cls & ((1u << node) - 1u));
       if (PREFIX) { if (seen) deep = M.label_off[0] + (int)d0; }
       else col[0] = effective_column(M, 0, seen, d0, rk[0]);
       if (present) kss += M.oa ? 1 : cnt[0];
@@ -176,7 +214,9 @@ score_pool_kernel(const ScoreParams P, const uint8_t* __restrict__ cells, int64_
         seen = table_probe(static_cast<const uint4*>(M.table[l]), M.table_mask[l], key, chk, dense);
       in_dict = seen;
       id64 = seen ? (uint64_t)dense : (NBW_UNSEEN_BIT | key);
-      class_count_rank<NMAX>(id64, endpoint, lane, sub_base, cnt[l], rk[l]);
+      cls = classes_refine<NMAX>(cls, id64, endpoint, node, lane, sub_base);
+      cnt[l] = __popc(cls);
+      rk[l] = __popc(cls & ((1u << node) - 1u));
       if (PREFIX) { if (endpoint && seen) deep = M.label_off[l] + (int)dense; }
       else col[l] = endpoint ? effective_column(M, l, seen, dense, rk[l]) : -1;
       if (endpoint) kss += M.oa ? 1 : cnt[l];
