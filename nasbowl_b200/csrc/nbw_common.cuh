@@ -191,17 +191,18 @@ __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
 }
 
 // Sums of the successors' hashes.  Each round every lane fetches ITS next successor (per-lane
-// source lane).  The first four rounds are unrolled without any vote or branch — the cells of
-// all three search spaces rarely exceed out-degree 4 — so their twelve shuffles are independent
-// and overlap; higher degrees fall through to a voted loop.
+// source lane).  The first rounds are unrolled without any vote or branch (most nodes of
+// the three search spaces have out-degree <= 2), so their shuffles are independent and overlap;
+// higher degrees fall through to a voted loop.
 template <int NMAX>
 __device__ __forceinline__ void successor_sums(uint32_t succ, int sub_base, int node, uint64_t ha, uint32_t hb,
                                                uint64_t& sum_a, uint32_t& sum_b) {
+  constexpr int kUnrolledSuccessorRounds = NMAX == 8 ? 2 : 4;   // measured: NB cells 2, DARTS cells 4
   sum_a = 0;
   sum_b = 0;
   uint32_t m = succ;
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
+  for (int t = 0; t < kUnrolledSuccessorRounds; ++t) {
     const bool has = m != 0u;
     const int j = has ? (__ffs(m) - 1) : node;
     const uint64_t oa = shfl64(ha, sub_base + j);
@@ -211,7 +212,7 @@ __device__ __forceinline__ void successor_sums(uint32_t succ, int sub_base, int 
     m &= m - 1u;      // 0 stays 0
   }
 #pragma unroll 1
-  for (int t = 4; t < NMAX; ++t) {
+  for (int t = kUnrolledSuccessorRounds; t < NMAX; ++t) {
     if (!__any_sync(0xffffffffu, m != 0u)) break;
     const bool has = m != 0u;
     const int j = has ? (__ffs(m) - 1) : node;
