@@ -1,2 +1,8 @@
-from .acquisitions import GraphExpectedImprovement, GraphUpperConfidentBound  # noqa: F401
-from .gp import GraphGP  # noqa: F401
+"""GP surrogate and acquisition functions with the reference's class names."""
+from . import acquisitions, gp
+
+GraphGP = gp.GraphGP
+GraphExpectedImprovement = acquisitions.GraphExpectedImprovement
+GraphUpperConfidentBound = acquisitions.GraphUpperConfidentBound
+
+__all__ = ["GraphGP", "GraphExpectedImprovement", "GraphUpperConfidentBound"]

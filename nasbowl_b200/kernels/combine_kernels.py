@@ -5,7 +5,7 @@ from __future__ import annotations
 import torch
 
 from ..cells import CellBatch
-from .graph_kernel import GraphKernels
+from .base import GraphKernels
 
 
 class CombineKernel:

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from ..cells import CellBatch, OpVocab, pack_networkx
-from .graph_kernel import GraphKernels
+from .base import GraphKernels
 
 GLOBAL_VOCAB = OpVocab()
 

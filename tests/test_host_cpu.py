@@ -330,3 +330,40 @@ def test_mutation_pool_host_twin():
                 G.nodes[i]['op_name'] = nm
             rb = pack_networkx([G], OpVocab(synth.NB101_OPS))
             assert mine is not None and list(rb.labels[0]) == mine[0][:8] and list(rb.succ[0]) == mine[1][:8]
+
+
+# ---------------------------------------------------------------------------- oracle invariants
+def test_oracle_invariants_on_random_cells():
+    """Properties any correct WL subtree kernel has; they guard the oracle itself (hypothesis)."""
+    from hypothesis import given, settings, strategies as st_
+
+    @settings(max_examples=25, deadline=None)
+    @given(st_.integers(0, 2 ** 31 - 1), st_.sampled_from([0, 1, 2]), st_.booleans())
+    def prop(seed, fam, oa):
+        batch = synth.generate_cells_host(fam, seed, seed % 1000, 12)
+        K = wl_oracle.gram_raw_levels(batch, 3, oa)
+        assert (K >= 0).all() and np.array_equal(K, K.transpose(0, 2, 1))
+        Ksum = K.sum(0)
+        d = np.diag(Ksum)
+        assert (Ksum.astype(np.float64) ** 2 <= np.outer(d, d) + 1e-9).all()          # Cauchy-Schwarz
+        if oa:
+            assert (Ksum <= wl_oracle.gram_raw(batch, 3, False)).all()                 # min-sum <= dot product
+            assert np.array_equal(d, 4 * batch.n_nodes)                                # (h+1) * n_nodes, SURVEY Q16
+        # renumbering the nodes of every cell leaves the kernel unchanged
+        rng = np.random.RandomState(seed % 9973)
+        lab = np.full_like(batch.labels, NO_NODE)
+        suc = np.zeros_like(batch.succ)
+        for i in range(len(batch)):
+            k = int(batch.n_nodes[i])
+            perm = rng.permutation(k)                  # old node v -> new index perm[v]
+            for v in range(k):
+                lab[i, perm[v]] = batch.labels[i, v]
+                m = 0
+                for j in range(k):
+                    if (int(batch.succ[i, v]) >> j) & 1:
+                        m |= 1 << int(perm[j])
+                suc[i, perm[v]] = m
+        assert np.array_equal(wl_oracle.gram_raw(CellBatch(batch.n_max, lab, suc), 3, oa), Ksum)
+        # the two restatements of the relabelling agree
+        assert np.array_equal(wl_oracle.gram_raw(batch, 3, oa, fast=False), Ksum)
+    prop()
