@@ -20,6 +20,22 @@ struct HistLevels {
   int64_t label_off[NBW_MAX_LEVELS + 1];
 };
 
+// Size of the node's label class inside its cell and its rank in it: dense 32-bit ids compared by
+// one shuffle sweep over the sub-warp (a warp match gives the same answer but is much slower).
+template <int NMAX>
+__device__ __forceinline__ void class_count_rank32(uint32_t id, bool valid, int node, int sub_base, int& count, int& rank) {
+  count = 0;
+  rank = 0;
+  const uint32_t mine = valid ? id : (0x80000000u | (uint32_t)node);   // uncounted nodes match nobody (ids < 2^31)
+#pragma unroll
+  for (int j = 0; j < NMAX; ++j) {
+    const uint32_t other = __shfl_sync(0xffffffffu, mine, sub_base + j);
+    const bool same = valid && other == mine;
+    count += same ? 1 : 0;
+    rank += (same && j < node) ? 1 : 0;
+  }
+}
+
 template <int NMAX>
 __global__ void __launch_bounds__(kHistThreads)
 hist_dense_kernel(const uint32_t* __restrict__ ids, int64_t n_cells, HistLevels lv,
@@ -48,7 +64,7 @@ hist_dense_kernel(const uint32_t* __restrict__ ids, int64_t n_cells, HistLevels 
     const uint32_t id = in_range ? ids[(int64_t)l * n_cells * NMAX + g * NMAX + node] : NBW_INVALID_ID;
     const bool valid = id != NBW_INVALID_ID;
     int count, rank;
-    class_count_rank<NMAX>((uint64_t)id, valid, lane, sub_base, count, rank);
+    class_count_rank32<NMAX>(id, valid, node, sub_base, count, rank);
     if (valid) {
       if (!oa) {
         self_acc += count;   // sum over nodes of class size = sum over classes of size^2
@@ -98,7 +114,7 @@ max_count_kernel(const uint32_t* __restrict__ ids, int64_t n_cells, HistLevels l
       const uint32_t id = in_range ? ids[(int64_t)l * n_cells * NMAX + g * NMAX + node] : NBW_INVALID_ID;
       const bool valid = id != NBW_INVALID_ID;
       int count, rank;
-      class_count_rank<NMAX>((uint64_t)id, valid, lane, sub_base, count, rank);
+      class_count_rank32<NMAX>(id, valid, node, sub_base, count, rank);
       if (valid && rank == 0) atomicMax(&max_count[lv.label_off[l] + id], (uint32_t)count);
     }
   }
