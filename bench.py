@@ -285,12 +285,12 @@ def run_b200(args):
         # host records in, top-5 indices + all EIs (host numpy) out
         xs, eis, idx = acq.propose_location(host_pool, top_n=TOP_N)
         return idx
-    for _ in range(max(1, args.warmup // 2)):
+    for _ in range(max(3, args.warmup)):
         e2e_step()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    e_steps = max(3, args.steps // 2)
+    e_steps = max(3, args.steps)
     t0 = time.perf_counter()
     for _ in range(e_steps):
         e2e_step()

@@ -241,6 +241,15 @@ int nbw_score_pool_host(nbw_ctx* ctx, const nbw_model* model_h, const void* cell
                         int64_t n_cells, float* scores_h, float* scores_dev, int chunks,
                         void* stream);
 
+/* Mapped form: `cells_h` must be PINNED host memory (cudaHostAlloc / cudaHostRegister); the kernel
+ * reads the records straight over PCIe through the mapped pointer — no staging copy, no per-chunk
+ * launches.  The pool is cut into `pieces` (1..64) kernels only so that the D2H copy of piece i's
+ * scores overlaps the kernel on piece i+1 (pieces = 1 measured best at 1M).  Pageable `cells_h` is refused (NBW_ERR_INVALID): use
+ * nbw_score_pool_host for it.  Same stream semantics as nbw_score_pool_host. */
+int nbw_score_pool_mapped(nbw_ctx* ctx, const nbw_model* model_h, const void* cells_h,
+                          int64_t n_cells, float* scores_h, float* scores_dev, int pieces,
+                          void* stream);
+
 /* Pool-side features only (test/diagnostic use): restricted dense feature rows
  * phi [M x ld_phi] int8 (columns < n_features) and self-similarity k_cc [M] i32. */
 int nbw_pool_features(nbw_ctx* ctx, const nbw_model* model_h, const void* cells,

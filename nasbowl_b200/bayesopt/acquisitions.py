@@ -87,8 +87,12 @@ class GraphExpectedImprovement(BaseAcquisition):
         eng = self.gp._dev['eng']
         host_scores = None
         if isinstance(candidates, torch.Tensor) and not candidates.is_cuda:
-            # packed records in host memory: H2D, kernel and D2H of the scores are pipelined
-            scores, host_scores = eng.score_host_pool(self._model(), candidates)
+            # packed records in host memory.  Pinned: the kernel reads them over PCIe, one D2H copy
+            # of the scores follows (nbw_score_pool_mapped).  Pageable: staged pipeline.
+            if candidates.is_pinned():
+                scores, host_scores = eng.score_host_pool(self._model(), candidates, chunks=1, mapped=True)
+            else:
+                scores, host_scores = eng.score_host_pool(self._model(), candidates)
         else:
             scores, _, _, _ = self.score_pool(candidates)
         vals, indices = eng.topk(scores, top_n, distinct=bool(return_distinct))      # syncs

@@ -321,11 +321,14 @@ class Engine:
                                             self._p(mu), self._p(var), self._p(sc), self.stream))
         return scores, mu, var, sc
 
-    def score_host_pool(self, model: "_lib.Model", host_cells: torch.Tensor, chunks: int = 8):
+    def score_host_pool(self, model: "_lib.Model", host_cells: torch.Tensor, chunks: int = 8,
+                        mapped: bool = False):
         """Score a pool that lives in HOST memory through nbw_score_pool_host: the H2D copy of
         chunk i+1, the kernel on chunk i and the D2H copy of chunk i-1's scores overlap.  Returns
         (scores on the device [M] f32, scores in pinned host memory [M] f32); the host copy is
-        complete after the next call that syncs the stream (e.g. topk)."""
+        complete after the next call that syncs the stream (e.g. topk).  `mapped=True` takes
+        nbw_score_pool_mapped instead (pinned memory only): the kernel reads the records over PCIe
+        itself and `chunks` is the number of kernel pieces."""
         assert not host_cells.is_cuda and host_cells.dtype == torch.uint8 and host_cells.dim() == 2
         host_cells = host_cells.contiguous()
         M = host_cells.shape[0]
@@ -335,9 +338,9 @@ class Engine:
         # a fresh pinned block per call (torch's caching host allocator recycles them): the caller
         # owns the returned scores, nothing is overwritten by the next pool
         host_scores = torch.empty((M,), dtype=torch.float32, pin_memory=True)
-        self._check(self.lib.nbw_score_pool_host(self.ctx, C.byref(model), C.c_void_p(host_cells.data_ptr()), M,
-                                                 C.c_void_p(host_scores.data_ptr()), self._p(st["scores"]),
-                                                 max(1, min(chunks, M)), self.stream))
+        fn = self.lib.nbw_score_pool_mapped if mapped else self.lib.nbw_score_pool_host
+        self._check(fn(self.ctx, C.byref(model), C.c_void_p(host_cells.data_ptr()), M,
+                       C.c_void_p(host_scores.data_ptr()), self._p(st["scores"]), max(1, min(chunks, M)), self.stream))
         return st["scores"], host_scores
 
     def pool_features(self, model: "_lib.Model", cells: torch.Tensor, n_cells: int):

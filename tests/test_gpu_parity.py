@@ -479,6 +479,35 @@ def test_host_pool_pipeline_matches_resident_path(eng):
         assert eis_h.shape == (M, 1) and eis_h.dtype == np.float32
 
 
+def test_mapped_and_staged_host_entry_points_agree(eng):
+    """nbw_score_pool_mapped (kernel reads pinned records over PCIe, mirrors the scores into pinned
+    host memory) == nbw_score_pool_host (staged) == nbw_score_pool (resident), bit for bit; pageable
+    records are refused by the mapped entry point."""
+    from nasbowl_b200 import _lib
+    from nasbowl_b200.bayesopt import GraphExpectedImprovement, GraphGP
+    from nasbowl_b200.kernels import WeisfilerLehman
+    for family, h in ((1, 3), (2, 2)):
+        train = synth.generate_cells_host(family, 5, 0, 40)
+        gp = GraphGP(train, torch.randn(40, generator=torch.Generator().manual_seed(2)), [WeisfilerLehman(h=h)],
+                     n_max=train.n_max)
+        gp.fit(wl_subtree_candidates=(h,), optimize_lik=False)
+        acq = GraphExpectedImprovement(gp)
+        model = acq._model()
+        for M in (1, 33, 50_001):
+            dev = eng.generate_cells(family, 17, 100, M)
+            resident = acq.score_pool(dev)[0].cpu()
+            pinned = dev.cpu().pin_memory()
+            for pieces in (1, 3):
+                s_dev, s_host = eng.score_host_pool(model, pinned, chunks=pieces, mapped=True)
+                torch.cuda.synchronize()
+                assert torch.equal(s_dev.cpu(), resident) and torch.equal(s_host, resident)
+            s_dev, s_host = eng.score_host_pool(model, pinned, chunks=4)
+            torch.cuda.synchronize()
+            assert torch.equal(s_dev.cpu(), resident) and torch.equal(s_host, resident)
+    with pytest.raises(_lib.NbwError, match="pinned"):
+        eng.score_host_pool(model, dev.cpu(), chunks=1, mapped=True)
+
+
 def test_device_mutation_pool_matches_host(eng):
     par = synth.generate_cells_host(0, 3, 0, 12)
     dev_par = eng.upload_cells(par)
