@@ -4,19 +4,22 @@
 // weisfeiler_lehman.py:316-327: WL levels are contiguous column blocks of Phi, so the sum over
 // levels 0..h is ONE GEMM over the K-range [0, col_off[h+1]).
 //
-// Product path (impl 0): tcgen05.mma kind::i8, cta_group::1, M = 128, N = 256 accumulator tiles
-// in TMEM (128 lanes x 256 columns of s32, two buffers), both operands K-major, staged by TMA
-// into 128B-swizzled shared memory (one 128-byte K-block per row per stage), 4-stage mbarrier
-// pipeline, persistent CTAs (one per SM) walking the tiles in a grouped order:
-//   warp 0 lane 0 : TMA producer          (cp.async.bulk.tensor.2d -> full barrier)
-//   warp 1 lane 0 : MMA issuer            (4 x UMMA_K=32 per stage, tcgen05.commit -> empty barrier)
+// Product path (impl 0): tcgen05.mma kind::i8, cta_group::2 — a cluster of two CTAs (one TPC) owns a
+// 256 x 256 output tile, accumulators in TMEM (128 lanes x 256 columns of s32 per CTA, two buffers),
+// both operands K-major, staged by TMA into 128B-swizzled shared memory (one 128-byte K-block per
+// row per stage; each CTA stages its 128 rows of A and its half of B), 6-stage mbarrier pipeline,
+// persistent CTA pairs walking the tiles in a grouped order:
+//   warp 0 lane 0 : TMA producer          (cp.async.bulk.tensor.2d -> the leader's full barrier)
+//   warp 1 lane 0 : MMA issuer (leader)   (4 x UMMA_K=32 per stage, multicast tcgen05.commit)
 //   warps 2..5    : epilogue              (tcgen05.ld 32x32b.x32 -> 128-byte row segments to HBM)
-// int32 accumulation of int8 products is exact.
+// int32 accumulation of int8 products is exact.  The single-CTA kernels (cta_group::1) are kept as
+// NBW_GRAM_VARIANT 0..4 for comparison.
 //
 // Cross-check path (impl 1): plain dp4a kernel, used by the tests to validate impl 0.
 #include "nbw_common.cuh"
 
 #include <cuda.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 namespace {
@@ -382,6 +385,205 @@ gram_i8_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
   }
 }
 
+// ------------------------------------------------------------------ CTA-pair variant (cta_group::2)
+// A cluster of two CTAs (one TPC) owns a 256 x 256 output tile.  Each CTA stages its own 128 rows of A
+// and its own 128 rows (= half of N) of B per K-block: 32 KB per stage instead of 48 KB, and every
+// operand byte is read from shared memory by one SM only — the single-CTA kernel is bound by exactly
+// that bandwidth.  The leader CTA (cluster rank 0) issues tcgen05.mma.cta_group::2 with M = 256; the
+// accumulator rows 128 r .. 128 r + 127 land in the TMEM of CTA r.  Barrier protocol:
+//   full[s]      lives in the leader: one arrive.expect_tx (64 KB) by the leader's producer, TMA of BOTH
+//                CTAs completes its bytes there (mbarrier address mapped to rank 0, .cta_group::2)
+//   empty[s]     one per CTA: tcgen05.commit ... multicast::cluster (mask 0b11) releases both producers
+//   tmem_full[b] one per CTA, same multicast commit
+//   tmem_empty[b] in the leader: 4 epilogue warps x 2 CTAs arrive (the peer's remotely)
+struct __align__(8) PairBarriers {
+  uint64_t full[MAX_STAGES];
+  uint64_t empty[MAX_STAGES];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+constexpr int PAIR_BN = 256;                       // N of the pair tile
+constexpr int PAIR_B_ROWS = PAIR_BN / 2;           // rows of B each CTA stages
+constexpr int PAIR_STAGE_BYTES = A_TILE_BYTES + PAIR_B_ROWS * BK;
+template <int STAGES>
+constexpr size_t gram_pair_smem_bytes() {
+  return 1024 + (size_t)STAGES * PAIR_STAGE_BYTES + sizeof(PairBarriers);
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t smem_addr, uint32_t rank) {
+  uint32_t out;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(out) : "r"(smem_addr), "r"(rank));
+  return out;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t leader_bar, void* dst, int32_t x, int32_t y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void umma_i8_pair(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_c), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+template <int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+gram_i8_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    int32_t* __restrict__ C, int64_t ldc, int64_t m, int64_t n, int32_t kblk0, int32_t k_blocks,
+                    int32_t m_tiles, int32_t n_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int B_HALF_BYTES = PAIR_B_ROWS * BK;
+  constexpr int PM = 2 * BM;                                                 // rows of the pair tile
+  constexpr uint32_t kIdesc =
+      (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(PAIR_BN >> 3) << 17) | ((uint32_t)(PM >> 4) << 24);
+  uint8_t* tile_a = smem;
+  uint8_t* tile_b = smem + (size_t)STAGES * A_TILE_BYTES;
+  PairBarriers* bars = reinterpret_cast<PairBarriers*>(smem + (size_t)STAGES * PAIR_STAGE_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_rank();
+  const bool leader = rank == 0;
+  const int64_t total_tiles = (int64_t)m_tiles * n_tiles;
+  const int64_t pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bars->tmem_full[b], 1);
+      mbar_init(&bars->tmem_empty[b], 8);   // 4 epilogue warps of each CTA (used in the leader only)
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();          // the peer's barriers exist before anything remote touches them
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int64_t t = pair_id; t < total_tiles; t += n_pairs) {
+        int32_t mt, nt;
+        tile_coords(t, m_tiles, n_tiles, mt, nt);
+        const int32_t row0 = mt * PM + (int32_t)rank * BM, col0 = nt * PAIR_BN + (int32_t)rank * PAIR_B_ROWS;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&bars->empty[stage], phase ^ 1u);
+          if (leader) mbar_expect_tx(&bars->full[stage], (uint32_t)(2 * PAIR_STAGE_BYTES));
+          const uint32_t leader_full = map_to_rank(smem_u32(&bars->full[stage]), 0);
+          const int32_t kx = (kblk0 + kb) * BK;
+          tma_load_2d_pair(&map_a, leader_full, tile_a + (size_t)stage * A_TILE_BYTES, kx, row0);
+          tma_load_2d_pair(&map_b, leader_full, tile_b + (size_t)stage * B_HALF_BYTES, kx, col0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int64_t t = pair_id; t < total_tiles; t += n_pairs) {
+        mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1u);        // both CTAs' epilogues have drained this buffer
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tmem_acc = tmem_base + acc * PAIR_BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&bars->full[stage], phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_addr = smem_u32(tile_a + (size_t)stage * A_TILE_BYTES);
+          const uint32_t b_addr = smem_u32(tile_b + (size_t)stage * B_HALF_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_i8_pair(tmem_acc, umma_smem_desc(a_addr + k * UMMA_K), umma_smem_desc(b_addr + k * UMMA_K), kIdesc,
+                         (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit_pair(&bars->empty[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_pair(&bars->tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else {
+    const int quarter = warp & 3;
+    const bool vec_ok = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+    uint32_t acc = 0, acc_phase = 0;
+    for (int64_t t = pair_id; t < total_tiles; t += n_pairs) {
+      int32_t mt, nt;
+      tile_coords(t, m_tiles, n_tiles, mt, nt);
+      const int64_t row0 = (int64_t)mt * PM + (int64_t)rank * BM, col0 = (int64_t)nt * PAIR_BN;
+      mbar_wait(&bars->tmem_full[acc], acc_phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int64_t r = row0 + quarter * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < PAIR_BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_load_32cols(tmem_base + acc * PAIR_BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), v);
+        if (r < m) {
+          const int64_t cbase = col0 + c * 32;
+          int32_t* dst = C + r * ldc + cbase;
+          if (vec_ok && cbase + 32 <= n) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<int4*>(dst + 4 * q) =
+                  make_int4((int)v[4 * q], (int)v[4 * q + 1], (int)v[4 * q + 2], (int)v[4 * q + 3]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 32; ++q)
+              if (cbase + q < n) dst[q] = (int32_t)v[q];
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(map_to_rank(smem_u32(&bars->tmem_empty[acc]), 0));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();          // nobody frees TMEM or leaves while the pair still computes / signals
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------ dp4a cross-check kernel
 __global__ void __launch_bounds__(256)
 gram_i8_simt_kernel(const int8_t* __restrict__ A, int64_t m, int64_t lda, const int8_t* __restrict__ B, int64_t n,
@@ -475,15 +677,17 @@ extern "C" int nbw_gram_i8(nbw_ctx* ctx, const int8_t* A, int64_t m, int64_t lda
     return NBW_OK;
   }
   NBW_REQUIRE(ctx, impl == 0, "unknown impl %d", impl);
-  // Default: the persistent kernel (variant 4): 128 x 256 tiles, one CTA per SM, epilogue of tile i
+  // Default: the CTA-pair kernel (variant 5): cta_group::2, 256 x 256 tiles, epilogue of tile i
   // overlapped with the main loop of tile i+1 through two TMEM accumulator buffers, grouped tile
-  // order for L2 reuse.  Measured int8 throughput: 2.89 Pop/s at 16384^2 x 8192, 3.48 Pop/s on the
-  // 200k x 200k x 33792 stress (profiles/).  NBW_GRAM_VARIANT selects the simpler one-tile-per-CTA
-  // variants for experiments: 0 = 128x128 3-stage, 1 = 128x256 4-stage, 2 = 128x128 6-stage,
-  // 3 = 128x256 2-stage (two CTAs per SM).
-  int variant = 4;
+  // order for L2 reuse.  Measured int8 throughput: 3.20 Pop/s at 16384^2 x 8192, 3.89 Pop/s on the
+  // 200k x 200k x 33792 stress (profiles/); the single-CTA persistent kernel (variant 4) reaches
+  // 2.89 / 3.44.  NBW_GRAM_VARIANT selects the other variants for experiments: 0 = 128x128 3-stage,
+  // 1 = 128x256 4-stage, 2 = 128x128 6-stage, 3 = 128x256 2-stage (two CTAs per SM), 4 = persistent
+  // single-CTA 128x256.
+  int variant = 5;
   if (const char* v = getenv("NBW_GRAM_VARIANT")) variant = atoi(v);
-  const int bn = (variant == 0 || variant == 2) ? 128 : 256;   // variants 1, 3, 4 use 256-wide tiles
+  // B rows per TMA box: variants 1, 3, 4 stage 256-wide tiles; the pair variant stages half of N per CTA
+  const int bn = (variant == 0 || variant == 2 || variant == 5) ? 128 : 256;
   CUtensorMap map_a, map_b;
   int rc = make_operand_map(ctx, &map_a, A, m, lda, BM);
   if (rc) return rc;
@@ -521,6 +725,42 @@ extern "C" int nbw_gram_i8(nbw_ctx* ctx, const int8_t* A, int64_t m, int64_t lda
       const int64_t tiles = (int64_t)mt_all * nt_all;
       const unsigned ctas = (unsigned)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
       gram_i8_persistent_kernel<256, 4><<<ctas, 192, kBytes, st>>>(map_a, map_b, C, ldc, m, n, kb0, nkb, mt_all, nt_all);
+      break;
+    }
+    case 5: {                                 // CTA pairs: cta_group::2, 256 x 256 tiles
+      int stages = 6;
+      if (const char* v = getenv("NBW_GRAM_STAGES")) stages = atoi(v);
+      const int32_t mt2 = (int32_t)((m + 2 * BM - 1) / (2 * BM)), nt2 = (int32_t)((n + PAIR_BN - 1) / PAIR_BN);
+      const int64_t tiles = (int64_t)mt2 * nt2;
+#define NBW_PAIR_LAUNCH(ST_)                                                                                  \
+  case ST_: {                                                                                                 \
+    static int max_pairs = 0;                                                                                 \
+    constexpr size_t kBytes = gram_pair_smem_bytes<ST_>();                                                    \
+    if (!max_pairs) {                                                                                         \
+      NBW_CUDA(ctx, cudaFuncSetAttribute(gram_i8_pair_kernel<ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         (int)kBytes));                                                       \
+      cudaLaunchConfig_t cfg = {};                                                                            \
+      cfg.gridDim = dim3((unsigned)(ctx->sm_count & ~1));                                                     \
+      cfg.blockDim = dim3(192);                                                                               \
+      cfg.dynamicSmemBytes = kBytes;                                                                          \
+      int clusters = 0;                                                                                       \
+      NBW_CUDA(ctx, cudaOccupancyMaxActiveClusters(&clusters, gram_i8_pair_kernel<ST_>, &cfg));               \
+      NBW_REQUIRE(ctx, clusters >= 1, "no CTA pair of the Gram kernel fits this device");                     \
+      max_pairs = clusters;                                                                                   \
+    }                                                                                                         \
+    const unsigned pairs = (unsigned)(tiles < max_pairs ? tiles : max_pairs);                                 \
+    gram_i8_pair_kernel<ST_><<<2 * pairs, 192, kBytes, st>>>(map_a, map_b, C, ldc, m, n, kb0, nkb, mt2, nt2);  \
+    break;                                                                                                    \
+  }
+      switch (stages) {
+        NBW_PAIR_LAUNCH(4)
+        NBW_PAIR_LAUNCH(5)
+        NBW_PAIR_LAUNCH(6)
+        NBW_PAIR_LAUNCH(7)
+        default: NBW_FAIL(ctx, NBW_ERR_INVALID, "NBW_GRAM_STAGES must be 4..7");
+      }
+#undef NBW_PAIR_LAUNCH
+      if (getenv("NBW_GRAM_VERBOSE")) fprintf(stderr, "[nbw] pair gram: %lld tiles, stages %d\n", (long long)tiles, stages);
       break;
     }
     default: NBW_FAIL(ctx, NBW_ERR_INVALID, "unknown NBW_GRAM_VARIANT %d", variant);
