@@ -371,11 +371,73 @@ class GraphGP:
         self._fitted = False
         self._dev = None
 
-    def dmu_dphi(self, *a, **k):
-        raise NotImplementedError("interpretability gradients (gp.py:296-424) are outside the GPU hot path")
+    def dmu_dphi(self, X_s=None, average_across_features=True, average_across_occurrences=False):
+        """Derivative of the posterior mean with respect to the WL embedding of each cell in X_s
+        (default: the training cells) — reference bayesopt/gp.py:296-424.
+
+        The reference differentiates k(phi*, Phi) = (phi* . x_i) / (|phi*| |x_i|) by autograd, one cell
+        at a time.  In closed form, with B = rows x_i / |x_i| and w = B^T alpha (alpha = K_i y):
+            d mu / d phi* = ( w - (phi^ . w) phi^ ) / |phi*|,   phi^ = phi* / |phi*|
+        w is one device GEMV over the training features; the embeddings of X_s come from the pool
+        feature kernel; the per-cell vector algebra (N x D) is host-side.  Like the reference, the
+        tensor form of the kernel is linear even for oa kernels.  Labels outside the training
+        vocabulary are dropped (the reference mis-aligns them, see WeisfilerLehman.forward_t); every
+        consumer in the reference passes the training cells, where the two agree."""
+        self._require_fit()
+        if len(self.kernels) != 1:
+            raise NotImplementedError("dmu_dphi handles a single WL kernel")
+        d = self._dev
+        eng, n, k = d['eng'], self.n, self.kernels[0]
+        X = k.embedding(None, pad_levels=True)                      # [n, W] training embedding, reference layout
+        Y = X if X_s is None else k.embedding(X_s, pad_levels=True)
+        D = X.shape[1]
+        # w = B^T alpha on the device (fp64): B = diag(1/|x_i|) X
+        Xd = torch.as_tensor(X / np.sqrt((X * X).sum(axis=1))[:, None], device=eng.device).contiguous()
+        w = eng.empty((D,), torch.float64)
+        eng.gemm(True, False, D, 1, n, float(self.weights[0]), Xd, D, d['alpha'], 1, 0.0, w, 1)
+        w = w.cpu().numpy()
+        ny = np.sqrt((Y * Y).sum(axis=1))
+        Yh = Y / ny[:, None]
+        grads = (w[None, :] - (Yh @ w)[:, None] * Yh) / ny[:, None]
+        feature_matrix = torch.tensor(Y)
+        if average_across_features:
+            return get_grad(torch.tensor(grads), feature_matrix, average_across_occurrences)
+        dmu = [torch.tensor(g).reshape(1, -1) for g in grads]
+        return dmu, None, feature_matrix.sum(dim=0) if average_across_occurrences else feature_matrix
 
     def __getstate__(self):
         st = dict(self.__dict__)
         st['_dev'] = None
         st['_fitted'] = False      # device state does not travel; call fit() after unpickling
         return st
+
+
+def get_grad(grad_matrix, feature_matrix, average_occurrences=False):
+    """Monte-Carlo average of the gradients over the sample, per feature (and per occurrence count) —
+    reference bayesopt/gp.py:427-476.  Host-side bookkeeping over an [N, D] matrix."""
+    assert grad_matrix.shape == feature_matrix.shape
+    keep = torch.nonzero((feature_matrix != 0).any(dim=0)).reshape(-1)      # drop all-zero columns
+    feature_matrix, grad_matrix = feature_matrix[:, keep], grad_matrix[:, keep]
+    N, D = feature_matrix.shape
+    if average_occurrences:
+        avg, var = torch.zeros(D), torch.zeros(D)
+        for c in range(D):
+            col = feature_matrix[:, c]
+            _, inverse, counts = torch.unique(col, return_inverse=True, return_counts=True)
+            wv = counts[inverse].to(torch.float32)
+            wv = wv / wv.sum()
+            mean = torch.sum(wv * grad_matrix[:, c])
+            avg[c] = mean
+            var[c] = torch.sum(wv * grad_matrix[:, c] ** 2) - mean ** 2
+        return avg, var, feature_matrix.sum(dim=0)
+    max_occur = 7                                                           # gp.py:459-461
+    avg, var, inc = torch.zeros(D, max_occur), torch.zeros(D, max_occur), torch.zeros(D, max_occur)
+    for c in range(D):
+        col = feature_matrix[:, c]
+        values, counts = torch.unique(col, return_counts=True)
+        for i, val in enumerate(values):
+            at = grad_matrix[col == val]        # all columns of those rows: the reference's own indexing (:471)
+            avg[c, int(val)] = torch.mean(at)
+            var[c, int(val)] = torch.var(at)
+            inc[c, int(val)] = counts[i]
+    return avg, var, inc

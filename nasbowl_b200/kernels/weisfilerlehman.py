@@ -155,20 +155,80 @@ class WeisfilerLehman(GraphKernels):
         out = [phi[:, fit.col_off[l]:fit.col_off[l] + fit.widths[l]] for l in range(self.h + 1)]
         return [torch.tensor(o) for o in out] if self.return_tensor else out
 
-    def feature_matrix(self, gr):
-        """(Phi restricted to the fitted vocabulary [M, D] int8 numpy, self-similarity [M])."""
+    def _linear_fit(self):
+        """The fitted vocabulary with the plain histogram layout (one column per label).  For an
+        oa kernel the device features are thermometer-coded and capped at the training counts; the
+        reference's embeddings (kern.transform(return_embedding_only=True)) are plain counts, so the
+        interpretability outputs are built from this second layout of the same label ids."""
+        fit = self._fit
+        if fit is None or not fit.oa:
+            return fit
+        if getattr(self, '_lin_cache', None) is not None and self._lin_cache[0] is fit:
+            return self._lin_cache[1]
+        import dataclasses
+        from ..engine import Engine, _round_up
+        col_off = [0]
+        for d in fit.dims:
+            col_off.append(col_off[-1] + _round_up(max(d, 1), 128))
+        lin = dataclasses.replace(fit, oa=False, widths=list(fit.dims), col_off=col_off, thermo_base=None,
+                                  max_count=None, phi=None, self_sim=None)
+        Engine.get().build_features(lin)
+        self._lin_cache = (fit, lin)
+        return lin
+
+    def feature_matrix(self, gr, linear=False):
+        """(Phi restricted to the fitted vocabulary [M, D] int8 numpy, self-similarity [M]).
+        linear=True: plain per-label counts even when the kernel is oa."""
         if self._fit is None:
             raise ValueError("The kernel has not been fitted. Call fit_transform first.")
         from ..engine import Engine
         from ..pool_model import PoolModel
         eng = Engine.get()
-        batch = self.pack(gr).widen(self._fit.n_max)
-        pm = PoolModel.from_fit(eng, self._fit, self.h)
+        fit = self._linear_fit() if linear else self._fit
+        batch = self.pack(gr).widen(fit.n_max)
+        pm = PoolModel.from_fit(eng, fit, self.h)
         phi, ss = eng.pool_features(pm.descriptor(), eng.upload_cells(batch), len(batch))
         return phi.cpu().numpy()[:, :pm.n_features], ss.cpu().numpy()
 
+    def embedding(self, gr=None, pad_levels: bool = False) -> np.ndarray:
+        """Histogram embedding [N, sum_l D_l] float64, columns in the reference's feature order
+        (feature_map order), restricted to the fitted vocabulary.  gr=None: the training cells.
+        pad_levels: one all-zero spare column after each level's block — the shape of the
+        reference's ordered feature matrices (vertex_histogram.py:184) that forward_t exposes."""
+        ref = self._reference_labels()
+        if ref is None:
+            raise ValueError("The kernel has not been fitted. Call fit_transform first.")
+        ref_id, _ = ref
+        lin = self._linear_fit()
+        if gr is None:
+            phi = lin.phi.cpu().numpy()
+        else:
+            phi, _ = self.feature_matrix(gr, linear=True)
+        total = sum(lin.dims[:self.h + 1])
+        emb = np.zeros((phi.shape[0], total), dtype=np.float64)
+        for l in range(self.h + 1):
+            emb[:, ref_id[l]] = phi[:, lin.col_off[l]:lin.col_off[l] + lin.dims[l]]
+        if pad_levels:
+            ends = np.cumsum(lin.dims[:self.h + 1])
+            spare = np.zeros((emb.shape[0], 1))
+            emb = np.concatenate([np.concatenate([emb[:, e - d:e], spare], axis=1)
+                                  for e, d in zip(ends, lin.dims[:self.h + 1])], axis=1)
+        return emb
+
     def forward_t(self, gr2, gr1=None):
-        raise NotImplementedError("kernel gradients (interpretability, gp.py:296-424) are outside the GPU hot path")
+        """(K, y_, x_): the cosine-normalised LINEAR kernel between gr1 (default: the training cells)
+        and gr2 as a torch graph over the leaf embeddings x_ (gr1) and y_ (gr2), for Jacobian-vector
+        products (reference kernels/weisfilerlehman.py:172-217 + grakel_replace/utils.py:20-71; like
+        the reference, the tensor form is linear even when the kernel is oa).  The embeddings come
+        from the device; the small differentiable product is host-side torch.
+        Deviation: labels of gr2 outside the training vocabulary are dropped; the reference keeps each
+        level's first unknown label in the spare column and, for a cell with two or more unknown labels
+        at one level, shifts the deeper levels (it truncates after concatenating) — DESIGN.md §8."""
+        x_ = torch.tensor(self.embedding(None if gr1 is None else gr1, pad_levels=True)).requires_grad_()
+        y_ = torch.tensor(self.embedding(gr2, pad_levels=True)).requires_grad_()
+        K = y_ @ x_.t()
+        K = K / torch.ger(torch.sqrt(torch.diag(y_ @ y_.t())), torch.sqrt(torch.diag(x_ @ x_.t())))
+        return K, y_, x_
 
     # ------------------------------------------------------------------ motif strings (row f3)
     def _reference_labels(self):
@@ -243,22 +303,7 @@ class WeisfilerLehman(GraphKernels):
         ref = self._reference_labels()
         if ref is None:
             raise ValueError("The kernel has not been fitted. Call fit_transform first.")
-        ref_id, _ = ref
-        fit = self._fit
-        phi, _ = self.feature_matrix(X_s)
-        total = sum(fit.dims[:self.h + 1])
-        emb = np.zeros((phi.shape[0], total), dtype=np.float64)
-        tb = fit.thermo_base.cpu().numpy() if fit.oa else None
-        mc = fit.max_count.cpu().numpy() if fit.oa else None
-        for l in range(self.h + 1):
-            for z in range(fit.dims[l]):
-                if fit.oa:      # thermometer columns of one label add up to its (capped) count
-                    sl = fit.label_off[l] + z
-                    c0 = fit.col_off[l] + int(tb[sl])
-                    col = phi[:, c0:c0 + int(mc[sl])].sum(axis=1)
-                else:
-                    col = phi[:, fit.col_off[l] + z]
-                emb[:, ref_id[l][z]] = col
+        emb = self.embedding(X_s)
         return torch.tensor(emb), list(self.feature_map(flatten=True).values())
 
     # device state does not travel through pickle (run_darts.py:110-125 pickles the GP)
@@ -267,4 +312,5 @@ class WeisfilerLehman(GraphKernels):
         st['_fit'] = None
         st['_fit_batch'] = None
         st['_ref_cache'] = None
+        st['_lin_cache'] = None
         return st

@@ -194,6 +194,53 @@ def gp_predict_full(st: GPState, train, pool):
     return mu, cov
 
 
+def dmu_dphi(st: GPState, X: np.ndarray, Y: np.ndarray, weight: float = 1.0) -> np.ndarray:
+    """Gradient of the posterior mean with respect to the embedding of each row of Y
+    (gp.py:296-376): the vector-Jacobian product of k(Y, X) = (Y X^T) / (|y| |x_i|)
+    (grakel_replace/utils.py:60-71, the tensor form is linear whatever `oa` is) with
+    alpha = K_i y.  X, Y: embeddings from wl_oracle.wl_embed_reference_order.  Returns [M, D]."""
+    alpha = st.K_i @ st.y_norm
+    nx = np.sqrt((X * X).sum(axis=1))
+    out = np.empty_like(Y)
+    for j in range(Y.shape[0]):
+        y = Y[j]
+        ny = np.sqrt(y @ y)
+        # d/dy [ (y . x_i) / (ny nx_i) ] = x_i / (ny nx_i) - (y . x_i) y / (ny^3 nx_i)
+        J = X / (ny * nx)[:, None] - np.outer((X @ y) / (ny ** 3 * nx), y)
+        out[j] = weight * (alpha @ J)
+    return out
+
+
+def get_grad(grad_matrix: np.ndarray, feature_matrix: np.ndarray, average_occurrences: bool = False):
+    """gp.py:427-476, incl. its indexing at :471 (the mean / variance run over ALL columns of the
+    rows whose feature d equals the value) and torch.var's n-1 denominator (nan for one row)."""
+    keep = [c for c in range(feature_matrix.shape[1]) if not np.all(feature_matrix[:, c] == 0)]
+    F, G = feature_matrix[:, keep], grad_matrix[:, keep]
+    N, D = F.shape
+    if average_occurrences:
+        avg, var = np.zeros(D), np.zeros(D)
+        for d in range(D):
+            vals, inverse, counts = np.unique(F[:, d], return_inverse=True, return_counts=True)
+            w = counts[inverse].astype(np.float32)
+            w = w / w.sum()
+            g = G[:, d]
+            mean = np.sum(w * g)
+            avg[d] = mean
+            var[d] = np.sum(w * g ** 2) - mean ** 2
+        return avg, var, F.sum(axis=0)
+    max_occur = 7
+    avg, var, inc = np.zeros((D, max_occur)), np.zeros((D, max_occur)), np.zeros((D, max_occur))
+    for d in range(D):
+        vals, counts = np.unique(F[:, d], return_counts=True)
+        for i, val in enumerate(vals):
+            at = G[F[:, d] == val]
+            avg[d, int(val)] = at.mean()
+            with np.errstate(invalid="ignore", divide="ignore"):
+                var[d, int(val)] = at.var(ddof=1) if at.size > 1 else np.nan
+            inc[d, int(val)] = counts[i]
+    return avg, var, inc
+
+
 def incumbent(st: GPState) -> float:
     """_get_incumbent (acquisitions.py:82-92): `in_fill == 'max'` is never true (Q13), so the
     incumbent is y_raw[argmax of the posterior mean at the training points]."""

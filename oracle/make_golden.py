@@ -206,11 +206,52 @@ def cfg1_case(R, seed=11, n_train=50, n_test=400):
 
 
 
+def dmu_case(R, n_train=30, n_pool=20):
+    """Interpretability gradients (gp.py:296-476) from the unmodified reference: per family and
+    base kernel, GraphGP.dmu_dphi over a pool (raw Jacobian-vector products + the embedding they
+    belong to) and its three averaged forms."""
+    out = {}
+    for family, seed in (("nasbench101", 111), ("nasbench201", 211), ("darts", 311)):
+        seed_all(seed)
+        graphs = sample_cells(R, family, n_train + n_pool)
+        vocab = OpVocab()
+        batch = pack_networkx(graphs, vocab)
+        train, pool = graphs[:n_train], graphs[n_train:]
+        y = torch.randn(n_train)
+        out[family + "_records"] = batch.to_records()
+        out[family + "_n_max"] = np.int64(batch.n_max)
+        out[family + "_op_names"] = np.array(vocab.names)
+        out[family + "_y"] = y.numpy().astype(np.float32)
+        for oa in (False, True):
+            tag = "%s_oa%d_" % (family, int(oa))
+            # requires_grad=True = ordered feature columns (vertex_histogram.py:160-162), the setting of
+            # every interpretability consumer (interpreter.py:23, transfer_nasbench201.py:89)
+            gp = R.GraphGP(train, y.clone(), [R.WeisfilerLehman(h=2, oa=oa, requires_grad=True)])
+            gp.fit(wl_subtree_candidates=(1, 2), optimize_lik=True, max_lik=0.01)
+            out[tag + "h"] = np.int64(gp.kernels[0].h)
+            out[tag + "lik"] = np.float64(gp.likelihood)
+            raw, _, feat = gp.dmu_dphi(pool, average_across_features=False)
+            out[tag + "raw"] = torch.cat(raw).detach().numpy()
+            out[tag + "feat"] = feat.detach().numpy()
+            for nm, kw in (("occ", dict(average_across_occurrences=False)), ("avg", dict(average_across_occurrences=True))):
+                a, v, inc = gp.dmu_dphi(pool, **kw)
+                out[tag + nm + "_mu"], out[tag + nm + "_var"], out[tag + nm + "_inc"] = \
+                    a.detach().numpy(), v.detach().numpy(), inc.detach().numpy()
+            a, v, inc = gp.dmu_dphi()
+            out[tag + "train_mu"], out[tag + "train_var"], out[tag + "train_inc"] = \
+                a.detach().numpy(), v.detach().numpy(), inc.detach().numpy()
+    return out
+
+
 def main():
     R = load_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "dmu":        # only the interpretability fixture
+        np.savez_compressed(os.path.join(OUT, "dmu_dphi.npz"), **dmu_case(R))
+        return
     os.makedirs(OUT, exist_ok=True)
     np.savez_compressed(os.path.join(OUT, "appendix_b.npz"), **appendix_b(R))
     np.savez_compressed(os.path.join(OUT, "cfg1_nb101.npz"), **cfg1_case(R))
+    np.savez_compressed(os.path.join(OUT, "dmu_dphi.npz"), **dmu_case(R))
     for family, seed in (("nasbench101", 101), ("nasbench201", 201), ("darts", 301)):
         case = family_case(R, family, seed)
         np.savez_compressed(os.path.join(OUT, family + ".npz"), **case)

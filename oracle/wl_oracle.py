@@ -94,6 +94,108 @@ def wl_labels_reference_order(batch: CellBatch, h: int, op_names=None):
     return ids, dims
 
 
+def wl_embed_reference_order(train: CellBatch, pool: CellBatch, h: int, op_names=None, layout: str = "trimmed"):
+    """Histogram embeddings in the reference's feature order: X [n, W] of the training cells and
+    Y [M, W] of `pool` over the training vocabulary.
+
+    Training pass = wl_labels_reference_order (weisfeiler_lehman.py:223-296).  Transform pass
+    (:364-516), ONE pool cell at a time as GraphGP.dmu_dphi calls it (gp.py:358-362): a node's
+    credential is looked up in the training dictionary of its level; unknown credentials are numbered
+    feature_dims[l+1] + rank in sorted(unknown credentials of that cell) (:452-466).
+
+    layout:
+      "trimmed"  W = sum D_l: unseen labels dropped (feature_value, kernels/weisfilerlehman.py:259-261).
+      "padded"   W = sum (D_l + 1): each level block followed by one all-zero spare column — the
+                 shape of forward_t's embeddings (vertex_histogram.py:184) with unseen labels dropped.
+      "forward_t" exactly what forward_t hands to autograd (kernels/weisfilerlehman.py:206-215): the
+                 level block of a cell with u >= 1 unknown labels is D_l + u wide (unknown label of
+                 rank r sits in column D_l + r, so rank 0 lands in the spare column), the blocks are
+                 concatenated and only THEN cut to the training width — a cell with two or more
+                 unknown labels at a level shifts all its deeper levels.  Identical to "padded" for
+                 cells without unknown labels (every consumer passes the training cells)."""
+    assert layout in ("trimmed", "padded", "forward_t")
+    ids_t, dims = wl_labels_reference_order(train, h, op_names)
+    D = dims[-1][1]
+    n_max = train.labels.shape[1]
+    assert pool.labels.shape[1] == n_max
+    X = np.zeros((len(train), D))
+    for l in range(h + 1):
+        for g in range(len(train)):
+            for v in range(n_max):
+                if ids_t[l][g, v] >= 0:
+                    X[g, ids_t[l][g, v]] += 1
+    # training dictionaries, rebuilt from the labelled training nodes
+    present_t = train.labels != NO_NODE
+    name_of = (lambda c: op_names[c]) if op_names is not None else (lambda c: c)
+    level0 = {int(train.labels[g, v]): int(ids_t[0][g, v]) for g in range(len(train)) for v in range(n_max)
+              if present_t[g, v]}
+    cred_maps = []
+    end_t = _endpoint_mask(train)
+    for l in range(1, h + 1):
+        m = {}
+        for g in range(len(train)):
+            for v in range(n_max):
+                if end_t[g, v]:
+                    nb = sorted(int(ids_t[l - 1][g, j]) for j in _successors(int(train.succ[g, v]), n_max))
+                    m[str(int(ids_t[l - 1][g, v])) + "," + str(nb)] = int(ids_t[l][g, v])
+        cred_maps.append(m)
+    M = len(pool)
+    present_p = pool.labels != NO_NODE
+    end_p = _endpoint_mask(pool)
+    rows = []
+    for g in range(M):
+        blocks = []
+        # level 0
+        unknown = sorted({name_of(int(pool.labels[g, v])) for v in range(n_max)
+                          if present_p[g, v] and int(pool.labels[g, v]) not in level0})
+        cur = {}
+        seen_cnt = np.zeros(dims[0][1] - dims[0][0])
+        unk_cnt = np.zeros(len(unknown))
+        for v in range(n_max):
+            if not present_p[g, v]:
+                continue
+            c = int(pool.labels[g, v])
+            if c in level0:
+                cur[v] = level0[c]
+                seen_cnt[cur[v] - dims[0][0]] += 1
+            else:
+                r = unknown.index(name_of(c))
+                cur[v] = dims[0][1] + r
+                unk_cnt[r] += 1
+        blocks.append((seen_cnt, unk_cnt))
+        for l in range(1, h + 1):
+            creds = {}
+            for v in range(n_max):
+                if end_p[g, v]:
+                    nb = sorted(cur[j] for j in _successors(int(pool.succ[g, v]), n_max))
+                    creds[v] = str(cur[v]) + "," + str(nb)
+            unknown = sorted({c for c in creds.values() if c not in cred_maps[l - 1]})
+            seen_cnt = np.zeros(dims[l][1] - dims[l][0])
+            unk_cnt = np.zeros(len(unknown))
+            nxt = {}
+            for v, c in creds.items():
+                if c in cred_maps[l - 1]:
+                    nxt[v] = cred_maps[l - 1][c]
+                    seen_cnt[nxt[v] - dims[l][0]] += 1
+                else:
+                    r = unknown.index(c)
+                    nxt[v] = dims[l][1] + r
+                    unk_cnt[r] += 1
+            blocks.append((seen_cnt, unk_cnt))
+            cur = nxt
+        if layout == "trimmed":
+            rows.append(np.concatenate([b[0] for b in blocks]))
+        elif layout == "padded":
+            rows.append(np.concatenate([np.concatenate([b[0], [0.0]]) for b in blocks]))
+        else:
+            full = np.concatenate([np.concatenate([b[0], b[1] if len(b[1]) else [0.0]]) for b in blocks])
+            rows.append(full[:D + h + 1])
+    Y = np.array(rows).reshape(M, -1)
+    if layout != "trimmed":
+        X = np.concatenate([np.concatenate([X[:, a:b], np.zeros((len(train), 1))], axis=1) for (a, b) in dims], axis=1)
+    return X, Y
+
+
 def wl_labels_fast(batch: CellBatch, h: int):
     """Same partition as wl_labels_reference_order, ids local to each level (0..D_l-1) in
     ascending tuple order.  Vectorised: one np.unique over (own, sorted successor ids) rows."""

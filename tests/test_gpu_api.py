@@ -170,3 +170,57 @@ def test_bo_loop_matches_oracle_every_iteration():
 
     best, x, y = bo_loop.run(iters=4, pool_size=3000, batch_size=5, n_init=20, verbose=False, check=check)
     assert len(x) == 40 and best[-1] >= best[0]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("oa", [False, True])
+@pytest.mark.parametrize("fam", ["nasbench101", "nasbench201", "darts"])
+def test_dmu_dphi_matches_reference_and_oracle(fam, oa):
+    """GraphGP.dmu_dphi / forward_t / get_grad (gp.py:296-476).  Against the reference's golden
+    vectors on every cell inside the training vocabulary (incl. the training-set call all of the
+    reference's consumers make) and against the oracle's aligned form on every cell."""
+    import os
+    from nasbowl_b200.bayesopt import GraphGP
+    from nasbowl_b200.cells import CellBatch, OpVocab
+    from nasbowl_b200.kernels import WeisfilerLehman
+    from oracle import gp_oracle, wl_oracle
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "dmu_dphi.npz"))
+    batch = CellBatch.from_records(z[fam + "_records"], int(z[fam + "_n_max"]))
+    names = list(z[fam + "_op_names"])
+    y = z[fam + "_y"]
+    n = len(y)
+    train, pool = batch[:n], batch[n:]
+    tag = "%s_oa%d_" % (fam, int(oa))
+    k = WeisfilerLehman(h=2, oa=oa, requires_grad=True)
+    k.vocab = OpVocab(names)
+    gp = GraphGP(train, torch.tensor(y), [k], n_max=batch.n_max)
+    gp.fit(wl_subtree_candidates=(1, 2), optimize_lik=True, max_lik=0.01)
+    h = int(z[tag + "h"])
+    assert gp.kernels[0].h == h
+    raw, _, feat = gp.dmu_dphi(pool, average_across_features=False)
+    raw = torch.cat(raw).numpy()
+    # --- oracle, aligned layout, every pool cell
+    st = gp_oracle.gp_fit(train, y.astype(np.float64), h_candidates=(1, 2), oa=oa, optimize_lik=True, max_lik=0.01)
+    X, Y = wl_oracle.wl_embed_reference_order(train, pool, h, names, layout="padded")
+    assert np.array_equal(feat.numpy(), Y)
+    np.testing.assert_allclose(raw, gp_oracle.dmu_dphi(st, X, Y), rtol=1e-6, atol=1e-9)
+    # --- reference golden vectors on the cells without unknown labels
+    # (NB201 has few distinct cells, so its pool has many; the sparser families are covered by the
+    # training-set call below, where no label can be unknown)
+    clean = np.all(z[tag + "feat"] == Y, axis=1)
+    assert clean.sum() >= 3 or fam != "nasbench201"
+    np.testing.assert_allclose(raw[clean], z[tag + "raw"][clean], rtol=2e-3, atol=2e-5)
+    # --- the consumers' call: training cells, averaged per occurrence count
+    a, v, inc = gp.dmu_dphi()
+    np.testing.assert_allclose(a.numpy(), z[tag + "train_mu"], rtol=2e-3, atol=2e-5)
+    np.testing.assert_allclose(v.numpy(), z[tag + "train_var"], rtol=2e-2, atol=2e-5, equal_nan=True)
+    assert np.array_equal(inc.numpy(), z[tag + "train_inc"])
+    a2, v2, tot = gp.dmu_dphi(average_across_occurrences=True)
+    ao, vo, to = gp_oracle.get_grad(gp_oracle.dmu_dphi(st, X, X), X, True)
+    np.testing.assert_allclose(a2.numpy(), ao, rtol=1e-4, atol=1e-6)
+    assert np.array_equal(tot.numpy(), to)
+    # --- forward_t: autograd through the returned graph gives the same Jacobian-vector product
+    K, y_, x_ = k.forward_t(pool[:2])
+    alpha = torch.tensor(st.K_i @ st.y_norm).reshape(1, -1)
+    jv = torch.autograd.grad(outputs=K[:1], inputs=y_, grad_outputs=alpha)[0][0].numpy()
+    np.testing.assert_allclose(jv, raw[0], rtol=1e-5, atol=1e-8)

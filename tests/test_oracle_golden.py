@@ -1,6 +1,8 @@
 """The CPU oracle (oracle/*.py) against golden vectors produced by the unmodified reference
 (oracle/make_golden.py).  This is what pins parity: the GPU tests then compare the CUDA path
 against the oracle."""
+import os
+
 import numpy as np
 import pytest
 
@@ -147,3 +149,41 @@ def test_cfg1_regression_case():
     if top != ref_top:
         vals = [z["ei"][i] for i in top ^ ref_top]
         assert max(vals) - min(vals) < 1e-4 * max(1.0, abs(max(vals)))
+
+
+def _dmu_fixture(family):
+    from nasbowl_b200.cells import CellBatch
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "dmu_dphi.npz"))
+    batch = CellBatch.from_records(z[family + "_records"], int(z[family + "_n_max"]))
+    n = len(z[family + "_y"])
+    return z, batch[:n], batch[n:], list(z[family + "_op_names"])
+
+
+@pytest.mark.parametrize("oa", [False, True])
+@pytest.mark.parametrize("fam", ["nasbench101", "nasbench201", "darts"])
+def test_dmu_dphi_matches_reference(fam, oa):
+    """Interpretability gradients (gp.py:296-476): embeddings bit-exact, raw Jacobian-vector
+    products and the three averaged forms at fp32 tolerance (the reference's K_i is fp32)."""
+    z, train, pool, names = _dmu_fixture(fam)
+    tag = "%s_oa%d_" % (fam, int(oa))
+    h = int(z[tag + "h"])
+    st = gp_oracle.gp_fit(train, z[fam + "_y"].astype(np.float64), h_candidates=(1, 2), oa=oa, optimize_lik=True,
+                          max_lik=0.01)
+    assert st.h == h and abs(st.lik - float(z[tag + "lik"])) < 1e-7
+    X, Y = wl_oracle.wl_embed_reference_order(train, pool, h, names, layout="forward_t")
+    assert np.array_equal(Y, z[tag + "feat"])
+    # cells without labels outside the training vocabulary: the aligned layout is the same thing
+    Xp, Yp = wl_oracle.wl_embed_reference_order(train, pool, h, names, layout="padded")
+    _, Yt = wl_oracle.wl_embed_reference_order(train, pool, h, names, layout="trimmed")
+    clean = Yt.sum(axis=1) == Y.sum(axis=1)
+    assert np.array_equal(Xp, X) and np.array_equal(Yp[clean], Y[clean])
+    g = gp_oracle.dmu_dphi(st, X, Y)
+    np.testing.assert_allclose(g, z[tag + "raw"], rtol=2e-3, atol=2e-5)
+    for nm, avg in (("occ", False), ("avg", True)):
+        a, v, inc = gp_oracle.get_grad(g, Y, avg)
+        np.testing.assert_allclose(a, z[tag + nm + "_mu"], rtol=2e-3, atol=2e-5)
+        np.testing.assert_allclose(v, z[tag + nm + "_var"], rtol=5e-3, atol=2e-5, equal_nan=True)
+        assert np.array_equal(inc, z[tag + nm + "_inc"])
+    a, v, inc = gp_oracle.get_grad(gp_oracle.dmu_dphi(st, X, X), X, False)
+    np.testing.assert_allclose(a, z[tag + "train_mu"], rtol=2e-3, atol=2e-5)
+    assert np.array_equal(inc, z[tag + "train_inc"])
