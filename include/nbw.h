@@ -147,6 +147,16 @@ int nbw_chol_f64(nbw_ctx* ctx, const double* A, int64_t lda, int64_t n, double s
 int nbw_gp_factor(nbw_ctx* ctx, const double* K, int64_t ldk, int64_t n, double lik,
                   const double* y, double* L, int64_t ldl, double* Linv, int64_t ldi,
                   double* alpha, double* stats_h, int* info_h, void* stream);
+/* Gradient of the reference's marginal likelihood with respect to the weights of a SUM of kernels
+ * (GraphGP.fit trains them by autograd: bayesopt/gp.py:141-210 through combine_kernels.py:36-56 and
+ * utils.py:102-140).  Kinv = (N + lik I)^-1, alpha = Kinv y, N = normalised sum, inv_sqrt_diag from
+ * nbw_gram_normalize, R_h = HOST array of n_kernels device pointers to the raw fp64 Grams [n x n].
+ * Writes d nlml'/d w_i to grad_h[0..n_kernels).  Syncs. */
+int nbw_kernel_weight_grad(nbw_ctx* ctx, const double* Kinv, int64_t ldk, const double* alpha,
+                           const double* N, int64_t ldn, const double* inv_sqrt_diag, int64_t n,
+                           const double* const* R_h, int64_t ldr, int n_kernels, double* grad_h,
+                           void* stream);
+
 /* Linv = L^-1 (lower triangular) */
 int nbw_trtri_lower_f64(nbw_ctx* ctx, const double* L, int64_t ldl, int64_t n, double* Linv,
                         int64_t ldi, void* stream);

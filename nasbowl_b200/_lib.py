@@ -81,6 +81,8 @@ _PROTOTYPES = {
     "nbw_trtri_lower_f64": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i64, _vp]),
     "nbw_gemm_f64": (C.c_int, [_vp, _i32, _i32, _i64, _i64, _i64, _f64, _vp, _i64, _vp, _i64, _f64, _vp,
                                _i64, _vp]),
+    "nbw_kernel_weight_grad": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, C.POINTER(_vp), _i64, _i32,
+                                         C.POINTER(C.c_double), _vp]),
     "nbw_scale_features": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _f64, _vp, _i64, _vp]),
     "nbw_label_parents": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "nbw_prefix_features": (C.c_int, [_vp, _vp, _i64, _i64, _i32, C.POINTER(_i64), C.POINTER(_i64), _vp, _vp,

@@ -170,13 +170,12 @@ class GraphGP:
 
         # 2. K = sum_i w_i K_raw,i, cosine-normalised (combine_kernels.py:36-56)
         weights = self.weights.clone()
-        if (not self.fixed_weights) and len(self.kernels) > 1:
-            raise NotImplementedError("trainable kernel weights (gp.py:141-142) are not implemented on the "
-                                      "GPU path; pass weights=[...] to fix them")
+        train_weights = (not self.fixed_weights) and len(self.kernels) > 1
         grams = [k.gram_device(f) for k, f in zip(self.sum_kernels.kernels, fits)]
         K, inv_sqrt_diag = self.sum_kernels.combine_device(weights, grams, normalize=True)
 
-        # 3. noise: Adam / SGD on the scalar lambda with the reference's clamp (gp.py:153-210)
+        # 3. noise (and, for several kernels, their weights): Adam / SGD with the reference's clamps
+        #    (gp.py:141-210).  Gradients are closed-form device reductions instead of autograd.
         likelihood = torch.tensor(self.likelihood, )
         nlml = None
         factor_cache = {}
@@ -187,22 +186,42 @@ class GraphGP:
             if lam not in factor_cache:
                 factor_cache[lam] = eng.pd_inverse(K, lam, y_dev)
             return factor_cache[lam]
-        if optimize_lik:
-            likelihood.requires_grad_(True)
+        if optimize_lik or train_weights:
+            optim_vars = []
+            if train_weights:
+                weights.requires_grad_(True)
+                optim_vars.append(weights)
+            if optimize_lik:
+                likelihood.requires_grad_(True)
+                optim_vars.append(likelihood)
             assert optimizer.lower() in ['adam', 'sgd']
-            optim = (torch.optim.Adam if optimizer.lower() == 'adam' else torch.optim.SGD)([likelihood],
+            optim = (torch.optim.Adam if optimizer.lower() == 'adam' else torch.optim.SGD)(optim_vars,
                                                                                          **optimizer_kwargs)
             for i in range(iters):
                 optim.zero_grad()
-                _, _, _, logdet, yKy, trKinv, alpha_sq = factor(float(likelihood.item()))
+                if train_weights:
+                    # K moves with the weights: rebuild and refactor every iteration.  The K of the LAST
+                    # iteration (weights before the final step) is the one the reference keeps (gp.py:186-215).
+                    with torch.no_grad():
+                        K, inv_sqrt_diag = self.sum_kernels.combine_device(weights, grams, normalize=True)
+                    factor_cache.clear()
+                _, Linv_i, alpha_i, logdet, yKy, trKinv, alpha_sq = factor(float(likelihood.item()))
                 nlml = _nlml_from_stats(logdet, yKy, self.n)
-                # d nlml / d lambda = -(|K_l^-1 y|^2 + tr K_l^-1) / (2n): always negative (Q9)
-                likelihood.grad = torch.tensor(-(0.5 * alpha_sq + 0.5 * trKinv) / self.n, dtype=likelihood.dtype)
+                if train_weights:
+                    g = eng.kernel_weight_grad(Linv_i, alpha_i, K, inv_sqrt_diag, grams)
+                    weights.grad = torch.tensor(g, dtype=weights.dtype)
+                if optimize_lik:
+                    # d nlml / d lambda = -(|K_l^-1 y|^2 + tr K_l^-1) / (2n): always negative (Q9)
+                    likelihood.grad = torch.tensor(-(0.5 * alpha_sq + 0.5 * trKinv) / self.n, dtype=likelihood.dtype)
                 if self.verbose and i % 10 == 0:
                     print('Iteration:', i, "/", iters, 'Negative log-marginal likelihood:', nlml, weights, likelihood)
                 optim.step()
                 with torch.no_grad():
-                    likelihood.clamp_(1e-5, max_lik)
+                    if train_weights:
+                        weights.clamp_(0., 1.)
+                    if optimize_lik:
+                        likelihood.clamp_(1e-5, max_lik)
+            weights = weights.detach()
         lik = float(likelihood.item())
         L, Linv, alpha, logdet, yKy, _, _ = factor(lik)
 

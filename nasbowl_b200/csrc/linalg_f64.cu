@@ -511,6 +511,84 @@ extern "C" int nbw_gp_factor(nbw_ctx* ctx, const double* K, int64_t ldk, int64_t
   return NBW_OK;
 }
 
+// ====================================================================== gradient of the marginal likelihood w.r.t. kernel weights
+// GraphGP.fit trains the weights of a sum of kernels by autograd through
+//   K = normalise(sum_i w_i R_i) + lik I,  nlml' = (0.5 y^T K^-1 y - 0.5 log|K| + c) / n
+// (bayesopt/gp.py:141-210, kernels/combine_kernels.py:36-56, utils.py:102-140 incl. the sign of the
+// log-det term).  Closed form, with M = alpha alpha^T + K^-1, S = sum_i w_i R_i, s_j = S_jj^-1/2 and
+// N = normalise(S):
+//   d nlml' / d w_i = -1/(2n) [ sum_jk M_jk R_i,jk s_j s_k  -  sum_j R_i,jj s_j^2 (sum_k M_jk N_jk) ]
+namespace {
+
+// rowdot[j] = sum_k (alpha_j alpha_k + Kinv_jk) N_jk ; one block per row
+__global__ void __launch_bounds__(256)
+weight_grad_rowdot_kernel(const double* __restrict__ Kinv, int64_t ldk, const double* __restrict__ alpha,
+                          const double* __restrict__ N, int64_t ldn, int64_t n, double* __restrict__ rowdot) {
+  __shared__ double red[256];
+  const int64_t j = blockIdx.x;
+  const double aj = alpha[j];
+  double acc = 0.0;
+  for (int64_t k = threadIdx.x; k < n; k += blockDim.x) acc += (aj * alpha[k] + Kinv[j * ldk + k]) * N[j * ldn + k];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) rowdot[j] = red[0];
+}
+
+// out += sum_k M_jk R_jk s_j s_k - R_jj s_j^2 rowdot_j for row j = blockIdx.x
+__global__ void __launch_bounds__(256)
+weight_grad_kernel(const double* __restrict__ Kinv, int64_t ldk, const double* __restrict__ alpha,
+                   const double* __restrict__ R, int64_t ldr, const double* __restrict__ s,
+                   const double* __restrict__ rowdot, int64_t n, double* out) {
+  __shared__ double red[256];
+  const int64_t j = blockIdx.x;
+  const double aj = alpha[j], sj = s[j];
+  double acc = 0.0;
+  for (int64_t k = threadIdx.x; k < n; k += blockDim.x)
+    acc += (aj * alpha[k] + Kinv[j * ldk + k]) * R[j * ldr + k] * sj * s[k];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) atomicAdd(out, red[0] - R[j * ldr + j] * sj * sj * rowdot[j]);
+}
+
+}  // namespace
+
+extern "C" int nbw_kernel_weight_grad(nbw_ctx* ctx, const double* Kinv, int64_t ldk, const double* alpha,
+                                      const double* N, int64_t ldn, const double* inv_sqrt_diag, int64_t n,
+                                      const double* const* R_h, int64_t ldr, int n_kernels, double* grad_h,
+                                      void* stream) {
+  if (!ctx) return NBW_ERR_INVALID;
+  NBW_REQUIRE(ctx, n > 0 && ldk >= n && ldn >= n && ldr >= n && n_kernels >= 1 && n_kernels <= 16, "bad shape");
+  NBW_REQUIRE(ctx, n < 65536, "n too large for one block per row");
+  NBW_REQUIRE(ctx, Kinv && alpha && N && inv_sqrt_diag && R_h && grad_h, "null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = nbw_scratch_ensure(ctx, Carver::pad(sizeof(double) * n) + 4096, st);
+  if (rc) return rc;
+  Carver cv(ctx->scratch);
+  double* d_out = cv.take<double>(16);
+  double* rowdot = cv.take<double>(n);
+  NBW_CUDA(ctx, cudaMemsetAsync(d_out, 0, sizeof(double) * 16, st));
+  weight_grad_rowdot_kernel<<<(unsigned)n, 256, 0, st>>>(Kinv, ldk, alpha, N, ldn, n, rowdot);
+  NBW_CHECK_LAUNCH(ctx);
+  for (int i = 0; i < n_kernels; ++i) {
+    NBW_REQUIRE(ctx, R_h[i] != nullptr, "R_h[%d] is NULL", i);
+    weight_grad_kernel<<<(unsigned)n, 256, 0, st>>>(Kinv, ldk, alpha, R_h[i], ldr, inv_sqrt_diag, rowdot, n, d_out + i);
+    NBW_CHECK_LAUNCH(ctx);
+  }
+  double hs[16];
+  NBW_CUDA(ctx, cudaMemcpyAsync(hs, d_out, sizeof(hs), cudaMemcpyDeviceToHost, st));
+  NBW_CUDA(ctx, cudaStreamSynchronize(st));
+  for (int i = 0; i < n_kernels; ++i) grad_h[i] = -hs[i] / (2.0 * (double)n);
+  return NBW_OK;
+}
+
 // ====================================================================== prefix form of the pool model
 namespace {
 

@@ -262,6 +262,19 @@ class Engine:
                 last = e
         raise RuntimeError("Gram matrix not positive definite despite of jitter") from last
 
+    def kernel_weight_grad(self, Linv: torch.Tensor, alpha: torch.Tensor, N: torch.Tensor, s: torch.Tensor,
+                           raw_grams: Sequence[torch.Tensor]) -> List[float]:
+        """d nlml'/d w_i for K = normalise(sum_i w_i R_i) + lik I (nbw_kernel_weight_grad)."""
+        n = N.shape[0]
+        Kinv = self.empty((n, n), torch.float64)
+        self.gemm(True, False, n, n, n, 1.0, Linv, n, Linv, n, 0.0, Kinv, n)
+        ptrs = (C.c_void_p * len(raw_grams))(*[C.c_void_p(R.data_ptr()) for R in raw_grams])
+        grad = (C.c_double * len(raw_grams))()
+        self._check(self.lib.nbw_kernel_weight_grad(self.ctx, self._p(Kinv), n, self._p(alpha), self._p(N),
+                                                    N.stride(0), self._p(s), n, ptrs, raw_grams[0].stride(0),
+                                                    len(raw_grams), grad, self.stream))
+        return [float(g) for g in grad]
+
     def scale_features(self, phi: torch.Tensor, k0: int, k1: int, s: torch.Tensor, sqrt_w: float,
                        out: torch.Tensor, ldo: int):
         n = phi.shape[0]

@@ -8,6 +8,7 @@ Not part of the product (see oracle/wl_oracle.py header).  Follows, formula by f
 * WL-depth grid search         bayesopt/gp.py:493-538       (un-normalised Gram, strict <, Q5)
 * cosine normalisation         kernels/combine_kernels.py:36-56
 * noise optimisation (Adam)    bayesopt/gp.py:179-219       (Q9)
+* trainable kernel weights     bayesopt/gp.py:139-212 + kernels/combine_kernels.py:36-56
 * posterior                    bayesopt/gp.py:240-283       (Q11)
 * EI / AEI / UCB, incumbent    bayesopt/acquisitions.py:59-92,130-138 (Q12-Q14)
 * top-n distinct by value      bayesopt/acquisitions.py:94-113 (Q15)
@@ -159,6 +160,105 @@ def gp_fit(train, y, h_candidates: Sequence[int] = tuple(range(5)), oa: bool = F
     return GPState(h=h_star, oa=oa, lik=lik, y_mean=float(y_mean), y_std=float(y_std),
                    y_norm=y_norm, y_raw=y, K=K, K_i=K_i, logDetK=ld, L=L,
                    diag_raw=np.diag(K_raw).astype(np.float64), nlml=nlml, nlml_grid=grid)
+
+
+@dataclass
+class SumGPState:
+    """State of a GraphGP over a SUM of WL kernels with trained weights (gp.py:139-219)."""
+    hs: list
+    oas: list
+    weights: np.ndarray      # as stored: post-step weights / their sum (gp.py:212)
+    lik: float
+    y_mean: float
+    y_std: float
+    y_norm: np.ndarray
+    y_raw: np.ndarray
+    K: np.ndarray            # the Gram of the LAST loop iteration (weights before the final step)
+    K_i: np.ndarray
+    nlml: Optional[float] = None
+
+
+def weight_gradient(K_i, alpha, S, raws, n):
+    """d nlml'/d w_i of nlml' = (0.5 y^T K^-1 y - 0.5 log|K| + c)/n with K = normalise(S) + lik I,
+    S = sum_i w_i R_i — the closed form of what the reference gets by autograd through
+    combine_kernels.py:36-56 and utils.py:102-140."""
+    Mm = np.outer(alpha, alpha) + K_i
+    s = 1.0 / np.sqrt(np.diag(S))
+    N = S * np.outer(s, s)
+    rowdot = (Mm * N).sum(axis=1)
+    out = []
+    for R in raws:
+        out.append(-((Mm * R * np.outer(s, s)).sum() - (np.diag(R) * s * s * rowdot).sum()) / (2.0 * n))
+    return np.array(out)
+
+
+def gp_fit_sum(train, y, kernels, h_candidates: Sequence[int] = tuple(range(5)), likelihood: float = 1e-3,
+               optimize_lik: bool = True, max_lik: float = 0.01, iters: int = 20, lr: float = 0.1,
+               optimizer: str = "adam") -> SumGPState:
+    """GraphGP([k_1, ..., k_m]).fit(...) with trainable kernel weights (gp.py:107-238).
+    kernels: [(h_initial, oa), ...].  Every kernel gets its own depth by the grid search of
+    gp.py:493-538; then Adam (fp32 state, lr 0.1) moves [weights, lambda] together, weights clamped
+    to [0, 1] and lambda to [1e-5, max_lik] after each step (:199-207)."""
+    y = np.asarray(y, dtype=np.float64)
+    y_norm, y_mean, y_std = normalize_y(y)
+    n = len(y)
+    lik0 = f32(likelihood)
+    hs, raws = [], []
+    for (h0, oa) in kernels:
+        if len(h_candidates):
+            K_levels = wl_oracle.gram_raw_levels(train, max(h_candidates), oa)
+            h_star, _ = grid_search_h(K_levels, y_norm, lik0, h_candidates)
+            raws.append(K_levels[:h_star + 1].sum(axis=0).astype(np.float64))
+        else:
+            h_star = h0
+            raws.append(wl_oracle.gram_raw(train, h_star, oa).astype(np.float64))
+        hs.append(h_star)
+    m = len(kernels)
+    x = np.array([1.0 / m] * m + [lik0], dtype=np.float32)            # optimiser variables: weights, lambda
+    n_opt = m + (1 if optimize_lik else 0)
+    mom, vel = np.zeros(m + 1, dtype=np.float32), np.zeros(m + 1, dtype=np.float32)
+    b1, b2, eps = np.float32(0.9), np.float32(0.999), np.float32(1e-8)
+    K = None
+    last = None
+    for t in range(1, iters + 1):
+        S = sum(float(x[i]) * raws[i] for i in range(m))
+        K = normalize_gram(S)
+        K_i, ld, _ = pd_inverse(K, float(x[m]))
+        last = nlml_prime(K_i, ld, y_norm)
+        alpha = K_i @ y_norm
+        g = np.zeros(m + 1, dtype=np.float32)
+        g[:m] = weight_gradient(K_i, alpha, S, raws, n).astype(np.float32)
+        g[m] = np.float32(-(0.5 * float(alpha @ alpha) + 0.5 * float(np.trace(K_i))) / n)
+        mom = b1 * mom + (np.float32(1) - b1) * g
+        vel = b2 * vel + (np.float32(1) - b2) * g * g
+        bc1, bc2 = np.float32(1.0 - 0.9 ** t), np.float32(1.0 - 0.999 ** t)
+        step = (np.float32(lr) / bc1) * (mom / (np.sqrt(vel) / np.sqrt(bc2) + eps))
+        if optimizer == "sgd":
+            step = np.float32(lr) * g
+        x[:n_opt] = (x - step.astype(np.float32))[:n_opt]
+        x[:m] = np.clip(x[:m], np.float32(0.0), np.float32(1.0))
+        x[m] = np.float32(min(max(x[m], np.float32(1e-5)), np.float32(max_lik)))
+    lik = float(x[m])
+    K_i, _, _ = pd_inverse(K, lik)
+    w = x[:m].astype(np.float64)
+    return SumGPState(hs=hs, oas=[oa for _, oa in kernels], weights=w / w.sum(), lik=lik, y_mean=float(y_mean),
+                      y_std=float(y_std), y_norm=y_norm, y_raw=y, K=K, K_i=K_i, nlml=last)
+
+
+def gp_predict_full_sum(st: SumGPState, train, pool):
+    """predict() of the multi-kernel GP (gp.py:240-283): joint Grams per kernel at the fitted depths,
+    weighted by the STORED weights (which are one optimiser step ahead of K_i, as in the reference)."""
+    n, M = len(train), len(pool)
+    from nasbowl_b200.cells import CellBatch
+    joint = CellBatch.concat([train, pool])
+    S = sum(w * wl_oracle.gram_raw(joint, h, oa).astype(np.float64) for w, h, oa in zip(st.weights, st.hs, st.oas))
+    K_full = normalize_gram(S)
+    K_s = K_full[:n, n:]
+    K_ss = K_full[n:, n:] + st.lik * np.eye(M)
+    mu = (K_s.T @ st.K_i @ st.y_norm) * st.y_std + st.y_mean
+    cov = np.maximum(K_ss - K_s.T @ st.K_i @ K_s, st.lik)
+    cov = (np.sqrt(cov) * st.y_std) ** 2
+    return mu, cov
 
 
 def gp_predict_diag(st: GPState, train, pool, chunk: int = 4096):

@@ -72,8 +72,6 @@ def test_two_kernels_fixed_weights_dense_predict(family):
     assert torch.allclose(gp.weights.double(), torch.tensor(w, dtype=torch.float64))
     with pytest.raises(NotImplementedError):
         gp.predict_diag(pool)                  # the fused pool path is single-kernel
-    with pytest.raises(NotImplementedError):   # trainable kernel weights are not on the GPU path
-        GraphGP(train, torch.tensor(y), [WeisfilerLehman(h=1), WeisfilerLehman(h=2)]).fit(wl_subtree_candidates=())
 
 
 def test_pickle_roundtrip_and_refit(family):
@@ -224,3 +222,51 @@ def test_dmu_dphi_matches_reference_and_oracle(fam, oa):
     alpha = torch.tensor(st.K_i @ st.y_norm).reshape(1, -1)
     jv = torch.autograd.grad(outputs=K[:1], inputs=y_, grad_outputs=alpha)[0][0].numpy()
     np.testing.assert_allclose(jv, raw[0], rtol=1e-5, atol=1e-8)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fam", ["nasbench101", "nasbench201"])
+def test_multi_kernel_trainable_weights(fam):
+    """GraphGP over a sum of two WL kernels: the kernel weights are trained with the noise
+    (gp.py:139-212) from closed-form device gradients (nbw_kernel_weight_grad)."""
+    import os
+    from nasbowl_b200.bayesopt import GraphGP
+    from nasbowl_b200.cells import CellBatch, OpVocab
+    from nasbowl_b200.kernels import WeisfilerLehman
+    from oracle import gp_oracle
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "multi_kernel.npz"))
+    batch = CellBatch.from_records(z[fam + "_records"], int(z[fam + "_n_max"]))
+    y = z[fam + "_y"]
+    n = len(y)
+    train, pool = batch[:n], batch[n:]
+
+    def kernels():
+        ks = [WeisfilerLehman(h=1, oa=False), WeisfilerLehman(h=2, oa=True)]
+        for k in ks:
+            k.vocab = OpVocab(list(z[fam + "_op_names"]))
+        return ks
+    gp = GraphGP(train, torch.tensor(y), kernels(), n_max=batch.n_max)
+    gp.fit(wl_subtree_candidates=(0, 1, 2), optimize_lik=True, max_lik=0.01)
+    st = gp_oracle.gp_fit_sum(train, y.astype(np.float64), [(1, False), (2, True)], h_candidates=(0, 1, 2),
+                              optimize_lik=True, max_lik=0.01)
+    assert [k.h for k in gp.kernels] == st.hs == list(z[fam + "_hs"])
+    np.testing.assert_allclose(gp.weights.numpy(), st.weights, atol=1e-6)
+    np.testing.assert_allclose(gp.weights.numpy(), z[fam + "_weights"], atol=1e-6)
+    assert abs(gp.likelihood - st.lik) < 1e-9
+    np.testing.assert_allclose(gp.K.numpy(), st.K, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(gp.K_i.numpy(), st.K_i, rtol=1e-6, atol=1e-6 * np.abs(st.K_i).max())
+    np.testing.assert_allclose(float(gp.nlml), st.nlml, rtol=1e-8)
+    mu, cov = gp.predict(pool)
+    mo, co = gp_oracle.gp_predict_full_sum(st, train, pool)
+    np.testing.assert_allclose(mu.numpy(), mo, rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(cov.numpy(), co, rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(mu.numpy(), z[fam + "_mu"], rtol=2e-3, atol=2e-3)
+    # gradient values: three small SGD steps
+    gp2 = GraphGP(train, torch.tensor(y), kernels(), n_max=batch.n_max)
+    gp2.fit(iters=3, optimizer='sgd', optimizer_kwargs={'lr': 0.02}, wl_subtree_candidates=(), optimize_lik=True,
+            max_lik=0.01)
+    np.testing.assert_allclose(gp2.weights.numpy(), z[fam + "_sgd_weights"], rtol=1e-4)
+    # fixed weights are left alone
+    gp3 = GraphGP(train, torch.tensor(y), kernels(), weights=[0.3, 0.7], n_max=batch.n_max)
+    gp3.fit(wl_subtree_candidates=(), optimize_lik=False)
+    np.testing.assert_allclose(gp3.weights.numpy(), [0.3, 0.7], rtol=1e-6)

@@ -187,3 +187,30 @@ def test_dmu_dphi_matches_reference(fam, oa):
     a, v, inc = gp_oracle.get_grad(gp_oracle.dmu_dphi(st, X, X), X, False)
     np.testing.assert_allclose(a, z[tag + "train_mu"], rtol=2e-3, atol=2e-5)
     assert np.array_equal(inc, z[tag + "train_inc"])
+
+
+@pytest.mark.parametrize("fam", ["nasbench101", "nasbench201"])
+def test_multi_kernel_trainable_weights(fam):
+    """Sum of two WL kernels with trained weights (gp.py:139-212): depth per kernel, weights, noise,
+    K of the last iteration, K_i, predictions.  Three SGD steps pin the gradient values (Adam's
+    sign-driven steps run into the [0, 1] clamp)."""
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "multi_kernel.npz"))
+    batch = CellBatch.from_records(z[fam + "_records"], int(z[fam + "_n_max"]))
+    y = z[fam + "_y"].astype(np.float64)
+    n = len(y)
+    train, pool = batch[:n], batch[n:]
+    kernels = [(1, False), (2, True)]
+    st = gp_oracle.gp_fit_sum(train, y, kernels, h_candidates=(0, 1, 2), optimize_lik=True, max_lik=0.01)
+    assert st.hs == list(z[fam + "_hs"])
+    np.testing.assert_allclose(st.weights, z[fam + "_weights"], atol=1e-6)
+    assert abs(st.lik - float(z[fam + "_lik"])) < 1e-7
+    np.testing.assert_allclose(st.nlml, float(z[fam + "_nlml"]), rtol=2e-3)
+    np.testing.assert_allclose(st.K, z[fam + "_K"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(st.K_i, z[fam + "_Ki"], rtol=5e-3, atol=5e-3 * np.abs(z[fam + "_Ki"]).max())
+    mu, cov = gp_oracle.gp_predict_full_sum(st, train, pool)
+    np.testing.assert_allclose(mu, z[fam + "_mu"], rtol=2e-3, atol=2e-3)
+    np.testing.assert_allclose(cov, z[fam + "_cov"], rtol=5e-3, atol=1e-4)
+    sg = gp_oracle.gp_fit_sum(train, y, kernels, h_candidates=(), optimize_lik=True, max_lik=0.01, iters=3, lr=0.02,
+                              optimizer="sgd")
+    np.testing.assert_allclose(sg.weights, z[fam + "_sgd_weights"], rtol=1e-4)
+    np.testing.assert_allclose(sg.nlml, float(z[fam + "_sgd_nlml"]), rtol=2e-3)
