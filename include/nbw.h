@@ -150,7 +150,8 @@ int nbw_gp_factor(nbw_ctx* ctx, const double* K, int64_t ldk, int64_t n, double 
 /* Gradient of the reference's marginal likelihood with respect to the weights of a SUM of kernels
  * (GraphGP.fit trains them by autograd: bayesopt/gp.py:141-210 through combine_kernels.py:36-56 and
  * utils.py:102-140).  Kinv = (N + lik I)^-1, alpha = Kinv y, N = normalised sum, inv_sqrt_diag from
- * nbw_gram_normalize, R_h = HOST array of n_kernels device pointers to the raw fp64 Grams [n x n].
+ * nbw_gram_normalize, R_h = HOST array of n_kernels (<= 64) device pointers to raw fp64 Grams [n x n]
+ * (the form is linear in R, so per-level Grams give the layer-weight gradients the same way).
  * Writes d nlml'/d w_i to grad_h[0..n_kernels).  Syncs. */
 int nbw_kernel_weight_grad(nbw_ctx* ctx, const double* Kinv, int64_t ldk, const double* alpha,
                            const double* N, int64_t ldn, const double* inv_sqrt_diag, int64_t n,

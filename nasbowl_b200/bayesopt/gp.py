@@ -145,8 +145,6 @@ class GraphGP:
             optimize_wl_layer_weights=False, optimizer_kwargs=None):
         if optimizer_kwargs is None:
             optimizer_kwargs = {'lr': 0.1}
-        if optimize_wl_layer_weights:
-            raise NotImplementedError("optimize_wl_layer_weights is outside the GPU hot path")
         eng = self._engine()
         batch = self._pack(self.x)
         if self.n_max is not None:
@@ -171,11 +169,45 @@ class GraphGP:
         # 2. K = sum_i w_i K_raw,i, cosine-normalised (combine_kernels.py:36-56)
         weights = self.weights.clone()
         train_weights = (not self.fixed_weights) and len(self.kernels) > 1
-        grams = [k.gram_device(f) for k, f in zip(self.sum_kernels.kernels, fits)]
-        K, inv_sqrt_diag = self.sum_kernels.combine_device(weights, grams, normalize=True)
+        kernels = self.sum_kernels.kernels
+        # trainable WL layer weights (gp.py:157-165): a vector of ones as long as the first kernel with
+        # more than one level; kernels of another depth keep ones (weisfeiler_lehman.py:126-127)
+        layer_weights = None
+        if optimize_wl_layer_weights:
+            for k in kernels:
+                if k.h + 1 > 1:
+                    layer_weights = torch.ones(k.h + 1)
+                    break
+        shares = [layer_weights is not None and k.h + 1 == layer_weights.shape[0] for k in kernels]
+        levels = None
+        if train_weights or layer_weights is not None:
+            levels = [k.level_grams_device(f) for k, f in zip(kernels, fits)]
 
-        # 3. noise (and, for several kernels, their weights): Adam / SGD with the reference's clamps
-        #    (gp.py:141-210).  Gradients are closed-form device reductions instead of autograd.
+        own_lw = [k._level_weights(k.h) for k in kernels]      # fixed, user-given layer weights (or None = ones)
+
+        def level_weight(ki, l):
+            if shares[ki]:
+                return float(layer_weights.detach()[l])
+            return 1.0 if own_lw[ki] is None else float(own_lw[ki][l])
+
+        def build_K():
+            """Raw Gram per kernel from its level Grams and the current layer weights, then the
+            weighted, cosine-normalised sum."""
+            if layer_weights is None:
+                gr = [k.gram_device(f) for k, f in zip(kernels, fits)]
+            else:
+                gr = []
+                for i, k in enumerate(kernels):
+                    R = eng.empty((self.n, self.n), torch.float64)
+                    for l, Kl in enumerate(levels[i]):
+                        eng.axpby(Kl, level_weight(i, l), 0.0 if l == 0 else 1.0, R)
+                    gr.append(R)
+            return self.sum_kernels.combine_device(weights, gr, normalize=True)
+        K, inv_sqrt_diag = build_K()
+
+        # 3. noise (and, for several kernels, their weights; optionally the layer weights): Adam / SGD
+        #    with the reference's clamps (gp.py:141-210).  Gradients are closed-form device reductions
+        #    instead of autograd.
         likelihood = torch.tensor(self.likelihood, )
         nlml = None
         factor_cache = {}
@@ -186,7 +218,7 @@ class GraphGP:
             if lam not in factor_cache:
                 factor_cache[lam] = eng.pd_inverse(K, lam, y_dev)
             return factor_cache[lam]
-        if optimize_lik or train_weights:
+        if optimize_lik or levels is not None:
             optim_vars = []
             if train_weights:
                 weights.requires_grad_(True)
@@ -194,22 +226,39 @@ class GraphGP:
             if optimize_lik:
                 likelihood.requires_grad_(True)
                 optim_vars.append(likelihood)
+            if layer_weights is not None:
+                layer_weights.requires_grad_(True)
+                optim_vars.append(layer_weights)
             assert optimizer.lower() in ['adam', 'sgd']
             optim = (torch.optim.Adam if optimizer.lower() == 'adam' else torch.optim.SGD)(optim_vars,
                                                                                          **optimizer_kwargs)
             for i in range(iters):
                 optim.zero_grad()
-                if train_weights:
+                if levels is not None:
                     # K moves with the weights: rebuild and refactor every iteration.  The K of the LAST
                     # iteration (weights before the final step) is the one the reference keeps (gp.py:186-215).
                     with torch.no_grad():
-                        K, inv_sqrt_diag = self.sum_kernels.combine_device(weights, grams, normalize=True)
+                        K, inv_sqrt_diag = build_K()
                     factor_cache.clear()
                 _, Linv_i, alpha_i, logdet, yKy, trKinv, alpha_sq = factor(float(likelihood.item()))
                 nlml = _nlml_from_stats(logdet, yKy, self.n)
-                if train_weights:
-                    g = eng.kernel_weight_grad(Linv_i, alpha_i, K, inv_sqrt_diag, grams)
-                    weights.grad = torch.tensor(g, dtype=weights.dtype)
+                if levels is not None:
+                    # the gradient form is linear in the raw Gram: one value per (kernel, level) Gram
+                    flat = [Kl for lev in levels for Kl in lev]
+                    g = eng.kernel_weight_grad(Linv_i, alpha_i, K, inv_sqrt_diag, flat)
+                    gw = torch.zeros(len(kernels))
+                    glw = torch.zeros(layer_weights.shape[0]) if layer_weights is not None else None
+                    pos = 0
+                    for ki, lev in enumerate(levels):
+                        for l in range(len(lev)):
+                            gw[ki] += level_weight(ki, l) * g[pos]
+                            if shares[ki]:
+                                glw[l] += float(weights.detach()[ki]) * g[pos]
+                            pos += 1
+                    if train_weights:
+                        weights.grad = gw.to(weights.dtype)
+                    if layer_weights is not None:
+                        layer_weights.grad = glw.to(layer_weights.dtype)
                 if optimize_lik:
                     # d nlml / d lambda = -(|K_l^-1 y|^2 + tr K_l^-1) / (2n): always negative (Q9)
                     likelihood.grad = torch.tensor(-(0.5 * alpha_sq + 0.5 * trKinv) / self.n, dtype=likelihood.dtype)
@@ -221,7 +270,15 @@ class GraphGP:
                         weights.clamp_(0., 1.)
                     if optimize_lik:
                         likelihood.clamp_(1e-5, max_lik)
+                    if layer_weights is not None:
+                        layer_weights.clamp_(0., 1.)
             weights = weights.detach()
+        if layer_weights is not None:
+            layer_weights = layer_weights.detach()
+            for ki, k in enumerate(kernels):       # predict() runs with the final layer weights (gp.py:218,269)
+                if shares[ki]:
+                    k.change_kernel_params({'layer_weights': layer_weights.clone()})
+        self.layer_weights = layer_weights
         lik = float(likelihood.item())
         L, Linv, alpha, logdet, yKy, _, _ = factor(lik)
 
@@ -310,6 +367,8 @@ class GraphGP:
             return d['score']
         if len(self.sum_kernels.kernels) != 1:
             raise NotImplementedError("the fused pool path handles a single WL kernel; use predict()")
+        if self.sum_kernels.kernels[0]._level_weights(d['hs'][0]) is not None:
+            raise NotImplementedError("the fused pool path assumes unit WL layer weights; use predict()")
         eng, n = d['eng'], self.n
         fit, h, w = d['fits'][0], d['hs'][0], d['weights'][0]
         D = fit.k_end(h)

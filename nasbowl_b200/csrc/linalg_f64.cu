@@ -565,16 +565,16 @@ extern "C" int nbw_kernel_weight_grad(nbw_ctx* ctx, const double* Kinv, int64_t 
                                       const double* const* R_h, int64_t ldr, int n_kernels, double* grad_h,
                                       void* stream) {
   if (!ctx) return NBW_ERR_INVALID;
-  NBW_REQUIRE(ctx, n > 0 && ldk >= n && ldn >= n && ldr >= n && n_kernels >= 1 && n_kernels <= 16, "bad shape");
+  NBW_REQUIRE(ctx, n > 0 && ldk >= n && ldn >= n && ldr >= n && n_kernels >= 1 && n_kernels <= 64, "bad shape");
   NBW_REQUIRE(ctx, n < 65536, "n too large for one block per row");
   NBW_REQUIRE(ctx, Kinv && alpha && N && inv_sqrt_diag && R_h && grad_h, "null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc = nbw_scratch_ensure(ctx, Carver::pad(sizeof(double) * n) + 4096, st);
   if (rc) return rc;
   Carver cv(ctx->scratch);
-  double* d_out = cv.take<double>(16);
+  double* d_out = cv.take<double>(64);
   double* rowdot = cv.take<double>(n);
-  NBW_CUDA(ctx, cudaMemsetAsync(d_out, 0, sizeof(double) * 16, st));
+  NBW_CUDA(ctx, cudaMemsetAsync(d_out, 0, sizeof(double) * 64, st));
   weight_grad_rowdot_kernel<<<(unsigned)n, 256, 0, st>>>(Kinv, ldk, alpha, N, ldn, n, rowdot);
   NBW_CHECK_LAUNCH(ctx);
   for (int i = 0; i < n_kernels; ++i) {
@@ -582,7 +582,7 @@ extern "C" int nbw_kernel_weight_grad(nbw_ctx* ctx, const double* Kinv, int64_t 
     weight_grad_kernel<<<(unsigned)n, 256, 0, st>>>(Kinv, ldk, alpha, R_h[i], ldr, inv_sqrt_diag, rowdot, n, d_out + i);
     NBW_CHECK_LAUNCH(ctx);
   }
-  double hs[16];
+  double hs[64];
   NBW_CUDA(ctx, cudaMemcpyAsync(hs, d_out, sizeof(hs), cudaMemcpyDeviceToHost, st));
   NBW_CUDA(ctx, cudaStreamSynchronize(st));
   for (int i = 0; i < n_kernels; ++i) grad_h[i] = -hs[i] / (2.0 * (double)n);

@@ -125,6 +125,19 @@ class WeisfilerLehman(GraphKernels):
                 eng.gram_accumulate(Ki, float(lw[l]), 0.0 if l == 0 else 1.0, out)
         return out
 
+    def level_grams_device(self, fit, h: Optional[int] = None) -> List[torch.Tensor]:
+        """fp64 device Grams of the single WL levels 0..h (K_raw = sum_l w_l K_l)."""
+        from ..engine import Engine
+        eng = Engine.get()
+        h = self.h if h is None else h
+        n = fit.n_cells
+        out = []
+        for l in range(h + 1):
+            Kl = eng.empty((n, n), torch.float64)
+            eng.gram_accumulate(eng.gram(fit.phi, fit.phi, fit.col_off[l], fit.col_off[l + 1]), 1.0, 0.0, Kl)
+            out.append(Kl)
+        return out
+
     def fit_transform(self, gr: list, rebuild_model=False, save_gram_matrix=True, layer_weights=None, **kwargs):
         if rebuild_model is False and self._gram is not None:
             return self._gram

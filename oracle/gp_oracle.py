@@ -194,40 +194,58 @@ def weight_gradient(K_i, alpha, S, raws, n):
 
 def gp_fit_sum(train, y, kernels, h_candidates: Sequence[int] = tuple(range(5)), likelihood: float = 1e-3,
                optimize_lik: bool = True, max_lik: float = 0.01, iters: int = 20, lr: float = 0.1,
-               optimizer: str = "adam") -> SumGPState:
-    """GraphGP([k_1, ..., k_m]).fit(...) with trainable kernel weights (gp.py:107-238).
-    kernels: [(h_initial, oa), ...].  Every kernel gets its own depth by the grid search of
-    gp.py:493-538; then Adam (fp32 state, lr 0.1) moves [weights, lambda] together, weights clamped
-    to [0, 1] and lambda to [1e-5, max_lik] after each step (:199-207)."""
+               optimizer: str = "adam", optimize_layer_weights: bool = False) -> SumGPState:
+    """GraphGP([k_1, ..., k_m]).fit(...) with trainable kernel weights and, optionally, trainable WL
+    layer weights (gp.py:107-238).  kernels: [(h_initial, oa), ...].  Every kernel gets its own depth
+    by the grid search of gp.py:493-538; then Adam (fp32 state, lr 0.1) moves [weights (if m > 1),
+    lambda, layer weights] together; weights and layer weights are clamped to [0, 1], lambda to
+    [1e-5, max_lik] after each step (:199-208).  The layer-weight vector has the length of the first
+    kernel with more than one level (:158-165) and applies to every kernel of that depth; the others
+    fall back to ones (weisfeiler_lehman.py:126-127)."""
     y = np.asarray(y, dtype=np.float64)
     y_norm, y_mean, y_std = normalize_y(y)
     n = len(y)
     lik0 = f32(likelihood)
-    hs, raws = [], []
+    hs, levels = [], []
     for (h0, oa) in kernels:
         if len(h_candidates):
             K_levels = wl_oracle.gram_raw_levels(train, max(h_candidates), oa)
             h_star, _ = grid_search_h(K_levels, y_norm, lik0, h_candidates)
-            raws.append(K_levels[:h_star + 1].sum(axis=0).astype(np.float64))
         else:
             h_star = h0
-            raws.append(wl_oracle.gram_raw(train, h_star, oa).astype(np.float64))
+            K_levels = wl_oracle.gram_raw_levels(train, h_star, oa)
+        levels.append([K_levels[l].astype(np.float64) for l in range(h_star + 1)])
         hs.append(h_star)
     m = len(kernels)
-    x = np.array([1.0 / m] * m + [lik0], dtype=np.float32)            # optimiser variables: weights, lambda
-    n_opt = m + (1 if optimize_lik else 0)
-    mom, vel = np.zeros(m + 1, dtype=np.float32), np.zeros(m + 1, dtype=np.float32)
+    n_lw = 0
+    if optimize_layer_weights:
+        for h in hs:
+            if h + 1 > 1:
+                n_lw = h + 1
+                break
+    shares = [n_lw > 0 and h + 1 == n_lw for h in hs]              # kernels the layer weights apply to
+    x = np.array([1.0 / m] * m + [lik0] + [1.0] * n_lw, dtype=np.float32)
+    trainable = np.array([m > 1] * m + [optimize_lik] + [True] * n_lw)
+    mom, vel = np.zeros_like(x), np.zeros_like(x)
     b1, b2, eps = np.float32(0.9), np.float32(0.999), np.float32(1e-8)
     K = None
     last = None
+
+    def kernel_gram(i, lw):
+        return sum((float(lw[l]) if shares[i] else 1.0) * levels[i][l] for l in range(hs[i] + 1))
     for t in range(1, iters + 1):
-        S = sum(float(x[i]) * raws[i] for i in range(m))
+        lw = x[m + 1:]
+        S = sum(float(x[i]) * kernel_gram(i, lw) for i in range(m))
         K = normalize_gram(S)
         K_i, ld, _ = pd_inverse(K, float(x[m]))
         last = nlml_prime(K_i, ld, y_norm)
         alpha = K_i @ y_norm
-        g = np.zeros(m + 1, dtype=np.float32)
-        g[:m] = weight_gradient(K_i, alpha, S, raws, n).astype(np.float32)
+        g = np.zeros_like(x)
+        for i in range(m):
+            gl = weight_gradient(K_i, alpha, S, levels[i], n)      # the form is linear in R: one value per level Gram
+            g[i] = np.float32(sum((float(lw[l]) if shares[i] else 1.0) * gl[l] for l in range(hs[i] + 1)))
+            if shares[i]:
+                g[m + 1:] += (float(x[i]) * gl).astype(np.float32)
         g[m] = np.float32(-(0.5 * float(alpha @ alpha) + 0.5 * float(np.trace(K_i))) / n)
         mom = b1 * mom + (np.float32(1) - b1) * g
         vel = b2 * vel + (np.float32(1) - b2) * g * g
@@ -235,14 +253,18 @@ def gp_fit_sum(train, y, kernels, h_candidates: Sequence[int] = tuple(range(5)),
         step = (np.float32(lr) / bc1) * (mom / (np.sqrt(vel) / np.sqrt(bc2) + eps))
         if optimizer == "sgd":
             step = np.float32(lr) * g
-        x[:n_opt] = (x - step.astype(np.float32))[:n_opt]
+        x = np.where(trainable, x - step.astype(np.float32), x).astype(np.float32)
         x[:m] = np.clip(x[:m], np.float32(0.0), np.float32(1.0))
         x[m] = np.float32(min(max(x[m], np.float32(1e-5)), np.float32(max_lik)))
+        x[m + 1:] = np.clip(x[m + 1:], np.float32(0.0), np.float32(1.0))
     lik = float(x[m])
     K_i, _, _ = pd_inverse(K, lik)
     w = x[:m].astype(np.float64)
-    return SumGPState(hs=hs, oas=[oa for _, oa in kernels], weights=w / w.sum(), lik=lik, y_mean=float(y_mean),
-                      y_std=float(y_std), y_norm=y_norm, y_raw=y, K=K, K_i=K_i, nlml=last)
+    st = SumGPState(hs=hs, oas=[oa for _, oa in kernels], weights=w / w.sum(), lik=lik, y_mean=float(y_mean),
+                    y_std=float(y_std), y_norm=y_norm, y_raw=y, K=K, K_i=K_i, nlml=last)
+    st.layer_weights = x[m + 1:].astype(np.float64) if n_lw else None
+    st.shares = shares
+    return st
 
 
 def gp_predict_full_sum(st: SumGPState, train, pool):
@@ -251,7 +273,12 @@ def gp_predict_full_sum(st: SumGPState, train, pool):
     n, M = len(train), len(pool)
     from nasbowl_b200.cells import CellBatch
     joint = CellBatch.concat([train, pool])
-    S = sum(w * wl_oracle.gram_raw(joint, h, oa).astype(np.float64) for w, h, oa in zip(st.weights, st.hs, st.oas))
+    lw = getattr(st, "layer_weights", None)
+    S = 0.0
+    for i, (w, h, oa) in enumerate(zip(st.weights, st.hs, st.oas)):
+        lev = wl_oracle.gram_raw_levels(joint, h, oa).astype(np.float64)
+        for l in range(h + 1):
+            S = S + w * (lw[l] if lw is not None and st.shares[i] else 1.0) * lev[l]
     K_full = normalize_gram(S)
     K_s = K_full[:n, n:]
     K_ss = K_full[n:, n:] + st.lik * np.eye(M)

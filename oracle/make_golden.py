@@ -275,6 +275,16 @@ def multi_kernel_case(R, n_train=40, n_pool=20):
         out[family + "_sgd_weights"] = gp.weights.detach().numpy().astype(np.float64)
         out[family + "_sgd_lik"] = np.float64(gp.likelihood)
         out[family + "_sgd_nlml"] = np.float64(gp.nlml)
+        # trainable WL layer weights (gp.py:157-165,208,218), one kernel: Adam run + three SGD steps
+        for tag, kw in (("lw", {}), ("lwsgd", dict(iters=3, optimizer='sgd', optimizer_kwargs={'lr': 0.02}))):
+            gp = R.GraphGP(train, y.clone(), [R.WeisfilerLehman(h=2, oa=False)])
+            gp.fit(wl_subtree_candidates=(), optimize_lik=True, max_lik=0.01, optimize_wl_layer_weights=True, **kw)
+            out[family + "_%s_layer_weights" % tag] = gp.layer_weights.detach().numpy().astype(np.float64)
+            out[family + "_%s_nlml" % tag] = np.float64(gp.nlml)
+            with torch.no_grad():
+                mu, cov = gp.predict(pool)
+                out[family + "_%s_mu" % tag] = mu.detach().numpy()
+                out[family + "_%s_var" % tag] = np.diag(cov.detach().numpy()).copy()
     return out
 
 

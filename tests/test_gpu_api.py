@@ -270,3 +270,40 @@ def test_multi_kernel_trainable_weights(fam):
     gp3 = GraphGP(train, torch.tensor(y), kernels(), weights=[0.3, 0.7], n_max=batch.n_max)
     gp3.fit(wl_subtree_candidates=(), optimize_lik=False)
     np.testing.assert_allclose(gp3.weights.numpy(), [0.3, 0.7], rtol=1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fam", ["nasbench101", "nasbench201"])
+def test_trainable_wl_layer_weights(fam):
+    """fit(optimize_wl_layer_weights=True) (gp.py:157-165,208,218): per-level weights of the WL kernel
+    trained with the noise; predict() uses the final layer weights with the K_i of the last iteration."""
+    import os
+    from nasbowl_b200.bayesopt import GraphGP
+    from nasbowl_b200.cells import CellBatch, OpVocab
+    from nasbowl_b200.kernels import WeisfilerLehman
+    from oracle import gp_oracle
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "multi_kernel.npz"))
+    batch = CellBatch.from_records(z[fam + "_records"], int(z[fam + "_n_max"]))
+    y = z[fam + "_y"]
+    n = len(y)
+    train, pool = batch[:n], batch[n:]
+    for tag, kw, okw in (("lw", {}, {}),
+                         ("lwsgd", dict(iters=3, optimizer='sgd', optimizer_kwargs={'lr': 0.02}),
+                          dict(iters=3, lr=0.02, optimizer="sgd"))):
+        k = WeisfilerLehman(h=2, oa=False)
+        k.vocab = OpVocab(list(z[fam + "_op_names"]))
+        gp = GraphGP(train, torch.tensor(y), [k], n_max=batch.n_max)
+        gp.fit(wl_subtree_candidates=(), optimize_lik=True, max_lik=0.01, optimize_wl_layer_weights=True, **kw)
+        st = gp_oracle.gp_fit_sum(train, y.astype(np.float64), [(2, False)], h_candidates=(), optimize_lik=True,
+                                  max_lik=0.01, optimize_layer_weights=True, **okw)
+        np.testing.assert_allclose(gp.layer_weights.numpy(), st.layer_weights, rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(gp.layer_weights.numpy(), z[fam + "_%s_layer_weights" % tag], rtol=1e-4, atol=1e-6)
+        # the optimiser state is fp32 (torch here, numpy in the oracle): agreement to ~1e-5
+        np.testing.assert_allclose(gp.K.numpy(), st.K, rtol=1e-4, atol=1e-7)
+        mu, cov = gp.predict(pool)
+        mo, co = gp_oracle.gp_predict_full_sum(st, train, pool)
+        np.testing.assert_allclose(mu.numpy(), mo, rtol=1e-3, atol=1e-4)
+        np.testing.assert_allclose(cov.numpy(), co, rtol=1e-3, atol=1e-6)
+        np.testing.assert_allclose(mu.numpy(), z[fam + "_%s_mu" % tag], rtol=2e-3, atol=2e-3)
+        with pytest.raises(NotImplementedError):       # the fused pool kernel has unit layer weights built in
+            gp.predict_diag(pool)

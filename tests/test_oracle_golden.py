@@ -214,3 +214,21 @@ def test_multi_kernel_trainable_weights(fam):
                               optimizer="sgd")
     np.testing.assert_allclose(sg.weights, z[fam + "_sgd_weights"], rtol=1e-4)
     np.testing.assert_allclose(sg.nlml, float(z[fam + "_sgd_nlml"]), rtol=2e-3)
+
+
+@pytest.mark.parametrize("fam", ["nasbench101", "nasbench201"])
+def test_trainable_wl_layer_weights(fam):
+    """fit(optimize_wl_layer_weights=True) on one WL kernel (gp.py:157-165,208,218)."""
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "multi_kernel.npz"))
+    batch = CellBatch.from_records(z[fam + "_records"], int(z[fam + "_n_max"]))
+    y = z[fam + "_y"].astype(np.float64)
+    n = len(y)
+    train, pool = batch[:n], batch[n:]
+    for tag, kw in (("lw", {}), ("lwsgd", dict(iters=3, lr=0.02, optimizer="sgd"))):
+        st = gp_oracle.gp_fit_sum(train, y, [(2, False)], h_candidates=(), optimize_lik=True, max_lik=0.01,
+                                  optimize_layer_weights=True, **kw)
+        np.testing.assert_allclose(st.layer_weights, z[fam + "_%s_layer_weights" % tag], rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(st.nlml, float(z[fam + "_%s_nlml" % tag]), rtol=2e-3)
+        mu, cov = gp_oracle.gp_predict_full_sum(st, train, pool)
+        np.testing.assert_allclose(mu, z[fam + "_%s_mu" % tag], rtol=2e-3, atol=2e-3)
+        np.testing.assert_allclose(np.diag(cov), z[fam + "_%s_var" % tag], rtol=5e-3, atol=1e-4)
