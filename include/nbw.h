@@ -307,6 +307,22 @@ int nbw_generate_cells(nbw_ctx* ctx, int family, uint64_t seed, int64_t first_in
 int nbw_mutate_cells(nbw_ctx* ctx, int family, const void* parents, int64_t n_parents, uint64_t seed,
                      int64_t first_index, int64_t n_children, void* cells, void* stream);
 
+/* NB201 / DARTS cells with their ENCODINGS (the pruned cell does not determine the architecture it came
+ * from, and mutation edits the architecture): NB201 = six edge choices (0..2 ops, 3 skip_connect, 4 none)
+ * in 8 bytes; DARTS = eight (op 0..6, input 0..5) pairs in 16 bytes.  Same cells as nbw_generate_cells
+ * for the same (seed, index).  Replaces random_sampling (generate_test_graphs.py:543-641) /
+ * random_sample_darts (darts/darts_objectives.py:159-198) when the parents of a later mutation are needed. */
+int nbw_generate_encoded(nbw_ctx* ctx, int family, uint64_t seed, int64_t first_index, int64_t n_cells,
+                         void* cells, uint8_t* enc, void* stream);
+
+/* BANANAS-style mutation on encodings: child i edits parent i % n_parents.  NB201: _banana_mutate
+ * (generate_test_graphs.py:412-431); DARTS: _mutate with `edits` edits, mutate_main_only, invalid children
+ * redrawn (darts/darts_objectives.py:201-245,258-260).  child_enc (optional) receives the children's
+ * encodings.  `edits` is ignored for NB201. */
+int nbw_mutate_encoded(nbw_ctx* ctx, int family, const uint8_t* parent_enc, int64_t n_parents,
+                       uint64_t seed, int64_t first_index, int64_t n_children, int edits, void* cells,
+                       uint8_t* child_enc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

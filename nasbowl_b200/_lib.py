@@ -100,6 +100,8 @@ _PROTOTYPES = {
                                  C.POINTER(_i32), _vp]),
     "nbw_generate_cells": (C.c_int, [_vp, _i32, _u64, _i64, _i64, _vp, _vp]),
     "nbw_mutate_cells": (C.c_int, [_vp, _i32, _vp, _i64, _u64, _i64, _i64, _vp, _vp]),
+    "nbw_generate_encoded": (C.c_int, [_vp, _i32, _u64, _i64, _i64, _vp, _vp, _vp]),
+    "nbw_mutate_encoded": (C.c_int, [_vp, _i32, _vp, _i64, _u64, _i64, _i64, _i32, _vp, _vp, _vp]),
 }
 EXPORTED = tuple(_PROTOTYPES)
 

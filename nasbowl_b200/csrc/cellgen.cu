@@ -81,59 +81,116 @@ __device__ void gen_nb101(uint64_t state, uint8_t* rec) {
   }
 }
 
-__device__ void gen_nb201(uint64_t state, uint8_t* rec) {
+// NB201 cell from its six edge choices (0..2 real ops, 3 skip_connect, 4 none); false = empty cell.
+__device__ bool build_nb201(const uint32_t* choice, uint8_t* rec) {
   // template edges (0,1),(0,2),(0,4),(1,3),(1,5),(2,6),(3,6),(4,7),(5,7),(6,7)
   const uint32_t succ0[8] = {0x16u, 0x28u, 0x40u, 0x40u, 0x80u, 0x80u, 0x80u, 0x00u};
   const uint32_t pred0[8] = {0x00u, 0x01u, 0x01u, 0x02u, 0x01u, 0x02u, 0x0Cu, 0x70u};
+  uint32_t succ[8];
+  for (int v = 0; v < 8; ++v) succ[v] = succ0[v];
+  uint32_t removed = 0;
+  for (int i = 1; i < 7; ++i) {
+    const uint32_t c = choice[i - 1];
+    if (c >= 3) {
+      removed |= 1u << i;
+      if (c == 3)
+        for (int u = 0; u < 8; ++u)
+          if ((pred0[i] >> u) & 1u) succ[u] |= succ0[i];
+    }
+  }
+  uint32_t keep = 0xFFu & ~removed;
+  uint32_t has_in = 0;
+  for (int v = 0; v < 8; ++v) {
+    succ[v] = ((keep >> v) & 1u) ? (succ[v] & keep) : 0u;
+    has_in |= succ[v];
+  }
+  uint32_t drop = 0;
+  for (int v = 0; v < 8; ++v) {
+    if (!((keep >> v) & 1u)) continue;
+    if (v != 0 && !((has_in >> v) & 1u)) drop |= 1u << v;
+    else if (v != 7 && succ[v] == 0) drop |= 1u << v;
+  }
+  keep &= ~drop;
+  uint32_t any_edge = 0;
+  for (int v = 0; v < 8; ++v) {
+    succ[v] = ((keep >> v) & 1u) ? (succ[v] & keep) : 0u;
+    any_edge |= succ[v];
+  }
+  if (keep == 0 || any_edge == 0) return false;
+  uint8_t ops[8];
+  ops[0] = 0;
+  ops[7] = 1;
+  for (int i = 0; i < 6; ++i) ops[1 + i] = (uint8_t)(2 + (choice[i] < 2 ? choice[i] : 2));
+  write_compact<8>(rec, ops, succ, keep, 8);
+  return true;
+}
+
+__device__ void gen_nb201(uint64_t state, uint8_t* rec, uint8_t* enc) {
   for (uint32_t attempt = 0;; ++attempt) {
     const uint64_t x = gen_draw(state, attempt, 0);
     uint32_t choice[6];
     for (int i = 0; i < 6; ++i) choice[i] = below(x, 5, i);
-    uint32_t succ[8];
-    for (int v = 0; v < 8; ++v) succ[v] = succ0[v];
-    uint32_t removed = 0;
-    for (int i = 1; i < 7; ++i) {
-      const uint32_t c = choice[i - 1];
-      if (c >= 3) {
-        removed |= 1u << i;
-        if (c == 3)
-          for (int u = 0; u < 8; ++u)
-            if ((pred0[i] >> u) & 1u) succ[u] |= succ0[i];
-      }
-    }
-    uint32_t keep = 0xFFu & ~removed;
-    uint32_t has_in = 0;
-    for (int v = 0; v < 8; ++v) {
-      succ[v] = ((keep >> v) & 1u) ? (succ[v] & keep) : 0u;
-      has_in |= succ[v];
-    }
-    uint32_t drop = 0;
-    for (int v = 0; v < 8; ++v) {
-      if (!((keep >> v) & 1u)) continue;
-      if (v != 0 && !((has_in >> v) & 1u)) drop |= 1u << v;
-      else if (v != 7 && succ[v] == 0) drop |= 1u << v;
-    }
-    keep &= ~drop;
-    uint32_t any_edge = 0;
-    for (int v = 0; v < 8; ++v) {
-      succ[v] = ((keep >> v) & 1u) ? (succ[v] & keep) : 0u;
-      any_edge |= succ[v];
-    }
-    if (keep == 0 || any_edge == 0) continue;
-    uint8_t ops[8];
-    ops[0] = 0;
-    ops[7] = 1;
-    for (int i = 0; i < 6; ++i) ops[1 + i] = (uint8_t)(2 + (choice[i] < 2 ? choice[i] : 2));
-    write_compact<8>(rec, ops, succ, keep, 8);
+    if (!build_nb201(choice, rec)) continue;
+    if (enc)
+      for (int i = 0; i < 8; ++i) enc[i] = i < 6 ? (uint8_t)choice[i] : 0;
     return;
   }
 }
 
-__device__ void gen_darts(uint64_t state, uint8_t* rec) {
+// DARTS cell from its genotype: eight (op 0..6, input 0..5) pairs; false = an input of the cell is unused
+// (is_valid_darts, darts/utils.py:148-153).  Inputs may point at a later block (the reference's _mutate
+// draws them from all six sources, darts_objectives.py:217-227); the construction does not care.
+__device__ bool build_darts(const uint32_t* op, const uint32_t* in, uint8_t* rec) {
+  uint32_t used = 0;
+  for (int k = 0; k < 8; ++k) used |= 1u << in[k];
+  if ((used & 3u) != 3u) return false;
+  const int n = 15;
+  uint8_t ops[15];
+  uint32_t succ[15];
+  for (int v = 0; v < n; ++v) { ops[v] = 0xFF; succ[v] = 0; }
+  ops[0] = 0; ops[1] = 1; ops[14] = 2;
+  for (int i = 0; i < 4; ++i) {
+    ops[3 * i + 2] = (uint8_t)(4 + op[2 * i]);
+    ops[3 * i + 3] = (uint8_t)(4 + op[2 * i + 1]);
+    ops[3 * i + 4] = 3;
+    succ[3 * i + 2] |= 1u << (3 * i + 4);
+    succ[3 * i + 3] |= 1u << (3 * i + 4);
+  }
+  for (int i = 0; i < 4; ++i)
+    for (int off = 0; off < 2; ++off) {
+      const uint32_t k = in[2 * i + off];
+      const uint32_t src = k <= 1 ? k : (k - 2) * 3 + 4;
+      succ[src] |= 1u << (3 * i + 2 + off);
+    }
+  for (int i = 0; i < 4; ++i) succ[3 * i + 4] |= 1u << 14;
+  uint32_t keep = (1u << n) - 1u;
+  for (int j = 0; j < n; ++j) {   // skip_connect contraction
+    if (((keep >> j) & 1u) && ops[j] == 6) {
+      const int out = __ffs(succ[j]) - 1;
+      for (int u = 0; u < n; ++u)
+        if (((keep >> u) & 1u) && ((succ[u] >> j) & 1u)) succ[u] = (succ[u] | (1u << out)) & ~(1u << j);
+      succ[j] = 0;
+      keep &= ~(1u << j);
+    }
+  }
+  for (int j = 0; j < n; ++j) {   // removal sweep, sequential
+    if (!((keep >> j) & 1u)) continue;
+    if (ops[j] > 1) {
+      bool has_in = false;
+      for (int u = 0; u < n; ++u) has_in |= ((keep >> u) & 1u) && ((succ[u] >> j) & 1u);
+      if (!has_in) { keep &= ~(1u << j); succ[j] = 0; }
+    } else if ((succ[j] & keep) == 0) {
+      keep &= ~(1u << j);
+    }
+  }
+  write_compact<16>(rec, ops, succ, keep, n);
+  return true;
+}
+
+__device__ void gen_darts(uint64_t state, uint8_t* rec, uint8_t* enc) {
   for (uint32_t attempt = 0;; ++attempt) {
     const uint64_t x = gen_draw(state, attempt, 0), y = gen_draw(state, attempt, 1);
     uint32_t op[8], in[8];
-    uint32_t used = 0;
     for (int i = 0; i < 4; ++i) {
       uint32_t a = (uint32_t)((((y >> (16 * i)) & 0xFFull) * (uint32_t)(i + 2)) >> 8);
       uint32_t b = (uint32_t)((((y >> (16 * i + 8)) & 0xFFull) * (uint32_t)(i + 1)) >> 8);
@@ -142,49 +199,10 @@ __device__ void gen_darts(uint64_t state, uint8_t* rec) {
       op[2 * i + 1] = below(x, 7, 2 * i + 1);
       in[2 * i] = a;
       in[2 * i + 1] = b;
-      used |= (1u << a) | (1u << b);
     }
-    if ((used & 3u) != 3u) continue;   // both cell inputs must be used
-    const int n = 15;
-    uint8_t ops[15];
-    uint32_t succ[15];
-    for (int v = 0; v < n; ++v) { ops[v] = 0xFF; succ[v] = 0; }
-    ops[0] = 0; ops[1] = 1; ops[14] = 2;
-    for (int i = 0; i < 4; ++i) {
-      ops[3 * i + 2] = (uint8_t)(4 + op[2 * i]);
-      ops[3 * i + 3] = (uint8_t)(4 + op[2 * i + 1]);
-      ops[3 * i + 4] = 3;
-      succ[3 * i + 2] |= 1u << (3 * i + 4);
-      succ[3 * i + 3] |= 1u << (3 * i + 4);
-    }
-    for (int i = 0; i < 4; ++i)
-      for (int off = 0; off < 2; ++off) {
-        const uint32_t k = in[2 * i + off];
-        const uint32_t src = k <= 1 ? k : (k - 2) * 3 + 4;
-        succ[src] |= 1u << (3 * i + 2 + off);
-      }
-    for (int i = 0; i < 4; ++i) succ[3 * i + 4] |= 1u << 14;
-    uint32_t keep = (1u << n) - 1u;
-    for (int j = 0; j < n; ++j) {   // skip_connect contraction
-      if (((keep >> j) & 1u) && ops[j] == 6) {
-        const int out = __ffs(succ[j]) - 1;
-        for (int u = 0; u < n; ++u)
-          if (((keep >> u) & 1u) && ((succ[u] >> j) & 1u)) succ[u] = (succ[u] | (1u << out)) & ~(1u << j);
-        succ[j] = 0;
-        keep &= ~(1u << j);
-      }
-    }
-    for (int j = 0; j < n; ++j) {   // removal sweep, sequential
-      if (!((keep >> j) & 1u)) continue;
-      if (ops[j] > 1) {
-        bool has_in = false;
-        for (int u = 0; u < n; ++u) has_in |= ((keep >> u) & 1u) && ((succ[u] >> j) & 1u);
-        if (!has_in) { keep &= ~(1u << j); succ[j] = 0; }
-      } else if ((succ[j] & keep) == 0) {
-        keep &= ~(1u << j);
-      }
-    }
-    write_compact<16>(rec, ops, succ, keep, n);
+    if (!build_darts(op, in, rec)) continue;   // both cell inputs must be used
+    if (enc)
+      for (int k = 0; k < 8; ++k) { enc[2 * k] = (uint8_t)op[k]; enc[2 * k + 1] = (uint8_t)in[k]; }
     return;
   }
 }
@@ -259,19 +277,99 @@ mutate_nb101_kernel(const uint8_t* __restrict__ parents, int64_t n_parents, uint
 }
 
 __global__ void __launch_bounds__(256)
-generate_cells_kernel(int family, uint64_t seed, int64_t first_index, int64_t n_cells, uint8_t* __restrict__ cells) {
+generate_cells_kernel(int family, uint64_t seed, int64_t first_index, int64_t n_cells, uint8_t* __restrict__ cells,
+                      uint8_t* __restrict__ enc) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int rec_bytes = family == 2 ? 48 : 16;
+  const int enc_bytes = family == 2 ? 16 : 8;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_cells; i += stride) {
     const uint64_t state = nbw_mix_a(seed + kGold * (uint64_t)(first_index + i + 1));
     __align__(16) uint8_t rec[48];
+    uint8_t e[16];
     if (family == 0) gen_nb101(state, rec);
-    else if (family == 1) gen_nb201(state, rec);
-    else gen_darts(state, rec);
+    else if (family == 1) gen_nb201(state, rec, e);
+    else gen_darts(state, rec, e);
     uint4* dst = reinterpret_cast<uint4*>(cells + i * rec_bytes);
     const uint32_t* w = reinterpret_cast<const uint32_t*>(rec);
     for (int q = 0; q < rec_bytes / 16; ++q)
       dst[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+    if (enc && family != 0)
+      for (int q = 0; q < enc_bytes; ++q) enc[i * enc_bytes + q] = e[q];
+  }
+}
+
+// BANANAS-style mutation on the ENCODINGS of NB201 / DARTS cells (the pruned cell does not determine its
+// parent architecture).  Child i edits parent i % n_parents; up to 64 attempts, then a fresh random cell.
+//   NB201 (generate_test_graphs.py:412-431): each of the six ops changes with probability ~1/5 to one of
+//   the other four, uniformly; an empty child is retried.
+//   DARTS (darts/darts_objectives.py:201-245, mutate_main_only): `edits` sequential edits; a coin picks op
+//   or wiring, a position 0..7; op: uniform over the seven ops; wiring: uniform over the six sources,
+//   redrawn while it equals the sibling's or its own current source; children that leave a cell input
+//   unused are retried (:258-260).
+// Bit-identical to synth.mutate_encoded_host.
+__global__ void __launch_bounds__(256)
+mutate_encoded_kernel(int family, const uint8_t* __restrict__ parents, int64_t n_parents, uint64_t seed,
+                      int64_t first_index, int64_t n_children, int edits, uint8_t* __restrict__ cells,
+                      uint8_t* __restrict__ enc) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int rec_bytes = family == 2 ? 48 : 16;
+  const int enc_bytes = family == 2 ? 16 : 8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_children; i += stride) {
+    const int64_t idx = first_index + i;
+    const uint8_t* par = parents + (idx % n_parents) * enc_bytes;
+    const uint64_t state = nbw_mix_a((seed ^ 0x6D75746174650000ull) + kGold * (uint64_t)(idx + 1));
+    __align__(16) uint8_t rec[48];
+    uint8_t e[16];
+    bool done = false;
+    for (uint32_t attempt = 0; attempt < 64 && !done; ++attempt) {
+      if (family == 1) {
+        const uint64_t d0 = gen_draw(state, attempt, 0), d1 = gen_draw(state, attempt, 1);
+        uint32_t choice[6];
+        for (int k = 0; k < 6; ++k) {
+          choice[k] = par[k];
+          if (below(d0, 5, k) == 0) {
+            const uint32_t pick = below(d1, 4, k);          // index among the four other ops
+            choice[k] = pick < par[k] ? pick : pick + 1;
+          }
+        }
+        done = build_nb201(choice, rec);
+        if (done)
+          for (int k = 0; k < 8; ++k) e[k] = k < 6 ? (uint8_t)choice[k] : 0;
+      } else {
+        uint32_t op[8], in[8];
+        for (int k = 0; k < 8; ++k) { op[k] = par[2 * k]; in[k] = par[2 * k + 1]; }
+        bool ok = true;
+        for (int ed = 0; ed < edits && ok; ++ed) {
+          const uint64_t d0 = gen_draw(state, attempt, 2 * ed), d1 = gen_draw(state, attempt, 2 * ed + 1);
+          const uint32_t coin = below(d0, 2, 0), pos = below(d0, 8, 1);
+          if (coin == 1) {
+            op[pos] = below(d0, 7, 2);
+          } else {
+            const uint32_t sibling = in[pos ^ 1u];
+            bool found = false;
+            for (int t = 0; t < 13 && !found; ++t) {       // fields 3..7 of d0, then 0..7 of d1
+              const uint32_t c = t < 5 ? below(d0, 6, 3 + t) : below(d1, 6, t - 5);
+              if (c != sibling && c != in[pos]) { in[pos] = c; found = true; }
+            }
+            ok = found;
+          }
+        }
+        done = ok && build_darts(op, in, rec);
+        if (done)
+          for (int k = 0; k < 8; ++k) { e[2 * k] = (uint8_t)op[k]; e[2 * k + 1] = (uint8_t)in[k]; }
+      }
+    }
+    if (!done) {
+      const uint64_t fb = nbw_mix_a((seed ^ 0x66616C6C6261636Bull) + kGold * (uint64_t)(idx + 1));
+      if (family == 1) gen_nb201(fb, rec, e);
+      else gen_darts(fb, rec, e);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(cells + i * rec_bytes);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(rec);
+    for (int q = 0; q < rec_bytes / 16; ++q)
+      dst[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+    if (enc)
+      for (int q = 0; q < enc_bytes; ++q) enc[i * enc_bytes + q] = e[q];
   }
 }
 
@@ -285,7 +383,35 @@ extern "C" int nbw_generate_cells(nbw_ctx* ctx, int family, uint64_t seed, int64
   if (n_cells == 0) return NBW_OK;
   NBW_REQUIRE(ctx, cells != nullptr && (reinterpret_cast<uintptr_t>(cells) & 15) == 0, "cells must be 16-byte aligned");
   generate_cells_kernel<<<nbw_grid_for(ctx, n_cells, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      family, seed, first_index, n_cells, static_cast<uint8_t*>(cells));
+      family, seed, first_index, n_cells, static_cast<uint8_t*>(cells), nullptr);
+  NBW_CHECK_LAUNCH(ctx);
+  return NBW_OK;
+}
+
+extern "C" int nbw_generate_encoded(nbw_ctx* ctx, int family, uint64_t seed, int64_t first_index, int64_t n_cells,
+                                    void* cells, uint8_t* enc, void* stream) {
+  if (!ctx) return NBW_ERR_INVALID;
+  NBW_REQUIRE(ctx, family == 1 || family == 2, "encodings exist for family 1 (NB201: 8 bytes) and 2 (DARTS: 16 bytes)");
+  NBW_REQUIRE(ctx, n_cells >= 0 && first_index >= 0, "bad range");
+  if (n_cells == 0) return NBW_OK;
+  NBW_REQUIRE(ctx, cells && enc && (reinterpret_cast<uintptr_t>(cells) & 15) == 0, "null / misaligned pointer");
+  generate_cells_kernel<<<nbw_grid_for(ctx, n_cells, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      family, seed, first_index, n_cells, static_cast<uint8_t*>(cells), enc);
+  NBW_CHECK_LAUNCH(ctx);
+  return NBW_OK;
+}
+
+extern "C" int nbw_mutate_encoded(nbw_ctx* ctx, int family, const uint8_t* parent_enc, int64_t n_parents,
+                                  uint64_t seed, int64_t first_index, int64_t n_children, int edits, void* cells,
+                                  uint8_t* child_enc, void* stream) {
+  if (!ctx) return NBW_ERR_INVALID;
+  NBW_REQUIRE(ctx, family == 1 || family == 2, "encoded mutation is for family 1 (NB201) and 2 (DARTS); NB101 uses nbw_mutate_cells");
+  NBW_REQUIRE(ctx, n_parents > 0 && n_children >= 0 && first_index >= 0, "bad range");
+  NBW_REQUIRE(ctx, family == 1 || (edits >= 1 && edits <= 16), "DARTS mutation takes 1..16 edits");
+  if (n_children == 0) return NBW_OK;
+  NBW_REQUIRE(ctx, parent_enc && cells && (reinterpret_cast<uintptr_t>(cells) & 15) == 0, "null / misaligned pointer");
+  mutate_encoded_kernel<<<nbw_grid_for(ctx, n_children, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      family, parent_enc, n_parents, seed, first_index, n_children, edits, static_cast<uint8_t*>(cells), child_enc);
   NBW_CHECK_LAUNCH(ctx);
   return NBW_OK;
 }
@@ -293,7 +419,7 @@ extern "C" int nbw_generate_cells(nbw_ctx* ctx, int family, uint64_t seed, int64
 extern "C" int nbw_mutate_cells(nbw_ctx* ctx, int family, const void* parents, int64_t n_parents, uint64_t seed,
                                 int64_t first_index, int64_t n_children, void* cells, void* stream) {
   if (!ctx) return NBW_ERR_INVALID;
-  NBW_REQUIRE(ctx, family == 0, "mutation is implemented for NAS-Bench-101 cells (NB201 / DARTS need the unpruned encoding)");
+  NBW_REQUIRE(ctx, family == 0, "nbw_mutate_cells edits pruned NAS-Bench-101 cells; NB201 / DARTS cells are edited on their encodings (nbw_mutate_encoded)");
   NBW_REQUIRE(ctx, n_parents > 0 && n_children >= 0 && first_index >= 0, "bad range");
   if (n_children == 0) return NBW_OK;
   NBW_REQUIRE(ctx, parents && cells && (reinterpret_cast<uintptr_t>(cells) & 15) == 0, "null / misaligned pointer");

@@ -406,3 +406,27 @@ class Engine:
         self._check(self.lib.nbw_mutate_cells(self.ctx, family, self._p(parents), parents.shape[0], C.c_uint64(seed),
                                               first_index, n_children, self._p(cells), self.stream))
         return cells
+
+    def generate_encoded(self, family: int, seed: int, first_index: int, n_cells: int):
+        """(device records, device encodings uint8 [n, 8 | 16]) of random NB201 / DARTS cells
+        (nbw_generate_encoded): the same cells as generate_cells plus what a later mutation needs."""
+        stride, eb = (48, 16) if family == 2 else (16, 8)
+        cells = self.empty((n_cells, stride), torch.uint8)
+        enc = self.empty((n_cells, eb), torch.uint8)
+        self._check(self.lib.nbw_generate_encoded(self.ctx, family, C.c_uint64(seed), first_index, n_cells,
+                                                  self._p(cells), self._p(enc), self.stream))
+        return cells, enc
+
+    def mutate_encoded(self, family: int, parent_enc: torch.Tensor, seed: int, first_index: int, n_children: int,
+                       edits: int = 1):
+        """BANANAS-style mutation of NB201 / DARTS architectures on their encodings
+        (nbw_mutate_encoded).  Returns (device records, device child encodings)."""
+        stride, eb = (48, 16) if family == 2 else (16, 8)
+        assert parent_enc.is_cuda and parent_enc.dtype == torch.uint8 and parent_enc.shape[1] == eb
+        parent_enc = parent_enc.contiguous()
+        cells = self.empty((n_children, stride), torch.uint8)
+        enc = self.empty((n_children, eb), torch.uint8)
+        self._check(self.lib.nbw_mutate_encoded(self.ctx, family, self._p(parent_enc), parent_enc.shape[0],
+                                                C.c_uint64(seed), first_index, n_children, int(edits),
+                                                self._p(cells), self._p(enc), self.stream))
+        return cells, enc

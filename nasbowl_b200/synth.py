@@ -121,102 +121,194 @@ def _compact(ops, succ, keep, n):
 _T201 = [(0, 1), (0, 2), (0, 4), (1, 3), (1, 5), (2, 6), (3, 6), (4, 7), (5, 7), (6, 7)]
 
 
-def _nb201_cell(seed, idx):
+def nb201_from_choice(choice):
+    """Packed NB201 cell from its six edge choices (0..2 real ops, 3 skip_connect, 4 none), or None
+    when nothing connects input and output (create_nasbench201_graph, generate_test_graphs.py:95-177)."""
+    succ0 = [0] * 8
+    pred0 = [0] * 8
+    for u, v in _T201:
+        succ0[u] |= 1 << v
+        pred0[v] |= 1 << u
+    succ = list(succ0)
+    removed = 0
+    for i in range(1, 7):
+        c = choice[i - 1]
+        if c >= 3:
+            removed |= 1 << i
+            if c == 3:       # bypass: original predecessors x original successors (:151-153)
+                for u in range(8):
+                    if (pred0[i] >> u) & 1:
+                        succ[u] |= succ0[i]
+    keep = 0xFF & ~removed
+    succ = [(succ[v] & keep) if (keep >> v) & 1 else 0 for v in range(8)]
+    indeg = [sum((succ[u] >> v) & 1 for u in range(8)) for v in range(8)]
+    drop = 0
+    for v in range(8):
+        if not (keep >> v) & 1:
+            continue
+        if v != 0 and indeg[v] == 0:
+            drop |= 1 << v
+        elif v != 7 and succ[v] == 0:
+            drop |= 1 << v
+    keep &= ~drop
+    succ = [(succ[v] & keep) if (keep >> v) & 1 else 0 for v in range(8)]
+    if keep == 0 or not any(succ):
+        return None
+    ops = [0] + [2 + min(c, 2) for c in choice] + [1]
+    return _compact(ops, succ, keep, 8)
+
+
+def _nb201_cell(seed, idx, want_encoding=False):
     attempt = 0
     while True:
         x = draw(seed, idx, attempt, 0)
         attempt += 1
-        choice = [_below(x, 5, i) for i in range(6)]       # 0..2 real ops, 3 skip_connect, 4 none
-        succ0 = [0] * 8
-        pred0 = [0] * 8
-        for u, v in _T201:
-            succ0[u] |= 1 << v
-            pred0[v] |= 1 << u
-        succ = list(succ0)
-        removed = 0
-        for i in range(1, 7):
-            c = choice[i - 1]
-            if c >= 3:
-                removed |= 1 << i
-                if c == 3:       # bypass: original predecessors x original successors (:151-153)
-                    for u in range(8):
-                        if (pred0[i] >> u) & 1:
-                            succ[u] |= succ0[i]
-        keep = 0xFF & ~removed
-        succ = [(succ[v] & keep) if (keep >> v) & 1 else 0 for v in range(8)]
-        indeg = [sum((succ[u] >> v) & 1 for u in range(8)) for v in range(8)]
-        drop = 0
-        for v in range(8):
-            if not (keep >> v) & 1:
-                continue
-            if v != 0 and indeg[v] == 0:
-                drop |= 1 << v
-            elif v != 7 and succ[v] == 0:
-                drop |= 1 << v
-        keep &= ~drop
-        succ = [(succ[v] & keep) if (keep >> v) & 1 else 0 for v in range(8)]
-        if keep == 0 or not any(succ):
+        choice = [_below(x, 5, i) for i in range(6)]
+        cell = nb201_from_choice(choice)
+        if cell is None:
             continue
-        ops = [0] + [2 + min(c, 2) for c in choice] + [1]
-        return _compact(ops, succ, keep, 8)
+        return (cell, choice + [0, 0]) if want_encoding else cell
 
 
 # ------------------------------------------------------------------------------- DARTS
-def _darts_cell(seed, idx):
+def darts_from_genotype(ops8, ins8):
+    """Packed DARTS cell from eight (op 0..6, input 0..5) pairs (darts2graph, darts/utils.py:11-98), or
+    None when a cell input is unused (is_valid_darts, :148-153).  Inputs may point at a later block:
+    the reference's _mutate draws them from all six sources (darts_objectives.py:217-227)."""
+    if 0 not in ins8 or 1 not in ins8:
+        return None
+    n = 15
+    ops = [NO_NODE] * n
+    ops[0], ops[1], ops[14] = 0, 1, 2
+    succ = [0] * n
+    for i in range(4):
+        ops[3 * i + 2] = 4 + ops8[2 * i]
+        ops[3 * i + 3] = 4 + ops8[2 * i + 1]
+        ops[3 * i + 4] = 3
+        succ[3 * i + 2] |= 1 << (3 * i + 4)
+        succ[3 * i + 3] |= 1 << (3 * i + 4)
+    for i in range(4):
+        for off in range(2):
+            k = ins8[2 * i + off]
+            src = k if k <= 1 else (k - 2) * 3 + 4
+            succ[src] |= 1 << (3 * i + 2 + off)
+    for i in range(4):
+        succ[3 * i + 4] |= 1 << 14
+    keep = (1 << n) - 1
+    skip = 4 + 2
+    for j in range(n):                             # skip_connect contraction (:53-64)
+        if (keep >> j) & 1 and ops[j] == skip:
+            out = (succ[j] & -succ[j]).bit_length() - 1
+            for u in range(n):
+                if (keep >> u) & 1 and (succ[u] >> j) & 1:
+                    succ[u] = (succ[u] | (1 << out)) & ~(1 << j)
+            succ[j] = 0
+            keep &= ~(1 << j)
+    for j in range(n):                             # removal sweep, sequential (:67-86)
+        if not (keep >> j) & 1:
+            continue
+        if ops[j] not in (0, 1):
+            if not any((keep >> u) & 1 and (succ[u] >> j) & 1 for u in range(n)):
+                keep &= ~(1 << j)
+                succ[j] = 0
+        else:
+            if succ[j] & keep == 0:
+                keep &= ~(1 << j)
+    return _compact(ops, succ, keep, n)
+
+
+def _darts_cell(seed, idx, want_encoding=False):
     attempt = 0
     while True:
         x = draw(seed, idx, attempt, 0)      # 8 op choices
         y = draw(seed, idx, attempt, 1)      # 8 input choices
         attempt += 1
-        cell = []
+        ops8, ins8 = [], []
         for i in range(4):
             a = (((y >> (16 * i)) & 0xFF) * (i + 2)) >> 8
             b = (((y >> (16 * i + 8)) & 0xFF) * (i + 1)) >> 8
             if b >= a:
                 b += 1
-            cell.append((_below(x, 7, 2 * i), a))
-            cell.append((_below(x, 7, 2 * i + 1), b))
-        conns = [c[1] for c in cell]
-        if 0 not in conns or 1 not in conns:          # is_valid_darts (darts/utils.py:148-153)
+            ops8 += [_below(x, 7, 2 * i), _below(x, 7, 2 * i + 1)]
+            ins8 += [a, b]
+        cell = darts_from_genotype(ops8, ins8)
+        if cell is None:
             continue
-        n = 15
-        ops = [NO_NODE] * n
-        ops[0], ops[1], ops[14] = 0, 1, 2
-        succ = [0] * n
-        for i in range(4):
-            ops[3 * i + 2] = 4 + cell[2 * i][0]
-            ops[3 * i + 3] = 4 + cell[2 * i + 1][0]
-            ops[3 * i + 4] = 3
-            succ[3 * i + 2] |= 1 << (3 * i + 4)
-            succ[3 * i + 3] |= 1 << (3 * i + 4)
-        for i in range(4):
-            for off in range(2):
-                k = cell[2 * i + off][1]
-                src = k if k <= 1 else (k - 2) * 3 + 4
-                succ[src] |= 1 << (3 * i + 2 + off)
-        for i in range(4):
-            succ[3 * i + 4] |= 1 << 14
-        keep = (1 << n) - 1
-        skip = 4 + 2
-        for j in range(n):                             # skip_connect contraction (:53-64)
-            if (keep >> j) & 1 and ops[j] == skip:
-                out = (succ[j] & -succ[j]).bit_length() - 1
-                for u in range(n):
-                    if (keep >> u) & 1 and (succ[u] >> j) & 1:
-                        succ[u] = (succ[u] | (1 << out)) & ~(1 << j)
-                succ[j] = 0
-                keep &= ~(1 << j)
-        for j in range(n):                             # removal sweep, sequential (:67-86)
-            if not (keep >> j) & 1:
-                continue
-            if ops[j] not in (0, 1):
-                if not any((keep >> u) & 1 and (succ[u] >> j) & 1 for u in range(n)):
-                    keep &= ~(1 << j)
-                    succ[j] = 0
+        if want_encoding:
+            return cell, [v for pair in zip(ops8, ins8) for v in pair]
+        return cell
+
+
+# ------------------------------------------------------------------------------- encoded mutation (NB201, DARTS)
+ENC_BYTES = {1: 8, 2: 16}
+
+
+def generate_encoded_host(family: int, seed: int, first_index: int, n_cells: int):
+    """Host twin of nbw_generate_encoded: (CellBatch, encodings uint8 [n, 8 | 16])."""
+    assert family in (1, 2)
+    n_max = FAMILY_NMAX[family]
+    labels = np.full((n_cells, n_max), NO_NODE, dtype=np.uint8)
+    succ = np.zeros((n_cells, n_max), dtype=np.uint16)
+    enc = np.zeros((n_cells, ENC_BYTES[family]), dtype=np.uint8)
+    gen = _nb201_cell if family == 1 else _darts_cell
+    for i in range(n_cells):
+        (lab, msk), e = gen(seed, first_index + i, want_encoding=True)
+        labels[i], succ[i], enc[i] = lab[:n_max], msk[:n_max], e
+    return CellBatch(n_max, labels, succ), enc
+
+
+def mutate_encoded_host(family: int, parent_enc: np.ndarray, seed: int, first_index: int, n_children: int,
+                        edits: int = 1):
+    """Host twin of nbw_mutate_encoded (rules in csrc/cellgen.cu: generate_test_graphs.py:412-431 for
+    NB201, darts/darts_objectives.py:201-245,258-260 for DARTS).  Returns (CellBatch, child encodings)."""
+    assert family in (1, 2)
+    n_max = FAMILY_NMAX[family]
+    labels = np.full((n_children, n_max), NO_NODE, dtype=np.uint8)
+    succ = np.zeros((n_children, n_max), dtype=np.uint16)
+    enc = np.zeros((n_children, ENC_BYTES[family]), dtype=np.uint8)
+    P = len(parent_enc)
+    for i in range(n_children):
+        idx = first_index + i
+        par = [int(v) for v in parent_enc[idx % P]]
+        mseed = seed ^ 0x6D75746174650000
+        cell = e = None
+        for attempt in range(MUTATION_ATTEMPTS):
+            if family == 1:
+                d0, d1 = draw(mseed, idx, attempt, 0), draw(mseed, idx, attempt, 1)
+                choice = par[:6]
+                for k in range(6):
+                    if _below(d0, 5, k) == 0:
+                        pick = _below(d1, 4, k)
+                        choice[k] = pick if pick < par[k] else pick + 1
+                cell = nb201_from_choice(choice)
+                e = choice + [0, 0]
             else:
-                if succ[j] & keep == 0:
-                    keep &= ~(1 << j)
-        return _compact(ops, succ, keep, n)
+                ops8, ins8 = par[0::2], par[1::2]
+                ok = True
+                for ed in range(edits):
+                    d0, d1 = draw(mseed, idx, attempt, 2 * ed), draw(mseed, idx, attempt, 2 * ed + 1)
+                    coin, pos = _below(d0, 2, 0), _below(d0, 8, 1)
+                    if coin == 1:
+                        ops8[pos] = _below(d0, 7, 2)
+                    else:
+                        sibling, found = ins8[pos ^ 1], False
+                        for t in range(13):
+                            c = _below(d0, 6, 3 + t) if t < 5 else _below(d1, 6, t - 5)
+                            if c != sibling and c != ins8[pos]:
+                                ins8[pos], found = c, True
+                                break
+                        if not found:
+                            ok = False
+                            break
+                cell = darts_from_genotype(ops8, ins8) if ok else None
+                e = [v for pair in zip(ops8, ins8) for v in pair]
+            if cell is not None:
+                break
+        if cell is None:
+            gen = _nb201_cell if family == 1 else _darts_cell       # 64 failed attempts: a random cell
+            cell, e = gen(seed ^ 0x66616C6C6261636B, idx, want_encoding=True)
+        labels[i], succ[i], enc[i] = cell[0][:n_max], cell[1][:n_max], e
+    return CellBatch(n_max, labels, succ), enc
 
 
 # ------------------------------------------------------------------------------- NB101 mutation

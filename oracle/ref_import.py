@@ -41,3 +41,22 @@ def load_reference():
         GraphUpperConfidentBound=ref_bayesopt.GraphUpperConfidentBound,
     )
     return ns
+
+
+def load_reference_functions(rel_path: str, names, namespace=None):
+    """Execute only the named top-level functions of one reference source file, unmodified, in
+    `namespace` — for modules whose own imports drag in things this container lacks (e.g.
+    darts/darts_objectives.py imports the NAS-Bench APIs and the CNN trainer).  Returns the namespace."""
+    import ast
+    path = os.path.join(REFERENCE_ROOT, rel_path)
+    src = open(path).read()
+    tree = ast.parse(src)
+    ns = {} if namespace is None else namespace
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in names:
+            code = compile(ast.Module(body=[node], type_ignores=[]), path, "exec")
+            exec(code, ns)
+    missing = [n for n in names if n not in ns]
+    if missing:
+        raise RuntimeError("not found in %s: %s" % (rel_path, missing))
+    return ns

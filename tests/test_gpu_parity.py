@@ -519,6 +519,38 @@ def test_device_mutation_pool_matches_host(eng):
     assert np.array_equal(np.concatenate([a, b]), dev)
 
 
+@pytest.mark.parametrize("family,edits", [(1, 1), (2, 1), (2, 4)])
+def test_device_encoded_generation_and_mutation_match_host(eng, family, edits):
+    """nbw_generate_encoded / nbw_mutate_encoded (NB201 and DARTS architectures edited on their
+    encodings) are bit-identical to the host twins, shard by shard, and feed the scoring path."""
+    cells, enc = eng.generate_encoded(family, 21, 1000, 300)
+    hb, henc = synth.generate_encoded_host(family, 21, 1000, 300)
+    assert np.array_equal(cells.cpu().numpy(), hb.to_records()) and np.array_equal(enc.cpu().numpy(), henc)
+    assert np.array_equal(cells.cpu().numpy(), eng.generate_cells(family, 21, 1000, 300).cpu().numpy())
+    par = enc[:12]
+    hc, he = synth.mutate_encoded_host(family, henc[:12], 7, 500, 2000, edits)
+    dc, de = eng.mutate_encoded(family, par, 7, 500, 2000, edits)
+    assert np.array_equal(dc.cpu().numpy(), hc.to_records()) and np.array_equal(de.cpu().numpy(), he)
+    a, ea = eng.mutate_encoded(family, par, 7, 500, 700, edits)
+    b, eb = eng.mutate_encoded(family, par, 7, 1200, 1300, edits)
+    assert torch.equal(torch.cat([a, b]), dc) and torch.equal(torch.cat([ea, eb]), de)
+    # second generation: children become parents
+    g2, e2 = eng.mutate_encoded(family, de[:50], 9, 0, 500, edits)
+    h2, he2 = synth.mutate_encoded_host(family, he[:50], 9, 0, 500, edits)
+    assert np.array_equal(g2.cpu().numpy(), h2.to_records()) and np.array_equal(e2.cpu().numpy(), he2)
+    # the mutated pool goes straight into the scoring kernel
+    from nasbowl_b200.bayesopt import GraphExpectedImprovement, GraphGP
+    from nasbowl_b200.kernels import WeisfilerLehman
+    train = synth.generate_cells_host(family, 3, 0, 30)
+    gp = GraphGP(train, torch.randn(30, generator=torch.Generator().manual_seed(1)), [WeisfilerLehman(h=1)],
+                 n_max=train.n_max)
+    gp.fit(wl_subtree_candidates=(1,), optimize_lik=False)
+    acq = GraphExpectedImprovement(gp)
+    s_dev = acq.score_pool(dc)[0].cpu().numpy()
+    s_host = acq.score_pool(hc)[0].cpu().numpy()
+    assert np.array_equal(s_dev, s_host) and np.isfinite(s_dev).all()
+
+
 def _random_dags(rng, n_cells, n_max, n_ops, p_edge, allow_isolated=True):
     """Arbitrary labelled DAGs (not sampler-shaped): random sizes, dense / sparse adjacency,
     isolated nodes, duplicate cells — the edge cases of the WL relabelling rules."""

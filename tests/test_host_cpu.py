@@ -295,7 +295,7 @@ def test_mutation_pool_host_twin():
     assert ch.n_edges.max() <= 9 and ch.n_edges.min() >= 1 and ch.n_nodes.max() <= 7
     assert (ch.n_nodes >= 4).mean() > 0.9                     # the rest are random fall-back cells
     assert not np.array_equal(ch.to_records()[:12], par.to_records())
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(NotImplementedError):       # NB201 / DARTS mutate on encodings (mutate_encoded_host)
         synth.mutate_cells_host(1, par, 7, 0, 4)
     from oracle.ref_import import load_reference, reference_available
     if not reference_available():
@@ -330,6 +330,93 @@ def test_mutation_pool_host_twin():
                 G.nodes[i]['op_name'] = nm
             rb = pack_networkx([G], OpVocab(synth.NB101_OPS))
             assert mine is not None and list(rb.labels[0]) == mine[0][:8] and list(rb.succ[0]) == mine[1][:8]
+
+
+def test_encoded_mutation_host_twin_and_reference_rules():
+    """NB201 / DARTS mutation on encodings: deterministic, shard-invariant, children valid; the
+    encoding -> cell construction agrees with the reference's own constructors for MUTATED
+    architectures too (DARTS wiring edits may point at later blocks); the edit statistics agree with
+    the reference's _banana_mutate / _mutate."""
+    import random
+    for family, edits in ((1, 1), (2, 1), (2, 3)):
+        _, par = synth.generate_encoded_host(family, 3, 0, 10)
+        ch, enc = synth.mutate_encoded_host(family, par, 11, 0, 300, edits)
+        a, ea = synth.mutate_encoded_host(family, par, 11, 0, 120, edits)
+        b, eb = synth.mutate_encoded_host(family, par, 11, 120, 180, edits)
+        assert np.array_equal(np.concatenate([a.to_records(), b.to_records()]), ch.to_records())
+        assert np.array_equal(np.concatenate([ea, eb]), enc)
+        assert ch.n_nodes.min() >= 2 and ch.n_edges.min() >= 1
+        diffs = np.array([(enc[i] != par[i % 10]).sum() for i in range(300)])
+        if family == 1:
+            assert 0.9 < diffs.mean() < 1.5                      # six ops x ~1/5
+            assert enc[:, :6].max() <= 4 and not enc[:, 6:].any()
+        else:
+            assert diffs.max() <= edits and diffs.mean() > 0.6 * edits
+            assert enc[:, 0::2].max() <= 6 and enc[:, 1::2].max() <= 5
+            assert all(0 in e[1::2] and 1 in e[1::2] for e in enc)                      # is_valid_darts
+            assert all(e[1] != e[3] and e[5] != e[7] and e[9] != e[11] and e[13] != e[15] for e in enc)
+        # children rebuilt from their encodings are the cells that were returned
+        for i in range(0, 300, 7):
+            e = [int(v) for v in enc[i]]
+            cell = synth.nb201_from_choice(e[:6]) if family == 1 else synth.darts_from_genotype(e[0::2], e[1::2])
+            n_max = ch.n_max
+            assert cell[0][:n_max] == list(ch.labels[i]) and cell[1][:n_max] == list(ch.succ[i])
+    from oracle.ref_import import load_reference, reference_available
+    if not reference_available():
+        return
+    R = load_reference()
+    from darts.cnn.genotypes import Genotype
+    from darts.utils import darts2graph
+    ops201 = ['nor_conv_3x3', 'nor_conv_1x1', 'avg_pool_3x3', 'skip_connect', 'none']
+    dops = synth.DARTS_OPS[4:]
+    _, par = synth.generate_encoded_host(2, 5, 0, 20)
+    _, enc = synth.mutate_encoded_host(2, par, 13, 0, 200, 4)
+    forward_refs = 0
+    for e in enc:
+        ops8, ins8 = [int(v) for v in e[0::2]], [int(v) for v in e[1::2]]
+        forward_refs += any(ins8[k] >= k // 2 + 2 for k in range(8))
+        normal = [(dops[o], i) for o, i in zip(ops8, ins8)]
+        gt = Genotype(normal=normal, normal_concat=range(2, 6), reduce=normal, reduce_concat=range(2, 6))
+        rb = pack_networkx([darts2graph(gt)[0]], OpVocab(synth.DARTS_OPS), n_max=16)
+        mine = synth.darts_from_genotype(ops8, ins8)
+        assert list(rb.labels[0]) == mine[0] and list(rb.succ[0]) == mine[1]
+    assert forward_refs > 10                                    # the case random sampling never produces
+    # edit statistics against the reference's own mutation code
+    import numpy.random as npr
+    import networkx as nx
+    random.seed(0)
+    npr.seed(0)
+    from oracle.ref_import import load_reference_functions
+    import networkx
+    # the module itself imports the NAS-Bench APIs and the CNN trainer: run just its two functions
+    _mutate = load_reference_functions("darts/darts_objectives.py", ["get_ops", "_mutate"],
+                                       dict(np=np, nx=networkx, Genotype=Genotype, darts2graph=darts2graph))["_mutate"]
+    gt0 = Genotype(normal=[(dops[int(o)], int(i)) for o, i in zip(par[0][0::2], par[0][1::2])], normal_concat=range(2, 6),
+                   reduce=[], reduce_concat=range(2, 6))
+    ref_same = ref_op = 0
+    N = 1500
+    for _ in range(N):
+        _, g = _mutate(gt0, 'darts', 1)
+        changed = [k for k in range(8) if g.normal[k] != gt0.normal[k]]
+        ref_same += not changed
+        ref_op += bool(changed) and g.normal[changed[0]][1] == gt0.normal[changed[0]][1]
+    _, enc1 = synth.mutate_encoded_host(2, par[:1], 17, 0, N, 1)
+    mine_same = sum(bool((e == par[0]).all()) for e in enc1)
+    mine_op = sum(bool((e != par[0]).any() and (e[1::2] == par[0][1::2]).all()) for e in enc1)
+    # (children that leave an input unused are redrawn on our side, so allow a wide band)
+    assert abs(ref_same - mine_same) < 0.05 * N and abs(ref_op - mine_op) < 0.08 * N
+    # NB201: number of changed ops per child, reference _banana_mutate vs ours
+    g0 = R.gtg.create_nasbench201_graph([ops201[int(c)] for c in synth.generate_encoded_host(1, 5, 0, 1)[1][0][:6]])
+    _, p201 = synth.generate_encoded_host(1, 5, 0, 1)
+    ref_counts = np.zeros(7)
+    for _ in range(N):
+        pool, _ = R.gtg.mutation([g0], [0.0], n_best=1, n_mutate=1, pool_size=1, allow_isomorphism=True,
+                                 benchmark='nasbench201')
+        child_ops = [s[:-2] for s in pool[0].name.split("|") if "~" in s]
+        ref_counts[sum(ops201.index(o) != int(c) for o, c in zip(child_ops, p201[0][:6]))] += 1
+    _, e201 = synth.mutate_encoded_host(1, p201, 19, 0, N)
+    mine_counts = np.bincount([(e[:6] != p201[0][:6]).sum() for e in e201], minlength=7)
+    assert np.abs(ref_counts - mine_counts).max() < 0.06 * N
 
 
 # ---------------------------------------------------------------------------- oracle invariants
