@@ -43,6 +43,8 @@ typedef enum {
 #define NBW_INVALID_ID 0xFFFFFFFFu
 #define NBW_INVALID_KEY 0xFFFFFFFFFFFFFFFFull
 
+/* Lifecycle and diagnostics: no counterpart in the reference (its state lives in Python objects,
+ * bayesopt/gp.py:28-73); one context per GPU replaces the module-level numpy / torch state. */
 int nbw_version(void);
 int nbw_create(nbw_ctx** out, int device);
 int nbw_destroy(nbw_ctx* ctx);
@@ -97,7 +99,9 @@ int nbw_hist_dense_i8(nbw_ctx* ctx, const uint32_t* ids, int64_t n_cells, int n_
                       const uint32_t* thermo_base, int oa, int8_t* phi, int64_t ld_phi,
                       int32_t* self_sim, void* stream);
 
-/* OA support: per-label maximum count over the batch -> thermometer column bases.
+/* OA support (histogram intersection sum_f min(x_f, y_f), vertex_histogram.py:233-249, evaluated
+ * exactly as a dot product of thermometer codes): per-label maximum count over the batch ->
+ * thermometer column bases.
  * level_off_h[l] = first stacked label index of level l (level_off_h[n_levels] = total labels).
  * thermo_base[i] (u32, i < total) = exclusive prefix sum of max counts *within its level*;
  * level_width_h[l] = sum of max counts of level l.  Syncs. */
@@ -124,7 +128,8 @@ int nbw_gram_i8(nbw_ctx* ctx, const int8_t* A, int64_t m, int64_t lda, const int
  *     products of GraphGP.fit / predict (bayesopt/gp.py:173-219, 271-276).
  * All matrices are row-major fp64 with explicit leading dimensions.
  */
-/* out[i,j] = beta*out[i,j] + w * K[i,j] (int32 -> fp64 accumulate) */
+/* out[i,j] = beta*out[i,j] + w * K[i,j] (int32 -> fp64 accumulate): the level sum with
+ * layer_weights of weisfeiler_lehman.py:316-327 when the levels are weighted separately */
 int nbw_gram_accumulate(nbw_ctx* ctx, const int32_t* K, int64_t ldk, int64_t m, int64_t n,
                         double w, double beta, double* out, int64_t ldo, void* stream);
 /* Y = a*X + b*Y on m x n fp64 blocks (weighted kernel sum, combine_kernels.py:40) */
@@ -133,7 +138,8 @@ int nbw_axpby_f64(nbw_ctx* ctx, const double* X, int64_t ldx, int64_t m, int64_t
 /* s[i] = 1/sqrt(K[i,i]);  K[i,j] *= s[i]*s[j]   (combine_kernels.py:54-56) */
 int nbw_gram_normalize(nbw_ctx* ctx, double* K, int64_t ld, int64_t n, double* inv_sqrt_diag,
                        void* stream);
-/* Factor A + shift*I = L L^T (lower, in `L`, upper part zeroed).  *info_h = 0 on success,
+/* torch.cholesky of K + jitter*I (bayesopt/utils.py:129-131):
+ * factor A + shift*I = L L^T (lower, in `L`, upper part zeroed).  *info_h = 0 on success,
  * k+1 if pivot k is not positive.  Writes log|A + shift I| to *logdet_h.  Syncs. */
 int nbw_chol_f64(nbw_ctx* ctx, const double* A, int64_t lda, int64_t n, double shift,
                  double* L, int64_t ldl, double* logdet_h, int* info_h, void* stream);
@@ -158,14 +164,16 @@ int nbw_kernel_weight_grad(nbw_ctx* ctx, const double* Kinv, int64_t ldk, const 
                            const double* const* R_h, int64_t ldr, int n_kernels, double* grad_h,
                            void* stream);
 
-/* Linv = L^-1 (lower triangular) */
+/* Linv = L^-1 (lower triangular); Linv^T Linv is torch.cholesky_inverse (bayesopt/utils.py:139) */
 int nbw_trtri_lower_f64(nbw_ctx* ctx, const double* L, int64_t ldl, int64_t n, double* Linv,
                         int64_t ldi, void* stream);
-/* C = alpha * op(A) op(B) + beta * C;  op(X) = X or X^T; C is m x n, inner dimension k */
+/* C = alpha * op(A) op(B) + beta * C;  op(X) = X or X^T; C is m x n, inner dimension k
+ * (the products K_s^T K_i y and K_s^T K_i K_s of GraphGP.predict, bayesopt/gp.py:271-276) */
 int nbw_gemm_f64(nbw_ctx* ctx, int trans_a, int trans_b, int64_t m, int64_t n, int64_t k,
                  double alpha, const double* A, int64_t lda, const double* B, int64_t ldb,
                  double beta, double* C, int64_t ldc, void* stream);
-/* B[i, j] = s[i] * sqrt_w * phi[i, k0 + j]  (int8 -> fp64), j < k1-k0 */
+/* B[i, j] = s[i] * sqrt_w * phi[i, k0 + j]  (int8 -> fp64), j < k1-k0: the training features with the
+ * cosine normalisation of combine_kernels.py:54-56 folded in (rows of K_s = B phi_c / sqrt(k_cc)) */
 int nbw_scale_features(nbw_ctx* ctx, const int8_t* phi, int64_t ld_phi, int64_t n, int64_t k0,
                        int64_t k1, const double* s, double sqrt_w, double* B, int64_t ldb,
                        void* stream);
@@ -173,7 +181,8 @@ int nbw_scale_features(nbw_ctx* ctx, const int8_t* phi, int64_t ld_phi, int64_t 
  * (all nodes sharing a label share the ancestor, weisfeiler_lehman.py:266-267). */
 int nbw_label_parents(nbw_ctx* ctx, const uint32_t* ids_prev, const uint32_t* ids_cur,
                       int64_t n_keys, uint32_t* parent, void* stream);
-/* Prefix-summed features over ancestor chains (see nbw_model.H):
+/* Prefix-summed features over ancestor chains (see nbw_model.H) — the feature-space form of
+ * K_s^T K_i K_s (bayesopt/gp.py:272-276) when labels refine level by level:
  *   Bp[i, label_off[0] + z]  = B[i, col_off[0] + z]
  *   Bp[i, label_off[l] + z]  = Bp[i, label_off[l-1] + parent[label_off[l] + z]] + B[i, col_off[l] + z]
  * B: [n x ldb] fp64 (feature-column layout), Bp: [n x ldp] fp64 (stacked-label layout);
@@ -233,16 +242,19 @@ typedef struct {
   double lik, y_mean, y_std, incumbent, xi, beta;
 } nbw_model;
 
-/* Build one level's lookup table from the sorted dictionary of nbw_dict_build.
+/* Build one level's lookup table from the sorted dictionary of nbw_dict_build — the device form of
+ * self._inv_labels[i], which WeisfeilerLehman.transform consults per node (weisfeiler_lehman.py:434-466).
  * table: capacity slots of 16 bytes, capacity = power of two >= 2 * n_unique. */
 int nbw_model_build_table(nbw_ctx* ctx, const uint64_t* uniq_keys, const uint64_t* uniq_chks,
                           int64_t n_unique, void* table, int64_t capacity, void* stream);
 
-/* scores: [M] f32 (required).  mu64/var64/score64: optional [M] f64 outputs (NULL to skip). */
+/* GraphGP.predict (bayesopt/gp.py:240-283, diagonal) + acquisition eval (acquisitions.py:59-80,130-138)
+ * over the pool.  scores: [M] f32 (required).  mu64/var64/score64: optional [M] f64 outputs (NULL to skip). */
 int nbw_score_pool(nbw_ctx* ctx, const nbw_model* model_h, const void* cells, int64_t n_cells,
                    float* scores, double* mu64, double* var64, double* score64, void* stream);
 
-/* Host-buffer form of nbw_score_pool — the call a host-side plugin makes: `cells_h` are packed
+/* Host-buffer form of nbw_score_pool — the call a host-side plugin makes from propose_location
+ * (bayesopt/acquisitions.py:94-113), which receives its candidates in host memory: `cells_h` are packed
  * records in HOST memory (pinned memory gives full overlap), `scores_h` (optional) receives the
  * acquisition values in host memory, `scores_dev` [M] keeps them on the device for nbw_topk.  The
  * pool is cut into `chunks` pieces; the H2D copy of piece i+1, the kernel on piece i and the D2H copy
@@ -252,7 +264,7 @@ int nbw_score_pool_host(nbw_ctx* ctx, const nbw_model* model_h, const void* cell
                         int64_t n_cells, float* scores_h, float* scores_dev, int chunks,
                         void* stream);
 
-/* Mapped form: `cells_h` must be PINNED host memory (cudaHostAlloc / cudaHostRegister); the kernel
+/* Mapped form of the same call (acquisitions.py:94-113): `cells_h` must be PINNED host memory (cudaHostAlloc / cudaHostRegister); the kernel
  * reads the records straight over PCIe through the mapped pointer — no staging copy, no per-chunk
  * launches.  The pool is cut into `pieces` (1..64) kernels only so that the D2H copy of piece i's
  * scores overlaps the kernel on piece i+1 (pieces = 1 measured best at 1M).  Pageable `cells_h` is refused (NBW_ERR_INVALID): use
@@ -261,7 +273,8 @@ int nbw_score_pool_mapped(nbw_ctx* ctx, const nbw_model* model_h, const void* ce
                           int64_t n_cells, float* scores_h, float* scores_dev, int pieces,
                           void* stream);
 
-/* Pool-side features only (test/diagnostic use): restricted dense feature rows
+/* Pool-side features only — WeisfeilerLehman.transform(..., return_embedding_only=True)
+ * (weisfeiler_lehman.py:364-516), used by feature_value / forward_t: restricted dense feature rows
  * phi [M x ld_phi] int8 (columns < n_features) and self-similarity k_cc [M] i32. */
 int nbw_pool_features(nbw_ctx* ctx, const nbw_model* model_h, const void* cells,
                       int64_t n_cells, int8_t* phi, int64_t ld_phi, int32_t* self_sim,
@@ -278,12 +291,13 @@ int nbw_topk(nbw_ctx* ctx, const float* scores, int64_t n, int k, int distinct,
              int64_t index_base, float* top_val_h, int64_t* top_idx_h, int* n_found_h,
              void* stream);
 
-/* The same selection with the result left on the device (no sync): out_cands[k] 16-byte entries
+/* The same selection (acquisitions.py:101-105) with the result left on the device (no sync): out_cands[k] 16-byte entries
  * {f32 value; i32 pad; i64 index}, index -1 = empty.  This is what each rank contributes to the
  * top-n all-gather. */
 int nbw_topk_device(nbw_ctx* ctx, const float* scores, int64_t n, int k, int distinct,
                     int64_t index_base, void* out_cands, void* stream);
-/* Merge `count` such entries (e.g. the all-gathered lists of every rank) into the global top k:
+/* Merge `count` such entries (e.g. the all-gathered lists of every rank) into the global top k
+ * (acquisitions.py:101-105 applied to the union):
  * same distinct-by-value rule, ties to the lowest index.  Syncs. */
 int nbw_topk_merge(nbw_ctx* ctx, const void* cands, int64_t count, int k, int distinct,
                    float* top_val_h, int64_t* top_idx_h, int* n_found_h, void* stream);
