@@ -32,7 +32,11 @@ def synthetic_objective(batch: CellBatch) -> np.ndarray:
     return (0.30 * conv3 + 0.12 * conv1 - 0.05 * pool + 0.04 * edges - 0.01 * (edges - 6) ** 2).astype(np.float64)
 
 
-def run(iters=10, pool_size=200_000, batch_size=5, n_init=30, family=0, seed=0, verbose=True, check=None):
+def run(iters=10, pool_size=200_000, batch_size=5, n_init=30, family=0, seed=0, verbose=True, check=None,
+        strategy="random", n_best=10):
+    """strategy "random": a fresh random pool per iteration (nasbench_optimisation.py --pool_strategy random);
+    "mutate": half of the pool are BANANAS-style edits of the n_best cells observed so far, the rest
+    random (generate_test_graphs.py:393-539), all generated on the device."""
     eng = Engine.get()
     x = CellBatch.from_records(eng.generate_cells(family, seed, 0, n_init).cpu().numpy(), 8)
     y = torch.tensor(synthetic_objective(x))
@@ -42,7 +46,14 @@ def run(iters=10, pool_size=200_000, batch_size=5, n_init=30, family=0, seed=0, 
     for it in range(iters):
         t0 = time.perf_counter()
         first = 1_000_000 + it * pool_size
-        pool = eng.generate_cells(family, seed + 1, first, pool_size)         # stays on the device
+        if strategy == "mutate" and family == 0:
+            top = np.argsort(-y.numpy())[:n_best]
+            parents = eng.upload_cells(x[[int(i) for i in top]])
+            n_mut = pool_size // 2
+            pool = torch.cat([eng.mutate_cells(0, parents, seed + 2 + it, first, n_mut),
+                              eng.generate_cells(family, seed + 1, first, pool_size - n_mut)])
+        else:
+            pool = eng.generate_cells(family, seed + 1, first, pool_size)     # stays on the device
         acq = GraphExpectedImprovement(gp, in_fill='best', augmented_ei=False)
         _, eis, idx = acq.propose_location(pool, top_n=batch_size)
         if check is not None:
@@ -63,6 +74,7 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--pool", type=int, default=200_000)
+    ap.add_argument("--strategy", default="random", choices=["random", "mutate"])
     ap.add_argument("--batch", type=int, default=5)
     a = ap.parse_args()
-    run(a.iters, a.pool, a.batch)
+    run(a.iters, a.pool, a.batch, strategy=a.strategy)

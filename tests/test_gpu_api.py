@@ -168,6 +168,10 @@ def test_bo_loop_matches_oracle_every_iteration():
 
     best, x, y = bo_loop.run(iters=4, pool_size=3000, batch_size=5, n_init=20, verbose=False, check=check)
     assert len(x) == 40 and best[-1] >= best[0]
+    # the reference's default pool strategy: half mutated from the best cells so far, half random
+    best, x, y = bo_loop.run(iters=3, pool_size=3000, batch_size=5, n_init=20, verbose=False, check=check,
+                             strategy="mutate")
+    assert len(x) == 35 and best[-1] >= best[0]
 
 
 @pytest.mark.gpu
