@@ -40,16 +40,20 @@ template <int NMAX>
 __global__ void __launch_bounds__(kHistThreads)
 hist_dense_kernel(const uint32_t* __restrict__ ids, int64_t n_cells, HistLevels lv,
                   const uint32_t* __restrict__ thermo_base, int oa, int8_t* __restrict__ phi,
-                  int64_t ld_phi, int32_t* __restrict__ self_sim) {
+                  int64_t ld_phi, int32_t* __restrict__ self_sim, int n_chunks) {
   constexpr int CPB = kHistThreads / NMAX;   // cells per block
+  // consecutive blocks are the column chunks of ONE block of cells: its ids are read from HBM once and
+  // from L2 by the other chunks (with the chunk index slow, every chunk re-streamed all ids: 13x the reads)
+  const int chunk = (int)(blockIdx.x % (unsigned)n_chunks);
+  const int64_t cell_block = blockIdx.x / (unsigned)n_chunks;
   __shared__ __align__(16) int8_t tile[CPB][kChunk];
   const int lane = threadIdx.x & 31;
   const int node = lane % NMAX;
   const int sub_base = (lane / NMAX) * NMAX;
   const int cell_local = threadIdx.x / NMAX;
-  const int64_t g = (int64_t)blockIdx.x * CPB + cell_local;
+  const int64_t g = cell_block * CPB + cell_local;
   const bool in_range = g < n_cells;
-  const int64_t c_begin = lv.col_off[0] + (int64_t)blockIdx.y * kChunk;
+  const int64_t c_begin = lv.col_off[0] + (int64_t)chunk * kChunk;
   const int64_t c_end_all = lv.col_off[lv.n_levels];
   const int64_t c_end = c_begin + kChunk < c_end_all ? c_begin + kChunk : c_end_all;
 
@@ -79,7 +83,7 @@ hist_dense_kernel(const uint32_t* __restrict__ ids, int64_t n_cells, HistLevels 
       }
     }
   }
-  if (blockIdx.y == 0 && self_sim != nullptr) {
+  if (chunk == 0 && self_sim != nullptr) {
     const int total = subwarp_sum<NMAX>(self_acc);
     if (in_range && node == 0) self_sim[g] = total;
   }
@@ -88,7 +92,7 @@ hist_dense_kernel(const uint32_t* __restrict__ ids, int64_t n_cells, HistLevels 
   const int width16 = (int)((c_end - c_begin + 15) / 16);   // c_end - c_begin is a multiple of 16
   for (int i = threadIdx.x; i < CPB * width16; i += kHistThreads) {
     const int r = i / width16, c = i % width16;
-    const int64_t gr = (int64_t)blockIdx.x * CPB + r;
+    const int64_t gr = cell_block * CPB + r;
     if (gr < n_cells)
       *reinterpret_cast<uint4*>(phi + gr * ld_phi + c_begin + (int64_t)c * 16) =
           *reinterpret_cast<const uint4*>(&tile[r][c * 16]);
@@ -198,12 +202,16 @@ extern "C" int nbw_hist_dense_i8(nbw_ctx* ctx, const uint32_t* ids, int64_t n_ce
   NBW_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(phi) & 15) == 0, "phi must be 16-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int cpb = kHistThreads / n_max;
-  dim3 grid((unsigned)((n_cells + cpb - 1) / cpb), (unsigned)((width + kChunk - 1) / kChunk));
-  NBW_REQUIRE(ctx, grid.y <= 65535, "too many feature columns");
+  const int64_t n_chunks = (width + kChunk - 1) / kChunk;
+  const int64_t blocks = ((n_cells + cpb - 1) / cpb) * n_chunks;
+  NBW_REQUIRE(ctx, blocks < ((int64_t)1 << 31), "histogram: too many tiles for one launch");
+  const unsigned grid = (unsigned)blocks;
   if (n_max == 8)
-    hist_dense_kernel<8><<<grid, kHistThreads, 0, st>>>(ids, n_cells, lv, thermo_base, oa, phi, ld_phi, self_sim);
+    hist_dense_kernel<8><<<grid, kHistThreads, 0, st>>>(ids, n_cells, lv, thermo_base, oa, phi, ld_phi, self_sim,
+                                                        (int)n_chunks);
   else
-    hist_dense_kernel<16><<<grid, kHistThreads, 0, st>>>(ids, n_cells, lv, thermo_base, oa, phi, ld_phi, self_sim);
+    hist_dense_kernel<16><<<grid, kHistThreads, 0, st>>>(ids, n_cells, lv, thermo_base, oa, phi, ld_phi, self_sim,
+                                                         (int)n_chunks);
   NBW_CHECK_LAUNCH(ctx);
   return NBW_OK;
 }
