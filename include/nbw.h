@@ -258,8 +258,9 @@ int nbw_score_pool(nbw_ctx* ctx, const nbw_model* model_h, const void* cells, in
  * records in HOST memory (pinned memory gives full overlap), `scores_h` (optional) receives the
  * acquisition values in host memory, `scores_dev` [M] keeps them on the device for nbw_topk.  The
  * pool is cut into `chunks` pieces; the H2D copy of piece i+1, the kernel on piece i and the D2H copy
- * of piece i-1 overlap on internal streams.  Enqueues only: `stream` is made to wait for the last
- * D2H copy, so a following call that syncs (nbw_topk) also completes scores_h. */
+ * of piece i-1 overlap on internal streams.  Enqueues only.  The D2H copies run BESIDE whatever is
+ * queued next on `stream` (normally the top-n selection on scores_dev): scores_h is complete after the
+ * next nbw_topk / nbw_topk_merge on this context or after nbw_wait_host_scores. */
 int nbw_score_pool_host(nbw_ctx* ctx, const nbw_model* model_h, const void* cells_h,
                         int64_t n_cells, float* scores_h, float* scores_dev, int chunks,
                         void* stream);
@@ -272,6 +273,11 @@ int nbw_score_pool_host(nbw_ctx* ctx, const nbw_model* model_h, const void* cell
 int nbw_score_pool_mapped(nbw_ctx* ctx, const nbw_model* model_h, const void* cells_h,
                           int64_t n_cells, float* scores_h, float* scores_dev, int pieces,
                           void* stream);
+
+/* Block until the host scores of the last nbw_score_pool_host / nbw_score_pool_mapped call have
+ * landed (no-op when nothing is pending).  The eis array propose_location returns
+ * (bayesopt/acquisitions.py:111-113) must be complete before the caller reads it. */
+int nbw_wait_host_scores(nbw_ctx* ctx);
 
 /* Pool-side features only — WeisfeilerLehman.transform(..., return_embedding_only=True)
  * (weisfeiler_lehman.py:364-516), used by feature_value / forward_t: restricted dense feature rows

@@ -92,6 +92,7 @@ _PROTOTYPES = {
     "nbw_score_pool": (C.c_int, [_vp, C.POINTER(Model), _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "nbw_score_pool_host": (C.c_int, [_vp, C.POINTER(Model), _vp, _i64, _vp, _vp, _i32, _vp]),
     "nbw_score_pool_mapped": (C.c_int, [_vp, C.POINTER(Model), _vp, _i64, _vp, _vp, _i32, _vp]),
+    "nbw_wait_host_scores": (C.c_int, [_vp]),
     "nbw_pool_features": (C.c_int, [_vp, C.POINTER(Model), _vp, _i64, _vp, _i64, _vp, _vp]),
     "nbw_topk": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i64, C.POINTER(C.c_float), C.POINTER(_i64),
                            C.POINTER(_i32), _vp]),

@@ -44,8 +44,15 @@ extern "C" int nbw_destroy(nbw_ctx* ctx) {
       cudaEventDestroy(ctx->ev_done[i]);
       if (ctx->stage[i]) cudaFree(ctx->stage[i]);
     }
+    cudaEventDestroy(ctx->ev_out);
   }
   delete ctx;
+  return NBW_OK;
+}
+
+extern "C" int nbw_wait_host_scores(nbw_ctx* ctx) {
+  if (!ctx) return NBW_ERR_INVALID;
+  NBW_CUDA(ctx, nbw_await_host_scores(ctx));
   return NBW_OK;
 }
 

@@ -19,10 +19,20 @@ struct nbw_ctx {
   // host-buffer pipeline of nbw_score_pool_host (score_pool.cu), created on first use
   cudaStream_t s_in, s_out;
   cudaEvent_t ev_ready[2], ev_free[2], ev_done[2];
+  cudaEvent_t ev_out;   // recorded on s_out after the last D2H copy of host scores
+  int out_pending;      // host scores of the last nbw_score_pool_host / _mapped call not yet awaited
   void* stage[2];
   size_t stage_bytes;
   int pipe_ready;
 };
+
+// Host scores written by the side stream are complete once this returns (called by every syncing
+// top-k entry point and by nbw_wait_host_scores).
+static inline cudaError_t nbw_await_host_scores(nbw_ctx* ctx) {
+  if (!ctx->out_pending) return cudaSuccess;
+  ctx->out_pending = 0;
+  return cudaEventSynchronize(ctx->ev_out);
+}
 
 #define NBW_FAIL(ctx, code, ...)                                  \
   do {                                                            \

@@ -457,8 +457,27 @@ int pipe_init(nbw_ctx* ctx) {
     NBW_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
     ctx->stage[i] = nullptr;
   }
+  NBW_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_out, cudaEventDisableTiming));
+  ctx->out_pending = 0;
   ctx->stage_bytes = 0;
   ctx->pipe_ready = 1;
+  return NBW_OK;
+}
+
+// The D2H copies of the host scores run on s_out BESIDE whatever the caller queues next on `stream`
+// (normally the top-k selection); nbw_topk / nbw_topk_merge / nbw_wait_host_scores await them.  A new
+// pipeline call first orders `stream` behind a still pending copy, because it rewrites scores_dev.
+int pipe_begin(nbw_ctx* ctx, cudaStream_t st) {
+  int rc = pipe_init(ctx);
+  if (rc) return rc;
+  if (ctx->out_pending) NBW_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_out, 0));
+  return NBW_OK;
+}
+int pipe_end(nbw_ctx* ctx, bool copied) {
+  if (copied) {
+    NBW_CUDA(ctx, cudaEventRecord(ctx->ev_out, ctx->s_out));
+    ctx->out_pending = 1;
+  }
   return NBW_OK;
 }
 }  // namespace
@@ -479,7 +498,7 @@ extern "C" int nbw_score_pool_mapped(nbw_ctx* ctx, const nbw_model* model_h, con
   NBW_REQUIRE(ctx, attr.type == cudaMemoryTypeHost && attr.devicePointer != nullptr,
               "nbw_score_pool_mapped needs pinned host memory (use nbw_score_pool_host for pageable buffers)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  rc = pipe_init(ctx);
+  rc = pipe_begin(ctx, st);
   if (rc) return rc;
   const int64_t rec = model_h->n_max == 8 ? 16 : 48;
   const uint8_t* src = static_cast<const uint8_t*>(attr.devicePointer);
@@ -500,11 +519,7 @@ extern "C" int nbw_score_pool_mapped(nbw_ctx* ctx, const nbw_model* model_h, con
                                     cudaMemcpyDeviceToHost, ctx->s_out));
     }
   }
-  if (scores_h) {
-    NBW_CUDA(ctx, cudaEventRecord(ctx->ev_done[0], ctx->s_out));
-    NBW_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_done[0], 0));
-  }
-  return NBW_OK;
+  return pipe_end(ctx, scores_h != nullptr);
 }
 
 // Host-buffer form: the pool lives in host memory (pinned for full overlap).  Chunk i+1's H2D copy,
@@ -519,7 +534,7 @@ extern "C" int nbw_score_pool_host(nbw_ctx* ctx, const nbw_model* model_h, const
   NBW_REQUIRE(ctx, cells_h && scores_dev, "null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t rec = model_h->n_max == 8 ? 16 : 48;
-  rc = pipe_init(ctx);
+  rc = pipe_begin(ctx, st);
   if (rc) return rc;
   const int64_t per = (n_cells + chunks - 1) / chunks;
   const size_t need = (size_t)per * rec;
@@ -555,8 +570,5 @@ extern "C" int nbw_score_pool_host(nbw_ctx* ctx, const nbw_model* model_h, const
                                     cudaMemcpyDeviceToHost, ctx->s_out));
     }
   }
-  // the caller's stream continues (e.g. nbw_topk on scores_dev) once the D2H copies are done
-  NBW_CUDA(ctx, cudaEventRecord(ctx->ev_done[0], ctx->s_out));
-  NBW_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_done[0], 0));
-  return NBW_OK;
+  return pipe_end(ctx, scores_h != nullptr);
 }

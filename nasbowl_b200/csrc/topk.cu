@@ -148,6 +148,7 @@ static int topk_readback(nbw_ctx* ctx, const Cand* dev, int k, float* top_val_h,
   if (!host) NBW_FAIL(ctx, NBW_ERR_INVALID, "host allocation failed");
   cudaError_t e = cudaMemcpyAsync(host, dev, sizeof(Cand) * k, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) e = nbw_await_host_scores(ctx);   // D2H of host scores runs beside the selection
   if (e != cudaSuccess) {
     free(host);
     NBW_FAIL(ctx, NBW_ERR_CUDA, "top-k readback failed: %s", cudaGetErrorString(e));

@@ -339,7 +339,8 @@ class Engine:
         """Score a pool that lives in HOST memory through nbw_score_pool_host: the H2D copy of
         chunk i+1, the kernel on chunk i and the D2H copy of chunk i-1's scores overlap.  Returns
         (scores on the device [M] f32, scores in pinned host memory [M] f32); the host copy is
-        complete after the next call that syncs the stream (e.g. topk).  `mapped=True` takes
+        complete after the next topk / topk_merge or wait_host_scores() (its D2H copy runs beside
+        the selection).  `mapped=True` takes
         nbw_score_pool_mapped instead (pinned memory only): the kernel reads the records over PCIe
         itself and `chunks` is the number of kernel pieces."""
         assert not host_cells.is_cuda and host_cells.dtype == torch.uint8 and host_cells.dim() == 2
@@ -355,6 +356,9 @@ class Engine:
         self._check(fn(self.ctx, C.byref(model), C.c_void_p(host_cells.data_ptr()), M,
                        C.c_void_p(host_scores.data_ptr()), self._p(st["scores"]), max(1, min(chunks, M)), self.stream))
         return st["scores"], host_scores
+
+    def wait_host_scores(self):
+        self._check(self.lib.nbw_wait_host_scores(self.ctx))
 
     def pool_features(self, model: "_lib.Model", cells: torch.Tensor, n_cells: int):
         ld = _round_up(model.n_features, 16)
