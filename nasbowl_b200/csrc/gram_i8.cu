@@ -12,14 +12,13 @@
 //   warp 0 lane 0 : TMA producer          (cp.async.bulk.tensor.2d -> the leader's full barrier)
 //   warp 1 lane 0 : MMA issuer (leader)   (4 x UMMA_K=32 per stage, multicast tcgen05.commit)
 //   warps 2..5    : epilogue              (tcgen05.ld 32x32b.x32 -> 128-byte row segments to HBM)
-// int32 accumulation of int8 products is exact.  The single-CTA kernels (cta_group::1) are kept as
-// NBW_GRAM_VARIANT 0..4 for comparison.
+// int32 accumulation of int8 products is exact.  The single-CTA persistent kernel (cta_group::1) it
+// replaced is kept as NBW_GRAM_VARIANT=4 for comparison.
 //
 // Cross-check path (impl 1): plain dp4a kernel, used by the tests to validate impl 0.
 #include "nbw_common.cuh"
 
 #include <cuda.h>
-#include <stdio.h>
 #include <stdlib.h>
 
 namespace {
@@ -29,18 +28,6 @@ constexpr int UMMA_K = 32;
 constexpr int MAX_STAGES = 8;
 constexpr int A_TILE_BYTES = BM * BK;          // 16 KB of A per stage
 constexpr uint32_t SPIN_LIMIT = 1u << 26;
-
-struct __align__(8) PipeBarriers {
-  uint64_t full[MAX_STAGES];
-  uint64_t empty[MAX_STAGES];
-  uint64_t tmem_full;
-  uint32_t tmem_base;
-  uint32_t pad;
-};
-template <int BN, int STAGES>
-constexpr size_t gram_smem_bytes() {
-  return 1024 /*align slack*/ + (size_t)STAGES * (A_TILE_BYTES + BN * BK) + sizeof(PipeBarriers);
-}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -128,114 +115,6 @@ struct IdescI8 {
   static constexpr uint32_t value =
       (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 };
-
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(128)
-gram_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                       int32_t* __restrict__ C, int64_t ldc, int64_t m, int64_t n, int32_t kblk0, int32_t k_blocks,
-                       int32_t m_tiles, int32_t n_tiles) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int B_TILE_BYTES = BN * BK;
-  constexpr int TMEM_COLS = BN;
-  constexpr uint32_t kIdescI8 = IdescI8<BN>::value;
-  uint8_t* tile_a = smem;                                   // [STAGES][128 rows][128 B]
-  uint8_t* tile_b = smem + (size_t)STAGES * A_TILE_BYTES;   // [STAGES][BN rows][128 B]
-  PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(smem + (size_t)STAGES * (A_TILE_BYTES + B_TILE_BYTES));
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int32_t mt, nt;
-  tile_coords(blockIdx.x, m_tiles, n_tiles, mt, nt);
-  const int32_t row0 = mt * BM, col0 = nt * BN;
-
-  if (warp == 0 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&bars->full[s], 1);
-      mbar_init(&bars->empty[s], 1);
-    }
-    mbar_init(&bars->tmem_full, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
-                 "r"((uint32_t)TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_acc = bars->tmem_base;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      // ---------------- TMA producer
-      uint32_t stage = 0, phase = 0;
-      for (int kb = 0; kb < k_blocks; ++kb) {
-        mbar_wait(&bars->empty[stage], phase ^ 1u);
-        mbar_expect_tx(&bars->full[stage], (uint32_t)(A_TILE_BYTES + B_TILE_BYTES));
-        const int32_t kx = (kblk0 + kb) * BK;
-        tma_load_2d(&map_a, &bars->full[stage], tile_a + (size_t)stage * A_TILE_BYTES, kx, row0);
-        tma_load_2d(&map_b, &bars->full[stage], tile_b + (size_t)stage * B_TILE_BYTES, kx, col0);
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------- MMA issuer
-      uint32_t stage = 0, phase = 0;
-      for (int kb = 0; kb < k_blocks; ++kb) {
-        mbar_wait(&bars->full[stage], phase);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_addr = smem_u32(tile_a + (size_t)stage * A_TILE_BYTES);
-        const uint32_t b_addr = smem_u32(tile_b + (size_t)stage * B_TILE_BYTES);
-#pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          const uint64_t da = umma_smem_desc(a_addr + k * UMMA_K);
-          const uint64_t db = umma_smem_desc(b_addr + k * UMMA_K);
-          umma_i8(tmem_acc, da, db, kIdescI8, (kb > 0 || k > 0) ? 1u : 0u);
-        }
-        umma_commit(&bars->empty[stage]);   // frees the smem slot once these MMAs have read it
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-      }
-      umma_commit(&bars->tmem_full);        // accumulator complete
-    }
-    __syncwarp();
-  }
-
-  // ---------------- epilogue: warp w owns TMEM lanes [32w, 32w+32) = output rows row0 + 32w + lane
-  mbar_wait(&bars->tmem_full, 0);
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const int64_t r = (int64_t)row0 + warp * 32 + lane;
-  const bool vec_ok = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
-#pragma unroll 1
-  for (int c = 0; c < BN / 32; ++c) {
-    uint32_t v[32];
-    tmem_load_32cols(tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), v);
-    if (r < m) {
-      const int64_t cbase = (int64_t)col0 + c * 32;
-      int32_t* dst = C + r * ldc + cbase;
-      if (vec_ok && cbase + 32 <= n) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<int4*>(dst + 4 * q) =
-              make_int4((int)v[4 * q], (int)v[4 * q + 1], (int)v[4 * q + 2], (int)v[4 * q + 3]);
-      } else {
-#pragma unroll
-        for (int q = 0; q < 32; ++q)
-          if (cbase + q < n) dst[q] = (int32_t)v[q];
-      }
-    }
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)TMEM_COLS)
-                 : "memory");
-  }
-}
 
 // ------------------------------------------------------------------ persistent variant
 // One CTA per SM walks the output tiles (128 x BN) in row-major tile order.  Six warps:
@@ -407,6 +286,7 @@ struct __align__(8) PairBarriers {
 constexpr int PAIR_BN = 256;                       // N of the pair tile
 constexpr int PAIR_B_ROWS = PAIR_BN / 2;           // rows of B each CTA stages
 constexpr int PAIR_STAGE_BYTES = A_TILE_BYTES + PAIR_B_ROWS * BK;
+constexpr int PAIR_STAGES = 6;                     // 4..7 measured within 1 % of each other (profiles/r01_gram_variants.txt)
 template <int STAGES>
 constexpr size_t gram_pair_smem_bytes() {
   return 1024 + (size_t)STAGES * PAIR_STAGE_BYTES + sizeof(PairBarriers);
@@ -677,95 +557,55 @@ extern "C" int nbw_gram_i8(nbw_ctx* ctx, const int8_t* A, int64_t m, int64_t lda
     return NBW_OK;
   }
   NBW_REQUIRE(ctx, impl == 0, "unknown impl %d", impl);
-  // Default: the CTA-pair kernel (variant 5): cta_group::2, 256 x 256 tiles, epilogue of tile i
-  // overlapped with the main loop of tile i+1 through two TMEM accumulator buffers, grouped tile
-  // order for L2 reuse.  Measured int8 throughput: 3.20 Pop/s at 16384^2 x 8192, 3.89 Pop/s on the
-  // 200k x 200k x 33792 stress (profiles/); the single-CTA persistent kernel (variant 4) reaches
-  // 2.89 / 3.44.  NBW_GRAM_VARIANT selects the other variants for experiments: 0 = 128x128 3-stage,
-  // 1 = 128x256 4-stage, 2 = 128x128 6-stage, 3 = 128x256 2-stage (two CTAs per SM), 4 = persistent
-  // single-CTA 128x256.
+  // Default: the CTA-pair kernel: cta_group::2, 256 x 256 tiles, epilogue of tile i overlapped with the
+  // main loop of tile i+1 through two TMEM accumulator buffers, grouped tile order for L2 reuse.
+  // Measured int8 throughput: 3.20 Pop/s at 16384^2 x 8192, 3.9-4.0 Pop/s on the 200k x 200k x 33792
+  // stress (profiles/).  NBW_GRAM_VARIANT=4 selects the single-CTA persistent kernel it replaced
+  // (128 x 256 tiles, cta_group::1: 2.89 / 3.44 Pop/s), kept for comparison.
   int variant = 5;
   if (const char* v = getenv("NBW_GRAM_VARIANT")) variant = atoi(v);
-  // B rows per TMA box: variants 1, 3, 4 stage 256-wide tiles; the pair variant stages half of N per CTA
-  const int bn = (variant == 0 || variant == 2 || variant == 5) ? 128 : 256;
+  NBW_REQUIRE(ctx, variant == 4 || variant == 5, "NBW_GRAM_VARIANT must be 4 (single CTA) or 5 (CTA pair)");
+  const int bn = variant == 5 ? PAIR_B_ROWS : 256;   // rows of B per TMA box
   CUtensorMap map_a, map_b;
   int rc = make_operand_map(ctx, &map_a, A, m, lda, BM);
   if (rc) return rc;
   rc = make_operand_map(ctx, &map_b, B, n, ldb, bn);
   if (rc) return rc;
-  const int32_t mt_all = (int32_t)((m + BM - 1) / BM), nt_all = (int32_t)((n + bn - 1) / bn);
-  NBW_REQUIRE(ctx, (int64_t)mt_all * nt_all < ((int64_t)1 << 31), "gram: too many tiles for one launch");
-  const unsigned grid = (unsigned)((int64_t)mt_all * nt_all);
   const int32_t kb0 = (int32_t)(k0 / BK), nkb = (int32_t)((k1 - k0) / BK);
-#define NBW_GRAM_LAUNCH(BN_, ST_)                                                                          \
-  do {                                                                                                     \
-    static bool attr_set = false;                                                                          \
-    if (!attr_set) {                                                                                       \
-      NBW_CUDA(ctx, cudaFuncSetAttribute(gram_i8_tcgen05_kernel<BN_, ST_>,                                  \
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize,                      \
-                                         (int)gram_smem_bytes<BN_, ST_>()));                                \
-      attr_set = true;                                                                                     \
-    }                                                                                                      \
-    gram_i8_tcgen05_kernel<BN_, ST_><<<grid, 128, gram_smem_bytes<BN_, ST_>(), st>>>(map_a, map_b, C, ldc, m, n, \
-                                                                                   kb0, nkb, mt_all, nt_all); \
-  } while (0)
-  switch (variant) {
-    case 0: NBW_GRAM_LAUNCH(128, 3); break;   // 97 KB: two CTAs per SM
-    case 1: NBW_GRAM_LAUNCH(256, 4); break;   // 193 KB: one CTA per SM, 256 TMEM columns
-    case 2: NBW_GRAM_LAUNCH(128, 6); break;   // experiment: deeper pipeline, one CTA per SM
-    case 3: NBW_GRAM_LAUNCH(256, 2); break;   // experiment: 97 KB, two CTAs per SM x 256 columns
-    case 4: {                                 // persistent, epilogue overlapped through two TMEM buffers
-      static bool attr4 = false;
-      constexpr size_t kBytes = gram_persist_smem_bytes<256, 4>();
-      if (!attr4) {
-        NBW_CUDA(ctx, cudaFuncSetAttribute(gram_i8_persistent_kernel<256, 4>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBytes));
-        attr4 = true;
-      }
-      const int64_t tiles = (int64_t)mt_all * nt_all;
-      const unsigned ctas = (unsigned)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
-      gram_i8_persistent_kernel<256, 4><<<ctas, 192, kBytes, st>>>(map_a, map_b, C, ldc, m, n, kb0, nkb, mt_all, nt_all);
-      break;
+  if (variant == 4) {
+    static bool attr4 = false;
+    constexpr size_t kBytes = gram_persist_smem_bytes<256, 4>();
+    if (!attr4) {
+      NBW_CUDA(ctx, cudaFuncSetAttribute(gram_i8_persistent_kernel<256, 4>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBytes));
+      attr4 = true;
     }
-    case 5: {                                 // CTA pairs: cta_group::2, 256 x 256 tiles
-      int stages = 6;
-      if (const char* v = getenv("NBW_GRAM_STAGES")) stages = atoi(v);
-      const int32_t mt2 = (int32_t)((m + 2 * BM - 1) / (2 * BM)), nt2 = (int32_t)((n + PAIR_BN - 1) / PAIR_BN);
-      const int64_t tiles = (int64_t)mt2 * nt2;
-#define NBW_PAIR_LAUNCH(ST_)                                                                                  \
-  case ST_: {                                                                                                 \
-    static int max_pairs = 0;                                                                                 \
-    constexpr size_t kBytes = gram_pair_smem_bytes<ST_>();                                                    \
-    if (!max_pairs) {                                                                                         \
-      NBW_CUDA(ctx, cudaFuncSetAttribute(gram_i8_pair_kernel<ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                         (int)kBytes));                                                       \
-      cudaLaunchConfig_t cfg = {};                                                                            \
-      cfg.gridDim = dim3((unsigned)(ctx->sm_count & ~1));                                                     \
-      cfg.blockDim = dim3(192);                                                                               \
-      cfg.dynamicSmemBytes = kBytes;                                                                          \
-      int clusters = 0;                                                                                       \
-      NBW_CUDA(ctx, cudaOccupancyMaxActiveClusters(&clusters, gram_i8_pair_kernel<ST_>, &cfg));               \
-      NBW_REQUIRE(ctx, clusters >= 1, "no CTA pair of the Gram kernel fits this device");                     \
-      max_pairs = clusters;                                                                                   \
-    }                                                                                                         \
-    const unsigned pairs = (unsigned)(tiles < max_pairs ? tiles : max_pairs);                                 \
-    gram_i8_pair_kernel<ST_><<<2 * pairs, 192, kBytes, st>>>(map_a, map_b, C, ldc, m, n, kb0, nkb, mt2, nt2);  \
-    break;                                                                                                    \
-  }
-      switch (stages) {
-        NBW_PAIR_LAUNCH(4)
-        NBW_PAIR_LAUNCH(5)
-        NBW_PAIR_LAUNCH(6)
-        NBW_PAIR_LAUNCH(7)
-        default: NBW_FAIL(ctx, NBW_ERR_INVALID, "NBW_GRAM_STAGES must be 4..7");
-      }
-#undef NBW_PAIR_LAUNCH
-      if (getenv("NBW_GRAM_VERBOSE")) fprintf(stderr, "[nbw] pair gram: %lld tiles, stages %d\n", (long long)tiles, stages);
-      break;
+    const int32_t mt = (int32_t)((m + BM - 1) / BM), nt = (int32_t)((n + 255) / 256);
+    const int64_t tiles = (int64_t)mt * nt;
+    NBW_REQUIRE(ctx, tiles < ((int64_t)1 << 31), "gram: too many tiles for one launch");
+    const unsigned ctas = (unsigned)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
+    gram_i8_persistent_kernel<256, 4><<<ctas, 192, kBytes, st>>>(map_a, map_b, C, ldc, m, n, kb0, nkb, mt, nt);
+  } else {
+    static int max_pairs = 0;
+    constexpr size_t kBytes = gram_pair_smem_bytes<PAIR_STAGES>();
+    if (!max_pairs) {
+      NBW_CUDA(ctx, cudaFuncSetAttribute(gram_i8_pair_kernel<PAIR_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kBytes));
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)(ctx->sm_count & ~1));
+      cfg.blockDim = dim3(192);
+      cfg.dynamicSmemBytes = kBytes;
+      int clusters = 0;
+      NBW_CUDA(ctx, cudaOccupancyMaxActiveClusters(&clusters, gram_i8_pair_kernel<PAIR_STAGES>, &cfg));
+      NBW_REQUIRE(ctx, clusters >= 1, "no CTA pair of the Gram kernel fits this device");
+      max_pairs = clusters;
     }
-    default: NBW_FAIL(ctx, NBW_ERR_INVALID, "unknown NBW_GRAM_VARIANT %d", variant);
+    const int32_t mt2 = (int32_t)((m + 2 * BM - 1) / (2 * BM)), nt2 = (int32_t)((n + PAIR_BN - 1) / PAIR_BN);
+    const int64_t tiles = (int64_t)mt2 * nt2;
+    NBW_REQUIRE(ctx, tiles < ((int64_t)1 << 31), "gram: too many tiles for one launch");
+    const unsigned pairs = (unsigned)(tiles < max_pairs ? tiles : max_pairs);
+    gram_i8_pair_kernel<PAIR_STAGES><<<2 * pairs, 192, kBytes, st>>>(map_a, map_b, C, ldc, m, n, kb0, nkb, mt2, nt2);
   }
-#undef NBW_GRAM_LAUNCH
   NBW_CHECK_LAUNCH(ctx);
   return NBW_OK;
 }

@@ -233,15 +233,3 @@ __device__ __forceinline__ void successor_sums(uint32_t succ, int sub_base, int 
     m &= m - 1u;
   }
 }
-
-// Size of the node's label class inside its cell and its rank in it, from ONE warp match:
-// lanes without a counted label get a class id no other lane can hold.
-template <int NMAX>
-__device__ __forceinline__ void class_count_rank(uint64_t id64, bool valid, int lane, int sub_base,
-                                                 int& count, int& rank) {
-  const unsigned long long cid = valid ? (unsigned long long)id64 : (NBW_NOCLASS_BIT | (unsigned long long)lane);
-  const uint32_t sub_mask = (NMAX == 32 ? 0xffffffffu : ((1u << NMAX) - 1u)) << sub_base;
-  const uint32_t peers = __match_any_sync(0xffffffffu, cid) & sub_mask;
-  count = valid ? __popc(peers) : 0;
-  rank = __popc(peers & ((1u << lane) - 1u));
-}

@@ -101,7 +101,7 @@ def main():
         Cout = eng.empty((n, n), torch.int32)
         ms = timed(lambda: eng.gram(A, A, 0, k, out=Cout), flush, reps=5)
         ops = 2.0 * n * n * k
-        out["kernels"]["gram_i8_tcgen05_kernel"] = {"ms": ms, "m": n, "n": n, "k": k, "int_ops": ops,
+        out["kernels"]["gram_i8_pair_kernel"] = {"ms": ms, "m": n, "n": n, "k": k, "int_ops": ops,
                                                     "achieved_tops": ops / ms / 1e9,
                                                     "frac_of_assumed_int8_peak": ops / ms / 1e9 / i8_peak,
                                                     "frac_of_bf16_peak": ops / ms / 1e9 / peaks["bf16_tflops"]}
