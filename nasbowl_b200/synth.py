@@ -243,6 +243,38 @@ def _darts_cell(seed, idx, want_encoding=False):
 ENC_BYTES = {1: 8, 2: 16}
 
 
+NB201_CHOICES = ['nor_conv_3x3', 'nor_conv_1x1', 'avg_pool_3x3', 'skip_connect', 'none']
+DARTS_CHOICES = ['max_pool_3x3', 'avg_pool_3x3', 'skip_connect', 'sep_conv_3x3', 'sep_conv_5x5', 'dil_conv_3x3',
+                 'dil_conv_5x5']
+
+
+def nb201_arch_string(enc) -> str:
+    """The NAS-Bench-201 query string of an encoding — what the reference stores as G.name
+    (generate_test_graphs.py:171-176) and hands to the benchmark look-up."""
+    o = [NB201_CHOICES[int(c)] for c in enc[:6]]
+    return '|%s~0|+|%s~0|%s~1|+|%s~0|%s~1|%s~2|' % tuple(o)
+
+
+def nb201_encoding(arch_string: str):
+    """Inverse of nb201_arch_string (how the reference's mutation reads its parents, :413-414)."""
+    ops = [tok[:-2] for tok in arch_string.split('|') if '~' in tok]
+    assert len(ops) == 6, arch_string
+    return [NB201_CHOICES.index(o) for o in ops] + [0, 0]
+
+
+def darts_genotype_pairs(enc):
+    """[(op_name, input)] x 8: the `normal` list of a DARTS Genotype (darts_objectives.py:159-198)."""
+    return [(DARTS_CHOICES[int(enc[2 * k])], int(enc[2 * k + 1])) for k in range(8)]
+
+
+def darts_encoding(pairs):
+    out = []
+    for op, src in pairs:
+        out += [DARTS_CHOICES.index(op), int(src)]
+    assert len(out) == 16
+    return out
+
+
 def generate_encoded_host(family: int, seed: int, first_index: int, n_cells: int):
     """Host twin of nbw_generate_encoded: (CellBatch, encodings uint8 [n, 8 | 16])."""
     assert family in (1, 2)

@@ -361,10 +361,20 @@ def test_encoded_mutation_host_twin_and_reference_rules():
             cell = synth.nb201_from_choice(e[:6]) if family == 1 else synth.darts_from_genotype(e[0::2], e[1::2])
             n_max = ch.n_max
             assert cell[0][:n_max] == list(ch.labels[i]) and cell[1][:n_max] == list(ch.succ[i])
+    # encodings <-> the architecture descriptions the reference's drivers evaluate
+    _, e201 = synth.generate_encoded_host(1, 3, 0, 20)
+    for e in e201:
+        assert synth.nb201_encoding(synth.nb201_arch_string(e)) == [int(v) for v in e]
+    _, ed = synth.generate_encoded_host(2, 3, 0, 20)
+    for e in ed:
+        assert synth.darts_encoding(synth.darts_genotype_pairs(e)) == [int(v) for v in e]
     from oracle.ref_import import load_reference, reference_available
     if not reference_available():
         return
     R = load_reference()
+    for e in e201[:5]:      # the string is the reference's own G.name for that architecture
+        g = R.gtg.create_nasbench201_graph([synth.NB201_CHOICES[int(c)] for c in e[:6]])
+        assert g.name == synth.nb201_arch_string(e)
     from darts.cnn.genotypes import Genotype
     from darts.utils import darts2graph
     ops201 = ['nor_conv_3x3', 'nor_conv_1x1', 'avg_pool_3x3', 'skip_connect', 'none']
