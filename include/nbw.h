@@ -148,6 +148,9 @@ int nbw_chol_f64(nbw_ctx* ctx, const double* A, int64_t lda, int64_t n, double s
  * gradient w.r.t. lik): L (lower), Linv = L^-1, alpha = (K + lik I)^-1 y and
  *   stats_h[0] = log|K + lik I|,  stats_h[1] = y^T (K + lik I)^-1 y,  stats_h[2] = tr (K + lik I)^-1,
  *   stats_h[3] = |alpha|^2   (stats_h has 4 entries).
+ * Linv = alpha = NULL asks for the likelihood terms only (stats_h[0], stats_h[1]; the others are 0):
+ * the inverse is skipped and z = L^-1 y comes from one forward substitution — what the grid search over
+ * h needs per candidate (bayesopt/gp.py:521-527).
  * Syncs.  Returns NBW_ERR_NOT_PD (and *info_h = failing pivot + 1) when the factorisation breaks
  * down; the caller retries with 10x the jitter like utils.py:127-133. */
 int nbw_gp_factor(nbw_ctx* ctx, const double* K, int64_t ldk, int64_t n, double lik,

@@ -130,7 +130,7 @@ class GraphGP:
         lik = float(np.float32(lik))
         for hc in subtree_candidates:
             K = k.gram_device(fit, hc)
-            _, _, _, logdet, yKy, _, _ = eng.pd_inverse(K, float(lik), y_dev)
+            _, _, _, logdet, yKy, _, _ = eng.pd_inverse(K, float(lik), y_dev, want_inverse=False)
             nlml = _nlml_from_stats(logdet, yKy, self.n)
             grid[int(hc)] = nlml
             if nlml < best_nlml:

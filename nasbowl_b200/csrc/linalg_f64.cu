@@ -358,6 +358,39 @@ trtri_lower_kernel(const double* __restrict__ L, int64_t ldl, int64_t n, double*
   }
 }
 
+// z = L^-1 y for ONE right-hand side (the grid search over h needs y^T K^-1 y = |z|^2 and log|K| only,
+// not the inverse): one CTA walks the 32-row blocks; eight warps form the products with the part of z
+// already known, warp 0 finishes the block by forward substitution.
+__global__ void __launch_bounds__(256)
+trsv_lower_kernel(const double* __restrict__ L, int64_t ldl, int64_t n, const double* __restrict__ y, double* z) {
+  __shared__ double rhs[NB];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int64_t r0 = 0; r0 < n; r0 += NB) {
+    for (int i = warp; i < NB; i += 8) {
+      const int64_t row = r0 + i;
+      double acc = 0.0;
+      if (row < n)
+        for (int64_t k = lane; k < r0; k += 32) acc = fma(L[row * ldl + k], __ldcg(z + k), acc);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) rhs[i] = row < n ? y[row] - acc : 0.0;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const int64_t row = r0 + lane;
+      double v = rhs[lane];
+      for (int p = 0; p < NB; ++p) {
+        const bool live = r0 + p < n;
+        const double zp = __shfl_sync(0xffffffffu, v, p) / (live ? L[(r0 + p) * ldl + r0 + p] : 1.0);
+        if (lane == p) v = zp;
+        else if (lane > p && row < n && live) v = fma(-L[row * ldl + r0 + p], zp, v);
+      }
+      if (row < n) z[row] = v;
+    }
+    __syncthreads();
+  }
+}
+
 int trtri_enqueue(nbw_ctx* ctx, const double* L, int64_t ldl, int64_t n, double* X, int64_t ldx, cudaStream_t st) {
   NBW_CUDA(ctx, cudaMemset2DAsync(X, ldx * sizeof(double), 0, n * sizeof(double), n, st));
   trtri_lower_kernel<<<(unsigned)((n + NB - 1) / NB), NB * NB, 0, st>>>(L, ldl, n, X, ldx);
@@ -474,8 +507,9 @@ extern "C" int nbw_gp_factor(nbw_ctx* ctx, const double* K, int64_t ldk, int64_t
                              const double* y, double* L, int64_t ldl, double* Linv, int64_t ldi,
                              double* alpha, double* stats_h, int* info_h, void* stream) {
   if (!ctx) return NBW_ERR_INVALID;
-  NBW_REQUIRE(ctx, n > 0 && ldk >= n && ldl >= n && ldi >= n, "bad shape");
-  NBW_REQUIRE(ctx, K && y && L && Linv && alpha && stats_h && info_h, "null pointer");
+  NBW_REQUIRE(ctx, n > 0 && ldk >= n && ldl >= n && (Linv == nullptr || ldi >= n), "bad shape");
+  NBW_REQUIRE(ctx, K && y && L && stats_h && info_h, "null pointer");
+  NBW_REQUIRE(ctx, (Linv == nullptr) == (alpha == nullptr), "Linv and alpha are requested together");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc = nbw_scratch_ensure(ctx, Carver::pad(sizeof(double) * n) + 4096, st);
   if (rc) return rc;
@@ -486,19 +520,26 @@ extern "C" int nbw_gp_factor(nbw_ctx* ctx, const double* K, int64_t ldk, int64_t
   NBW_CUDA(ctx, cudaMemsetAsync(d_stats, 0, sizeof(double) * 4, st));
   rc = chol_enqueue(ctx, K, ldk, n, lik, L, ldl, d_stats + 0, d_info, st);
   if (rc) return rc;
-  rc = trtri_enqueue(ctx, L, ldl, n, Linv, ldi, st);
-  if (rc) return rc;
-  // z = Linv y ; alpha = Linv^T z
-  rc = gemm_enqueue(ctx, 0, 0, n, 1, n, 1.0, Linv, ldi, y, 1, 0.0, z, 1, st);
-  if (rc) return rc;
-  rc = gemm_enqueue(ctx, 1, 0, n, 1, n, 1.0, Linv, ldi, z, 1, 0.0, alpha, 1, st);
-  if (rc) return rc;
+  if (Linv) {
+    rc = trtri_enqueue(ctx, L, ldl, n, Linv, ldi, st);
+    if (rc) return rc;
+    // z = Linv y ; alpha = Linv^T z
+    rc = gemm_enqueue(ctx, 0, 0, n, 1, n, 1.0, Linv, ldi, y, 1, 0.0, z, 1, st);
+    if (rc) return rc;
+    rc = gemm_enqueue(ctx, 1, 0, n, 1, n, 1.0, Linv, ldi, z, 1, 0.0, alpha, 1, st);
+    if (rc) return rc;
+  } else {
+    trsv_lower_kernel<<<1, 256, 0, st>>>(L, ldl, n, y, z);   // likelihood only: no inverse
+    NBW_CHECK_LAUNCH(ctx);
+  }
   sumsq_kernel<<<1, 256, 0, st>>>(z, 1, n, 1, d_stats + 1);
   NBW_CHECK_LAUNCH(ctx);
-  sumsq_kernel<<<nbw_grid_for(ctx, n * n, 256, 2), 256, 0, st>>>(Linv, ldi, n, n, d_stats + 2);
-  NBW_CHECK_LAUNCH(ctx);
-  sumsq_kernel<<<1, 256, 0, st>>>(alpha, 1, n, 1, d_stats + 3);
-  NBW_CHECK_LAUNCH(ctx);
+  if (Linv) {
+    sumsq_kernel<<<nbw_grid_for(ctx, n * n, 256, 2), 256, 0, st>>>(Linv, ldi, n, n, d_stats + 2);
+    NBW_CHECK_LAUNCH(ctx);
+    sumsq_kernel<<<1, 256, 0, st>>>(alpha, 1, n, 1, d_stats + 3);
+    NBW_CHECK_LAUNCH(ctx);
+  }
   double hs[4];
   NBW_CUDA(ctx, cudaMemcpyAsync(hs, d_stats, sizeof(hs), cudaMemcpyDeviceToHost, st));
   NBW_CUDA(ctx, cudaMemcpyAsync(info_h, d_info, sizeof(int), cudaMemcpyDeviceToHost, st));

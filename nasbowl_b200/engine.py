@@ -238,13 +238,14 @@ class Engine:
         self._check(self.lib.nbw_gemm_f64(self.ctx, int(ta), int(tb), m, n, k, float(alpha), self._p(A), lda,
                                           self._p(B), ldb, float(beta), self._p(Cm), ldc, self.stream))
 
-    def gp_factor(self, K: torch.Tensor, lik: float, y: torch.Tensor):
+    def gp_factor(self, K: torch.Tensor, lik: float, y: torch.Tensor, want_inverse: bool = True):
         """One attempt of compute_pd_inverse (bayesopt/utils.py:127-140) at jitter `lik`.
-        Returns (L, Linv, alpha, logdet, yKy, trKinv, |alpha|^2); raises NotPositiveDefinite."""
+        Returns (L, Linv, alpha, logdet, yKy, trKinv, |alpha|^2); raises NotPositiveDefinite.
+        want_inverse=False: likelihood terms only (Linv = alpha = None, the last two stats 0)."""
         n = K.shape[0]
         L = self.empty((n, n), torch.float64)
-        Linv = self.empty((n, n), torch.float64)
-        alpha = self.empty((n,), torch.float64)
+        Linv = self.empty((n, n), torch.float64) if want_inverse else None
+        alpha = self.empty((n,), torch.float64) if want_inverse else None
         stats = (C.c_double * 4)()
         info = C.c_int(0)
         self._check(self.lib.nbw_gp_factor(self.ctx, self._p(K), K.stride(0), n, float(lik), self._p(y),
@@ -252,12 +253,12 @@ class Engine:
                                            C.byref(info), self.stream))
         return L, Linv, alpha, float(stats[0]), float(stats[1]), float(stats[2]), float(stats[3])
 
-    def pd_inverse(self, K: torch.Tensor, jitter: float, y: torch.Tensor):
+    def pd_inverse(self, K: torch.Tensor, jitter: float, y: torch.Tensor, want_inverse: bool = True):
         """compute_pd_inverse with its jitter retry (x10, x100) — bayesopt/utils.py:120-140."""
         last = None
         for fail in range(3):
             try:
-                return self.gp_factor(K, jitter * (10 ** fail), y)
+                return self.gp_factor(K, jitter * (10 ** fail), y, want_inverse)
             except _lib.NotPositiveDefinite as e:
                 last = e
         raise RuntimeError("Gram matrix not positive definite despite of jitter") from last

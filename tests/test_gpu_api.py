@@ -311,3 +311,25 @@ def test_trainable_wl_layer_weights(fam):
         np.testing.assert_allclose(mu.numpy(), z[fam + "_%s_mu" % tag], rtol=2e-3, atol=2e-3)
         with pytest.raises(NotImplementedError):       # the fused pool kernel has unit layer weights built in
             gp.predict_diag(pool)
+
+
+@pytest.mark.gpu
+def test_likelihood_only_factorisation_matches_full():
+    """nbw_gp_factor without the inverse (what the h grid search uses per candidate) gives the same
+    log-determinant and y^T K^-1 y as the full factorisation and as numpy."""
+    from nasbowl_b200.engine import Engine
+    eng = Engine.get()
+    rng = np.random.RandomState(0)
+    for n in (1, 5, 32, 33, 150, 700):
+        A = rng.randn(n, n + 3)
+        K = A @ A.T / (n + 3) + 0.05 * np.eye(n)
+        y = rng.randn(n)
+        Kd, yd = torch.tensor(K, device="cuda"), torch.tensor(y, device="cuda")
+        full = eng.gp_factor(Kd, 0.01, yd)
+        lite = eng.gp_factor(Kd, 0.01, yd, want_inverse=False)
+        assert lite[1] is None and lite[2] is None
+        Kl = K + 0.01 * np.eye(n)
+        np.testing.assert_allclose(lite[3], np.linalg.slogdet(Kl)[1], rtol=1e-10, atol=1e-10)
+        np.testing.assert_allclose(lite[4], y @ np.linalg.solve(Kl, y), rtol=1e-9)
+        np.testing.assert_allclose([lite[3], lite[4]], [full[3], full[4]], rtol=1e-11, atol=1e-12)
+        assert torch.equal(full[0], lite[0])
