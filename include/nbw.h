@@ -271,7 +271,9 @@ int nbw_score_pool_host(nbw_ctx* ctx, const nbw_model* model_h, const void* cell
 /* Mapped form of the same call (acquisitions.py:94-113): `cells_h` must be PINNED host memory (cudaHostAlloc / cudaHostRegister); the kernel
  * reads the records straight over PCIe through the mapped pointer — no staging copy, no per-chunk
  * launches.  The pool is cut into `pieces` (1..64) kernels only so that the D2H copy of piece i's
- * scores overlaps the kernel on piece i+1 (pieces = 1 measured best at 1M).  Pageable `cells_h` is refused (NBW_ERR_INVALID): use
+ * scores overlaps the kernel on piece i+1 (pieces = 1 measured best at 1M).  Pays only when the kernel is
+ * slower than the PCIe transfer of its records (16-byte records, h >= 5: 0.57 vs 0.61 ms per 1M); a
+ * transfer-bound pool is faster through the DMA pipeline of nbw_score_pool_host.  Pageable `cells_h` is refused (NBW_ERR_INVALID): use
  * nbw_score_pool_host for it.  Same stream semantics as nbw_score_pool_host. */
 int nbw_score_pool_mapped(nbw_ctx* ctx, const nbw_model* model_h, const void* cells_h,
                           int64_t n_cells, float* scores_h, float* scores_dev, int pieces,

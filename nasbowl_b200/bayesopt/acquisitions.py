@@ -87,12 +87,16 @@ class GraphExpectedImprovement(BaseAcquisition):
         eng = self.gp._dev['eng']
         host_scores = None
         if isinstance(candidates, torch.Tensor) and not candidates.is_cuda:
-            # packed records in host memory.  Pinned: the kernel reads them over PCIe, one D2H copy
-            # of the scores follows (nbw_score_pool_mapped).  Pageable: staged pipeline.
-            if candidates.is_pinned():
-                scores, host_scores = eng.score_host_pool(self._model(), candidates, chunks=1, mapped=True)
+            # packed records in host memory: the staged H2D / kernel / D2H pipeline, unless the pool is
+            # pinned AND the kernel is clearly slower than the PCIe transfer of its records — then the
+            # kernel reads them itself (nbw_score_pool_mapped).  Measured per 1M candidates
+            # (profiles/r01_e2e_probe*.txt): 16-byte records at h = 5: mapped 0.57 ms vs staged 0.61;
+            # 16-byte records at h = 2: 0.54 vs 0.46; 48-byte records at h = 2: 1.96 vs 1.10.
+            model = self._model()
+            if candidates.is_pinned() and model.n_max == 8 and model.h >= 5:
+                scores, host_scores = eng.score_host_pool(model, candidates, chunks=1, mapped=True)
             else:
-                scores, host_scores = eng.score_host_pool(self._model(), candidates)
+                scores, host_scores = eng.score_host_pool(model, candidates, chunks=8)
         else:
             scores, _, _, _ = self.score_pool(candidates)
         vals, indices = eng.topk(scores, top_n, distinct=bool(return_distinct))      # syncs

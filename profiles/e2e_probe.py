@@ -5,18 +5,23 @@ from nasbowl_b200.bayesopt import GraphExpectedImprovement, GraphGP
 from nasbowl_b200.engine import Engine
 from nasbowl_b200.kernels import WeisfilerLehman
 eng = Engine.get()
+wl_name = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
+wl = bench.WORKLOADS[wl_name]
+bench.FAMILY, bench.N_TRAIN, bench.H_GRID = wl["family"], wl["n_train"], wl["h_grid"]
 train, y = bench.make_training_set()
-gp = GraphGP(train, y, [WeisfilerLehman(h=2)]); gp.fit(wl_subtree_candidates=tuple(range(6)))
+gp = GraphGP(train, y, [WeisfilerLehman(h=2)]); gp.fit(wl_subtree_candidates=wl["h_grid"])
 acq = GraphExpectedImprovement(gp)
-M = 1_000_000
-dev = eng.generate_cells(1, 1234, 10000, M)
-host = torch.empty((M, 16), dtype=torch.uint8).pin_memory(); host.copy_(dev.cpu())
+M = wl["pool"]
+dev = eng.generate_cells(wl["family"], 1234, 10000, M)
+stride = dev.shape[1]
+print("workload", wl_name, "pool", M, "record bytes", stride, "h*", gp.kernels[0].h)
+host = torch.empty((M, stride), dtype=torch.uint8).pin_memory(); host.copy_(dev.cpu())
 d2 = torch.empty_like(dev)
 torch.cuda.synchronize()
 t=time.perf_counter()
 for _ in range(20): d2.copy_(host, non_blocking=True)
 torch.cuda.synchronize(); dt=(time.perf_counter()-t)/20
-print("H2D 16MB pinned: %.3f ms = %.1f GB/s" % (dt*1e3, 16e6/dt/1e9))
+print("H2D %.0f MB pinned: %.3f ms = %.1f GB/s" % (M*stride/1e6, dt*1e3, M*stride/dt/1e9))
 hs = torch.empty((M,), dtype=torch.float32).pin_memory(); ds = torch.empty((M,), dtype=torch.float32, device='cuda')
 t=time.perf_counter()
 for _ in range(20): hs.copy_(ds, non_blocking=True)
