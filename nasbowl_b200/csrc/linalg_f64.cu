@@ -180,36 +180,45 @@ __global__ void chol_init_kernel(const double* __restrict__ A, int64_t lda, int6
   }
 }
 
-// Unblocked factorisation of the nb x nb diagonal block at (k0, k0); 32 x 32 threads.
-__global__ void __launch_bounds__(NB * NB)
-potrf_diag_kernel(double* __restrict__ L, int64_t ldl, int64_t k0, int nb, int* __restrict__ info) {
-  __shared__ double a[NB][NB + 1];
-  const int c = threadIdx.x % NB, r = threadIdx.x / NB;
-  const bool in = r < nb && c < nb;
-  a[r][c] = (in && c <= r) ? L[(k0 + r) * ldl + k0 + c] : 0.0;
-  __syncthreads();
-  for (int j = 0; j < nb; ++j) {
-    if (r == j && c == j) {
-      const double d = a[j][j];
-      if (!(d > 0.0)) atomicCAS(info, 0, (int)(k0 + j + 1));
-      a[j][j] = sqrt(d);
-    }
-    __syncthreads();
-    if (c == j && r > j && r < nb) a[r][j] /= a[j][j];
-    __syncthreads();
-    if (c > j && r >= c && r < nb) a[r][c] -= a[r][j] * a[c][j];
-    __syncthreads();
-  }
-  if (in && c <= r) L[(k0 + r) * ldl + k0 + c] = a[r][c];
-}
-
-// Rows below the diagonal block: X = A21 * L11^-T (one thread per row).
+// One panel step: factor the nb x nb diagonal block at (k0, k0) and solve the rows below it,
+// X = A21 L11^-T.  Measured on B200, the three-kernel form of this step cost ~40 us per panel whatever
+// n was: the time went into serial chains (a 32-step block-synchronous diagonal factorisation and a
+// 32 x 16 deep dependent FMA chain per row), not into launches or flops.  Here
+//   - warp 0 of EVERY CTA factors the diagonal block warp-synchronously: lane r keeps row r in
+//     registers, the loops are fully unrolled, the column a(., j) travels by shuffle — no block barrier
+//     inside the 32 steps; CTA 0 writes the factor back;
+//   - the row solve is right-looking (x_j known -> all later x_t updated independently), which
+//     turns the long dependent chain into 32 short ones.
 __global__ void __launch_bounds__(128)
-trsm_panel_kernel(double* __restrict__ L, int64_t ldl, int64_t k0, int nb, int64_t n) {
+panel_kernel(double* __restrict__ L, int64_t ldl, int64_t k0, int nb, int64_t n, int* __restrict__ info) {
   __shared__ double l11[NB][NB + 1];
-  for (int t = threadIdx.x; t < NB * NB; t += blockDim.x) {
-    const int r = t / NB, c = t % NB;
-    l11[r][c] = (r < nb && c <= r) ? L[(k0 + r) * ldl + k0 + c] : 0.0;
+  __shared__ double inv_diag[NB];   // 1 / L11[j][j]: the chains below multiply instead of dividing
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x < 32) {
+    double a[NB];
+#pragma unroll
+    for (int c = 0; c < NB; ++c) a[c] = (lane < nb && c <= lane && c < nb) ? L[(k0 + lane) * ldl + k0 + c] : 0.0;
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      if (j < nb) {                                            // uniform
+        const double ajj = __shfl_sync(0xffffffffu, a[j], j);
+        if (!(ajj > 0.0) && lane == j && blockIdx.x == 0) atomicCAS(info, 0, (int)(k0 + j + 1));
+        const double rinv = rsqrt(ajj);          // fp64 sqrt and divide are long dependent sequences
+        if (lane == j) { a[j] = ajj * rinv; inv_diag[j] = rinv; }
+        else if (lane > j) a[j] *= rinv;
+#pragma unroll
+        for (int c = j + 1; c < NB; ++c) {
+          const double acj = __shfl_sync(0xffffffffu, a[j], c);
+          if (lane >= c) a[c] = fma(-a[j], acj, a[c]);
+        }
+      }
+    }
+    if (lane >= nb) inv_diag[lane] = 0.0;
+#pragma unroll
+    for (int c = 0; c < NB; ++c) {
+      l11[lane][c] = (c <= lane) ? a[c] : 0.0;
+      if (blockIdx.x == 0 && lane < nb && c <= lane && c < nb) L[(k0 + lane) * ldl + k0 + c] = a[c];
+    }
   }
   __syncthreads();
   const int64_t i = k0 + nb + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -221,11 +230,10 @@ trsm_panel_kernel(double* __restrict__ L, int64_t ldl, int64_t k0, int nb, int64
 #pragma unroll
   for (int j = 0; j < NB; ++j) {
     if (j < nb) {
-      double v = x[j];
+      const double xj = x[j] * inv_diag[j];
+      x[j] = xj;
 #pragma unroll
-      for (int t = 0; t < NB; ++t)
-        if (t < j) v -= x[t] * l11[j][t];
-      x[j] = v / l11[j][j];
+      for (int t = j + 1; t < NB; ++t) x[t] = fma(-xj, l11[t][j], x[t]);
     }
   }
 #pragma unroll
@@ -302,12 +310,10 @@ int chol_enqueue(nbw_ctx* ctx, const double* A, int64_t lda, int64_t n, double s
   NBW_CHECK_LAUNCH(ctx);
   for (int64_t k0 = 0; k0 < n; k0 += NB) {
     const int nb = (int)((n - k0) < NB ? (n - k0) : NB);
-    potrf_diag_kernel<<<1, NB * NB, 0, st>>>(L, ldl, k0, nb, d_info);
-    NBW_CHECK_LAUNCH(ctx);
     const int64_t rest = n - k0 - nb;
+    panel_kernel<<<(unsigned)(rest > 0 ? (rest + 127) / 128 : 1), 128, 0, st>>>(L, ldl, k0, nb, n, d_info);
+    NBW_CHECK_LAUNCH(ctx);
     if (rest > 0) {
-      trsm_panel_kernel<<<(unsigned)((rest + 127) / 128), 128, 0, st>>>(L, ldl, k0, nb, n);
-      NBW_CHECK_LAUNCH(ctx);
       const unsigned tiles = (unsigned)((rest + 63) / 64);
       syrk_update_kernel<<<dim3(tiles, tiles), 256, 0, st>>>(L, ldl, k0, nb, n);
       NBW_CHECK_LAUNCH(ctx);
@@ -319,43 +325,133 @@ int chol_enqueue(nbw_ctx* ctx, const double* A, int64_t lda, int64_t n, double s
 }
 
 // ------------------------------------------------------------------ triangular inverse
-// One CTA per 32-wide block column c of X = L^-1; rows are produced top to bottom:
-//   X[r,c] = L[r,r]^-1 * ( [r==c] I - sum_{c <= t < r} L[r,t] X[t,c] )
-__global__ void __launch_bounds__(NB * NB)
-trtri_lower_kernel(const double* __restrict__ L, int64_t ldl, int64_t n, double* X, int64_t ldx) {
-  __shared__ double Ls[NB][NB + 1];
-  __shared__ double Xs[NB][NB + 1];
-  const int j = threadIdx.x % NB, i = threadIdx.x / NB;
-  const int64_t nblk = (n + NB - 1) / NB;
-  const int64_t c = blockIdx.x, c0 = c * NB;
-  for (int64_t r = c; r < nblk; ++r) {
-    const int64_t r0 = r * NB;
-    double acc = 0.0;
-    for (int64_t t = c; t < r; ++t) {
-      const int64_t t0 = t * NB;
-      Ls[i][j] = (r0 + i < n && t0 + j < n) ? L[(r0 + i) * ldl + t0 + j] : 0.0;
-      Xs[i][j] = (t0 + i < n && c0 + j < n) ? X[(t0 + i) * ldx + c0 + j] : 0.0;
-      __syncthreads();
-#pragma unroll 8
-      for (int p = 0; p < NB; ++p) acc = fma(Ls[i][p], Xs[p][j], acc);
-      __syncthreads();
-    }
-    // right-hand side and the diagonal block
-    Xs[i][j] = (r == c) ? ((i == j) ? 1.0 : 0.0) : -acc;
-    Ls[i][j] = (r0 + i < n && r0 + j < n && j <= i) ? L[(r0 + i) * ldl + r0 + j]
-                                                   : ((i == j) ? 1.0 : 0.0);
-    __syncthreads();
-    if (i == 0) {   // lane j forward-substitutes column j
-      for (int p = 0; p < NB; ++p) {
-        double v = Xs[p][j];
-        for (int q = 0; q < p; ++q) v -= Ls[p][q] * Xs[q][j];
-        Xs[p][j] = v / Ls[p][p];
+// X = L^-1 by recursive doubling: invert the 32 x 32 diagonal blocks (one warp each, right-looking
+// substitution out of shared memory), then for s = 32, 64, 128, ... merge neighbouring s-blocks,
+//     [ L11  0  ]^-1   [ X11            0  ]
+//     [ L21 L22 ]    = [ -X22 L21 X11  X22 ],
+// as two batched block products per level (W = L21 X11, X21 = -X22 W; all block pairs of a level in one
+// launch).  1 + 2 log2(n / 32) launches of GEMM-shaped work replace the block-column sweep this file
+// used before, whose n / 32 sequential steps per column made it the longest piece of the factorisation
+// (1.4 ms of 3.2 ms at n = 1000).
+static inline size_t trtri_front_bytes(int64_t n) { return Carver::pad(sizeof(double) * (size_t)n) + 8192; }
+static inline size_t trtri_scratch_bytes(int64_t n) {
+  return trtri_front_bytes(n) + Carver::pad(sizeof(double) * (size_t)n * (size_t)n);
+}
+
+__global__ void __launch_bounds__(32)
+trtri_diag_kernel(const double* __restrict__ L, int64_t ldl, int64_t n, double* __restrict__ X, int64_t ldx) {
+  __shared__ double l[NB][NB + 1];
+  const int lane = threadIdx.x;
+  const int64_t k0 = (int64_t)blockIdx.x * NB;
+  const int nb = (int)((n - k0) < NB ? (n - k0) : NB);
+  for (int r = 0; r < NB; ++r) l[r][lane] = (r < nb && lane <= r) ? L[(k0 + r) * ldl + k0 + lane] : (r == lane ? 1.0 : 0.0);
+  __syncwarp();
+  // lane j solves L x = e_j
+  double x[NB];
+#pragma unroll
+  for (int p = 0; p < NB; ++p) x[p] = (p == lane) ? 1.0 : 0.0;
+#pragma unroll
+  for (int p = 0; p < NB; ++p) {
+    const double xp = x[p] / l[p][p];
+    x[p] = xp;
+#pragma unroll
+    for (int t = p + 1; t < NB; ++t) x[t] = fma(-xp, l[t][p], x[t]);
+  }
+  if (lane < nb) {
+#pragma unroll
+    for (int p = 0; p < NB; ++p)
+      if (p < nb) X[(k0 + p) * ldx + k0 + lane] = (p >= lane) ? x[p] : 0.0;
+  }
+}
+
+// phase 0: W21 = L21 * X11 ; phase 1: X21 = -X22 * W21, for every pair of neighbouring s-blocks (blockIdx.z)
+__global__ void __launch_bounds__(256)
+trtri_merge_kernel(int phase, int64_t s, int64_t n, const double* __restrict__ L, int64_t ldl, double* X, int64_t ldx,
+                   double* W, int64_t ldw) {
+  constexpr int BM = 64, BN = 64, BK = 16;
+  __shared__ double As[BK][BM + 2];
+  __shared__ double Bs[BK][BN + 2];
+  const int64_t c0 = (int64_t)blockIdx.z * 2 * s, r0 = c0 + s;
+  if (r0 >= n) return;
+  const int64_t m = (n - r0) < s ? (n - r0) : s;       // rows of the lower-left block
+  const int64_t kdim = phase == 0 ? s : m;
+  const double* A = phase == 0 ? L + r0 * ldl + c0 : X + r0 * ldx + r0;
+  const int64_t lda = phase == 0 ? ldl : ldx;
+  const double* B = phase == 0 ? X + c0 * ldx + c0 : W + r0 * ldw + c0;
+  const int64_t ldb = phase == 0 ? ldx : ldw;
+  double* C = phase == 0 ? W + r0 * ldw + c0 : X + r0 * ldx + c0;
+  const int64_t ldc = phase == 0 ? ldw : ldx;
+  const double alpha = phase == 0 ? 1.0 : -1.0;
+  const int64_t row0 = (int64_t)blockIdx.y * BM, col0 = (int64_t)blockIdx.x * BN;
+  if (row0 >= m) return;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  double acc[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
+  // triangular operands: X11 is lower (phase 0: B[k][j] = 0 for k < j), X22 is lower (phase 1: A[i][k] = 0 for k > i)
+  const int64_t k_lo = phase == 0 ? (col0 / BK) * BK : 0;
+  const int64_t k_hi = phase == 0 ? kdim : ((row0 + BM) < kdim ? (row0 + BM) : kdim);
+  for (int64_t k0 = k_lo; k0 < k_hi; k0 += BK) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int idx = threadIdx.x + q * 256;
+      {
+        const int kk = idx % BK, i = idx / BK;
+        const int64_t gi = row0 + i, gk = k0 + kk;
+        As[kk][i] = (gi < m && gk < kdim) ? A[gi * lda + gk] : 0.0;
+      }
+      {
+        const int j = idx % BN, kk = idx / BN;
+        const int64_t gj = col0 + j, gk = k0 + kk;
+        Bs[kk][j] = (gj < s && gk < kdim) ? B[gk * ldb + gj] : 0.0;
       }
     }
     __syncthreads();
-    if (r0 + i < n && c0 + j < n) X[(r0 + i) * ldx + c0 + j] = Xs[i][j];
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      double av[4], bv[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) av[r] = As[kk][ty * 4 + r];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) bv[c] = Bs[kk][tx * 4 + c];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = fma(av[r], bv[c], acc[r][c]);
+    }
     __syncthreads();
   }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int64_t gi = row0 + ty * 4 + r;
+    if (gi >= m) continue;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int64_t gj = col0 + tx * 4 + c;
+      if (gj < s) C[gi * ldc + gj] = alpha * acc[r][c];
+    }
+  }
+}
+
+int trtri_enqueue(nbw_ctx* ctx, const double* L, int64_t ldl, int64_t n, double* X, int64_t ldx, cudaStream_t st) {
+  int rc = nbw_scratch_ensure(ctx, trtri_scratch_bytes(n), st);
+  if (rc) return rc;
+  // W lives behind the front region, where nbw_gp_factor keeps its statistics and one n-vector
+  double* W = reinterpret_cast<double*>(static_cast<char*>(ctx->scratch) + trtri_front_bytes(n));
+  NBW_CUDA(ctx, cudaMemset2DAsync(X, ldx * sizeof(double), 0, n * sizeof(double), n, st));
+  trtri_diag_kernel<<<(unsigned)((n + NB - 1) / NB), 32, 0, st>>>(L, ldl, n, X, ldx);
+  NBW_CHECK_LAUNCH(ctx);
+  for (int64_t s = NB; s < n; s *= 2) {
+    const unsigned pairs = (unsigned)((n + 2 * s - 1) / (2 * s));
+    const unsigned tiles = (unsigned)((s + 63) / 64);
+    for (int phase = 0; phase < 2; ++phase) {
+      trtri_merge_kernel<<<dim3(tiles, tiles, pairs), 256, 0, st>>>(phase, s, n, L, ldl, X, ldx, W, n);
+      NBW_CHECK_LAUNCH(ctx);
+    }
+  }
+  return NBW_OK;
 }
 
 // z = L^-1 y for ONE right-hand side (the grid search over h needs y^T K^-1 y = |z|^2 and log|K| only,
@@ -363,14 +459,25 @@ trtri_lower_kernel(const double* __restrict__ L, int64_t ldl, int64_t n, double*
 // already known, warp 0 finishes the block by forward substitution.
 __global__ void __launch_bounds__(256)
 trsv_lower_kernel(const double* __restrict__ L, int64_t ldl, int64_t n, const double* __restrict__ y, double* z) {
+  extern __shared__ double zs[];            // the part of z already known (n doubles)
   __shared__ double rhs[NB];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int64_t r0 = 0; r0 < n; r0 += NB) {
     for (int i = warp; i < NB; i += 8) {
       const int64_t row = r0 + i;
-      double acc = 0.0;
-      if (row < n)
-        for (int64_t k = lane; k < r0; k += 32) acc = fma(L[row * ldl + k], __ldcg(z + k), acc);
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;   // four loads in flight per lane
+      if (row < n) {
+        const double* lr = L + row * ldl;
+        int64_t k = lane;
+        for (; k + 96 < r0; k += 128) {
+          a0 = fma(lr[k], zs[k], a0);
+          a1 = fma(lr[k + 32], zs[k + 32], a1);
+          a2 = fma(lr[k + 64], zs[k + 64], a2);
+          a3 = fma(lr[k + 96], zs[k + 96], a3);
+        }
+        for (; k < r0; k += 32) a0 = fma(lr[k], zs[k], a0);
+      }
+      double acc = (a0 + a1) + (a2 + a3);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
       if (lane == 0) rhs[i] = row < n ? y[row] - acc : 0.0;
@@ -378,24 +485,25 @@ trsv_lower_kernel(const double* __restrict__ L, int64_t ldl, int64_t n, const do
     __syncthreads();
     if (warp == 0) {
       const int64_t row = r0 + lane;
+      // this lane's row of the diagonal block, fetched before the serial chain starts
+      double lrow[NB];
+#pragma unroll
+      for (int p = 0; p < NB; ++p) lrow[p] = (row < n && p <= lane && r0 + p < n) ? L[row * ldl + r0 + p] : 0.0;
+      double dinv = 0.0;
+#pragma unroll
+      for (int p = 0; p < NB; ++p)
+        if (p == lane) dinv = (row < n) ? 1.0 / lrow[p] : 1.0;
       double v = rhs[lane];
+#pragma unroll
       for (int p = 0; p < NB; ++p) {
-        const bool live = r0 + p < n;
-        const double zp = __shfl_sync(0xffffffffu, v, p) / (live ? L[(r0 + p) * ldl + r0 + p] : 1.0);
+        const double zp = __shfl_sync(0xffffffffu, v * dinv, p);
         if (lane == p) v = zp;
-        else if (lane > p && row < n && live) v = fma(-L[row * ldl + r0 + p], zp, v);
+        else if (lane > p) v = fma(-lrow[p], zp, v);
       }
-      if (row < n) z[row] = v;
+      if (row < n) { z[row] = v; zs[row] = v; }
     }
     __syncthreads();
   }
-}
-
-int trtri_enqueue(nbw_ctx* ctx, const double* L, int64_t ldl, int64_t n, double* X, int64_t ldx, cudaStream_t st) {
-  NBW_CUDA(ctx, cudaMemset2DAsync(X, ldx * sizeof(double), 0, n * sizeof(double), n, st));
-  trtri_lower_kernel<<<(unsigned)((n + NB - 1) / NB), NB * NB, 0, st>>>(L, ldl, n, X, ldx);
-  NBW_CHECK_LAUNCH(ctx);
-  return NBW_OK;
 }
 
 }  // namespace
@@ -511,7 +619,8 @@ extern "C" int nbw_gp_factor(nbw_ctx* ctx, const double* K, int64_t ldk, int64_t
   NBW_REQUIRE(ctx, K && y && L && stats_h && info_h, "null pointer");
   NBW_REQUIRE(ctx, (Linv == nullptr) == (alpha == nullptr), "Linv and alpha are requested together");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int rc = nbw_scratch_ensure(ctx, Carver::pad(sizeof(double) * n) + 4096, st);
+  // everything this call carves out of the arena is reserved up front: a later growth would move it
+  int rc = nbw_scratch_ensure(ctx, Linv ? trtri_scratch_bytes(n) : Carver::pad(sizeof(double) * n) + 4096, st);
   if (rc) return rc;
   Carver cv(ctx->scratch);
   double* d_stats = cv.take<double>(4);   // logdet, yKy, trKinv, |alpha|^2
@@ -529,7 +638,14 @@ extern "C" int nbw_gp_factor(nbw_ctx* ctx, const double* K, int64_t ldk, int64_t
     rc = gemm_enqueue(ctx, 1, 0, n, 1, n, 1.0, Linv, ldi, z, 1, 0.0, alpha, 1, st);
     if (rc) return rc;
   } else {
-    trsv_lower_kernel<<<1, 256, 0, st>>>(L, ldl, n, y, z);   // likelihood only: no inverse
+    // likelihood only: no inverse.  z is kept in shared memory, which bounds n for this path.
+    NBW_REQUIRE(ctx, (size_t)n * sizeof(double) <= 200 * 1024, "likelihood-only factorisation handles n <= 25600");
+    static bool trsv_attr = false;
+    if (!trsv_attr) {
+      NBW_CUDA(ctx, cudaFuncSetAttribute(trsv_lower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      trsv_attr = true;
+    }
+    trsv_lower_kernel<<<1, 256, (size_t)n * sizeof(double), st>>>(L, ldl, n, y, z);
     NBW_CHECK_LAUNCH(ctx);
   }
   sumsq_kernel<<<1, 256, 0, st>>>(z, 1, n, 1, d_stats + 1);

@@ -333,3 +333,33 @@ def test_likelihood_only_factorisation_matches_full():
         np.testing.assert_allclose(lite[4], y @ np.linalg.solve(Kl, y), rtol=1e-9)
         np.testing.assert_allclose([lite[3], lite[4]], [full[3], full[4]], rtol=1e-11, atol=1e-12)
         assert torch.equal(full[0], lite[0])
+
+
+@pytest.mark.gpu
+def test_blocked_cholesky_and_inverse_at_block_boundaries():
+    """L L^T = K + lik I, Linv L = I and the NotPositiveDefinite path, at sizes around the 32-wide
+    panels (the diagonal block is factored warp-synchronously inside the panel kernel)."""
+    from nasbowl_b200 import _lib
+    from nasbowl_b200.engine import Engine
+    eng = Engine.get()
+    rng = np.random.RandomState(1)
+    for n in (1, 2, 31, 32, 33, 64, 65, 150, 257, 1000):
+        A = rng.randn(n, n + 2)
+        Kh = A @ A.T / (n + 2) + 0.1 * np.eye(n)
+        K = torch.tensor(Kh, device="cuda")
+        y = torch.tensor(rng.randn(n), device="cuda")
+        L, Linv, alpha, logdet, yKy, trKinv, a2 = eng.gp_factor(K, 0.01, y)
+        Lh, Lih = L.cpu().numpy(), Linv.cpu().numpy()
+        Kl = Kh + 0.01 * np.eye(n)
+        assert np.array_equal(np.triu(Lh, 1), np.zeros_like(Lh))
+        np.testing.assert_allclose(Lh @ Lh.T, Kl, rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(Lh, np.linalg.cholesky(Kl), rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(Lih @ Lh, np.eye(n), atol=1e-9)
+        np.testing.assert_allclose(alpha.cpu().numpy(), np.linalg.solve(Kl, y.cpu().numpy()), rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(trKinv, np.trace(np.linalg.inv(Kl)), rtol=1e-9)
+    bad = torch.tensor(np.array([[1.0, 2.0], [2.0, 1.0]]), device="cuda")
+    with pytest.raises(_lib.NotPositiveDefinite):
+        eng.gp_factor(bad, 0.0, torch.zeros(2, dtype=torch.float64, device="cuda"))
+    bad = torch.tensor(Kh - 5.0 * np.eye(1000), device="cuda")        # breaks down in a later panel
+    with pytest.raises(_lib.NotPositiveDefinite):
+        eng.gp_factor(bad, 0.0, torch.zeros(1000, dtype=torch.float64, device="cuda"))
