@@ -9,6 +9,8 @@
 // shared-memory atomics and the order of equal digits is preserved.
 #include "nbw_common.cuh"
 
+#include <stdlib.h>
+
 namespace {
 
 constexpr int kSortThreads = 256;
@@ -182,6 +184,44 @@ radix_scatter_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __res
 }
 
 // ---------------------------------------------------------------- unique / ids / verification
+// ---------------------------------------------------------------- small inputs: one-CTA sort
+// A training set is a few hundred cells: a few thousand keys.  The eight radix passes above are then
+// ~30 launches of almost empty kernels per WL level; one CTA sorting (key, index) pairs in shared memory
+// (bitonic network, lexicographic on (key, original index), so the result equals the stable radix
+// order) does the same in one launch.
+constexpr int kSmallSortMax = 8192;    // measured: at 16000 keys the radix passes win (1.2 vs 1.6 ms per fit)
+__global__ void __launch_bounds__(1024)
+small_sort_kernel(const uint64_t* __restrict__ keys, int n, int n_pad, uint64_t* __restrict__ out_k,
+                  uint32_t* __restrict__ out_v) {
+  extern __shared__ uint64_t sk[];
+  uint32_t* sv = reinterpret_cast<uint32_t*>(sk + n_pad);
+  for (int i = threadIdx.x; i < n_pad; i += 1024) {
+    sk[i] = i < n ? keys[i] : ~0ull;      // padding sorts behind every real entry: same key at most, larger index
+    sv[i] = (uint32_t)i;
+  }
+  __syncthreads();
+  for (int k = 2; k <= n_pad; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < (n_pad >> 1); t += 1024) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int l = i | j;
+        const uint64_t ka = sk[i], kb = sk[l];
+        const uint32_t va = sv[i], vb = sv[l];
+        const bool gt = ka > kb || (ka == kb && va > vb);
+        if (gt == ((i & k) == 0)) {
+          sk[i] = kb; sk[l] = ka;
+          sv[i] = vb; sv[l] = va;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < n; i += 1024) {
+    out_k[i] = sk[i];
+    out_v[i] = sv[i];
+  }
+}
+
 __global__ void mark_heads_kernel(const uint64_t* __restrict__ sk, int64_t n, uint32_t* __restrict__ flags) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -306,7 +346,23 @@ extern "C" int nbw_dict_build(nbw_ctx* ctx, const uint64_t* keys, const uint64_t
   const uint64_t* kin = keys;
   const uint32_t* vin = nullptr;
   int cur = 0;
-  for (int shift = 0; shift < key_bits; shift += 8) {
+  const bool small = n_keys <= kSmallSortMax && !getenv("NBW_DICT_RADIX");
+  if (small) {
+    int n_pad = 2;
+    while (n_pad < n_keys) n_pad <<= 1;
+    const size_t smem = (size_t)n_pad * (sizeof(uint64_t) + sizeof(uint32_t));
+    static bool attr = false;
+    if (!attr) {
+      NBW_CUDA(ctx, cudaFuncSetAttribute(small_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kSmallSortMax * (int)(sizeof(uint64_t) + sizeof(uint32_t))));
+      attr = true;
+    }
+    small_sort_kernel<<<1, 1024, smem, st>>>(keys, (int)n_keys, n_pad, kbuf[0], vbuf[0]);
+    NBW_CHECK_LAUNCH(ctx);
+    kin = kbuf[0];
+    vin = vbuf[0];
+  }
+  for (int shift = 0; !small && shift < key_bits; shift += 8) {
     radix_count_kernel<<<n_tiles, kSortThreads, 0, st>>>(kin, n_keys, shift, n_tiles, counts);
     NBW_CHECK_LAUNCH(ctx);
     rc = device_exclusive_scan(ctx, counts, counts, (int64_t)n_counts, stmp, st);

@@ -551,6 +551,25 @@ def test_device_encoded_generation_and_mutation_match_host(eng, family, edits):
     assert np.array_equal(s_dev, s_host) and np.isfinite(s_dev).all()
 
 
+@pytest.mark.parametrize("family", [0, 2])
+def test_small_sort_path_equals_radix_path(eng, family):
+    """The dictionary build sorts up to 8192 keys in one CTA and larger inputs by radix passes: both
+    give the same ids, dictionary and features (and each size class is exercised here)."""
+    import os
+    for n_cells in (1, 7, 500, 1024, 2500):
+        cells = eng.generate_cells(family, 5, 77, n_cells)
+        n_max = 16 if family == 2 else 8
+        a = eng.wl_fit(cells, n_max, 3, False)
+        os.environ["NBW_DICT_RADIX"] = "1"
+        try:
+            b = eng.wl_fit(cells, n_max, 3, False)
+        finally:
+            del os.environ["NBW_DICT_RADIX"]
+        assert a.dims == b.dims and torch.equal(a.ids, b.ids) and torch.equal(a.phi, b.phi)
+        for l in range(4):
+            assert torch.equal(a.uniq_keys[l], b.uniq_keys[l]) and torch.equal(a.uniq_chks[l], b.uniq_chks[l])
+
+
 def _random_dags(rng, n_cells, n_max, n_ops, p_edge, allow_isolated=True):
     """Arbitrary labelled DAGs (not sampler-shaped): random sizes, dense / sparse adjacency,
     isolated nodes, duplicate cells — the edge cases of the WL relabelling rules."""
