@@ -197,7 +197,8 @@ def run_b200(args):
     gp = GraphGP(train, y, [WeisfilerLehman(h=2)])
     fit_ms = bcast_ms = None
     if rank == 0:
-        gp.fit(wl_subtree_candidates=H_GRID, optimize_lik=True, max_lik=0.01)       # warm (first-call costs)
+        gp.fit(wl_subtree_candidates=H_GRID, optimize_lik=True, max_lik=0.01)       # warm (first-call costs:
+        gp._score_state()                                                           #  module loading, allocator)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         gp.reset_XY(train, y)
@@ -344,7 +345,7 @@ def run_b200(args):
                      "kernel_ms": kernel_ms, "bytes_per_unit": SURVEY_BYTES_PER_CANDIDATE,
                      "layout_bytes_per_unit": LAYOUT_BYTES_PER_CANDIDATE,
                      "kernel_share_of_step": kernel_ms / (elapsed_ms / args.steps), "survey_8d": survey_8d,
-                     "note": "not HBM-bound: ncu shows DRAM 0.3 %, issue-active 53-60 % (64-bit integer hashing); see profiles/"},
+                     "note": "not HBM-bound: ncu shows DRAM 0.3 %, issue slots 75 % active (64-bit integer hashing); see profiles/r01f_summary.md"},
         "cpu_baseline": cpu_baseline,
         "e2e": {"value": world * M * e_steps / (e2e_ms / 1e3), "unit": "candidates/s",
                 "h2d_bytes_per_step": M * stride, "d2h_bytes_per_step": M * 4 + TOP_N * 12, "steps": e_steps,
