@@ -249,8 +249,7 @@ def run_b200(args):
         scores, _, _, _ = eng.score_pool(model, cells, M, scores=score_buf)
         if ev is not None:
             ev[1].record()
-        local = eng.topk_device(scores, TOP_N, distinct=True, index_base=first, out=cand_buf)
-        return parallel.allgather_topk_device(eng, local, TOP_N, True, gathered=gather_buf)
+        return parallel.select_topk(eng, scores, TOP_N, True, first, cand_buf, gather_buf)
 
     model = acq._model()
     score_buf = eng.empty((M,), torch.float32)

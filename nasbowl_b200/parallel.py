@@ -95,6 +95,17 @@ def allgather_topk_device(eng, local_cands: torch.Tensor, k: int, distinct: bool
     return eng.topk_merge(gathered, k, distinct)
 
 
+def select_topk(eng, scores: torch.Tensor, k: int, distinct: bool = True, index_base: int = 0,
+                cand_buf: Optional[torch.Tensor] = None, gathered: Optional[torch.Tensor] = None):
+    """Global top-k of the ranks' score shards: (values, global indices) on the host, identical on
+    every rank.  One rank: one tournament + readback (nbw_topk).  Several: local tournament left on the
+    device, one all-gather of k entries per rank, merge (nbw_topk_device / nbw_topk_merge)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return eng.topk(scores, k, distinct=distinct, index_base=index_base)
+    local = eng.topk_device(scores, k, distinct=distinct, index_base=index_base, out=cand_buf)
+    return allgather_topk_device(eng, local, k, distinct, gathered=gathered)
+
+
 def broadcast_pool_model(pm: Optional[PoolModel], src: int = 0, device=None) -> PoolModel:
     """Broadcast the fitted surrogate from `src` to every rank (NCCL: over NVLink)."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
@@ -117,6 +128,5 @@ def propose_location_sharded(acq, pool_shard, index_base: int, top_n: int = 5, r
     acq.iters += 1
     scores, _, _, _ = acq.score_pool(pool_shard)
     eng = acq.gp._dev['eng']
-    local = eng.topk_device(scores, top_n, distinct=bool(return_distinct), index_base=index_base)
-    vals, idx = allgather_topk_device(eng, local, top_n, return_distinct)
+    vals, idx = select_topk(eng, scores, top_n, bool(return_distinct), index_base)
     return vals, idx, scores
