@@ -242,6 +242,14 @@ typedef struct {
   int32_t ld_h;                          /* >= T + 1 */
   const double* H;                       /* [(T+1) x ld_h], row/column T all zero */
   const double* w_mu_prefix;             /* [T+1], entry T = 0 */
+  /* Stable suffix of the WL refinement (optional; first_stable = 0 disables it).  Once the training
+   * dictionary stops refining (D_{l-1} == D_{l-2}, l - 2 >= 1) every deeper parent map is a bijection:
+   * a pool node is in the dictionary at level l >= first_stable iff it and all its successors were at
+   * level l-1, and its label is then child[label_off[l-1] + id_{l-1}] — no signature, no probe.  Label
+   * classes inside the cell (needed for k_cc) are refined exactly from the previous classes. */
+  const int32_t* child;                  /* stacked [T]: level-(l-1) label -> its only level-l label */
+  int32_t first_stable;                  /* levels l >= first_stable (>= 3) take the fast path; 0 = none */
+  int32_t reserved0;
   double lik, y_mean, y_std, incumbent, xi, beta;
 } nbw_model;
 

@@ -137,6 +137,11 @@ __device__ __forceinline__ void finish_candidate(const nbw_model& M, double mu_a
   if (score64) score64[g] = score;
 }
 
+// class-count signature of the stable levels: 4 bits per previous class (a node has fewer than NMAX successors)
+template <int NMAX> struct StableSig;
+template <> struct StableSig<8> { typedef uint32_t type; };
+template <> struct StableSig<16> { typedef uint64_t type; };
+
 struct ScoreParams {
   nbw_model M;
   LevelSalt salt[NBW_MAX_LEVELS];   // per-level hash salts, derived from M.seed on the host
@@ -198,8 +203,44 @@ score_pool_kernel(const ScoreParams P, const uint8_t* __restrict__ cells, int64_
       if (present) kss += M.oa ? 1 : cnt[0];
     }
     // ---- levels 1..h
+    uint32_t dense_prev = 0;   // dictionary id at the previous level (meaningful while in_dict)
 #pragma unroll
     for (int l = 1; l < NL; ++l) {
+      if (l >= 3 && M.first_stable != 0 && l >= M.first_stable) {
+        // Stable suffix (nbw_model.child): the training dictionary no longer refines, so membership
+        // is inherited — this node and all its successors were in the dictionary one level up — and
+        // the label is the only child of the previous one.  The classes inside the cell still refine
+        // (labels outside the dictionary can): exactly, from the multiset of the successors'
+        // previous classes, four bits of count per class.
+        using Sig = typename StableSig<NMAX>::type;
+        const uint32_t word = (in_dict ? 0x80000000u : 0u) | (cls ? (uint32_t)(__ffs(cls) - 1) : 0u);
+        Sig sig = 0;
+        bool all_in = true;
+        uint32_t m = succ;
+#pragma unroll 1
+        for (int t = 0; t < NMAX; ++t) {
+          if (!__any_sync(0xffffffffu, m != 0u)) break;
+          const bool has = m != 0u;
+          const int j = has ? (__ffs(m) - 1) : node;
+          const uint32_t w = __shfl_sync(0xffffffffu, word, sub_base + j);
+          if (has) {
+            sig += (Sig)1 << (4 * (w & 31u));
+            all_in = all_in && (w >> 31);
+          }
+          m &= m - 1u;
+        }
+        const bool seen = endpoint && in_dict && all_in;
+        const uint32_t dense = seen ? (uint32_t)__ldg(M.child + M.label_off[l - 1] + (int)dense_prev) : 0u;
+        in_dict = seen;
+        dense_prev = dense;
+        cls = classes_refine<NMAX>(cls, (uint64_t)sig, endpoint, node, lane, sub_base);
+        cnt[l] = __popc(cls);
+        rk[l] = __popc(cls & ((1u << node) - 1u));
+        if (PREFIX) { if (seen) deep = M.label_off[l] + (int)dense; }
+        else col[l] = endpoint ? effective_column(M, l, seen, dense, rk[l]) : -1;
+        if (endpoint) kss += M.oa ? 1 : cnt[l];
+        continue;
+      }
       const LevelSalt salt = P.salt[l];
       const uint64_t ha = nbw_hash_a(id64, salt);
       const uint32_t hb = nbw_hash_b(id64, salt);
@@ -213,6 +254,7 @@ score_pool_kernel(const ScoreParams P, const uint8_t* __restrict__ cells, int64_
       if (endpoint && in_dict)
         seen = table_probe(static_cast<const uint4*>(M.table[l]), M.table_mask[l], key, chk, dense);
       in_dict = seen;
+      dense_prev = dense;
       id64 = seen ? (uint64_t)dense : (NBW_UNSEEN_BIT | key);
       cls = classes_refine<NMAX>(cls, id64, endpoint, node, lane, sub_base);
       cnt[l] = __popc(cls);
@@ -373,6 +415,8 @@ int check_model(nbw_ctx* ctx, const nbw_model* M, bool need_posterior) {
   }
   NBW_REQUIRE(ctx, !M->oa || (M->thermo_base && M->max_count), "oa model needs thermo_base/max_count");
   NBW_REQUIRE(ctx, M->n_features > 0, "model.n_features must be positive");
+  NBW_REQUIRE(ctx, M->first_stable == 0 || (M->first_stable >= 3 && M->first_stable <= M->h && M->child != nullptr),
+              "model.first_stable must be 0 or in [3, h] with a child table");
   if (need_posterior && !(M->H != nullptr && !M->oa)) {
     NBW_REQUIRE(ctx, M->G && M->w_mu && M->ld_g >= M->n_features + 1, "model.G / w_mu missing or ld_g < n_features + 1");
   }

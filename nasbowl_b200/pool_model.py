@@ -15,7 +15,7 @@ ACQ = {"EI": 0, "AEI": 1, "UCB": 2, "MEAN": 3}
 
 
 class PoolModel:
-    TENSOR_FIELDS = ("level0", "thermo_base", "max_count", "G", "w_mu", "H", "w_mu_prefix")
+    TENSOR_FIELDS = ("level0", "thermo_base", "max_count", "G", "w_mu", "H", "w_mu_prefix", "child")
 
     def __init__(self):
         self.n_max = 8
@@ -35,6 +35,8 @@ class PoolModel:
         self.n_labels = 0
         self.H: Optional[torch.Tensor] = None                # fp64 [T + 1, T + 1] (linear kernel only)
         self.w_mu_prefix: Optional[torch.Tensor] = None      # fp64 [T + 1]
+        self.child: Optional[torch.Tensor] = None            # int32 [T]: label -> its only child label (stable levels)
+        self.first_stable = 0                                # first WL level on the stable fast path (0 = none)
         self.use_prefix = True                               # False forces the general G path
         self.general_builder = None                          # builds (G, w_mu) on demand (fitting rank only)
         self.lik = 0.0
@@ -55,7 +57,31 @@ class PoolModel:
         m.thermo_base, m.max_count = fit.thermo_base, fit.max_count
         m.n_features = fit.k_end(h)
         m.n_labels = fit.label_off[h + 1]
+        m._find_stable_suffix(fit, int(h))
         return m
+
+    def _find_stable_suffix(self, fit, h: int):
+        """Levels whose training dictionary no longer refines (see nbw_model.child): the first level
+        l >= 3 with D_{l-1} == D_{l-2}; WL keeps a stable partition stable, so every deeper level has
+        the same size too (checked; otherwise the fast path stays off)."""
+        import os
+        dims = list(fit.dims[:h + 1])
+        first = 0
+        for l in range(3, h + 1):
+            if dims[l - 1] == dims[l - 2]:
+                first = l
+                break
+        if not first or os.environ.get("NBW_NO_STABLE") or fit.parents is None:
+            return
+        if any(dims[l] != dims[first - 1] for l in range(first, h + 1)):
+            return
+        T = fit.label_off[h + 1]
+        child = torch.zeros((max(T, 1),), dtype=torch.int32, device=fit.parents.device)
+        for l in range(first, h + 1):
+            par = fit.parents[fit.label_off[l]:fit.label_off[l + 1]].long()          # parent of each level-l label
+            z = torch.arange(dims[l], dtype=torch.int32, device=par.device)
+            child[fit.label_off[l - 1] + par] = z
+        self.child, self.first_stable = child, first
 
     # ------------------------------------------------------------------ C descriptor
     def descriptor(self, acq: str = "MEAN", xi: float = 0.0, beta: float = 0.0,
@@ -86,6 +112,8 @@ class PoolModel:
         d.n_labels = self.n_labels
         if prefix:
             d.H, d.ld_h, d.w_mu_prefix = self.H.data_ptr(), self.H.stride(0), self.w_mu_prefix.data_ptr()
+        if self.first_stable and self.child is not None:
+            d.child, d.first_stable = self.child.data_ptr(), int(self.first_stable)
         d.lik, d.y_mean, d.y_std = float(self.lik), float(self.y_mean), float(self.y_std)
         d.incumbent = float(self.incumbent if incumbent is None else incumbent)
         d.xi, d.beta = float(xi), float(beta)
@@ -97,7 +125,7 @@ class PoolModel:
                   for f in self.TENSOR_FIELDS}
         return dict(n_max=self.n_max, h=self.h, oa=self.oa, seed=self.seed, masks=list(self.masks),
                     col_off=list(self.col_off), label_off=list(self.label_off), n_features=self.n_features,
-                    n_labels=self.n_labels,
+                    n_labels=self.n_labels, first_stable=self.first_stable,
                     lik=self.lik, y_mean=self.y_mean, y_std=self.y_std, incumbent=self.incumbent,
                     incumbent_idx=self.incumbent_idx, shapes=shapes,
                     table_sizes=[0 if t is None else int(t.numel()) for t in self.tables])
@@ -110,8 +138,8 @@ class PoolModel:
     @classmethod
     def empty_from_meta(cls, meta: dict, device) -> "PoolModel":
         m = cls()
-        for k in ("n_max", "h", "oa", "seed", "masks", "col_off", "label_off", "n_features", "n_labels", "lik", "y_mean",
-                  "y_std", "incumbent", "incumbent_idx"):
+        for k in ("n_max", "h", "oa", "seed", "masks", "col_off", "label_off", "n_features", "n_labels", "first_stable",
+                  "lik", "y_mean", "y_std", "incumbent", "incumbent_idx"):
             setattr(m, k, meta[k])
         for f, sd in meta["shapes"].items():
             if sd is not None:

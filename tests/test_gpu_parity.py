@@ -642,3 +642,53 @@ def test_cfg1_regression_case():
     if got != ref_top:
         vals = [z["ei"][i] for i in got ^ ref_top]
         assert max(vals) - min(vals) < 1e-4 * max(1.0, abs(max(vals)))
+
+
+@pytest.mark.parametrize("family,h,oa", [(1, 5, False), (1, 5, True), (0, 5, False), (2, 4, False)])
+def test_stable_suffix_fast_path_is_exact(eng, family, h, oa):
+    """When the training dictionary stops refining, deeper WL levels inherit membership and take the
+    child label instead of hashing and probing (nbw_model.child).  Same scores, features and
+    self-similarities as the hashed path, bit for bit, and agreement with the oracle."""
+    import os
+    from nasbowl_b200.bayesopt import GraphExpectedImprovement, GraphGP
+    from nasbowl_b200.kernels import WeisfilerLehman
+    from nasbowl_b200.pool_model import PoolModel
+    train = synth.generate_cells_host(family, 3, 0, 150)
+    y = torch.randn(150, generator=torch.Generator().manual_seed(7))
+    M = 60_000
+    pool = eng.generate_cells(family, 9, 500, M)
+
+    def run(no_stable):
+        if no_stable:
+            os.environ["NBW_NO_STABLE"] = "1"
+        try:
+            gp = GraphGP(train, y, [WeisfilerLehman(h=h, oa=oa)], n_max=train.n_max)
+            gp.fit(wl_subtree_candidates=(h,), optimize_lik=False)
+            pm = gp._score_state()
+            acq = GraphExpectedImprovement(gp)
+            s, mu, var, s64 = acq.score_pool(pool, want64=True)
+            out = [s.clone(), mu.clone(), var.clone()]
+            if not oa:
+                pm.use_prefix = False                       # the general G path through the same levels
+                out.append(acq.score_pool(pool)[0].clone())
+                pm.use_prefix = True
+            fitm = PoolModel.from_fit(eng, gp._dev['fits'][0], h)
+            phi, ss = eng.pool_features(fitm.descriptor(), pool, M)
+            out += [phi.clone(), ss.clone()]
+            return pm.first_stable, gp, out
+        finally:
+            os.environ.pop("NBW_NO_STABLE", None)
+    first, gp, fast = run(False)
+    first_off, _, slow = run(True)
+    assert first_off == 0
+    dims = gp._dev['fits'][0].dims
+    if first == 0:
+        pytest.skip("the dictionary of this training set keeps refining: dims %s" % dims)
+    assert first >= 3 and dims[first - 1] == dims[first - 2]
+    for a, b in zip(fast, slow):
+        assert torch.equal(a, b)
+    sub = CellBatch.from_records(pool[:300].cpu().numpy(), train.n_max)
+    st = gp_oracle.gp_fit(train, y.numpy().astype(np.float64), h_candidates=(h,), oa=oa, optimize_lik=False)
+    mu_o, var_o = gp_oracle.gp_predict_diag(st, train, sub)
+    np.testing.assert_allclose(fast[1][:300].cpu().numpy(), mu_o, rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(fast[2][:300].cpu().numpy(), var_o, rtol=1e-6, atol=1e-12)
