@@ -229,18 +229,6 @@ def run_b200(args):
         pools.append((eng.generate_cells(FAMILY, 1234, first, M), first))
     torch.cuda.synchronize()
 
-    # ---- CPU baseline + parity of the timed path on a bounded sample (rank 0, N=1 only)
-    cpu_baseline, parity = None, None
-    if rank == 0 and world == 1 and not args.skip_cpu:
-        S = args.cpu_sample
-        sample = CellBatch.from_records(pools[0][0][:S].cpu().numpy(), n_max)
-        rate, st, ei_ref, top_ref = cpu_port_rate(train, y, sample)
-        sc, _, _, sc64 = acq.score_pool(pools[0][0][:S].contiguous(), want64=True)
-        err = float(np.max(np.abs(sc64.cpu().numpy() - ei_ref) / (np.abs(ei_ref) + 1e-12)))
-        parity = {"sample": S, "max_rel_err_ei_fp64": err, "h_star_equal": bool(st.h == h_star)}
-        cpu_baseline = {"value": rate, "unit": "candidates/s", "cores": blas_threads(), "kind": "port",
-                        "sample": "first %d candidates of pool 0 (oracle/gp_oracle.py: joint WL + fp64 GP + EI + top-5)" % S}
-
     def step(i, ev=None):
         cells, first = pools[i % ROTATING_POOLS]
         acq.iters += 1
@@ -285,7 +273,9 @@ def run_b200(args):
         # host records in, top-5 indices + all EIs (host numpy) out
         xs, eis, idx = acq.propose_location(host_pool, top_n=TOP_N)
         return idx
-    for _ in range(max(3, args.warmup)):
+    # (the clock sampler's shutdown above idles the GPU for ~0.15 s: warm up long enough to ramp clocks
+    # and the PCIe link again before timing)
+    for _ in range(5 * max(3, args.warmup)):
         e2e_step()
     if world > 1:
         dist.barrier()
@@ -296,6 +286,20 @@ def run_b200(args):
         e2e_step()
     torch.cuda.synchronize()
     e2e_ms = 1e3 * (time.perf_counter() - t0)
+
+    # ---- CPU baseline + parity of the timed path on a bounded sample (rank 0, N=1 only).  Runs AFTER the GPU
+    # measurements: its BLAS worker threads keep spinning for a while and would slow the per-step host
+    # work (launch, top-5 readback) of the timed loops — the e2e figure dropped by up to 35 % when it ran first.
+    cpu_baseline, parity = None, None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        S = args.cpu_sample
+        sample = CellBatch.from_records(pools[0][0][:S].cpu().numpy(), n_max)
+        rate, st, ei_ref, top_ref = cpu_port_rate(train, y, sample)
+        sc, _, _, sc64 = acq.score_pool(pools[0][0][:S].contiguous(), want64=True)
+        err = float(np.max(np.abs(sc64.cpu().numpy() - ei_ref) / (np.abs(ei_ref) + 1e-12)))
+        parity = {"sample": S, "max_rel_err_ei_fp64": err, "h_star_equal": bool(st.h == h_star)}
+        cpu_baseline = {"value": rate, "unit": "candidates/s", "cores": blas_threads(), "kind": "port",
+                        "sample": "first %d candidates of pool 0 (oracle/gp_oracle.py: joint WL + fp64 GP + EI + top-5)" % S}
 
     # ---- max over ranks
     if world > 1:

@@ -217,16 +217,24 @@ score_pool_kernel(const ScoreParams P, const uint8_t* __restrict__ cells, int64_
         Sig sig = 0;
         bool all_in = true;
         uint32_t m = succ;
+        constexpr int kUnrolled = NMAX == 8 ? 2 : 4;      // as in successor_sums: most nodes have few successors
+#pragma unroll
+        for (int t = 0; t < kUnrolled; ++t) {
+          const bool has = m != 0u;
+          const int j = has ? (__ffs(m) - 1) : node;
+          const uint32_t w = __shfl_sync(0xffffffffu, word, sub_base + j);
+          sig += has ? ((Sig)1 << (4 * (w & 31u))) : (Sig)0;
+          all_in = all_in && (!has || (w >> 31));
+          m &= m - 1u;
+        }
 #pragma unroll 1
-        for (int t = 0; t < NMAX; ++t) {
+        for (int t = kUnrolled; t < NMAX; ++t) {
           if (!__any_sync(0xffffffffu, m != 0u)) break;
           const bool has = m != 0u;
           const int j = has ? (__ffs(m) - 1) : node;
           const uint32_t w = __shfl_sync(0xffffffffu, word, sub_base + j);
-          if (has) {
-            sig += (Sig)1 << (4 * (w & 31u));
-            all_in = all_in && (w >> 31);
-          }
+          sig += has ? ((Sig)1 << (4 * (w & 31u))) : (Sig)0;
+          all_in = all_in && (!has || (w >> 31));
           m &= m - 1u;
         }
         const bool seen = endpoint && in_dict && all_in;
