@@ -35,6 +35,7 @@ extern "C" int nbw_create(nbw_ctx** out, int device) {
 extern "C" int nbw_destroy(nbw_ctx* ctx) {
   if (!ctx) return NBW_OK;
   if (ctx->scratch) cudaFree(ctx->scratch);
+  if (ctx->pinned_small) cudaFreeHost(ctx->pinned_small);
   if (ctx->pipe_ready) {
     cudaStreamDestroy(ctx->s_in);
     cudaStreamDestroy(ctx->s_out);

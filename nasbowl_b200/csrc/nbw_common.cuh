@@ -24,6 +24,7 @@ struct nbw_ctx {
   void* stage[2];
   size_t stage_bytes;
   int pipe_ready;
+  void* pinned_small;   // 16 KB of pinned host memory for small synchronous read-backs (top-k lists)
 };
 
 // Host scores written by the side stream are complete once this returns (called by every syncing

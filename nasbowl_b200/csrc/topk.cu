@@ -144,15 +144,13 @@ static int topk_enqueue(nbw_ctx* ctx, const float* scores, const Cand* cands, in
 
 static int topk_readback(nbw_ctx* ctx, const Cand* dev, int k, float* top_val_h, int64_t* top_idx_h, int* n_found_h,
                          cudaStream_t st) {
-  Cand* host = static_cast<Cand*>(malloc(sizeof(Cand) * k));
-  if (!host) NBW_FAIL(ctx, NBW_ERR_INVALID, "host allocation failed");
-  cudaError_t e = cudaMemcpyAsync(host, dev, sizeof(Cand) * k, cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  if (e == cudaSuccess) e = nbw_await_host_scores(ctx);   // D2H of host scores runs beside the selection
-  if (e != cudaSuccess) {
-    free(host);
-    NBW_FAIL(ctx, NBW_ERR_CUDA, "top-k readback failed: %s", cudaGetErrorString(e));
-  }
+  // k <= 1024 entries of 16 bytes: read back through a pinned block owned by the context (a pageable
+  // destination makes the driver stage the copy and costs several microseconds per pool)
+  if (!ctx->pinned_small) NBW_CUDA(ctx, cudaHostAlloc(&ctx->pinned_small, sizeof(Cand) * 1024, cudaHostAllocDefault));
+  Cand* host = static_cast<Cand*>(ctx->pinned_small);
+  NBW_CUDA(ctx, cudaMemcpyAsync(host, dev, sizeof(Cand) * k, cudaMemcpyDeviceToHost, st));
+  NBW_CUDA(ctx, cudaStreamSynchronize(st));
+  NBW_CUDA(ctx, nbw_await_host_scores(ctx));   // D2H of host scores runs beside the selection
   int found = 0;
   for (int i = 0; i < k; ++i) {
     if (host[i].idx < 0) break;
@@ -160,7 +158,6 @@ static int topk_readback(nbw_ctx* ctx, const Cand* dev, int k, float* top_val_h,
     top_idx_h[found] = host[i].idx;
     ++found;
   }
-  free(host);
   *n_found_h = found;
   return NBW_OK;
 }
