@@ -464,3 +464,73 @@ def test_oracle_invariants_on_random_cells():
         # the two restatements of the relabelling agree
         assert np.array_equal(wl_oracle.gram_raw(batch, 3, oa, fast=False), Ksum)
     prop()
+
+
+def test_weight_gradient_closed_form_matches_finite_differences():
+    """The closed form the oracle (and nbw_kernel_weight_grad) uses for d nlml'/d w_i of
+    K = normalise(sum_i w_i R_i) + lik I, against central differences of the reference's
+    marginal-likelihood formula (utils.py:102-140, incl. the sign of its log-det term)."""
+    from oracle import gp_oracle
+    rng = np.random.RandomState(3)
+    n, m = 25, 3
+    raws = []
+    for _ in range(m):
+        F = rng.randint(0, 4, size=(n, 12)).astype(np.float64)
+        raws.append(F @ F.T + np.eye(n))                      # integer Grams with a positive diagonal
+    y = rng.randn(n)
+    w = np.array([0.2, 0.5, 0.3])
+    lik = 0.01
+
+    def nlml(wv):
+        K = gp_oracle.normalize_gram(sum(wv[i] * raws[i] for i in range(m)))
+        K_i, ld, _ = gp_oracle.pd_inverse(K, lik)
+        return gp_oracle.nlml_prime(K_i, ld, y)
+    S = sum(w[i] * raws[i] for i in range(m))
+    K_i, _, _ = gp_oracle.pd_inverse(gp_oracle.normalize_gram(S), lik)
+    g = gp_oracle.weight_gradient(K_i, K_i @ y, S, raws, n)
+    for i in range(m):
+        e = np.zeros(m)
+        e[i] = 1e-6
+        fd = (nlml(w + e) - nlml(w - e)) / 2e-6
+        assert abs(fd - g[i]) < 1e-6 * max(1.0, abs(fd)), (i, fd, g[i])
+
+
+def test_stable_suffix_detection_and_child_table():
+    """PoolModel._find_stable_suffix: the first level l >= 3 with D_{l-1} == D_{l-2}, only if every deeper
+    level keeps that size; child[parent] = label for the levels on the fast path."""
+    from types import SimpleNamespace
+    from nasbowl_b200.pool_model import PoolModel
+
+    def fake(dims, perms):
+        off = [0]
+        for d in dims:
+            off.append(off[-1] + d)
+        parents = torch.zeros(off[-1], dtype=torch.int32)
+        for l, p in perms.items():
+            parents[off[l]:off[l + 1]] = torch.tensor(p, dtype=torch.int32)
+        return SimpleNamespace(dims=dims, label_off=off, parents=parents)
+    # levels 2, 3, 4 have four labels each: level 4 is the first with D_3 == D_2
+    fit = fake([3, 3, 4, 4, 4], {3: [2, 0, 3, 1], 4: [1, 3, 0, 2]})
+    pm = PoolModel()
+    pm._find_stable_suffix(fit, 4)
+    assert pm.first_stable == 4
+    child = pm.child.tolist()
+    off = fit.label_off
+    for z, par in enumerate([1, 3, 0, 2]):                    # label z of level 4 has parent `par` at level 3
+        assert child[off[3] + par] == z
+    # depth 3 only: level 3 needs D_2 == D_1 (4 vs 4 here -> stable from 3)
+    pm = PoolModel()
+    pm._find_stable_suffix(fake([3, 4, 4, 4], {3: [2, 0, 3, 1]}), 3)
+    assert pm.first_stable == 3 and pm.child.tolist()[3 + 4 + 2] == 0        # D_2 == D_1: level 3 already stable
+    # still refining, or too shallow: off
+    for dims in ([3, 5, 9, 12, 14], [3, 4, 4], [3, 4, 6, 6]):
+        pm = PoolModel()
+        pm._find_stable_suffix(fake(dims, {}), len(dims) - 1)
+        assert pm.first_stable == 0 and pm.child is None
+    os.environ["NBW_NO_STABLE"] = "1"
+    try:
+        pm = PoolModel()
+        pm._find_stable_suffix(fit, 4)
+        assert pm.first_stable == 0
+    finally:
+        del os.environ["NBW_NO_STABLE"]
