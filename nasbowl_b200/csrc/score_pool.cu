@@ -204,9 +204,25 @@ score_pool_kernel(const ScoreParams P, const uint8_t* __restrict__ cells, int64_
     }
     // ---- levels 1..h
     uint32_t dense_prev = 0;   // dictionary id at the previous level (meaningful while in_dict)
+    bool settled = false;      // warp-uniform: a stable level changed neither classes nor membership
 #pragma unroll
     for (int l = 1; l < NL; ++l) {
       if (l >= 3 && M.first_stable != 0 && l >= M.first_stable) {
+        if (settled) {
+          // Every stable level applies the same map to (classes, membership); it reproduced its input
+          // for all cells of this warp, so it will again: only the labels move down the child chain.
+          const bool seen = in_dict;
+          const uint32_t dense = seen ? (uint32_t)__ldg(M.child + M.label_off[l - 1] + (int)dense_prev) : 0u;
+          dense_prev = dense;
+          cnt[l] = cnt[l - 1];
+          rk[l] = rk[l - 1];
+          if (PREFIX) { if (seen) deep = M.label_off[l] + (int)dense; }
+          else col[l] = endpoint ? effective_column(M, l, seen, dense, rk[l]) : -1;
+          if (endpoint) kss += M.oa ? 1 : cnt[l];
+          continue;
+        }
+        const uint32_t cls_in = cls;
+        const bool dict_in = in_dict;
         // Stable suffix (nbw_model.child): the training dictionary no longer refines, so membership
         // is inherited — this node and all its successors were in the dictionary one level up — and
         // the label is the only child of the previous one.  The classes inside the cell still refine
@@ -242,6 +258,7 @@ score_pool_kernel(const ScoreParams P, const uint8_t* __restrict__ cells, int64_
         in_dict = seen;
         dense_prev = dense;
         cls = classes_refine<NMAX>(cls, (uint64_t)sig, endpoint, node, lane, sub_base);
+        settled = !__any_sync(0xffffffffu, cls != cls_in || in_dict != dict_in);
         cnt[l] = __popc(cls);
         rk[l] = __popc(cls & ((1u << node) - 1u));
         if (PREFIX) { if (seen) deep = M.label_off[l] + (int)dense; }
