@@ -2,7 +2,7 @@
 
 Only usable in the build container (the reference tree does not travel to the GPU box).
 Used by oracle/make_golden.py to generate tests/golden/*.npz and by the optional
-`tests/test_oracle_vs_reference.py` differential tests (skipped when the tree is absent).
+`tests/test_oracle_vs_reference.py` differential tests on fresh seeds (skipped when the tree is absent).
 """
 import collections
 import collections.abc
