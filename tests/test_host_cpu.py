@@ -534,3 +534,28 @@ def test_stable_suffix_detection_and_child_table():
         assert pm.first_stable == 0
     finally:
         del os.environ["NBW_NO_STABLE"]
+
+
+def test_dmu_dphi_closed_form_matches_finite_differences():
+    """gp_oracle.dmu_dphi (the closed form GraphGP.dmu_dphi evaluates) against central differences of
+    mu(phi*) = sum_i alpha_i (phi* . x_i) / (|phi*| |x_i|)."""
+    from oracle import gp_oracle
+    rng = np.random.RandomState(5)
+    n, D = 12, 9
+    X = rng.randint(0, 4, size=(n, D)).astype(np.float64) + np.eye(n, D)
+    Y = rng.randint(0, 3, size=(4, D)).astype(np.float64) + 1.0
+    A = rng.randn(n, n)
+    st = gp_oracle.GPState(h=0, oa=False, lik=0.01, y_mean=0.0, y_std=1.0, y_norm=rng.randn(n), y_raw=None,
+                           K=None, K_i=A @ A.T / n + np.eye(n), logDetK=0.0, L=None, diag_raw=None)
+    alpha = st.K_i @ st.y_norm
+    nx_ = np.sqrt((X * X).sum(1))
+
+    def mu(yv):
+        return float(alpha @ ((X @ yv) / (np.sqrt(yv @ yv) * nx_)))
+    g = gp_oracle.dmu_dphi(st, X, Y)
+    for j in range(Y.shape[0]):
+        for c in range(D):
+            e = np.zeros(D)
+            e[c] = 1e-6
+            fd = (mu(Y[j] + e) - mu(Y[j] - e)) / 2e-6
+            assert abs(fd - g[j, c]) < 1e-7, (j, c, fd, g[j, c])
