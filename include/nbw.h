@@ -50,6 +50,14 @@ int nbw_create(nbw_ctx** out, int device);
 int nbw_destroy(nbw_ctx* ctx);
 const char* nbw_last_error(const nbw_ctx* ctx);
 int nbw_reserve(nbw_ctx* ctx, uint64_t scratch_bytes);
+/* NVTX range markers for the host layer (no reference counterpart; SURVEY.md §5 tracing row): the ranges
+ * "fit", "score_state", "broadcast", "propose_location" bracket the kernels in an Nsight timeline. */
+int nbw_range_push(const char* name);
+int nbw_range_pop(void);
+/* Measurement hook: two caller-owned cudaEvent_t (NULL, NULL to clear) that the next scoring entry point records
+ * on its stream immediately before and after the SCORING KERNEL launch (not the small top-n merge behind it):
+ * bench.py's per-launch kernel duration "measured live with CUDA events on the launching stream". */
+int nbw_profile_events(nbw_ctx* ctx, void* ev_start, void* ev_stop);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t nbw_launch_count(const nbw_ctx* ctx);
 
@@ -121,6 +129,24 @@ int nbw_oa_thermo_layout(nbw_ctx* ctx, const uint32_t* ids, int64_t n_cells, int
 int nbw_gram_i8(nbw_ctx* ctx, const int8_t* A, int64_t m, int64_t lda, const int8_t* B,
                 int64_t n, int64_t ldb, int64_t k0, int64_t k1, int32_t* C, int64_t ldc,
                 int impl, void* stream);
+
+/* The same product with the epilogue chosen per launch and a symmetric tile schedule (the Gram of a batch with
+ * itself, vertex_histogram.py:243: K = Phi Phi^T is symmetric, computing both triangles doubles the work).
+ *   out_mode    what leaves TMEM: s32 (C int32), u8 / s16 with saturation (*overflow |= 1 when a value did not
+ *               fit: entries of NAS-cell Grams are <= (h+1) n_max^2), or fp32 K_ij * scale_a[i] * scale_b[j] — the
+ *               cosine normalisation of kernels/combine_kernels.py:54-56 with scale = 1/sqrt(K_ii) fused in.
+ *   upper_only  A = rows [row_offset, row_offset + m) of the matrix whose rows are B: 256 x 256 tiles that lie
+ *               strictly below the diagonal of the global matrix are neither computed nor written;
+ *               nbw_sym_mirror fills them from their mirror images afterwards (or the consumer uses symmetry).
+ * ldc counts elements of the output type.  Always the CTA-pair tcgen05 kernel. */
+typedef enum { NBW_GRAM_S32 = 0, NBW_GRAM_U8 = 1, NBW_GRAM_S16 = 2, NBW_GRAM_F32_NORM = 3 } nbw_gram_out;
+int nbw_gram_i8_ex(nbw_ctx* ctx, const int8_t* A, int64_t m, int64_t lda, const int8_t* B, int64_t n,
+                   int64_t ldb, int64_t k0, int64_t k1, void* C, int64_t ldc, int out_mode,
+                   int upper_only, int64_t row_offset, const float* scale_a, const float* scale_b,
+                   uint32_t* overflow, void* stream);
+/* C[i][j] = C[j][i] for all i > j of a square matrix [n x ldc] of 1-, 2- or 4-byte elements (the lower
+ * triangle of a symmetric Gram computed with upper_only; vertex_histogram.py:243). */
+int nbw_sym_mirror(nbw_ctx* ctx, void* C, int64_t n, int64_t ldc, int elem_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * (5) GP linear algebra in fp64 — replaces kernels/combine_kernels.py:36-56 (weighted sum +
@@ -251,7 +277,31 @@ typedef struct {
   int32_t first_stable;                  /* levels l >= first_stable (>= 3) take the fast path; 0 = none */
   int32_t reserved0;
   double lik, y_mean, y_std, incumbent, xi, beta;
+  /* ---- packed scoring path (csrc/score_packed.cu; optional: bucket_tags[1] == NULL keeps the first-generation
+   * kernel).  Same dictionaries in a branch-free form:
+   *   id_hash[l]        [D_{l-1}] 16-byte entries {u64 ha; u32 hb; u32 0}: the per-node hashes of every level-(l-1)
+   *                     dictionary id salted for level l (nbw_model_build_id_hash) — pool nodes FETCH them;
+   *   bucket_tags[l]    [n_buckets] 16-byte buckets of four 32-bit tags (low word of the key, 0 = empty);
+   *   bucket_entries[l] [4 * n_buckets] 16-byte entries {u32 key_hi; u32 chk; u32 id; u32 0} (nbw_model_build_buckets);
+   *   final_label       stacked [T]: a label of a stable level -> GLOBAL stacked index of its descendant at level h.
+   * Sum of kernels (kernels/combine_kernels.py:36-56): the parts of the sum form a chain through `next`
+   * (HOST pointer, NULL = last).  A candidate is `rec_stride` bytes (0 = one record); part p reads its cell
+   * record at byte `rec_offset` of it ("normal | reduce": two records per candidate).  H / w_mu_prefix /
+   * n_labels / ld_h and the scalars are taken from the FIRST part and span the stacked labels of all
+   * parts; label_base is the first stacked index of this part.  level_weight[l] = kernel weight x WL layer
+   * weight of level l (weisfeiler_lehman.py:316-327); weighted == 0 promises they are all 1 (k_cc stays an
+   * integer).  undirected != 0 symmetrises the adjacency in the kernel (kernels/weisfilerlehman.py:127-128). */
+  const void* id_hash[NBW_MAX_LEVELS];
+  const void* bucket_tags[NBW_MAX_LEVELS];
+  const void* bucket_entries[NBW_MAX_LEVELS];
+  uint32_t bucket_mask[NBW_MAX_LEVELS];  /* n_buckets - 1 (power of two) */
+  const int32_t* final_label;
+  double level_weight[NBW_MAX_LEVELS];
+  int32_t weighted, undirected, rec_offset, rec_stride, label_base, reserved1;
+  const void* next;                      /* const nbw_model* of the next part (host memory) */
 } nbw_model;
+
+#define NBW_MAX_PARTS 4                  /* kernels in a sum the fused pool path accepts */
 
 /* Build one level's lookup table from the sorted dictionary of nbw_dict_build — the device form of
  * self._inv_labels[i], which WeisfeilerLehman.transform consults per node (weisfeiler_lehman.py:434-466).
@@ -259,10 +309,31 @@ typedef struct {
 int nbw_model_build_table(nbw_ctx* ctx, const uint64_t* uniq_keys, const uint64_t* uniq_chks,
                           int64_t n_unique, void* table, int64_t capacity, void* stream);
 
+/* Packed-path dictionary forms (see nbw_model): replace self._inv_labels[i] lookups of
+ * WeisfeilerLehman.transform (weisfeiler_lehman.py:434-466).
+ * nbw_model_build_id_hash: out[d] = hashes of dictionary id d (d < n_ids) salted for `level` (>= 1).
+ * nbw_model_build_buckets: four-entry buckets over the sorted dictionary of nbw_dict_build; n_buckets a
+ * power of two.  *flags (device u32, caller zeroes) gets bit 0 when a bucket overflows and bit 1 when two
+ * keys of one bucket share a tag: the caller rebuilds with more buckets.  Both enqueue only. */
+int nbw_model_build_id_hash(nbw_ctx* ctx, int64_t n_ids, uint64_t seed, int level, void* out, void* stream);
+int nbw_model_build_buckets(nbw_ctx* ctx, const uint64_t* uniq_keys, const uint64_t* uniq_chks,
+                            int64_t n_unique, void* tags, void* entries, int64_t n_buckets,
+                            uint32_t* flags, void* stream);
+
 /* GraphGP.predict (bayesopt/gp.py:240-283, diagonal) + acquisition eval (acquisitions.py:59-80,130-138)
  * over the pool.  scores: [M] f32 (required).  mu64/var64/score64: optional [M] f64 outputs (NULL to skip). */
 int nbw_score_pool(nbw_ctx* ctx, const nbw_model* model_h, const void* cells, int64_t n_cells,
                    float* scores, double* mu64, double* var64, double* score64, void* stream);
+
+/* nbw_score_pool fused with the local top-n selection of propose_location (acquisitions.py:94-113):
+ * every lane keeps the k best (distinct) scores it produced, CTAs merge them at kernel end, one small
+ * tournament merges the per-CTA lists.  out_cands: k 16-byte entries {f32 value; i32 pad; i64 index}
+ * (index_base added; -1 = empty) left on the device — what a rank contributes to the top-n all-gather.
+ * k <= 8 and the packed path only (NBW_ERR_UNSUPPORTED otherwise: use nbw_score_pool + nbw_topk_device).
+ * scores may be NULL when only the selection is wanted.  Enqueues only. */
+int nbw_score_pool_topk(nbw_ctx* ctx, const nbw_model* model_h, const void* cells, int64_t n_cells,
+                        float* scores, int k, int distinct, int64_t index_base, void* out_cands,
+                        void* stream);
 
 /* Host-buffer form of nbw_score_pool — the call a host-side plugin makes from propose_location
  * (bayesopt/acquisitions.py:94-113), which receives its candidates in host memory: `cells_h` are packed
@@ -320,6 +391,19 @@ int nbw_topk_device(nbw_ctx* ctx, const float* scores, int64_t n, int k, int dis
  * same distinct-by-value rule, ties to the lowest index.  Syncs. */
 int nbw_topk_merge(nbw_ctx* ctx, const void* cands, int64_t count, int k, int distinct,
                    float* top_val_h, int64_t* top_idx_h, int* n_found_h, void* stream);
+
+/* Read a k-entry device list (nbw_topk_device / nbw_score_pool_topk / nbw_propose_host) back to the host:
+ * the indices propose_location returns (acquisitions.py:105-113).  Syncs, and awaits pending host scores. */
+int nbw_cands_read(nbw_ctx* ctx, const void* cands, int k, float* top_val_h, int64_t* top_idx_h,
+                   int* n_found_h, void* stream);
+
+/* propose_location (bayesopt/acquisitions.py:94-113) on a pool in HOST memory in one call: the staged
+ * (mapped == 0, nbw_score_pool_host) or mapped (nbw_score_pool_mapped) pipeline with the local top-n of
+ * every piece fused into its scoring kernel and merged on the device: out_cands as for
+ * nbw_score_pool_topk.  k <= 8, packed path only.  Enqueues only; same host-score semantics. */
+int nbw_propose_host(nbw_ctx* ctx, const nbw_model* model_h, const void* cells_h, int64_t n_cells,
+                     float* scores_h, float* scores_dev, int mapped, int pieces, int k, int distinct,
+                     int64_t index_base, void* out_cands, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Synthetic pools shaped like the reference's samplers, generated on device

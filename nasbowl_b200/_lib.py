@@ -12,9 +12,10 @@ LIB_PATH = os.path.join(_HERE, "libnbw.so")
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 SOURCES = ["nbw_api.cu", "wl_relabel.cu", "dict_build.cu", "histogram.cu", "gram_i8.cu",
-           "linalg_f64.cu", "score_pool.cu", "topk.cu", "cellgen.cu"]
+           "linalg_f64.cu", "score_pool.cu", "score_packed.cu", "topk.cu", "cellgen.cu"]
 
 NBW_MAX_LEVELS = 8
+NBW_MAX_PARTS = 4
 INVALID_ID = 0xFFFFFFFF
 
 STATUS = {0: "OK", 1: "INVALID", 2: "CUDA", 3: "NOT_PD", 4: "HASH_COLLISION", 5: "CAPACITY",
@@ -54,6 +55,16 @@ class Model(C.Structure):
         ("child", C.c_void_p), ("first_stable", C.c_int32), ("reserved0", C.c_int32),
         ("lik", C.c_double), ("y_mean", C.c_double), ("y_std", C.c_double),
         ("incumbent", C.c_double), ("xi", C.c_double), ("beta", C.c_double),
+        # packed scoring path (csrc/score_packed.cu)
+        ("id_hash", C.c_void_p * NBW_MAX_LEVELS),
+        ("bucket_tags", C.c_void_p * NBW_MAX_LEVELS),
+        ("bucket_entries", C.c_void_p * NBW_MAX_LEVELS),
+        ("bucket_mask", C.c_uint32 * NBW_MAX_LEVELS),
+        ("final_label", C.c_void_p),
+        ("level_weight", C.c_double * NBW_MAX_LEVELS),
+        ("weighted", C.c_int32), ("undirected", C.c_int32), ("rec_offset", C.c_int32),
+        ("rec_stride", C.c_int32), ("label_base", C.c_int32), ("reserved1", C.c_int32),
+        ("next", C.c_void_p),
     ]
 
 
@@ -65,6 +76,9 @@ _PROTOTYPES = {
     "nbw_last_error": (C.c_char_p, [_vp]),
     "nbw_reserve": (C.c_int, [_vp, _u64]),
     "nbw_launch_count": (C.c_uint64, [_vp]),
+    "nbw_profile_events": (C.c_int, [_vp, _vp, _vp]),
+    "nbw_range_push": (C.c_int, [C.c_char_p]),
+    "nbw_range_pop": (C.c_int, []),
     "nbw_wl_signatures": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _i32, _u64, _vp, _vp, _vp]),
     "nbw_dict_build": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i64,
                                  C.POINTER(_i64), _vp]),
@@ -73,6 +87,9 @@ _PROTOTYPES = {
     "nbw_oa_thermo_layout": (C.c_int, [_vp, _vp, _i64, _i32, _i32, C.POINTER(_i64), _vp, _vp,
                                        C.POINTER(_i64), _vp]),
     "nbw_gram_i8": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _i32, _vp]),
+    "nbw_gram_i8_ex": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _i32, _i32, _i64, _vp, _vp,
+                                 _vp, _vp]),
+    "nbw_sym_mirror": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _vp]),
     "nbw_gram_accumulate": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _f64, _f64, _vp, _i64, _vp]),
     "nbw_axpby_f64": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _f64, _f64, _vp, _i64, _vp]),
     "nbw_gram_normalize": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
@@ -90,13 +107,18 @@ _PROTOTYPES = {
                                       _i64, _vp]),
     "nbw_posterior_cov_finish": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _f64, _f64, _vp, _i64, _vp]),
     "nbw_model_build_table": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i64, _vp]),
+    "nbw_model_build_id_hash": (C.c_int, [_vp, _i64, _u64, _i32, _vp, _vp]),
+    "nbw_model_build_buckets": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp]),
     "nbw_score_pool": (C.c_int, [_vp, C.POINTER(Model), _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "nbw_score_pool_topk": (C.c_int, [_vp, C.POINTER(Model), _vp, _i64, _vp, _i32, _i32, _i64, _vp, _vp]),
     "nbw_score_pool_host": (C.c_int, [_vp, C.POINTER(Model), _vp, _i64, _vp, _vp, _i32, _vp]),
     "nbw_score_pool_mapped": (C.c_int, [_vp, C.POINTER(Model), _vp, _i64, _vp, _vp, _i32, _vp]),
     "nbw_wait_host_scores": (C.c_int, [_vp]),
     "nbw_pool_features": (C.c_int, [_vp, C.POINTER(Model), _vp, _i64, _vp, _i64, _vp, _vp]),
     "nbw_topk": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i64, C.POINTER(C.c_float), C.POINTER(_i64),
                            C.POINTER(_i32), _vp]),
+    "nbw_cands_read": (C.c_int, [_vp, _vp, _i32, C.POINTER(C.c_float), C.POINTER(_i64), C.POINTER(_i32), _vp]),
+    "nbw_propose_host": (C.c_int, [_vp, C.POINTER(Model), _vp, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _i64, _vp, _vp]),
     "nbw_topk_device": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i64, _vp, _vp]),
     "nbw_topk_merge": (C.c_int, [_vp, _vp, _i64, _i32, _i32, C.POINTER(C.c_float), C.POINTER(_i64),
                                  C.POINTER(_i32), _vp]),
@@ -112,7 +134,7 @@ _lib = None
 
 def nvcc_command(out_path: str = LIB_PATH):
     return ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-            "-shared", "-Xcompiler", "-fPIC", "-I" + INCLUDE, "-I" + CSRC, "-o", out_path] + \
+            "--threads", str(min(len(SOURCES), os.cpu_count() or 1)), "-shared", "-Xcompiler", "-fPIC", "-I" + INCLUDE, "-I" + CSRC, "-o", out_path] + \
            [os.path.join(CSRC, s) for s in SOURCES]
 
 

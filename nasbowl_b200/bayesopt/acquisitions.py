@@ -13,7 +13,7 @@ from abc import ABC
 import numpy as np
 import torch
 
-from ..cells import CellBatch
+from ..cells import CellBatch, CellSlots
 
 
 class BaseAcquisition(ABC):
@@ -63,13 +63,14 @@ class GraphExpectedImprovement(BaseAcquisition):
 
     def score_pool(self, candidates, want64=False):
         """Acquisition values of a whole pool: (scores f32 device tensor [M], mu, var, score64)."""
-        cells, M = self.gp.upload_pool(candidates)
+        cells, M = self.gp.upload_pool(candidates)      # (may re-derive the device state for wider cells)
         eng = self.gp._dev['eng']
         return eng.score_pool(self._model(), cells, M, want64=want64)
 
     # -- reference API --------------------------------------------------------------------
     def eval(self, x, asscalar=False):
-        single = not isinstance(x, (list, tuple, CellBatch))
+        single = not isinstance(x, (list, tuple, CellBatch, CellSlots)) or \
+            (isinstance(x, tuple) and len(x) > 0 and hasattr(x[0], 'nodes'))     # one multi-slot example
         try:
             _, _, _, sc = self.score_pool([x] if single else x, want64=True)
         except Exception:
@@ -82,24 +83,53 @@ class GraphExpectedImprovement(BaseAcquisition):
         return ei
 
     def propose_location(self, candidates, top_n=5, return_distinct=True):
-        """top_n: return the top n candidates wrt the acquisition function (acquisitions.py:94-113)."""
+        """top_n: return the top n candidates wrt the acquisition function (acquisitions.py:94-113).
+        One fused launch scores the pool and keeps the local top-n (nbw_score_pool_topk / nbw_propose_host);
+        sums of kernels, oa kernels on the general path or top_n > 8 fall back to score + tournament."""
         self.iters += 1
+        self.gp._require_fit()
+        model = self._model()
         eng = self.gp._dev['eng']
-        host_scores = None
+        eng.lib.nbw_range_push(b"propose_location")
+        try:
+            return self._propose(eng, model, candidates, top_n, return_distinct)
+        finally:
+            eng.lib.nbw_range_pop()
+
+    def _host_policy(self, model, candidates):
+        """(mapped, pieces) for a pool of packed records in host memory: the staged H2D / kernel / D2H
+        pipeline, unless the pool is pinned AND the kernel is clearly slower than the PCIe transfer of its
+        records — then the kernel reads them itself (nbw_score_pool_mapped).  Measured per 1M candidates
+        (profiles/r01_e2e_probe*.txt, first-generation kernel): 16-byte records at h = 5: mapped 0.57 ms vs
+        staged 0.61; at h = 2: 0.54 vs 0.46; 48-byte records at h = 2: 1.96 vs 1.10.  The packed kernel is
+        faster than the transfer of its records everywhere measured, so only oa models (general path)
+        still take the mapped form."""
+        if candidates.is_pinned() and model.oa and model.n_max == 8 and model.h >= 5:
+            return True, 1
+        return False, 8
+
+    def _propose(self, eng, model, candidates, top_n, return_distinct):
+        host_scores = scores = None
+        distinct = bool(return_distinct)
+        fused = eng.fused_topk_ok(model, top_n)
         if isinstance(candidates, torch.Tensor) and not candidates.is_cuda:
-            # packed records in host memory: the staged H2D / kernel / D2H pipeline, unless the pool is
-            # pinned AND the kernel is clearly slower than the PCIe transfer of its records — then the
-            # kernel reads them itself (nbw_score_pool_mapped).  Measured per 1M candidates
-            # (profiles/r01_e2e_probe*.txt): 16-byte records at h = 5: mapped 0.57 ms vs staged 0.61;
-            # 16-byte records at h = 2: 0.54 vs 0.46; 48-byte records at h = 2: 1.96 vs 1.10.
-            model = self._model()
-            if candidates.is_pinned() and model.n_max == 8 and model.h >= 5:
-                scores, host_scores = eng.score_host_pool(model, candidates, chunks=1, mapped=True)
+            mapped, pieces = self._host_policy(model, candidates)
+            if fused:
+                cands, host_scores = eng.propose_host(model, candidates, top_n, distinct, chunks=pieces, mapped=mapped)
+                scores = eng._host_state["scores"]
+                vals, indices = eng.cands_read(cands, top_n)                             # syncs
             else:
-                scores, host_scores = eng.score_host_pool(model, candidates, chunks=8)
+                scores, host_scores = eng.score_host_pool(model, candidates, chunks=pieces, mapped=mapped)
+                vals, indices = eng.topk(scores, top_n, distinct=distinct)              # syncs
         else:
-            scores, _, _, _ = self.score_pool(candidates)
-        vals, indices = eng.topk(scores, top_n, distinct=bool(return_distinct))      # syncs
+            cells, M = self.gp.upload_pool(candidates)
+            if fused:
+                scores = eng.empty((M,), torch.float32)
+                cands = eng.score_pool_topk(model, cells, M, top_n, distinct, scores=scores)
+                vals, indices = eng.cands_read(cands, top_n)                             # syncs
+            else:
+                scores, _, _, _ = eng.score_pool(model, cells, M)
+                vals, indices = eng.topk(scores, top_n, distinct=distinct)              # syncs
         if return_distinct and len(indices) < top_n:
             # fewer than top_n distinct values: the reference falls back to plain top-k (:106-108)
             vals, indices = eng.topk(scores, top_n, distinct=False)
@@ -107,7 +137,7 @@ class GraphExpectedImprovement(BaseAcquisition):
             eis = host_scores.numpy().reshape(-1, 1)       # view of a pinned block owned by this result
         else:
             eis = scores.cpu().numpy().reshape(-1, 1)
-        if isinstance(candidates, (CellBatch, torch.Tensor)):
+        if isinstance(candidates, (CellBatch, CellSlots, torch.Tensor)):
             xs = tuple(int(i) for i in indices)
         else:
             xs = tuple([candidates[int(i)] for i in indices])

@@ -23,7 +23,7 @@ import numpy as np
 import torch
 
 from .. import _lib
-from ..cells import CellBatch
+from ..cells import CellBatch, CellSlots, pack_networkx
 from ..kernels import GraphKernels, SumKernel, WeisfilerLehman
 from ..pool_model import PoolModel
 
@@ -61,8 +61,11 @@ class GraphGP:
                  weights=None, vector_theta_bounds: tuple = (1e-5, 0.1), graph_theta_bounds: tuple = (1e-1, 1.e1),
                  verbose=False, n_max=None):
         assert len(train_x) == train_y.shape[0], 'mismatch of length between train and test GP'
-        if not isinstance(train_x, CellBatch):
-            assert all([isinstance(x, nx.Graph) for x in train_x]), \
+        if not isinstance(train_x, (CellBatch, CellSlots)):
+            # (extension: an example may be a TUPLE of graphs, one per record slot — "normal | reduce" —
+            # for sums whose kernels read different cells of the architecture, WeisfilerLehman(slot=i))
+            assert all([isinstance(x, nx.Graph) or (isinstance(x, tuple) and all(isinstance(g, nx.Graph) for g in x))
+                        for x in train_x]), \
                 'each of the training example in train_x needs to be a networkX graph!'
         self.likelihood = likelihood
         self.kernels = kernels
@@ -104,16 +107,57 @@ class GraphGP:
         from ..engine import Engine
         return Engine.get()
 
-    def _pack(self, gr) -> CellBatch:
-        return self.kernels[0].pack(gr)
+    def _pack(self, gr) -> CellSlots:
+        """list[nx.DiGraph] | list[tuple of nx.DiGraph] | CellBatch | CellSlots -> CellSlots (directed; every
+        kernel symmetrises its own view if it is `undirected`, like the per-kernel conversion of
+        kernels/weisfilerlehman.py:127-136)."""
+        if isinstance(gr, CellSlots):
+            return gr
+        if isinstance(gr, CellBatch):
+            return CellSlots([gr])
+        wl = [k for k in self.kernels if isinstance(k, WeisfilerLehman)]
+        labels = set(k.node_label for k in wl)
+        if len(labels) > 1:
+            raise NotImplementedError("kernels of one GP must read the same node attribute (got %s)" % sorted(labels))
+        k0 = wl[0]
+        gr = list(gr)
+        if len(gr) and isinstance(gr[0], tuple):
+            n_slots = len(gr[0])
+            return CellSlots([pack_networkx([g[i] for g in gr], k0.vocab, node_label=k0.node_label)
+                              for i in range(n_slots)])
+        return CellSlots([pack_networkx(gr, k0.vocab, node_label=k0.node_label)])
 
-    def _like_train(self, batch: CellBatch) -> CellBatch:
-        """Bring a pool batch to the record width the GP was fitted with."""
+    @staticmethod
+    def _kernel_view(slots: CellSlots, k) -> CellBatch:
+        """The cells kernel k reads: its record slot, symmetrised if the kernel is undirected."""
+        slot = int(getattr(k, 'slot', 0))
+        if slot >= slots.n_slots:
+            raise ValueError("kernel reads record slot %d but the inputs have %d slot(s)" % (slot, slots.n_slots))
+        b = slots.slots[slot]
+        return b.to_undirected() if getattr(k, 'undirected', False) else b
+
+    def _like_train(self, slots: CellSlots) -> CellSlots:
+        """Bring a pool batch to the record width the GP was fitted with.  A pool with wider cells than the
+        training set (the reference accepts any size) makes the GP re-derive its device state on 16-node
+        records — same h, lambda and weights, no grid search, no optimisation."""
         n_max = self._dev['n_max']
-        if batch.n_max > n_max:
-            raise ValueError("pool cells have up to %d nodes but the GP was fitted on %d-node records; "
-                             "construct the GP with n_max=16" % (batch.n_max, n_max))
-        return batch.widen(n_max)
+        if slots.n_slots != self._dev['n_slots']:
+            raise ValueError("the GP was fitted on %d-slot examples, the pool has %d" % (self._dev['n_slots'], slots.n_slots))
+        if slots.n_max > n_max:
+            self._rewiden(slots.n_max)
+            n_max = self._dev['n_max']
+        return slots.widen(n_max)
+
+    def _rewiden(self, n_max: int):
+        saved = (self.nlml, dict(self.nlml_grid), self.logDetK, self.weights.clone(), self.layer_weights)
+        self.n_max = n_max
+        fixed = self.fixed_weights
+        self.fixed_weights = True                    # keep the fitted weights: nothing is trained here
+        try:
+            self.fit(iters=0, wl_subtree_candidates=(), optimize_lik=False)
+        finally:
+            self.fixed_weights = fixed
+        self.nlml, self.nlml_grid, self.logDetK, self.weights, self.layer_weights = saved
 
     def _y_device(self, eng):
         return torch.as_tensor(np.asarray(self.y.detach().cpu().numpy(), dtype=np.float64)).to(eng.device)
@@ -146,19 +190,34 @@ class GraphGP:
         if optimizer_kwargs is None:
             optimizer_kwargs = {'lr': 0.1}
         eng = self._engine()
-        batch = self._pack(self.x)
+        eng.lib.nbw_range_push(b"GraphGP.fit")
+        try:
+            return self._fit(eng, iters, optimizer, wl_subtree_candidates, optimize_lik, max_lik,
+                             optimize_wl_layer_weights, optimizer_kwargs)
+        finally:
+            eng.lib.nbw_range_pop()
+
+    def _fit(self, eng, iters, optimizer, wl_subtree_candidates, optimize_lik, max_lik, optimize_wl_layer_weights,
+             optimizer_kwargs):
+        slots = self._pack(self.x)
         if self.n_max is not None:
-            batch = batch.widen(self.n_max)
-        cells = eng.upload_cells(batch)
+            slots = slots.widen(self.n_max)
         y_dev = self._y_device(eng)
         self.nlml_grid = {}
 
-        # 1. WL features once per kernel, deep enough for every candidate; h by marginal likelihood
-        fits = []
+        # 1. WL features once per kernel, deep enough for every candidate; h by marginal likelihood.
+        #    Every kernel reads ITS view of the examples (record slot, undirected or not): uploaded once per view.
+        fits, views, view_cells = [], [], {}
         for k in self.sum_kernels.kernels:
             if not isinstance(k, WeisfilerLehman):
                 logging.warning('Graph kernel optimisation for ' + str(k) + " not implemented yet.")
                 raise NotImplementedError("only WeisfilerLehman kernels run on the GPU path")
+            key = (int(getattr(k, 'slot', 0)), bool(k.undirected))
+            if key not in view_cells:
+                vb = self._kernel_view(slots, k)
+                view_cells[key] = (vb, eng.upload_cells(vb))
+            batch, cells = view_cells[key]
+            views.append(key)
             cands = [int(c) for c in wl_subtree_candidates]
             h_fit = max(cands + [k.h])
             fit = k.fit_device(cells, batch.n_max, h=h_fit, batch=batch)
@@ -281,6 +340,13 @@ class GraphGP:
         self.layer_weights = layer_weights
         lik = float(likelihood.item())
         L, Linv, alpha, logdet, yKy, _, _ = factor(lik)
+        # predict() normalises the joint Gram with the STORED weights, which are one optimiser step ahead of
+        # the K behind K_i (gp.py:186-215 keeps the K of the last loop iteration): the pool path needs the
+        # training diagonal under those final weights
+        s_pool = inv_sqrt_diag
+        if levels is not None and iters > 0:
+            _, s_pool = self.sum_kernels.combine_device(weights, [k.gram_device(f) for k, f in zip(kernels, fits)],
+                                                        normalize=True)
 
         # 4. state (gp.py:212-219)
         self.weights = weights.clone() / torch.sum(weights)
@@ -290,7 +356,8 @@ class GraphGP:
         self.sum_kernels.weights = weights.clone()
         self._fitted = True
         self._dev = dict(eng=eng, fits=fits, hs=[k.h for k in self.sum_kernels.kernels], K=K, L=L, Linv=Linv,
-                         alpha=alpha, s=inv_sqrt_diag, y=y_dev, n_max=batch.n_max, cells=cells, batch=batch,
+                         alpha=alpha, s=inv_sqrt_diag, s_pool=s_pool, y=y_dev, n_max=slots.n_max, n_slots=slots.n_slots,
+                         views=views, view_cells=view_cells, slots=slots,
                          weights=[float(w) for w in weights], score=None, K_host=None, Ki_host=None)
         if self.verbose:
             print('Optimisation summary: ')
@@ -329,19 +396,21 @@ class GraphGP:
     def predict(self, X_s, preserve_comp_graph=False):
         """Kriging predictions (mu [M], cov [M, M]) exactly as bayesopt/gp.py:240-283: joint WL
         on train ∪ test, full M x M covariance with the element-wise clamp."""
-        if not isinstance(X_s, (list, CellBatch)):
+        if not isinstance(X_s, (list, CellBatch, CellSlots)):
             X_s = [X_s]
         self._require_fit()
-        d = self._dev
-        eng = d['eng']
         n, M = self.n, len(X_s)
         test = self._like_train(self._pack(X_s))
-        cells_all = torch.cat([d['cells'], eng.upload_cells(test)], dim=0).contiguous()
-        grams = []
-        for k, h in zip(self.sum_kernels.kernels, d['hs']):
-            fit = eng.wl_fit(cells_all, d['n_max'], h, k.oa)
-            k._fit = fit          # the reference leaves the kernel fitted on train ∪ test (Q19)
-            k._fit_batch, k._ref_cache = CellBatch.concat([d['batch'], test]), None
+        d = self._dev                            # (a wider pool re-derives the device state)
+        eng = d['eng']
+        grams, joint = [], {}
+        for k, h, key in zip(self.sum_kernels.kernels, d['hs'], d['views']):
+            if key not in joint:
+                tb = self._kernel_view(test, k)
+                joint[key] = torch.cat([d['view_cells'][key][1], eng.upload_cells(tb)], dim=0).contiguous()
+            # The reference leaves the kernel object fitted on train ∪ test (Q19), which silently corrupts its
+            # own interpretability outputs afterwards; here the kernel keeps its TRAINING fit (k._fit).
+            fit = eng.wl_fit(joint[key], d['n_max'], h, k.oa)
             grams.append(k.gram_device(fit, h))
         K_full, _ = self.sum_kernels.combine_device(d['weights'], grams, normalize=True)
         N = n + M
@@ -359,27 +428,72 @@ class GraphGP:
 
     # ------------------------------------------------------------------ fused pool path
     def _score_state(self):
-        """Feature-space posterior operators (see csrc/score_pool.cu): w_mu = B^T alpha,
-        G = (L^-1 B)^T (L^-1 B) with B = diag(1/sqrt(K_raw,ii)) sqrt(w) Phi_train."""
+        """Feature-space posterior operators of the fitted surrogate (csrc/score_packed.cu, score_pool.cu).
+
+        With omega_a = kernel weight x WL layer weight of feature column a (combine_kernels.py:36-40,
+        weisfeiler_lehman.py:316-327) and s_i = 1/sqrt(K_comb,ii) (combine_kernels.py:54-56):
+            B = diag(s) [Phi_1 | Phi_2 | ...] diag(omega),   k_s = B phi_c / sqrt(k_cc),
+            k_cc = sum_a omega_a phi_c,a^2 over ALL labels of the candidate,
+        so mu ~ phi_c . (B^T alpha) and k_s^T K_lam^-1 k_s = phi_c^T (B^T K_lam^-1 B) phi_c / k_cc.  A sum
+        of kernels is the same computation over the concatenated feature space; its kernels may read
+        different records of the candidate (WeisfilerLehman(slot=i))."""
         self._require_fit()
         d = self._dev
         if d.get('score') is not None:
             return d['score']
-        if len(self.sum_kernels.kernels) != 1:
-            raise NotImplementedError("the fused pool path handles a single WL kernel; use predict()")
-        if self.sum_kernels.kernels[0]._level_weights(d['hs'][0]) is not None:
-            raise NotImplementedError("the fused pool path assumes unit WL layer weights; use predict()")
         eng, n = d['eng'], self.n
-        fit, h, w = d['fits'][0], d['hs'][0], d['weights'][0]
-        D = fit.k_end(h)
-        # the normalisation of K uses diag(w * K_raw): s already contains 1/sqrt(w K_raw,ii)
-        B = eng.empty((n, D), torch.float64)
-        eng.scale_features(fit.phi, 0, D, d['s'], math.sqrt(w), B, D)
+        with eng.range("GraphGP.score_state"):
+            pm = self._build_score_state(eng, d, n)
+        d['score'] = pm
+        return pm
+
+    def _build_score_state(self, eng, d, n):
+        kernels = list(self.sum_kernels.kernels)
+        fits, hs, weights = d['fits'], d['hs'], d['weights']
         Linv, alpha = d['Linv'], d['alpha']
+        lws = [k._level_weights(h) for k, h in zip(kernels, hs)]           # None = ones
+        plain = len(kernels) == 1 and lws[0] is None
+        any_oa = any(f.oa for f in fits)
+        if not plain and any_oa:
+            raise NotImplementedError("the fused pool path scores sums / layer-weighted kernels in prefix form, which "
+                                      "needs linear WL kernels (oa=False); use predict() for oa sums")
+        if len(kernels) > _lib.NBW_MAX_PARTS:
+            raise NotImplementedError("the fused pool path takes sums of up to %d kernels; use predict()" % _lib.NBW_MAX_PARTS)
+        parts = []
+        for i, (k, fit, h) in enumerate(zip(kernels, fits, hs)):
+            pm = PoolModel.from_fit(eng, fit, h)
+            pm.slot, pm.undirected = d['views'][i]
+            if not plain:
+                lw = np.ones(h + 1) if lws[i] is None else lws[i]
+                pm.level_weight = [float(weights[i]) * float(x) for x in lw]
+            parts.append(pm)
+        first = parts[0]
+        first.more = parts[1:]
+        first.n_slots = d['n_slots']
+        base = 0
+        for pm in parts:
+            pm.set_label_base(base)
+            base += pm.n_labels
+        T = first.total_labels = base
+
+        def scaled_features(i):
+            """B_i = diag(s) Phi_i diag(omega) [n, D_i]; the single plain kernel folds sqrt(w) instead (its
+            weight cancels against the integer k_cc the kernels accumulate)."""
+            fit, h = fits[i], hs[i]
+            D = fit.k_end(h)
+            B = eng.empty((n, D), torch.float64)
+            if plain:
+                eng.scale_features(fit.phi, 0, D, d['s_pool'], math.sqrt(weights[i]), B, D)
+            else:
+                for l in range(h + 1):
+                    c0, c1 = fit.col_off[l], fit.col_off[l + 1]
+                    eng.scale_features(fit.phi, c0, c1, d['s_pool'], parts[i].level_weight[l], B[:, c0:], D)
+            return B, D
 
         def build_general():
             """G and w_mu over feature columns: needed by the oa kernel and by the general path of
             the linear kernel; the prefix form below does not use them, so they are built lazily."""
+            B, D = scaled_features(0)
             Wt = eng.empty((n, D), torch.float64)
             eng.gemm(False, False, n, D, n, 1.0, Linv, n, B, D, 0.0, Wt, D)
             # one extra all-zero row/column: the landing slot of labels outside the dictionary
@@ -390,33 +504,35 @@ class GraphGP:
             return G, w_mu
         # incumbent: y_raw[argmax of the posterior mean at the training points] (acquisitions.py:82-92)
         mu_train = eng.empty((n,), torch.float64)
-        eng.gemm(False, False, n, 1, n, 1.0, d['K'], n, d['alpha'], 1, 0.0, mu_train, 1)
-        inc_idx = int(np.argmax(mu_train.cpu().numpy()))
-        pm = PoolModel.from_fit(eng, fit, h)
-        pm.general_builder = build_general
-        if fit.oa:
-            pm.G, pm.w_mu = build_general()
-        if not fit.oa:
-            # prefix form (nbw_model.H): the same operators summed over ancestor chains of labels
-            T = fit.label_off[h + 1]
-            Bp = eng.prefix_features(B, fit, h)                       # [n, T+1], last column zero
+        eng.gemm(False, False, n, 1, n, 1.0, d['K'], n, alpha, 1, 0.0, mu_train, 1)
+        if plain:
+            first.general_builder = build_general
+        if any_oa:
+            first.G, first.w_mu = build_general()
+        else:
+            # prefix form (nbw_model.H): the operators summed over ancestor chains of labels, all parts
+            # side by side: Bp [n, T + 1], last column zero (landing slot of labels outside the dictionary)
+            Bp = torch.zeros((n, T + 1), dtype=torch.float64, device=eng.device)
+            for i, pm in enumerate(parts):
+                B, _ = scaled_features(i)
+                eng.prefix_features(B, fits[i], hs[i], out=Bp[:, pm.label_base:], ldp=T + 1)
             Wp = eng.empty((n, T + 1), torch.float64)
-            eng.gemm(False, False, n, T + 1, n, 1.0, d['Linv'], n, Bp, T + 1, 0.0, Wp, T + 1)
+            eng.gemm(False, False, n, T + 1, n, 1.0, Linv, n, Bp, T + 1, 0.0, Wp, T + 1)
             H = eng.empty((T + 1, T + 1), torch.float64)
             eng.gemm(True, False, T + 1, T + 1, n, 1.0, Wp, T + 1, Wp, T + 1, 0.0, H, T + 1)
             w_mu_p = eng.empty((T + 1,), torch.float64)
-            eng.gemm(True, False, T + 1, 1, n, 1.0, Bp, T + 1, d['alpha'], 1, 0.0, w_mu_p, 1)
-            pm.H, pm.w_mu_prefix = H, w_mu_p
-        pm.lik, pm.y_mean, pm.y_std = float(self.likelihood), float(self.y_mean), float(self.y_std)
-        pm.incumbent_idx, pm.incumbent = inc_idx, float(self.y_[inc_idx])
-        d['score'] = pm
-        return pm
+            eng.gemm(True, False, T + 1, 1, n, 1.0, Bp, T + 1, alpha, 1, 0.0, w_mu_p, 1)
+            first.H, first.w_mu_prefix = H, w_mu_p
+        inc_idx = int(np.argmax(mu_train.cpu().numpy()))
+        first.lik, first.y_mean, first.y_std = float(self.likelihood), float(self.y_mean), float(self.y_std)
+        first.incumbent_idx, first.incumbent = inc_idx, float(self.y_[inc_idx])
+        return first
 
     def set_pool_model(self, pm: "PoolModel"):
         """Install a pool model received from another rank (parallel.broadcast_pool_model)."""
         from ..engine import Engine
         self._fitted = True
-        self._dev = dict(eng=Engine.get(), n_max=pm.n_max, score=pm)
+        self._dev = dict(eng=Engine.get(), n_max=pm.n_max, n_slots=pm.n_slots, score=pm)
         self.likelihood = pm.lik
 
     def pool_model(self, acq="MEAN", xi=0.0, beta=0.0, incumbent=None):
@@ -425,17 +541,16 @@ class GraphGP:
 
     def upload_pool(self, X):
         """list[nx.DiGraph] | CellBatch | device records -> (device records, n_cells)."""
-        d = self._dev
         if isinstance(X, torch.Tensor):
             return X, X.shape[0]
         batch = self._like_train(self._pack(X))
-        return d['eng'].upload_cells(batch), len(batch)
+        return self._dev['eng'].upload_cells(batch), len(batch)
 
     def predict_diag(self, X_s):
         """(mu [M], var [M]) — the diagonal of predict() — through the fused pool kernel."""
         self._require_fit()
-        eng = self._dev['eng']
         cells, M = self.upload_pool(X_s)
+        eng = self._dev['eng']
         _, mu, var, _ = eng.score_pool(self.pool_model("MEAN"), cells, M, want64=True)
         return mu.cpu(), var.cpu()
 

@@ -163,6 +163,47 @@ class CellBatch:
         return out
 
 
+class CellSlots:
+    """Candidates made of SEVERAL cells each (e.g. DARTS "normal | reduce"): one CellBatch per slot, all of
+    the same length.  Kernel i of a sum reads slot `kernel.slot` (default 0, the reference's behaviour:
+    every kernel of a SumKernel sees the same graph list, kernels/combine_kernels.py:36-56).  Device layout:
+    the slot records of a candidate are concatenated, (N, n_slots * stride) u8."""
+
+    def __init__(self, slots: Sequence[CellBatch]):
+        slots = list(slots)
+        assert len(slots) >= 1 and all(len(s) == len(slots[0]) for s in slots), "slots must have equal lengths"
+        n_max = max(s.n_max for s in slots)
+        self.slots = [s.widen(n_max) for s in slots]
+        self.n_max = n_max
+
+    def __len__(self):
+        return len(self.slots[0])
+
+    @property
+    def n_slots(self) -> int:
+        return len(self.slots)
+
+    def __getitem__(self, idx) -> "CellSlots":
+        return CellSlots([s[idx] for s in self.slots])
+
+    def widen(self, n_max: int) -> "CellSlots":
+        return self if n_max == self.n_max else CellSlots([s.widen(n_max) for s in self.slots])
+
+    def to_records(self) -> np.ndarray:
+        return np.concatenate([s.to_records() for s in self.slots], axis=1)
+
+    @staticmethod
+    def from_records(rec: np.ndarray, n_max: int, n_slots: int) -> "CellSlots":
+        st = record_stride(n_max)
+        rec = np.ascontiguousarray(rec, dtype=np.uint8).reshape(-1, n_slots * st)
+        return CellSlots([CellBatch.from_records(rec[:, i * st:(i + 1) * st], n_max) for i in range(n_slots)])
+
+    @staticmethod
+    def concat(items: Iterable["CellSlots"]) -> "CellSlots":
+        items = list(items)
+        return CellSlots([CellBatch.concat([it.slots[i] for it in items]) for i in range(items[0].n_slots)])
+
+
 def pack_networkx(graphs, vocab: OpVocab, node_label: str = "op_name",
                   undirected: bool = False, n_max: Optional[int] = None) -> CellBatch:
     """list[nx.DiGraph] -> CellBatch (the conversion the reference does with

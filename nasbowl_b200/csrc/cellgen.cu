@@ -378,6 +378,7 @@ mutate_encoded_kernel(int family, const uint8_t* __restrict__ parents, int64_t n
 extern "C" int nbw_generate_cells(nbw_ctx* ctx, int family, uint64_t seed, int64_t first_index, int64_t n_cells,
                                   void* cells, void* stream) {
   if (!ctx) return NBW_ERR_INVALID;
+  NbwRange range("nbw_generate_cells");
   NBW_REQUIRE(ctx, family >= 0 && family <= 2, "family must be 0 (NB101), 1 (NB201) or 2 (DARTS)");
   NBW_REQUIRE(ctx, n_cells >= 0 && first_index >= 0, "bad range");
   if (n_cells == 0) return NBW_OK;
@@ -419,6 +420,7 @@ extern "C" int nbw_mutate_encoded(nbw_ctx* ctx, int family, const uint8_t* paren
 extern "C" int nbw_mutate_cells(nbw_ctx* ctx, int family, const void* parents, int64_t n_parents, uint64_t seed,
                                 int64_t first_index, int64_t n_children, void* cells, void* stream) {
   if (!ctx) return NBW_ERR_INVALID;
+  NbwRange range("nbw_mutate_cells");
   NBW_REQUIRE(ctx, family == 0, "nbw_mutate_cells edits pruned NAS-Bench-101 cells; NB201 / DARTS cells are edited on their encodings (nbw_mutate_encoded)");
   NBW_REQUIRE(ctx, n_parents > 0 && n_children >= 0 && first_index >= 0, "bad range");
   if (n_children == 0) return NBW_OK;

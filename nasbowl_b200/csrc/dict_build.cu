@@ -313,6 +313,7 @@ extern "C" int nbw_dict_build(nbw_ctx* ctx, const uint64_t* keys, const uint64_t
                               uint32_t* ids, uint64_t* uniq_keys, uint64_t* uniq_chks,
                               int64_t uniq_cap, int64_t* n_unique_h, void* stream) {
   if (!ctx) return NBW_ERR_INVALID;
+  NbwRange range("nbw_dict_build");
   NBW_REQUIRE(ctx, n_keys >= 0 && n_keys < (int64_t)1 << 31, "n_keys out of range");
   NBW_REQUIRE(ctx, key_bits >= 8 && key_bits <= 64 && key_bits % 8 == 0, "key_bits must be a multiple of 8 in [8,64]");
   NBW_REQUIRE(ctx, n_unique_h != nullptr, "n_unique_h is NULL");
@@ -351,11 +352,10 @@ extern "C" int nbw_dict_build(nbw_ctx* ctx, const uint64_t* keys, const uint64_t
     int n_pad = 2;
     while (n_pad < n_keys) n_pad <<= 1;
     const size_t smem = (size_t)n_pad * (sizeof(uint64_t) + sizeof(uint32_t));
-    static bool attr = false;
-    if (!attr) {
+    if (!(ctx->attr_set & NBW_ATTR_SMALL_SORT)) {
       NBW_CUDA(ctx, cudaFuncSetAttribute(small_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          kSmallSortMax * (int)(sizeof(uint64_t) + sizeof(uint32_t))));
-      attr = true;
+      ctx->attr_set |= NBW_ATTR_SMALL_SORT;
     }
     small_sort_kernel<<<1, 1024, smem, st>>>(keys, (int)n_keys, n_pad, kbuf[0], vbuf[0]);
     NBW_CHECK_LAUNCH(ctx);

@@ -264,6 +264,107 @@ gram_i8_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
   }
 }
 
+// ------------------------------------------------------------------ epilogue forms
+// One thread owns 32 consecutive columns of one output row (tcgen05.ld 32x32b.x32).  The accumulator leaves
+// TMEM as s32; what reaches HBM is chosen per launch (nbw_gram_out): s32 (128 B per segment), u8 / s16
+// with saturation (32 / 64 B: Gram entries of NAS cells are <= (h+1) n_max^2, 196 for NB101 at h = 3) or the
+// cosine-normalised fp32 kernel value K_ij rsqrt(K_ii) rsqrt(K_jj) of kernels/combine_kernels.py:54-56.
+struct GramOut {
+  void* C;
+  int64_t ldc;              // in elements of the output type
+  const float* scale_a;     // F32_NORM: 1/sqrt(K_ii) of the rows of A / of B
+  const float* scale_b;
+  uint32_t* overflow;       // set to 1 when a narrow store had to saturate
+  int64_t row_offset;       // global row index of A's first row (symmetric schedule)
+  int upper_only;           // skip tiles strictly below the diagonal of the global matrix
+};
+
+template <int MODE>
+__device__ __forceinline__ void store_segment(const GramOut& O, int64_t r, int64_t cbase, const uint32_t (&v)[32], int64_t n,
+                                              bool vec_ok) {
+  if (MODE == NBW_GRAM_S32) {
+    int32_t* dst = static_cast<int32_t*>(O.C) + r * O.ldc + cbase;
+    if (vec_ok && cbase + 32 <= n) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<int4*>(dst + 4 * q) = make_int4((int)v[4 * q], (int)v[4 * q + 1], (int)v[4 * q + 2], (int)v[4 * q + 3]);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 32; ++q)
+        if (cbase + q < n) dst[q] = (int32_t)v[q];
+    }
+  } else if (MODE == NBW_GRAM_U8) {
+    uint8_t* dst = static_cast<uint8_t*>(O.C) + r * O.ldc + cbase;
+    uint32_t w[8];
+    bool sat = false;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      uint32_t b[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int x = (int)v[4 * q + t];
+        sat = sat || x > 255 || x < 0;
+        b[t] = (uint32_t)(x < 0 ? 0 : (x > 255 ? 255 : x));
+      }
+      w[q] = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+    }
+    if (sat && O.overflow) atomicOr(O.overflow, 1u);
+    if (vec_ok && cbase + 32 <= n) {
+      *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+      *reinterpret_cast<uint4*>(dst + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 32; ++q)
+        if (cbase + q < n) dst[q] = (uint8_t)(w[q >> 2] >> (8 * (q & 3)));
+    }
+  } else if (MODE == NBW_GRAM_S16) {
+    int16_t* dst = static_cast<int16_t*>(O.C) + r * O.ldc + cbase;
+    uint32_t w[16];
+    bool sat = false;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      int a = (int)v[2 * q], b = (int)v[2 * q + 1];
+      sat = sat || a > 32767 || a < -32768 || b > 32767 || b < -32768;
+      a = a > 32767 ? 32767 : (a < -32768 ? -32768 : a);
+      b = b > 32767 ? 32767 : (b < -32768 ? -32768 : b);
+      w[q] = ((uint32_t)a & 0xFFFFu) | ((uint32_t)b << 16);
+    }
+    if (sat && O.overflow) atomicOr(O.overflow, 1u);
+    if (vec_ok && cbase + 32 <= n) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<uint4*>(dst + 8 * q) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 32; ++q)
+        if (cbase + q < n) dst[q] = (int16_t)(w[q >> 1] >> (16 * (q & 1)));
+    }
+  } else {
+    float* dst = static_cast<float*>(O.C) + r * O.ldc + cbase;
+    const float sa = __ldg(O.scale_a + r);
+    if (vec_ok && cbase + 32 <= n) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 sb = __ldg(reinterpret_cast<const float4*>(O.scale_b + cbase) + q);
+        *reinterpret_cast<float4*>(dst + 4 * q) =
+            make_float4((float)(int)v[4 * q] * sa * sb.x, (float)(int)v[4 * q + 1] * sa * sb.y,
+                        (float)(int)v[4 * q + 2] * sa * sb.z, (float)(int)v[4 * q + 3] * sa * sb.w);
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 32; ++q)
+        if (cbase + q < n) dst[q] = (float)(int)v[q] * sa * __ldg(O.scale_b + cbase + q);
+    }
+  }
+}
+
+// Symmetric schedule (A and B are row ranges of the same matrix): a 256 x 256 tile whose last column lies
+// left of its first global row holds only entries K_ij with i > j — the mirror image of a tile that is
+// computed — and is skipped by producer, MMA issuer and epilogue alike.
+__device__ __forceinline__ bool tile_skipped(const GramOut& O, int32_t mt, int32_t nt, int tile_rows, int tile_cols) {
+  return O.upper_only && ((int64_t)nt * tile_cols + (tile_cols - 1) < O.row_offset + (int64_t)mt * tile_rows);
+}
+
 // ------------------------------------------------------------------ CTA-pair variant (cta_group::2)
 // A cluster of two CTAs (one TPC) owns a 256 x 256 output tile.  Each CTA stages its own 128 rows of A
 // and its own 128 rows (= half of N) of B per K-block: 32 KB per stage instead of 48 KB, and every
@@ -333,10 +434,10 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
-template <int STAGES>
+template <int STAGES, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
 gram_i8_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                    int32_t* __restrict__ C, int64_t ldc, int64_t m, int64_t n, int32_t kblk0, int32_t k_blocks,
+                    const GramOut O, int64_t m, int64_t n, int32_t kblk0, int32_t k_blocks,
                     int32_t m_tiles, int32_t n_tiles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -383,6 +484,7 @@ gram_i8_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       for (int64_t t = pair_id; t < total_tiles; t += n_pairs) {
         int32_t mt, nt;
         tile_coords(t, m_tiles, n_tiles, mt, nt);
+        if (tile_skipped(O, mt, nt, PM, PAIR_BN)) continue;
         const int32_t row0 = mt * PM + (int32_t)rank * BM, col0 = nt * PAIR_BN + (int32_t)rank * PAIR_B_ROWS;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&bars->empty[stage], phase ^ 1u);
@@ -400,6 +502,11 @@ gram_i8_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (leader && lane == 0) {
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int64_t t = pair_id; t < total_tiles; t += n_pairs) {
+        {
+          int32_t mt, nt;
+          tile_coords(t, m_tiles, n_tiles, mt, nt);
+          if (tile_skipped(O, mt, nt, PM, PAIR_BN)) continue;
+        }
         mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1u);        // both CTAs' epilogues have drained this buffer
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tmem_acc = tmem_base + acc * PAIR_BN;
@@ -422,11 +529,14 @@ gram_i8_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     __syncwarp();
   } else {
     const int quarter = warp & 3;
-    const bool vec_ok = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+    constexpr int kElem = MODE == NBW_GRAM_U8 ? 1 : (MODE == NBW_GRAM_S16 ? 2 : 4);
+    const bool vec_ok = ((O.ldc * kElem) % 16 == 0) && ((reinterpret_cast<uintptr_t>(O.C) & 15) == 0) &&
+                        (MODE != NBW_GRAM_F32_NORM || (reinterpret_cast<uintptr_t>(O.scale_b) & 15) == 0);
     uint32_t acc = 0, acc_phase = 0;
     for (int64_t t = pair_id; t < total_tiles; t += n_pairs) {
       int32_t mt, nt;
       tile_coords(t, m_tiles, n_tiles, mt, nt);
+      if (tile_skipped(O, mt, nt, PM, PAIR_BN)) continue;
       const int64_t row0 = (int64_t)mt * PM + (int64_t)rank * BM, col0 = (int64_t)nt * PAIR_BN;
       mbar_wait(&bars->tmem_full[acc], acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -435,20 +545,7 @@ gram_i8_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       for (int c = 0; c < PAIR_BN / 32; ++c) {
         uint32_t v[32];
         tmem_load_32cols(tmem_base + acc * PAIR_BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), v);
-        if (r < m) {
-          const int64_t cbase = col0 + c * 32;
-          int32_t* dst = C + r * ldc + cbase;
-          if (vec_ok && cbase + 32 <= n) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              *reinterpret_cast<int4*>(dst + 4 * q) =
-                  make_int4((int)v[4 * q], (int)v[4 * q + 1], (int)v[4 * q + 2], (int)v[4 * q + 3]);
-          } else {
-#pragma unroll
-            for (int q = 0; q < 32; ++q)
-              if (cbase + q < n) dst[q] = (int32_t)v[q];
-          }
-        }
+        if (r < m) store_segment<MODE>(O, r, col0 + c * 32, v, n, vec_ok);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -536,18 +633,142 @@ int make_operand_map(nbw_ctx* ctx, CUtensorMap* map, const int8_t* base, int64_t
 
 }  // namespace
 
-extern "C" int nbw_gram_i8(nbw_ctx* ctx, const int8_t* A, int64_t m, int64_t lda, const int8_t* B, int64_t n,
-                           int64_t ldb, int64_t k0, int64_t k1, int32_t* C, int64_t ldc, int impl, void* stream) {
-  if (!ctx) return NBW_ERR_INVALID;
-  NBW_REQUIRE(ctx, m >= 0 && n >= 0 && ldc >= n, "bad shape");
+namespace {
+
+template <int MODE>
+int launch_pair(nbw_ctx* ctx, const CUtensorMap& map_a, const CUtensorMap& map_b, const GramOut& O, int64_t m, int64_t n,
+                int32_t kb0, int32_t nkb, cudaStream_t st) {
+  constexpr size_t kBytes = gram_pair_smem_bytes<PAIR_STAGES>();
+  auto kern = gram_i8_pair_kernel<PAIR_STAGES, MODE>;
+  if (!(ctx->attr_set & (NBW_ATTR_GRAM_PAIR << MODE))) {
+    NBW_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBytes));
+    ctx->attr_set |= (NBW_ATTR_GRAM_PAIR << MODE);
+  }
+  int& max_pairs = ctx->gram_max_pairs;
+  if (!max_pairs) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(ctx->sm_count & ~1));
+    cfg.blockDim = dim3(192);
+    cfg.dynamicSmemBytes = kBytes;
+    int clusters = 0;
+    NBW_CUDA(ctx, cudaOccupancyMaxActiveClusters(&clusters, kern, &cfg));
+    NBW_REQUIRE(ctx, clusters >= 1, "no CTA pair of the Gram kernel fits this device");
+    max_pairs = clusters;
+  }
+  const int32_t mt2 = (int32_t)((m + 2 * BM - 1) / (2 * BM)), nt2 = (int32_t)((n + PAIR_BN - 1) / PAIR_BN);
+  const int64_t tiles = (int64_t)mt2 * nt2;
+  NBW_REQUIRE(ctx, tiles < ((int64_t)1 << 31), "gram: too many tiles for one launch");
+  const unsigned pairs = (unsigned)(tiles < max_pairs ? tiles : max_pairs);
+  kern<<<2 * pairs, 192, kBytes, st>>>(map_a, map_b, O, m, n, kb0, nkb, mt2, nt2);
+  NBW_CHECK_LAUNCH(ctx);
+  return NBW_OK;
+}
+
+int check_operands(nbw_ctx* ctx, const int8_t* A, int64_t m, int64_t lda, const int8_t* B, int64_t n, int64_t ldb, int64_t k0,
+                   int64_t k1) {
   NBW_REQUIRE(ctx, k0 >= 0 && k1 > k0 && k0 % 128 == 0 && k1 % 128 == 0, "k0, k1 must be multiples of 128 with k1 > k0");
   NBW_REQUIRE(ctx, lda % 128 == 0 && ldb % 128 == 0 && lda >= k1 && ldb >= k1, "lda/ldb must be multiples of 128 and >= k1");
-  if (m == 0 || n == 0) return NBW_OK;
-  NBW_REQUIRE(ctx, A && B && C, "null pointer");
+  NBW_REQUIRE(ctx, A && B, "null pointer");
   NBW_REQUIRE(ctx, ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 127) == 0,
               "A and B must be 128-byte aligned");
   NBW_REQUIRE(ctx, m < ((int64_t)1 << 31) && n < ((int64_t)1 << 31) && lda < ((int64_t)1 << 31) && ldb < ((int64_t)1 << 31),
               "dimension too large");
+  return NBW_OK;
+}
+
+// C[i][j] = C[j][i] for i > j: completes a matrix of which only the upper 256 x 256 tiles were computed.
+// 32 x 32 tiles through shared memory: coalesced reads of the upper tile, coalesced writes of its mirror.
+template <typename T>
+__global__ void __launch_bounds__(256)
+sym_mirror_kernel(T* __restrict__ C, int64_t n, int64_t ldc) {
+  __shared__ T tile[32][33];
+  // triangular enumeration of tile pairs (bi < bj) plus the diagonal tiles (bi == bj)
+  const int64_t nb = (n + 31) / 32;
+  int64_t t = blockIdx.x;
+  // row bi has nb - bi tiles; invert the triangular index with a float estimate and a fix-up
+  int64_t bi = (int64_t)((2.0 * nb + 1.0 - sqrt((2.0 * nb + 1.0) * (2.0 * nb + 1.0) - 8.0 * (double)t)) * 0.5);
+  while (bi > 0 && bi * nb - bi * (bi - 1) / 2 > t) --bi;
+  while ((bi + 1) * nb - (bi + 1) * bi / 2 <= t) ++bi;
+  const int64_t bj = bi + (t - (bi * nb - bi * (bi - 1) / 2));
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t i = bi * 32 + r, j = bj * 32 + tx;
+    tile[r][tx] = (i < n && j < n) ? C[i * ldc + j] : T(0);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t i = bj * 32 + r, j = bi * 32 + tx;    // the mirrored tile: rows of bj, columns of bi
+    if (i < n && j < n && i > j) C[i * ldc + j] = tile[tx][r];
+  }
+}
+
+}  // namespace
+
+extern "C" int nbw_gram_i8_ex(nbw_ctx* ctx, const int8_t* A, int64_t m, int64_t lda, const int8_t* B, int64_t n,
+                              int64_t ldb, int64_t k0, int64_t k1, void* C, int64_t ldc, int out_mode, int upper_only,
+                              int64_t row_offset, const float* scale_a, const float* scale_b, uint32_t* overflow,
+                              void* stream) {
+  if (!ctx) return NBW_ERR_INVALID;
+  NbwRange range("nbw_gram_i8_ex");
+  NBW_REQUIRE(ctx, m >= 0 && n >= 0 && ldc >= n, "bad shape");
+  NBW_REQUIRE(ctx, out_mode >= NBW_GRAM_S32 && out_mode <= NBW_GRAM_F32_NORM, "unknown output mode %d", out_mode);
+  NBW_REQUIRE(ctx, out_mode != NBW_GRAM_F32_NORM || (scale_a && scale_b), "the normalised output needs both scale vectors");
+  NBW_REQUIRE(ctx, row_offset >= 0, "row_offset negative");
+  if (m == 0 || n == 0) return NBW_OK;
+  NBW_REQUIRE(ctx, C != nullptr, "C is NULL");
+  int rc = check_operands(ctx, A, m, lda, B, n, ldb, k0, k1);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUtensorMap map_a, map_b;
+  rc = make_operand_map(ctx, &map_a, A, m, lda, BM);
+  if (rc) return rc;
+  rc = make_operand_map(ctx, &map_b, B, n, ldb, PAIR_B_ROWS);
+  if (rc) return rc;
+  GramOut O;
+  O.C = C;
+  O.ldc = ldc;
+  O.scale_a = scale_a;
+  O.scale_b = scale_b;
+  O.overflow = overflow;
+  O.row_offset = row_offset;
+  O.upper_only = upper_only;
+  const int32_t kb0 = (int32_t)(k0 / BK), nkb = (int32_t)((k1 - k0) / BK);
+  switch (out_mode) {
+    case NBW_GRAM_S32: return launch_pair<NBW_GRAM_S32>(ctx, map_a, map_b, O, m, n, kb0, nkb, st);
+    case NBW_GRAM_U8: return launch_pair<NBW_GRAM_U8>(ctx, map_a, map_b, O, m, n, kb0, nkb, st);
+    case NBW_GRAM_S16: return launch_pair<NBW_GRAM_S16>(ctx, map_a, map_b, O, m, n, kb0, nkb, st);
+    default: return launch_pair<NBW_GRAM_F32_NORM>(ctx, map_a, map_b, O, m, n, kb0, nkb, st);
+  }
+}
+
+extern "C" int nbw_sym_mirror(nbw_ctx* ctx, void* C, int64_t n, int64_t ldc, int elem_bytes, void* stream) {
+  if (!ctx) return NBW_ERR_INVALID;
+  NbwRange range("nbw_sym_mirror");
+  NBW_REQUIRE(ctx, n >= 0 && ldc >= n && (elem_bytes == 1 || elem_bytes == 2 || elem_bytes == 4), "bad argument");
+  if (n == 0) return NBW_OK;
+  NBW_REQUIRE(ctx, C != nullptr, "C is NULL");
+  const int64_t nb = (n + 31) / 32;
+  const int64_t tiles = nb * (nb + 1) / 2;
+  NBW_REQUIRE(ctx, tiles < ((int64_t)1 << 31), "matrix too large for one mirror launch");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (elem_bytes == 1) sym_mirror_kernel<uint8_t><<<(unsigned)tiles, 256, 0, st>>>(static_cast<uint8_t*>(C), n, ldc);
+  else if (elem_bytes == 2) sym_mirror_kernel<uint16_t><<<(unsigned)tiles, 256, 0, st>>>(static_cast<uint16_t*>(C), n, ldc);
+  else sym_mirror_kernel<uint32_t><<<(unsigned)tiles, 256, 0, st>>>(static_cast<uint32_t*>(C), n, ldc);
+  NBW_CHECK_LAUNCH(ctx);
+  return NBW_OK;
+}
+
+extern "C" int nbw_gram_i8(nbw_ctx* ctx, const int8_t* A, int64_t m, int64_t lda, const int8_t* B, int64_t n,
+                           int64_t ldb, int64_t k0, int64_t k1, int32_t* C, int64_t ldc, int impl, void* stream) {
+  if (!ctx) return NBW_ERR_INVALID;
+  NbwRange range("nbw_gram_i8");
+  NBW_REQUIRE(ctx, m >= 0 && n >= 0 && ldc >= n, "bad shape");
+  if (m == 0 || n == 0) return NBW_OK;
+  NBW_REQUIRE(ctx, C != nullptr, "null pointer");
+  int rc = check_operands(ctx, A, m, lda, B, n, ldb, k0, k1);
+  if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (impl == 1) {
     dim3 grid((unsigned)((n + 63) / 64), (unsigned)((m + 63) / 64));
@@ -565,47 +786,25 @@ extern "C" int nbw_gram_i8(nbw_ctx* ctx, const int8_t* A, int64_t m, int64_t lda
   int variant = 5;
   if (const char* v = getenv("NBW_GRAM_VARIANT")) variant = atoi(v);
   NBW_REQUIRE(ctx, variant == 4 || variant == 5, "NBW_GRAM_VARIANT must be 4 (single CTA) or 5 (CTA pair)");
-  const int bn = variant == 5 ? PAIR_B_ROWS : 256;   // rows of B per TMA box
+  if (variant == 5)
+    return nbw_gram_i8_ex(ctx, A, m, lda, B, n, ldb, k0, k1, C, ldc, NBW_GRAM_S32, 0, 0, nullptr, nullptr, nullptr, stream);
   CUtensorMap map_a, map_b;
-  int rc = make_operand_map(ctx, &map_a, A, m, lda, BM);
+  rc = make_operand_map(ctx, &map_a, A, m, lda, BM);
   if (rc) return rc;
-  rc = make_operand_map(ctx, &map_b, B, n, ldb, bn);
+  rc = make_operand_map(ctx, &map_b, B, n, ldb, 256);
   if (rc) return rc;
   const int32_t kb0 = (int32_t)(k0 / BK), nkb = (int32_t)((k1 - k0) / BK);
-  if (variant == 4) {
-    static bool attr4 = false;
-    constexpr size_t kBytes = gram_persist_smem_bytes<256, 4>();
-    if (!attr4) {
-      NBW_CUDA(ctx, cudaFuncSetAttribute(gram_i8_persistent_kernel<256, 4>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBytes));
-      attr4 = true;
-    }
-    const int32_t mt = (int32_t)((m + BM - 1) / BM), nt = (int32_t)((n + 255) / 256);
-    const int64_t tiles = (int64_t)mt * nt;
-    NBW_REQUIRE(ctx, tiles < ((int64_t)1 << 31), "gram: too many tiles for one launch");
-    const unsigned ctas = (unsigned)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
-    gram_i8_persistent_kernel<256, 4><<<ctas, 192, kBytes, st>>>(map_a, map_b, C, ldc, m, n, kb0, nkb, mt, nt);
-  } else {
-    static int max_pairs = 0;
-    constexpr size_t kBytes = gram_pair_smem_bytes<PAIR_STAGES>();
-    if (!max_pairs) {
-      NBW_CUDA(ctx, cudaFuncSetAttribute(gram_i8_pair_kernel<PAIR_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kBytes));
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3((unsigned)(ctx->sm_count & ~1));
-      cfg.blockDim = dim3(192);
-      cfg.dynamicSmemBytes = kBytes;
-      int clusters = 0;
-      NBW_CUDA(ctx, cudaOccupancyMaxActiveClusters(&clusters, gram_i8_pair_kernel<PAIR_STAGES>, &cfg));
-      NBW_REQUIRE(ctx, clusters >= 1, "no CTA pair of the Gram kernel fits this device");
-      max_pairs = clusters;
-    }
-    const int32_t mt2 = (int32_t)((m + 2 * BM - 1) / (2 * BM)), nt2 = (int32_t)((n + PAIR_BN - 1) / PAIR_BN);
-    const int64_t tiles = (int64_t)mt2 * nt2;
-    NBW_REQUIRE(ctx, tiles < ((int64_t)1 << 31), "gram: too many tiles for one launch");
-    const unsigned pairs = (unsigned)(tiles < max_pairs ? tiles : max_pairs);
-    gram_i8_pair_kernel<PAIR_STAGES><<<2 * pairs, 192, kBytes, st>>>(map_a, map_b, C, ldc, m, n, kb0, nkb, mt2, nt2);
+  constexpr size_t kBytes = gram_persist_smem_bytes<256, 4>();
+  if (!(ctx->attr_set & NBW_ATTR_GRAM_SINGLE)) {
+    NBW_CUDA(ctx, cudaFuncSetAttribute(gram_i8_persistent_kernel<256, 4>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBytes));
+    ctx->attr_set |= NBW_ATTR_GRAM_SINGLE;
   }
+  const int32_t mt = (int32_t)((m + BM - 1) / BM), nt = (int32_t)((n + 255) / 256);
+  const int64_t tiles = (int64_t)mt * nt;
+  NBW_REQUIRE(ctx, tiles < ((int64_t)1 << 31), "gram: too many tiles for one launch");
+  const unsigned ctas = (unsigned)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
+  gram_i8_persistent_kernel<256, 4><<<ctas, 192, kBytes, st>>>(map_a, map_b, C, ldc, m, n, kb0, nkb, mt, nt);
   NBW_CHECK_LAUNCH(ctx);
   return NBW_OK;
 }

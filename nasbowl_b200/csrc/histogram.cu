@@ -187,6 +187,7 @@ extern "C" int nbw_hist_dense_i8(nbw_ctx* ctx, const uint32_t* ids, int64_t n_ce
                                  const uint32_t* thermo_base, int oa, int8_t* phi, int64_t ld_phi,
                                  int32_t* self_sim, void* stream) {
   if (!ctx) return NBW_ERR_INVALID;
+  NbwRange range("nbw_hist_dense_i8");
   NBW_REQUIRE(ctx, n_max == 8 || n_max == 16, "n_max must be 8 or 16");
   NBW_REQUIRE(ctx, col_off_h != nullptr, "col_off_h is NULL");
   NBW_REQUIRE(ctx, !oa || (thermo_base && label_off_h), "oa needs thermo_base and label_off_h");

@@ -586,6 +586,7 @@ extern "C" int nbw_gemm_f64(nbw_ctx* ctx, int trans_a, int trans_b, int64_t m, i
 extern "C" int nbw_chol_f64(nbw_ctx* ctx, const double* A, int64_t lda, int64_t n, double shift, double* L,
                             int64_t ldl, double* logdet_h, int* info_h, void* stream) {
   if (!ctx) return NBW_ERR_INVALID;
+  NbwRange range("nbw_chol_f64");
   NBW_REQUIRE(ctx, n > 0 && lda >= n && ldl >= n && A && L && info_h, "bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc = nbw_scratch_ensure(ctx, 1024, st);
@@ -615,6 +616,7 @@ extern "C" int nbw_gp_factor(nbw_ctx* ctx, const double* K, int64_t ldk, int64_t
                              const double* y, double* L, int64_t ldl, double* Linv, int64_t ldi,
                              double* alpha, double* stats_h, int* info_h, void* stream) {
   if (!ctx) return NBW_ERR_INVALID;
+  NbwRange range("nbw_gp_factor");
   NBW_REQUIRE(ctx, n > 0 && ldk >= n && ldl >= n && (Linv == nullptr || ldi >= n), "bad shape");
   NBW_REQUIRE(ctx, K && y && L && stats_h && info_h, "null pointer");
   NBW_REQUIRE(ctx, (Linv == nullptr) == (alpha == nullptr), "Linv and alpha are requested together");
@@ -640,10 +642,9 @@ extern "C" int nbw_gp_factor(nbw_ctx* ctx, const double* K, int64_t ldk, int64_t
   } else {
     // likelihood only: no inverse.  z is kept in shared memory, which bounds n for this path.
     NBW_REQUIRE(ctx, (size_t)n * sizeof(double) <= 200 * 1024, "likelihood-only factorisation handles n <= 25600");
-    static bool trsv_attr = false;
-    if (!trsv_attr) {
+    if (!(ctx->attr_set & NBW_ATTR_TRSV)) {
       NBW_CUDA(ctx, cudaFuncSetAttribute(trsv_lower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      trsv_attr = true;
+      ctx->attr_set |= NBW_ATTR_TRSV;
     }
     trsv_lower_kernel<<<1, 256, (size_t)n * sizeof(double), st>>>(L, ldl, n, y, z);
     NBW_CHECK_LAUNCH(ctx);
@@ -722,6 +723,7 @@ extern "C" int nbw_kernel_weight_grad(nbw_ctx* ctx, const double* Kinv, int64_t 
                                       const double* const* R_h, int64_t ldr, int n_kernels, double* grad_h,
                                       void* stream) {
   if (!ctx) return NBW_ERR_INVALID;
+  NbwRange range("nbw_kernel_weight_grad");
   NBW_REQUIRE(ctx, n > 0 && ldk >= n && ldn >= n && ldr >= n && n_kernels >= 1 && n_kernels <= 64, "bad shape");
   NBW_REQUIRE(ctx, n < 65536, "n too large for one block per row");
   NBW_REQUIRE(ctx, Kinv && alpha && N && inv_sqrt_diag && R_h && grad_h, "null pointer");

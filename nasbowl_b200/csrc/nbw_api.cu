@@ -36,6 +36,8 @@ extern "C" int nbw_destroy(nbw_ctx* ctx) {
   if (!ctx) return NBW_OK;
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->pinned_small) cudaFreeHost(ctx->pinned_small);
+  if (ctx->topk_blocks) cudaFree(ctx->topk_blocks);
+  if (ctx->piece_cands) cudaFree(ctx->piece_cands);
   if (ctx->pipe_ready) {
     cudaStreamDestroy(ctx->s_in);
     cudaStreamDestroy(ctx->s_out);
@@ -54,6 +56,18 @@ extern "C" int nbw_destroy(nbw_ctx* ctx) {
 extern "C" int nbw_wait_host_scores(nbw_ctx* ctx) {
   if (!ctx) return NBW_ERR_INVALID;
   NBW_CUDA(ctx, nbw_await_host_scores(ctx));
+  return NBW_OK;
+}
+
+// NVTX ranges for the host layer (fit / score state / broadcast / propose_location), so that a timeline shows the
+// BO iteration structure around the kernels; the C entry points open their own ranges (NbwRange).
+extern "C" int nbw_range_push(const char* name) { return nvtxRangePushA(name ? name : "nbw"); }
+extern "C" int nbw_range_pop(void) { return nvtxRangePop(); }
+
+extern "C" int nbw_profile_events(nbw_ctx* ctx, void* ev_start, void* ev_stop) {
+  if (!ctx) return NBW_ERR_INVALID;
+  ctx->prof_ev[0] = static_cast<cudaEvent_t>(ev_start);
+  ctx->prof_ev[1] = static_cast<cudaEvent_t>(ev_stop);
   return NBW_OK;
 }
 

@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -25,6 +26,24 @@ struct nbw_ctx {
   size_t stage_bytes;
   int pipe_ready;
   void* pinned_small;   // 16 KB of pinned host memory for small synchronous read-backs (top-k lists)
+  // per-device launch state (cudaFuncSetAttribute applies to the CURRENT device, and one process may
+  // hold a context per GPU: these flags must not be process-wide statics)
+  uint32_t attr_set;    // bit i = opt-in shared-memory size already set for kernel i on this device
+  int gram_max_pairs;   // co-resident CTA pairs of the Gram kernel on this device (0 = not queried yet)
+  cudaEvent_t prof_ev[2];   // optional caller-owned events recorded right before / after the scoring kernel
+  int packed_occ[32];   // resident CTAs per SM of each score_packed_kernel variant (0 = not queried yet)
+  void* piece_cands;    // per-piece top-n lists of the host-buffer entry points (score_pool.cu)
+  void* topk_blocks;    // per-CTA top-n lists of the fused scoring kernel (score_packed.cu)
+  size_t topk_blocks_bytes;
+};
+enum { NBW_ATTR_TRSV = 1u << 0, NBW_ATTR_SMALL_SORT = 1u << 1, NBW_ATTR_GRAM_SINGLE = 1u << 2, NBW_ATTR_CHOL_SMALL = 1u << 3,
+       NBW_ATTR_GRAM_PAIR = 1u << 8 /* << output mode: bits 8..11 */ };
+
+// NVTX range around a C-ABI entry point (visible in Nsight Systems / ncu --nvtx); header-only NVTX3,
+// a no-op costing one predicted branch when no tool is attached.
+struct NbwRange {
+  explicit NbwRange(const char* name) { nvtxRangePushA(name); }
+  ~NbwRange() { nvtxRangePop(); }
 };
 
 // Host scores written by the side stream are complete once this returns (called by every syncing
@@ -59,6 +78,23 @@ static inline cudaError_t nbw_await_host_scores(nbw_ctx* ctx) {
   do {                              \
     if (!(cond)) NBW_FAIL(ctx, NBW_ERR_INVALID, __VA_ARGS__); \
   } while (0)
+
+// One entry of a top-n list (topk.cu; the 16-byte wire format of the per-rank top-n all-gather).
+struct NbwCand {
+  float v;
+  int32_t pad;
+  int64_t idx;   // -1 = empty
+};
+// Tournament merge of `count` device candidates into the k best, left on the device in *result (scratch
+// memory, valid until the next scratch user).  topk.cu.
+int nbw_topk_merge_enqueue(nbw_ctx* ctx, const NbwCand* cands, int64_t count, int k, int distinct, NbwCand** result,
+                           cudaStream_t st);
+
+// Packed scoring path (score_packed.cu): applicability test and launch (k = 0: scores only).
+bool nbw_packed_applicable(const nbw_model* M);
+int nbw_score_packed(nbw_ctx* ctx, const nbw_model* M, const void* cells, int64_t n_cells, float* scores, double* mu64,
+                     double* var64, double* score64, int k, int distinct, int64_t index_base, void* out_cands,
+                     cudaStream_t st);
 
 // Scratch arena: grows on demand (syncs the stream before releasing the old block).
 int nbw_scratch_ensure(nbw_ctx* ctx, size_t bytes, cudaStream_t stream);
@@ -139,14 +175,17 @@ __host__ __device__ __forceinline__ uint32_t nbw_hash_b(uint64_t id64, const Lev
   return nbw_mix32(((uint32_t)id64 * 0x9e3779b1u) ^ ((uint32_t)(id64 >> 32) * 0x85ebca77u) ^ s.b_nbr);
 }
 // signature from the node's own hashes and the sums over its successors
+// (No finalising mix: the per-node hashes are already outputs of a full mixer, sums of them are uniform,
+// and the pool-side kernel fetches them from a table per dictionary id — a final mix would be the only
+// 64-bit mixing left on its critical path.)
 __host__ __device__ __forceinline__ uint64_t nbw_key_from(uint64_t ha_own, uint64_t sum_a, const LevelSalt& s) {
   const uint64_t own = ((ha_own << 27) | (ha_own >> 37)) * 0x9e3779b97f4a7c15ull + s.a_own;
-  const uint64_t k = nbw_mix_a(own + sum_a);
+  const uint64_t k = own + sum_a;
   return k == NBW_INVALID_KEY ? k - 1 : k;
 }
 __host__ __device__ __forceinline__ uint32_t nbw_chk_from(uint32_t hb_own, uint32_t sum_b, const LevelSalt& s) {
   const uint32_t own = ((hb_own << 13) | (hb_own >> 19)) * 0xcc9e2d51u + s.b_own;
-  return nbw_mix32(own + sum_b);
+  return own + sum_b;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -1,0 +1,718 @@
+// Fused pool scoring, second generation ("packed" path): WL relabelling -> dictionary lookup -> GP
+// posterior -> acquisition -> local top-n, one launch for the whole candidate pool.
+// Replaces, per candidate, GraphGP.predict (bayesopt/gp.py:240-283: a WL refit on train ∪ {candidate}
+// and an (n+1)^2 Gram per kernel of the sum, kernels/combine_kernels.py:36-56),
+// GraphExpectedImprovement.eval / GraphUpperConfidentBound.eval (bayesopt/acquisitions.py:59-80,130-138)
+// and the np.unique + argpartition selection of propose_location (:101-105).
+//
+// Same mathematics as score_pool.cu (prefix form: a node is described by its deepest dictionary label,
+// the posterior is a sum over node pairs of H = B'^T K_lam^-1 B'), different execution:
+//   * cells are packed DENSELY into the warp: a warp takes as many consecutive cells as fit its 32
+//     lanes (NAS-Bench cells average 4.4-5.1 nodes: 6-7 cells per pass instead of 4);
+//   * nodes that are in the dictionary FETCH their hashes (nbw_model.id_hash) instead of mixing
+//     64-bit integers; nodes outside it need no hash at all, because
+//   * label classes inside a cell are refined exactly from (previous class, multiset of the successors'
+//     previous classes) — 4 bits of count per class — at every level, not only on the stable suffix;
+//   * the dictionary probe is branch-free: one 16-byte load of four 32-bit tags, one of the entry;
+//   * a SUM of WL kernels is evaluated in one pass: part p reads its own record of the candidate and
+//     contributes one stacked label index per node; pairs run over (node, part) x (node, part);
+//   * every lane keeps the k best scores it produced; CTAs merge them at kernel end.
+#include "nbw_common.cuh"
+
+#include <math.h>
+#include <stdlib.h>
+
+#include <type_traits>
+
+namespace {
+
+constexpr int kPackThreads = 256;
+constexpr int kPackWarps = kPackThreads / 32;
+constexpr int kTopMax = 8;   // fused top-n handles k <= 8 (propose_location's default is 5)
+
+struct PartParams {
+  const uint16_t* level0_table;
+  const uint4* id_hash[NBW_MAX_LEVELS];
+  const uint4* tags[NBW_MAX_LEVELS];
+  const uint4* entries[NBW_MAX_LEVELS];
+  uint32_t bucket_mask[NBW_MAX_LEVELS];
+  uint64_t a_own[NBW_MAX_LEVELS];
+  uint32_t b_own[NBW_MAX_LEVELS];
+  int32_t loff[NBW_MAX_LEVELS];     // stacked offset of level l inside this part
+  double lw[NBW_MAX_LEVELS];        // level weights (kernel weight x layer weight)
+  double wsuf[NBW_MAX_LEVELS];      // sum of lw over the levels deeper than l
+  const int32_t* child;
+  const int32_t* final_label;
+  int32_t h, first_stable, undirected, rec_offset, label_base, pad;
+};
+
+struct PackedParams {
+  PartParams part[NBW_MAX_PARTS];
+  const double* H;
+  const double* w_mu;
+  int64_t ld_h;
+  int32_t zero_slot, rec_stride, acq, pad;
+  double lik, y_mean, y_std, incumbent, xi, beta;
+};
+
+template <int NMAX> struct SigOf;
+template <> struct SigOf<8> { typedef uint32_t type; };
+template <> struct SigOf<16> { typedef uint64_t type; };
+__device__ __forceinline__ uint32_t shfl_sig(uint32_t v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ uint64_t shfl_sig(uint64_t v, int src) { return shfl64(v, src); }
+
+__device__ __forceinline__ double shfl_down_f64(double v, int o) { return __shfl_down_sync(0xffffffffu, v, o); }
+
+// bit i = byte i of w is not 0xFF
+__device__ __forceinline__ uint32_t present_bits4(uint32_t w) {
+  return ((__vcmpne4(w, 0xFFFFFFFFu) & 0x08040201u) * 0x01010101u) >> 24;
+}
+
+// Posterior scaling + acquisition for one candidate (fp64): gp.py:272-280, acquisitions.py:68-77,136.
+__device__ __forceinline__ double finish_score(const PackedParams& P, double mu_acc, double q_acc, double kcc,
+                                               double& mu, double& var) {
+  const double inv_kcc = kcc > 0.0 ? 1.0 / kcc : 0.0;   // a cell without nodes falls back to the prior
+  const double mu_n = mu_acc * sqrt(inv_kcc);
+  const double q = q_acc * inv_kcc;
+  const double var_n = fmax(1.0 + P.lik - q, P.lik);    // gp.py:272-276 (diagonal)
+  const double sd = sqrt(var_n) * P.y_std;              // gp.py:278-279
+  var = sd * sd;                                        // gp.py:280
+  mu = mu_n * P.y_std + P.y_mean;                       // gp.py:277
+  if (P.acq == NBW_ACQ_UCB) return mu + P.beta * sd;    // acquisitions.py:136
+  if (P.acq == NBW_ACQ_MEAN) return mu;
+  const double d = mu - P.incumbent - P.xi;             // acquisitions.py:71-74
+  const double u = d / sd;
+  const double pdf = exp(-0.5 * u * u) * 0.3989422804014327;
+  const double cdf = 0.5 * erfc(-u * 0.7071067811865476);
+  double score = sd * pdf + d * cdf;
+  if (P.acq == NBW_ACQ_AEI) score *= 1.0 - sqrt(P.lik) / sqrt(P.lik + var);   // :75-77
+  return score;
+}
+
+__device__ __forceinline__ bool cand_better(float v, int i, float bv, int bi) {
+  if (i < 0) return false;
+  if (bi < 0) return true;
+  return v > bv || (v == bv && i < bi);
+}
+
+template <int NMAX, int NP, bool WEIGHTED, bool TOPK>
+__global__ void __launch_bounds__(kPackThreads, 3)
+score_packed_kernel(const __grid_constant__ PackedParams P, const uint8_t* __restrict__ cells, int64_t n_cells,
+                    int64_t per_warp, float* __restrict__ scores, double* __restrict__ mu64,
+                    double* __restrict__ var64, double* __restrict__ score64, NbwCand* __restrict__ block_cands,
+                    int k_top, int distinct, int64_t index_base) {
+  constexpr int PEEK = NMAX == 8 ? 8 : 4;     // cells inspected per pass
+  constexpr unsigned FULL = 0xffffffffu;
+  using SigT = typename SigOf<NMAX>::type;
+  using KccT = typename std::conditional<WEIGHTED, double, int>::type;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t c0 = warp_id * per_warp;
+  const int64_t c1 = (c0 + per_warp < n_cells) ? c0 + per_warp : n_cells;
+  const int64_t stride = P.rec_stride;
+  const int zero_slot = P.zero_slot;
+  const double* __restrict__ H = P.H;
+  const int64_t ldh = P.ld_h;
+
+  // results staged until (almost) every lane holds a candidate: the fp64 acquisition epilogue then runs
+  // with the warp full instead of once per pass with a few lanes
+  double st_mu = 0.0, st_q = 0.0, st_k = 0.0;
+  int64_t st_g = -1;
+  int staged = 0;
+  float tv[kTopMax];
+  int ti[kTopMax];
+#pragma unroll
+  for (int j = 0; j < kTopMax; ++j) { tv[j] = 0.f; ti[j] = -1; }
+
+  auto flush = [&]() {
+    if (st_g >= 0) {
+      double mu, var;
+      const double sc = finish_score(P, st_mu, st_q, st_k, mu, var);
+      const float scf = (float)sc;
+      if (scores) scores[st_g] = scf;
+      if (mu64) mu64[st_g] = mu;
+      if (var64) var64[st_g] = var;
+      if (score64) score64[st_g] = sc;
+      if (TOPK && scf == scf) {
+        // sorted insert into this lane's list: value desc, index asc; in distinct mode a value already in the
+        // list keeps its lowest index (warps walk their cells in ascending order, but stay order-agnostic)
+        const int ci0 = (int)st_g;
+        bool skip = false;
+        if (distinct) {
+#pragma unroll
+          for (int j = 0; j < kTopMax; ++j)
+            if (ti[j] >= 0 && tv[j] == scf) { ti[j] = ci0 < ti[j] ? ci0 : ti[j]; skip = true; }
+        }
+        if (!skip) {
+          float cv = scf;
+          int ci = ci0;
+#pragma unroll
+          for (int j = 0; j < kTopMax; ++j) {
+            if (j < k_top && ci >= 0 && cand_better(cv, ci, tv[j], ti[j])) {
+              const float ov = tv[j];
+              const int oi = ti[j];
+              tv[j] = cv; ti[j] = ci;
+              cv = ov; ci = oi;
+            }
+          }
+        }
+      }
+    }
+    st_g = -1;
+    staged = 0;
+  };
+
+  for (int64_t g = c0; g < c1;) {
+    // ---------------------------------------------------------------- pack cells into the warp
+    int allot = 0;
+    const bool peek = lane < PEEK && g + lane < c1;
+    if (peek) {
+      const uint8_t* rec = cells + (g + lane) * stride;
+      uint32_t pm = 0;
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        if (NMAX == 8) {
+          const uint2 w = __ldg(reinterpret_cast<const uint2*>(rec + P.part[p].rec_offset));
+          pm |= present_bits4(w.x) | (present_bits4(w.y) << 4);
+        } else {
+          const uint4 w = __ldg(reinterpret_cast<const uint4*>(rec + P.part[p].rec_offset));
+          pm |= present_bits4(w.x) | (present_bits4(w.y) << 4) | (present_bits4(w.z) << 8) | (present_bits4(w.w) << 12);
+        }
+      }
+      allot = pm ? 32 - __clz(pm) : 1;     // lanes up to the highest node; an empty cell still owns one lane
+    }
+    int end = allot;
+#pragma unroll
+    for (int o = 1; o < PEEK; o <<= 1) {
+      const int t = __shfl_up_sync(FULL, end, o);
+      if (lane >= o) end += t;
+    }
+    const bool fits = peek && end <= 32;
+    const int m = __popc(__ballot_sync(FULL, fits));          // `fits` is a prefix of the lanes; m >= 1
+    const int begin = end - allot;
+    const unsigned starts = __reduce_or_sync(FULL, fits ? (1u << begin) : 0u);
+    const int total = __shfl_sync(FULL, end, m - 1);
+    const unsigned below = starts & (FULL >> (31 - lane));
+    const bool active = lane < total;
+    const int k = active ? __popc(below) - 1 : 0;
+    const int sub_base = active ? 31 - __clz(below) : 0;
+    const int node = lane - sub_base;
+    const int my_n = __shfl_sync(FULL, allot, k);
+    const int64_t my_g = g + k;
+
+    int deep[NP];
+    KccT kacc = 0;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      const PartParams& Q = P.part[p];
+      const uint8_t* rec = cells + my_g * stride + Q.rec_offset;
+      const uint32_t label = active ? (uint32_t)__ldg(rec + node) : 0xFFu;
+      const bool present = label != 0xFFu;
+      uint32_t succ = 0u;
+      if (present)
+        succ = (NMAX == 8 ? (uint32_t)__ldg(rec + 8 + node) : (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(rec + 16) + node)) &
+               ((1u << my_n) - 1u);     // edges to absent nodes would reach into a neighbouring cell's lanes
+      if (Q.undirected) {
+        // kernels/weisfilerlehman.py:127-128: neighbourhood = successors and predecessors
+        uint32_t pred = 0u;
+#pragma unroll
+        for (int j = 0; j < NMAX; ++j) {
+          const uint32_t sj = __shfl_sync(FULL, succ, (sub_base + j) & 31);
+          pred |= (j < my_n && ((sj >> node) & 1u)) ? (1u << j) : 0u;
+        }
+        succ = present ? (succ | pred) : 0u;
+      }
+      // nodes that are an endpoint of no edge are not relabelled
+      const unsigned has_pred = __reduce_or_sync(FULL, succ << sub_base);
+      const bool endpoint = present && (succ != 0u || ((has_pred >> lane) & 1u));
+      const unsigned epm = __ballot_sync(FULL, endpoint) >> sub_base;
+
+      // ---- level 0: op code -> dense id (weisfeiler_lehman.py:430-441 in transform form)
+      const uint32_t d0 = present ? (uint32_t)__ldg(Q.level0_table + label) : 0xFFFFu;
+      bool in_dict = present && d0 != 0xFFFFu;
+      uint32_t dense_prev = in_dict ? d0 : 0u;
+      uint32_t cls = 0u;      // nodes of my cell (bit j) that share my label at the current level
+      {
+        const uint32_t mine = present ? label : (0x100u + (uint32_t)node);
+#pragma unroll
+        for (int j = 0; j < NMAX; ++j) {
+          const uint32_t other = __shfl_sync(FULL, mine, (sub_base + j) & 31);
+          cls |= (j < my_n && other == mine) ? (1u << j) : 0u;
+        }
+        if (!present) cls = 0u;
+      }
+      int cnt = __popc(cls);
+      KccT kss = 0;
+      if (present) kss = WEIGHTED ? (KccT)(Q.lw[0] * cnt) : (KccT)cnt;
+      int dp = in_dict ? Q.label_base + Q.loff[0] + (int)d0 : zero_slot;
+
+      // ---- levels 1..h
+      const int h = Q.h, fs = Q.first_stable;
+#pragma unroll 1
+      for (int l = 1; l <= h; ++l) {
+        const bool stable = fs != 0 && l >= fs;   // nbw_model.child: membership is inherited, no signature
+        const uint32_t rep = cls ? (uint32_t)(__ffs(cls) - 1) : 0u;
+        const uint32_t word = (in_dict ? 0x80000000u : 0u) | (rep << 24) | dense_prev;
+        const uint4* __restrict__ idh = Q.id_hash[l];
+        SigT sig = 0;           // multiset of the successors' previous classes, 4 bits of count per class
+        bool all_in = true;     // every successor's previous label is in the dictionary
+        uint64_t sum_a = 0;
+        uint32_t sum_b = 0;
+        uint32_t ms = succ;
+        constexpr int kUnrolled = NMAX == 8 ? 2 : 4;   // most nodes of the three search spaces have few successors
+#define NBW_SUCC_ROUND()                                                                       \
+  {                                                                                            \
+    const bool has = ms != 0u;                                                                 \
+    const int j = has ? (__ffs(ms) - 1) : node;                                                \
+    const uint32_t w = __shfl_sync(FULL, word, (sub_base + j) & 31);                           \
+    sig += has ? ((SigT)1 << (4 * ((w >> 24) & 15u))) : (SigT)0;                               \
+    all_in = all_in && (!has || (w >> 31));                                                    \
+    if (!stable && has && (w >> 31)) {                                                         \
+      const uint4 e = __ldg(idh + (w & 0xFFFFFFu));                                            \
+      sum_a += ((uint64_t)e.y << 32) | e.x;                                                    \
+      sum_b += e.z;                                                                            \
+    }                                                                                          \
+    ms &= ms - 1u;                                                                             \
+  }
+#pragma unroll
+        for (int t = 0; t < kUnrolled; ++t) NBW_SUCC_ROUND()
+#pragma unroll 1
+        for (int t = kUnrolled; t < NMAX; ++t) {
+          if (!__any_sync(FULL, ms != 0u)) break;
+          NBW_SUCC_ROUND()
+        }
+#undef NBW_SUCC_ROUND
+        // a credential can only be in the training dictionary if all its ids are
+        const bool cand = endpoint && in_dict && all_in;
+        bool seen = false;
+        uint32_t dense = 0u;
+        if (!stable) {
+          if (cand) {
+            const uint4 e = __ldg(idh + dense_prev);
+            LevelSalt salt;
+            salt.a_own = Q.a_own[l];
+            salt.b_own = Q.b_own[l];
+            const uint64_t key = nbw_key_from(((uint64_t)e.y << 32) | e.x, sum_a, salt);
+            const uint32_t chk = nbw_chk_from(e.z, sum_b, salt);
+            const uint32_t tag = (uint32_t)key, khi = (uint32_t)(key >> 32);
+            const uint32_t b = khi & Q.bucket_mask[l];
+            const uint4 t4 = __ldg(Q.tags[l] + b);
+            const int idx = t4.x == tag ? 0 : t4.y == tag ? 1 : t4.z == tag ? 2 : t4.w == tag ? 3 : -1;
+            if (idx >= 0) {
+              const uint4 en = __ldg(Q.entries[l] + 4 * (size_t)b + idx);
+              if (en.x == khi && en.y == chk) { seen = true; dense = en.z; }
+            }
+          }
+        } else if (cand) {
+          seen = true;
+          dense = (uint32_t)__ldg(Q.child + Q.loff[l - 1] + (int)dense_prev);
+        }
+        // classes refine exactly: same previous class, both relabelled, same successor-class multiset
+        const uint32_t cls_in = cls;
+        uint32_t rem = endpoint ? (cls & epm & ~(1u << node)) : 0u;
+        cls = endpoint ? (1u << node) : 0u;
+#pragma unroll 1
+        while (__any_sync(FULL, rem != 0u)) {
+          const bool has = rem != 0u;
+          const int j = has ? (__ffs(rem) - 1) : node;
+          const SigT other = shfl_sig(sig, (sub_base + j) & 31);
+          cls |= (has && other == sig) ? (1u << j) : 0u;
+          rem &= rem - 1u;
+        }
+        const bool changed = cls != cls_in || seen != in_dict;
+        in_dict = seen;
+        dense_prev = dense;
+        cnt = __popc(cls);
+        if (endpoint) kss += WEIGHTED ? (KccT)(Q.lw[l] * cnt) : (KccT)cnt;
+        if (seen) dp = Q.label_base + Q.loff[l] + (int)dense;
+        if (stable && l < h && !__any_sync(FULL, changed)) {
+          // A stable level reproduced (classes, membership) for every cell of this warp: all deeper levels
+          // apply the same map, so they reproduce it too; only the labels move down the child chain.
+          if (endpoint) kss += WEIGHTED ? (KccT)(Q.wsuf[l] * cnt) : (KccT)((h - l) * cnt);
+          if (seen) dp = __ldg(Q.final_label + Q.loff[l] + (int)dense);
+          break;
+        }
+      }
+      deep[p] = dp;
+      kacc += kss;
+    }
+
+    // ---------------------------------------------------------------- posterior (prefix form)
+    double mu_acc = 0.0, q_acc = 0.0;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      if (deep[p] != zero_slot) {
+        mu_acc += __ldg(P.w_mu + deep[p]);
+        const double* __restrict__ hrow = H + (int64_t)deep[p] * ldh;
+#pragma unroll
+        for (int p2 = p; p2 < NP; ++p2)
+          if (deep[p2] != zero_slot) {
+            const double gv = __ldg(hrow + deep[p2]);
+            q_acc += (p2 == p) ? gv : 2.0 * gv;
+          }
+      }
+    }
+#pragma unroll
+    for (int r = 1; r <= NMAX / 2; ++r) {
+      // unordered node pairs at cyclic distance r: the rotation meets each once (twice when 2r == my_n)
+      int t = node + r;
+      t -= (t >= my_n) ? my_n : 0;
+      const bool use = active && 2 * r <= my_n;
+      const double f = (2 * r == my_n) ? 1.0 : 2.0;
+      int pd[NP];
+#pragma unroll
+      for (int p2 = 0; p2 < NP; ++p2) pd[p2] = __shfl_sync(FULL, deep[p2], (sub_base + t) & 31);
+      if (use) {
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          if (deep[p] != zero_slot) {
+            const double* __restrict__ hrow = H + (int64_t)deep[p] * ldh;
+#pragma unroll
+            for (int p2 = 0; p2 < NP; ++p2)
+              if (pd[p2] != zero_slot) q_acc += f * __ldg(hrow + pd[p2]);
+          }
+        }
+      }
+    }
+    // segmented sums over the lanes of a cell: totals land on its first lane, in an order that
+    // depends on the node index only (scores do not depend on how cells were packed)
+    double kcc = (double)kacc;
+#pragma unroll
+    for (int o = 1; o < NMAX; o <<= 1) {
+      const double tm = shfl_down_f64(mu_acc, o), tq = shfl_down_f64(q_acc, o), tk = shfl_down_f64(kcc, o);
+      if (node + o < my_n) { mu_acc += tm; q_acc += tq; kcc += tk; }
+    }
+
+    // ---------------------------------------------------------------- stage the m finished cells
+    {
+      const int c = lane - staged;
+      const bool take = c >= 0 && c < m;
+      const int src = __shfl_sync(FULL, begin, take ? c : 0);
+      const double s_mu = __shfl_sync(FULL, mu_acc, src);
+      const double s_q = __shfl_sync(FULL, q_acc, src);
+      const double s_k = __shfl_sync(FULL, kcc, src);
+      if (take) { st_mu = s_mu; st_q = s_q; st_k = s_k; st_g = g + c; }
+    }
+    staged += m;
+    g += m;
+    if (staged > 32 - PEEK) flush();
+  }
+  if (staged > 0) flush();
+
+  if (TOPK) {
+    // ---- CTA tournament over the lanes' lists: k rounds of (value desc, index asc) arg-max with the
+    // distinct-by-value rule of acquisitions.py:101-105; the list of the block goes to block_cands
+    __shared__ float sv[kPackWarps];
+    __shared__ int si[kPackWarps];
+    __shared__ float best_v_s;
+    __shared__ int best_i_s;
+    const int warp = threadIdx.x >> 5;
+    float last_v = 0.f;
+    int last_i = -1;
+    for (int round = 0; round < k_top; ++round) {
+      float bv = 0.f;
+      int bi = -1;
+#pragma unroll
+      for (int j = 0; j < kTopMax; ++j) {
+        bool eligible = j < k_top && ti[j] >= 0;
+        if (eligible && last_i >= 0)
+          eligible = distinct ? (tv[j] < last_v) : (tv[j] < last_v || (tv[j] == last_v && ti[j] > last_i));
+        if (eligible && cand_better(tv[j], ti[j], bv, bi)) { bv = tv[j]; bi = ti[j]; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(FULL, bv, o);
+        const int oi = __shfl_xor_sync(FULL, bi, o);
+        if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+      }
+      if (lane == 0) { sv[warp] = bv; si[warp] = bi; }
+      __syncthreads();
+      if (warp == 0) {
+        bv = lane < kPackWarps ? sv[lane] : 0.f;
+        bi = lane < kPackWarps ? si[lane] : -1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(FULL, bv, o);
+          const int oi = __shfl_xor_sync(FULL, bi, o);
+          if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) {
+          best_v_s = bv;
+          best_i_s = bi;
+          NbwCand c;
+          c.v = bv;
+          c.pad = 0;
+          c.idx = bi >= 0 ? index_base + bi : -1;
+          block_cands[(int64_t)blockIdx.x * k_top + round] = c;
+        }
+      }
+      __syncthreads();
+      last_v = best_v_s;
+      last_i = best_i_s;
+      __syncthreads();
+      if (last_i < 0) {   // block exhausted: the rest of its list is empty
+        for (int r = round + 1 + threadIdx.x; r < k_top; r += kPackThreads) {
+          NbwCand c;
+          c.v = 0.f;
+          c.pad = 0;
+          c.idx = -1;
+          block_cands[(int64_t)blockIdx.x * k_top + r] = c;
+        }
+        break;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ dictionary forms of the packed path
+__global__ void id_hash_kernel(int64_t n_ids, LevelSalt salt, uint4* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_ids) return;
+  const uint64_t ha = nbw_hash_a((uint64_t)i, salt);
+  const uint32_t hb = nbw_hash_b((uint64_t)i, salt);
+  out[i] = make_uint4((uint32_t)ha, (uint32_t)(ha >> 32), hb, 0u);
+}
+
+__global__ void bucket_insert_kernel(const uint64_t* __restrict__ uniq_keys, const uint64_t* __restrict__ uniq_chks,
+                                     int64_t n_unique, uint32_t* __restrict__ tags, uint4* __restrict__ entries,
+                                     uint32_t mask, uint32_t* __restrict__ fill, uint32_t* __restrict__ flags) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_unique) return;
+  const uint64_t key = uniq_keys[i];
+  const uint32_t tag = (uint32_t)key, khi = (uint32_t)(key >> 32);
+  const uint32_t b = khi & mask;
+  const uint32_t pos = atomicAdd(fill + b, 1u);
+  if (pos >= 4u) {
+    atomicOr(flags, 1u);
+    return;
+  }
+  tags[4 * (size_t)b + pos] = tag;
+  entries[4 * (size_t)b + pos] = make_uint4(khi, (uint32_t)uniq_chks[i], (uint32_t)i, 0u);
+}
+
+// two keys of one bucket with the same tag (or a real tag 0 behind an empty slot) would make the first
+// tag match ambiguous: report it, the caller rebuilds with more buckets
+__global__ void bucket_check_kernel(const uint32_t* __restrict__ tags, const uint32_t* __restrict__ fill,
+                                    int64_t n_buckets, uint32_t* __restrict__ flags) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_buckets) return;
+  const uint32_t f = fill[b] < 4u ? fill[b] : 4u;
+  bool dup = false;
+  for (uint32_t i = 0; i < f; ++i)
+    for (uint32_t j = i + 1; j < f; ++j) dup = dup || tags[4 * b + i] == tags[4 * b + j];
+  if (dup) atomicOr(flags, 2u);
+}
+
+// ------------------------------------------------------------------ host side
+int fill_part(nbw_ctx* ctx, const nbw_model* M, PartParams& Q) {
+  NBW_REQUIRE(ctx, M->level0_table != nullptr, "model.level0_table is NULL");
+  NBW_REQUIRE(ctx, M->h >= 0 && M->h < NBW_MAX_LEVELS, "model.h out of range");
+  NBW_REQUIRE(ctx, M->first_stable == 0 || (M->first_stable >= 3 && M->first_stable <= M->h && M->child && M->final_label),
+              "model.first_stable needs child and final_label tables");
+  memset(&Q, 0, sizeof(Q));
+  Q.level0_table = M->level0_table;
+  Q.h = M->h;
+  Q.first_stable = M->first_stable;
+  Q.undirected = M->undirected;
+  Q.rec_offset = M->rec_offset;
+  Q.label_base = M->label_base;
+  Q.child = M->child;
+  Q.final_label = M->final_label;
+  double suffix = 0.0;
+  for (int l = M->h; l >= 0; --l) {
+    Q.lw[l] = M->weighted ? M->level_weight[l] : 1.0;
+    Q.wsuf[l] = suffix;
+    suffix += Q.lw[l];
+  }
+  for (int l = 0; l <= M->h; ++l) {
+    Q.loff[l] = M->label_off[l];
+    if (l == 0) continue;
+    const LevelSalt s = nbw_level_salt(M->seed, l);
+    Q.a_own[l] = s.a_own;
+    Q.b_own[l] = s.b_own;
+    const bool hashed = M->first_stable == 0 || l < M->first_stable;
+    if (hashed) {
+      NBW_REQUIRE(ctx, M->id_hash[l] && M->bucket_tags[l] && M->bucket_entries[l], "model level %d lacks the packed-path tables", l);
+      NBW_REQUIRE(ctx, ((M->bucket_mask[l] + 1) & M->bucket_mask[l]) == 0, "bucket count must be a power of two");
+    }
+    Q.id_hash[l] = static_cast<const uint4*>(M->id_hash[l]);
+    Q.tags[l] = static_cast<const uint4*>(M->bucket_tags[l]);
+    Q.entries[l] = static_cast<const uint4*>(M->bucket_entries[l]);
+    Q.bucket_mask[l] = M->bucket_mask[l];
+  }
+  return NBW_OK;
+}
+
+template <int NMAX, int NP, bool WEIGHTED, bool TOPK>
+int launch_variant(nbw_ctx* ctx, int variant, const PackedParams& P, const uint8_t* cells, int64_t n, float* scores,
+                   double* mu64, double* var64, double* score64, int k, int distinct, int64_t index_base,
+                   NbwCand* out_cands, cudaStream_t st) {
+  auto kern = score_packed_kernel<NMAX, NP, WEIGHTED, TOPK>;
+  if (!ctx->packed_occ[variant]) {
+    int occ = 0;
+    NBW_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kPackThreads, 0));
+    NBW_REQUIRE(ctx, occ >= 1, "score_packed_kernel does not fit this device");
+    ctx->packed_occ[variant] = occ;
+  }
+  // one resident wave of long-lived warps, each walking a contiguous share of the pool
+  constexpr int kMinCellsPerWarp = NMAX == 8 ? 32 : 8;
+  int64_t grid = (int64_t)ctx->sm_count * ctx->packed_occ[variant];
+  const int64_t need = (n + (int64_t)kPackWarps * kMinCellsPerWarp - 1) / ((int64_t)kPackWarps * kMinCellsPerWarp);
+  if (need < grid) grid = need;
+  if (grid < 1) grid = 1;
+  const int64_t warps = grid * kPackWarps;
+  const int64_t per_warp = (n + warps - 1) / warps;
+  NbwCand* blocks = nullptr;
+  if (TOPK) {
+    const size_t bytes = sizeof(NbwCand) * (size_t)ctx->sm_count * 32 * kTopMax;
+    if (ctx->topk_blocks_bytes < bytes) {
+      if (ctx->topk_blocks) {
+        NBW_CUDA(ctx, cudaStreamSynchronize(st));
+        NBW_CUDA(ctx, cudaFree(ctx->topk_blocks));
+        ctx->topk_blocks = nullptr;
+        ctx->topk_blocks_bytes = 0;
+      }
+      NBW_CUDA(ctx, cudaMalloc(&ctx->topk_blocks, bytes));
+      ctx->topk_blocks_bytes = bytes;
+    }
+    blocks = static_cast<NbwCand*>(ctx->topk_blocks);
+  }
+  if (ctx->prof_ev[0]) NBW_CUDA(ctx, cudaEventRecord(ctx->prof_ev[0], st));
+  kern<<<(unsigned)grid, kPackThreads, 0, st>>>(P, cells, n, per_warp, scores, mu64, var64, score64, blocks, k, distinct,
+                                               index_base);
+  NBW_CHECK_LAUNCH(ctx);
+  if (ctx->prof_ev[1]) NBW_CUDA(ctx, cudaEventRecord(ctx->prof_ev[1], st));
+  if (TOPK) {
+    NbwCand* res = nullptr;
+    int rc = nbw_topk_merge_enqueue(ctx, blocks, grid * k, k, distinct, &res, st);
+    if (rc) return rc;
+    NBW_CUDA(ctx, cudaMemcpyAsync(out_cands, res, sizeof(NbwCand) * k, cudaMemcpyDeviceToDevice, st));
+  }
+  return NBW_OK;
+}
+
+template <int NMAX, bool TOPK>
+int launch_parts(nbw_ctx* ctx, int np, bool weighted, const PackedParams& P, const uint8_t* cells, int64_t n,
+                 float* scores, double* mu64, double* var64, double* score64, int k, int distinct, int64_t index_base,
+                 NbwCand* out_cands, cudaStream_t st) {
+  const int base = (NMAX == 16 ? 16 : 0) + (TOPK ? 8 : 0);
+#define NBW_ARGS P, cells, n, scores, mu64, var64, score64, k, distinct, index_base, out_cands, st
+  if (np == 1 && !weighted) return launch_variant<NMAX, 1, false, TOPK>(ctx, base + 0, NBW_ARGS);
+  if (np == 1) return launch_variant<NMAX, 1, true, TOPK>(ctx, base + 1, NBW_ARGS);
+  if (np == 2) return launch_variant<NMAX, 2, true, TOPK>(ctx, base + 2, NBW_ARGS);
+  if (np == 3) return launch_variant<NMAX, 3, true, TOPK>(ctx, base + 3, NBW_ARGS);
+  if (np == 4) return launch_variant<NMAX, 4, true, TOPK>(ctx, base + 4, NBW_ARGS);
+#undef NBW_ARGS
+  NBW_FAIL(ctx, NBW_ERR_UNSUPPORTED, "the fused pool path takes sums of up to %d kernels", NBW_MAX_PARTS);
+}
+
+}  // namespace
+
+// Is this model scored by the packed kernel?  (Linear kernels in prefix form with the packed-path tables.)
+bool nbw_packed_applicable(const nbw_model* M) {
+  if (!M || M->oa || !M->H || !M->w_mu_prefix) return false;
+  if (getenv("NBW_SCORE_LEGACY")) return false;     // diagnostic switch: first-generation kernel (single part only)
+  const bool hashed1 = M->h >= 1 && (M->first_stable == 0 || 1 < M->first_stable);
+  return !hashed1 || M->bucket_tags[1] != nullptr;
+}
+
+int nbw_score_packed(nbw_ctx* ctx, const nbw_model* M, const void* cells, int64_t n_cells, float* scores, double* mu64,
+                     double* var64, double* score64, int k, int distinct, int64_t index_base, void* out_cands,
+                     cudaStream_t st) {
+  PackedParams P;
+  memset(&P, 0, sizeof(P));
+  int np = 0;
+  bool weighted = false;
+  const int n_max = M->n_max;
+  NBW_REQUIRE(ctx, n_max == 8 || n_max == 16, "model.n_max must be 8 or 16");
+  const int rec = n_max == 8 ? 16 : 48;
+  for (const nbw_model* part = M; part; part = static_cast<const nbw_model*>(part->next)) {
+    NBW_REQUIRE(ctx, np < NBW_MAX_PARTS, "the fused pool path takes sums of up to %d kernels", NBW_MAX_PARTS);
+    NBW_REQUIRE(ctx, part->n_max == n_max && !part->oa, "parts of a sum must share n_max and be linear WL kernels");
+    int rc = fill_part(ctx, part, P.part[np]);
+    if (rc) return rc;
+    weighted = weighted || part->weighted != 0;
+    ++np;
+  }
+  weighted = weighted || np > 1;
+  P.H = M->H;
+  P.w_mu = M->w_mu_prefix;
+  P.ld_h = M->ld_h;
+  P.zero_slot = M->n_labels;
+  P.rec_stride = M->rec_stride > 0 ? M->rec_stride : rec;
+  NBW_REQUIRE(ctx, P.ld_h >= (int64_t)P.zero_slot + 1, "model.ld_h must be >= n_labels + 1");
+  NBW_REQUIRE(ctx, P.rec_stride % 16 == 0, "rec_stride must be a multiple of 16 bytes");
+  for (int p = 0; p < np; ++p)
+    NBW_REQUIRE(ctx, P.part[p].rec_offset % 16 == 0 && P.part[p].rec_offset + rec <= P.rec_stride,
+                "part %d: rec_offset outside the candidate record", p);
+  NBW_REQUIRE(ctx, M->acq >= NBW_ACQ_EI && M->acq <= NBW_ACQ_MEAN, "unknown acquisition");
+  P.acq = M->acq;
+  P.lik = M->lik; P.y_mean = M->y_mean; P.y_std = M->y_std;
+  P.incumbent = M->incumbent; P.xi = M->xi; P.beta = M->beta;
+  const uint8_t* c = static_cast<const uint8_t*>(cells);
+  NbwCand* oc = static_cast<NbwCand*>(out_cands);
+  if (k > 0) {
+    NBW_REQUIRE(ctx, k <= kTopMax && n_cells < ((int64_t)1 << 31), "fused top-n handles k <= %d and < 2^31 cells per launch", kTopMax);
+    if (n_max == 8) return launch_parts<8, true>(ctx, np, weighted, P, c, n_cells, scores, mu64, var64, score64, k, distinct, index_base, oc, st);
+    return launch_parts<16, true>(ctx, np, weighted, P, c, n_cells, scores, mu64, var64, score64, k, distinct, index_base, oc, st);
+  }
+  if (n_max == 8) return launch_parts<8, false>(ctx, np, weighted, P, c, n_cells, scores, mu64, var64, score64, 0, 0, 0, nullptr, st);
+  return launch_parts<16, false>(ctx, np, weighted, P, c, n_cells, scores, mu64, var64, score64, 0, 0, 0, nullptr, st);
+}
+
+extern "C" int nbw_model_build_id_hash(nbw_ctx* ctx, int64_t n_ids, uint64_t seed, int level, void* out, void* stream) {
+  if (!ctx) return NBW_ERR_INVALID;
+  NBW_REQUIRE(ctx, n_ids >= 0 && level >= 1 && level < NBW_MAX_LEVELS, "bad n_ids / level");
+  if (n_ids == 0) return NBW_OK;
+  NBW_REQUIRE(ctx, out != nullptr, "out is NULL");
+  id_hash_kernel<<<(unsigned)((n_ids + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      n_ids, nbw_level_salt(seed, level), static_cast<uint4*>(out));
+  NBW_CHECK_LAUNCH(ctx);
+  return NBW_OK;
+}
+
+extern "C" int nbw_model_build_buckets(nbw_ctx* ctx, const uint64_t* uniq_keys, const uint64_t* uniq_chks,
+                                       int64_t n_unique, void* tags, void* entries, int64_t n_buckets, uint32_t* flags,
+                                       void* stream) {
+  if (!ctx) return NBW_ERR_INVALID;
+  NBW_REQUIRE(ctx, n_buckets > 0 && (n_buckets & (n_buckets - 1)) == 0 && n_buckets <= ((int64_t)1 << 28),
+              "n_buckets must be a power of two");
+  NBW_REQUIRE(ctx, n_unique >= 0 && tags && entries && flags, "bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = nbw_scratch_ensure(ctx, Carver::pad(sizeof(uint32_t) * (size_t)n_buckets) + 1024, st);
+  if (rc) return rc;
+  Carver cv(ctx->scratch);
+  uint32_t* fill = cv.take<uint32_t>(n_buckets);
+  NBW_CUDA(ctx, cudaMemsetAsync(fill, 0, sizeof(uint32_t) * (size_t)n_buckets, st));
+  NBW_CUDA(ctx, cudaMemsetAsync(tags, 0, 16 * (size_t)n_buckets, st));
+  NBW_CUDA(ctx, cudaMemsetAsync(entries, 0xFF, 64 * (size_t)n_buckets, st));
+  if (n_unique == 0) return NBW_OK;
+  NBW_REQUIRE(ctx, uniq_keys && uniq_chks, "null pointer");
+  bucket_insert_kernel<<<(unsigned)((n_unique + 255) / 256), 256, 0, st>>>(
+      uniq_keys, uniq_chks, n_unique, static_cast<uint32_t*>(tags), static_cast<uint4*>(entries),
+      (uint32_t)(n_buckets - 1), fill, flags);
+  NBW_CHECK_LAUNCH(ctx);
+  bucket_check_kernel<<<(unsigned)((n_buckets + 255) / 256), 256, 0, st>>>(static_cast<const uint32_t*>(tags), fill,
+                                                                          n_buckets, flags);
+  NBW_CHECK_LAUNCH(ctx);
+  return NBW_OK;
+}
+
+extern "C" int nbw_score_pool_topk(nbw_ctx* ctx, const nbw_model* model_h, const void* cells, int64_t n_cells,
+                                   float* scores, int k, int distinct, int64_t index_base, void* out_cands,
+                                   void* stream) {
+  if (!ctx) return NBW_ERR_INVALID;
+  NbwRange range("nbw_score_pool_topk");
+  NBW_REQUIRE(ctx, model_h != nullptr && out_cands != nullptr, "null pointer");
+  NBW_REQUIRE(ctx, k >= 1 && n_cells >= 0, "bad k / n_cells");
+  if (k > kTopMax || !nbw_packed_applicable(model_h))
+    NBW_FAIL(ctx, NBW_ERR_UNSUPPORTED, "fused top-n needs the packed scoring path and k <= %d", kTopMax);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n_cells == 0) {   // an empty shard contributes k empty entries (index -1)
+    NBW_CUDA(ctx, cudaMemsetAsync(out_cands, 0xFF, sizeof(NbwCand) * k, st));
+    return NBW_OK;
+  }
+  NBW_REQUIRE(ctx, cells != nullptr, "cells is NULL");
+  return nbw_score_packed(ctx, model_h, cells, n_cells, scores, nullptr, nullptr, nullptr, k, distinct, index_base,
+                          out_cands, st);
+}

@@ -111,7 +111,7 @@ __device__ __forceinline__ void finish_candidate(const nbw_model& M, double mu_a
                                                  float* __restrict__ scores, double* __restrict__ mu64,
                                                  double* __restrict__ var64, double* __restrict__ score64) {
   if (g < 0) return;
-  const double inv_kcc = 1.0 / (double)kcc_i;
+  const double inv_kcc = kcc_i > 0 ? 1.0 / (double)kcc_i : 0.0;   // a cell without nodes falls back to the prior
   const double mu_n = mu_acc * sqrt(inv_kcc);
   const double q = q_acc * inv_kcc;
   const double var_n = fmax(1.0 + M.lik - q, M.lik);    // gp.py:272-276 (diagonal)
@@ -412,6 +412,7 @@ int launch_levels(nbw_ctx* ctx, const nbw_model& M, const uint8_t* cells, int64_
     score_pool_kernel<NMAX, NLV, MODE><<<grid, kScoreThreads, 0, st>>>(P, cells, n, scores, mu64, var64, \
                                                                     score64, phi, ld_phi, self_sim); \
     break;
+  if (ctx->prof_ev[0]) NBW_CUDA(ctx, cudaEventRecord(ctx->prof_ev[0], st));
   switch (M.h + 1) {
     NBW_LAUNCH_NL(1)
     NBW_LAUNCH_NL(2)
@@ -426,6 +427,7 @@ int launch_levels(nbw_ctx* ctx, const nbw_model& M, const uint8_t* cells, int64_
   }
 #undef NBW_LAUNCH_NL
   NBW_CHECK_LAUNCH(ctx);
+  if (ctx->prof_ev[1]) NBW_CUDA(ctx, cudaEventRecord(ctx->prof_ev[1], st));
   return NBW_OK;
 }
 
@@ -447,6 +449,12 @@ int check_model(nbw_ctx* ctx, const nbw_model* M, bool need_posterior) {
   }
   if (need_posterior) NBW_REQUIRE(ctx, M->acq >= NBW_ACQ_EI && M->acq <= NBW_ACQ_MEAN, "unknown acquisition");
   return NBW_OK;
+}
+
+// the first-generation kernel scores one kernel with unit level weights on plain records
+bool legacy_ok(const nbw_model* M) {
+  return M->next == nullptr && !M->weighted && !M->undirected && M->rec_offset == 0 &&
+         (M->rec_stride == 0 || M->rec_stride == (M->n_max == 8 ? 16 : 48));
 }
 
 }  // namespace
@@ -471,6 +479,7 @@ extern "C" int nbw_model_build_table(nbw_ctx* ctx, const uint64_t* uniq_keys, co
 extern "C" int nbw_score_pool(nbw_ctx* ctx, const nbw_model* model_h, const void* cells, int64_t n_cells,
                               float* scores, double* mu64, double* var64, double* score64, void* stream) {
   if (!ctx) return NBW_ERR_INVALID;
+  NbwRange range("nbw_score_pool");
   int rc = check_model(ctx, model_h, true);
   if (rc) return rc;
   NBW_REQUIRE(ctx, n_cells >= 0, "n_cells negative");
@@ -478,6 +487,9 @@ extern "C" int nbw_score_pool(nbw_ctx* ctx, const nbw_model* model_h, const void
   NBW_REQUIRE(ctx, cells && scores, "null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const uint8_t* c = static_cast<const uint8_t*>(cells);
+  if (nbw_packed_applicable(model_h))
+    return nbw_score_packed(ctx, model_h, cells, n_cells, scores, mu64, var64, score64, 0, 0, 0, nullptr, st);
+  NBW_REQUIRE(ctx, legacy_ok(model_h), "sums of kernels / weighted levels / per-part records need the packed scoring path");
   const bool prefix = model_h->H != nullptr && !model_h->oa;
   if (prefix)
     NBW_REQUIRE(ctx, model_h->w_mu_prefix && model_h->n_labels > 0 && model_h->ld_h >= model_h->n_labels + 1,
@@ -493,6 +505,7 @@ extern "C" int nbw_score_pool(nbw_ctx* ctx, const nbw_model* model_h, const void
 extern "C" int nbw_pool_features(nbw_ctx* ctx, const nbw_model* model_h, const void* cells, int64_t n_cells,
                                  int8_t* phi, int64_t ld_phi, int32_t* self_sim, void* stream) {
   if (!ctx) return NBW_ERR_INVALID;
+  NbwRange range("nbw_pool_features");
   int rc = check_model(ctx, model_h, false);
   if (rc) return rc;
   NBW_REQUIRE(ctx, n_cells >= 0 && ld_phi >= model_h->n_features, "bad shape");
@@ -507,7 +520,12 @@ extern "C" int nbw_pool_features(nbw_ctx* ctx, const nbw_model* model_h, const v
 }
 
 namespace {
-int score_dispatch(nbw_ctx* ctx, const nbw_model& M, const uint8_t* dev, int64_t n, float* scores, cudaStream_t st) {
+int score_dispatch(nbw_ctx* ctx, const nbw_model& M, const uint8_t* dev, int64_t n, float* scores, cudaStream_t st,
+                   int k = 0, int distinct = 0, int64_t index_base = 0, void* out_cands = nullptr) {
+  if (nbw_packed_applicable(&M))
+    return nbw_score_packed(ctx, &M, dev, n, scores, nullptr, nullptr, nullptr, k, distinct, index_base, out_cands, st);
+  NBW_REQUIRE(ctx, k == 0, "fused top-n needs the packed scoring path");
+  NBW_REQUIRE(ctx, legacy_ok(&M), "sums of kernels / weighted levels / per-part records need the packed scoring path");
   const bool prefix = M.H != nullptr && !M.oa;
   if (M.n_max == 8)
     return prefix ? launch_levels<8, 2>(ctx, M, dev, n, scores, nullptr, nullptr, nullptr, nullptr, 0, nullptr, st)
@@ -549,14 +567,60 @@ int pipe_end(nbw_ctx* ctx, bool copied) {
   }
   return NBW_OK;
 }
+// device buffer for the per-piece top-n lists of the host-buffer entry points (64 pieces x 8 entries)
+int piece_cands(nbw_ctx* ctx, NbwCand** out) {
+  if (!ctx->piece_cands) NBW_CUDA(ctx, cudaMalloc(&ctx->piece_cands, sizeof(NbwCand) * 64 * 8));
+  *out = static_cast<NbwCand*>(ctx->piece_cands);
+  return NBW_OK;
+}
+int merge_pieces(nbw_ctx* ctx, NbwCand* lists, int pieces, int k, int distinct, void* out_cands, cudaStream_t st) {
+  NbwCand* res = nullptr;
+  int rc = nbw_topk_merge_enqueue(ctx, lists, (int64_t)pieces * k, k, distinct, &res, st);
+  if (rc) return rc;
+  NBW_CUDA(ctx, cudaMemcpyAsync(out_cands, res, sizeof(NbwCand) * k, cudaMemcpyDeviceToDevice, st));
+  return NBW_OK;
+}
 }  // namespace
+
+static int score_pool_mapped_impl(nbw_ctx* ctx, const nbw_model* model_h, const void* cells_h, int64_t n_cells,
+                                  float* scores_h, float* scores_dev, int pieces, int k, int distinct,
+                                  int64_t index_base, void* out_cands, void* stream);
+static int score_pool_host_impl(nbw_ctx* ctx, const nbw_model* model_h, const void* cells_h, int64_t n_cells,
+                                float* scores_h, float* scores_dev, int chunks, int k, int distinct,
+                                int64_t index_base, void* out_cands, void* stream);
+
+extern "C" int nbw_score_pool_mapped(nbw_ctx* ctx, const nbw_model* model_h, const void* cells_h, int64_t n_cells,
+                                     float* scores_h, float* scores_dev, int pieces, void* stream) {
+  if (!ctx) return NBW_ERR_INVALID;
+  NbwRange range("nbw_score_pool_mapped");
+  return score_pool_mapped_impl(ctx, model_h, cells_h, n_cells, scores_h, scores_dev, pieces, 0, 0, 0, nullptr, stream);
+}
+extern "C" int nbw_score_pool_host(nbw_ctx* ctx, const nbw_model* model_h, const void* cells_h, int64_t n_cells,
+                                   float* scores_h, float* scores_dev, int chunks, void* stream) {
+  if (!ctx) return NBW_ERR_INVALID;
+  NbwRange range("nbw_score_pool_host");
+  return score_pool_host_impl(ctx, model_h, cells_h, n_cells, scores_h, scores_dev, chunks, 0, 0, 0, nullptr, stream);
+}
+extern "C" int nbw_propose_host(nbw_ctx* ctx, const nbw_model* model_h, const void* cells_h, int64_t n_cells,
+                                float* scores_h, float* scores_dev, int mapped, int pieces, int k, int distinct,
+                                int64_t index_base, void* out_cands, void* stream) {
+  if (!ctx) return NBW_ERR_INVALID;
+  NbwRange range("nbw_propose_host");
+  NBW_REQUIRE(ctx, k >= 1 && k <= 8 && out_cands != nullptr, "k must be in [1, 8] and out_cands non-NULL");
+  if (n_cells == 0) {
+    NBW_CUDA(ctx, cudaMemsetAsync(out_cands, 0xFF, sizeof(NbwCand) * k, static_cast<cudaStream_t>(stream)));
+    return NBW_OK;
+  }
+  if (mapped) return score_pool_mapped_impl(ctx, model_h, cells_h, n_cells, scores_h, scores_dev, pieces, k, distinct, index_base, out_cands, stream);
+  return score_pool_host_impl(ctx, model_h, cells_h, n_cells, scores_h, scores_dev, pieces, k, distinct, index_base, out_cands, stream);
+}
 
 // Mapped form: the kernel reads pinned host records through the device alias of the host pointer.
 // (Letting the kernel also store the scores into mapped host memory was measured and is slower than
 // one D2H copy of the [M] f32 vector: 0.74 ms vs 0.60 ms per 1M candidates.)
-extern "C" int nbw_score_pool_mapped(nbw_ctx* ctx, const nbw_model* model_h, const void* cells_h, int64_t n_cells,
-                                     float* scores_h, float* scores_dev, int pieces, void* stream) {
-  if (!ctx) return NBW_ERR_INVALID;
+static int score_pool_mapped_impl(nbw_ctx* ctx, const nbw_model* model_h, const void* cells_h, int64_t n_cells,
+                                  float* scores_h, float* scores_dev, int pieces, int k, int distinct,
+                                  int64_t index_base, void* out_cands, void* stream) {
   int rc = check_model(ctx, model_h, true);
   if (rc) return rc;
   NBW_REQUIRE(ctx, n_cells >= 0 && pieces >= 1 && pieces <= 64, "bad n_cells / pieces");
@@ -569,9 +633,15 @@ extern "C" int nbw_score_pool_mapped(nbw_ctx* ctx, const nbw_model* model_h, con
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   rc = pipe_begin(ctx, st);
   if (rc) return rc;
-  const int64_t rec = model_h->n_max == 8 ? 16 : 48;
+  const int64_t rec = model_h->rec_stride > 0 ? model_h->rec_stride : (model_h->n_max == 8 ? 16 : 48);
   const uint8_t* src = static_cast<const uint8_t*>(attr.devicePointer);
   const int64_t per = (n_cells + pieces - 1) / pieces;
+  NbwCand* lists = nullptr;
+  int used = 0;
+  if (k > 0) {
+    rc = piece_cands(ctx, &lists);
+    if (rc) return rc;
+  }
   if (scores_h) {
     NBW_CUDA(ctx, cudaEventRecord(ctx->ev_done[0], st));
     NBW_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_done[0], 0));
@@ -579,8 +649,10 @@ extern "C" int nbw_score_pool_mapped(nbw_ctx* ctx, const nbw_model* model_h, con
   for (int c = 0; c < pieces; ++c) {
     const int64_t lo = (int64_t)c * per, hi = (lo + per < n_cells) ? lo + per : n_cells;
     if (lo >= hi) break;
-    rc = score_dispatch(ctx, *model_h, src + lo * rec, hi - lo, scores_dev + lo, st);
+    rc = score_dispatch(ctx, *model_h, src + lo * rec, hi - lo, scores_dev + lo, st, k, distinct, index_base + lo,
+                        lists ? lists + (size_t)c * k : nullptr);
     if (rc) return rc;
+    ++used;
     if (scores_h) {
       NBW_CUDA(ctx, cudaEventRecord(ctx->ev_done[c & 1], st));
       NBW_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_done[c & 1], 0));
@@ -588,21 +660,25 @@ extern "C" int nbw_score_pool_mapped(nbw_ctx* ctx, const nbw_model* model_h, con
                                     cudaMemcpyDeviceToHost, ctx->s_out));
     }
   }
+  if (k > 0) {
+    rc = merge_pieces(ctx, lists, used, k, distinct, out_cands, st);
+    if (rc) return rc;
+  }
   return pipe_end(ctx, scores_h != nullptr);
 }
 
 // Host-buffer form: the pool lives in host memory (pinned for full overlap).  Chunk i+1's H2D copy,
 // chunk i's kernel and chunk i-1's D2H copy of the scores run on three streams.
-extern "C" int nbw_score_pool_host(nbw_ctx* ctx, const nbw_model* model_h, const void* cells_h, int64_t n_cells,
-                                   float* scores_h, float* scores_dev, int chunks, void* stream) {
-  if (!ctx) return NBW_ERR_INVALID;
+static int score_pool_host_impl(nbw_ctx* ctx, const nbw_model* model_h, const void* cells_h, int64_t n_cells,
+                                float* scores_h, float* scores_dev, int chunks, int k, int distinct,
+                                int64_t index_base, void* out_cands, void* stream) {
   int rc = check_model(ctx, model_h, true);
   if (rc) return rc;
   NBW_REQUIRE(ctx, n_cells >= 0 && chunks >= 1 && chunks <= 64, "bad n_cells / chunks");
   if (n_cells == 0) return NBW_OK;
   NBW_REQUIRE(ctx, cells_h && scores_dev, "null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int64_t rec = model_h->n_max == 8 ? 16 : 48;
+  const int64_t rec = model_h->rec_stride > 0 ? model_h->rec_stride : (model_h->n_max == 8 ? 16 : 48);
   rc = pipe_begin(ctx, st);
   if (rc) return rc;
   const int64_t per = (n_cells + chunks - 1) / chunks;
@@ -620,6 +696,12 @@ extern "C" int nbw_score_pool_host(nbw_ctx* ctx, const nbw_model* model_h, const
   NBW_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_done[0], 0));
   NBW_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_done[0], 0));
   const uint8_t* src = static_cast<const uint8_t*>(cells_h);
+  NbwCand* lists = nullptr;
+  int used = 0;
+  if (k > 0) {
+    rc = piece_cands(ctx, &lists);
+    if (rc) return rc;
+  }
   for (int c = 0; c < chunks; ++c) {
     const int64_t lo = (int64_t)c * per, hi = (lo + per < n_cells) ? lo + per : n_cells;
     if (lo >= hi) break;
@@ -629,8 +711,10 @@ extern "C" int nbw_score_pool_host(nbw_ctx* ctx, const nbw_model* model_h, const
     NBW_CUDA(ctx, cudaEventRecord(ctx->ev_ready[b], ctx->s_in));
     NBW_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_ready[b], 0));
     const uint8_t* dev = static_cast<const uint8_t*>(ctx->stage[b]);
-    rc = score_dispatch(ctx, *model_h, dev, hi - lo, scores_dev + lo, st);
+    rc = score_dispatch(ctx, *model_h, dev, hi - lo, scores_dev + lo, st, k, distinct, index_base + lo,
+                        lists ? lists + (size_t)c * k : nullptr);
     if (rc) return rc;
+    ++used;
     NBW_CUDA(ctx, cudaEventRecord(ctx->ev_free[b], st));
     if (scores_h) {
       NBW_CUDA(ctx, cudaEventRecord(ctx->ev_done[b], st));
@@ -638,6 +722,10 @@ extern "C" int nbw_score_pool_host(nbw_ctx* ctx, const nbw_model* model_h, const
       NBW_CUDA(ctx, cudaMemcpyAsync(scores_h + lo, scores_dev + lo, (size_t)(hi - lo) * sizeof(float),
                                     cudaMemcpyDeviceToHost, ctx->s_out));
     }
+  }
+  if (k > 0) {
+    rc = merge_pieces(ctx, lists, used, k, distinct, out_cands, st);
+    if (rc) return rc;
   }
   return pipe_end(ctx, scores_h != nullptr);
 }

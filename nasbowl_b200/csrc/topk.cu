@@ -16,11 +16,7 @@ constexpr int kTopThreads = 256;
 constexpr int kTopItems = 16;
 constexpr int kTopChunk = kTopThreads * kTopItems;
 
-struct Cand {
-  float v;
-  int32_t pad;
-  int64_t idx;   // -1 = empty
-};
+typedef NbwCand Cand;
 
 __device__ __forceinline__ bool better(float v, int64_t i, float bv, int64_t bi) {
   // (v, i) beats (bv, bi): larger value, or equal value and lower index; empty loses
@@ -142,6 +138,11 @@ static int topk_enqueue(nbw_ctx* ctx, const float* scores, const Cand* cands, in
   return NBW_OK;
 }
 
+int nbw_topk_merge_enqueue(nbw_ctx* ctx, const NbwCand* cands, int64_t count, int k, int distinct, NbwCand** result,
+                           cudaStream_t st) {
+  return topk_enqueue(ctx, nullptr, cands, count, k, distinct, 0, result, st);
+}
+
 static int topk_readback(nbw_ctx* ctx, const Cand* dev, int k, float* top_val_h, int64_t* top_idx_h, int* n_found_h,
                          cudaStream_t st) {
   // k <= 1024 entries of 16 bytes: read back through a pinned block owned by the context (a pageable
@@ -165,6 +166,7 @@ static int topk_readback(nbw_ctx* ctx, const Cand* dev, int k, float* top_val_h,
 extern "C" int nbw_topk(nbw_ctx* ctx, const float* scores, int64_t n, int k, int distinct, int64_t index_base,
                         float* top_val_h, int64_t* top_idx_h, int* n_found_h, void* stream) {
   if (!ctx) return NBW_ERR_INVALID;
+  NbwRange range("nbw_topk");
   NBW_REQUIRE(ctx, k >= 1 && k <= 1024, "k must be in [1, 1024]");
   NBW_REQUIRE(ctx, n >= 0 && top_val_h && top_idx_h && n_found_h, "bad argument");
   *n_found_h = 0;
@@ -180,6 +182,7 @@ extern "C" int nbw_topk(nbw_ctx* ctx, const float* scores, int64_t n, int k, int
 extern "C" int nbw_topk_device(nbw_ctx* ctx, const float* scores, int64_t n, int k, int distinct,
                                int64_t index_base, void* out_cands, void* stream) {
   if (!ctx) return NBW_ERR_INVALID;
+  NbwRange range("nbw_topk_device");
   NBW_REQUIRE(ctx, k >= 1 && k <= 1024, "k must be in [1, 1024]");
   NBW_REQUIRE(ctx, n >= 0 && out_cands, "bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -198,6 +201,7 @@ extern "C" int nbw_topk_device(nbw_ctx* ctx, const float* scores, int64_t n, int
 extern "C" int nbw_topk_merge(nbw_ctx* ctx, const void* cands, int64_t count, int k, int distinct,
                               float* top_val_h, int64_t* top_idx_h, int* n_found_h, void* stream) {
   if (!ctx) return NBW_ERR_INVALID;
+  NbwRange range("nbw_topk_merge");
   NBW_REQUIRE(ctx, k >= 1 && k <= 1024, "k must be in [1, 1024]");
   NBW_REQUIRE(ctx, count >= 0 && top_val_h && top_idx_h && n_found_h, "bad argument");
   *n_found_h = 0;
@@ -208,4 +212,12 @@ extern "C" int nbw_topk_merge(nbw_ctx* ctx, const void* cands, int64_t count, in
   int rc = topk_enqueue(ctx, nullptr, static_cast<const Cand*>(cands), count, k, distinct, 0, &res, st);
   if (rc) return rc;
   return topk_readback(ctx, res, k, top_val_h, top_idx_h, n_found_h, st);
+}
+
+extern "C" int nbw_cands_read(nbw_ctx* ctx, const void* cands, int k, float* top_val_h, int64_t* top_idx_h,
+                              int* n_found_h, void* stream) {
+  if (!ctx) return NBW_ERR_INVALID;
+  NBW_REQUIRE(ctx, k >= 1 && k <= 1024 && cands && top_val_h && top_idx_h && n_found_h, "bad argument");
+  return topk_readback(ctx, static_cast<const Cand*>(cands), k, top_val_h, top_idx_h, n_found_h,
+                       static_cast<cudaStream_t>(stream));
 }

@@ -56,6 +56,7 @@ extern "C" int nbw_wl_signatures(nbw_ctx* ctx, const void* cells, int64_t n_cell
                                  const uint32_t* ids_prev, int level, uint64_t seed,
                                  uint64_t* keys, uint64_t* chks, void* stream) {
   if (!ctx) return NBW_ERR_INVALID;
+  NbwRange range("nbw_wl_signatures");
   NBW_REQUIRE(ctx, n_max == 8 || n_max == 16, "n_max must be 8 or 16 (got %d)", n_max);
   NBW_REQUIRE(ctx, n_cells >= 0 && level >= 0 && level < NBW_MAX_LEVELS, "bad n_cells/level");
   NBW_REQUIRE(ctx, (level == 0) == (ids_prev == nullptr), "ids_prev must be NULL exactly at level 0");

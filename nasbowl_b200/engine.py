@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .cells import CellBatch, record_stride
+from .cells import CellBatch, CellSlots, record_stride
 
 ACQ = {"EI": 0, "AEI": 1, "UCB": 2, "MEAN": 3}
 DEFAULT_SEED = 0x5EEDB200
@@ -116,7 +116,8 @@ class Engine:
     def empty(self, shape, dtype):
         return torch.empty(shape, dtype=dtype, device=self.device)
 
-    def upload_cells(self, batch: CellBatch) -> torch.Tensor:
+    def upload_cells(self, batch) -> torch.Tensor:
+        """CellBatch | CellSlots -> device records (N, stride) / (N, n_slots * stride)."""
         rec = torch.from_numpy(batch.to_records())
         return rec.to(self.device, non_blocking=False)
 
@@ -216,6 +217,94 @@ class Engine:
                                          k0, k1, self._p(out), out.stride(0), impl, self.stream))
         return out[:, :n]
 
+    GRAM_OUT = {"s32": (0, torch.int32), "u8": (1, torch.uint8), "s16": (2, torch.int16), "f32norm": (3, torch.float32)}
+
+    def gram_ex(self, A: torch.Tensor, B: torch.Tensor, k0: int, k1: int, mode: str = "s32", upper_only: bool = False,
+                row_offset: int = 0, scale_a: Optional[torch.Tensor] = None, scale_b: Optional[torch.Tensor] = None,
+                out: Optional[torch.Tensor] = None, overflow: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """nbw_gram_i8_ex: A[:, k0:k1] @ B[:, k0:k1].T with the output form chosen per launch (s32 / u8 / s16 with
+        saturation / cosine-normalised fp32) and, for the Gram of a batch with itself, the symmetric tile schedule
+        (tiles strictly below the global diagonal are neither computed nor written)."""
+        code, dtype = self.GRAM_OUT[mode]
+        m, n = A.shape[0], B.shape[0]
+        if out is None:
+            out = self.empty((m, _round_up(n, 16)), dtype)
+        assert out.dtype == dtype and out.shape[0] >= m and out.stride(1) == 1
+        self._check(self.lib.nbw_gram_i8_ex(self.ctx, self._p(A), m, A.stride(0), self._p(B), n, B.stride(0), k0, k1,
+                                            self._p(out), out.stride(0), code, int(upper_only), int(row_offset),
+                                            self._p(scale_a), self._p(scale_b), self._p(overflow), self.stream))
+        return out[:m, :n]
+
+    def sym_mirror(self, Cm: torch.Tensor):
+        """Fill the lower triangle of a square matrix from its upper triangle (nbw_sym_mirror)."""
+        n = Cm.shape[0]
+        self._check(self.lib.nbw_sym_mirror(self.ctx, self._p(Cm), n, Cm.stride(0), Cm.element_size(), self.stream))
+
+    def gram_stress(self, fit: WLFit, D: int, block: int, rank: int = 0, world: int = 1, mode: str = "u8",
+                    symmetric: bool = True):
+        """BASELINE configs[4]: the N x N Gram of a fitted batch, materialised in HBM as `mode` elements.  Row blocks
+        of `block` rows are dealt round-robin to the ranks; with `symmetric` only the tiles on or above the
+        diagonal are computed and (one GPU) the lower triangle is filled by nbw_sym_mirror afterwards.  Returns
+        timings (CUDA events), the result-independent checks and a description for the bench record."""
+        import time
+        N = fit.n_cells
+        code, dtype = self.GRAM_OUT[mode]
+        starts = list(range(0, N, block))
+        mine = [r0 for i, r0 in enumerate(starts) if i % world == rank]
+        ld = _round_up(N, 16)
+        rows_mine = sum(min(block, N - r0) for r0 in mine)
+        out = self.empty((max(rows_mine, 1), ld), dtype)          # this rank's row blocks, stacked
+        overflow = torch.zeros((1,), dtype=torch.int32, device=self.device)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        # warm-up: one small block (module load, tensor-map encode, launch attributes)
+        self.gram_ex(fit.phi[:min(512, N)], fit.phi[:min(512, N)], 0, D, mode=mode)
+        torch.cuda.synchronize()
+        t_begin = time.time()
+        ev[0].record()
+        pos, tiles_done, tiles_all, placed = 0, 0, 0, []
+        for r0 in mine:
+            rows = min(block, N - r0)
+            self.gram_ex(fit.phi[r0:r0 + rows], fit.phi, 0, D, mode=mode, upper_only=symmetric, row_offset=r0,
+                         out=out[pos:pos + rows], overflow=overflow)
+            placed.append((r0, rows, pos))
+            pos += rows
+            for mt in range((rows + 255) // 256):
+                nt_all = (N + 255) // 256
+                first = 0
+                if symmetric:       # tiles with nt * 256 + 255 < r0 + mt * 256 are skipped
+                    first = min(nt_all, max(0, (r0 + mt * 256 - 255 + 255) // 256))
+                tiles_all += nt_all
+                tiles_done += nt_all - first
+        if symmetric and world == 1:
+            self.sym_mirror(out[:N])
+        ev[1].record()
+        torch.cuda.synchronize()
+        t_end = time.time()
+        ms = ev[0].elapsed_time(ev[1])
+        # checks that do not need the whole oracle: diagonal == self-similarity; mirrored entries equal;
+        # SIMT cross-check of a corner; no saturation
+        checks = {"no_saturation": bool(int(overflow.item()) == 0)}
+        ok_diag = True
+        for r0, rows, p in placed:
+            d = out[p:p + rows][torch.arange(rows, device=self.device), torch.arange(r0, r0 + rows, device=self.device)]
+            ok_diag &= bool(torch.equal(d.to(torch.int32), fit.self_sim[r0:r0 + rows]))
+        checks["diag_equals_self_similarity"] = ok_diag
+        if placed:
+            r0, rows, p = placed[0]
+            c = min(rows, 2048)
+            ref = self.gram(fit.phi[r0:r0 + c], fit.phi[N - c:], 0, D, impl=1)          # SIMT dp4a, far corner
+            checks["simt_crosscheck_corner"] = bool(torch.equal(ref, out[p:p + c, N - c:N].to(torch.int32)))
+            if symmetric and world == 1 and N > c:
+                low = out[N - c:N, r0:r0 + c].to(torch.int32)                            # filled by the mirror pass
+                checks["mirrored_corner_equals_transpose"] = bool(torch.equal(low, ref.t().contiguous()))
+        return {"ms": ms, "checks": checks, "t_begin": t_begin, "t_end": t_end,
+                "computed_fraction": tiles_done / max(tiles_all, 1), "dims": list(fit.dims),
+                "schedule": ("symmetric: 256x256 tiles strictly below the diagonal skipped, lower triangle filled by a mirror pass"
+                             if symmetric else "all tiles"),
+                "output": "%s [%d x %d] materialised in HBM (%.1f GB on this rank)" % (mode, rows_mine, N, rows_mine * ld * out.element_size() / 1e9),
+                "output_bytes": rows_mine * N * out.element_size() * world if world > 1 else N * N * out.element_size(),
+                "kernel": "gram_i8_pair_kernel<%s>" % mode, "result": out}
+
     # ------------------------------------------------------------------ fp64 linear algebra
     def gram_accumulate(self, K: torch.Tensor, w: float, beta: float, out: torch.Tensor):
         m, n = K.shape
@@ -282,17 +371,21 @@ class Engine:
         self._check(self.lib.nbw_scale_features(self.ctx, self._p(phi), phi.stride(0), n, k0, k1, self._p(s),
                                                 float(sqrt_w), self._p(out), ldo, self.stream))
 
-    def prefix_features(self, B: torch.Tensor, fit: "WLFit", h: int) -> torch.Tensor:
+    def prefix_features(self, B: torch.Tensor, fit: "WLFit", h: int, out: Optional[torch.Tensor] = None,
+                        ldp: Optional[int] = None) -> torch.Tensor:
         """Bp [n, T+1]: features summed over ancestor chains (nbw_prefix_features); the extra
-        last column stays zero."""
+        last column stays zero.  `out` (with leading dimension ldp) places the T columns of this kernel
+        inside the side-by-side matrix of a sum of kernels."""
         n = B.shape[0]
         T = fit.label_off[h + 1]
-        Bp = torch.zeros((n, T + 1), dtype=torch.float64, device=self.device)
+        if out is None:
+            out = torch.zeros((n, T + 1), dtype=torch.float64, device=self.device)
+            ldp = T + 1
         co = (C.c_int64 * (h + 2))(*fit.col_off[:h + 2])
         lo = (C.c_int64 * (h + 2))(*fit.label_off[:h + 2])
         self._check(self.lib.nbw_prefix_features(self.ctx, self._p(B), B.stride(0), n, h + 1, co, lo,
-                                                 self._p(fit.parents), self._p(Bp), Bp.stride(0), self.stream))
-        return Bp
+                                                 self._p(fit.parents), C.c_void_p(out.data_ptr()), ldp, self.stream))
+        return out
 
     def posterior_cov_finish(self, Kss: torch.Tensor, ldk: int, Q: torch.Tensor, m: int, lik: float,
                              y_std: float) -> torch.Tensor:
@@ -321,7 +414,79 @@ class Engine:
         level0 = torch.from_numpy(l0.view(np.int16)).to(self.device)
         return level0, tables, masks
 
+    def build_packed_tables(self, fit: WLFit, last_hashed: int):
+        """Packed-path dictionary forms for the hashed levels 1..last_hashed (nbw_model.id_hash / bucket_*):
+        per level the hashes of the previous level's ids and the tag buckets of this level's keys.  Buckets
+        hold four entries; n_buckets >= 4 D keeps an overflow (five keys in one bucket) a < 1 % event, which
+        is answered by doubling."""
+        n = last_hashed + 1
+        id_hash, tags, entries, masks = [None] * n, [None] * n, [None] * n, [0] * n
+        if last_hashed < 1:
+            return id_hash, tags, entries, masks
+        flags = torch.zeros((n,), dtype=torch.int32, device=self.device)
+        seed = C.c_uint64(fit.seed & 0xFFFFFFFFFFFFFFFF)
+
+        def build(l, nb):
+            d = fit.dims[l]
+            tags[l] = self.empty((nb * 16,), torch.uint8)
+            entries[l] = self.empty((nb * 64,), torch.uint8)
+            masks[l] = nb - 1
+            self._check(self.lib.nbw_model_build_buckets(self.ctx, self._p(fit.uniq_keys[l]), self._p(fit.uniq_chks[l]), d,
+                                                         self._p(tags[l]), self._p(entries[l]), nb, self._p(flags[l:]),
+                                                         self.stream))
+        for l in range(1, n):
+            dp = max(fit.dims[l - 1], 1)
+            id_hash[l] = self.empty((dp * 16,), torch.uint8)
+            self._check(self.lib.nbw_model_build_id_hash(self.ctx, fit.dims[l - 1], seed, l, self._p(id_hash[l]), self.stream))
+            build(l, _pow2_at_least(max(4 * fit.dims[l], 16)))
+        for attempt in range(8):
+            bad = np.nonzero(flags.cpu().numpy())[0]
+            if len(bad) == 0:
+                return id_hash, tags, entries, masks
+            flags.zero_()
+            for l in bad:
+                build(int(l), 2 * (masks[int(l)] + 1))
+        raise RuntimeError("packed dictionary buckets keep overflowing")
+
+    class _Range:
+        def __init__(self, lib, name):
+            self.lib, self.name = lib, name.encode()
+
+        def __enter__(self):
+            self.lib.nbw_range_push(self.name)
+
+        def __exit__(self, *exc):
+            self.lib.nbw_range_pop()
+
+    def profile_events(self, ev_start=None, ev_stop=None):
+        """nbw_profile_events: torch.cuda.Event pair recorded around the next scoring kernel launches."""
+        a = None if ev_start is None else C.c_void_p(ev_start.cuda_event)
+        b = None if ev_stop is None else C.c_void_p(ev_stop.cuda_event)
+        self._check(self.lib.nbw_profile_events(self.ctx, a, b))
+
+    def range(self, name: str):
+        """NVTX range (nbw_range_push / nbw_range_pop) around a host-layer phase."""
+        return Engine._Range(self.lib, name)
+
     # ------------------------------------------------------------------ pool scoring
+    def score_pool_topk(self, model: "_lib.Model", cells: torch.Tensor, n_cells: int, k: int, distinct: bool = True,
+                        index_base: int = 0, scores: Optional[torch.Tensor] = None,
+                        out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Fused scoring + local top-k (nbw_score_pool_topk): returns the device list uint8 [k * 16]."""
+        if out is None:
+            out = self.empty((k * 16,), torch.uint8)
+        self._check(self.lib.nbw_score_pool_topk(self.ctx, C.byref(model), self._p(cells), n_cells, self._p(scores), k,
+                                                 int(distinct), index_base, self._p(out), self.stream))
+        return out
+
+    def fused_topk_ok(self, model: "_lib.Model", k: int) -> bool:
+        """The packed kernel serves this model and k (else: nbw_score_pool + nbw_topk*)."""
+        import os
+        if k > 8 or model.oa or not model.H or os.environ.get("NBW_SCORE_LEGACY"):
+            return False
+        hashed1 = model.h >= 1 and (model.first_stable == 0 or model.first_stable > 1)
+        return (not hashed1) or bool(model.bucket_tags[1])
+
     def score_pool(self, model: "_lib.Model", cells: torch.Tensor, n_cells: int,
                    scores: Optional[torch.Tensor] = None, want64: bool = False):
         if scores is None:
@@ -350,16 +515,61 @@ class Engine:
         st = self._host_state = getattr(self, "_host_state", None) or {}
         if st.get("M") != M:
             st.update(M=M, scores=self.empty((M,), torch.float32))
-        # a fresh pinned block per call (torch's caching host allocator recycles them): the caller
-        # owns the returned scores, nothing is overwritten by the next pool
+        # a fresh pinned block per call: the caller owns the returned HOST scores (the device copy is a
+        # work buffer, valid until the next host-pool call).  The D2H copy runs on the library's side
+        # stream, which torch's caching host allocator does not know: the engine keeps the block (and the
+        # records it reads) referenced until the copy has been awaited, so it cannot be recycled mid-flight.
+        if st.get("pending") is not None:
+            self.wait_host_scores()
         host_scores = torch.empty((M,), dtype=torch.float32, pin_memory=True)
+        st["pending"] = (host_scores, host_cells)
         fn = self.lib.nbw_score_pool_mapped if mapped else self.lib.nbw_score_pool_host
         self._check(fn(self.ctx, C.byref(model), C.c_void_p(host_cells.data_ptr()), M,
                        C.c_void_p(host_scores.data_ptr()), self._p(st["scores"]), max(1, min(chunks, M)), self.stream))
         return st["scores"], host_scores
 
+    def propose_host(self, model: "_lib.Model", host_cells: torch.Tensor, k: int, distinct: bool = True,
+                     index_base: int = 0, chunks: int = 8, mapped: bool = False, out: Optional[torch.Tensor] = None):
+        """nbw_propose_host: score a HOST pool (staged or mapped pipeline) with the top-k fused into the
+        scoring kernels.  Returns (device list uint8 [k * 16], host scores [M] f32 pinned); the host scores
+        are complete after cands_read() / topk_merge() / wait_host_scores()."""
+        assert not host_cells.is_cuda and host_cells.dtype == torch.uint8 and host_cells.dim() == 2
+        host_cells = host_cells.contiguous()
+        M = host_cells.shape[0]
+        st = self._host_state = getattr(self, "_host_state", None) or {}
+        if st.get("M") != M:
+            st.update(M=M, scores=self.empty((M,), torch.float32))
+        if st.get("pending") is not None:
+            self.wait_host_scores()
+        host_scores = torch.empty((M,), dtype=torch.float32, pin_memory=True)
+        st["pending"] = (host_scores, host_cells)
+        if out is None:
+            out = self.empty((k * 16,), torch.uint8)
+        self._check(self.lib.nbw_propose_host(self.ctx, C.byref(model), C.c_void_p(host_cells.data_ptr()), M,
+                                              C.c_void_p(host_scores.data_ptr()), self._p(st["scores"]), int(mapped),
+                                              max(1, min(chunks, M)), k, int(distinct), index_base, self._p(out),
+                                              self.stream))
+        return out, host_scores
+
+    def cands_read(self, cands: torch.Tensor, k: int):
+        """Device top-k list -> (values, indices) on the host (nbw_cands_read; syncs)."""
+        vals = (C.c_float * k)()
+        idx = (C.c_int64 * k)()
+        found = C.c_int(0)
+        self._check(self.lib.nbw_cands_read(self.ctx, self._p(cands), k, vals, idx, C.byref(found), self.stream))
+        f = found.value
+        self.host_scores_done()
+        return np.array(vals[:f], dtype=np.float32), np.array(idx[:f], dtype=np.int64)
+
     def wait_host_scores(self):
         self._check(self.lib.nbw_wait_host_scores(self.ctx))
+        if getattr(self, "_host_state", None):
+            self._host_state["pending"] = None
+
+    def host_scores_done(self):
+        """Called after an entry point that awaited the host scores itself (nbw_topk / nbw_topk_merge)."""
+        if getattr(self, "_host_state", None):
+            self._host_state["pending"] = None
 
     def pool_features(self, model: "_lib.Model", cells: torch.Tensor, n_cells: int):
         ld = _round_up(model.n_features, 16)
@@ -377,6 +587,7 @@ class Engine:
         self._check(self.lib.nbw_topk(self.ctx, self._p(scores), n, k, int(distinct), index_base, vals, idx,
                                       C.byref(found), self.stream))
         f = found.value
+        self.host_scores_done()
         return np.array(vals[:f], dtype=np.float32), np.array(idx[:f], dtype=np.int64)
 
     def topk_device(self, scores: torch.Tensor, k: int, distinct: bool = True, index_base: int = 0,
@@ -396,6 +607,7 @@ class Engine:
         self._check(self.lib.nbw_topk_merge(self.ctx, self._p(cands), count, k, int(distinct), vals, idx,
                                             C.byref(found), self.stream))
         f = found.value
+        self.host_scores_done()
         return np.array(vals[:f], dtype=np.float32), np.array(idx[:f], dtype=np.int64)
 
     def generate_cells(self, family: int, seed: int, first_index: int, n_cells: int) -> torch.Tensor:

@@ -47,11 +47,15 @@ class CombineKernel:
         eng = Engine.get()
         grams = []
         layer_weights = kwargs.get('layer_weights', None)
-        batch = None
+        packed = {}
         for k in self.kernels:
-            if batch is None:
-                batch = k.pack(gr1)
-                cells = eng.upload_cells(batch)
+            # every kernel converts the graphs itself (its own node_label / undirected view, like the
+            # per-kernel graph_from_networkx of kernels/weisfilerlehman.py:127-136); equal views are shared
+            key = (getattr(k, 'node_label', None), bool(getattr(k, 'undirected', False)))
+            if key not in packed:
+                b = k.pack(gr1)
+                packed[key] = (b, eng.upload_cells(b))
+            batch, cells = packed[key]
             if layer_weights is not None and layer_weights is not k.layer_weights:
                 k.change_kernel_params({'layer_weights': layer_weights})
             if rebuild_model or k._fit is None:

@@ -34,8 +34,12 @@ class _KernState:
 class WeisfilerLehman(GraphKernels):
     def __init__(self, h: int = 0, type='subtree', se_kernel=None, layer_weights=None, node_weights=None,
                  oa=False, node_label: str = 'op_name', edge_label: tuple = 'op_name', n_jobs: int = None,
-                 return_tensor: bool = True, requires_grad: bool = False, undirected: bool = False, **kwargs):
+                 return_tensor: bool = True, requires_grad: bool = False, undirected: bool = False, slot: int = 0,
+                 **kwargs):
+        """slot (extension): which cell of a multi-cell example this kernel reads when the GP is given
+        tuples of graphs / CellSlots ("normal | reduce"); 0 = the reference's behaviour."""
         super().__init__(**kwargs)
+        self.slot = int(slot)
         if se_kernel is not None and oa:
             raise ValueError("Only one or none of se (successive embedding) and oa (optimal assignment) may be true!")
         assert type in ['subtree', 'sp', 'edge']

@@ -107,26 +107,54 @@ def select_topk(eng, scores: torch.Tensor, k: int, distinct: bool = True, index_
 
 
 def broadcast_pool_model(pm: Optional[PoolModel], src: int = 0, device=None) -> PoolModel:
-    """Broadcast the fitted surrogate from `src` to every rank (NCCL: over NVLink)."""
+    """Broadcast the fitted surrogate from `src` to every rank (NCCL: over NVLink) as ONE flat byte
+    buffer: a 256-byte head (json length, payload length), the json meta and every tensor at an aligned
+    offset — two collectives (head, buffer) instead of a pickled object list plus one per tensor.
+    Receivers get views into the received buffer."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return pm
     rank = dist.get_rank()
     if device is None:
-        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else "cpu"
-    box = [pm.meta() if rank == src else None]
-    dist.broadcast_object_list(box, src=src)
-    if rank != src:
-        pm = PoolModel.empty_from_meta(box[0], device)
-    for t in pm.tensors():
-        dist.broadcast(t.view(torch.uint8), src=src)      # raw bytes: every backend moves uint8
-    return pm
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    head = torch.zeros((2,), dtype=torch.int64, device=device)
+    buf = None
+    if rank == src:
+        buf = pm.pack_flat()
+        if buf.device != device:
+            buf = buf.to(device)
+        head.copy_(buf[:16].view(torch.int64))
+    dist.broadcast(head, src=src)
+    if rank == src:
+        dist.broadcast(buf, src=src)
+        return pm
+    hlen, plen = [int(v) for v in head.cpu()]
+    buf = torch.empty((256 + ((hlen + 255) & ~255) + plen,), dtype=torch.uint8, device=device)
+    dist.broadcast(buf, src=src)
+    header = bytes(buf[256:256 + hlen].cpu().numpy())
+    return PoolModel.unpack_flat(buf, header)
+
+
+def score_and_select(eng, model, cells: torch.Tensor, n_cells: int, k: int, distinct: bool = True, index_base: int = 0,
+                     scores: Optional[torch.Tensor] = None, cand_buf: Optional[torch.Tensor] = None,
+                     gathered: Optional[torch.Tensor] = None):
+    """One pool step of a rank: score its shard and agree on the global top-k.  The local top-k is fused
+    into the scoring kernel when the packed path serves the model (nbw_score_pool_topk); the per-rank
+    lists are all-gathered (k x 16 B per rank) and merged on every rank.  Returns (values, global indices)."""
+    if eng.fused_topk_ok(model, k):
+        local = eng.score_pool_topk(model, cells, n_cells, k, distinct, index_base, scores=scores, out=cand_buf)
+        if not dist.is_initialized() or dist.get_world_size() == 1:
+            return eng.cands_read(local, k)
+        return allgather_topk_device(eng, local, k, distinct, gathered=gathered)
+    sc, _, _, _ = eng.score_pool(model, cells, n_cells, scores=scores)
+    return select_topk(eng, sc, k, distinct, index_base, cand_buf, gathered)
 
 
 def propose_location_sharded(acq, pool_shard, index_base: int, top_n: int = 5, return_distinct: bool = True):
     """Score this rank's shard (device records) and agree on the global top-n.
     Returns (top values, global indices, local scores device tensor)."""
     acq.iters += 1
-    scores, _, _, _ = acq.score_pool(pool_shard)
+    cells, M = acq.gp.upload_pool(pool_shard)
     eng = acq.gp._dev['eng']
-    vals, idx = select_topk(eng, scores, top_n, bool(return_distinct), index_base)
+    scores = eng.empty((M,), torch.float32)
+    vals, idx = score_and_select(eng, acq._model(), cells, M, top_n, bool(return_distinct), index_base, scores=scores)
     return vals, idx, scores

@@ -288,6 +288,67 @@ def gp_predict_full_sum(st: SumGPState, train, pool):
     return mu, cov
 
 
+def _per_kernel(x, m):
+    """One CellBatch for every kernel of the sum (the reference's behaviour, combine_kernels.py:36-56), or a
+    list with one CellBatch per kernel (kernels that read different record slots of an example)."""
+    return list(x) if isinstance(x, (list, tuple)) else [x] * m
+
+
+def gp_fit_sum_fixed(train, y, kernels, weights, likelihood: float = 1e-3, layer_weights=None):
+    """GraphGP(train, y, [k_1..k_m], weights=w).fit(wl_subtree_candidates=(), optimize_lik=False): a sum of WL
+    kernels with FIXED weights and depths (gp.py:139-219 with nothing to train).  kernels: [(h, oa), ...];
+    train: see _per_kernel; layer_weights: optional list (per kernel) of per-level weights."""
+    y = np.asarray(y, dtype=np.float64)
+    y_norm, y_mean, y_std = normalize_y(y)
+    m = len(kernels)
+    trains = _per_kernel(train, m)
+    w = np.array([f32(v) for v in weights], dtype=np.float64)      # the reference keeps the weights in fp32 (gp.py:66)
+    lik = f32(likelihood)
+    S = 0.0
+    for i, (h, oa) in enumerate(kernels):
+        lev = wl_oracle.gram_raw_levels(trains[i], h, oa).astype(np.float64)
+        lw = np.ones(h + 1) if layer_weights is None or layer_weights[i] is None else np.asarray(layer_weights[i], dtype=np.float64)
+        S = S + w[i] * sum(lw[l] * lev[l] for l in range(h + 1))
+    K = normalize_gram(S)
+    K_i, _, _ = pd_inverse(K, lik)
+    st = SumGPState(hs=[h for h, _ in kernels], oas=[oa for _, oa in kernels], weights=w / w.sum(), lik=lik,
+                    y_mean=float(y_mean), y_std=float(y_std), y_norm=y_norm, y_raw=y, K=K, K_i=K_i, nlml=None)
+    st.raw_weights = w
+    st.level_weights = [np.ones(h + 1) if layer_weights is None or layer_weights[i] is None
+                        else np.asarray(layer_weights[i], dtype=np.float64) for i, (h, _) in enumerate(kernels)]
+    return st
+
+
+def gp_predict_diag_sum(st: SumGPState, train, pool, chunk: int = 2048):
+    """Posterior mean and marginal variance of a sum-of-kernels GP over a pool (the diagonal of
+    gp_predict_full_sum, gp.py:240-283), chunked.  Uses st.weights and, if present, st.level_weights."""
+    m = len(st.hs)
+    trains, pools = _per_kernel(train, m), _per_kernel(pool, m)
+    M = len(pools[0])
+    mu, var = np.empty(M), np.empty(M)
+    a = st.K_i @ st.y_norm
+    lws = getattr(st, "level_weights", None)
+    for s in range(0, M, chunk):
+        K_s, kss, ktt = 0.0, 0.0, 0.0
+        for i, (w, h, oa) in enumerate(zip(st.weights, st.hs, st.oas)):
+            lw = np.ones(h + 1) if lws is None else lws[i]
+            Ks_i, kss_i, ktt_i = wl_oracle.pool_features_weighted(trains[i], pools[i][s:s + chunk], h, oa, lw)
+            K_s, kss, ktt = K_s + w * Ks_i, kss + w * kss_i, ktt + w * ktt_i
+        K_s = K_s / np.sqrt(np.outer(ktt, kss))
+        mu[s:s + chunk] = (K_s.T @ a) * st.y_std + st.y_mean
+        q = np.einsum("ij,ij->j", K_s, st.K_i @ K_s)
+        cov = np.maximum(1.0 + st.lik - q, st.lik)
+        var[s:s + chunk] = (np.sqrt(cov) * st.y_std) ** 2
+    return mu, var
+
+
+def incumbent_sum(st: SumGPState) -> float:
+    """_get_incumbent (acquisitions.py:82-92) for a sum-of-kernels state: y_raw[argmax of the posterior mean at
+    the training points]."""
+    mu_train = st.K @ (st.K_i @ st.y_norm)
+    return float(st.y_raw[int(np.argmax(mu_train))])
+
+
 def gp_predict_diag(st: GPState, train, pool, chunk: int = 4096):
     """Posterior mean and marginal variance over a pool (gp.py:240-283, diagonal only):
     mu = (K_s^T K_i y)*y_std + y_mean ; var = clamp(1 + lik - k_s^T K_i k_s, lik) * y_std^2."""

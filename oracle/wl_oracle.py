@@ -293,3 +293,26 @@ def pool_features(train: CellBatch, pool: CellBatch, h: int, oa: bool = False):
             kss += (pp * pp).sum(axis=1)
             ktt += (pt * pt).sum(axis=1)
     return K_s, kss, ktt
+
+
+def pool_features_weighted(train: CellBatch, pool: CellBatch, h: int, oa: bool, level_weights):
+    """pool_features with one weight per WL level (weisfeiler_lehman.py:316-327: K_raw = sum_l w_l K_l):
+    float64 (K_s [n, M], kss [M], ktt [n])."""
+    n, M = len(train), len(pool)
+    joint = CellBatch.concat([train, pool])
+    phis = wl_features(joint, h, fast=True)
+    K_s = np.zeros((n, M))
+    kss = np.zeros(M)
+    ktt = np.zeros(n)
+    for l, p in enumerate(phis):
+        w = float(level_weights[l])
+        pt, pp = p[:n], p[n:]
+        if oa:
+            K_s += w * level_gram(pt, pp, True)
+            kss += w * pp.sum(axis=1)
+            ktt += w * pt.sum(axis=1)
+        else:
+            K_s += w * (pt @ pp.T)
+            kss += w * (pp * pp).sum(axis=1)
+            ktt += w * (pt * pt).sum(axis=1)
+    return K_s, kss, ktt

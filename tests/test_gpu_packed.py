@@ -1,0 +1,411 @@
+"""GPU parity tests of the packed scoring path (csrc/score_packed.cu): dense lane packing, fetched hashes,
+exact in-cell class refinement, tag-bucket probes, sums of kernels over one or several records per
+candidate, weighted WL levels, undirected kernels and the fused top-n — against the CPU oracle, against
+the first-generation kernel (NBW_SCORE_LEGACY=1) and at the sizes of BASELINE configs[2] / configs[3]."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from nasbowl_b200 import synth
+from nasbowl_b200.cells import NO_NODE, CellBatch, CellSlots
+from oracle import gp_oracle
+
+pytestmark = pytest.mark.gpu
+
+RTOL64 = 1e-6
+RTOL32 = 1e-4
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from nasbowl_b200.engine import Engine
+    return Engine.get()
+
+
+def _gp(train, y, kernels, **kw):
+    from nasbowl_b200.bayesopt import GraphGP
+    return GraphGP(train, torch.as_tensor(np.asarray(y, dtype=np.float64)), kernels, **kw)
+
+
+def _legacy(fn):
+    os.environ["NBW_SCORE_LEGACY"] = "1"
+    try:
+        return fn()
+    finally:
+        os.environ.pop("NBW_SCORE_LEGACY", None)
+
+
+# ---------------------------------------------------------------------------- packed vs legacy vs oracle
+@pytest.mark.parametrize("fam,h", [(0, 0), (0, 1), (0, 2), (0, 3), (1, 2), (1, 5), (2, 2), (2, 4)])
+def test_packed_kernel_matches_first_generation_and_oracle(eng, fam, h):
+    from nasbowl_b200.bayesopt import GraphExpectedImprovement
+    from nasbowl_b200.kernels import WeisfilerLehman
+    n, M = 120, 30_011                       # a pool size that is a multiple of nothing
+    train = synth.generate_cells_host(fam, 5, 0, n)
+    y = np.random.RandomState(fam * 10 + h).randn(n)
+    gp = _gp(train, y, [WeisfilerLehman(h=h)], n_max=train.n_max)
+    gp.fit(wl_subtree_candidates=(h,), optimize_lik=False)
+    pool = eng.generate_cells(fam, 77, 1000, M)
+    acq = GraphExpectedImprovement(gp)
+    assert eng.fused_topk_ok(acq._model(), 5)
+    s, mu, var, s64 = [t.clone() for t in acq.score_pool(pool, want64=True)]
+    s_l, mu_l, var_l, s64_l = _legacy(lambda: [t.clone() for t in acq.score_pool(pool, want64=True)])
+    # two evaluation orders of the same sums of fp64 terms
+    np.testing.assert_allclose(mu.cpu().numpy(), mu_l.cpu().numpy(), rtol=1e-11, atol=1e-13)
+    np.testing.assert_allclose(var.cpu().numpy(), var_l.cpu().numpy(), rtol=1e-9, atol=1e-14)
+    np.testing.assert_allclose(s64.cpu().numpy(), s64_l.cpu().numpy(), rtol=1e-8, atol=1e-14)
+    sub = CellBatch.from_records(pool[:1500].cpu().numpy(), train.n_max)
+    st = gp_oracle.gp_fit(train, y, h_candidates=(h,), optimize_lik=False)
+    mu_o, var_o = gp_oracle.gp_predict_diag(st, train, sub)
+    np.testing.assert_allclose(mu.cpu().numpy()[:1500], mu_o, rtol=RTOL64, atol=1e-9)
+    np.testing.assert_allclose(var.cpu().numpy()[:1500], var_o, rtol=RTOL64, atol=1e-12)
+    # packing must not leak into the numbers: any split of the pool gives bitwise the same scores
+    for cut in (1, 4097, M - 3):
+        a = acq.score_pool(pool[:cut].contiguous())[0].clone()
+        b = acq.score_pool(pool[cut:].contiguous())[0].clone()
+        assert torch.equal(torch.cat([a, b]), s)
+    # fused top-5 == tournament on the score vector == numpy
+    xs, eis, idx = acq.propose_location(pool, top_n=5)
+    ref = gp_oracle.top_n_distinct(s.cpu().numpy(), 5)
+    assert set(int(i) for i in idx) == set(int(i) for i in ref)
+    v_t, i_t = eng.topk(s, 5, distinct=True)
+    assert np.array_equal(np.sort(idx), np.sort(i_t))
+    np.testing.assert_array_equal(eis.reshape(-1), s.cpu().numpy())
+
+
+def test_packing_edge_cases(eng):
+    """Cells of 1..8 nodes in every order, empty records, isolated nodes, pools of 1..40 cells."""
+    from nasbowl_b200.bayesopt import GraphExpectedImprovement
+    from nasbowl_b200.kernels import WeisfilerLehman
+    train = synth.generate_cells_host(0, 5, 0, 80)
+    y = np.random.RandomState(3).randn(80)
+    gp = _gp(train, y, [WeisfilerLehman(h=3)])
+    gp.fit(wl_subtree_candidates=(3,), optimize_lik=False)
+    acq = GraphExpectedImprovement(gp)
+    rng = np.random.RandomState(0)
+    N = 3000
+    labels = np.full((N, 8), NO_NODE, dtype=np.uint8)
+    succ = np.zeros((N, 8), dtype=np.uint16)
+    for g in range(N):
+        k = int(rng.randint(0, 9))             # 0 = an empty record
+        labels[g, :k] = rng.randint(0, 6, size=k)   # op code 5 is outside the training vocabulary
+        for v in range(k):
+            for j in range(v + 1, k):
+                if rng.rand() < 0.35:
+                    succ[g, v] |= 1 << j
+    pool = CellBatch(8, labels, succ)
+    st = gp_oracle.gp_fit(train, y, h_candidates=(3,), optimize_lik=False)
+    nonempty = pool.n_nodes > 0
+    mu_o, var_o = gp_oracle.gp_predict_diag(st, train, pool[np.nonzero(nonempty)[0]])
+    mu, var = gp.predict_diag(pool)
+    np.testing.assert_allclose(mu.numpy()[nonempty], mu_o, rtol=RTOL64, atol=1e-9)
+    np.testing.assert_allclose(var.numpy()[nonempty], var_o, rtol=RTOL64, atol=1e-12)
+    # an empty record falls back to the prior
+    prior_var = (np.sqrt(1.0 + st.lik) * st.y_std) ** 2
+    np.testing.assert_allclose(mu.numpy()[~nonempty], st.y_mean, rtol=1e-12)
+    np.testing.assert_allclose(var.numpy()[~nonempty], prior_var, rtol=1e-12)
+    full = acq.score_pool(pool)[0].clone()
+    for m in (1, 2, 7, 8, 9, 31, 40):
+        part = acq.score_pool(pool[:m])[0]
+        assert torch.equal(part, full[:m])
+        xs, eis, idx = acq.propose_location(pool[:m], top_n=5)
+        ref = gp_oracle.top_n_distinct(eis.reshape(-1), 5)
+        if len(ref) >= 5:
+            assert set(int(i) for i in idx) == set(int(i) for i in ref)
+
+
+# ---------------------------------------------------------------------------- sums of kernels
+def test_sum_of_kernels_on_the_same_cells(eng, family):
+    """SumKernel of linear WL kernels with fixed weights (kernels/combine_kernels.py:36-56) through the fused
+    pool path == dense predict() == oracle."""
+    from nasbowl_b200.bayesopt import GraphExpectedImprovement
+    from nasbowl_b200.kernels import WeisfilerLehman
+    _, z, train, pool = family
+    y = z["y"].astype(np.float64)
+    w = [0.3, 0.7]
+    gp = _gp(train, y, [WeisfilerLehman(h=1), WeisfilerLehman(h=3)], weights=w)
+    gp.fit(wl_subtree_candidates=(), optimize_lik=False)
+    st = gp_oracle.gp_fit_sum_fixed(train, y, [(1, False), (3, False)], w)
+    mu_o, var_o = gp_oracle.gp_predict_diag_sum(st, train, pool)
+    mu_d, var_d = gp.predict_diag(pool)
+    np.testing.assert_allclose(mu_d.numpy(), mu_o, rtol=RTOL64, atol=1e-9)
+    np.testing.assert_allclose(var_d.numpy(), var_o, rtol=RTOL64, atol=1e-12)
+    mu_f, cov_f = gp.predict(pool)
+    np.testing.assert_allclose(mu_d.numpy(), mu_f.numpy(), rtol=1e-8, atol=1e-11)
+    np.testing.assert_allclose(var_d.numpy(), np.diag(cov_f.numpy()), rtol=1e-8, atol=1e-13)
+    acq = GraphExpectedImprovement(gp)
+    ei_o = gp_oracle.expected_improvement(mu_o, var_o, gp_oracle.incumbent_sum(st))
+    xs, eis, idx = acq.propose_location(pool, top_n=5)
+    np.testing.assert_allclose(eis.reshape(-1), ei_o, rtol=RTOL32, atol=1e-9)
+    assert set(int(i) for i in idx) == set(int(i) for i in gp_oracle.top_n_distinct(eis.reshape(-1), 5))
+    # three and four kernels (the limit of the fused path)
+    for hs in ([0, 1, 2], [2, 2, 1, 0]):
+        ws = [1.0 / len(hs)] * len(hs)
+        gp = _gp(train, y, [WeisfilerLehman(h=h) for h in hs], weights=ws)
+        gp.fit(wl_subtree_candidates=(), optimize_lik=False)
+        st = gp_oracle.gp_fit_sum_fixed(train, y, [(h, False) for h in hs], ws)
+        mu_o, var_o = gp_oracle.gp_predict_diag_sum(st, train, pool)
+        mu_d, var_d = gp.predict_diag(pool)
+        np.testing.assert_allclose(mu_d.numpy(), mu_o, rtol=RTOL64, atol=1e-9)
+        np.testing.assert_allclose(var_d.numpy(), var_o, rtol=RTOL64, atol=1e-12)
+
+
+def test_trained_weights_then_fused_pool(eng, family):
+    """Kernel weights trained by fit() (gp.py:139-212) feed the fused path like fixed ones."""
+    from nasbowl_b200.kernels import WeisfilerLehman
+    name, z, train, pool = family
+    y = z["y"].astype(np.float64)
+    gp = _gp(train, y, [WeisfilerLehman(h=1), WeisfilerLehman(h=2)])
+    gp.fit(wl_subtree_candidates=(), optimize_lik=True, iters=5)
+    mu_d, var_d = gp.predict_diag(pool)
+    mu_f, cov_f = gp.predict(pool)
+    np.testing.assert_allclose(mu_d.numpy(), mu_f.numpy(), rtol=1e-8, atol=1e-11)
+    np.testing.assert_allclose(var_d.numpy(), np.diag(cov_f.numpy()), rtol=1e-8, atol=1e-13)
+
+
+def test_sum_over_record_slots_normal_and_reduce(eng):
+    """An architecture = (normal cell, reduce cell): k = w1 k_WL(normal, normal') + w2 k_WL(reduce, reduce')
+    (BASELINE configs[3]).  Two records per candidate, one kernel per record slot."""
+    from nasbowl_b200.bayesopt import GraphExpectedImprovement
+    from nasbowl_b200.kernels import WeisfilerLehman
+    n, M = 90, 2500
+    normal = synth.generate_cells_host(2, 11, 0, n + M)
+    reduce_ = synth.generate_cells_host(2, 12, 50_000, n + M)
+    y = np.random.RandomState(4).randn(n)
+    tr = CellSlots([normal[:n], reduce_[:n]])
+    po = CellSlots([normal[n:], reduce_[n:]])
+    w = [0.5, 0.5]
+    gp = _gp(tr, y, [WeisfilerLehman(h=2, slot=0), WeisfilerLehman(h=2, slot=1)], weights=w)
+    gp.fit(wl_subtree_candidates=(), optimize_lik=False)
+    st = gp_oracle.gp_fit_sum_fixed([normal[:n], reduce_[:n]], y, [(2, False), (2, False)], w)
+    np.testing.assert_allclose(gp.K.numpy(), st.K, rtol=1e-12)
+    mu_o, var_o = gp_oracle.gp_predict_diag_sum(st, [normal[:n], reduce_[:n]], [normal[n:], reduce_[n:]])
+    mu_d, var_d = gp.predict_diag(po)
+    np.testing.assert_allclose(mu_d.numpy(), mu_o, rtol=RTOL64, atol=1e-9)
+    np.testing.assert_allclose(var_d.numpy(), var_o, rtol=RTOL64, atol=1e-12)
+    mu_f, cov_f = gp.predict(po[:300])
+    np.testing.assert_allclose(mu_d.numpy()[:300], mu_f.numpy(), rtol=1e-8, atol=1e-11)
+    # host records (two per candidate, 96 bytes) through propose_location
+    acq = GraphExpectedImprovement(gp)
+    rec = torch.from_numpy(po.to_records()).pin_memory()
+    assert rec.shape == (M, 96)
+    xs, eis, idx = acq.propose_location(rec, top_n=5)
+    ei_o = gp_oracle.expected_improvement(mu_o, var_o, gp_oracle.incumbent_sum(st))
+    np.testing.assert_allclose(eis.reshape(-1), ei_o, rtol=RTOL32, atol=1e-9)
+    assert set(int(i) for i in idx) == set(int(i) for i in gp_oracle.top_n_distinct(eis.reshape(-1), 5))
+    # tuples of networkx graphs are the same thing
+    from nasbowl_b200.cells import OpVocab
+    vocab = OpVocab(synth.FAMILY_OPS[2])
+
+    def to_nx(b):
+        return b.to_networkx(vocab)
+    pairs = list(zip(to_nx(normal[n:n + 40]), to_nx(reduce_[n:n + 40])))
+    gp2 = _gp(list(zip(to_nx(normal[:n]), to_nx(reduce_[:n]))), y,
+              [WeisfilerLehman(h=2, slot=0), WeisfilerLehman(h=2, slot=1)], weights=w)
+    gp2.fit(wl_subtree_candidates=(), optimize_lik=False)
+    mu2, var2 = gp2.predict_diag(pairs)
+    np.testing.assert_allclose(mu2.numpy(), mu_o[:40], rtol=RTOL64, atol=1e-9)
+    np.testing.assert_allclose(var2.numpy(), var_o[:40], rtol=RTOL64, atol=1e-12)
+
+
+def test_layer_weights_and_undirected_kernels_on_the_fused_path(eng, family):
+    from nasbowl_b200.kernels import WeisfilerLehman
+    _, z, train, pool = family
+    y = z["y"].astype(np.float64)
+    lw = [1.0, 0.5, 0.25]
+    gp = _gp(train, y, [WeisfilerLehman(h=2, layer_weights=torch.tensor(lw))])
+    gp.fit(wl_subtree_candidates=(), optimize_lik=False)
+    st = gp_oracle.gp_fit_sum_fixed(train, y, [(2, False)], [1.0], layer_weights=[lw])
+    mu_o, var_o = gp_oracle.gp_predict_diag_sum(st, train, pool)
+    mu_d, var_d = gp.predict_diag(pool)
+    np.testing.assert_allclose(mu_d.numpy(), mu_o, rtol=RTOL64, atol=1e-9)
+    np.testing.assert_allclose(var_d.numpy(), var_o, rtol=RTOL64, atol=1e-12)
+    # undirected: the pool kernel symmetrises the adjacency itself (kernels/weisfilerlehman.py:127-128)
+    gp = _gp(train, y, [WeisfilerLehman(h=2, undirected=True)])
+    gp.fit(wl_subtree_candidates=(), optimize_lik=False)
+    st = gp_oracle.gp_fit(train.to_undirected(), y, h_candidates=(2,), optimize_lik=False)
+    mu_o, var_o = gp_oracle.gp_predict_diag(st, train.to_undirected(), pool.to_undirected())
+    mu_d, var_d = gp.predict_diag(pool)
+    np.testing.assert_allclose(mu_d.numpy(), mu_o, rtol=RTOL64, atol=1e-9)
+    np.testing.assert_allclose(var_d.numpy(), var_o, rtol=RTOL64, atol=1e-12)
+    # a directed and an undirected kernel of one sum read the same record
+    gp = _gp(train, y, [WeisfilerLehman(h=2), WeisfilerLehman(h=1, undirected=True)], weights=[0.6, 0.4])
+    gp.fit(wl_subtree_candidates=(), optimize_lik=False)
+    st = gp_oracle.gp_fit_sum_fixed([train, train.to_undirected()], y, [(2, False), (1, False)], [0.6, 0.4])
+    mu_o, var_o = gp_oracle.gp_predict_diag_sum(st, [train, train.to_undirected()], [pool, pool.to_undirected()])
+    mu_d, var_d = gp.predict_diag(pool)
+    np.testing.assert_allclose(mu_d.numpy(), mu_o, rtol=RTOL64, atol=1e-9)
+    np.testing.assert_allclose(var_d.numpy(), var_o, rtol=RTOL64, atol=1e-12)
+
+
+def test_pool_with_wider_cells_than_the_training_set(eng):
+    """A GP fitted on <= 8-node cells scores 16-node records: the device state is re-derived on wide records."""
+    from nasbowl_b200.kernels import WeisfilerLehman
+    train = synth.generate_cells_host(0, 5, 0, 60)
+    y = np.random.RandomState(1).randn(60)
+    gp = _gp(train, y, [WeisfilerLehman(h=2)])
+    gp.fit(wl_subtree_candidates=(1, 2), optimize_lik=True)
+    h, lik, nlml = gp.kernels[0].h, gp.likelihood, float(gp.nlml)
+    small = synth.generate_cells_host(0, 6, 500, 50)
+    mu_a, var_a = gp.predict_diag(small)
+    wide = synth.generate_cells_host(2, 6, 0, 50)             # DARTS cells, ops outside the training vocabulary
+    mu_w, var_w = gp.predict_diag(wide)
+    assert gp._dev['n_max'] == 16 and gp.kernels[0].h == h and gp.likelihood == lik and float(gp.nlml) == nlml
+    mu_b, var_b = gp.predict_diag(small)
+    np.testing.assert_allclose(mu_a.numpy(), mu_b.numpy(), rtol=1e-10)
+    np.testing.assert_allclose(var_a.numpy(), var_b.numpy(), rtol=1e-10)
+    st = gp_oracle.gp_fit(train, y, h_candidates=(1, 2), optimize_lik=True)
+    mu_o, var_o = gp_oracle.gp_predict_diag(st, train.widen(16), wide)
+    np.testing.assert_allclose(mu_w.numpy(), mu_o, rtol=RTOL64, atol=1e-9)
+    np.testing.assert_allclose(var_w.numpy(), var_o, rtol=RTOL64, atol=1e-12)
+
+
+def test_fused_topk_distinct_rule_and_host_pipelines(eng):
+    """NB201 pools repeat architectures: equal scores must be reported once, at their first index
+    (acquisitions.py:101-105).  Device, staged-host and mapped-host entry points agree."""
+    from nasbowl_b200.bayesopt import GraphExpectedImprovement
+    from nasbowl_b200.kernels import WeisfilerLehman
+    train = synth.generate_cells_host(1, 5, 0, 100)
+    y = np.random.RandomState(2).randn(100)
+    gp = _gp(train, y, [WeisfilerLehman(h=2)])
+    gp.fit(wl_subtree_candidates=(2,), optimize_lik=False)
+    acq = GraphExpectedImprovement(gp)
+    M = 200_003
+    pool = eng.generate_cells(1, 9, 0, M)
+    s = acq.score_pool(pool)[0].cpu().numpy()
+    for k in (1, 3, 5, 8):
+        for distinct in (True, False):
+            xs, eis, idx = acq.propose_location(pool, top_n=k, return_distinct=distinct)
+            v_t, i_t = eng.topk(torch.from_numpy(s).cuda(), k, distinct=distinct)
+            assert np.array_equal(idx, i_t), (k, distinct)
+    host = torch.empty((M, 16), dtype=torch.uint8).pin_memory()
+    host.copy_(pool.cpu())
+    ref_v, ref_i = eng.topk(torch.from_numpy(s).cuda(), 5, distinct=True)
+    model = acq._model()
+    for mapped, pieces in ((False, 1), (False, 8), (False, 5), (True, 1), (True, 4)):
+        cands, hs = eng.propose_host(model, host, 5, True, chunks=pieces, mapped=mapped)
+        v, i = eng.cands_read(cands, 5)
+        assert np.array_equal(i, ref_i) and np.array_equal(v, ref_v), (mapped, pieces)
+        np.testing.assert_array_equal(hs.numpy(), s)
+    xs, eis, idx = acq.propose_location(host, top_n=5)
+    assert np.array_equal(idx, ref_i)
+    np.testing.assert_array_equal(eis.reshape(-1), s)
+    # k > 8 falls back to score + tournament
+    xs, eis, idx = acq.propose_location(pool, top_n=12)
+    v_t, i_t = eng.topk(torch.from_numpy(s).cuda(), 12, distinct=True)
+    assert np.array_equal(idx, i_t)
+
+
+# ---------------------------------------------------------------------------- BASELINE configs[2] / configs[3] sizes
+def test_cfg3_nb101_n500(eng):
+    """BASELINE configs[2]: NAS-Bench-101-shaped cells, n_train = 500, WL h = 2, EI + top-5 — at the
+    training-set size of the config, 6000 candidates against the oracle, 1M through properties."""
+    from nasbowl_b200.bayesopt import GraphExpectedImprovement
+    from nasbowl_b200.kernels import WeisfilerLehman
+    n = 500
+    train = synth.generate_cells_host(0, 0, 0, n)
+    y = torch.randn(n, generator=torch.Generator().manual_seed(0)).numpy().astype(np.float64)
+    gp = _gp(train, y, [WeisfilerLehman(h=2)])
+    gp.fit(wl_subtree_candidates=(2,), optimize_lik=True, max_lik=0.01)
+    st = gp_oracle.gp_fit(train, y, h_candidates=(2,), optimize_lik=True, max_lik=0.01)
+    assert np.float32(gp.likelihood) == np.float32(st.lik)
+    M = 1_000_000
+    pool = eng.generate_cells(0, 1234, 10_000, M)
+    acq = GraphExpectedImprovement(gp)
+    s, mu, var, s64 = acq.score_pool(pool, want64=True)
+    S = 6000
+    sub = CellBatch.from_records(pool[:S].cpu().numpy(), 8)
+    mu_o, var_o = gp_oracle.gp_predict_diag(st, train, sub)
+    ei_o = gp_oracle.expected_improvement(mu_o, var_o, gp_oracle.incumbent(st))
+    np.testing.assert_allclose(mu.cpu().numpy()[:S], mu_o, rtol=RTOL64, atol=1e-9)
+    np.testing.assert_allclose(var.cpu().numpy()[:S], var_o, rtol=RTOL64, atol=1e-12)
+    np.testing.assert_allclose(s64.cpu().numpy()[:S], ei_o, rtol=RTOL64, atol=1e-12)
+    np.testing.assert_allclose(s.cpu().numpy()[:S], ei_o, rtol=RTOL32, atol=1e-9)
+    xs, eis, idx = acq.propose_location(pool[:S].contiguous(), top_n=5)
+    assert set(int(i) for i in idx) == set(int(i) for i in gp_oracle.top_n_distinct(ei_o.astype(np.float32), 5))
+    xs, eis, idx = acq.propose_location(pool, top_n=5)
+    assert set(int(i) for i in idx) == set(int(i) for i in gp_oracle.top_n_distinct(s.cpu().numpy(), 5))
+
+
+def test_cfg4_darts_n1000(eng):
+    """BASELINE configs[3]: DARTS-space normal + reduce cells, summed WL kernels, n_train = 1000, h = 2."""
+    from nasbowl_b200.bayesopt import GraphExpectedImprovement
+    from nasbowl_b200.kernels import WeisfilerLehman
+    n = 1000
+    normal = synth.generate_cells_host(2, 0, 0, n)
+    reduce_ = synth.generate_cells_host(2, 1, 0, n)
+    y = torch.randn(n, generator=torch.Generator().manual_seed(0)).numpy().astype(np.float64)
+    w = [0.5, 0.5]
+    gp = _gp(CellSlots([normal, reduce_]), y, [WeisfilerLehman(h=2, slot=0), WeisfilerLehman(h=2, slot=1)], weights=w)
+    gp.fit(wl_subtree_candidates=(), optimize_lik=False)
+    st = gp_oracle.gp_fit_sum_fixed([normal, reduce_], y, [(2, False), (2, False)], w)
+    np.testing.assert_allclose(gp.K.numpy(), st.K, rtol=1e-12)
+    M = 200_000
+    pn = eng.generate_cells(2, 1234, 10_000, M)
+    pr = eng.generate_cells(2, 4321, 10_000, M)
+    pool = torch.cat([pn, pr], dim=1).contiguous()            # two 48-byte records per candidate
+    acq = GraphExpectedImprovement(gp)
+    s, mu, var, s64 = acq.score_pool(pool, want64=True)
+    S = 2000
+    subs = [CellBatch.from_records(pn[:S].cpu().numpy(), 16), CellBatch.from_records(pr[:S].cpu().numpy(), 16)]
+    mu_o, var_o = gp_oracle.gp_predict_diag_sum(st, [normal, reduce_], subs, chunk=1000)
+    ei_o = gp_oracle.expected_improvement(mu_o, var_o, gp_oracle.incumbent_sum(st))
+    np.testing.assert_allclose(mu.cpu().numpy()[:S], mu_o, rtol=RTOL64, atol=1e-9)
+    np.testing.assert_allclose(var.cpu().numpy()[:S], var_o, rtol=RTOL64, atol=1e-12)
+    np.testing.assert_allclose(s64.cpu().numpy()[:S], ei_o, rtol=RTOL64, atol=1e-12)
+    xs, eis, idx = acq.propose_location(pool, top_n=5)
+    assert set(int(i) for i in idx) == set(int(i) for i in gp_oracle.top_n_distinct(s.cpu().numpy(), 5))
+
+
+# ---------------------------------------------------------------------------- Gram epilogues / symmetric schedule
+def test_gram_output_modes_and_symmetric_schedule(eng):
+    """nbw_gram_i8_ex: u8 / s16 (saturating) / cosine-normalised fp32 epilogues and the upper-tiles-only
+    schedule + mirror pass are bit-identical to the int32 product (vertex_histogram.py:243)."""
+    rng = np.random.RandomState(5)
+    for (m, k, hi) in [(1, 128, 3), (300, 256, 3), (513, 384, 4), (1100, 640, 2), (2049, 128, 9)]:
+        A = torch.from_numpy(rng.randint(0, hi, size=(m, k)).astype(np.int8)).cuda()
+        ref = A.cpu().numpy().astype(np.int64) @ A.cpu().numpy().astype(np.int64).T
+        assert np.array_equal(eng.gram_ex(A, A, 0, k, mode="s32").cpu().numpy(), ref)
+        ovf = torch.zeros(1, dtype=torch.int32, device="cuda")
+        u8 = eng.gram_ex(A, A, 0, k, mode="u8", overflow=ovf).cpu().numpy()
+        assert np.array_equal(u8, np.clip(ref, 0, 255).astype(np.uint8))
+        assert bool(ovf.item()) == bool((ref > 255).any())
+        s16 = eng.gram_ex(A, A, 0, k, mode="s16").cpu().numpy()
+        assert np.array_equal(s16, np.clip(ref, -32768, 32767).astype(np.int16))
+        d = np.maximum(np.diag(ref), 1).astype(np.float64)
+        sc = torch.from_numpy((1.0 / np.sqrt(d)).astype(np.float32)).cuda()
+        f32 = eng.gram_ex(A, A, 0, k, mode="f32norm", scale_a=sc, scale_b=sc).cpu().numpy()
+        np.testing.assert_allclose(f32, ref * np.outer(sc.cpu().numpy(), sc.cpu().numpy()), rtol=3e-7)
+        # symmetric schedule in row blocks of 512 + mirror == full product
+        ld = (m + 15) // 16 * 16
+        full = torch.zeros((m, ld), dtype=torch.uint8, device="cuda")
+        for r0 in range(0, m, 512):
+            rows = min(512, m - r0)
+            eng.gram_ex(A[r0:r0 + rows], A, 0, k, mode="u8", upper_only=True, row_offset=r0, out=full[r0:r0 + rows])
+        upper = full[:, :m].cpu().numpy()
+        iu = np.triu_indices(m)
+        assert np.array_equal(upper[iu], np.clip(ref, 0, 255).astype(np.uint8)[iu])
+        eng.sym_mirror(full)
+        assert np.array_equal(full[:, :m].cpu().numpy(), np.clip(ref, 0, 255).astype(np.uint8))
+    # negative operands through the signed narrow path
+    A = torch.from_numpy(rng.randint(-128, 128, size=(200, 256)).astype(np.int8)).cuda()
+    B = torch.from_numpy(rng.randint(-128, 128, size=(333, 256)).astype(np.int8)).cuda()
+    ref = A.cpu().numpy().astype(np.int64) @ B.cpu().numpy().astype(np.int64).T
+    ovf = torch.zeros(1, dtype=torch.int32, device="cuda")
+    s16 = eng.gram_ex(A, B, 0, 256, mode="s16", overflow=ovf).cpu().numpy()
+    assert np.array_equal(s16, np.clip(ref, -32768, 32767).astype(np.int16)) and int(ovf.item()) == 1
+
+
+def test_gram_stress_small(eng):
+    """The configs[4] driver (Engine.gram_stress) at a size the oracle finishes: u8 result == oracle Gram."""
+    from oracle import wl_oracle
+    N = 3000
+    cells = eng.generate_cells(0, 2024, 0, N)
+    fit = eng.wl_fit(cells, 8, 3, False)
+    res = eng.gram_stress(fit, fit.k_end(3), 1024)
+    assert all(res["checks"].values()), res["checks"]
+    assert 0.5 < res["computed_fraction"] < 0.75
+    K_o = wl_oracle.gram_raw(CellBatch.from_records(cells.cpu().numpy(), 8), 3)
+    assert np.array_equal(res["result"][:N, :N].cpu().numpy().astype(np.int64), K_o)

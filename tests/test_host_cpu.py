@@ -249,7 +249,26 @@ if rank == 0:
     pm.H = torch.full((61, 61), 2.5, dtype=torch.float64)
     pm.w_mu_prefix = torch.zeros(61, dtype=torch.float64)
     pm.lik, pm.y_mean, pm.y_std, pm.incumbent, pm.incumbent_idx = 0.01, 0.5, 2.0, 1.25, 9
+    # packed-path tables and a second part of a sum (reads record slot 1, undirected, weighted levels)
+    pm.id_hash = [None, torch.full((80,), 7, dtype=torch.uint8), None]
+    pm.bucket_tags = [None, torch.full((256,), 1, dtype=torch.uint8), None]
+    pm.bucket_entries = [None, torch.full((1024,), 2, dtype=torch.uint8), None]
+    pm.bucket_masks = [0, 15, 0]
+    pm.n_slots, pm.total_labels = 2, 100
+    p2 = PoolModel()
+    p2.n_max, p2.h, p2.seed, p2.slot, p2.undirected = 8, 1, 78, 1, True
+    p2.level0 = torch.zeros(256, dtype=torch.int16)
+    p2.tables, p2.masks = [None, torch.full((32,), 9, dtype=torch.uint8)], [0, 1]
+    p2.col_off, p2.label_off, p2.n_features, p2.n_labels = [0, 128, 256], [0, 5, 40], 256, 40
+    p2.level_weight, p2.label_base = [0.5, 0.25], 60
+    p2.child = torch.arange(40, dtype=torch.int32)
+    pm.more = [p2]
 pm = parallel.broadcast_pool_model(pm, src=0, device="cpu")
+assert len(pm.more) == 1 and pm.n_slots == 2 and pm.total_labels == 100 and pm.bucket_masks == [0, 15, 0]
+assert pm.id_hash[0] is None and int(pm.id_hash[1].sum()) == 7 * 80 and int(pm.bucket_entries[1].sum()) == 2048
+q = pm.more[0]
+assert (q.slot, q.undirected, q.level_weight, q.label_base, q.h) == (1, True, [0.5, 0.25], 60, 1)
+assert q.child.dtype == torch.int32 and q.child.tolist() == list(range(40)) and int(q.tables[1].sum()) == 9 * 32
 assert pm.h == 2 and pm.seed == 77 and pm.masks == [0, 3, 7] and pm.incumbent == 1.25
 assert pm.tables[0] is None and int(pm.tables[2].sum()) == 5 * 128 and float(pm.G[384, 384]) == 385 * 385 - 1
 assert float(pm.H.sum()) == 2.5 * 61 * 61 and pm.level0[255] == 255
@@ -518,6 +537,18 @@ def test_stable_suffix_detection_and_child_table():
     off = fit.label_off
     for z, par in enumerate([1, 3, 0, 2]):                    # label z of level 4 has parent `par` at level 3
         assert child[off[3] + par] == z
+    # final_label: a stable label -> global stacked index of its descendant at the deepest level
+    assert pm.final_label.tolist()[off[4]:off[5]] == [off[4] + z for z in range(4)]
+    pm.set_label_base(100)
+    assert pm.final_label.tolist()[off[4]:off[5]] == [100 + off[4] + z for z in range(4)]
+    fit5 = fake([3, 3, 4, 4, 4, 4], {3: [2, 0, 3, 1], 4: [1, 3, 0, 2], 5: [3, 2, 1, 0]})
+    pm5 = PoolModel()
+    pm5._find_stable_suffix(fit5, 5)
+    o5 = fit5.label_off
+    fl = pm5.final_label.tolist()
+    for z4 in range(4):                                        # level-4 label z4 -> its child at level 5
+        kid = [z for z, par in enumerate([3, 2, 1, 0]) if par == z4][0]
+        assert fl[o5[4] + z4] == o5[5] + kid
     # depth 3 only: level 3 needs D_2 == D_1 (4 vs 4 here -> stable from 3)
     pm = PoolModel()
     pm._find_stable_suffix(fake([3, 4, 4, 4], {3: [2, 0, 3, 1]}), 3)
