@@ -392,6 +392,12 @@ int nbw_topk_device(nbw_ctx* ctx, const float* scores, int64_t n, int k, int dis
 int nbw_topk_merge(nbw_ctx* ctx, const void* cands, int64_t count, int k, int distinct,
                    float* top_val_h, int64_t* top_idx_h, int* n_found_h, void* stream);
 
+/* nbw_topk_merge without the read-back (acquisitions.py:101-105 applied to the union of the ranks' lists): the
+ * merged list stays on the device in out_cands[k]; enqueues only.  Up to 4096 entries are merged by one CTA
+ * without touching the context's scratch arena, so the call may run on a side stream beside a scoring launch. */
+int nbw_topk_merge_device(nbw_ctx* ctx, const void* cands, int64_t count, int k, int distinct,
+                          void* out_cands, void* stream);
+
 /* Read a k-entry device list (nbw_topk_device / nbw_score_pool_topk / nbw_propose_host) back to the host:
  * the indices propose_location returns (acquisitions.py:105-113).  Syncs, and awaits pending host scores. */
 int nbw_cands_read(nbw_ctx* ctx, const void* cands, int k, float* top_val_h, int64_t* top_idx_h,

@@ -117,6 +117,7 @@ _PROTOTYPES = {
     "nbw_pool_features": (C.c_int, [_vp, C.POINTER(Model), _vp, _i64, _vp, _i64, _vp, _vp]),
     "nbw_topk": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i64, C.POINTER(C.c_float), C.POINTER(_i64),
                            C.POINTER(_i32), _vp]),
+    "nbw_topk_merge_device": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "nbw_cands_read": (C.c_int, [_vp, _vp, _i32, C.POINTER(C.c_float), C.POINTER(_i64), C.POINTER(_i32), _vp]),
     "nbw_propose_host": (C.c_int, [_vp, C.POINTER(Model), _vp, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _i64, _vp, _vp]),
     "nbw_topk_device": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i64, _vp, _vp]),

@@ -97,16 +97,16 @@ class GraphExpectedImprovement(BaseAcquisition):
             eng.lib.nbw_range_pop()
 
     def _host_policy(self, model, candidates):
-        """(mapped, pieces) for a pool of packed records in host memory: the staged H2D / kernel / D2H
-        pipeline, unless the pool is pinned AND the kernel is clearly slower than the PCIe transfer of its
-        records — then the kernel reads them itself (nbw_score_pool_mapped).  Measured per 1M candidates
-        (profiles/r01_e2e_probe*.txt, first-generation kernel): 16-byte records at h = 5: mapped 0.57 ms vs
-        staged 0.61; at h = 2: 0.54 vs 0.46; 48-byte records at h = 2: 1.96 vs 1.10.  The packed kernel is
-        faster than the transfer of its records everywhere measured, so only oa models (general path)
-        still take the mapped form."""
-        if candidates.is_pinned() and model.oa and model.n_max == 8 and model.h >= 5:
+        """(mapped, pieces) for a pool of packed records in host memory.  The packed kernel is faster than the
+        PCIe transfer of its records on every workload measured (profiles/r02_e2e_probe_*.txt), so the pool goes
+        through the staged H2D / kernel / D2H pipeline in pieces of ~12 MB (2 pieces for 1M 16-byte records:
+        0.63 ms; 8-16 for 192 MB of DARTS pairs: 4.6 ms, against 16-22 ms when the kernel reads mapped host
+        memory itself).  Only pinned oa pools on the general path at h >= 5 — a kernel slower than the
+        transfer — still take the mapped form (profiles/r01_e2e_probe.txt: 0.57 vs 0.61 ms)."""
+        if model.oa and model.n_max == 8 and model.h >= 5 and candidates.is_pinned():
             return True, 1
-        return False, 8
+        nbytes = candidates.shape[0] * candidates.shape[1]
+        return False, int(min(16, max(2, -(-nbytes // (12 << 20)))))
 
     def _propose(self, eng, model, candidates, top_n, return_distinct):
         host_scores = scores = None

@@ -33,8 +33,9 @@ struct nbw_ctx {
   cudaEvent_t prof_ev[2];   // optional caller-owned events recorded right before / after the scoring kernel
   int packed_occ[32];   // resident CTAs per SM of each score_packed_kernel variant (0 = not queried yet)
   void* piece_cands;    // per-piece top-n lists of the host-buffer entry points (score_pool.cu)
-  void* topk_blocks;    // per-CTA top-n lists of the fused scoring kernel (score_packed.cu)
+  void* topk_blocks;    // per-CTA top-n lists of the fused scoring kernel (score_packed.cu), two alternating slots
   size_t topk_blocks_bytes;
+  int topk_slot;
 };
 enum { NBW_ATTR_TRSV = 1u << 0, NBW_ATTR_SMALL_SORT = 1u << 1, NBW_ATTR_GRAM_SINGLE = 1u << 2, NBW_ATTR_CHOL_SMALL = 1u << 3,
        NBW_ATTR_GRAM_PAIR = 1u << 8 /* << output mode: bits 8..11 */ };
@@ -87,8 +88,9 @@ struct NbwCand {
 };
 // Tournament merge of `count` device candidates into the k best, left on the device in *result (scratch
 // memory, valid until the next scratch user).  topk.cu.
+// `direct` (optional): when the input fits one chunk the list is written there and no scratch is touched.
 int nbw_topk_merge_enqueue(nbw_ctx* ctx, const NbwCand* cands, int64_t count, int k, int distinct, NbwCand** result,
-                           cudaStream_t st);
+                           cudaStream_t st, NbwCand* direct = nullptr);
 
 // Packed scoring path (score_packed.cu): applicability test and launch (k = 0: scores only).
 bool nbw_packed_applicable(const nbw_model* M);

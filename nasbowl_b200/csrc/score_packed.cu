@@ -96,7 +96,7 @@ __device__ __forceinline__ bool cand_better(float v, int i, float bv, int bi) {
 }
 
 template <int NMAX, int NP, bool WEIGHTED, bool TOPK>
-__global__ void __launch_bounds__(kPackThreads, 3)
+__global__ void __launch_bounds__(kPackThreads, NMAX == 8 ? 5 : 4)
 score_packed_kernel(const __grid_constant__ PackedParams P, const uint8_t* __restrict__ cells, int64_t n_cells,
                     int64_t per_warp, float* __restrict__ scores, double* __restrict__ mu64,
                     double* __restrict__ var64, double* __restrict__ score64, NbwCand* __restrict__ block_cands,
@@ -114,51 +114,75 @@ score_packed_kernel(const __grid_constant__ PackedParams P, const uint8_t* __res
   const double* __restrict__ H = P.H;
   const int64_t ldh = P.ld_h;
 
-  // results staged until (almost) every lane holds a candidate: the fp64 acquisition epilogue then runs
-  // with the warp full instead of once per pass with a few lanes
-  double st_mu = 0.0, st_q = 0.0, st_k = 0.0;
-  int64_t st_g = -1;
-  int staged = 0;
-  float tv[kTopMax];
-  int ti[kTopMax];
+  // Results are staged until (almost) every lane holds a candidate: the fp64 acquisition epilogue then runs
+  // with the warp full instead of once per pass with a few lanes.  Staging slots and the lanes' top-n lists
+  // live in shared memory (one column per thread, conflict-free): they are touched once per pass / per flush,
+  // and keeping them out of the register file buys a fourth and fifth resident CTA.
+  __shared__ double sh_mu[kPackThreads], sh_q[kPackThreads], sh_k[kPackThreads];
+  __shared__ int sh_g[kPackThreads];
+  __shared__ float sh_tv[TOPK ? kTopMax : 1][kPackThreads];
+  __shared__ int sh_ti[TOPK ? kTopMax : 1][kPackThreads];
+  const int tid = threadIdx.x;
+  // succ_lut[mask]: positions of the four lowest set bits of an 8-bit successor mask (4 bits each; positions
+  // beyond the population repeat a harmless 0) | the remaining bits << 16
+  __shared__ uint32_t succ_lut[NMAX == 8 ? 256 : 1];
+  if (NMAX == 8) {
+    uint32_t m = (uint32_t)tid, pk = 0u;
 #pragma unroll
-  for (int j = 0; j < kTopMax; ++j) { tv[j] = 0.f; ti[j] = -1; }
+    for (int t = 0; t < 4; ++t) {
+      if (m) pk |= (uint32_t)(__ffs(m) - 1) << (4 * t);
+      m &= m - 1u;
+    }
+    succ_lut[tid] = pk | (m << 16);
+    __syncthreads();
+  }
+  int staged = 0;
+  sh_g[tid] = -1;
+  if constexpr (TOPK) {
+#pragma unroll
+    for (int j = 0; j < kTopMax; ++j) { sh_tv[j][tid] = 0.f; sh_ti[j][tid] = -1; }
+  }
+  __syncwarp();
 
   auto flush = [&]() {
-    if (st_g >= 0) {
+    const int gl = sh_g[tid];                 // index of the staged candidate inside this launch's pool
+    if (gl >= 0) {
       double mu, var;
-      const double sc = finish_score(P, st_mu, st_q, st_k, mu, var);
+      const double sc = finish_score(P, sh_mu[tid], sh_q[tid], sh_k[tid], mu, var);
       const float scf = (float)sc;
-      if (scores) scores[st_g] = scf;
-      if (mu64) mu64[st_g] = mu;
-      if (var64) var64[st_g] = var;
-      if (score64) score64[st_g] = sc;
-      if (TOPK && scf == scf) {
+      if (scores) scores[gl] = scf;
+      if (mu64) mu64[gl] = mu;
+      if (var64) var64[gl] = var;
+      if (score64) score64[gl] = sc;
+      if constexpr (TOPK) if (scf == scf) {
         // sorted insert into this lane's list: value desc, index asc; in distinct mode a value already in the
-        // list keeps its lowest index (warps walk their cells in ascending order, but stay order-agnostic)
-        const int ci0 = (int)st_g;
+        // list keeps its lowest index
         bool skip = false;
         if (distinct) {
 #pragma unroll
-          for (int j = 0; j < kTopMax; ++j)
-            if (ti[j] >= 0 && tv[j] == scf) { ti[j] = ci0 < ti[j] ? ci0 : ti[j]; skip = true; }
+          for (int j = 0; j < kTopMax; ++j) {
+            const int tj = sh_ti[j][tid];
+            if (tj >= 0 && sh_tv[j][tid] == scf) { sh_ti[j][tid] = gl < tj ? gl : tj; skip = true; }
+          }
         }
-        if (!skip) {
+        if (!skip && cand_better(scf, gl, sh_tv[k_top - 1][tid], sh_ti[k_top - 1][tid])) {
           float cv = scf;
-          int ci = ci0;
+          int ci = gl;
 #pragma unroll
           for (int j = 0; j < kTopMax; ++j) {
-            if (j < k_top && ci >= 0 && cand_better(cv, ci, tv[j], ti[j])) {
-              const float ov = tv[j];
-              const int oi = ti[j];
-              tv[j] = cv; ti[j] = ci;
-              cv = ov; ci = oi;
+            if (j < k_top && ci >= 0) {
+              const float ov = sh_tv[j][tid];
+              const int oi = sh_ti[j][tid];
+              if (cand_better(cv, ci, ov, oi)) {
+                sh_tv[j][tid] = cv; sh_ti[j][tid] = ci;
+                cv = ov; ci = oi;
+              }
             }
           }
         }
       }
     }
-    st_g = -1;
+    sh_g[tid] = -1;
     staged = 0;
   };
 
@@ -231,55 +255,98 @@ score_packed_kernel(const __grid_constant__ PackedParams P, const uint8_t* __res
       const uint32_t d0 = present ? (uint32_t)__ldg(Q.level0_table + label) : 0xFFFFu;
       bool in_dict = present && d0 != 0xFFFFu;
       uint32_t dense_prev = in_dict ? d0 : 0u;
-      uint32_t cls = 0u;      // nodes of my cell (bit j) that share my label at the current level
+      // nodes of my cell (bit j) that share my label at the current level.  Level 0: equal op codes, found
+      // with eight ballots over the bits of the code (exact for any u8 code) instead of a shuffle sweep.
+      uint32_t cls;
       {
-        const uint32_t mine = present ? label : (0x100u + (uint32_t)node);
+        const unsigned cell_lanes = ((my_n >= 32 ? 0u : (1u << my_n)) - 1u) << sub_base;
+        unsigned same = __ballot_sync(FULL, present) & cell_lanes;
 #pragma unroll
-        for (int j = 0; j < NMAX; ++j) {
-          const uint32_t other = __shfl_sync(FULL, mine, (sub_base + j) & 31);
-          cls |= (j < my_n && other == mine) ? (1u << j) : 0u;
+        for (int b = 0; b < 8; ++b) {
+          const unsigned vote = __ballot_sync(FULL, (label >> b) & 1u);
+          same &= ((label >> b) & 1u) ? vote : ~vote;
         }
-        if (!present) cls = 0u;
+        cls = present ? (same >> sub_base) : 0u;
       }
       int cnt = __popc(cls);
       KccT kss = 0;
       if (present) kss = WEIGHTED ? (KccT)(Q.lw[0] * cnt) : (KccT)cnt;
       int dp = in_dict ? Q.label_base + Q.loff[0] + (int)d0 : zero_slot;
 
+      // The successors of a node do not change from level to level: their lanes are resolved once.  8-node
+      // cells look the (up to four) lowest successor positions up in a 256-entry table built at kernel start
+      // (find-first-set runs on the quarter-rate XU pipe).
+      constexpr int kCached = 4;
+      int sl[kCached];
+      uint32_t rest;
+      if (NMAX == 8) {
+        const uint32_t pk = succ_lut[succ & 0xFFu];
+#pragma unroll
+        for (int t = 0; t < kCached; ++t) sl[t] = sub_base + (int)((pk >> (4 * t)) & 7u);
+        rest = pk >> 16;                      // successors beyond the fourth (bitmask)
+      } else {
+        rest = succ;
+#pragma unroll
+        for (int t = 0; t < kCached; ++t) {
+          sl[t] = rest ? (sub_base + __ffs(rest) - 1) : lane;
+          rest &= rest - 1u;
+        }
+      }
+      const int ns = __popc(succ);
+      const bool more2 = __any_sync(FULL, ns > 2);
+      const bool more4 = __any_sync(FULL, rest != 0u);
+      const unsigned succ_lanes = succ << sub_base;        // my successors as lanes of the warp
+
       // ---- levels 1..h
       const int h = Q.h, fs = Q.first_stable;
 #pragma unroll 1
       for (int l = 1; l <= h; ++l) {
         const bool stable = fs != 0 && l >= fs;   // nbw_model.child: membership is inherited, no signature
-        const uint32_t rep = cls ? (uint32_t)(__ffs(cls) - 1) : 0u;
-        const uint32_t word = (in_dict ? 0x80000000u : 0u) | (rep << 24) | dense_prev;
-        const uint4* __restrict__ idh = Q.id_hash[l];
+        // every successor's previous label is in the dictionary: one ballot instead of per-successor bookkeeping
+        const bool all_in = (succ_lanes & __ballot_sync(FULL, present && !in_dict)) == 0u;
+        // what a node contributes to its predecessors: one count in the 4-bit field of its previous class
+        // (the class representative is the lowest member: 2^rep -> 2^(4 rep) by two squarings on the FMA pipe)
+        SigT sigbit;
+        {
+          const uint32_t low = cls & (0u - cls);
+          const uint32_t sq = low * low;
+          sigbit = (SigT)sq * (SigT)sq;
+        }
+        // ... and, on hashed levels, the hashes of its previous id, FETCHED (nbw_model.id_hash)
+        uint32_t ha_lo = 0u, ha_hi = 0u, hb = 0u;
+        if (!stable) {
+          const uint4 e = __ldg(Q.id_hash[l] + dense_prev);
+          ha_lo = e.x; ha_hi = e.y; hb = e.z;
+        }
         SigT sig = 0;           // multiset of the successors' previous classes, 4 bits of count per class
-        bool all_in = true;     // every successor's previous label is in the dictionary
         uint64_t sum_a = 0;
         uint32_t sum_b = 0;
-        uint32_t ms = succ;
-        constexpr int kUnrolled = NMAX == 8 ? 2 : 4;   // most nodes of the three search spaces have few successors
-#define NBW_SUCC_ROUND()                                                                       \
+#define NBW_SUCC_ROUND(HAS, SRC)                                                               \
   {                                                                                            \
-    const bool has = ms != 0u;                                                                 \
-    const int j = has ? (__ffs(ms) - 1) : node;                                                \
-    const uint32_t w = __shfl_sync(FULL, word, (sub_base + j) & 31);                           \
-    sig += has ? ((SigT)1 << (4 * ((w >> 24) & 15u))) : (SigT)0;                               \
-    all_in = all_in && (!has || (w >> 31));                                                    \
-    if (!stable && has && (w >> 31)) {                                                         \
-      const uint4 e = __ldg(idh + (w & 0xFFFFFFu));                                            \
-      sum_a += ((uint64_t)e.y << 32) | e.x;                                                    \
-      sum_b += e.z;                                                                            \
+    const bool has = (HAS);                                                                    \
+    const SigT osb = shfl_sig(sigbit, (SRC));                                                  \
+    if (has) sig += osb;                                                                       \
+    if (!stable) {                                                                             \
+      const uint32_t olo = __shfl_sync(FULL, ha_lo, (SRC));                                    \
+      const uint32_t ohi = __shfl_sync(FULL, ha_hi, (SRC));                                    \
+      const uint32_t ob = __shfl_sync(FULL, hb, (SRC));                                        \
+      if (has) { sum_a += ((uint64_t)ohi << 32) | olo; sum_b += ob; }                          \
     }                                                                                          \
-    ms &= ms - 1u;                                                                             \
   }
-#pragma unroll
-        for (int t = 0; t < kUnrolled; ++t) NBW_SUCC_ROUND()
+        NBW_SUCC_ROUND(ns > 0, sl[0])
+        NBW_SUCC_ROUND(ns > 1, sl[1])
+        if (more2) {
+          NBW_SUCC_ROUND(ns > 2, sl[2])
+          NBW_SUCC_ROUND(ns > 3, sl[3])
+          if (more4) {
+            uint32_t ms = rest;
 #pragma unroll 1
-        for (int t = kUnrolled; t < NMAX; ++t) {
-          if (!__any_sync(FULL, ms != 0u)) break;
-          NBW_SUCC_ROUND()
+            while (__any_sync(FULL, ms != 0u)) {
+              const int j = ms ? (sub_base + __ffs(ms) - 1) : lane;
+              NBW_SUCC_ROUND(ms != 0u, j)
+              ms &= ms - 1u;
+            }
+          }
         }
 #undef NBW_SUCC_ROUND
         // a credential can only be in the training dictionary if all its ids are
@@ -287,21 +354,20 @@ score_packed_kernel(const __grid_constant__ PackedParams P, const uint8_t* __res
         bool seen = false;
         uint32_t dense = 0u;
         if (!stable) {
-          if (cand) {
-            const uint4 e = __ldg(idh + dense_prev);
-            LevelSalt salt;
-            salt.a_own = Q.a_own[l];
-            salt.b_own = Q.b_own[l];
-            const uint64_t key = nbw_key_from(((uint64_t)e.y << 32) | e.x, sum_a, salt);
-            const uint32_t chk = nbw_chk_from(e.z, sum_b, salt);
-            const uint32_t tag = (uint32_t)key, khi = (uint32_t)(key >> 32);
-            const uint32_t b = khi & Q.bucket_mask[l];
-            const uint4 t4 = __ldg(Q.tags[l] + b);
-            const int idx = t4.x == tag ? 0 : t4.y == tag ? 1 : t4.z == tag ? 2 : t4.w == tag ? 3 : -1;
-            if (idx >= 0) {
-              const uint4 en = __ldg(Q.entries[l] + 4 * (size_t)b + idx);
-              if (en.x == khi && en.y == chk) { seen = true; dense = en.z; }
-            }
+          // branch-free probe: every lane computes a key (lanes that are no candidates from id 0) and
+          // fetches one bucket of four tags; only a tag hit fetches the entry
+          LevelSalt salt;
+          salt.a_own = Q.a_own[l];
+          salt.b_own = Q.b_own[l];
+          const uint64_t key = nbw_key_from(((uint64_t)ha_hi << 32) | ha_lo, sum_a, salt);
+          const uint32_t chk = nbw_chk_from(hb, sum_b, salt);
+          const uint32_t tag = (uint32_t)key, khi = (uint32_t)(key >> 32);
+          const uint32_t b = khi & Q.bucket_mask[l];
+          const uint4 t4 = __ldg(Q.tags[l] + b);
+          const int idx = t4.x == tag ? 0 : t4.y == tag ? 1 : t4.z == tag ? 2 : t4.w == tag ? 3 : -1;
+          if (cand && idx >= 0) {
+            const uint4 en = __ldg(Q.entries[l] + 4 * (size_t)b + idx);
+            if (en.x == khi && en.y == chk) { seen = true; dense = en.z; }
           }
         } else if (cand) {
           seen = true;
@@ -391,7 +457,7 @@ score_packed_kernel(const __grid_constant__ PackedParams P, const uint8_t* __res
       const double s_mu = __shfl_sync(FULL, mu_acc, src);
       const double s_q = __shfl_sync(FULL, q_acc, src);
       const double s_k = __shfl_sync(FULL, kcc, src);
-      if (take) { st_mu = s_mu; st_q = s_q; st_k = s_k; st_g = g + c; }
+      if (take) { sh_mu[tid] = s_mu; sh_q[tid] = s_q; sh_k[tid] = s_k; sh_g[tid] = (int)(g + c); }
     }
     staged += m;
     g += m;
@@ -399,7 +465,7 @@ score_packed_kernel(const __grid_constant__ PackedParams P, const uint8_t* __res
   }
   if (staged > 0) flush();
 
-  if (TOPK) {
+  if constexpr (TOPK) {
     // ---- CTA tournament over the lanes' lists: k rounds of (value desc, index asc) arg-max with the
     // distinct-by-value rule of acquisitions.py:101-105; the list of the block goes to block_cands
     __shared__ float sv[kPackWarps];
@@ -414,10 +480,12 @@ score_packed_kernel(const __grid_constant__ PackedParams P, const uint8_t* __res
       int bi = -1;
 #pragma unroll
       for (int j = 0; j < kTopMax; ++j) {
-        bool eligible = j < k_top && ti[j] >= 0;
+        const float tvj = sh_tv[j][tid];
+        const int tij = sh_ti[j][tid];
+        bool eligible = j < k_top && tij >= 0;
         if (eligible && last_i >= 0)
-          eligible = distinct ? (tv[j] < last_v) : (tv[j] < last_v || (tv[j] == last_v && ti[j] > last_i));
-        if (eligible && cand_better(tv[j], ti[j], bv, bi)) { bv = tv[j]; bi = ti[j]; }
+          eligible = distinct ? (tvj < last_v) : (tvj < last_v || (tvj == last_v && tij > last_i));
+        if (eligible && cand_better(tvj, tij, bv, bi)) { bv = tvj; bi = tij; }
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -564,7 +632,9 @@ int launch_variant(nbw_ctx* ctx, int variant, const PackedParams& P, const uint8
   const int64_t per_warp = (n + warps - 1) / warps;
   NbwCand* blocks = nullptr;
   if (TOPK) {
-    const size_t bytes = sizeof(NbwCand) * (size_t)ctx->sm_count * 32 * kTopMax;
+    // two slots, alternating: the merge of launch i may still read its lists while launch i + 1 writes
+    const size_t slot_bytes = sizeof(NbwCand) * (size_t)ctx->sm_count * 32 * kTopMax;
+    const size_t bytes = 2 * slot_bytes;
     if (ctx->topk_blocks_bytes < bytes) {
       if (ctx->topk_blocks) {
         NBW_CUDA(ctx, cudaStreamSynchronize(st));
@@ -575,7 +645,8 @@ int launch_variant(nbw_ctx* ctx, int variant, const PackedParams& P, const uint8
       NBW_CUDA(ctx, cudaMalloc(&ctx->topk_blocks, bytes));
       ctx->topk_blocks_bytes = bytes;
     }
-    blocks = static_cast<NbwCand*>(ctx->topk_blocks);
+    ctx->topk_slot ^= 1;
+    blocks = reinterpret_cast<NbwCand*>(static_cast<char*>(ctx->topk_blocks) + (size_t)ctx->topk_slot * slot_bytes);
   }
   if (ctx->prof_ev[0]) NBW_CUDA(ctx, cudaEventRecord(ctx->prof_ev[0], st));
   kern<<<(unsigned)grid, kPackThreads, 0, st>>>(P, cells, n, per_warp, scores, mu64, var64, score64, blocks, k, distinct,
@@ -584,9 +655,9 @@ int launch_variant(nbw_ctx* ctx, int variant, const PackedParams& P, const uint8
   if (ctx->prof_ev[1]) NBW_CUDA(ctx, cudaEventRecord(ctx->prof_ev[1], st));
   if (TOPK) {
     NbwCand* res = nullptr;
-    int rc = nbw_topk_merge_enqueue(ctx, blocks, grid * k, k, distinct, &res, st);
+    int rc = nbw_topk_merge_enqueue(ctx, blocks, grid * k, k, distinct, &res, st, out_cands);
     if (rc) return rc;
-    NBW_CUDA(ctx, cudaMemcpyAsync(out_cands, res, sizeof(NbwCand) * k, cudaMemcpyDeviceToDevice, st));
+    if (res != out_cands) NBW_CUDA(ctx, cudaMemcpyAsync(out_cands, res, sizeof(NbwCand) * k, cudaMemcpyDeviceToDevice, st));
   }
   return NBW_OK;
 }
@@ -625,6 +696,7 @@ int nbw_score_packed(nbw_ctx* ctx, const nbw_model* M, const void* cells, int64_
   bool weighted = false;
   const int n_max = M->n_max;
   NBW_REQUIRE(ctx, n_max == 8 || n_max == 16, "model.n_max must be 8 or 16");
+  NBW_REQUIRE(ctx, n_cells < ((int64_t)1 << 31), "at most 2^31 - 1 cells per launch");
   const int rec = n_max == 8 ? 16 : 48;
   for (const nbw_model* part = M; part; part = static_cast<const nbw_model*>(part->next)) {
     NBW_REQUIRE(ctx, np < NBW_MAX_PARTS, "the fused pool path takes sums of up to %d kernels", NBW_MAX_PARTS);

@@ -575,9 +575,9 @@ int piece_cands(nbw_ctx* ctx, NbwCand** out) {
 }
 int merge_pieces(nbw_ctx* ctx, NbwCand* lists, int pieces, int k, int distinct, void* out_cands, cudaStream_t st) {
   NbwCand* res = nullptr;
-  int rc = nbw_topk_merge_enqueue(ctx, lists, (int64_t)pieces * k, k, distinct, &res, st);
+  int rc = nbw_topk_merge_enqueue(ctx, lists, (int64_t)pieces * k, k, distinct, &res, st, static_cast<NbwCand*>(out_cands));
   if (rc) return rc;
-  NBW_CUDA(ctx, cudaMemcpyAsync(out_cands, res, sizeof(NbwCand) * k, cudaMemcpyDeviceToDevice, st));
+  if (res != out_cands) NBW_CUDA(ctx, cudaMemcpyAsync(out_cands, res, sizeof(NbwCand) * k, cudaMemcpyDeviceToDevice, st));
   return NBW_OK;
 }
 }  // namespace

@@ -110,8 +110,19 @@ topk_round_kernel(const float* __restrict__ scores, const Cand* __restrict__ can
 // Tournament over `n` scores (or, when scores == NULL, over `n` candidates in `cands`); the
 // final k-entry list ends up in *result (scratch memory, valid until the next scratch user).
 static int topk_enqueue(nbw_ctx* ctx, const float* scores, const Cand* cands, int64_t n, int k, int distinct,
-                        int64_t index_base, Cand** result, cudaStream_t st) {
+                        int64_t index_base, Cand** result, cudaStream_t st, Cand* direct = nullptr) {
   int64_t blocks = (n + kTopChunk - 1) / kTopChunk;
+  if (blocks == 1 && direct != nullptr) {
+    // one chunk: its list IS the result — written straight to the caller's buffer, no scratch involved
+    // (which also makes this form safe on a side stream)
+    if (scores)
+      topk_round_kernel<false><<<1, kTopThreads, 0, st>>>(scores, nullptr, n, k, distinct, index_base, direct);
+    else
+      topk_round_kernel<true><<<1, kTopThreads, 0, st>>>(nullptr, cands, n, k, distinct, 0, direct);
+    NBW_CHECK_LAUNCH(ctx);
+    *result = direct;
+    return NBW_OK;
+  }
   const size_t list0 = (size_t)blocks * k;
   const size_t blocks1 = (list0 + kTopChunk - 1) / kTopChunk;
   const size_t list1 = blocks1 * (size_t)k;
@@ -139,8 +150,8 @@ static int topk_enqueue(nbw_ctx* ctx, const float* scores, const Cand* cands, in
 }
 
 int nbw_topk_merge_enqueue(nbw_ctx* ctx, const NbwCand* cands, int64_t count, int k, int distinct, NbwCand** result,
-                           cudaStream_t st) {
-  return topk_enqueue(ctx, nullptr, cands, count, k, distinct, 0, result, st);
+                           cudaStream_t st, NbwCand* direct) {
+  return topk_enqueue(ctx, nullptr, cands, count, k, distinct, 0, result, st, direct);
 }
 
 static int topk_readback(nbw_ctx* ctx, const Cand* dev, int k, float* top_val_h, int64_t* top_idx_h, int* n_found_h,
@@ -220,4 +231,22 @@ extern "C" int nbw_cands_read(nbw_ctx* ctx, const void* cands, int k, float* top
   NBW_REQUIRE(ctx, k >= 1 && k <= 1024 && cands && top_val_h && top_idx_h && n_found_h, "bad argument");
   return topk_readback(ctx, static_cast<const Cand*>(cands), k, top_val_h, top_idx_h, n_found_h,
                        static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int nbw_topk_merge_device(nbw_ctx* ctx, const void* cands, int64_t count, int k, int distinct,
+                                     void* out_cands, void* stream) {
+  if (!ctx) return NBW_ERR_INVALID;
+  NBW_REQUIRE(ctx, k >= 1 && k <= 1024 && count >= 0 && out_cands, "bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (count == 0) {
+    NBW_CUDA(ctx, cudaMemsetAsync(out_cands, 0xFF, sizeof(Cand) * k, st));
+    return NBW_OK;
+  }
+  NBW_REQUIRE(ctx, cands != nullptr, "cands is NULL");
+  Cand* res = nullptr;
+  int rc = topk_enqueue(ctx, nullptr, static_cast<const Cand*>(cands), count, k, distinct, 0, &res, st,
+                        static_cast<Cand*>(out_cands));
+  if (rc) return rc;
+  if (res != out_cands) NBW_CUDA(ctx, cudaMemcpyAsync(out_cands, res, sizeof(Cand) * k, cudaMemcpyDeviceToDevice, st));
+  return NBW_OK;
 }

@@ -599,6 +599,15 @@ class Engine:
                                              index_base, self._p(out), self.stream))
         return out
 
+    def topk_merge_device(self, cands: torch.Tensor, k: int, distinct: bool = True,
+                          out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """nbw_topk_merge_device: merge device lists into one device list uint8 [k * 16]; no sync."""
+        if out is None:
+            out = self.empty((k * 16,), torch.uint8)
+        self._check(self.lib.nbw_topk_merge_device(self.ctx, self._p(cands), cands.numel() // 16, k, int(distinct),
+                                                   self._p(out), self.stream))
+        return out
+
     def topk_merge(self, cands: torch.Tensor, k: int, distinct: bool = True):
         count = cands.numel() // 16
         vals = (C.c_float * k)()

@@ -149,6 +149,72 @@ def score_and_select(eng, model, cells: torch.Tensor, n_cells: int, k: int, dist
     return select_topk(eng, sc, k, distinct, index_base, cand_buf, gathered)
 
 
+CAND_DTYPE = np.dtype([("v", "<f4"), ("pad", "<i4"), ("idx", "<i8")])
+
+
+def parse_cands(raw: np.ndarray):
+    """16-byte device list entries {f32 value; i32 pad; i64 index} -> (values, indices), empties dropped."""
+    c = np.frombuffer(raw.tobytes(), dtype=CAND_DTYPE)
+    keep = c["idx"] >= 0
+    return c["v"][keep].astype(np.float32), c["idx"][keep].astype(np.int64)
+
+
+class PoolPipeline:
+    """Pool steps in flight: while pool i+1 is being scored on the main stream, the exchange of pool i — the
+    all-gather of the ranks' k-entry lists (NCCL over NVLink), the device merge and the 16 k-byte copy to pinned
+    host memory — runs on a side stream.  The per-pool collective thus leaves the critical path, and
+    a single GPU no longer stalls on a read-back between pools.
+
+        t = pipe.submit(model, cells, n, index_base)    # enqueue; returns a ticket
+        vals, idx = pipe.collect(t)                      # blocks until that pool's selection is on the host
+    """
+
+    def __init__(self, eng, k: int, distinct: bool = True, depth: int = 2):
+        self.eng, self.k, self.distinct, self.depth = eng, int(k), bool(distinct), int(depth)
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.side = torch.cuda.Stream(device=eng.device)
+        self.slots = []
+        for _ in range(depth):
+            self.slots.append(dict(cand=eng.empty((k * 16,), torch.uint8),
+                                   gathered=eng.empty((self.world * k * 16,), torch.uint8),
+                                   merged=eng.empty((k * 16,), torch.uint8),
+                                   host=torch.empty((k * 16,), dtype=torch.uint8).pin_memory(),
+                                   scored=torch.cuda.Event(), done=torch.cuda.Event(), busy=False))
+        self.head = 0
+
+    def submit(self, model, cells: torch.Tensor, n_cells: int, index_base: int = 0,
+               scores: Optional[torch.Tensor] = None) -> int:
+        eng, k = self.eng, self.k
+        ticket = self.head
+        slot = self.slots[ticket % self.depth]
+        if slot["busy"]:
+            raise RuntimeError("PoolPipeline: collect() ticket %d before submitting more pools" % (ticket - self.depth))
+        self.head += 1
+        if eng.fused_topk_ok(model, k):
+            eng.score_pool_topk(model, cells, n_cells, k, self.distinct, index_base, scores=scores, out=slot["cand"])
+        else:
+            sc, _, _, _ = eng.score_pool(model, cells, n_cells, scores=scores)
+            eng.topk_device(sc, k, distinct=self.distinct, index_base=index_base, out=slot["cand"])
+        main = torch.cuda.current_stream(eng.device)
+        slot["scored"].record(main)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(slot["scored"])
+            src = slot["cand"]
+            if self.world > 1:
+                dist.all_gather_into_tensor(slot["gathered"], slot["cand"])
+                src = eng.topk_merge_device(slot["gathered"], k, self.distinct, out=slot["merged"])
+            slot["host"].copy_(src, non_blocking=True)
+            slot["done"].record(self.side)
+        slot["busy"] = True
+        return ticket
+
+    def collect(self, ticket: int):
+        slot = self.slots[ticket % self.depth]
+        slot["done"].synchronize()
+        slot["busy"] = False
+        return parse_cands(slot["host"].numpy())
+
+
 def propose_location_sharded(acq, pool_shard, index_base: int, top_n: int = 5, return_distinct: bool = True):
     """Score this rank's shard (device records) and agree on the global top-n.
     Returns (top values, global indices, local scores device tensor)."""

@@ -1,0 +1,8 @@
+#!/bin/bash
+# quick iteration on the scoring kernel: parity tests of the packed path, then kernel time per config
+python -m pytest tests/test_gpu_packed.py -m gpu -q -x -k "not cfg4 and not gram" 2>&1 | tail -5
+for CFG in cfg2 cfg3 cfg4; do
+python bench.py --workload $CFG --configs "" --steps 10 --warmup 3 --skip-cpu 2> gpurun_out/iter_$CFG.err | python -c "
+import json,sys
+r=json.loads(sys.stdin.read()); print('$CFG', 'value %.3e'%r['value'], 'kernel_ms %.4f'%r['roofline']['kernel_ms'], 'ms/step %.4f'%r['ms_per_step'], 'e2e %.3e'%r['e2e']['value'])"
+done
