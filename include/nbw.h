@@ -89,6 +89,14 @@ int nbw_dict_build(nbw_ctx* ctx, const uint64_t* keys, const uint64_t* chks, int
                    uint32_t* ids, uint64_t* uniq_keys, uint64_t* uniq_chks, int64_t uniq_cap,
                    int64_t* n_unique_h, void* stream);
 
+/* (1) + (2) for every WL level of a batch in one call — the whole relabelling loop of
+ * WeisfeilerLehman.parse_input (weisfeiler_lehman.py:223-296): levels 0..h are relabelled and their dictionaries
+ * built back to back on the stream, with ONE read-back of the dictionary sizes at the end.
+ * ids: [h+1][N * n_max] u32; uniq_keys / uniq_chks: [h+1][N * n_max] u64 (level l's sorted dictionary at offset
+ * l * N * n_max); dims_h: [h+1] dictionary sizes.  Syncs once.  NBW_ERR_HASH_COLLISION as for nbw_dict_build. */
+int nbw_wl_fit(nbw_ctx* ctx, const void* cells, int64_t n_cells, int n_max, int h, uint64_t seed,
+               uint32_t* ids, uint64_t* uniq_keys, uint64_t* uniq_chks, int64_t* dims_h, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * (3) Vertex histograms — replaces VertexHistogram.parse_input,
  *     grakel_replace/vertex_histogram.py:98-209 (dense Phi of small integer counts).
@@ -182,6 +190,16 @@ int nbw_chol_f64(nbw_ctx* ctx, const double* A, int64_t lda, int64_t n, double s
 int nbw_gp_factor(nbw_ctx* ctx, const double* K, int64_t ldk, int64_t n, double lik,
                   const double* y, double* L, int64_t ldl, double* Linv, int64_t ldi,
                   double* alpha, double* stats_h, int* info_h, void* stream);
+/* The whole grid search over the WL depth in one launch (_grid_search_wl_kernel, bayesopt/gp.py:493-538): for
+ * every candidate c the UN-normalised Gram K_raw(h_c) = sum of the first n_levels_h[c] int32 level Grams
+ * (level l at level_grams + l * level_stride, [n x ldg] each) + lik I is factored by its own thread-block
+ * cluster; stats_h[2c] = log|K_raw(h_c) + lik I|, stats_h[2c + 1] = y^T (.)^-1 y, info_h[c] = 0 or failing
+ * pivot + 1 (the caller retries that candidate with 10x the jitter, utils.py:127-133).  Up to 8 candidates.
+ * Syncs once. */
+int nbw_gp_grid(nbw_ctx* ctx, const int32_t* level_grams, int64_t ldg, int64_t level_stride, int64_t n,
+                const int* n_levels_h, int n_cands, double lik, const double* y, double* stats_h,
+                int* info_h, void* stream);
+
 /* Gradient of the reference's marginal likelihood with respect to the weights of a SUM of kernels
  * (GraphGP.fit trains them by autograd: bayesopt/gp.py:141-210 through combine_kernels.py:36-56 and
  * utils.py:102-140).  Kinv = (N + lik I)^-1, alpha = Kinv y, N = normalised sum, inv_sqrt_diag from

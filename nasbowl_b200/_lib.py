@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libnbw.so")
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 SOURCES = ["nbw_api.cu", "wl_relabel.cu", "dict_build.cu", "histogram.cu", "gram_i8.cu",
-           "linalg_f64.cu", "score_pool.cu", "score_packed.cu", "topk.cu", "cellgen.cu"]
+           "linalg_f64.cu", "gp_factor.cu", "score_pool.cu", "score_packed.cu", "topk.cu", "cellgen.cu"]
 
 NBW_MAX_LEVELS = 8
 NBW_MAX_PARTS = 4
@@ -82,6 +82,7 @@ _PROTOTYPES = {
     "nbw_wl_signatures": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _i32, _u64, _vp, _vp, _vp]),
     "nbw_dict_build": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i64,
                                  C.POINTER(_i64), _vp]),
+    "nbw_wl_fit": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _u64, _vp, _vp, _vp, C.POINTER(_i64), _vp]),
     "nbw_hist_dense_i8": (C.c_int, [_vp, _vp, _i64, _i32, _i32, C.POINTER(_i64), C.POINTER(_i64), _vp,
                                     _i32, _vp, _i64, _vp, _vp]),
     "nbw_oa_thermo_layout": (C.c_int, [_vp, _vp, _i64, _i32, _i32, C.POINTER(_i64), _vp, _vp,
@@ -96,6 +97,8 @@ _PROTOTYPES = {
     "nbw_chol_f64": (C.c_int, [_vp, _vp, _i64, _i64, _f64, _vp, _i64, C.POINTER(_f64), C.POINTER(_i32), _vp]),
     "nbw_gp_factor": (C.c_int, [_vp, _vp, _i64, _i64, _f64, _vp, _vp, _i64, _vp, _i64, _vp,
                                 C.POINTER(_f64), C.POINTER(_i32), _vp]),
+    "nbw_gp_grid": (C.c_int, [_vp, _vp, _i64, _i64, _i64, C.POINTER(_i32), _i32, _f64, _vp, C.POINTER(_f64),
+                              C.POINTER(_i32), _vp]),
     "nbw_trtri_lower_f64": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i64, _vp]),
     "nbw_gemm_f64": (C.c_int, [_vp, _i32, _i32, _i64, _i64, _i64, _f64, _vp, _i64, _vp, _i64, _f64, _vp,
                                _i64, _vp]),

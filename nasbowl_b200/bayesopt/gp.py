@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import logging
 import math
+import os
 from copy import deepcopy
 from typing import List, Optional, Sequence
 
@@ -54,6 +55,32 @@ def _nlml_from_stats(logdet: float, yKy: float, n: int) -> float:
     """-compute_log_marginal_likelihood (bayesopt/utils.py:102-117) with the reference's
     logDetK = -log|K| (utils.py:138): (yKy/2 - log|K|/2 + n/2 log 2pi) / n."""
     return (0.5 * yKy - 0.5 * logdet + 0.5 * n * _LOG_2PI) / n
+
+
+class _Optim32:
+    """Adam / SGD on a handful of fp32 scalars with torch.optim's default arithmetic (Adam: betas (0.9, 0.999),
+    eps 1e-8, bias-corrected step lr / (1 - b1^t), denominator sqrt(v) / sqrt(1 - b2^t) + eps — the update of
+    gp.py:182-207).  The reference optimises <= 3 + #levels numbers; a torch optimiser object costs ~0.1 ms per
+    step on the host, twenty steps more than the whole device side of a fit."""
+
+    def __init__(self, kind: str, lr: float):
+        self.kind, self.lr, self.t = kind, np.float32(lr), 0
+        self.m, self.v = {}, {}
+
+    def step(self, name: str, p: torch.Tensor, grad: torch.Tensor):
+        x = p.detach().numpy()
+        g = grad.detach().numpy().astype(np.float32)
+        if self.kind == 'sgd':
+            x -= self.lr * g
+            return
+        b1, b2, eps = np.float32(0.9), np.float32(0.999), np.float32(1e-8)
+        m = self.m.get(name, np.zeros_like(x))
+        v = self.v.get(name, np.zeros_like(x))
+        m = b1 * m + (np.float32(1) - b1) * g
+        v = b2 * v + (np.float32(1) - b2) * g * g
+        self.m[name], self.v[name] = m, v
+        bc1, bc2 = np.float32(1.0 - 0.9 ** self.t), np.float32(1.0 - 0.999 ** self.t)
+        x -= (self.lr / bc1) * (m / (np.sqrt(v) / np.sqrt(bc2) + eps))
 
 
 class GraphGP:
@@ -172,9 +199,24 @@ class GraphGP:
         # the reference builds the jitter as `lik * torch.eye(n)` in fp32 (utils.py:129): the value
         # that reaches the fp64 Gram is fp32(lik); near-singular K_raw(h=0) makes that visible
         lik = float(np.float32(lik))
-        for hc in subtree_candidates:
-            K = k.gram_device(fit, hc)
-            _, _, _, logdet, yKy, _, _ = eng.pd_inverse(K, float(lik), y_dev, want_inverse=False)
+        cands = [int(c) for c in subtree_candidates]
+        batched = {}
+        plain = all(k._level_weights(hc) is None for hc in cands)
+        # (measured, profiles/r02_factor_bench.json: 6 candidates at n = 150 1.58 -> 0.24 ms, 4 at n = 500 2.9 -> 1.0 ms,
+        # 4 at n = 1000 6.1 -> 3.8 ms; a single candidate beyond n = 256 is faster through the per-panel launches)
+        if plain and 0 < len(cands) <= 8 and self.n <= int(os.environ.get("NBW_GRID_FUSED_MAX", "2048")) and \
+                (len(cands) >= 2 or self.n <= 256):
+            # all candidates in one launch, one cluster per depth, each summing its own level Grams (nbw_gp_grid)
+            G = eng.level_grams_i32(fit, max(cands))
+            for hc, (logdet, yKy, info) in zip(cands, eng.gp_grid(G, self.n, [hc + 1 for hc in cands], lik, y_dev)):
+                if info == 0:
+                    batched[hc] = (logdet, yKy)
+        for hc in cands:
+            if hc in batched:
+                logdet, yKy = batched[hc]
+            else:       # weighted levels, or a breakdown: compute_pd_inverse's retry with 10x / 100x the jitter
+                K = k.gram_device(fit, hc)
+                _, _, _, logdet, yKy, _, _ = eng.pd_inverse(K, float(lik), y_dev, want_inverse=False)
             nlml = _nlml_from_stats(logdet, yKy, self.n)
             grid[int(hc)] = nlml
             if nlml < best_nlml:
@@ -289,10 +331,30 @@ class GraphGP:
                 layer_weights.requires_grad_(True)
                 optim_vars.append(layer_weights)
             assert optimizer.lower() in ['adam', 'sgd']
-            optim = (torch.optim.Adam if optimizer.lower() == 'adam' else torch.optim.SGD)(optim_vars,
-                                                                                         **optimizer_kwargs)
+            light = set(optimizer_kwargs) <= {'lr'}          # default arithmetic: the fp32 numpy twin of torch.optim
+            if light:
+                optim = _Optim32(optimizer.lower(), optimizer_kwargs.get('lr', 1e-3 if optimizer.lower() == 'adam' else None))
+                for v in optim_vars:
+                    v.requires_grad_(False)
+            else:
+                optim = (torch.optim.Adam if optimizer.lower() == 'adam' else torch.optim.SGD)(optim_vars,
+                                                                                             **optimizer_kwargs)
+            # With the reference's sign quirk the noise gradient is negative for every K (Q9:
+            # -(|alpha|^2 + tr K_l^-1) / 2n, and tr K_l^-1 >= n / (n + lambda) for a unit-diagonal K), so the
+            # first Adam step is +lr (1 - eps/|g|) = +lr in fp32 and the clamp lands on max_lik: when only the
+            # noise is trained and lambda_0 + lr >= max_lik, the factorisation at lambda_0 cannot influence
+            # anything the fit returns (nlml is the value of the LAST iteration) and is skipped.
+            skip_first = (light and optimizer.lower() == 'adam' and optimize_lik and levels is None and iters >= 2
+                          and not self.verbose and float(likelihood) + float(optimizer_kwargs.get('lr', 1e-3)) * 0.999 >= max_lik
+                          and max_lik >= 1e-5)
             for i in range(iters):
-                optim.zero_grad()
+                if not light:
+                    optim.zero_grad()
+                if skip_first and i == 0:
+                    likelihood.fill_(max_lik)
+                    optim.t = 1
+                    optim.m['lik'], optim.v['lik'] = np.float32(-0.1) * np.ones((), np.float32), np.float32(1e-3) * np.ones((), np.float32)
+                    continue
                 if levels is not None:
                     # K moves with the weights: rebuild and refactor every iteration.  The K of the LAST
                     # iteration (weights before the final step) is the one the reference keeps (gp.py:186-215).
@@ -323,7 +385,16 @@ class GraphGP:
                     likelihood.grad = torch.tensor(-(0.5 * alpha_sq + 0.5 * trKinv) / self.n, dtype=likelihood.dtype)
                 if self.verbose and i % 10 == 0:
                     print('Iteration:', i, "/", iters, 'Negative log-marginal likelihood:', nlml, weights, likelihood)
-                optim.step()
+                if light:
+                    optim.t += 1
+                    if train_weights:
+                        optim.step('w', weights, weights.grad)
+                    if optimize_lik:
+                        optim.step('lik', likelihood, likelihood.grad)
+                    if layer_weights is not None:
+                        optim.step('lw', layer_weights, layer_weights.grad)
+                else:
+                    optim.step()
                 with torch.no_grad():
                     if train_weights:
                         weights.clamp_(0., 1.)

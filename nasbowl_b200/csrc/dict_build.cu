@@ -308,21 +308,9 @@ __global__ void assign_ids_kernel(const uint64_t* __restrict__ sk, const uint32_
 
 }  // namespace
 
-extern "C" int nbw_dict_build(nbw_ctx* ctx, const uint64_t* keys, const uint64_t* chks, int64_t n_keys,
-                              int key_bits, const void* cells, int n_max, const uint32_t* ids_prev,
-                              uint32_t* ids, uint64_t* uniq_keys, uint64_t* uniq_chks,
-                              int64_t uniq_cap, int64_t* n_unique_h, void* stream) {
-  if (!ctx) return NBW_ERR_INVALID;
-  NbwRange range("nbw_dict_build");
-  NBW_REQUIRE(ctx, n_keys >= 0 && n_keys < (int64_t)1 << 31, "n_keys out of range");
-  NBW_REQUIRE(ctx, key_bits >= 8 && key_bits <= 64 && key_bits % 8 == 0, "key_bits must be a multiple of 8 in [8,64]");
-  NBW_REQUIRE(ctx, n_unique_h != nullptr, "n_unique_h is NULL");
-  NBW_REQUIRE(ctx, cells == nullptr || n_max == 8 || n_max == 16, "n_max must be 8 or 16");
-  *n_unique_h = 0;
-  if (n_keys == 0) return NBW_OK;
-  NBW_REQUIRE(ctx, keys && chks && ids && uniq_keys && uniq_chks, "null pointer");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-
+// Enqueue one dictionary build (no sync, no read-back): the counters land in *counters (device).  `work` is a
+// scratch region of dict_scratch_bytes(n_keys) bytes.
+static size_t dict_scratch_bytes(int64_t n_keys) {
   const int n_tiles = (int)((n_keys + kTile - 1) / kTile);
   const size_t n_counts = (size_t)256 * n_tiles;
   const size_t scan_tmp = scan_scratch_elems((int64_t)(n_counts > (size_t)n_keys ? n_counts : (size_t)n_keys));
@@ -332,18 +320,23 @@ extern "C" int nbw_dict_build(nbw_ctx* ctx, const uint64_t* keys, const uint64_t
   need += Carver::pad(sizeof(uint32_t) * n_counts);
   need += Carver::pad(sizeof(uint32_t) * n_keys) * 2;   // flags, rank
   need += Carver::pad(sizeof(uint32_t) * scan_tmp);
-  need += Carver::pad(sizeof(DictCounters)) + 4096;
-  int rc = nbw_scratch_ensure(ctx, need, st);
-  if (rc) return rc;
-  Carver cv(ctx->scratch);
+  return need + 4096;
+}
+
+static int dict_build_enqueue(nbw_ctx* ctx, const uint64_t* keys, const uint64_t* chks, int64_t n_keys, int key_bits,
+                              const void* cells, int n_max, const uint32_t* ids_prev, uint32_t* ids, uint64_t* uniq_keys,
+                              uint64_t* uniq_chks, int64_t uniq_cap, DictCounters* counters, void* work, cudaStream_t st) {
+  const int n_tiles = (int)((n_keys + kTile - 1) / kTile);
+  const size_t n_counts = (size_t)256 * n_tiles;
+  const size_t scan_tmp = scan_scratch_elems((int64_t)(n_counts > (size_t)n_keys ? n_counts : (size_t)n_keys));
+  Carver cv(work);
   uint64_t* kbuf[2] = {cv.take<uint64_t>(n_keys), cv.take<uint64_t>(n_keys)};
   uint32_t* vbuf[2] = {cv.take<uint32_t>(n_keys), cv.take<uint32_t>(n_keys)};
   uint32_t* counts = cv.take<uint32_t>(n_counts);
   uint32_t* flags = cv.take<uint32_t>(n_keys);
   uint32_t* rank = cv.take<uint32_t>(n_keys);
   uint32_t* stmp = cv.take<uint32_t>(scan_tmp);
-  DictCounters* counters = cv.take<DictCounters>(1);
-
+  int rc;
   const uint64_t* kin = keys;
   const uint32_t* vin = nullptr;
   int cur = 0;
@@ -384,6 +377,31 @@ extern "C" int nbw_dict_build(nbw_ctx* ctx, const uint64_t* keys, const uint64_t
                                          static_cast<const uint8_t*>(cells), n_max, ids_prev, ids,
                                          uniq_keys, uniq_chks, uniq_cap, counters);
   NBW_CHECK_LAUNCH(ctx);
+  return NBW_OK;
+}
+
+extern "C" int nbw_dict_build(nbw_ctx* ctx, const uint64_t* keys, const uint64_t* chks, int64_t n_keys,
+                              int key_bits, const void* cells, int n_max, const uint32_t* ids_prev,
+                              uint32_t* ids, uint64_t* uniq_keys, uint64_t* uniq_chks,
+                              int64_t uniq_cap, int64_t* n_unique_h, void* stream) {
+  if (!ctx) return NBW_ERR_INVALID;
+  NbwRange range("nbw_dict_build");
+  NBW_REQUIRE(ctx, n_keys >= 0 && n_keys < (int64_t)1 << 31, "n_keys out of range");
+  NBW_REQUIRE(ctx, key_bits >= 8 && key_bits <= 64 && key_bits % 8 == 0, "key_bits must be a multiple of 8 in [8,64]");
+  NBW_REQUIRE(ctx, n_unique_h != nullptr, "n_unique_h is NULL");
+  NBW_REQUIRE(ctx, cells == nullptr || n_max == 8 || n_max == 16, "n_max must be 8 or 16");
+  *n_unique_h = 0;
+  if (n_keys == 0) return NBW_OK;
+  NBW_REQUIRE(ctx, keys && chks && ids && uniq_keys && uniq_chks, "null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = nbw_scratch_ensure(ctx, dict_scratch_bytes(n_keys) + 1024, st);
+  if (rc) return rc;
+  Carver cv(ctx->scratch);
+  DictCounters* counters = cv.take<DictCounters>(1);
+  void* work = static_cast<char*>(ctx->scratch) + 1024;
+  rc = dict_build_enqueue(ctx, keys, chks, n_keys, key_bits, cells, n_max, ids_prev, ids, uniq_keys, uniq_chks, uniq_cap,
+                          counters, work, st);
+  if (rc) return rc;
   DictCounters host;
   NBW_CUDA(ctx, cudaMemcpyAsync(&host, counters, sizeof(host), cudaMemcpyDeviceToHost, st));
   NBW_CUDA(ctx, cudaStreamSynchronize(st));
@@ -392,5 +410,47 @@ extern "C" int nbw_dict_build(nbw_ctx* ctx, const uint64_t* keys, const uint64_t
     NBW_FAIL(ctx, NBW_ERR_HASH_COLLISION, "two distinct WL credentials share a key; retry with another seed");
   if ((int64_t)host.n_unique > uniq_cap)
     NBW_FAIL(ctx, NBW_ERR_CAPACITY, "dictionary has %u entries, capacity %lld", host.n_unique, (long long)uniq_cap);
+  return NBW_OK;
+}
+
+// All WL levels of a batch in one call: relabel + dictionary build for levels 0..h back to back on the stream,
+// ONE read-back of the dictionary sizes at the end (the per-level entry points sync once per level, which is
+// most of a small training set's fit time).  ids: [h+1][n_keys] u32; uniq_keys / uniq_chks: [h+1][n_keys] u64
+// (level l's dictionary at offset l * n_keys); dims_h: [h+1].
+extern "C" int nbw_wl_fit(nbw_ctx* ctx, const void* cells, int64_t n_cells, int n_max, int h, uint64_t seed,
+                          uint32_t* ids, uint64_t* uniq_keys, uint64_t* uniq_chks, int64_t* dims_h, void* stream) {
+  if (!ctx) return NBW_ERR_INVALID;
+  NbwRange range("nbw_wl_fit");
+  NBW_REQUIRE(ctx, n_max == 8 || n_max == 16, "n_max must be 8 or 16 (got %d)", n_max);
+  NBW_REQUIRE(ctx, n_cells > 0 && h >= 0 && h < NBW_MAX_LEVELS, "bad n_cells / h");
+  NBW_REQUIRE(ctx, cells && ids && uniq_keys && uniq_chks && dims_h, "null pointer");
+  const int64_t n_keys = n_cells * n_max;
+  NBW_REQUIRE(ctx, n_keys < (int64_t)1 << 31, "n_keys out of range");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t head = 1024 + 2 * Carver::pad(sizeof(uint64_t) * n_keys);
+  int rc = nbw_scratch_ensure(ctx, head + dict_scratch_bytes(n_keys), st);
+  if (rc) return rc;
+  Carver cv(ctx->scratch);
+  DictCounters* counters = cv.take<DictCounters>(NBW_MAX_LEVELS);
+  cv.off = 1024;
+  uint64_t* keys = cv.take<uint64_t>(n_keys);
+  uint64_t* chks = cv.take<uint64_t>(n_keys);
+  void* work = static_cast<char*>(ctx->scratch) + head;
+  for (int l = 0; l <= h; ++l) {
+    const uint32_t* prev = l > 0 ? ids + (size_t)(l - 1) * n_keys : nullptr;
+    rc = nbw_wl_signatures_enqueue(ctx, cells, n_cells, n_max, prev, l, seed, keys, chks, st);
+    if (rc) return rc;
+    rc = dict_build_enqueue(ctx, keys, chks, n_keys, l == 0 ? 8 : 64, cells, n_max, prev, ids + (size_t)l * n_keys,
+                            uniq_keys + (size_t)l * n_keys, uniq_chks + (size_t)l * n_keys, n_keys, counters + l, work, st);
+    if (rc) return rc;
+  }
+  DictCounters host[NBW_MAX_LEVELS];
+  NBW_CUDA(ctx, cudaMemcpyAsync(host, counters, sizeof(DictCounters) * (h + 1), cudaMemcpyDeviceToHost, st));
+  NBW_CUDA(ctx, cudaStreamSynchronize(st));
+  for (int l = 0; l <= h; ++l) {
+    dims_h[l] = host[l].n_unique;
+    if (host[l].collision)
+      NBW_FAIL(ctx, NBW_ERR_HASH_COLLISION, "two distinct WL credentials share a key at level %d; retry with another seed", l);
+  }
   return NBW_OK;
 }

@@ -195,22 +195,30 @@ panel_kernel(double* __restrict__ L, int64_t ldl, int64_t k0, int nb, int64_t n,
   __shared__ double inv_diag[NB];   // 1 / L11[j][j]: the chains below multiply instead of dividing
   const int lane = threadIdx.x & 31;
   if (threadIdx.x < 32) {
+    // right-looking in registers, the scaled pivot column broadcast through shared memory (see gp_factor.cu)
+    __shared__ double colbuf[NB];
     double a[NB];
 #pragma unroll
     for (int c = 0; c < NB; ++c) a[c] = (lane < nb && c <= lane && c < nb) ? L[(k0 + lane) * ldl + k0 + c] : 0.0;
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
       if (j < nb) {                                            // uniform
-        const double ajj = __shfl_sync(0xffffffffu, a[j], j);
-        if (!(ajj > 0.0) && lane == j && blockIdx.x == 0) atomicCAS(info, 0, (int)(k0 + j + 1));
-        const double rinv = rsqrt(ajj);          // fp64 sqrt and divide are long dependent sequences
-        if (lane == j) { a[j] = ajj * rinv; inv_diag[j] = rinv; }
-        else if (lane > j) a[j] *= rinv;
-#pragma unroll
-        for (int c = j + 1; c < NB; ++c) {
-          const double acj = __shfl_sync(0xffffffffu, a[j], c);
-          if (lane >= c) a[c] = fma(-a[j], acj, a[c]);
+        if (lane == j) {
+          const double ajj = a[j];
+          if (!(ajj > 0.0) && blockIdx.x == 0) atomicCAS(info, 0, (int)(k0 + j + 1));
+          const double rinv = rsqrt(ajj);          // fp64 sqrt and divide are long dependent sequences
+          a[j] = ajj * rinv;
+          inv_diag[j] = rinv;
         }
+        __syncwarp();
+        const double rinv = inv_diag[j];
+        if (lane > j) a[j] *= rinv;
+        colbuf[lane] = (lane >= j) ? a[j] : 0.0;
+        __syncwarp();
+#pragma unroll
+        for (int c = j + 1; c < NB; ++c)
+          if (lane >= c) a[c] = fma(-a[j], colbuf[c], a[c]);
+        __syncwarp();
       }
     }
     if (lane >= nb) inv_diag[lane] = 0.0;
@@ -335,7 +343,8 @@ int chol_enqueue(nbw_ctx* ctx, const double* A, int64_t lda, int64_t n, double s
 // (1.4 ms of 3.2 ms at n = 1000).
 static inline size_t trtri_front_bytes(int64_t n) { return Carver::pad(sizeof(double) * (size_t)n) + 8192; }
 static inline size_t trtri_scratch_bytes(int64_t n) {
-  return trtri_front_bytes(n) + Carver::pad(sizeof(double) * (size_t)n * (size_t)n);
+  // (+ n + 32 doubles: the one-launch factorisation keeps its alpha accumulator in front of the merge buffer)
+  return trtri_front_bytes(n) + Carver::pad(sizeof(double) * ((size_t)n * (size_t)n + (size_t)n + 128));
 }
 
 __global__ void __launch_bounds__(32)
@@ -628,6 +637,19 @@ extern "C" int nbw_gp_factor(nbw_ctx* ctx, const double* K, int64_t ldk, int64_t
   double* d_stats = cv.take<double>(4);   // logdet, yKy, trKinv, |alpha|^2
   int* d_info = cv.take<int>(1);
   double* z = cv.take<double>(n);
+  if (nbw_factor_fused_ok(n)) {
+    // one launch: a cluster of CTAs walks the panels, the inverse merges and the reductions (gp_factor.cu)
+    double* W = Linv ? reinterpret_cast<double*>(static_cast<char*>(ctx->scratch) + trtri_front_bytes(n)) : nullptr;
+    rc = nbw_factor_fused(ctx, K, ldk, n, lik, y, L, ldl, Linv, ldi, W, alpha, z, d_stats, d_info, st);
+    if (rc) return rc;
+    double hs4[4];
+    NBW_CUDA(ctx, cudaMemcpyAsync(hs4, d_stats, sizeof(hs4), cudaMemcpyDeviceToHost, st));
+    NBW_CUDA(ctx, cudaMemcpyAsync(info_h, d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
+    NBW_CUDA(ctx, cudaStreamSynchronize(st));
+    for (int i = 0; i < 4; ++i) stats_h[i] = hs4[i];
+    if (*info_h != 0) NBW_FAIL(ctx, NBW_ERR_NOT_PD, "matrix not positive definite at pivot %d", *info_h - 1);
+    return NBW_OK;
+  }
   NBW_CUDA(ctx, cudaMemsetAsync(d_stats, 0, sizeof(double) * 4, st));
   rc = chol_enqueue(ctx, K, ldk, n, lik, L, ldl, d_stats + 0, d_info, st);
   if (rc) return rc;

@@ -37,7 +37,7 @@ struct nbw_ctx {
   size_t topk_blocks_bytes;
   int topk_slot;
 };
-enum { NBW_ATTR_TRSV = 1u << 0, NBW_ATTR_SMALL_SORT = 1u << 1, NBW_ATTR_GRAM_SINGLE = 1u << 2, NBW_ATTR_CHOL_SMALL = 1u << 3,
+enum { NBW_ATTR_TRSV = 1u << 0, NBW_ATTR_SMALL_SORT = 1u << 1, NBW_ATTR_GRAM_SINGLE = 1u << 2, NBW_ATTR_FACTOR_NP = 1u << 3,
        NBW_ATTR_GRAM_PAIR = 1u << 8 /* << output mode: bits 8..11 */ };
 
 // NVTX range around a C-ABI entry point (visible in Nsight Systems / ncu --nvtx); header-only NVTX3,
@@ -97,6 +97,16 @@ bool nbw_packed_applicable(const nbw_model* M);
 int nbw_score_packed(nbw_ctx* ctx, const nbw_model* M, const void* cells, int64_t n_cells, float* scores, double* mu64,
                      double* var64, double* score64, int k, int distinct, int64_t index_base, void* out_cands,
                      cudaStream_t st);
+
+// WL relabelling of one level, enqueue only (wl_relabel.cu; used by nbw_wl_fit in dict_build.cu)
+int nbw_wl_signatures_enqueue(nbw_ctx* ctx, const void* cells, int64_t n_cells, int n_max, const uint32_t* ids_prev,
+                              int level, uint64_t seed, uint64_t* keys, uint64_t* chks, cudaStream_t st);
+
+// One-launch GP factorisation (gp_factor.cu)
+bool nbw_factor_fused_ok(int64_t n);
+int nbw_factor_fused(nbw_ctx* ctx, const double* K, int64_t ldk, int64_t n, double lik, const double* y, double* L,
+                     int64_t ldl, double* Linv, int64_t ldi, double* W, double* alpha, double* z, double* stats,
+                     int* info, cudaStream_t st);
 
 // Scratch arena: grows on demand (syncs the stream before releasing the old block).
 int nbw_scratch_ensure(nbw_ctx* ctx, size_t bytes, cudaStream_t stream);

@@ -62,7 +62,12 @@ extern "C" int nbw_wl_signatures(nbw_ctx* ctx, const void* cells, int64_t n_cell
   NBW_REQUIRE(ctx, (level == 0) == (ids_prev == nullptr), "ids_prev must be NULL exactly at level 0");
   if (n_cells == 0) return NBW_OK;
   NBW_REQUIRE(ctx, cells && keys && chks, "null pointer");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return nbw_wl_signatures_enqueue(ctx, cells, n_cells, n_max, ids_prev, level, seed, keys, chks,
+                                   static_cast<cudaStream_t>(stream));
+}
+
+int nbw_wl_signatures_enqueue(nbw_ctx* ctx, const void* cells, int64_t n_cells, int n_max, const uint32_t* ids_prev,
+                              int level, uint64_t seed, uint64_t* keys, uint64_t* chks, cudaStream_t st) {
   const int cells_per_block = 256 / n_max;
   const int grid = nbw_grid_for(ctx, n_cells, cells_per_block);
   const uint8_t* c = static_cast<const uint8_t*>(cells);

@@ -144,23 +144,15 @@ class Engine:
         lib, ctx, st = self.lib, self.ctx, self.stream
         n_keys = n * n_max
         ids = self.empty((h + 1, n_keys), torch.int32)
-        keys = self.empty((n_keys,), torch.int64)
-        chks = self.empty((n_keys,), torch.int64)
-        uk = self.empty((n_keys,), torch.int64)
-        uc = self.empty((n_keys,), torch.int64)
-        dims, ukeys, uchks = [], [], []
-        for l in range(h + 1):
-            prev = ids[l - 1] if l > 0 else None
-            self._check(lib.nbw_wl_signatures(ctx, self._p(cells), n, n_max, self._p(prev), l,
-                                              C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), self._p(keys),
-                                              self._p(chks), st))
-            d = C.c_int64(0)
-            self._check(lib.nbw_dict_build(ctx, self._p(keys), self._p(chks), n_keys, 8 if l == 0 else 64,
-                                           self._p(cells), n_max, self._p(prev), self._p(ids[l]),
-                                           self._p(uk), self._p(uc), n_keys, C.byref(d), st))
-            dims.append(int(d.value))
-            ukeys.append(uk[:d.value].clone())
-            uchks.append(uc[:d.value].clone())
+        # all levels in one call, one sync (nbw_wl_fit); the dictionaries are views into two level-major buffers
+        uk = self.empty((h + 1, n_keys), torch.int64)
+        uc = self.empty((h + 1, n_keys), torch.int64)
+        dd = (C.c_int64 * (h + 1))()
+        self._check(lib.nbw_wl_fit(ctx, self._p(cells), n, n_max, h, C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), self._p(ids),
+                                   self._p(uk), self._p(uc), dd, st))
+        dims = [int(v) for v in dd]
+        ukeys = [uk[l, :dims[l]] for l in range(h + 1)]
+        uchks = [uc[l, :dims[l]] for l in range(h + 1)]
         label_off = [0]
         for d in dims:
             label_off.append(label_off[-1] + d)
@@ -341,6 +333,26 @@ class Engine:
                                            self._p(L), n, self._p(Linv), n, self._p(alpha), stats,
                                            C.byref(info), self.stream))
         return L, Linv, alpha, float(stats[0]), float(stats[1]), float(stats[2]), float(stats[3])
+
+    def level_grams_i32(self, fit: WLFit, hmax: int) -> torch.Tensor:
+        """int32 [hmax + 1, n, ld]: the Gram of every single WL level (vertex_histogram.py:243 per level)."""
+        n = fit.n_cells
+        ld = _round_up(n, 4)
+        G = self.empty((hmax + 1, n, ld), torch.int32)
+        for l in range(hmax + 1):
+            self.gram(fit.phi, fit.phi, fit.col_off[l], fit.col_off[l + 1], out=G[l])
+        return G
+
+    def gp_grid(self, G: torch.Tensor, n: int, n_levels: Sequence[int], lik: float, y: torch.Tensor):
+        """nbw_gp_grid: every candidate depth of the grid search factored in ONE launch.  Returns
+        [(logdet, yKy, info)] per candidate; info != 0 marks a candidate whose factorisation broke down."""
+        m = len(n_levels)
+        nl = (C.c_int * m)(*[int(v) for v in n_levels])
+        stats = (C.c_double * (2 * m))()
+        info = (C.c_int * m)()
+        self._check(self.lib.nbw_gp_grid(self.ctx, self._p(G), G.stride(1), G.stride(0), n, nl, m, float(lik), self._p(y),
+                                         stats, info, self.stream))
+        return [(float(stats[2 * c]), float(stats[2 * c + 1]), int(info[c])) for c in range(m)]
 
     def pd_inverse(self, K: torch.Tensor, jitter: float, y: torch.Tensor, want_inverse: bool = True):
         """compute_pd_inverse with its jitter retry (x10, x100) — bayesopt/utils.py:120-140."""
