@@ -65,13 +65,15 @@ uint64_t nbw_launch_count(const nbw_ctx* ctx);
  * (1) WL relabelling — replaces the credential loop of WeisfeilerLehman.parse_input,
  *     grakel_replace/weisfeiler_lehman.py:258-296.
  * Level 0 (ids_prev == NULL): key = op code of each node, chk = 0.
- * Level l >= 1: key/chk = two independent 64-bit multiset hashes of
- *     (ids_prev[v], {ids_prev[s] : s in successors(v)}), salted by (seed, level);
+ * Level l >= 1: key/chk = two independent multiset hashes of
+ *     (label_{l-1}(v), {label_{l-1}(s) : s in successors(v)}), salted by (seed, level), where a label enters
+ *     through its KEY uniq_keys_prev[ids_prev[.]] (the level-(l-1) dictionary of nbw_dict_build; level 0: the op
+ *     code): signatures depend on the cell and the seed only, not on how a batch numbered its labels;
  *     nodes that are not an endpoint of any edge get NBW_INVALID_KEY.
  * keys/chks: [N * n_max] u64.  ids_prev: [N * n_max] u32 (NBW_INVALID_ID = not counted).
  */
 int nbw_wl_signatures(nbw_ctx* ctx, const void* cells, int64_t n_cells, int n_max,
-                      const uint32_t* ids_prev, int level, uint64_t seed,
+                      const uint32_t* ids_prev, const uint64_t* uniq_keys_prev, int level, uint64_t seed,
                       uint64_t* keys, uint64_t* chks, void* stream);
 
 /* ---------------------------------------------------------------------------------------
@@ -329,11 +331,12 @@ int nbw_model_build_table(nbw_ctx* ctx, const uint64_t* uniq_keys, const uint64_
 
 /* Packed-path dictionary forms (see nbw_model): replace self._inv_labels[i] lookups of
  * WeisfeilerLehman.transform (weisfeiler_lehman.py:434-466).
- * nbw_model_build_id_hash: out[d] = hashes of dictionary id d (d < n_ids) salted for `level` (>= 1).
+ * nbw_model_build_id_hash: out[d] = hashes of the key of level-(level-1) dictionary id d (d < n_ids), salted for `level`.
  * nbw_model_build_buckets: four-entry buckets over the sorted dictionary of nbw_dict_build; n_buckets a
  * power of two.  *flags (device u32, caller zeroes) gets bit 0 when a bucket overflows and bit 1 when two
  * keys of one bucket share a tag: the caller rebuilds with more buckets.  Both enqueue only. */
-int nbw_model_build_id_hash(nbw_ctx* ctx, int64_t n_ids, uint64_t seed, int level, void* out, void* stream);
+int nbw_model_build_id_hash(nbw_ctx* ctx, const uint64_t* uniq_keys_prev, int64_t n_ids, uint64_t seed, int level,
+                            void* out, void* stream);
 int nbw_model_build_buckets(nbw_ctx* ctx, const uint64_t* uniq_keys, const uint64_t* uniq_chks,
                             int64_t n_unique, void* tags, void* entries, int64_t n_buckets,
                             uint32_t* flags, void* stream);
@@ -447,6 +450,17 @@ int nbw_generate_cells(nbw_ctx* ctx, int family, uint64_t seed, int64_t first_in
  * isomorphism de-duplication (a host-side graph search) is not reproduced.  family must be 0. */
 int nbw_mutate_cells(nbw_ctx* ctx, int family, const void* parents, int64_t n_parents, uint64_t seed,
                      int64_t first_index, int64_t n_children, void* cells, void* stream);
+
+/* Pool de-duplication — `allow_isomorphism=False` of mutation() (bayesopt/generate_test_graphs.py:497-520: a child
+ * isomorphic to its parent or to an earlier pool member is dropped; the reference searches pairwise with networkx).
+ * Every cell gets a 128-bit Weisfeiler-Lehman signature (colour refinement over both edge directions to depth
+ * n_max; labeled == 0 ignores the op codes like the reference's is_isomorphic call without node_match, labeled != 0
+ * also requires equal ops); keep[i] = 1 iff no cell j < i has the same signature.  The first n_protected cells
+ * are references (parents, already evaluated cells): they count as "earlier" but are not counted in *n_kept_h.
+ * *n_classes_h = number of distinct signatures.  Syncs.  NBW_ERR_HASH_COLLISION: retry with another seed. */
+int nbw_pool_dedup(nbw_ctx* ctx, const void* cells, int64_t n_cells, int n_max, int labeled,
+                   int64_t n_protected, uint64_t seed, uint8_t* keep, int64_t* n_classes_h,
+                   int64_t* n_kept_h, void* stream);
 
 /* NB201 / DARTS cells with their ENCODINGS (the pruned cell does not determine the architecture it came
  * from, and mutation edits the architecture): NB201 = six edge choices (0..2 ops, 3 skip_connect, 4 none)

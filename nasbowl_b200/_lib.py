@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libnbw.so")
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 SOURCES = ["nbw_api.cu", "wl_relabel.cu", "dict_build.cu", "histogram.cu", "gram_i8.cu",
-           "linalg_f64.cu", "gp_factor.cu", "score_pool.cu", "score_packed.cu", "topk.cu", "cellgen.cu"]
+           "linalg_f64.cu", "gp_factor.cu", "score_pool.cu", "score_packed.cu", "topk.cu", "cellgen.cu", "pool_dedup.cu"]
 
 NBW_MAX_LEVELS = 8
 NBW_MAX_PARTS = 4
@@ -79,7 +79,7 @@ _PROTOTYPES = {
     "nbw_profile_events": (C.c_int, [_vp, _vp, _vp]),
     "nbw_range_push": (C.c_int, [C.c_char_p]),
     "nbw_range_pop": (C.c_int, []),
-    "nbw_wl_signatures": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _i32, _u64, _vp, _vp, _vp]),
+    "nbw_wl_signatures": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _i32, _u64, _vp, _vp, _vp]),
     "nbw_dict_build": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i64,
                                  C.POINTER(_i64), _vp]),
     "nbw_wl_fit": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _u64, _vp, _vp, _vp, C.POINTER(_i64), _vp]),
@@ -110,7 +110,7 @@ _PROTOTYPES = {
                                       _i64, _vp]),
     "nbw_posterior_cov_finish": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _f64, _f64, _vp, _i64, _vp]),
     "nbw_model_build_table": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i64, _vp]),
-    "nbw_model_build_id_hash": (C.c_int, [_vp, _i64, _u64, _i32, _vp, _vp]),
+    "nbw_model_build_id_hash": (C.c_int, [_vp, _vp, _i64, _u64, _i32, _vp, _vp]),
     "nbw_model_build_buckets": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp]),
     "nbw_score_pool": (C.c_int, [_vp, C.POINTER(Model), _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "nbw_score_pool_topk": (C.c_int, [_vp, C.POINTER(Model), _vp, _i64, _vp, _i32, _i32, _i64, _vp, _vp]),
@@ -128,6 +128,7 @@ _PROTOTYPES = {
                                  C.POINTER(_i32), _vp]),
     "nbw_generate_cells": (C.c_int, [_vp, _i32, _u64, _i64, _i64, _vp, _vp]),
     "nbw_mutate_cells": (C.c_int, [_vp, _i32, _vp, _i64, _u64, _i64, _i64, _vp, _vp]),
+    "nbw_pool_dedup": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i64, _u64, _vp, C.POINTER(_i64), C.POINTER(_i64), _vp]),
     "nbw_generate_encoded": (C.c_int, [_vp, _i32, _u64, _i64, _i64, _vp, _vp, _vp]),
     "nbw_mutate_encoded": (C.c_int, [_vp, _i32, _vp, _i64, _u64, _i64, _i64, _i32, _vp, _vp, _vp]),
 }

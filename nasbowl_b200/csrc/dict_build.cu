@@ -264,10 +264,7 @@ __device__ bool same_credential(const uint8_t* cells, const uint32_t* ids_prev, 
   return true;
 }
 
-struct DictCounters {
-  uint32_t n_unique;
-  uint32_t collision;
-};
+typedef NbwDictCounters DictCounters;
 
 __global__ void assign_ids_kernel(const uint64_t* __restrict__ sk, const uint32_t* __restrict__ sv,
                                   const uint64_t* __restrict__ chks, const uint32_t* __restrict__ flags,
@@ -276,7 +273,7 @@ __global__ void assign_ids_kernel(const uint64_t* __restrict__ sk, const uint32_
                                   const uint32_t* __restrict__ ids_prev,
                                   uint32_t* __restrict__ ids, uint64_t* __restrict__ uniq_keys,
                                   uint64_t* __restrict__ uniq_chks, int64_t cap,
-                                  DictCounters* __restrict__ counters) {
+                                  DictCounters* __restrict__ counters, uint8_t* __restrict__ first_flag) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const uint64_t k = sk[i];
@@ -284,11 +281,13 @@ __global__ void assign_ids_kernel(const uint64_t* __restrict__ sk, const uint32_
     if (i == n - 1) counters->n_unique = rank[i] + flags[i];
     if (k == NBW_INVALID_KEY) {
       ids[src] = NBW_INVALID_ID;
+      if (first_flag) first_flag[src] = 0;
       continue;
     }
     const uint32_t head = flags[i];
     const uint32_t id = rank[i] + head - 1u;
     ids[src] = id;
+    if (first_flag) first_flag[src] = (uint8_t)head;     // the sort is stable: the head of a run is the first occurrence
     if (head) {
       if ((int64_t)id < cap) {
         uniq_keys[id] = k;
@@ -309,8 +308,8 @@ __global__ void assign_ids_kernel(const uint64_t* __restrict__ sk, const uint32_
 }  // namespace
 
 // Enqueue one dictionary build (no sync, no read-back): the counters land in *counters (device).  `work` is a
-// scratch region of dict_scratch_bytes(n_keys) bytes.
-static size_t dict_scratch_bytes(int64_t n_keys) {
+// scratch region of nbw_dict_scratch_bytes(n_keys) bytes.
+size_t nbw_dict_scratch_bytes(int64_t n_keys) {
   const int n_tiles = (int)((n_keys + kTile - 1) / kTile);
   const size_t n_counts = (size_t)256 * n_tiles;
   const size_t scan_tmp = scan_scratch_elems((int64_t)(n_counts > (size_t)n_keys ? n_counts : (size_t)n_keys));
@@ -323,9 +322,10 @@ static size_t dict_scratch_bytes(int64_t n_keys) {
   return need + 4096;
 }
 
-static int dict_build_enqueue(nbw_ctx* ctx, const uint64_t* keys, const uint64_t* chks, int64_t n_keys, int key_bits,
-                              const void* cells, int n_max, const uint32_t* ids_prev, uint32_t* ids, uint64_t* uniq_keys,
-                              uint64_t* uniq_chks, int64_t uniq_cap, DictCounters* counters, void* work, cudaStream_t st) {
+int nbw_dict_build_enqueue(nbw_ctx* ctx, const uint64_t* keys, const uint64_t* chks, int64_t n_keys, int key_bits,
+                           const void* cells, int n_max, const uint32_t* ids_prev, uint32_t* ids, uint64_t* uniq_keys,
+                           uint64_t* uniq_chks, int64_t uniq_cap, NbwDictCounters* counters, void* work, cudaStream_t st,
+                           uint8_t* first_flag) {
   const int n_tiles = (int)((n_keys + kTile - 1) / kTile);
   const size_t n_counts = (size_t)256 * n_tiles;
   const size_t scan_tmp = scan_scratch_elems((int64_t)(n_counts > (size_t)n_keys ? n_counts : (size_t)n_keys));
@@ -375,7 +375,7 @@ static int dict_build_enqueue(nbw_ctx* ctx, const uint64_t* keys, const uint64_t
   NBW_CUDA(ctx, cudaMemsetAsync(counters, 0, sizeof(DictCounters), st));
   assign_ids_kernel<<<grid, 256, 0, st>>>(kin, vin, chks, flags, rank, n_keys,
                                          static_cast<const uint8_t*>(cells), n_max, ids_prev, ids,
-                                         uniq_keys, uniq_chks, uniq_cap, counters);
+                                         uniq_keys, uniq_chks, uniq_cap, counters, first_flag);
   NBW_CHECK_LAUNCH(ctx);
   return NBW_OK;
 }
@@ -394,12 +394,12 @@ extern "C" int nbw_dict_build(nbw_ctx* ctx, const uint64_t* keys, const uint64_t
   if (n_keys == 0) return NBW_OK;
   NBW_REQUIRE(ctx, keys && chks && ids && uniq_keys && uniq_chks, "null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int rc = nbw_scratch_ensure(ctx, dict_scratch_bytes(n_keys) + 1024, st);
+  int rc = nbw_scratch_ensure(ctx, nbw_dict_scratch_bytes(n_keys) + 1024, st);
   if (rc) return rc;
   Carver cv(ctx->scratch);
   DictCounters* counters = cv.take<DictCounters>(1);
   void* work = static_cast<char*>(ctx->scratch) + 1024;
-  rc = dict_build_enqueue(ctx, keys, chks, n_keys, key_bits, cells, n_max, ids_prev, ids, uniq_keys, uniq_chks, uniq_cap,
+  rc = nbw_dict_build_enqueue(ctx, keys, chks, n_keys, key_bits, cells, n_max, ids_prev, ids, uniq_keys, uniq_chks, uniq_cap,
                           counters, work, st);
   if (rc) return rc;
   DictCounters host;
@@ -428,7 +428,7 @@ extern "C" int nbw_wl_fit(nbw_ctx* ctx, const void* cells, int64_t n_cells, int 
   NBW_REQUIRE(ctx, n_keys < (int64_t)1 << 31, "n_keys out of range");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t head = 1024 + 2 * Carver::pad(sizeof(uint64_t) * n_keys);
-  int rc = nbw_scratch_ensure(ctx, head + dict_scratch_bytes(n_keys), st);
+  int rc = nbw_scratch_ensure(ctx, head + nbw_dict_scratch_bytes(n_keys), st);
   if (rc) return rc;
   Carver cv(ctx->scratch);
   DictCounters* counters = cv.take<DictCounters>(NBW_MAX_LEVELS);
@@ -438,9 +438,10 @@ extern "C" int nbw_wl_fit(nbw_ctx* ctx, const void* cells, int64_t n_cells, int 
   void* work = static_cast<char*>(ctx->scratch) + head;
   for (int l = 0; l <= h; ++l) {
     const uint32_t* prev = l > 0 ? ids + (size_t)(l - 1) * n_keys : nullptr;
-    rc = nbw_wl_signatures_enqueue(ctx, cells, n_cells, n_max, prev, l, seed, keys, chks, st);
+    rc = nbw_wl_signatures_enqueue(ctx, cells, n_cells, n_max, prev, l > 0 ? uniq_keys + (size_t)(l - 1) * n_keys : nullptr,
+                                   l, seed, keys, chks, st);
     if (rc) return rc;
-    rc = dict_build_enqueue(ctx, keys, chks, n_keys, l == 0 ? 8 : 64, cells, n_max, prev, ids + (size_t)l * n_keys,
+    rc = nbw_dict_build_enqueue(ctx, keys, chks, n_keys, l == 0 ? 8 : 64, cells, n_max, prev, ids + (size_t)l * n_keys,
                             uniq_keys + (size_t)l * n_keys, uniq_chks + (size_t)l * n_keys, n_keys, counters + l, work, st);
     if (rc) return rc;
   }

@@ -100,7 +100,21 @@ int nbw_score_packed(nbw_ctx* ctx, const nbw_model* M, const void* cells, int64_
 
 // WL relabelling of one level, enqueue only (wl_relabel.cu; used by nbw_wl_fit in dict_build.cu)
 int nbw_wl_signatures_enqueue(nbw_ctx* ctx, const void* cells, int64_t n_cells, int n_max, const uint32_t* ids_prev,
-                              int level, uint64_t seed, uint64_t* keys, uint64_t* chks, cudaStream_t st);
+                              const uint64_t* uniq_prev, int level, uint64_t seed, uint64_t* keys, uint64_t* chks,
+                              cudaStream_t st);
+
+// Sort / unique / dense ids of n_keys 64-bit keys, enqueue only (dict_build.cu): the counters land in *counters
+// (device); `work` is scratch of nbw_dict_scratch_bytes(n_keys) bytes; first_flag[i] (optional) = 1 iff key i is
+// the first occurrence of its value.
+struct NbwDictCounters {
+  uint32_t n_unique;
+  uint32_t collision;
+};
+size_t nbw_dict_scratch_bytes(int64_t n_keys);
+int nbw_dict_build_enqueue(nbw_ctx* ctx, const uint64_t* keys, const uint64_t* chks, int64_t n_keys, int key_bits,
+                           const void* cells, int n_max, const uint32_t* ids_prev, uint32_t* ids, uint64_t* uniq_keys,
+                           uint64_t* uniq_chks, int64_t uniq_cap, NbwDictCounters* counters, void* work, cudaStream_t st,
+                           uint8_t* first_flag = nullptr);
 
 // One-launch GP factorisation (gp_factor.cu)
 bool nbw_factor_fused_ok(int64_t n);
@@ -142,6 +156,7 @@ static inline int nbw_grid_for(const nbw_ctx* ctx, int64_t work_items, int per_b
 // apart from "s with successor v".  Ids are 64-bit: a dense dictionary id (< 2^32) for labels
 // known to the dictionary, UNSEEN_BIT | key for labels outside it.  96 signature bits decide
 // pool-side membership; the training-side partition is verified exactly (dict_build.cu).
+// What is hashed per node is the KEY of its previous label (level 0: the op code), never a batch-local id.
 // ---------------------------------------------------------------------------------------
 #define NBW_UNSEEN_BIT 0x8000000000000000ull
 #define NBW_NOCLASS_BIT 0x4000000000000000ull   // | lane: a class id no other lane can have

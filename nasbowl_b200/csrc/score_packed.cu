@@ -533,11 +533,13 @@ score_packed_kernel(const __grid_constant__ PackedParams P, const uint8_t* __res
 }
 
 // ------------------------------------------------------------------ dictionary forms of the packed path
-__global__ void id_hash_kernel(int64_t n_ids, LevelSalt salt, uint4* __restrict__ out) {
+__global__ void id_hash_kernel(const uint64_t* __restrict__ uniq_prev, int64_t n_ids, LevelSalt salt,
+                               uint4* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_ids) return;
-  const uint64_t ha = nbw_hash_a((uint64_t)i, salt);
-  const uint32_t hb = nbw_hash_b((uint64_t)i, salt);
+  const uint64_t k = uniq_prev[i];
+  const uint64_t ha = nbw_hash_a(k, salt);
+  const uint32_t hb = nbw_hash_b(k, salt);
   out[i] = make_uint4((uint32_t)ha, (uint32_t)(ha >> 32), hb, 0u);
 }
 
@@ -732,13 +734,14 @@ int nbw_score_packed(nbw_ctx* ctx, const nbw_model* M, const void* cells, int64_
   return launch_parts<16, false>(ctx, np, weighted, P, c, n_cells, scores, mu64, var64, score64, 0, 0, 0, nullptr, st);
 }
 
-extern "C" int nbw_model_build_id_hash(nbw_ctx* ctx, int64_t n_ids, uint64_t seed, int level, void* out, void* stream) {
+extern "C" int nbw_model_build_id_hash(nbw_ctx* ctx, const uint64_t* uniq_keys_prev, int64_t n_ids, uint64_t seed,
+                                       int level, void* out, void* stream) {
   if (!ctx) return NBW_ERR_INVALID;
   NBW_REQUIRE(ctx, n_ids >= 0 && level >= 1 && level < NBW_MAX_LEVELS, "bad n_ids / level");
   if (n_ids == 0) return NBW_OK;
-  NBW_REQUIRE(ctx, out != nullptr, "out is NULL");
+  NBW_REQUIRE(ctx, out != nullptr && uniq_keys_prev != nullptr, "null pointer");
   id_hash_kernel<<<(unsigned)((n_ids + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      n_ids, nbw_level_salt(seed, level), static_cast<uint4*>(out));
+      uniq_keys_prev, n_ids, nbw_level_salt(seed, level), static_cast<uint4*>(out));
   NBW_CHECK_LAUNCH(ctx);
   return NBW_OK;
 }

@@ -194,7 +194,7 @@ score_pool_kernel(const ScoreParams P, const uint8_t* __restrict__ cells, int64_
       const uint32_t d0 = present ? (uint32_t)__ldg(M.level0_table + label) : 0xFFFFu;
       const bool seen = present && d0 != 0xFFFFu;
       in_dict = seen;
-      id64 = seen ? (uint64_t)d0 : (NBW_UNSEEN_BIT | (uint64_t)label);
+      id64 = (uint64_t)label;      // the level-0 key of a label is its op code, in or out of the dictionary
       cls = classes_level0<NMAX>(label, present, node, sub_base);
       cnt[0] = __popc(cls);
       rk[0] = __popc(cls & ((1u << node) - 1u));
@@ -280,7 +280,7 @@ score_pool_kernel(const ScoreParams P, const uint8_t* __restrict__ cells, int64_
         seen = table_probe(static_cast<const uint4*>(M.table[l]), M.table_mask[l], key, chk, dense);
       in_dict = seen;
       dense_prev = dense;
-      id64 = seen ? (uint64_t)dense : (NBW_UNSEEN_BIT | key);
+      id64 = key;                  // labels are hashed through their keys (see wl_relabel.cu)
       cls = classes_refine<NMAX>(cls, id64, endpoint, node, lane, sub_base);
       cnt[l] = __popc(cls);
       rk[l] = __popc(cls & ((1u << node) - 1u));

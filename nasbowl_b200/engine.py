@@ -449,7 +449,8 @@ class Engine:
         for l in range(1, n):
             dp = max(fit.dims[l - 1], 1)
             id_hash[l] = self.empty((dp * 16,), torch.uint8)
-            self._check(self.lib.nbw_model_build_id_hash(self.ctx, fit.dims[l - 1], seed, l, self._p(id_hash[l]), self.stream))
+            self._check(self.lib.nbw_model_build_id_hash(self.ctx, self._p(fit.uniq_keys[l - 1]), fit.dims[l - 1], seed, l,
+                                                         self._p(id_hash[l]), self.stream))
             build(l, _pow2_at_least(max(4 * fit.dims[l], 16)))
         for attempt in range(8):
             bad = np.nonzero(flags.cpu().numpy())[0]
@@ -644,6 +645,23 @@ class Engine:
         self._check(self.lib.nbw_mutate_cells(self.ctx, family, self._p(parents), parents.shape[0], C.c_uint64(seed),
                                               first_index, n_children, self._p(cells), self.stream))
         return cells
+
+    def pool_dedup(self, cells: torch.Tensor, n_max: int, labeled: bool = True, n_protected: int = 0,
+                   seed: int = DEFAULT_SEED):
+        """nbw_pool_dedup: keep-first de-duplication of device records by WL isomorphism signature.
+        Returns (keep mask uint8 [n] on the device, number of classes, number kept beyond the protected prefix)."""
+        n = cells.shape[0]
+        keep = self.empty((n,), torch.uint8)
+        nc, nk = C.c_int64(0), C.c_int64(0)
+        for attempt in range(4):
+            try:
+                self._check(self.lib.nbw_pool_dedup(self.ctx, self._p(cells), n, n_max, int(labeled), int(n_protected),
+                                                    C.c_uint64((seed + attempt * 0x9E3779B1) & 0xFFFFFFFFFFFFFFFF),
+                                                    self._p(keep), C.byref(nc), C.byref(nk), self.stream))
+                return keep, int(nc.value), int(nk.value)
+            except _lib.HashCollision:
+                continue
+        raise RuntimeError("cell signatures collided for 4 different seeds")
 
     def generate_encoded(self, family: int, seed: int, first_index: int, n_cells: int):
         """(device records, device encodings uint8 [n, 8 | 16]) of random NB201 / DARTS cells

@@ -434,3 +434,47 @@ def generate_cells_host(family: int, seed: int, first_index: int, n_cells: int) 
         labels[i] = l[:n_max]
         succ[i] = m[:n_max]
     return CellBatch(n_max, labels, succ)
+
+
+# --------------------------------------------------------------------------------------------- pool de-duplication
+def isomorphism_classes_host(batch: CellBatch, labeled: bool = True, rounds: int = None):
+    """Host twin of nbw_pool_dedup's partition: colour refinement over BOTH edge directions (a node's colour is
+    refined by the multiset of its successors' colours and, separately, of its predecessors' colours), run to
+    depth n_max; a cell's class is the multiset of its final node colours (+ node and edge counts).  Returns an
+    int64 array of class ids numbered by first occurrence.
+
+    This is the Weisfeiler-Lehman isomorphism test the reference's mutation() comments on
+    (generate_test_graphs.py:497-520): `allow_isomorphism=False` drops a child that is isomorphic to its parent or
+    to an earlier member of the pool.  labeled=False ignores the op names, like the reference's
+    `iso.is_isomorphic(child.arch, prev_edit)` call (no node_match); labeled=True also requires equal ops."""
+    N, n_max = batch.labels.shape
+    rounds = n_max if rounds is None else rounds
+    out = np.empty(N, dtype=np.int64)
+    seen = {}
+    for g in range(N):
+        lab = batch.labels[g]
+        nodes = [v for v in range(n_max) if lab[v] != NO_NODE]
+        succ = {v: [j for j in range(n_max) if (int(batch.succ[g, v]) >> j) & 1] for v in nodes}
+        pred = {v: [u for u in nodes if v in succ[u]] for v in nodes}
+        # colours are hashes of (own colour, sorted successor colours, sorted predecessor colours): canonical across
+        # cells (Python hashes tuples of ints deterministically), so the multiset of final colours is the cell's class
+        sig = {v: (int(lab[v]) if labeled else 0) for v in nodes}
+        for _ in range(rounds):
+            sig = {v: hash((sig[v], tuple(sorted(sig[s] for s in succ[v])), tuple(sorted(sig[p] for p in pred[v]))))
+                   for v in nodes}
+        key = (len(nodes), sum(len(s) for s in succ.values()), tuple(sorted(sig[v] for v in nodes)))
+        out[g] = seen.setdefault(key, len(seen))
+    return out
+
+
+def dedup_keep_first_host(batch: CellBatch, labeled: bool = True, n_protected: int = 0) -> np.ndarray:
+    """keep[i] for the cells after the first n_protected: True iff no earlier cell (protected ones included)
+    belongs to the same isomorphism class — the keep-first rule of mutation()'s evaluation pool."""
+    cls = isomorphism_classes_host(batch, labeled)
+    first = {}
+    keep = np.zeros(len(cls), dtype=bool)
+    for i, c in enumerate(cls):
+        if c not in first:
+            first[c] = i
+            keep[i] = True
+    return keep[n_protected:]

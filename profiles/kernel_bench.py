@@ -67,7 +67,7 @@ def main():
         # ---- relabel, level 1 (reads records + level-0 ids, writes key + chk per node)
         fit = eng.wl_fit(cells, n_max, h, False)
         ids0 = fit.ids[0]
-        ms = timed(lambda: eng._check(lib.nbw_wl_signatures(ctx, eng._p(cells), N, n_max, eng._p(ids0), 1,
+        ms = timed(lambda: eng._check(lib.nbw_wl_signatures(ctx, eng._p(cells), N, n_max, eng._p(ids0), eng._p(fit.uniq_keys[0]), 1,
                                                             C.c_uint64(7), eng._p(keys), eng._p(chks), st)), flush)
         byt = N * stride + nk * 4 + nk * 16
         out["kernels"]["wl_signature_kernel"] = {"ms": ms, "cells": N, "algorithmic_bytes": byt,

@@ -409,3 +409,58 @@ def test_gram_stress_small(eng):
     assert 0.5 < res["computed_fraction"] < 0.75
     K_o = wl_oracle.gram_raw(CellBatch.from_records(cells.cpu().numpy(), 8), 3)
     assert np.array_equal(res["result"][:N, :N].cpu().numpy().astype(np.int64), K_o)
+
+
+# ---------------------------------------------------------------------------- pool de-duplication (row f1)
+@pytest.mark.parametrize("fam", [0, 1, 2])
+@pytest.mark.parametrize("labeled", [True, False])
+def test_pool_dedup_matches_host_twin_and_networkx(eng, fam, labeled):
+    """nbw_pool_dedup (allow_isomorphism=False of generate_test_graphs.py:497-520): the keep-first mask equals the
+    host twin's, and on a small pool the classes are exactly networkx's isomorphism classes."""
+    import networkx as nx
+    from nasbowl_b200.cells import OpVocab
+    N = 1500 if fam < 2 else 300
+    batch = synth.generate_cells_host(fam, 21, 0, N)
+    n_max = batch.n_max
+    cells = eng.upload_cells(batch)
+    for n_prot in (0, 40):
+        keep, n_classes, n_kept = eng.pool_dedup(cells, n_max, labeled=labeled, n_protected=n_prot)
+        ref = synth.dedup_keep_first_host(batch, labeled=labeled, n_protected=n_prot)
+        got = keep.cpu().numpy().astype(bool)
+        assert np.array_equal(got[n_prot:], ref)
+        assert n_kept == int(ref.sum()) and n_classes == len(set(synth.isomorphism_classes_host(batch, labeled)))
+    # networkx on the first 120 cells: same signature <=> isomorphic
+    M = 120
+    keep, _, _ = eng.pool_dedup(cells[:M].contiguous(), n_max, labeled=labeled)
+    k = keep.cpu().numpy().astype(bool)
+    gs = batch[:M].to_networkx(OpVocab(synth.FAMILY_OPS[fam]))
+    nm = (lambda a, c: a['op_name'] == c['op_name']) if labeled else None
+    reps = [i for i in range(M) if k[i]]
+    for i in range(M):
+        iso_earlier = any(nx.is_isomorphic(gs[i], gs[j], node_match=nm) for j in reps if j < i)
+        assert k[i] == (not iso_earlier), (i, k[i], iso_earlier)
+
+
+def test_mutation_pool_has_no_isomorphic_members(eng):
+    """pools.mutation_pool: distinct children that are not isomorphic to a parent, topped up with random cells."""
+    import networkx as nx
+    from nasbowl_b200 import pools
+    from nasbowl_b200.cells import OpVocab
+    parents_b = synth.generate_cells_host(0, 3, 0, 10)
+    parents = eng.upload_cells(parents_b)
+    pool = pools.mutation_pool(eng, parents, pool_size=120, seed=5, labeled=True)
+    assert pool.shape == (120, 16)
+    b = CellBatch.from_records(pool.cpu().numpy(), 8)
+    vocab = OpVocab(synth.FAMILY_OPS[0])
+    kids = b[:60].to_networkx(vocab)
+    pg = parents_b.to_networkx(vocab)
+    nm = lambda a, c: a['op_name'] == c['op_name']
+    for i, g in enumerate(kids):
+        assert not any(nx.is_isomorphic(g, p, node_match=nm) for p in pg)
+        assert not any(nx.is_isomorphic(g, kids[j], node_match=nm) for j in range(i))
+    # the reference's structure-only rule leaves far fewer children per batch, the pool is still filled
+    pool2 = pools.mutation_pool(eng, parents, pool_size=40, seed=5, labeled=False)
+    assert pool2.shape == (40, 16)
+    # allow_isomorphism=True: plain mutation batch
+    pool3 = pools.mutation_pool(eng, parents, pool_size=40, seed=5, allow_isomorphism=True)
+    assert torch.equal(pool3[:20], eng.mutate_cells(0, parents, 5, 0, 64)[:20])
