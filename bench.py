@@ -398,30 +398,58 @@ def run_scoring(name, args, ctx):
     torch.cuda.synchronize()
     e2e_ms = 1e3 * (time.perf_counter() - t0)
 
-    # ---- one whole BO iteration on the fitting rank: refit + score state (+ broadcast) + score + top-5
-    bo_iter_ms = None
-    bo_t = []
-    for it in range(3):
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
+    # ---- whole BO iterations (nasbench_optimisation.py:153-216): five new evaluated cells join the training set,
+    # the surrogate is refitted (reset_XY + fit: appended to the previous fit where the path allows),
+    # the pool operators are rebuilt, broadcast, and one pool is scored with its top-5.  Wall clock, best of 3.
+    import copy
+    bo = {}
+    for mode in ("incremental", "scratch"):
+        big, y_big = make_training_set(dict(w, n_train=w["n_train"] + 20))
+        n0 = w["n_train"]
         if rank == 0:
-            reset_gp(w, gp, train, y)
-            fit_gp(w, gp, train, y)
-            pm2 = gp._score_state()
-        else:
-            pm2 = None
-        if world > 1:
-            pm2 = parallel.broadcast_pool_model(pm2, src=0)
-            if rank != 0:
-                gp.set_pool_model(pm2)
-        acq2 = GraphExpectedImprovement(gp)
-        parallel.score_and_select(eng, acq2._model(), pools[0], M, TOP_N, True, lo, scores=score_buf,
-                                  cand_buf=cand_buf, gathered=gather_buf)
-        torch.cuda.synchronize()
-        bo_t.append(1e3 * (time.perf_counter() - t0))
-    bo_iter_ms = min(bo_t)
+            gp.incremental = mode == "incremental"
+            reset_gp(w, gp, big[:n0], y_big[:n0])
+            fit_gp(w, gp, big[:n0], y_big[:n0])
+            gp._score_state()
+        ts = []
+        for it in range(1, 4):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            if rank == 0:
+                nn = n0 + 5 * it
+                gp.reset_XY(big[:nn], y_big[:nn])
+                fit_gp(w, gp, big[:nn], y_big[:nn])
+                pm2 = gp._score_state()
+            else:
+                pm2 = None
+            if world > 1:
+                pm2 = parallel.broadcast_pool_model(pm2, src=0)
+                if rank != 0:
+                    gp.set_pool_model(pm2)
+            acq2 = GraphExpectedImprovement(gp)
+            parallel.score_and_select(eng, acq2._model(), pools[0], M, TOP_N, True, lo, scores=score_buf,
+                                      cand_buf=cand_buf, gathered=gather_buf)
+            torch.cuda.synchronize()
+            ts.append(1e3 * (time.perf_counter() - t0))
+        bo[mode] = min(ts)
+        if rank == 0 and mode == "incremental":
+            bo["appended"] = bool(gp.last_fit_incremental)
+    bo_iter_ms, bo_scratch_ms = bo["incremental"], bo["scratch"]
+    # back to the benchmark's surrogate for the parity checks below
+    if rank == 0:
+        gp.incremental = True
+        reset_gp(w, gp, train, y)
+        gp._prev = None
+        fit_gp(w, gp, train, y)
+        pm2 = gp._score_state()
+    else:
+        pm2 = None
+    if world > 1:
+        pm2 = parallel.broadcast_pool_model(pm2, src=0)
+        if rank != 0:
+            gp.set_pool_model(pm2)
     model = GraphExpectedImprovement(gp)._model()
     acq = GraphExpectedImprovement(gp)
 
@@ -472,9 +500,9 @@ def run_scoring(name, args, ctx):
 
     # ---- max over ranks
     if world > 1:
-        t = torch.tensor([elapsed_ms, e2e_ms, kernel_ms, bo_iter_ms], dtype=torch.float64, device="cuda")
+        t = torch.tensor([elapsed_ms, e2e_ms, kernel_ms, bo_iter_ms, bo_scratch_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms, e2e_ms, kernel_ms, bo_iter_ms = [float(x) for x in t.cpu()]
+        elapsed_ms, e2e_ms, kernel_ms, bo_iter_ms, bo_scratch_ms = [float(x) for x in t.cpu()]
         lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
         dist.all_reduce(lt, op=dist.ReduceOp.SUM)
         launches = int(lt.item())
@@ -516,7 +544,10 @@ def run_scoring(name, args, ctx):
                    "l2": "inputs larger than L2: %d rotating pools x %.0f MB per GPU" % (n_pools, M * rec_bytes / 1e6),
                    "fused_topk": bool(fused), "pipeline": "one pool in flight: exchange of pool i under the scoring of pool i+1",
                    "fit_ms": fit_ms, "score_state_ms": state_ms, "broadcast_ms": bcast_ms,
-                   "broadcast_cold_ms": bcast_cold_ms, "bo_iter_ms": bo_iter_ms, "model_bytes": pm.nbytes()},
+                   "broadcast_cold_ms": bcast_cold_ms, "bo_iter_ms": bo_iter_ms, "bo_iter_from_scratch_ms": bo_scratch_ms,
+                   "bo_iter_appended": bo.get("appended"),
+                   "bo_iter": "5 cells appended, reset_XY + fit + pool operators + broadcast + one pool scored + top-5 (wall clock, best of 3)",
+                   "model_bytes": pm.nbytes()},
         "roofline": roof,
         "cpu_baseline": cpu_baseline,
         "e2e": {"value": total * e_steps / (e2e_ms / 1e3), "unit": "candidates/s",

@@ -99,6 +99,13 @@ int nbw_dict_build(nbw_ctx* ctx, const uint64_t* keys, const uint64_t* chks, int
 int nbw_wl_fit(nbw_ctx* ctx, const void* cells, int64_t n_cells, int n_max, int h, uint64_t seed,
                uint32_t* ids, uint64_t* uniq_keys, uint64_t* uniq_chks, int64_t* dims_h, void* stream);
 
+/* ids_out[i] = map[ids_in[i]] (NBW_INVALID_ID is kept): renumber the labels of one level — from the sorted order
+ * of a fresh nbw_dict_build to the APPEND-ONLY numbering of a training dictionary that grows across BO iterations
+ * (the reference re-derives all ids from scratch on every fit, weisfeiler_lehman.py:223-296; keys are canonical
+ * here, so the labels of the previous fit keep their ids and columns and new labels are appended). */
+int nbw_remap_ids(nbw_ctx* ctx, const uint32_t* ids_in, int64_t n, const uint32_t* map, uint32_t* ids_out,
+                  void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * (3) Vertex histograms — replaces VertexHistogram.parse_input,
  *     grakel_replace/vertex_histogram.py:98-209 (dense Phi of small integer counts).

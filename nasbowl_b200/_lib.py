@@ -83,6 +83,7 @@ _PROTOTYPES = {
     "nbw_dict_build": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i64,
                                  C.POINTER(_i64), _vp]),
     "nbw_wl_fit": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _u64, _vp, _vp, _vp, C.POINTER(_i64), _vp]),
+    "nbw_remap_ids": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "nbw_hist_dense_i8": (C.c_int, [_vp, _vp, _i64, _i32, _i32, C.POINTER(_i64), C.POINTER(_i64), _vp,
                                     _i32, _vp, _i64, _vp, _vp]),
     "nbw_oa_thermo_layout": (C.c_int, [_vp, _vp, _i64, _i32, _i32, C.POINTER(_i64), _vp, _vp,

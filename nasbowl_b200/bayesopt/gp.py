@@ -128,6 +128,9 @@ class GraphGP:
         self.logDetK = None
         self._fitted = False
         self._dev = None           # device state of the last fit (not pickled)
+        self._prev = None          # ... of the fit before reset_XY: the next fit may append to it
+        self.incremental = True    # False: every fit() starts from scratch
+        self.last_fit_incremental = False
 
     # ------------------------------------------------------------------ device helpers
     def _engine(self):
@@ -189,6 +192,67 @@ class GraphGP:
     def _y_device(self, eng):
         return torch.as_tensor(np.asarray(self.y.detach().cpu().numpy(), dtype=np.float64)).to(eng.device)
 
+    # ------------------------------------------------------------------ incremental refit
+    def _incremental_base(self, slots: CellSlots, wl_subtree_candidates, optimize_wl_layer_weights):
+        """The previous fit's device state if this fit can extend it: one plain linear WL kernel, the same record
+        width and WL depth, and the old training cells as a prefix of the new ones."""
+        prev = self._prev
+        if prev is None or not self.incremental or os.environ.get("NBW_NO_INCREMENTAL"):
+            return None
+        ks = list(self.sum_kernels.kernels)
+        if len(ks) != 1 or not isinstance(ks[0], WeisfilerLehman) or ks[0].oa or ks[0].undirected or optimize_wl_layer_weights:
+            return None
+        k = ks[0]
+        if prev.get('records') is None or slots.n_slots != 1 or prev['n_max'] != slots.n_max or len(prev['fits']) != 1:
+            return None
+        old = prev['records']
+        n_old = old.shape[0]
+        if n_old >= len(slots) or prev['fits'][0].oa:
+            return None
+        h_fit = max([int(c) for c in wl_subtree_candidates] + [k.h])
+        if prev['fits'][0].h != h_fit or k._level_weights(k.h) is not None:
+            return None
+        if not np.array_equal(slots.slots[0].labels[:n_old], old[:, :slots.n_max]) or \
+                not np.array_equal(slots.slots[0].to_records()[:n_old], old):
+            return None
+        return prev
+
+    def _append_factor(self, eng, prev, K, lik, y_dev):
+        """Rank-k append of the Cholesky factor and its inverse: with K' = [[K, k12], [k12^T, K22]] (the old block
+        is unchanged: raw Gram entries and the cosine normalisation of old cells do not depend on the new ones),
+            L' = [[L, 0], [A^T, L22]],  A = L^-1 k12,  L22 L22^T = K22 + lik I - A^T A,
+            L'^-1 = [[L^-1, 0], [-L22^-1 A^T L^-1, L22^-1]],
+        O(n^2 k) instead of the O(n^3) of compute_pd_inverse (utils.py:120-140).  Returns None when the Schur
+        complement is not positive definite (the caller factors from scratch with the reference's jitter retry)."""
+        n, m = prev['fits'][0].n_cells, self.n
+        kk = m - n
+        Lo, Li = prev['L'], prev['Linv']
+        A = eng.empty((n, kk), torch.float64)
+        eng.gemm(False, False, n, kk, n, 1.0, Li, n, K[:n, n:], m, 0.0, A, kk)
+        S = K[n:, n:].clone()
+        eng.gemm(True, False, kk, kk, n, -1.0, A, kk, A, kk, 1.0, S, kk)
+        try:
+            L22, L22i, _, logdet_s, _, _, _ = eng.gp_factor(S, lik, y_dev[:kk].contiguous(), True)
+        except _lib.NotPositiveDefinite:
+            return None
+        L = torch.zeros((m, m), dtype=torch.float64, device=eng.device)
+        Linv = torch.zeros((m, m), dtype=torch.float64, device=eng.device)
+        L[:n, :n].copy_(Lo)
+        L[n:, :n].copy_(A.t())
+        L[n:, n:].copy_(L22)
+        Linv[:n, :n].copy_(Li)
+        Linv[n:, n:].copy_(L22i)
+        T1 = eng.empty((kk, n), torch.float64)
+        eng.gemm(True, False, kk, n, n, 1.0, A, kk, Li, n, 0.0, T1, n)
+        eng.gemm(False, False, kk, n, kk, -1.0, L22i, kk, T1, n, 0.0, Linv[n:, :n], m)
+        z = eng.empty((m,), torch.float64)
+        eng.gemm(False, False, m, 1, m, 1.0, Linv, m, y_dev, 1, 0.0, z, 1)
+        alpha = eng.empty((m,), torch.float64)
+        eng.gemm(True, False, m, 1, m, 1.0, Linv, m, z, 1, 0.0, alpha, 1)
+        yKy = eng.empty((1,), torch.float64)
+        eng.gemm(True, False, 1, 1, m, 1.0, z, 1, z, 1, 0.0, yKy, 1)
+        return L, Linv, alpha, prev['logdet'] + logdet_s, float(yKy.item())
+
     # ------------------------------------------------------------------ grid search over h
     def _grid_search_wl_kernel(self, k: WeisfilerLehman, fit, subtree_candidates, y_dev, lik):
         """bayesopt/gp.py:493-538: for each candidate h, marginal likelihood of the
@@ -246,6 +310,9 @@ class GraphGP:
             slots = slots.widen(self.n_max)
         y_dev = self._y_device(eng)
         self.nlml_grid = {}
+        prev = self._incremental_base(slots, wl_subtree_candidates, optimize_wl_layer_weights)
+        self._prev = None
+        self.last_fit_incremental = False
 
         # 1. WL features once per kernel, deep enough for every candidate; h by marginal likelihood.
         #    Every kernel reads ITS view of the examples (record slot, undirected or not): uploaded once per view.
@@ -262,7 +329,15 @@ class GraphGP:
             views.append(key)
             cands = [int(c) for c in wl_subtree_candidates]
             h_fit = max(cands + [k.h])
-            fit = k.fit_device(cells, batch.n_max, h=h_fit, batch=batch)
+            fit = None
+            if prev is not None:
+                fit = eng.wl_fit_append(prev['fits'][0], cells)
+                if fit is None:
+                    prev = None
+                else:
+                    k._fit, k._fit_batch, k._ref_cache, k._lin_cache = fit, batch, None, None
+            if fit is None:
+                fit = k.fit_device(cells, batch.n_max, h=h_fit, batch=batch)
             if len(cands):
                 self._grid_search_wl_kernel(k, fit, cands, y_dev, self.likelihood)
             fits.append(fit)
@@ -311,6 +386,7 @@ class GraphGP:
         #    instead of autograd.
         likelihood = torch.tensor(self.likelihood, )
         nlml = None
+        nlml_pending = False
         factor_cache = {}
 
         def factor(lam: float):
@@ -347,7 +423,15 @@ class GraphGP:
             skip_first = (light and optimizer.lower() == 'adam' and optimize_lik and levels is None and iters >= 2
                           and not self.verbose and float(likelihood) + float(optimizer_kwargs.get('lr', 1e-3)) * 0.999 >= max_lik
                           and max_lik >= 1e-5)
+            # (when the loop only ever visits max_lik and the previous fit can be extended, the factorisation is
+            #  left to the append below: nlml of the last iteration is that of the final factor)
+            defer = skip_first and prev is not None and prev['hs'] == [k.h for k in kernels] and \
+                prev['lik'] == float(np.float32(max_lik))
             for i in range(iters):
+                if defer:
+                    likelihood.fill_(max_lik)
+                    nlml_pending = True
+                    break
                 if not light:
                     optim.zero_grad()
                 if skip_first and i == 0:
@@ -410,7 +494,17 @@ class GraphGP:
                     k.change_kernel_params({'layer_weights': layer_weights.clone()})
         self.layer_weights = layer_weights
         lik = float(likelihood.item())
-        L, Linv, alpha, logdet, yKy, _, _ = factor(lik)
+        appended = None
+        if prev is not None and lik not in factor_cache and prev['hs'] == [k.h for k in kernels] and prev['lik'] == lik:
+            appended = self._append_factor(eng, prev, K, lik, y_dev)
+        if appended is not None:
+            L, Linv, alpha, logdet, yKy = appended
+            nlml = _nlml_from_stats(logdet, yKy, self.n) if nlml_pending else nlml
+            self.last_fit_incremental = True
+        else:
+            L, Linv, alpha, logdet, yKy, _, _ = factor(lik)
+            if nlml_pending:
+                nlml = _nlml_from_stats(logdet, yKy, self.n)
         # predict() normalises the joint Gram with the STORED weights, which are one optimiser step ahead of
         # the K behind K_i (gp.py:186-215 keeps the K of the last loop iteration): the pool path needs the
         # training diagonal under those final weights
@@ -426,7 +520,10 @@ class GraphGP:
         self.nlml = torch.tensor(nlml, dtype=torch.float64) if nlml is not None else None
         self.sum_kernels.weights = weights.clone()
         self._fitted = True
-        self._dev = dict(eng=eng, fits=fits, hs=[k.h for k in self.sum_kernels.kernels], K=K, L=L, Linv=Linv,
+        self._dev = dict(eng=eng, fits=fits, hs=[k.h for k in self.sum_kernels.kernels], K=K, L=L, Linv=Linv, logdet=logdet,
+                         lik=lik, records=slots.slots[0].to_records() if slots.n_slots == 1 else None,
+                         prev_score=(prev.get('score') if prev is not None and self.last_fit_incremental else None),
+                         prev_n=(prev['fits'][0].n_cells if prev is not None else 0),
                          alpha=alpha, s=inv_sqrt_diag, s_pool=s_pool, y=y_dev, n_max=slots.n_max, n_slots=slots.n_slots,
                          views=views, view_cells=view_cells, slots=slots,
                          weights=[float(w) for w in weights], score=None, K_host=None, Ki_host=None)
@@ -587,10 +684,34 @@ class GraphGP:
             for i, pm in enumerate(parts):
                 B, _ = scaled_features(i)
                 eng.prefix_features(B, fits[i], hs[i], out=Bp[:, pm.label_base:], ldp=T + 1)
-            Wp = eng.empty((n, T + 1), torch.float64)
-            eng.gemm(False, False, n, T + 1, n, 1.0, Linv, n, Bp, T + 1, 0.0, Wp, T + 1)
-            H = eng.empty((T + 1, T + 1), torch.float64)
-            eng.gemm(True, False, T + 1, T + 1, n, 1.0, Wp, T + 1, Wp, T + 1, 0.0, H, T + 1)
+            ps, n_old = d.get('prev_score'), d.get('prev_n', 0)
+            if ps is not None and plain and ps.H is not None and ps.h == first.h and not ps.more and 0 < n_old < n:
+                # Rank-k update (row f2): the factor was APPENDED, so L^-1 of the old cells is unchanged, and — the
+                # dictionary being append-only — so are their rows of Bp in the columns of old labels; in the
+                # column of a NEW label an old cell carries the prefix sum of that label's nearest old ancestor
+                # (its own count there is zero).  Hence H' = E H E^T + Wn^T Wn: E copies row / column p(a) of the
+                # previous H to every label a (p = nearest old ancestor, a itself if old, the zero slot if none),
+                # Wn = the k new rows of L'^-1 Bp'.  O(k n T + k T^2 + T^2) instead of O(n^2 T + n T^2).
+                kk = n - n_old
+                Wn = eng.empty((kk, T + 1), torch.float64)
+                eng.gemm(False, False, kk, T + 1, n, 1.0, Linv[n_old:, :], n, Bp, T + 1, 0.0, Wn, T + 1)
+                lo_o, lo_n = ps.label_off, first.label_off
+                par = fits[0].parents.cpu().numpy().astype(np.int64)
+                anc = np.full(T + 1, ps.total_labels, dtype=np.int64)          # default: the zero slot of the old H
+                for l in range(first.h + 1):
+                    d_old, d_new = lo_o[l + 1] - lo_o[l], lo_n[l + 1] - lo_n[l]
+                    anc[lo_n[l]:lo_n[l] + d_old] = lo_o[l] + np.arange(d_old)
+                    if l > 0 and d_new > d_old:
+                        pa = par[lo_n[l] + d_old:lo_n[l + 1]]                    # level-(l-1) ids of the new labels' parents
+                        anc[lo_n[l] + d_old:lo_n[l + 1]] = anc[lo_n[l - 1] + pa]
+                idx = torch.from_numpy(anc).to(eng.device)
+                H = ps.H.index_select(0, idx).index_select(1, idx).contiguous()
+                eng.gemm(True, False, T + 1, T + 1, kk, 1.0, Wn, T + 1, Wn, T + 1, 1.0, H, T + 1)
+            else:
+                Wp = eng.empty((n, T + 1), torch.float64)
+                eng.gemm(False, False, n, T + 1, n, 1.0, Linv, n, Bp, T + 1, 0.0, Wp, T + 1)
+                H = eng.empty((T + 1, T + 1), torch.float64)
+                eng.gemm(True, False, T + 1, T + 1, n, 1.0, Wp, T + 1, Wp, T + 1, 0.0, H, T + 1)
             w_mu_p = eng.empty((T + 1,), torch.float64)
             eng.gemm(True, False, T + 1, 1, n, 1.0, Bp, T + 1, alpha, 1, 0.0, w_mu_p, 1)
             first.H, first.w_mu_prefix = H, w_mu_p
@@ -632,6 +753,11 @@ class GraphGP:
         self.y_ = train_y
         self.y, self.y_mean, self.y_std = normalize_y(_as_f64(train_y))
         self.logDetK = None
+        # the device state of the last fit stays around: when the new examples EXTEND the old ones (the BO loop
+        # appends a batch per iteration, nasbench_optimisation.py:209-213) the next fit() appends to it instead of
+        # starting over (row f2 of SURVEY §8: rank-k Cholesky append, append-only dictionary)
+        if self._fitted and self._dev is not None and 'fits' in self._dev:
+            self._prev = self._dev
         self._fitted = False
         self._dev = None
 
@@ -672,6 +798,7 @@ class GraphGP:
     def __getstate__(self):
         st = dict(self.__dict__)
         st['_dev'] = None
+        st['_prev'] = None
         st['_fitted'] = False      # device state does not travel; call fit() after unpickling
         return st
 

@@ -455,3 +455,27 @@ extern "C" int nbw_wl_fit(nbw_ctx* ctx, const void* cells, int64_t n_cells, int 
   }
   return NBW_OK;
 }
+
+// ids_out[i] = map[ids_in[i]] (NBW_INVALID_ID stays): renumbering of a level's labels, e.g. from the sorted order
+// of a fresh dictionary build to the append-only numbering of a growing training dictionary.
+namespace {
+__global__ void remap_ids_kernel(const uint32_t* __restrict__ in, int64_t n, const uint32_t* __restrict__ map,
+                                 uint32_t* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t v = in[i];
+    out[i] = v == NBW_INVALID_ID ? v : map[v];
+  }
+}
+}  // namespace
+
+extern "C" int nbw_remap_ids(nbw_ctx* ctx, const uint32_t* ids_in, int64_t n, const uint32_t* map, uint32_t* ids_out,
+                             void* stream) {
+  if (!ctx) return NBW_ERR_INVALID;
+  NBW_REQUIRE(ctx, n >= 0, "n negative");
+  if (n == 0) return NBW_OK;
+  NBW_REQUIRE(ctx, ids_in && map && ids_out, "null pointer");
+  remap_ids_kernel<<<nbw_grid_for(ctx, n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(ids_in, n, map, ids_out);
+  NBW_CHECK_LAUNCH(ctx);
+  return NBW_OK;
+}

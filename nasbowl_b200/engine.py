@@ -185,6 +185,66 @@ class Engine:
             self.build_features(fit)
         return fit
 
+    def wl_fit_append(self, prev: WLFit, cells: torch.Tensor, build_features: bool = True) -> Optional[WLFit]:
+        """WL fit of a batch whose first prev.n_cells cells are the batch `prev` was fitted on, with the
+        dictionary grown APPEND-ONLY: every label of the previous fit keeps its id (hence its feature column and
+        its place in the pool operators), labels that the new cells introduce get the next ids of their level.
+        Keys are canonical (a label is hashed through the key of its previous label, wl_relabel.cu), so the
+        fresh dictionary of the whole batch is matched against the previous one key by key on the host (a few
+        thousand u64) and the node ids are renumbered on the device (nbw_remap_ids).  Returns None when the
+        hashing collided for the previous seed (the caller refits from scratch)."""
+        n_max, h = prev.n_max, prev.h
+        n = cells.numel() // record_stride(n_max)
+        try:
+            fresh = self._wl_fit_once(cells, n, n_max, h, prev.oa, prev.seed, build_features=False)
+        except _lib.HashCollision:
+            return None
+        n_keys = n * n_max
+        ids = self.empty((h + 1, n_keys), torch.int32)
+        dims, ukeys, uchks = [], [], []
+        host_keys = getattr(prev, "_host_keys", None) or [k.cpu().numpy().view(np.uint64) for k in prev.uniq_keys]
+        new_host = []
+        for l in range(h + 1):
+            old = host_keys[l]
+            order = np.argsort(old, kind="stable")
+            old_sorted = old[order]
+            new = fresh.uniq_keys[l].cpu().numpy().view(np.uint64)
+            pos = np.searchsorted(old_sorted, new)
+            pos_c = np.minimum(pos, max(len(old) - 1, 0))
+            found = (pos < len(old)) & (old_sorted[pos_c] == new) if len(old) else np.zeros(len(new), dtype=bool)
+            mapping = np.empty(len(new), dtype=np.uint32)
+            mapping[found] = order[pos_c[found]]
+            extra = np.nonzero(~found)[0]
+            mapping[extra] = len(old) + np.arange(len(extra), dtype=np.uint32)
+            if int(found.sum()) != len(old):
+                return None                 # a previous label vanished: the old cells are not a prefix of this batch
+            map_dev = torch.from_numpy(mapping.view(np.int32)).to(self.device)
+            self._check(self.lib.nbw_remap_ids(self.ctx, self._p(fresh.ids[l]), n_keys, self._p(map_dev), self._p(ids[l]),
+                                               self.stream))
+            extra_dev = torch.from_numpy(extra.astype(np.int64)).to(self.device)
+            ukeys.append(torch.cat([prev.uniq_keys[l], fresh.uniq_keys[l][extra_dev]]))
+            uchks.append(torch.cat([prev.uniq_chks[l], fresh.uniq_chks[l][extra_dev]]))
+            new_host.append(np.concatenate([old, new[extra]]))
+            dims.append(len(old) + len(extra))
+        label_off = [0]
+        for d in dims:
+            label_off.append(label_off[-1] + d)
+        parents = torch.zeros((max(label_off[-1], 1),), dtype=torch.int32, device=self.device)
+        for l in range(1, h + 1):
+            if dims[l] > 0:
+                self._check(self.lib.nbw_label_parents(self.ctx, self._p(ids[l - 1]), self._p(ids[l]), n_keys,
+                                                       self._p(parents[label_off[l]:]), self.stream))
+        col_off = [0]
+        for w in dims:
+            col_off.append(col_off[-1] + _round_up(max(w, 1), 128))
+        fit = WLFit(n_cells=n, n_max=n_max, h=h, oa=prev.oa, seed=prev.seed, ids=ids, dims=dims, uniq_keys=ukeys,
+                    uniq_chks=uchks, label_off=label_off, widths=list(dims), col_off=col_off, phi=None, self_sim=None,
+                    op_codes=new_host[0].astype(np.int64), parents=parents)
+        fit._host_keys = new_host
+        if build_features:
+            self.build_features(fit)
+        return fit
+
     def build_features(self, fit: WLFit):
         """Dense int8 histogram rows (VertexHistogram.parse_input, vertex_histogram.py:98-209)."""
         n, h = fit.n_cells, fit.h

@@ -47,6 +47,39 @@ def main():
         gathered = [None] * world
         dist.all_gather_object(gathered, [int(i) for i in idx])
         assert all(g == gathered[0] for g in gathered), "ranks disagree on the proposal"
+    # a sum of kernels over two record slots (normal | reduce), pool steps in flight (PoolPipeline): the exchange of
+    # pool i runs under the scoring of pool i + 1 and every selection still equals the single-GPU one
+    from nasbowl_b200.cells import CellSlots
+    n = 50
+    tr = CellSlots([synth.generate_cells_host(2, 5, 0, n), synth.generate_cells_host(2, 6, 0, n)])
+    y = torch.randn(n, generator=torch.Generator().manual_seed(9))
+    gp = GraphGP(tr, y, [WeisfilerLehman(h=2, slot=0), WeisfilerLehman(h=2, slot=1)], weights=[0.5, 0.5])
+    pm = None
+    if rank == 0:
+        gp.fit(wl_subtree_candidates=(), optimize_lik=False)
+        pm = gp._score_state()
+    pm = parallel.broadcast_pool_model(pm, src=0)
+    if rank != 0:
+        gp.set_pool_model(pm)
+    assert len(pm.more) == 1 and pm.n_slots == 2
+    acq = GraphExpectedImprovement(gp)
+    model = acq._model()
+    M = 60_001
+    lo, hi = parallel.shard_range(M, rank, world)
+    pipe = parallel.PoolPipeline(eng, 5, True, depth=2)
+    pools, tickets, results = [], [], []
+    for p in range(4):
+        shard = torch.cat([eng.generate_cells(2, 100 + p, 1000 + lo, hi - lo), eng.generate_cells(2, 200 + p, 1000 + lo, hi - lo)], dim=1).contiguous()
+        pools.append(shard)
+        tickets.append(pipe.submit(model, shard, hi - lo, lo))
+        if p >= 1:
+            results.append(pipe.collect(tickets[p - 1]))
+    results.append(pipe.collect(tickets[-1]))
+    for p in range(4):
+        whole = torch.cat([eng.generate_cells(2, 100 + p, 1000, M), eng.generate_cells(2, 200 + p, 1000, M)], dim=1).contiguous()
+        s_all = acq.score_pool(whole)[0]
+        v1, i1 = eng.topk(s_all, 5, distinct=True)
+        assert np.array_equal(results[p][1], i1) and np.array_equal(results[p][0], v1), (rank, p, results[p], i1)
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:

@@ -367,3 +367,54 @@ def test_blocked_cholesky_and_inverse_at_block_boundaries():
     bad = torch.tensor(Kh - 5.0 * np.eye(1000), device="cuda")        # breaks down in a later panel
     with pytest.raises(_lib.NotPositiveDefinite):
         eng.gp_factor(bad, 0.0, torch.zeros(1000, dtype=torch.float64, device="cuda"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fam,n0,h_grid", [(0, 60, (1, 2)), (1, 150, tuple(range(6))), (2, 120, (2,))])
+def test_incremental_refit_matches_from_scratch(fam, n0, h_grid):
+    """a BO loop appends a batch per iteration (nasbench_optimisation.py:209-213) and refits.
+    reset_XY + fit on examples that EXTEND the previous ones appends to the previous fit — append-only
+    dictionary, rank-k Cholesky / inverse append, rank-k update of the pool operators — and must agree with a
+    from-scratch fit at 1e-9, iteration after iteration."""
+    from nasbowl_b200 import synth
+    from nasbowl_b200.bayesopt import GraphExpectedImprovement, GraphGP
+    from nasbowl_b200.cells import CellBatch
+    from nasbowl_b200.kernels import WeisfilerLehman
+    total = n0 + 4 * 5
+    cells = synth.generate_cells_host(fam, 8, 0, total)
+    y_all = torch.randn(total, generator=torch.Generator().manual_seed(fam)).double()
+    pool = synth.generate_cells_host(fam, 9, 5000, 3000)
+    gp = GraphGP(cells[:n0], y_all[:n0], [WeisfilerLehman(h=2)], n_max=cells.n_max)
+    gp.fit(wl_subtree_candidates=h_grid, optimize_lik=True, max_lik=0.01)
+    assert not gp.last_fit_incremental
+    used = 0
+    for it in range(1, 5):
+        n = n0 + 5 * it
+        gp.reset_XY(cells[:n], y_all[:n])
+        gp.fit(wl_subtree_candidates=h_grid, optimize_lik=True, max_lik=0.01)
+        used += int(gp.last_fit_incremental)
+        ref = GraphGP(cells[:n], y_all[:n], [WeisfilerLehman(h=2)], n_max=cells.n_max)
+        ref.incremental = False
+        if it > 1:
+            ref.likelihood = 0.01                  # the noise the loop carries over from the previous fit (Q5)
+            ref.likelihood = float(np.float32(0.01))
+        ref.fit(wl_subtree_candidates=h_grid, optimize_lik=True, max_lik=0.01)
+        assert gp.kernels[0].h == ref.kernels[0].h and gp.likelihood == ref.likelihood
+        np.testing.assert_allclose(float(gp.nlml), float(ref.nlml), rtol=1e-10)
+        np.testing.assert_allclose(float(gp.logDetK), float(ref.logDetK), rtol=1e-10)
+        np.testing.assert_allclose(gp.K.numpy(), ref.K.numpy(), rtol=0, atol=0)
+        np.testing.assert_allclose(gp.K_i.numpy(), ref.K_i.numpy(), rtol=1e-9, atol=1e-9)
+        mu_a, var_a = gp.predict_diag(pool)
+        mu_b, var_b = ref.predict_diag(pool)
+        np.testing.assert_allclose(mu_a.numpy(), mu_b.numpy(), rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(var_a.numpy(), var_b.numpy(), rtol=1e-9, atol=1e-12)
+        ia = GraphExpectedImprovement(gp).propose_location(pool, top_n=5)[2]
+        ib = GraphExpectedImprovement(ref).propose_location(pool, top_n=5)[2]
+        assert set(int(i) for i in ia) == set(int(i) for i in ib)
+        # same vocabulary sizes as the from-scratch dictionary, old labels kept their ids
+        assert gp._dev['fits'][0].dims == ref._dev['fits'][0].dims
+    assert used >= 3, "the incremental path was not taken"
+    # examples that do not extend the old ones: from scratch again
+    gp.reset_XY(cells[5:n0 + 5], y_all[5:n0 + 5])
+    gp.fit(wl_subtree_candidates=h_grid, optimize_lik=True, max_lik=0.01)
+    assert not gp.last_fit_incremental
