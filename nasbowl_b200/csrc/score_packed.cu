@@ -532,6 +532,337 @@ score_packed_kernel(const __grid_constant__ PackedParams P, const uint8_t* __res
   }
 }
 
+// ------------------------------------------------------------------ one THREAD per cell (8-node records)
+// The lane-per-node kernel above spends most of its instructions on moving data between lanes (shuffles, votes,
+// segmented reductions, rounds that run to the widest node of the warp).  For 8-node cells a single thread can
+// hold a whole cell: labels, adjacency rows and label classes are bytes of 64-bit registers, per-node arrays
+// are statically indexed registers, and the only dynamically indexed data — what a node contributes to its
+// predecessors (fetched hashes + class count) — sits in a per-thread column of shared memory (bank =
+// thread, whatever the node: conflict-free).  A warp scores 32 cells per pass with no inter-lane traffic at
+// all; divergence (cells of different sizes) costs less than the idle lanes it replaces.
+constexpr int kCellThreads = 128;
+
+// bit j of byte i of the result = bit i of byte j of x: transpose of an 8 x 8 bit matrix (successor rows ->
+// predecessor rows)
+__device__ __forceinline__ uint64_t transpose8x8(uint64_t x) {
+  uint64_t t;
+  t = (x ^ (x >> 7)) & 0x00AA00AA00AA00AAull; x ^= t ^ (t << 7);
+  t = (x ^ (x >> 14)) & 0x0000CCCC0000CCCCull; x ^= t ^ (t << 14);
+  t = (x ^ (x >> 28)) & 0x00000000F0F0F0F0ull; x ^= t ^ (t << 28);
+  return x;
+}
+// bit i = byte i of w is not zero
+__device__ __forceinline__ uint32_t nonzero_bits4(uint32_t w) {
+  return ((__vcmpne4(w, 0u) & 0x08040201u) * 0x01010101u) >> 24;
+}
+__device__ __forceinline__ uint32_t eq_bits8(uint64_t w, uint32_t byte) {
+  const uint32_t rep = byte * 0x01010101u;
+  const uint32_t lo = ((__vcmpeq4((uint32_t)w, rep) & 0x08040201u) * 0x01010101u) >> 24;
+  const uint32_t hi = ((__vcmpeq4((uint32_t)(w >> 32), rep) & 0x08040201u) * 0x01010101u) >> 24;
+  return lo | (hi << 4);
+}
+
+template <int NP, bool WEIGHTED, bool TOPK>
+__global__ void __launch_bounds__(kCellThreads)
+score_cell_kernel(const __grid_constant__ PackedParams P, const uint8_t* __restrict__ cells, int64_t n_cells,
+                  float* __restrict__ scores, double* __restrict__ mu64, double* __restrict__ var64,
+                  double* __restrict__ score64, NbwCand* __restrict__ block_cands, int k_top, int distinct,
+                  int64_t index_base) {
+  constexpr unsigned FULL = 0xffffffffu;
+  using KccT = typename std::conditional<WEIGHTED, double, int>::type;
+  __shared__ uint4 ent[8][kCellThreads];     // per node: {ha_lo, ha_hi, hb, class count field}
+  __shared__ float sh_tv[TOPK ? kTopMax : 1][kCellThreads];
+  __shared__ int sh_ti[TOPK ? kTopMax : 1][kCellThreads];
+  const int tid = threadIdx.x;
+  const int zero_slot = P.zero_slot;
+  const double* __restrict__ H = P.H;
+  const int64_t ldh = P.ld_h;
+  const int64_t stride = P.rec_stride;
+  if constexpr (TOPK) {
+#pragma unroll
+    for (int j = 0; j < kTopMax; ++j) { sh_tv[j][tid] = 0.f; sh_ti[j][tid] = -1; }
+  }
+
+  for (int64_t g = (int64_t)blockIdx.x * kCellThreads + tid; g < n_cells; g += (int64_t)gridDim.x * kCellThreads) {
+    int deep[NP][8];
+    KccT kacc = 0;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      const PartParams& Q = P.part[p];
+      const uint4 rec = __ldg(reinterpret_cast<const uint4*>(cells + g * stride + Q.rec_offset));
+      const uint64_t labw = ((uint64_t)rec.y << 32) | rec.x;
+      const uint32_t pm = present_bits4(rec.x) | (present_bits4(rec.y) << 4);       // present nodes
+      // adjacency rows, restricted to present nodes on both ends
+      uint64_t succw = ((uint64_t)rec.w << 32) | rec.z;
+      {
+        uint64_t rowmask = 0;                       // byte v = 0xFF for present v
+#pragma unroll
+        for (int v = 0; v < 8; ++v) rowmask |= ((pm >> v) & 1u) ? (0xFFull << (8 * v)) : 0ull;
+        succw &= rowmask & (0x0101010101010101ull * pm);
+      }
+      if (Q.undirected) succw |= transpose8x8(succw);   // kernels/weisfilerlehman.py:127-128
+      // nodes that are an endpoint of no edge are not relabelled
+      uint32_t tgt;
+      {
+        uint64_t x = succw | (succw >> 32);
+        x |= x >> 16;
+        x |= x >> 8;
+        tgt = (uint32_t)x & 0xFFu;
+      }
+      const uint32_t em = pm & (tgt | nonzero_bits4((uint32_t)succw) | (nonzero_bits4((uint32_t)(succw >> 32)) << 4));
+
+      // ---- level 0: op code -> dense id; classes = equal op codes
+      uint32_t dense[8];
+      uint32_t im = 0;           // nodes whose current label is in the dictionary
+      uint64_t clsw = 0;         // byte v = nodes that share v's label at the current level
+      int* dp = deep[p];
+#pragma unroll
+      for (int v = 0; v < 8; ++v) {
+        const uint32_t lab = (uint32_t)(labw >> (8 * v)) & 0xFFu;
+        const bool present = (pm >> v) & 1u;
+        const uint32_t d0 = present ? (uint32_t)__ldg(Q.level0_table + lab) : 0xFFFFu;
+        const bool seen = present && d0 != 0xFFFFu;
+        dense[v] = seen ? d0 : 0u;
+        im |= seen ? (1u << v) : 0u;
+        dp[v] = seen ? Q.label_base + Q.loff[0] + (int)d0 : zero_slot;
+        if (present) clsw |= (uint64_t)(eq_bits8(labw, lab) & pm) << (8 * v);
+      }
+      KccT kss = WEIGHTED ? (KccT)(Q.lw[0] * __popcll(clsw)) : (KccT)__popcll(clsw);
+
+      // ---- levels 1..h
+      const int h = Q.h, fs = Q.first_stable;
+#pragma unroll 1
+      for (int l = 1; l <= h; ++l) {
+        const bool stable = fs != 0 && l >= fs;
+        // what every node contributes to its predecessors
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+          if ((pm >> v) & 1u) {
+            const uint32_t c = (uint32_t)(clsw >> (8 * v)) & 0xFFu;
+            const uint32_t low = c & (0u - c);
+            const uint32_t sq = low * low;
+            uint4 e = make_uint4(0u, 0u, 0u, sq * sq);        // one count in the 4-bit field of the class representative
+            if (!stable && ((im >> v) & 1u)) {
+              const uint4 hsh = __ldg(Q.id_hash[l] + dense[v]);
+              e.x = hsh.x; e.y = hsh.y; e.z = hsh.z;
+            }
+            ent[v][tid] = e;
+          }
+        }
+        uint32_t sig[8];
+        uint32_t im_new = 0;
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+          sig[v] = 0u;
+          if ((em >> v) & 1u) {
+            const uint32_t sv = (uint32_t)(succw >> (8 * v)) & 0xFFu;
+            uint64_t sum_a = 0;
+            uint32_t sum_b = 0, sg = 0, m = sv;
+            while (m) {
+              const int j = __ffs(m) - 1;
+              m &= m - 1u;
+              const uint4 e = ent[j][tid];
+              sum_a += ((uint64_t)e.y << 32) | e.x;
+              sum_b += e.z;
+              sg += e.w;
+            }
+            sig[v] = sg;
+            // a credential can only be in the training dictionary if all its ids are
+            const bool cand = ((im >> v) & 1u) && (sv & ~im) == 0u;
+            if (cand) {
+              bool seen = false;
+              uint32_t dn = 0u;
+              if (!stable) {
+                const uint4 own = ent[v][tid];
+                LevelSalt salt;
+                salt.a_own = Q.a_own[l];
+                salt.b_own = Q.b_own[l];
+                const uint64_t key = nbw_key_from(((uint64_t)own.y << 32) | own.x, sum_a, salt);
+                const uint32_t chk = nbw_chk_from(own.z, sum_b, salt);
+                const uint32_t tag = (uint32_t)key, khi = (uint32_t)(key >> 32);
+                const uint32_t b = khi & Q.bucket_mask[l];
+                const uint4 t4 = __ldg(Q.tags[l] + b);
+                const int idx = t4.x == tag ? 0 : t4.y == tag ? 1 : t4.z == tag ? 2 : t4.w == tag ? 3 : -1;
+                if (idx >= 0) {
+                  const uint4 en = __ldg(Q.entries[l] + 4 * (size_t)b + idx);
+                  if (en.x == khi && en.y == chk) { seen = true; dn = en.z; }
+                }
+              } else {
+                seen = true;
+                dn = (uint32_t)__ldg(Q.child + Q.loff[l - 1] + (int)dense[v]);
+              }
+              if (seen) {
+                im_new |= 1u << v;
+                dense[v] = dn;
+                dp[v] = Q.label_base + Q.loff[l] + (int)dn;
+              }
+            }
+          }
+        }
+        // classes refine exactly: same previous class, both relabelled, same successor-class multiset
+        uint64_t cls_new = 0;
+        {
+          // only cells that still have a class of two or more nodes need the pairwise comparison
+          const uint32_t lo = (uint32_t)clsw, hi = (uint32_t)(clsw >> 32);
+          const bool multi = ((lo & __vsubus4(lo, 0x01010101u)) | (hi & __vsubus4(hi, 0x01010101u))) != 0u;
+          if (multi) {
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+              if ((em >> v) & 1u) {
+                const uint32_t c = (uint32_t)(clsw >> (8 * v)) & em;
+                uint32_t nc = 1u << v;
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                  if (u != v) nc |= (((c >> u) & 1u) && sig[u] == sig[v]) ? (1u << u) : 0u;
+                cls_new |= (uint64_t)nc << (8 * v);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int v = 0; v < 8; ++v) cls_new |= ((em >> v) & 1u) ? (1ull << (9 * v)) : 0ull;
+          }
+        }
+        const bool changed = cls_new != clsw || im_new != im;
+        clsw = cls_new;
+        im = im_new;
+        const int cnt = __popcll(clsw);
+        kss += WEIGHTED ? (KccT)(Q.lw[l] * cnt) : (KccT)cnt;
+        if (stable && l < h && !changed) {
+          // this cell reproduced (classes, membership) at a stable level: every deeper level will too; only the
+          // labels move down the child chain (nbw_model.final_label)
+          kss += WEIGHTED ? (KccT)(Q.wsuf[l] * cnt) : (KccT)((h - l) * cnt);
+#pragma unroll
+          for (int v = 0; v < 8; ++v)
+            if ((im >> v) & 1u) dp[v] = __ldg(Q.final_label + Q.loff[l] + (int)dense[v]);
+          break;
+        }
+      }
+      kacc += kss;
+    }
+
+    // ---------------------------------------------------------------- posterior (prefix form), all in registers
+    double mu_acc = 0.0, q_acc = 0.0;
+#pragma unroll
+    for (int p = 0; p < NP; ++p)
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int du = deep[p][u];
+        if (du != zero_slot) {
+          mu_acc += __ldg(P.w_mu + du);
+          const double* __restrict__ hrow = H + (int64_t)du * ldh;
+#pragma unroll
+          for (int p2 = p; p2 < NP; ++p2)
+#pragma unroll
+            for (int v = (p2 == p ? u : 0); v < 8; ++v) {
+              const int dv = deep[p2][v];
+              if (dv != zero_slot) {
+                const double gv = __ldg(hrow + dv);
+                q_acc += (p2 == p && v == u) ? gv : 2.0 * gv;
+              }
+            }
+        }
+      }
+    double mu, var;
+    const double sc = finish_score(P, mu_acc, q_acc, (double)kacc, mu, var);
+    const float scf = (float)sc;
+    if (scores) scores[g] = scf;
+    if (mu64) mu64[g] = mu;
+    if (var64) var64[g] = var;
+    if (score64) score64[g] = sc;
+    if constexpr (TOPK) if (scf == scf) {
+      const int gl = (int)g;
+      bool skip = false;
+      if (distinct) {
+#pragma unroll
+        for (int j = 0; j < kTopMax; ++j) {
+          const int tj = sh_ti[j][tid];
+          if (tj >= 0 && sh_tv[j][tid] == scf) { sh_ti[j][tid] = gl < tj ? gl : tj; skip = true; }
+        }
+      }
+      if (!skip && cand_better(scf, gl, sh_tv[k_top - 1][tid], sh_ti[k_top - 1][tid])) {
+        float cv = scf;
+        int ci = gl;
+#pragma unroll
+        for (int j = 0; j < kTopMax; ++j) {
+          if (j < k_top && ci >= 0) {
+            const float ov = sh_tv[j][tid];
+            const int oi = sh_ti[j][tid];
+            if (cand_better(cv, ci, ov, oi)) {
+              sh_tv[j][tid] = cv; sh_ti[j][tid] = ci;
+              cv = ov; ci = oi;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  if constexpr (TOPK) {
+    // CTA tournament over the threads' lists (see score_packed_kernel)
+    __shared__ float sv[kCellThreads / 32];
+    __shared__ int si[kCellThreads / 32];
+    __shared__ float best_v_s;
+    __shared__ int best_i_s;
+    const int lane = tid & 31, warp = tid >> 5;
+    float last_v = 0.f;
+    int last_i = -1;
+    for (int round = 0; round < k_top; ++round) {
+      float bv = 0.f;
+      int bi = -1;
+#pragma unroll
+      for (int j = 0; j < kTopMax; ++j) {
+        const float tvj = sh_tv[j][tid];
+        const int tij = sh_ti[j][tid];
+        bool eligible = j < k_top && tij >= 0;
+        if (eligible && last_i >= 0)
+          eligible = distinct ? (tvj < last_v) : (tvj < last_v || (tvj == last_v && tij > last_i));
+        if (eligible && cand_better(tvj, tij, bv, bi)) { bv = tvj; bi = tij; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(FULL, bv, o);
+        const int oi = __shfl_xor_sync(FULL, bi, o);
+        if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+      }
+      if (lane == 0) { sv[warp] = bv; si[warp] = bi; }
+      __syncthreads();
+      if (warp == 0) {
+        bv = lane < kCellThreads / 32 ? sv[lane] : 0.f;
+        bi = lane < kCellThreads / 32 ? si[lane] : -1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(FULL, bv, o);
+          const int oi = __shfl_xor_sync(FULL, bi, o);
+          if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) {
+          best_v_s = bv;
+          best_i_s = bi;
+          NbwCand c;
+          c.v = bv;
+          c.pad = 0;
+          c.idx = bi >= 0 ? index_base + bi : -1;
+          block_cands[(int64_t)blockIdx.x * k_top + round] = c;
+        }
+      }
+      __syncthreads();
+      last_v = best_v_s;
+      last_i = best_i_s;
+      __syncthreads();
+      if (last_i < 0) {
+        for (int r = round + 1 + tid; r < k_top; r += kCellThreads) {
+          NbwCand c;
+          c.v = 0.f;
+          c.pad = 0;
+          c.idx = -1;
+          block_cands[(int64_t)blockIdx.x * k_top + r] = c;
+        }
+        break;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ dictionary forms of the packed path
 __global__ void id_hash_kernel(const uint64_t* __restrict__ uniq_prev, int64_t n_ids, LevelSalt salt,
                                uint4* __restrict__ out) {
@@ -664,6 +995,66 @@ int launch_variant(nbw_ctx* ctx, int variant, const PackedParams& P, const uint8
   return NBW_OK;
 }
 
+template <int NP, bool WEIGHTED, bool TOPK>
+int launch_cell_variant(nbw_ctx* ctx, int variant, const PackedParams& P, const uint8_t* cells, int64_t n, float* scores,
+                        double* mu64, double* var64, double* score64, int k, int distinct, int64_t index_base,
+                        NbwCand* out_cands, cudaStream_t st) {
+  auto kern = score_cell_kernel<NP, WEIGHTED, TOPK>;
+  if (!ctx->packed_occ[variant]) {
+    int occ = 0;
+    NBW_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kCellThreads, 0));
+    NBW_REQUIRE(ctx, occ >= 1, "score_cell_kernel does not fit this device");
+    ctx->packed_occ[variant] = occ;
+  }
+  int64_t grid = (int64_t)ctx->sm_count * ctx->packed_occ[variant];
+  const int64_t need = (n + kCellThreads - 1) / kCellThreads;
+  if (need < grid) grid = need;
+  if (grid < 1) grid = 1;
+  NbwCand* blocks = nullptr;
+  if (TOPK) {
+    const size_t slot_bytes = sizeof(NbwCand) * (size_t)ctx->sm_count * 32 * kTopMax;
+    const size_t bytes = 2 * slot_bytes;
+    if (ctx->topk_blocks_bytes < bytes) {
+      if (ctx->topk_blocks) {
+        NBW_CUDA(ctx, cudaStreamSynchronize(st));
+        NBW_CUDA(ctx, cudaFree(ctx->topk_blocks));
+        ctx->topk_blocks = nullptr;
+        ctx->topk_blocks_bytes = 0;
+      }
+      NBW_CUDA(ctx, cudaMalloc(&ctx->topk_blocks, bytes));
+      ctx->topk_blocks_bytes = bytes;
+    }
+    ctx->topk_slot ^= 1;
+    blocks = reinterpret_cast<NbwCand*>(static_cast<char*>(ctx->topk_blocks) + (size_t)ctx->topk_slot * slot_bytes);
+    NBW_REQUIRE(ctx, (size_t)grid * kTopMax * sizeof(NbwCand) <= slot_bytes, "too many CTAs for the top-n block lists");
+  }
+  if (ctx->prof_ev[0]) NBW_CUDA(ctx, cudaEventRecord(ctx->prof_ev[0], st));
+  kern<<<(unsigned)grid, kCellThreads, 0, st>>>(P, cells, n, scores, mu64, var64, score64, blocks, k, distinct, index_base);
+  NBW_CHECK_LAUNCH(ctx);
+  if (ctx->prof_ev[1]) NBW_CUDA(ctx, cudaEventRecord(ctx->prof_ev[1], st));
+  if (TOPK) {
+    NbwCand* res = nullptr;
+    int rc = nbw_topk_merge_enqueue(ctx, blocks, grid * k, k, distinct, &res, st, out_cands);
+    if (rc) return rc;
+    if (res != out_cands) NBW_CUDA(ctx, cudaMemcpyAsync(out_cands, res, sizeof(NbwCand) * k, cudaMemcpyDeviceToDevice, st));
+  }
+  return NBW_OK;
+}
+
+template <bool TOPK>
+int launch_cell_parts(nbw_ctx* ctx, int np, bool weighted, const PackedParams& P, const uint8_t* cells, int64_t n,
+                      float* scores, double* mu64, double* var64, double* score64, int k, int distinct, int64_t index_base,
+                      NbwCand* out_cands, cudaStream_t st) {
+  const int base = 20 + (TOPK ? 4 : 0);
+#define NBW_ARGS P, cells, n, scores, mu64, var64, score64, k, distinct, index_base, out_cands, st
+  if (np == 1 && !weighted) return launch_cell_variant<1, false, TOPK>(ctx, base + 0, NBW_ARGS);
+  if (np == 1) return launch_cell_variant<1, true, TOPK>(ctx, base + 1, NBW_ARGS);
+  if (np == 2) return launch_cell_variant<2, true, TOPK>(ctx, base + 2, NBW_ARGS);
+  if (np == 3) return launch_cell_variant<3, true, TOPK>(ctx, base + 3, NBW_ARGS);
+#undef NBW_ARGS
+  return -1;     // four parts: the lane-per-node kernel
+}
+
 template <int NMAX, bool TOPK>
 int launch_parts(nbw_ctx* ctx, int np, bool weighted, const PackedParams& P, const uint8_t* cells, int64_t n,
                  float* scores, double* mu64, double* var64, double* score64, int k, int distinct, int64_t index_base,
@@ -725,8 +1116,16 @@ int nbw_score_packed(nbw_ctx* ctx, const nbw_model* M, const void* cells, int64_
   P.incumbent = M->incumbent; P.xi = M->xi; P.beta = M->beta;
   const uint8_t* c = static_cast<const uint8_t*>(cells);
   NbwCand* oc = static_cast<NbwCand*>(out_cands);
+  if (k > 0) NBW_REQUIRE(ctx, k <= kTopMax, "fused top-n handles k <= %d", kTopMax);
+  if (n_max == 8 && np <= 3 && !getenv("NBW_SCORE_LANES")) {
+    // 8-node records: one thread per cell (NBW_SCORE_LANES=1 keeps the lane-per-node kernel for comparison)
+    const int rc = k > 0 ? launch_cell_parts<true>(ctx, np, weighted, P, c, n_cells, scores, mu64, var64, score64, k, distinct,
+                                                   index_base, oc, st)
+                         : launch_cell_parts<false>(ctx, np, weighted, P, c, n_cells, scores, mu64, var64, score64, 0, 0, 0,
+                                                    nullptr, st);
+    if (rc >= 0) return rc;
+  }
   if (k > 0) {
-    NBW_REQUIRE(ctx, k <= kTopMax && n_cells < ((int64_t)1 << 31), "fused top-n handles k <= %d and < 2^31 cells per launch", kTopMax);
     if (n_max == 8) return launch_parts<8, true>(ctx, np, weighted, P, c, n_cells, scores, mu64, var64, score64, k, distinct, index_base, oc, st);
     return launch_parts<16, true>(ctx, np, weighted, P, c, n_cells, scores, mu64, var64, score64, k, distinct, index_base, oc, st);
   }

@@ -52,6 +52,19 @@ def test_packed_kernel_matches_first_generation_and_oracle(eng, fam, h):
     assert eng.fused_topk_ok(acq._model(), 5)
     s, mu, var, s64 = [t.clone() for t in acq.score_pool(pool, want64=True)]
     s_l, mu_l, var_l, s64_l = _legacy(lambda: [t.clone() for t in acq.score_pool(pool, want64=True)])
+    if train.n_max == 8:
+        # 8-node records are scored one THREAD per cell; the lane-per-node kernel must give the same numbers
+        os.environ["NBW_SCORE_LANES"] = "1"
+        try:
+            s_n, mu_n, var_n, s64_n = [t.clone() for t in acq.score_pool(pool, want64=True)]
+            _, _, idx_n = acq.propose_location(pool, top_n=5)
+        finally:
+            os.environ.pop("NBW_SCORE_LANES", None)
+        np.testing.assert_allclose(mu.cpu().numpy(), mu_n.cpu().numpy(), rtol=1e-11, atol=1e-13)
+        np.testing.assert_allclose(var.cpu().numpy(), var_n.cpu().numpy(), rtol=1e-9, atol=1e-14)
+        _, _, idx_c = acq.propose_location(pool, top_n=5)
+        if torch.equal(s, s_n):
+            assert np.array_equal(np.sort(idx_c), np.sort(idx_n))
     # two evaluation orders of the same sums of fp64 terms
     np.testing.assert_allclose(mu.cpu().numpy(), mu_l.cpu().numpy(), rtol=1e-11, atol=1e-13)
     np.testing.assert_allclose(var.cpu().numpy(), var_l.cpu().numpy(), rtol=1e-9, atol=1e-14)
