@@ -324,7 +324,14 @@ typedef struct {
   uint32_t bucket_mask[NBW_MAX_LEVELS];  /* n_buckets - 1 (power of two) */
   const int32_t* final_label;
   double level_weight[NBW_MAX_LEVELS];
-  int32_t weighted, undirected, rec_offset, rec_stride, label_base, reserved1;
+  int32_t weighted, undirected, rec_offset, rec_stride, label_base;
+  /* compact != 0 (n_max = 8 only): the part's record is the 8-byte WIRE form of a cell — half the PCIe bytes of a
+   * pool that arrives in host memory.  Little-endian u64: bits [3v, 3v+3) = palette index of node v's op code
+   * (7 = no node), bits [24, 52) = the strict upper triangle of the adjacency, row by row (edge u -> v, u < v,
+   * at bit 24 + u (15 - u) / 2 + (v - u - 1)): cells whose nodes are numbered topologically, at most 7 distinct
+   * ops.  palette[c] = the op code (level-0 key) of index c.  The kernel expands it in its prologue. */
+  int32_t compact;
+  uint8_t palette[8];
   const void* next;                      /* const nbw_model* of the next part (host memory) */
 } nbw_model;
 
@@ -432,7 +439,8 @@ int nbw_cands_read(nbw_ctx* ctx, const void* cands, int k, float* top_val_h, int
                    int* n_found_h, void* stream);
 
 /* propose_location (bayesopt/acquisitions.py:94-113) on a pool in HOST memory in one call: the staged
- * (mapped == 0, nbw_score_pool_host) or mapped (nbw_score_pool_mapped) pipeline with the local top-n of
+ * (mapped == 0, nbw_score_pool_host) or mapped (mapped == 1: nbw_score_pool_mapped; mapped == 2: the kernel also
+ * writes the scores through the mapped alias of a pinned scores_h, no D2H copy, scores_dev untouched) pipeline with the local top-n of
  * every piece fused into its scoring kernel and merged on the device: out_cands as for
  * nbw_score_pool_topk.  k <= 8, packed path only.  Enqueues only; same host-score semantics. */
 int nbw_propose_host(nbw_ctx* ctx, const nbw_model* model_h, const void* cells_h, int64_t n_cells,

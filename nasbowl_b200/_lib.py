@@ -63,7 +63,8 @@ class Model(C.Structure):
         ("final_label", C.c_void_p),
         ("level_weight", C.c_double * NBW_MAX_LEVELS),
         ("weighted", C.c_int32), ("undirected", C.c_int32), ("rec_offset", C.c_int32),
-        ("rec_stride", C.c_int32), ("label_base", C.c_int32), ("reserved1", C.c_int32),
+        ("rec_stride", C.c_int32), ("label_base", C.c_int32), ("compact", C.c_int32),
+        ("palette", C.c_uint8 * 8),
         ("next", C.c_void_p),
     ]
 

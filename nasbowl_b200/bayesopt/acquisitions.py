@@ -13,7 +13,7 @@ from abc import ABC
 import numpy as np
 import torch
 
-from ..cells import CellBatch, CellSlots
+from ..cells import CellBatch, CellSlots, CompactRecords
 
 
 class BaseAcquisition(ABC):
@@ -49,12 +49,12 @@ class GraphExpectedImprovement(BaseAcquisition):
         self.strict = strict
 
     # -- model configuration ------------------------------------------------------------
-    def _model(self):
+    def _model(self, palettes=None):
         if self.in_fill == 'max':                      # never true (assert above): SURVEY Q13
             inc = float(torch.max(self.gp.y_))
         else:
             inc = None                                 # posterior-mean incumbent (acquisitions.py:89-92)
-        return self.gp.pool_model("AEI" if self.augmented_ei else "EI", xi=self.xi, incumbent=inc)
+        return self.gp.pool_model("AEI" if self.augmented_ei else "EI", xi=self.xi, incumbent=inc, palettes=palettes)
 
     def _get_incumbent(self):
         if self.in_fill == 'max':
@@ -88,7 +88,12 @@ class GraphExpectedImprovement(BaseAcquisition):
         sums of kernels, oa kernels on the general path or top_n > 8 fall back to score + tournament."""
         self.iters += 1
         self.gp._require_fit()
-        model = self._model()
+        if isinstance(candidates, CompactRecords):
+            # 8-byte wire records (cells.CompactRecords): half the PCIe bytes of a pool that lives in host memory
+            model = self._model(palettes=candidates.palettes)
+            candidates = candidates.data
+        else:
+            model = self._model()
         eng = self.gp._dev['eng']
         eng.lib.nbw_range_push(b"propose_location")
         try:
@@ -97,16 +102,19 @@ class GraphExpectedImprovement(BaseAcquisition):
             eng.lib.nbw_range_pop()
 
     def _host_policy(self, model, candidates):
-        """(mapped, pieces) for a pool of packed records in host memory.  The packed kernel is faster than the
-        PCIe transfer of its records on every workload measured (profiles/r02_e2e_probe_*.txt), so the pool goes
-        through the staged H2D / kernel / D2H pipeline in pieces of ~12 MB (2 pieces for 1M 16-byte records:
-        0.63 ms; 8-16 for 192 MB of DARTS pairs: 4.6 ms, against 16-22 ms when the kernel reads mapped host
-        memory itself).  Only pinned oa pools on the general path at h >= 5 — a kernel slower than the
-        transfer — still take the mapped form (profiles/r01_e2e_probe.txt: 0.57 vs 0.61 ms)."""
+        """(mapped, pieces) for a pool of packed records in host memory (profiles/r02_e2e_probe*.txt, per 1M
+        candidates).  8-node records are scored one thread per cell with one coalesced vector load per record,
+        which PCIe serves at full rate: a PINNED pool is read by the kernel itself, and the scores go back through
+        the mapped alias of the pinned result block — no staging copy, no D2H copy (8-byte wire records:
+        0.41 ms against 0.56 staged; 2M NB101 cells: 0.49 against 0.68).  Everything else (16-node records, whose
+        lane-per-node kernel reads bytes; pageable pools) takes the staged H2D / kernel / D2H pipeline in pieces
+        of ~12 MB (192 MB of DARTS pairs: 4.6 ms staged, 16-22 ms mapped)."""
+        if model.n_max == 8 and not model.oa and candidates.is_pinned():
+            return 2, 1
         if model.oa and model.n_max == 8 and model.h >= 5 and candidates.is_pinned():
-            return True, 1
+            return 1, 1
         nbytes = candidates.shape[0] * candidates.shape[1]
-        return False, int(min(16, max(2, -(-nbytes // (12 << 20)))))
+        return 0, int(min(16, max(2, -(-nbytes // (12 << 20)))))
 
     def _propose(self, eng, model, candidates, top_n, return_distinct):
         host_scores = scores = None
@@ -119,7 +127,7 @@ class GraphExpectedImprovement(BaseAcquisition):
                 scores = eng._host_state["scores"]
                 vals, indices = eng.cands_read(cands, top_n)                             # syncs
             else:
-                scores, host_scores = eng.score_host_pool(model, candidates, chunks=pieces, mapped=mapped)
+                scores, host_scores = eng.score_host_pool(model, candidates, chunks=pieces, mapped=bool(mapped))
                 vals, indices = eng.topk(scores, top_n, distinct=distinct)              # syncs
         else:
             cells, M = self.gp.upload_pool(candidates)
@@ -132,6 +140,9 @@ class GraphExpectedImprovement(BaseAcquisition):
                 vals, indices = eng.topk(scores, top_n, distinct=distinct)              # syncs
         if return_distinct and len(indices) < top_n:
             # fewer than top_n distinct values: the reference falls back to plain top-k (:106-108)
+            if host_scores is not None:
+                eng.wait_host_scores()
+                scores = host_scores.to(eng.device)       # (write-through pools leave no device copy)
             vals, indices = eng.topk(scores, top_n, distinct=False)
         if host_scores is not None:
             eis = host_scores.numpy().reshape(-1, 1)       # view of a pinned block owned by this result
@@ -152,7 +163,7 @@ class GraphUpperConfidentBound(GraphExpectedImprovement):
         super().__init__(surrogate_model, strict=strict)
         self.beta = beta
 
-    def _model(self):
+    def _model(self, palettes=None):
         if self.beta is None:                          # acquisitions.py:133-135
             self.beta = 3. * torch.sqrt(0.5 * torch.log(torch.tensor(2. * self.iters + 1.)))
-        return self.gp.pool_model("UCB", beta=float(self.beta))
+        return self.gp.pool_model("UCB", beta=float(self.beta), palettes=palettes)

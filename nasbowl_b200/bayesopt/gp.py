@@ -727,9 +727,9 @@ class GraphGP:
         self._dev = dict(eng=Engine.get(), n_max=pm.n_max, n_slots=pm.n_slots, score=pm)
         self.likelihood = pm.lik
 
-    def pool_model(self, acq="MEAN", xi=0.0, beta=0.0, incumbent=None):
+    def pool_model(self, acq="MEAN", xi=0.0, beta=0.0, incumbent=None, palettes=None):
         """nbw_model descriptor of the fitted surrogate configured for one acquisition."""
-        return self._score_state().descriptor(acq, xi=xi, beta=beta, incumbent=incumbent)
+        return self._score_state().descriptor(acq, xi=xi, beta=beta, incumbent=incumbent, palettes=palettes)
 
     def upload_pool(self, X):
         """list[nx.DiGraph] | CellBatch | device records -> (device records, n_cells)."""

@@ -126,6 +126,42 @@ class CellBatch:
         return CellBatch(n_max, np.concatenate([b.labels for b in batches]),
                          np.concatenate([b.succ for b in batches]))
 
+    def to_compact(self, palette: Optional[np.ndarray] = None):
+        """(records uint8 [N, 8], palette uint8 [8]): the 8-byte wire form (nbw_model.compact).  Needs 8-node
+        records, at most seven distinct op codes and topologically numbered nodes (every edge u -> v has u < v);
+        raises ValueError otherwise (such pools travel as full records)."""
+        if self.n_max != 8:
+            raise ValueError("compact records hold 8-node cells")
+        present = self.labels != NO_NODE
+        if palette is None:
+            codes = np.unique(self.labels[present])
+            if len(codes) > 7:
+                raise ValueError("compact records hold at most 7 distinct op codes (got %d)" % len(codes))
+            palette = np.zeros(8, dtype=np.uint8)
+            palette[:len(codes)] = codes
+            n_codes = len(codes)
+        else:
+            palette = np.asarray(palette, dtype=np.uint8)
+            n_codes = 7
+        lut = np.full(256, 255, dtype=np.int64)
+        lut[palette[:n_codes]] = np.arange(n_codes)
+        idx = np.where(present, lut[self.labels], 7)
+        if (idx == 255).any():
+            raise ValueError("an op code is not in the palette")
+        w = np.zeros(len(self), dtype=np.uint64)
+        for v in range(8):
+            w |= idx[:, v].astype(np.uint64) << np.uint64(3 * v)
+        s = self.succ.astype(np.uint64)
+        for u in range(8):
+            if (s[:, u] & np.uint64((1 << (u + 1)) - 1)).any():
+                raise ValueError("compact records need topologically numbered nodes (an edge u -> v with v <= u)")
+        off = 24
+        for u in range(7):
+            field = (s[:, u] >> np.uint64(u + 1)) & np.uint64((1 << (7 - u)) - 1)
+            w |= field << np.uint64(off)
+            off += 7 - u
+        return w.view(np.uint8).reshape(len(self), 8).copy(), palette
+
     def widen(self, n_max: int) -> "CellBatch":
         if n_max == self.n_max:
             return self
@@ -161,6 +197,22 @@ class CellBatch:
                         g.add_edge(v, j)
             out.append(g)
         return out
+
+
+class CompactRecords:
+    """A pool in the 8-byte WIRE form of nbw_model.compact: `data` uint8 [N, 8 * n_slots] (host tensor, pin it for
+    full PCIe speed), `palettes[s][c]` = op code of palette index c in slot s.  Half the bytes of the 16-byte
+    records — what matters when a pool arrives from host memory.  Built by CellBatch.to_compact()."""
+
+    def __init__(self, data, palettes):
+        self.data, self.palettes = data, [np.asarray(p, dtype=np.uint8) for p in palettes]
+
+    def __len__(self):
+        return self.data.shape[0]
+
+    @property
+    def n_slots(self) -> int:
+        return len(self.palettes)
 
 
 class CellSlots:

@@ -43,7 +43,8 @@ struct PartParams {
   double wsuf[NBW_MAX_LEVELS];      // sum of lw over the levels deeper than l
   const int32_t* child;
   const int32_t* final_label;
-  int32_t h, first_stable, undirected, rec_offset, label_base, pad;
+  int32_t h, first_stable, undirected, rec_offset, label_base, compact;
+  uint8_t palette[8];
 };
 
 struct PackedParams {
@@ -589,11 +590,34 @@ score_cell_kernel(const __grid_constant__ PackedParams P, const uint8_t* __restr
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
       const PartParams& Q = P.part[p];
-      const uint4 rec = __ldg(reinterpret_cast<const uint4*>(cells + g * stride + Q.rec_offset));
-      const uint64_t labw = ((uint64_t)rec.y << 32) | rec.x;
-      const uint32_t pm = present_bits4(rec.x) | (present_bits4(rec.y) << 4);       // present nodes
+      uint64_t labw, succw;
+      if (Q.compact) {
+        // 8-byte wire record (nbw_model.compact): 3-bit palette indices + the strict upper triangle of the adjacency
+        const uint2 r = __ldg(reinterpret_cast<const uint2*>(cells + g * stride + Q.rec_offset));
+        const uint64_t w = ((uint64_t)r.y << 32) | r.x;
+        uint64_t pal = 0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) pal |= (uint64_t)(c == 7 ? 0xFFu : Q.palette[c]) << (8 * c);
+        labw = 0;
+        succw = 0;
+        uint32_t tri = (uint32_t)(w >> 24);
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+          const uint32_t c = (uint32_t)(w >> (3 * v)) & 7u;
+          labw |= ((pal >> (8 * c)) & 0xFFull) << (8 * v);
+          if (v < 7) {
+            const uint32_t row = (tri & ((1u << (7 - v)) - 1u)) << (v + 1);
+            succw |= (uint64_t)row << (8 * v);
+            tri >>= (7 - v);
+          }
+        }
+      } else {
+        const uint4 rec = __ldg(reinterpret_cast<const uint4*>(cells + g * stride + Q.rec_offset));
+        labw = ((uint64_t)rec.y << 32) | rec.x;
+        succw = ((uint64_t)rec.w << 32) | rec.z;
+      }
+      const uint32_t pm = present_bits4((uint32_t)labw) | (present_bits4((uint32_t)(labw >> 32)) << 4);   // present nodes
       // adjacency rows, restricted to present nodes on both ends
-      uint64_t succw = ((uint64_t)rec.w << 32) | rec.z;
       {
         uint64_t rowmask = 0;                       // byte v = 0xFF for present v
 #pragma unroll
@@ -917,6 +941,8 @@ int fill_part(nbw_ctx* ctx, const nbw_model* M, PartParams& Q) {
   Q.undirected = M->undirected;
   Q.rec_offset = M->rec_offset;
   Q.label_base = M->label_base;
+  Q.compact = M->compact;
+  memcpy(Q.palette, M->palette, 8);
   Q.child = M->child;
   Q.final_label = M->final_label;
   double suffix = 0.0;
@@ -1106,10 +1132,18 @@ int nbw_score_packed(nbw_ctx* ctx, const nbw_model* M, const void* cells, int64_
   P.zero_slot = M->n_labels;
   P.rec_stride = M->rec_stride > 0 ? M->rec_stride : rec;
   NBW_REQUIRE(ctx, P.ld_h >= (int64_t)P.zero_slot + 1, "model.ld_h must be >= n_labels + 1");
-  NBW_REQUIRE(ctx, P.rec_stride % 16 == 0, "rec_stride must be a multiple of 16 bytes");
-  for (int p = 0; p < np; ++p)
-    NBW_REQUIRE(ctx, P.part[p].rec_offset % 16 == 0 && P.part[p].rec_offset + rec <= P.rec_stride,
-                "part %d: rec_offset outside the candidate record", p);
+  NBW_REQUIRE(ctx, P.rec_stride % (M->compact ? 8 : 16) == 0, "rec_stride must be a multiple of the record size");
+  const bool compact = M->compact != 0;
+  for (int p = 0; p < np; ++p) {
+    NBW_REQUIRE(ctx, (P.part[p].compact != 0) == compact, "all parts of a sum must use the same record form");
+    if (compact)
+      NBW_REQUIRE(ctx, n_max == 8 && P.part[p].rec_offset % 8 == 0 && P.part[p].rec_offset + 8 <= P.rec_stride,
+                  "part %d: compact records are 8 bytes, 8-node cells only", p);
+    else
+      NBW_REQUIRE(ctx, P.part[p].rec_offset % 16 == 0 && P.part[p].rec_offset + rec <= P.rec_stride,
+                  "part %d: rec_offset outside the candidate record", p);
+  }
+  NBW_REQUIRE(ctx, !compact || np <= 3, "compact records are scored by the thread-per-cell kernel (sums of up to 3 kernels)");
   NBW_REQUIRE(ctx, M->acq >= NBW_ACQ_EI && M->acq <= NBW_ACQ_MEAN, "unknown acquisition");
   P.acq = M->acq;
   P.lik = M->lik; P.y_mean = M->y_mean; P.y_std = M->y_std;
@@ -1117,7 +1151,7 @@ int nbw_score_packed(nbw_ctx* ctx, const nbw_model* M, const void* cells, int64_
   const uint8_t* c = static_cast<const uint8_t*>(cells);
   NbwCand* oc = static_cast<NbwCand*>(out_cands);
   if (k > 0) NBW_REQUIRE(ctx, k <= kTopMax, "fused top-n handles k <= %d", kTopMax);
-  if (n_max == 8 && np <= 3 && !getenv("NBW_SCORE_LANES")) {
+  if (n_max == 8 && np <= 3 && (compact || !getenv("NBW_SCORE_LANES"))) {
     // 8-node records: one thread per cell (NBW_SCORE_LANES=1 keeps the lane-per-node kernel for comparison)
     const int rc = k > 0 ? launch_cell_parts<true>(ctx, np, weighted, P, c, n_cells, scores, mu64, var64, score64, k, distinct,
                                                    index_base, oc, st)

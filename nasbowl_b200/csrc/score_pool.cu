@@ -453,7 +453,7 @@ int check_model(nbw_ctx* ctx, const nbw_model* M, bool need_posterior) {
 
 // the first-generation kernel scores one kernel with unit level weights on plain records
 bool legacy_ok(const nbw_model* M) {
-  return M->next == nullptr && !M->weighted && !M->undirected && M->rec_offset == 0 &&
+  return M->next == nullptr && !M->weighted && !M->undirected && M->rec_offset == 0 && !M->compact &&
          (M->rec_stride == 0 || M->rec_stride == (M->n_max == 8 ? 16 : 48));
 }
 
@@ -584,7 +584,7 @@ int merge_pieces(nbw_ctx* ctx, NbwCand* lists, int pieces, int k, int distinct, 
 
 static int score_pool_mapped_impl(nbw_ctx* ctx, const nbw_model* model_h, const void* cells_h, int64_t n_cells,
                                   float* scores_h, float* scores_dev, int pieces, int k, int distinct,
-                                  int64_t index_base, void* out_cands, void* stream);
+                                  int64_t index_base, void* out_cands, void* stream, bool write_through = false);
 static int score_pool_host_impl(nbw_ctx* ctx, const nbw_model* model_h, const void* cells_h, int64_t n_cells,
                                 float* scores_h, float* scores_dev, int chunks, int k, int distinct,
                                 int64_t index_base, void* out_cands, void* stream);
@@ -611,7 +611,7 @@ extern "C" int nbw_propose_host(nbw_ctx* ctx, const nbw_model* model_h, const vo
     NBW_CUDA(ctx, cudaMemsetAsync(out_cands, 0xFF, sizeof(NbwCand) * k, static_cast<cudaStream_t>(stream)));
     return NBW_OK;
   }
-  if (mapped) return score_pool_mapped_impl(ctx, model_h, cells_h, n_cells, scores_h, scores_dev, pieces, k, distinct, index_base, out_cands, stream);
+  if (mapped) return score_pool_mapped_impl(ctx, model_h, cells_h, n_cells, scores_h, scores_dev, pieces, k, distinct, index_base, out_cands, stream, mapped == 2);
   return score_pool_host_impl(ctx, model_h, cells_h, n_cells, scores_h, scores_dev, pieces, k, distinct, index_base, out_cands, stream);
 }
 
@@ -620,7 +620,7 @@ extern "C" int nbw_propose_host(nbw_ctx* ctx, const nbw_model* model_h, const vo
 // one D2H copy of the [M] f32 vector: 0.74 ms vs 0.60 ms per 1M candidates.)
 static int score_pool_mapped_impl(nbw_ctx* ctx, const nbw_model* model_h, const void* cells_h, int64_t n_cells,
                                   float* scores_h, float* scores_dev, int pieces, int k, int distinct,
-                                  int64_t index_base, void* out_cands, void* stream) {
+                                  int64_t index_base, void* out_cands, void* stream, bool write_through) {
   int rc = check_model(ctx, model_h, true);
   if (rc) return rc;
   NBW_REQUIRE(ctx, n_cells >= 0 && pieces >= 1 && pieces <= 64, "bad n_cells / pieces");
@@ -642,18 +642,29 @@ static int score_pool_mapped_impl(nbw_ctx* ctx, const nbw_model* model_h, const 
     rc = piece_cands(ctx, &lists);
     if (rc) return rc;
   }
-  if (scores_h) {
+  // write_through: the kernel also stores its scores through the mapped alias of scores_h — no D2H copy behind the
+  // kernel (with the thread-per-cell kernel the stores are one coalesced 128-byte line per warp, which PCIe takes
+  // at full rate; the lane-per-node kernel of the first build scattered 4-byte stores and lost to the copy)
+  float* sink = scores_dev;
+  if (write_through) {
+    NBW_REQUIRE(ctx, scores_h != nullptr, "write-through needs scores_h");
+    cudaPointerAttributes oa;
+    NBW_CUDA(ctx, cudaPointerGetAttributes(&oa, scores_h));
+    NBW_REQUIRE(ctx, oa.type == cudaMemoryTypeHost && oa.devicePointer != nullptr, "write-through needs pinned scores_h");
+    sink = static_cast<float*>(oa.devicePointer);
+  }
+  if (scores_h && !write_through) {
     NBW_CUDA(ctx, cudaEventRecord(ctx->ev_done[0], st));
     NBW_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_done[0], 0));
   }
   for (int c = 0; c < pieces; ++c) {
     const int64_t lo = (int64_t)c * per, hi = (lo + per < n_cells) ? lo + per : n_cells;
     if (lo >= hi) break;
-    rc = score_dispatch(ctx, *model_h, src + lo * rec, hi - lo, scores_dev + lo, st, k, distinct, index_base + lo,
+    rc = score_dispatch(ctx, *model_h, src + lo * rec, hi - lo, sink + lo, st, k, distinct, index_base + lo,
                         lists ? lists + (size_t)c * k : nullptr);
     if (rc) return rc;
     ++used;
-    if (scores_h) {
+    if (scores_h && !write_through) {
       NBW_CUDA(ctx, cudaEventRecord(ctx->ev_done[c & 1], st));
       NBW_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_done[c & 1], 0));
       NBW_CUDA(ctx, cudaMemcpyAsync(scores_h + lo, scores_dev + lo, (size_t)(hi - lo) * sizeof(float),
@@ -664,7 +675,7 @@ static int score_pool_mapped_impl(nbw_ctx* ctx, const nbw_model* model_h, const 
     rc = merge_pieces(ctx, lists, used, k, distinct, out_cands, st);
     if (rc) return rc;
   }
-  return pipe_end(ctx, scores_h != nullptr);
+  return pipe_end(ctx, scores_h != nullptr && !write_through);
 }
 
 // Host-buffer form: the pool lives in host memory (pinned for full overlap).  Chunk i+1's H2D copy,

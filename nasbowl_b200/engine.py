@@ -602,7 +602,7 @@ class Engine:
         return st["scores"], host_scores
 
     def propose_host(self, model: "_lib.Model", host_cells: torch.Tensor, k: int, distinct: bool = True,
-                     index_base: int = 0, chunks: int = 8, mapped: bool = False, out: Optional[torch.Tensor] = None):
+                     index_base: int = 0, chunks: int = 8, mapped: int = 0, out: Optional[torch.Tensor] = None):
         """nbw_propose_host: score a HOST pool (staged or mapped pipeline) with the top-k fused into the
         scoring kernels.  Returns (device list uint8 [k * 16], host scores [M] f32 pinned); the host scores
         are complete after cands_read() / topk_merge() / wait_host_scores()."""

@@ -135,8 +135,14 @@ class PoolModel:
         return [self] + list(self.more)
 
     # ------------------------------------------------------------------ C descriptor
-    def _part_descriptor(self, rec: int) -> "_lib.Model":
+    def _part_descriptor(self, rec: int, palettes=None) -> "_lib.Model":
         d = _lib.Model()
+        if palettes is not None:
+            if self.n_max != 8:
+                raise ValueError("compact records hold 8-node cells")
+            d.compact = 1
+            for c in range(8):
+                d.palette[c] = int(palettes[self.slot][c])
         d.n_max, d.h, d.oa = self.n_max, self.h, int(self.oa)
         d.seed = self.seed & 0xFFFFFFFFFFFFFFFF
         d.level0_table = self.level0.data_ptr()
@@ -170,9 +176,10 @@ class PoolModel:
         return d
 
     def descriptor(self, acq: str = "MEAN", xi: float = 0.0, beta: float = 0.0,
-                   incumbent: Optional[float] = None) -> "_lib.Model":
-        rec = 16 if self.n_max == 8 else 48
-        d = self._part_descriptor(rec)
+                   incumbent: Optional[float] = None, palettes=None) -> "_lib.Model":
+        """palettes (one uint8[8] per record slot): the pool arrives as 8-byte compact records (nbw_model.compact)."""
+        rec = (16 if self.n_max == 8 else 48) if palettes is None else 8
+        d = self._part_descriptor(rec, palettes)
         d.acq = ACQ[acq]
         multi = len(self.more) > 0
         prefix = self.H is not None and self.use_prefix and not self.oa
@@ -196,7 +203,7 @@ class PoolModel:
         chain = []
         prev = d
         for part in self.more:
-            pd = part._part_descriptor(rec)
+            pd = part._part_descriptor(rec, palettes)
             chain.append(pd)
             prev.next = C.addressof(pd)
             prev = pd

@@ -477,3 +477,55 @@ def test_mutation_pool_has_no_isomorphic_members(eng):
     # allow_isomorphism=True: plain mutation batch
     pool3 = pools.mutation_pool(eng, parents, pool_size=40, seed=5, allow_isomorphism=True)
     assert torch.equal(pool3[:20], eng.mutate_cells(0, parents, 5, 0, 64)[:20])
+
+
+# ---------------------------------------------------------------------------- compact wire records
+def test_compact_wire_records_score_identically(eng):
+    """nbw_model.compact: 8-byte records (3-bit palette indices + the upper triangle of the adjacency) are expanded
+    in the kernel prologue: bitwise the same scores and selection as the 16-byte records, resident or from host
+    memory, one or two record slots."""
+    from nasbowl_b200.bayesopt import GraphExpectedImprovement
+    from nasbowl_b200.cells import CompactRecords
+    from nasbowl_b200.kernels import WeisfilerLehman
+    for fam in (0, 1):
+        train = synth.generate_cells_host(fam, 5, 0, 100)
+        y = np.random.RandomState(fam).randn(100)
+        gp = _gp(train, y, [WeisfilerLehman(h=3)])
+        gp.fit(wl_subtree_candidates=(3,), optimize_lik=False)
+        acq = GraphExpectedImprovement(gp)
+        M = 100_003
+        pool_dev = eng.generate_cells(fam, 7, 0, M)
+        batch = CellBatch.from_records(pool_dev.cpu().numpy(), 8)
+        rec, pal = batch.to_compact()
+        assert rec.shape == (M, 8)
+        full = acq.score_pool(pool_dev)[0].clone()
+        xs, eis, idx = acq.propose_location(pool_dev, top_n=5)
+        host = torch.from_numpy(rec).pin_memory()
+        xs_c, eis_c, idx_c = acq.propose_location(CompactRecords(host, [pal]), top_n=5)
+        np.testing.assert_array_equal(eis_c.reshape(-1), full.cpu().numpy())
+        assert np.array_equal(idx, idx_c)
+        xs_d, eis_d, idx_d = acq.propose_location(CompactRecords(host.cuda(), [pal]), top_n=5)      # resident compact pool
+        np.testing.assert_array_equal(eis_d.reshape(-1), full.cpu().numpy())
+        assert np.array_equal(idx, idx_d)
+    # two slots
+    a, b = synth.generate_cells_host(0, 11, 0, 2080), synth.generate_cells_host(1, 12, 0, 2080)
+    y = np.random.RandomState(4).randn(80)
+    gp = _gp(CellSlots([a[:80], b[:80]]), y, [WeisfilerLehman(h=2, slot=0), WeisfilerLehman(h=2, slot=1)], weights=[0.5, 0.5])
+    gp.fit(wl_subtree_candidates=(), optimize_lik=False)
+    acq = GraphExpectedImprovement(gp)
+    po = CellSlots([a[80:], b[80:]])
+    mu_f, var_f = gp.predict_diag(po)
+    ra, pa = a[80:].to_compact()
+    rb, pb = b[80:].to_compact()
+    host = torch.from_numpy(np.concatenate([ra, rb], axis=1)).pin_memory()
+    xs, eis_c, idx_c = acq.propose_location(CompactRecords(host, [pa, pb]), top_n=5)
+    xs, eis_f, idx_f = acq.propose_location(torch.from_numpy(po.to_records()).pin_memory(), top_n=5)
+    np.testing.assert_array_equal(eis_c, eis_f)
+    assert np.array_equal(idx_c, idx_f)
+    # what does not fit the wire form is refused on the host
+    with pytest.raises(ValueError):
+        synth.generate_cells_host(2, 1, 0, 10).to_compact()                 # 16-node records
+    bad = CellBatch(8, np.array([[0, 1, 255, 255, 255, 255, 255, 255]], dtype=np.uint8),
+                    np.array([[0, 1, 0, 0, 0, 0, 0, 0]], dtype=np.uint16))  # edge 1 -> 0
+    with pytest.raises(ValueError):
+        bad.to_compact()

@@ -44,7 +44,7 @@ def test_model_struct_layout_matches_header():
     text = open(os.path.join(ROOT, "include", "nbw.h")).read()
     body = text[text.index("typedef struct {"):text.index("} nbw_model;")]
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
-    names = re.findall(r"\b([a-zA-Z_][a-zA-Z0-9_]*)\s*(?:\[[A-Z_]+\])?\s*[;,]", body)
+    names = re.findall(r"\b([a-zA-Z_][a-zA-Z0-9_]*)\s*(?:\[[A-Z_0-9]+\])?\s*[;,]", body)
     names = [n for n in names if n not in ("NBW_MAX_LEVELS",)]
     assert names == [f[0] for f in _lib.Model._fields_]
     assert _lib.Model.G.offset % 8 == 0 and _lib.Model.H.offset % 8 == 0 and _lib.Model.lik.offset % 8 == 0
