@@ -307,9 +307,151 @@ __global__ void assign_ids_kernel(const uint64_t* __restrict__ sk, const uint32_
 
 }  // namespace
 
+// ---------------------------------------------------------------- hash pre-dedup for large key counts
+// A WL level of a large batch has millions of keys but few distinct ones (the 200k-cell stress: 16M keys, 5 ..
+// 23 493 labels per level).  Sorting all of them moves every key eight times; instead every key is looked up
+// in an open-addressing table that lives in L2 (2 MB), only the DISTINCT keys are sorted (for the same
+// deterministic, key-ordered ids), and one more sweep gives every node its id, verifies its credential against
+// the first node of its class and flags first occurrences.  ~30 B of traffic per key instead of ~290.
+namespace {
+constexpr int64_t kHashDistinctCap = 65536;            // more distinct keys than this: radix path
+constexpr int64_t kHashSlots = 4 * kHashDistinctCap;   // load factor <= 1/4
+constexpr uint32_t kOverflowBit = 2u;
+
+// A CTA keeps the slots of the keys it has met in a small insert-only shared-memory cache (with the smallest node
+// index it saw for each), so that the few hot labels of a level are looked up in the global table once per CTA
+// and not once per node; keys that lose the race for a cache entry take the global path.
+constexpr int kCtaCache = 2048;
+__global__ void __launch_bounds__(256)
+hash_insert_kernel(const uint64_t* __restrict__ keys, int64_t n, unsigned long long* __restrict__ tab,
+                   uint32_t* __restrict__ first, uint32_t* __restrict__ node_slot, uint64_t* __restrict__ dkeys,
+                   uint32_t* __restrict__ dslot, uint32_t* __restrict__ dcount, DictCounters* __restrict__ counters) {
+  __shared__ unsigned long long c_key[kCtaCache];
+  __shared__ uint32_t c_slot[kCtaCache];
+  __shared__ uint32_t c_min[kCtaCache];
+  constexpr uint32_t PENDING = 0xFFFFFFFFu;
+  for (int e = threadIdx.x; e < kCtaCache; e += blockDim.x) {
+    c_key[e] = (unsigned long long)NBW_INVALID_KEY;
+    c_slot[e] = PENDING;
+    c_min[e] = 0xFFFFFFFFu;
+  }
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const uint32_t mask = (uint32_t)(kHashSlots - 1);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint64_t key = keys[i];
+    if (key == NBW_INVALID_KEY) {
+      node_slot[i] = 0xFFFFFFFFu;
+      continue;
+    }
+    const uint64_t hk = nbw_mix_b(key);
+    const int e = (int)(hk >> 44) & (kCtaCache - 1);
+    unsigned long long ck = *(volatile unsigned long long*)(c_key + e);
+    bool owner = false;
+    if (ck == (unsigned long long)NBW_INVALID_KEY) {
+      ck = atomicCAS(c_key + e, (unsigned long long)NBW_INVALID_KEY, (unsigned long long)key);
+      owner = ck == (unsigned long long)NBW_INVALID_KEY;
+      if (owner) ck = key;
+    }
+    if (!owner && ck == (unsigned long long)key) {
+      const uint32_t s = *(volatile uint32_t*)(c_slot + e);
+      if (s != PENDING) {
+        node_slot[i] = s;
+        if ((uint32_t)i < *(volatile uint32_t*)(c_min + e)) atomicMin(c_min + e, (uint32_t)i);
+        continue;
+      }
+    }
+    uint32_t slot = (uint32_t)(hk >> 20) & mask;
+    bool placed = false;
+    for (int probe = 0; probe < 512; ++probe) {
+      unsigned long long cur = *(volatile unsigned long long*)(tab + slot);
+      if (cur == (unsigned long long)NBW_INVALID_KEY) {
+        cur = atomicCAS(tab + slot, (unsigned long long)NBW_INVALID_KEY, (unsigned long long)key);
+        if (cur == (unsigned long long)NBW_INVALID_KEY) {
+          const uint32_t pos = atomicAdd(dcount, 1u);
+          if (pos < (uint32_t)kHashDistinctCap) {
+            dkeys[pos] = key;
+            dslot[pos] = slot;
+          } else {
+            atomicOr(&counters->collision, kOverflowBit);
+          }
+          placed = true;
+          break;
+        }
+      }
+      if (cur == (unsigned long long)key) { placed = true; break; }
+      slot = (slot + 1u) & mask;
+    }
+    if (!placed) {
+      atomicOr(&counters->collision, kOverflowBit);
+      node_slot[i] = 0xFFFFFFFFu;
+      continue;
+    }
+    node_slot[i] = slot;
+    if (owner) {
+      atomicMin(c_min + e, (uint32_t)i);
+      __threadfence_block();
+      *(volatile uint32_t*)(c_slot + e) = slot;
+    } else if ((uint32_t)i < *(volatile uint32_t*)(first + slot)) {
+      atomicMin(first + slot, (uint32_t)i);
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < kCtaCache; e += blockDim.x) {
+    const uint32_t s = c_slot[e], m = c_min[e];
+    if (s != PENDING && m != 0xFFFFFFFFu && m < *(volatile uint32_t*)(first + s)) atomicMin(first + s, m);
+  }
+}
+
+// sorted distinct keys -> ids: slot_id[slot] = rank; the dictionary in key order
+__global__ void rank_slots_kernel(const uint64_t* __restrict__ skeys, const uint32_t* __restrict__ svals,
+                                  const uint32_t* __restrict__ dslot, const uint32_t* __restrict__ first,
+                                  const uint64_t* __restrict__ chks, uint32_t* __restrict__ slot_id,
+                                  uint64_t* __restrict__ uniq_keys, uint64_t* __restrict__ uniq_chks, int64_t cap,
+                                  int64_t n_distinct) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_distinct) return;
+  const uint64_t key = skeys[r];
+  if (key == NBW_INVALID_KEY) return;
+  const uint32_t slot = dslot[svals[r]];
+  slot_id[slot] = (uint32_t)r;
+  if (r < cap) {
+    uniq_keys[r] = key;
+    uniq_chks[r] = chks[first[slot]];
+  }
+}
+
+__global__ void assign_from_slots_kernel(const uint32_t* __restrict__ node_slot, const uint32_t* __restrict__ slot_id,
+                                         const uint32_t* __restrict__ first, const uint64_t* __restrict__ chks, int64_t n,
+                                         const uint8_t* __restrict__ cells, int n_max, const uint32_t* __restrict__ ids_prev,
+                                         uint32_t* __restrict__ ids, const uint32_t* __restrict__ dcount,
+                                         DictCounters* __restrict__ counters, uint8_t* __restrict__ first_flag) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    if (i == 0) counters->n_unique = *dcount;
+    const uint32_t slot = node_slot[i];
+    if (slot == 0xFFFFFFFFu) {
+      ids[i] = NBW_INVALID_ID;
+      if (first_flag) first_flag[i] = 0;
+      continue;
+    }
+    ids[i] = slot_id[slot];
+    const uint32_t rep = first[slot];
+    if (first_flag) first_flag[i] = rep == (uint32_t)i ? 1 : 0;
+    if (rep != (uint32_t)i) {
+      bool ok = chks[i] == chks[rep];
+      if (ok && cells != nullptr && ids_prev != nullptr)
+        ok = (n_max == 8) ? same_credential<8>(cells, ids_prev, rep, (uint32_t)i) : same_credential<16>(cells, ids_prev, rep, (uint32_t)i);
+      if (!ok) atomicOr(&counters->collision, 1u);
+    }
+  }
+}
+}  // namespace
+
 // Enqueue one dictionary build (no sync, no read-back): the counters land in *counters (device).  `work` is a
 // scratch region of nbw_dict_scratch_bytes(n_keys) bytes.
 size_t nbw_dict_scratch_bytes(int64_t n_keys) {
+  if (n_keys < kHashDistinctCap) n_keys = kHashDistinctCap;      // the distinct keys of the hash path are sorted here
   const int n_tiles = (int)((n_keys + kTile - 1) / kTile);
   const size_t n_counts = (size_t)256 * n_tiles;
   const size_t scan_tmp = scan_scratch_elems((int64_t)(n_counts > (size_t)n_keys ? n_counts : (size_t)n_keys));
@@ -319,13 +461,94 @@ size_t nbw_dict_scratch_bytes(int64_t n_keys) {
   need += Carver::pad(sizeof(uint32_t) * n_counts);
   need += Carver::pad(sizeof(uint32_t) * n_keys) * 2;   // flags, rank
   need += Carver::pad(sizeof(uint32_t) * scan_tmp);
+  // hash pre-dedup: table, first index and id per slot, slot per node, distinct keys / slots (+ their sort buffers
+  // are the radix buffers above, sized for at least kHashDistinctCap keys)
+  need += Carver::pad(sizeof(uint64_t) * kHashSlots) + 2 * Carver::pad(sizeof(uint32_t) * kHashSlots);
+  need += Carver::pad(sizeof(uint32_t) * n_keys);
+  need += Carver::pad(sizeof(uint64_t) * kHashDistinctCap) + Carver::pad(sizeof(uint32_t) * kHashDistinctCap) + 256;
   return need + 4096;
 }
 
 int nbw_dict_build_enqueue(nbw_ctx* ctx, const uint64_t* keys, const uint64_t* chks, int64_t n_keys, int key_bits,
                            const void* cells, int n_max, const uint32_t* ids_prev, uint32_t* ids, uint64_t* uniq_keys,
                            uint64_t* uniq_chks, int64_t uniq_cap, NbwDictCounters* counters, void* work, cudaStream_t st,
-                           uint8_t* first_flag) {
+                           uint8_t* first_flag, bool allow_hash) {
+  if (allow_hash && n_keys > kSmallSortMax && !getenv("NBW_DICT_RADIX") && !getenv("NBW_DICT_NOHASH")) {
+    // ---- hash pre-dedup (see above)
+    const int64_t size_n = n_keys > kHashDistinctCap ? n_keys : kHashDistinctCap;
+    const size_t n_counts_full = (size_t)256 * (int)((size_n + kTile - 1) / kTile);
+    const size_t scan_tmp_full = scan_scratch_elems((int64_t)(n_counts_full > (size_t)size_n ? n_counts_full : (size_t)size_n));
+    Carver cv(work);
+    uint64_t* kbuf[2] = {cv.take<uint64_t>(size_n), cv.take<uint64_t>(size_n)};
+    uint32_t* vbuf[2] = {cv.take<uint32_t>(size_n), cv.take<uint32_t>(size_n)};
+    uint32_t* counts = cv.take<uint32_t>(n_counts_full);
+    cv.take<uint32_t>(size_n);   // flags (radix path)
+    cv.take<uint32_t>(size_n);   // rank  (radix path)
+    uint32_t* stmp = cv.take<uint32_t>(scan_tmp_full);
+    unsigned long long* tab = cv.take<unsigned long long>(kHashSlots);
+    uint32_t* first = cv.take<uint32_t>(kHashSlots);
+    uint32_t* slot_id = cv.take<uint32_t>(kHashSlots);
+    uint32_t* node_slot = cv.take<uint32_t>(n_keys);
+    uint64_t* dkeys = cv.take<uint64_t>(kHashDistinctCap);
+    uint32_t* dslot = cv.take<uint32_t>(kHashDistinctCap);
+    uint32_t* dcount = cv.take<uint32_t>(1);
+    NBW_CUDA(ctx, cudaMemsetAsync(counters, 0, sizeof(DictCounters), st));
+    NBW_CUDA(ctx, cudaMemsetAsync(tab, 0xFF, sizeof(uint64_t) * kHashSlots, st));
+    NBW_CUDA(ctx, cudaMemsetAsync(first, 0xFF, sizeof(uint32_t) * kHashSlots, st));
+    NBW_CUDA(ctx, cudaMemsetAsync(dcount, 0, sizeof(uint32_t), st));
+    const int grid = nbw_grid_for(ctx, n_keys, 256);
+    hash_insert_kernel<<<grid, 256, 0, st>>>(keys, n_keys, tab, first, node_slot, dkeys, dslot, dcount, counters);
+    NBW_CHECK_LAUNCH(ctx);
+    // the number of distinct keys decides how they are sorted (one sync; this path only runs for large inputs)
+    uint32_t hd = 0;
+    DictCounters hc;
+    NBW_CUDA(ctx, cudaMemcpyAsync(&hd, dcount, sizeof(hd), cudaMemcpyDeviceToHost, st));
+    NBW_CUDA(ctx, cudaMemcpyAsync(&hc, counters, sizeof(hc), cudaMemcpyDeviceToHost, st));
+    NBW_CUDA(ctx, cudaStreamSynchronize(st));
+    if (!(hc.collision & kOverflowBit) && hd <= (uint32_t)kHashDistinctCap) {
+      const int64_t D = hd;
+      const uint64_t* kin = dkeys;
+      const uint32_t* vin = nullptr;
+      if (D <= kSmallSortMax) {
+        int n_pad = 2;
+        while (n_pad < D) n_pad <<= 1;
+        if (!(ctx->attr_set & NBW_ATTR_SMALL_SORT)) {
+          NBW_CUDA(ctx, cudaFuncSetAttribute(small_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             kSmallSortMax * (int)(sizeof(uint64_t) + sizeof(uint32_t))));
+          ctx->attr_set |= NBW_ATTR_SMALL_SORT;
+        }
+        small_sort_kernel<<<1, 1024, (size_t)n_pad * (sizeof(uint64_t) + sizeof(uint32_t)), st>>>(dkeys, (int)D, n_pad, kbuf[0],
+                                                                                                 vbuf[0]);
+        NBW_CHECK_LAUNCH(ctx);
+        kin = kbuf[0];
+        vin = vbuf[0];
+      } else {
+        const int n_tiles_d = (int)((D + kTile - 1) / kTile);
+        int cur = 0;
+        for (int shift = 0; shift < key_bits; shift += 8) {
+          radix_count_kernel<<<n_tiles_d, kSortThreads, 0, st>>>(kin, D, shift, n_tiles_d, counts);
+          NBW_CHECK_LAUNCH(ctx);
+          int rc2 = device_exclusive_scan(ctx, counts, counts, (int64_t)256 * n_tiles_d, stmp, st);
+          if (rc2) return rc2;
+          radix_scatter_kernel<<<n_tiles_d, kSortThreads, 0, st>>>(kin, vin, kbuf[cur], vbuf[cur], D, shift, n_tiles_d, counts);
+          NBW_CHECK_LAUNCH(ctx);
+          kin = kbuf[cur];
+          vin = vbuf[cur];
+          cur ^= 1;
+        }
+      }
+      if (D > 0) {
+        rank_slots_kernel<<<(unsigned)((D + 255) / 256), 256, 0, st>>>(kin, vin, dslot, first, chks, slot_id, uniq_keys, uniq_chks,
+                                                                      uniq_cap, D);
+        NBW_CHECK_LAUNCH(ctx);
+      }
+      assign_from_slots_kernel<<<grid, 256, 0, st>>>(node_slot, slot_id, first, chks, n_keys, static_cast<const uint8_t*>(cells),
+                                                    n_max, ids_prev, ids, dcount, counters, first_flag);
+      NBW_CHECK_LAUNCH(ctx);
+      return NBW_OK;
+    }
+    // more distinct keys than the table holds: sort them all (below)
+  }
   const int n_tiles = (int)((n_keys + kTile - 1) / kTile);
   const size_t n_counts = (size_t)256 * n_tiles;
   const size_t scan_tmp = scan_scratch_elems((int64_t)(n_counts > (size_t)n_keys ? n_counts : (size_t)n_keys));
@@ -400,7 +623,7 @@ extern "C" int nbw_dict_build(nbw_ctx* ctx, const uint64_t* keys, const uint64_t
   DictCounters* counters = cv.take<DictCounters>(1);
   void* work = static_cast<char*>(ctx->scratch) + 1024;
   rc = nbw_dict_build_enqueue(ctx, keys, chks, n_keys, key_bits, cells, n_max, ids_prev, ids, uniq_keys, uniq_chks, uniq_cap,
-                          counters, work, st);
+                              counters, work, st);
   if (rc) return rc;
   DictCounters host;
   NBW_CUDA(ctx, cudaMemcpyAsync(&host, counters, sizeof(host), cudaMemcpyDeviceToHost, st));
@@ -442,7 +665,7 @@ extern "C" int nbw_wl_fit(nbw_ctx* ctx, const void* cells, int64_t n_cells, int 
                                    l, seed, keys, chks, st);
     if (rc) return rc;
     rc = nbw_dict_build_enqueue(ctx, keys, chks, n_keys, l == 0 ? 8 : 64, cells, n_max, prev, ids + (size_t)l * n_keys,
-                            uniq_keys + (size_t)l * n_keys, uniq_chks + (size_t)l * n_keys, n_keys, counters + l, work, st);
+                                uniq_keys + (size_t)l * n_keys, uniq_chks + (size_t)l * n_keys, n_keys, counters + l, work, st);
     if (rc) return rc;
   }
   DictCounters host[NBW_MAX_LEVELS];

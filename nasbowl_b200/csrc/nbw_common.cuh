@@ -114,7 +114,9 @@ size_t nbw_dict_scratch_bytes(int64_t n_keys);
 int nbw_dict_build_enqueue(nbw_ctx* ctx, const uint64_t* keys, const uint64_t* chks, int64_t n_keys, int key_bits,
                            const void* cells, int n_max, const uint32_t* ids_prev, uint32_t* ids, uint64_t* uniq_keys,
                            uint64_t* uniq_chks, int64_t uniq_cap, NbwDictCounters* counters, void* work, cudaStream_t st,
-                           uint8_t* first_flag = nullptr);
+                           uint8_t* first_flag = nullptr, bool allow_hash = true);
+// allow_hash: inputs above 8192 keys go through a hash pre-dedup (one stream sync inside to size the sort of the
+// distinct keys; falls back to the full sort when there are more than 65536 of them)
 
 // One-launch GP factorisation (gp_factor.cu)
 bool nbw_factor_fused_ok(int64_t n);

@@ -114,7 +114,7 @@ extern "C" int nbw_pool_dedup(nbw_ctx* ctx, const void* cells, int64_t n_cells, 
   else cell_iso_signature_kernel<16><<<grid, 256, 0, st>>>(c, n_cells, labeled, seed, keys, chks);
   NBW_CHECK_LAUNCH(ctx);
   rc = nbw_dict_build_enqueue(ctx, keys, chks, n_cells, 64, nullptr, n_max, nullptr, ids, uk, uc, n_cells, counters, work,
-                              st, keep);
+                              st, keep, /*allow_hash=*/false);   // a pool has far more classes than the hash path holds
   if (rc) return rc;
   NBW_CUDA(ctx, cudaMemsetAsync(kept, 0, sizeof(unsigned long long), st));
   count_kept_kernel<<<nbw_grid_for(ctx, n_cells, 256), 256, 0, st>>>(keep, n_cells, n_protected, kept);

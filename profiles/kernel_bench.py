@@ -80,8 +80,21 @@ def main():
         ms = timed(lambda: eng._check(lib.nbw_dict_build(ctx, eng._p(keys), eng._p(chks), nk, 64, eng._p(cells), n_max,
                                                          eng._p(ids0), eng._p(ids), eng._p(uk), eng._p(uc), nk,
                                                          C.byref(d), st)), flush)
+        # hash pre-dedup path (default above 8192 keys): key + chk read, slot written and read, id written, credential
+        # check of every node against the first of its class (record + previous ids of both)
+        byt = nk * (8 + 4 + 4 + 8 + 4 + 4) + N * stride
+        out["kernels"]["dict_build (hash pre-dedup + sort of distinct keys)"] = {
+            "ms": ms, "keys": nk, "unique": int(d.value), "algorithmic_bytes": byt,
+            "achieved_gbs": byt / ms / 1e6, "frac_hbm": byt / ms / 1e6 / hbm, "mkeys_per_s": nk / ms / 1e3}
+        ids_hash = ids.clone()
+        os.environ["NBW_DICT_RADIX"] = "1"
+        ms = timed(lambda: eng._check(lib.nbw_dict_build(ctx, eng._p(keys), eng._p(chks), nk, 64, eng._p(cells), n_max,
+                                                         eng._p(ids0), eng._p(ids), eng._p(uk), eng._p(uc), nk,
+                                                         C.byref(d), st)), flush)
+        del os.environ["NBW_DICT_RADIX"]
+        assert torch.equal(ids, ids_hash)
         byt = 8 * nk * (8 + 12 + 12) + nk * (12 + 8 + 4 + 4 + 4)
-        out["kernels"]["dict_build (radix sort + unique)"] = {
+        out["kernels"]["dict_build (radix sort + unique, NBW_DICT_RADIX=1)"] = {
             "ms": ms, "keys": nk, "unique": int(d.value), "algorithmic_bytes": byt,
             "achieved_gbs": byt / ms / 1e6, "frac_hbm": byt / ms / 1e6 / hbm, "mkeys_per_s": nk / ms / 1e3}
         # ---- histogram (reads ids of all levels, writes every byte of Phi once)

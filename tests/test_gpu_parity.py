@@ -100,7 +100,8 @@ def test_gram_tcgen05_random_shapes(eng):
 def test_sort_unique_large(eng):
     import ctypes as C
     rng = np.random.RandomState(1)
-    for n, distinct in [(1, 1), (37, 5), (4096, 100), (4097, 4097), (300000, 20000)]:
+    for n, distinct in [(1, 1), (37, 5), (4096, 100), (4097, 4097), (300000, 20000),
+                        (10000, 9000), (70000, 65536), (300000, 100000), (2000000, 23493)]:
         pool = rng.randint(0, 2 ** 63 - 1, size=distinct, dtype=np.int64)
         keys = pool[rng.randint(0, distinct, size=n)]
         invalid = rng.rand(n) < 0.1
@@ -122,6 +123,37 @@ def test_sort_unique_large(eng):
         assert np.all(got[invalid] == 0xFFFFFFFF)
         assert np.array_equal(got[valid].astype(np.int64), inv.reshape(-1))
         assert np.array_equal(uk.cpu().numpy()[:d.value].view(np.uint64), uniq)
+        assert np.array_equal(uc.cpu().numpy()[:d.value].view(np.uint64), (uniq * np.uint64(3)) ^ np.uint64(0x1234))
+
+
+def test_dict_build_hash_path_matches_full_sort(eng, monkeypatch):
+    """Above 8192 keys the dictionary is built by hash pre-dedup + a sort of the distinct keys only; the ids, the
+    dictionary and the collision check must be those of the full radix sort (NBW_DICT_RADIX=1)."""
+    cells = eng.generate_cells(0, 5, 0, 30000)
+    a = eng.wl_fit(cells, 8, 3, build_features=False)
+    monkeypatch.setenv("NBW_DICT_RADIX", "1")
+    b = eng.wl_fit(cells, 8, 3, build_features=False)
+    assert a.dims == b.dims
+    assert torch.equal(a.ids, b.ids)
+    for l in range(4):
+        assert torch.equal(a.uniq_keys[l], b.uniq_keys[l]) and torch.equal(a.uniq_chks[l], b.uniq_chks[l])
+
+
+def test_hash_collision_is_detected_large(eng):
+    import ctypes as C
+    n = 50000
+    rng = np.random.RandomState(3)
+    keys = rng.randint(0, 1000, size=n).astype(np.int64)
+    chks = keys * 7
+    chks[31337] += 1
+    dk, dc = torch.from_numpy(keys).cuda(), torch.from_numpy(chks).cuda()
+    ids = torch.empty(n, dtype=torch.int32, device="cuda")
+    uk = torch.empty(n, dtype=torch.int64, device="cuda")
+    uc = torch.empty(n, dtype=torch.int64, device="cuda")
+    d = C.c_int64(0)
+    rc = eng.lib.nbw_dict_build(eng.ctx, eng._p(dk), eng._p(dc), n, 64, None, 8, None, eng._p(ids),
+                                eng._p(uk), eng._p(uc), n, C.byref(d), eng.stream)
+    assert rc == 4
 
 
 def test_hash_collision_is_detected(eng):
