@@ -528,7 +528,9 @@ def run_scoring(name, args, ctx):
     prof = instruction_profile(name)
     sm_mhz = (clocks or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
     issue_peak = 148 * 4 * sm_mhz * 1e6 / 1e9                       # G warp-instructions / s: 4 schedulers per SM
-    roof = {"kernel": "score_packed_kernel<%d,%d>" % (n_max, len(kernels)), "kernel_ms": kernel_ms,
+    kname = (prof or {}).get("kernel") or ("score_cell_kernel<%d>" % len(kernels) if n_max == 8 and len(kernels) <= 3
+                                           else "score_packed_kernel<%d,%d>" % (n_max, len(kernels)))
+    roof = {"kernel": kname, "kernel_ms": kernel_ms,
             "kernel_share_of_step": kernel_ms / (elapsed_ms / steps), "candidates_per_launch": M,
             "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
                     "bytes_per_unit": w["bytes"], "layout_bytes_per_unit": rec_bytes + 4, "peak_source": peak_src + " hbm_gbs, burst copy"}}
