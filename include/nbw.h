@@ -332,6 +332,17 @@ typedef struct {
    * ops.  palette[c] = the op code (level-0 key) of index c.  The kernel expands it in its prologue. */
   int32_t compact;
   uint8_t palette[8];
+  /* Histogram intersection on the packed path (oa != 0, optional: NULL keeps the general G path).  In thermometer
+   * form (vertex_histogram.py:233-249: sum_label min(count, count') = sum_(label, t) [count >= t][count' >= t]) every
+   * (node, level) of a candidate activates ONE column: (its label, its rank among the cell's nodes with that label).
+   * Ranks are non-increasing along a node's ancestor chain, so a node is its rank-1 chain — described by its deepest
+   * dictionary label, like the linear kernel — plus one EXCEPTION item per level at which its rank exceeds 1:
+   *   e(label, r) = column (label, r) [if r <= max training count of the label] - column (label, 1).
+   * H / w_mu_prefix then span n_labels = T + X stacked items: the T chain items (label_off) followed by the
+   * exception items, and the posterior is the same sum over item pairs.
+   * oa_exc[label_off[l] + id] = (stacked index of e(label, 2)) << 5 | max training count (<= 16); the item of rank r
+   * is that index + min(r, max + 1) - 2.  Single part only. */
+  const uint32_t* oa_exc;
   const void* next;                      /* const nbw_model* of the next part (host memory) */
 } nbw_model;
 
@@ -354,6 +365,14 @@ int nbw_model_build_id_hash(nbw_ctx* ctx, const uint64_t* uniq_keys_prev, int64_
 int nbw_model_build_buckets(nbw_ctx* ctx, const uint64_t* uniq_keys, const uint64_t* uniq_chks,
                             int64_t n_unique, void* tags, void* entries, int64_t n_buckets,
                             uint32_t* flags, void* stream);
+
+/* out[i, j] = sum_k sign(k) * B[i, col(k)] over the K entries idx[j * K + k]: v >= 0 adds column v, v < 0 subtracts
+ * column ~v, 0x7FFFFFFF is skipped.  Builds the item features of the packed histogram-intersection path (rank-1
+ * chains and exception items, see nbw_model.oa_exc) from the scaled thermometer features of the training set —
+ * the feature-space form of VertexHistogram._calculate_kernel_matrix's min-sum (vertex_histogram.py:233-249).
+ * B: [n x ldb] f64, idx: [J x K] i32 (device), out: [n x ldo] f64.  Enqueues only. */
+int nbw_combine_columns(nbw_ctx* ctx, const double* B, int64_t n, int64_t ldb, const int32_t* idx, int64_t J, int K,
+                        double* out, int64_t ldo, void* stream);
 
 /* GraphGP.predict (bayesopt/gp.py:240-283, diagonal) + acquisition eval (acquisitions.py:59-80,130-138)
  * over the pool.  scores: [M] f32 (required).  mu64/var64/score64: optional [M] f64 outputs (NULL to skip). */

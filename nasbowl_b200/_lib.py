@@ -65,6 +65,7 @@ class Model(C.Structure):
         ("weighted", C.c_int32), ("undirected", C.c_int32), ("rec_offset", C.c_int32),
         ("rec_stride", C.c_int32), ("label_base", C.c_int32), ("compact", C.c_int32),
         ("palette", C.c_uint8 * 8),
+        ("oa_exc", C.c_void_p),
         ("next", C.c_void_p),
     ]
 
@@ -108,6 +109,7 @@ _PROTOTYPES = {
                                          C.POINTER(C.c_double), _vp]),
     "nbw_scale_features": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _f64, _vp, _i64, _vp]),
     "nbw_label_parents": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    "nbw_combine_columns": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i64, _i32, _vp, _i64, _vp]),
     "nbw_prefix_features": (C.c_int, [_vp, _vp, _i64, _i64, _i32, C.POINTER(_i64), C.POINTER(_i64), _vp, _vp,
                                       _i64, _vp]),
     "nbw_posterior_cov_finish": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _f64, _f64, _vp, _i64, _vp]),

@@ -675,8 +675,56 @@ class GraphGP:
         eng.gemm(False, False, n, 1, n, 1.0, d['K'], n, alpha, 1, 0.0, mu_train, 1)
         if plain:
             first.general_builder = build_general
-        if any_oa:
+        # Histogram intersection has two evaluation forms: items (below) and the general G path ((node, level)^2
+        # gathers over thermometer columns).  Measured (profiles/r02_oa_bench.json): items win on 8-node cells at
+        # every depth (1.3-2.3x) and on 16-node cells from h = 3; 16-node cells at h <= 2 stay on the general path
+        # (the item operator of a DARTS dictionary outgrows L2).  NBW_OA_FORM=items|general overrides.
+        oa_form = os.environ.get("NBW_OA_FORM") or ("general" if fits[0].n_max == 16 and hs[0] <= 2 else "items")
+        if any_oa and oa_form == "general":
             first.G, first.w_mu = build_general()
+        elif any_oa:
+            # Histogram intersection in ITEM form (nbw_model.oa_exc): every (node, level) of a candidate activates the
+            # thermometer column (label, rank inside the label class).  Item s < T = the rank-1 columns along the
+            # ancestor chain of label s; item T + x = exception e(label, r) = column (label, r) [r <= max count]
+            # - column (label, 1).  Bs = B [A1^T | Dx^T], then H and w_mu exactly like the prefix form.
+            fit, h = fits[0], hs[0]
+            B, D = scaled_features(0)
+            lo, co = fit.label_off, fit.col_off
+            Tl = lo[h + 1]
+            tb = fit.thermo_base[:Tl].cpu().numpy().astype(np.int64)
+            mc = fit.max_count[:Tl].cpu().numpy().astype(np.int64)
+            par = fit.parents[:Tl].cpu().numpy().astype(np.int64)
+            level_of = np.repeat(np.arange(h + 1), [lo[l + 1] - lo[l] for l in range(h + 1)])
+            lo_a, co_a = np.asarray(lo, dtype=np.int64), np.asarray(co, dtype=np.int64)
+            col1 = co_a[level_of] + tb
+            X = int(mc.sum())
+            S = Tl + X
+            Kc = max(h + 1, 2)
+            SKIP = 0x7FFFFFFF
+            idx = np.full((S, Kc), SKIP, dtype=np.int64)
+            cur, lev = np.arange(Tl), level_of.copy()
+            for k in range(h + 1):
+                alive = lev >= 0
+                idx[:Tl][alive, k] = col1[cur[alive]]
+                up = alive & (lev > 0)
+                cur[up] = lo_a[lev[up] - 1] + par[cur[up]]
+                lev = np.where(up, lev - 1, -1)
+            first_exc = Tl + np.cumsum(mc) - mc                      # item of e(label, 2)
+            lab = np.repeat(np.arange(Tl), mc)                       # label of every exception item
+            r = np.arange(X) - (first_exc[lab] - Tl) + 2             # its rank (2 .. max + 1)
+            idx[Tl:, 0] = np.where(r <= mc[lab], col1[lab] + r - 1, SKIP)
+            idx[Tl:, 1] = ~col1[lab]
+            Bs = torch.zeros((n, S + 1), dtype=torch.float64, device=eng.device)
+            eng.combine_columns(B, torch.from_numpy(idx.astype(np.int32)).to(eng.device), Bs, S + 1)
+            Wp = eng.empty((n, S + 1), torch.float64)
+            eng.gemm(False, False, n, S + 1, n, 1.0, Linv, n, Bs, S + 1, 0.0, Wp, S + 1)
+            H = eng.empty((S + 1, S + 1), torch.float64)
+            eng.gemm(True, False, S + 1, S + 1, n, 1.0, Wp, S + 1, Wp, S + 1, 0.0, H, S + 1)
+            w_mu_p = eng.empty((S + 1,), torch.float64)
+            eng.gemm(True, False, S + 1, 1, n, 1.0, Bs, S + 1, alpha, 1, 0.0, w_mu_p, 1)
+            first.H, first.w_mu_prefix, first.total_labels = H, w_mu_p, S
+            exc = (first_exc << 5) | np.minimum(mc, 31)
+            first.oa_exc = torch.from_numpy(exc.astype(np.uint32).view(np.int32)).to(eng.device)
         else:
             # prefix form (nbw_model.H): the operators summed over ancestor chains of labels, all parts
             # side by side: Bp [n, T + 1], last column zero (landing slot of labels outside the dictionary)

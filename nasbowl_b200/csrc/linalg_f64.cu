@@ -826,3 +826,34 @@ extern "C" int nbw_prefix_features(nbw_ctx* ctx, const double* B, int64_t ldb, i
   }
   return NBW_OK;
 }
+
+// ====================================================================== item features of the packed OA path
+namespace {
+__global__ void combine_columns_kernel(const double* __restrict__ B, int64_t n, int64_t ldb, const int32_t* __restrict__ idx,
+                                       int64_t J, int K, double* __restrict__ out, int64_t ldo) {
+  const int64_t total = n * J, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const int64_t i = t / J, j = t % J;
+    const double* __restrict__ row = B + i * ldb;
+    double v = 0.0;
+    for (int k = 0; k < K; ++k) {
+      const int32_t c = idx[j * K + k];
+      if (c == 0x7FFFFFFF) continue;
+      v += c >= 0 ? row[c] : -row[~c];
+    }
+    out[i * ldo + j] = v;
+  }
+}
+}  // namespace
+
+extern "C" int nbw_combine_columns(nbw_ctx* ctx, const double* B, int64_t n, int64_t ldb, const int32_t* idx, int64_t J,
+                                   int K, double* out, int64_t ldo, void* stream) {
+  if (!ctx) return NBW_ERR_INVALID;
+  NBW_REQUIRE(ctx, n >= 0 && J >= 0 && K >= 1 && K <= 64 && ldo >= J, "bad shape");
+  if (n == 0 || J == 0) return NBW_OK;
+  NBW_REQUIRE(ctx, B && idx && out, "null pointer");
+  combine_columns_kernel<<<nbw_grid_for(ctx, n * J, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(B, n, ldb, idx, J, K,
+                                                                                                      out, ldo);
+  NBW_CHECK_LAUNCH(ctx);
+  return NBW_OK;
+}

@@ -31,7 +31,7 @@ struct nbw_ctx {
   uint32_t attr_set;    // bit i = opt-in shared-memory size already set for kernel i on this device
   int gram_max_pairs;   // co-resident CTA pairs of the Gram kernel on this device (0 = not queried yet)
   cudaEvent_t prof_ev[2];   // optional caller-owned events recorded right before / after the scoring kernel
-  int packed_occ[32];   // resident CTAs per SM of each score_packed_kernel variant (0 = not queried yet)
+  int packed_occ[64];   // resident CTAs per SM of each score_packed_kernel variant (0 = not queried yet)
   void* piece_cands;    // per-piece top-n lists of the host-buffer entry points (score_pool.cu)
   void* topk_blocks;    // per-CTA top-n lists of the fused scoring kernel (score_packed.cu), two alternating slots
   size_t topk_blocks_bytes;

@@ -43,6 +43,7 @@ struct PartParams {
   double wsuf[NBW_MAX_LEVELS];      // sum of lw over the levels deeper than l
   const int32_t* child;
   const int32_t* final_label;
+  const uint32_t* oa_exc;           // histogram intersection: (first exception item << 5 | max count) per label
   int32_t h, first_stable, undirected, rec_offset, label_base, compact;
   uint8_t palette[8];
 };
@@ -96,7 +97,13 @@ __device__ __forceinline__ bool cand_better(float v, int i, float bv, int bi) {
   return v > bv || (v == bv && i < bi);
 }
 
-template <int NMAX, int NP, bool WEIGHTED, bool TOPK>
+// Exception item of a node with 0-based rank r0 > 0 inside its label class (nbw_model.oa_exc)
+__device__ __forceinline__ int oa_item(uint32_t info, int r0) {
+  const int mc = (int)(info & 31u);
+  return (int)(info >> 5) + (r0 < mc ? r0 : mc) - 1;
+}
+
+template <int NMAX, int NP, bool WEIGHTED, bool TOPK, bool OA = false>
 __global__ void __launch_bounds__(kPackThreads, NMAX == 8 ? 5 : 4)
 score_packed_kernel(const __grid_constant__ PackedParams P, const uint8_t* __restrict__ cells, int64_t n_cells,
                     int64_t per_warp, float* __restrict__ scores, double* __restrict__ mu64,
@@ -123,6 +130,10 @@ score_packed_kernel(const __grid_constant__ PackedParams P, const uint8_t* __res
   __shared__ int sh_g[kPackThreads];
   __shared__ float sh_tv[TOPK ? kTopMax : 1][kPackThreads];
   __shared__ int sh_ti[TOPK ? kTopMax : 1][kPackThreads];
+  // histogram intersection: the exception item of this lane's node at every level (a prefix of the levels: ranks
+  // do not grow along a node's chain), one column per thread
+  __shared__ int exc_s[OA ? NBW_MAX_LEVELS : 1][kPackThreads];
+  static_assert(!OA || NP == 1, "the packed histogram-intersection path takes one kernel");
   const int tid = threadIdx.x;
   // succ_lut[mask]: positions of the four lowest set bits of an 8-bit successor mask (4 bits each; positions
   // beyond the population repeat a harmless 0) | the remaining bits << 16
@@ -226,6 +237,7 @@ score_packed_kernel(const __grid_constant__ PackedParams P, const uint8_t* __res
     const int64_t my_g = g + k;
 
     int deep[NP];
+    int n_exc = 0;              // OA: exception levels of this lane's node
     KccT kacc = 0;
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
@@ -271,8 +283,19 @@ score_packed_kernel(const __grid_constant__ PackedParams P, const uint8_t* __res
       }
       int cnt = __popc(cls);
       KccT kss = 0;
-      if (present) kss = WEIGHTED ? (KccT)(Q.lw[0] * cnt) : (KccT)cnt;
+      // self-similarity: sum over labels of count^2 (linear) or of min(count, count) = count (intersection)
+      if (present) kss = WEIGHTED ? (KccT)(Q.lw[0] * (OA ? 1 : cnt)) : (KccT)(OA ? 1 : cnt);
       int dp = in_dict ? Q.label_base + Q.loff[0] + (int)d0 : zero_slot;
+      int ec = 0;                 // levels 0 .. ec-1 carry an exception item
+      if constexpr (OA) {
+        const int r0 = __popc(cls & ((1u << node) - 1u));
+        int item = zero_slot;
+        if (in_dict && r0 > 0) {
+          item = oa_item(__ldg(Q.oa_exc + Q.loff[0] + (int)d0), r0);
+          ec = 1;
+        }
+        exc_s[0][tid] = item;
+      }
 
       // The successors of a node do not change from level to level: their lanes are resolved once.  8-node
       // cells look the (up to four) lowest successor positions up in a 256-entry table built at kernel start
@@ -390,9 +413,18 @@ score_packed_kernel(const __grid_constant__ PackedParams P, const uint8_t* __res
         in_dict = seen;
         dense_prev = dense;
         cnt = __popc(cls);
-        if (endpoint) kss += WEIGHTED ? (KccT)(Q.lw[l] * cnt) : (KccT)cnt;
+        if (endpoint) kss += WEIGHTED ? (KccT)(Q.lw[l] * (OA ? 1 : cnt)) : (KccT)(OA ? 1 : cnt);
         if (seen) dp = Q.label_base + Q.loff[l] + (int)dense;
-        if (stable && l < h && !__any_sync(FULL, changed)) {
+        if constexpr (OA) {
+          const int r0 = __popc(cls & ((1u << node) - 1u));
+          int item = zero_slot;
+          if (seen && r0 > 0) {
+            item = oa_item(__ldg(Q.oa_exc + Q.loff[l] + (int)dense), r0);
+            ec = l + 1;
+          }
+          exc_s[l][tid] = item;
+        }
+        if (!OA && stable && l < h && !__any_sync(FULL, changed)) {
           // A stable level reproduced (classes, membership) for every cell of this warp: all deeper levels
           // apply the same map, so they reproduce it too; only the labels move down the child chain.
           if (endpoint) kss += WEIGHTED ? (KccT)(Q.wsuf[l] * cnt) : (KccT)((h - l) * cnt);
@@ -401,11 +433,55 @@ score_packed_kernel(const __grid_constant__ PackedParams P, const uint8_t* __res
         }
       }
       deep[p] = dp;
+      n_exc = ec;
       kacc += kss;
     }
 
     // ---------------------------------------------------------------- posterior (prefix form)
     double mu_acc = 0.0, q_acc = 0.0;
+    if constexpr (OA) {
+      // items of a node: its deepest label + its exception items; the sum runs over all item pairs of the cell
+      __syncwarp();
+      const int own = deep[0];
+      if (own != zero_slot) {
+        mu_acc += __ldg(P.w_mu + own);
+        q_acc += __ldg(H + (int64_t)own * ldh + own);
+      }
+      for (int a = 0; a < n_exc; ++a) {
+        const int xa = exc_s[a][tid];
+        mu_acc += __ldg(P.w_mu + xa);
+        const double* __restrict__ hrow = H + (int64_t)xa * ldh;
+        double acc = own != zero_slot ? __ldg(hrow + own) : 0.0;
+        for (int b = a + 1; b < n_exc; ++b) acc += __ldg(hrow + exc_s[b][tid]);
+        q_acc += 2.0 * acc + __ldg(hrow + xa);
+      }
+#pragma unroll 1
+      for (int r = 1; r <= NMAX / 2; ++r) {
+        int t = node + r;
+        t -= (t >= my_n) ? my_n : 0;
+        const bool use = active && 2 * r <= my_n;
+        const double f = (2 * r == my_n) ? 1.0 : 2.0;
+        const int pl = (sub_base + t) & 31;
+        const int pd = __shfl_sync(FULL, own, pl);
+        const int pec = __shfl_sync(FULL, n_exc, pl);
+        if (use) {
+          const int ptid = tid - lane + pl;
+          double acc = 0.0;
+          if (own != zero_slot) {
+            const double* __restrict__ hrow = H + (int64_t)own * ldh;
+            if (pd != zero_slot) acc += __ldg(hrow + pd);
+            for (int b = 0; b < pec; ++b) acc += __ldg(hrow + exc_s[b][ptid]);
+          }
+          for (int a = 0; a < n_exc; ++a) {
+            const double* __restrict__ hrow = H + (int64_t)exc_s[a][tid] * ldh;
+            if (pd != zero_slot) acc += __ldg(hrow + pd);
+            for (int b = 0; b < pec; ++b) acc += __ldg(hrow + exc_s[b][ptid]);
+          }
+          q_acc += f * acc;
+        }
+      }
+      __syncwarp();
+    } else {
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
       if (deep[p] != zero_slot) {
@@ -440,6 +516,7 @@ score_packed_kernel(const __grid_constant__ PackedParams P, const uint8_t* __res
           }
         }
       }
+    }
     }
     // segmented sums over the lanes of a cell: totals land on its first lane, in an order that
     // depends on the node index only (scores do not depend on how cells were packed)
@@ -563,7 +640,7 @@ __device__ __forceinline__ uint32_t eq_bits8(uint64_t w, uint32_t byte) {
   return lo | (hi << 4);
 }
 
-template <int NP, bool WEIGHTED, bool TOPK>
+template <int NP, bool WEIGHTED, bool TOPK, bool OA = false>
 __global__ void __launch_bounds__(kCellThreads)
 score_cell_kernel(const __grid_constant__ PackedParams P, const uint8_t* __restrict__ cells, int64_t n_cells,
                   float* __restrict__ scores, double* __restrict__ mu64, double* __restrict__ var64,
@@ -571,6 +648,10 @@ score_cell_kernel(const __grid_constant__ PackedParams P, const uint8_t* __restr
                   int64_t index_base) {
   constexpr unsigned FULL = 0xffffffffu;
   using KccT = typename std::conditional<WEIGHTED, double, int>::type;
+  static_assert(!OA || NP == 1, "the packed histogram-intersection path takes one kernel");
+  // histogram intersection: the exception items of this thread's cell (nbw_model.oa_exc), at most one per node and
+  // level, one column per thread: [8 * (h + 1)][kCellThreads] ints of dynamic shared memory
+  extern __shared__ int exs[];
   __shared__ uint4 ent[8][kCellThreads];     // per node: {ha_lo, ha_hi, hb, class count field}
   __shared__ float sh_tv[TOPK ? kTopMax : 1][kCellThreads];
   __shared__ int sh_ti[TOPK ? kTopMax : 1][kCellThreads];
@@ -586,6 +667,7 @@ score_cell_kernel(const __grid_constant__ PackedParams P, const uint8_t* __restr
 
   for (int64_t g = (int64_t)blockIdx.x * kCellThreads + tid; g < n_cells; g += (int64_t)gridDim.x * kCellThreads) {
     int deep[NP][8];
+    int ne = 0;                  // OA: exception items collected so far
     KccT kacc = 0;
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
@@ -651,7 +733,21 @@ score_cell_kernel(const __grid_constant__ PackedParams P, const uint8_t* __restr
         dp[v] = seen ? Q.label_base + Q.loff[0] + (int)d0 : zero_slot;
         if (present) clsw |= (uint64_t)(eq_bits8(labw, lab) & pm) << (8 * v);
       }
-      KccT kss = WEIGHTED ? (KccT)(Q.lw[0] * __popcll(clsw)) : (KccT)__popcll(clsw);
+      // self-similarity: sum over labels of count^2 (linear) or of min(count, count) = count (intersection)
+      const int cnt0 = OA ? __popc(pm) : __popcll(clsw);
+      KccT kss = WEIGHTED ? (KccT)(Q.lw[0] * cnt0) : (KccT)cnt0;
+      // exception items of the current level: nodes in the dictionary that are not the first of their class
+      auto emit_exceptions = [&](int l) {
+#pragma unroll
+        for (int v = 1; v < 8; ++v) {
+          const int r0 = __popc((uint32_t)(clsw >> (8 * v)) & ((1u << v) - 1u));
+          if (((im >> v) & 1u) && r0 > 0) {
+            exs[ne * kCellThreads + tid] = oa_item(__ldg(Q.oa_exc + Q.loff[l] + (int)dense[v]), r0);
+            ++ne;
+          }
+        }
+      };
+      if constexpr (OA) emit_exceptions(0);
 
       // ---- levels 1..h
       const int h = Q.h, fs = Q.first_stable;
@@ -749,9 +845,10 @@ score_cell_kernel(const __grid_constant__ PackedParams P, const uint8_t* __restr
         const bool changed = cls_new != clsw || im_new != im;
         clsw = cls_new;
         im = im_new;
-        const int cnt = __popcll(clsw);
+        const int cnt = OA ? __popc(em) : __popcll(clsw);
         kss += WEIGHTED ? (KccT)(Q.lw[l] * cnt) : (KccT)cnt;
-        if (stable && l < h && !changed) {
+        if constexpr (OA) emit_exceptions(l);
+        if (!OA && stable && l < h && !changed) {
           // this cell reproduced (classes, membership) at a stable level: every deeper level will too; only the
           // labels move down the child chain (nbw_model.final_label)
           kss += WEIGHTED ? (KccT)(Q.wsuf[l] * cnt) : (KccT)((h - l) * cnt);
@@ -786,6 +883,21 @@ score_cell_kernel(const __grid_constant__ PackedParams P, const uint8_t* __restr
             }
         }
       }
+    if constexpr (OA) {
+      for (int a = 0; a < ne; ++a) {
+        const int xa = exs[a * kCellThreads + tid];
+        mu_acc += __ldg(P.w_mu + xa);
+        const double* __restrict__ hrow = H + (int64_t)xa * ldh;
+        double acc = 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int du = deep[0][u];
+          if (du != zero_slot) acc += __ldg(hrow + du);
+        }
+        for (int b = a + 1; b < ne; ++b) acc += __ldg(hrow + exs[b * kCellThreads + tid]);
+        q_acc += 2.0 * acc + __ldg(hrow + xa);
+      }
+    }
     double mu, var;
     const double sc = finish_score(P, mu_acc, q_acc, (double)kacc, mu, var);
     const float scf = (float)sc;
@@ -945,6 +1057,7 @@ int fill_part(nbw_ctx* ctx, const nbw_model* M, PartParams& Q) {
   memcpy(Q.palette, M->palette, 8);
   Q.child = M->child;
   Q.final_label = M->final_label;
+  Q.oa_exc = M->oa_exc;
   double suffix = 0.0;
   for (int l = M->h; l >= 0; --l) {
     Q.lw[l] = M->weighted ? M->level_weight[l] : 1.0;
@@ -970,11 +1083,11 @@ int fill_part(nbw_ctx* ctx, const nbw_model* M, PartParams& Q) {
   return NBW_OK;
 }
 
-template <int NMAX, int NP, bool WEIGHTED, bool TOPK>
+template <int NMAX, int NP, bool WEIGHTED, bool TOPK, bool OA = false>
 int launch_variant(nbw_ctx* ctx, int variant, const PackedParams& P, const uint8_t* cells, int64_t n, float* scores,
                    double* mu64, double* var64, double* score64, int k, int distinct, int64_t index_base,
                    NbwCand* out_cands, cudaStream_t st) {
-  auto kern = score_packed_kernel<NMAX, NP, WEIGHTED, TOPK>;
+  auto kern = score_packed_kernel<NMAX, NP, WEIGHTED, TOPK, OA>;
   if (!ctx->packed_occ[variant]) {
     int occ = 0;
     NBW_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kPackThreads, 0));
@@ -1021,12 +1134,22 @@ int launch_variant(nbw_ctx* ctx, int variant, const PackedParams& P, const uint8
   return NBW_OK;
 }
 
-template <int NP, bool WEIGHTED, bool TOPK>
+template <int NP, bool WEIGHTED, bool TOPK, bool OA = false>
 int launch_cell_variant(nbw_ctx* ctx, int variant, const PackedParams& P, const uint8_t* cells, int64_t n, float* scores,
                         double* mu64, double* var64, double* score64, int k, int distinct, int64_t index_base,
                         NbwCand* out_cands, cudaStream_t st) {
-  auto kern = score_cell_kernel<NP, WEIGHTED, TOPK>;
-  if (!ctx->packed_occ[variant]) {
+  auto kern = score_cell_kernel<NP, WEIGHTED, TOPK, OA>;
+  // histogram intersection: one exception slot per node and level (the occupancy is queried for the deepest model)
+  constexpr size_t kExcMax = OA ? sizeof(int) * 8 * NBW_MAX_LEVELS * kCellThreads : 0;
+  const size_t dyn = OA ? sizeof(int) * 8 * (size_t)(P.part[0].h + 1) * kCellThreads : 0;
+  if (OA) {
+    // the exception columns depend on the model's depth: attribute once, occupancy per launch (a host-side formula)
+    if (!ctx->packed_occ[variant]) NBW_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kExcMax));
+    int occ = 0;
+    NBW_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kCellThreads, dyn));
+    NBW_REQUIRE(ctx, occ >= 1, "score_cell_kernel does not fit this device");
+    ctx->packed_occ[variant] = occ;
+  } else if (!ctx->packed_occ[variant]) {
     int occ = 0;
     NBW_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kCellThreads, 0));
     NBW_REQUIRE(ctx, occ >= 1, "score_cell_kernel does not fit this device");
@@ -1055,7 +1178,7 @@ int launch_cell_variant(nbw_ctx* ctx, int variant, const PackedParams& P, const 
     NBW_REQUIRE(ctx, (size_t)grid * kTopMax * sizeof(NbwCand) <= slot_bytes, "too many CTAs for the top-n block lists");
   }
   if (ctx->prof_ev[0]) NBW_CUDA(ctx, cudaEventRecord(ctx->prof_ev[0], st));
-  kern<<<(unsigned)grid, kCellThreads, 0, st>>>(P, cells, n, scores, mu64, var64, score64, blocks, k, distinct, index_base);
+  kern<<<(unsigned)grid, kCellThreads, dyn, st>>>(P, cells, n, scores, mu64, var64, score64, blocks, k, distinct, index_base);
   NBW_CHECK_LAUNCH(ctx);
   if (ctx->prof_ev[1]) NBW_CUDA(ctx, cudaEventRecord(ctx->prof_ev[1], st));
   if (TOPK) {
@@ -1100,7 +1223,8 @@ int launch_parts(nbw_ctx* ctx, int np, bool weighted, const PackedParams& P, con
 
 // Is this model scored by the packed kernel?  (Linear kernels in prefix form with the packed-path tables.)
 bool nbw_packed_applicable(const nbw_model* M) {
-  if (!M || M->oa || !M->H || !M->w_mu_prefix) return false;
+  if (!M || !M->H || !M->w_mu_prefix) return false;
+  if (M->oa && (!M->oa_exc || M->next)) return false;   // histogram intersection: item form, single kernel
   if (getenv("NBW_SCORE_LEGACY")) return false;     // diagnostic switch: first-generation kernel (single part only)
   const bool hashed1 = M->h >= 1 && (M->first_stable == 0 || 1 < M->first_stable);
   return !hashed1 || M->bucket_tags[1] != nullptr;
@@ -1119,7 +1243,8 @@ int nbw_score_packed(nbw_ctx* ctx, const nbw_model* M, const void* cells, int64_
   const int rec = n_max == 8 ? 16 : 48;
   for (const nbw_model* part = M; part; part = static_cast<const nbw_model*>(part->next)) {
     NBW_REQUIRE(ctx, np < NBW_MAX_PARTS, "the fused pool path takes sums of up to %d kernels", NBW_MAX_PARTS);
-    NBW_REQUIRE(ctx, part->n_max == n_max && !part->oa, "parts of a sum must share n_max and be linear WL kernels");
+    NBW_REQUIRE(ctx, part->n_max == n_max && (!part->oa || (part == M && !part->next && part->oa_exc)),
+                "parts of a sum must share n_max and be linear WL kernels");
     int rc = fill_part(ctx, part, P.part[np]);
     if (rc) return rc;
     weighted = weighted || part->weighted != 0;
@@ -1151,6 +1276,25 @@ int nbw_score_packed(nbw_ctx* ctx, const nbw_model* M, const void* cells, int64_
   const uint8_t* c = static_cast<const uint8_t*>(cells);
   NbwCand* oc = static_cast<NbwCand*>(out_cands);
   if (k > 0) NBW_REQUIRE(ctx, k <= kTopMax, "fused top-n handles k <= %d", kTopMax);
+  if (M->oa) {
+    // histogram intersection in item form (nbw_model.oa_exc): single kernel, unit weights; variants 32.. of the
+    // occupancy cache
+    NBW_REQUIRE(ctx, !weighted, "the packed histogram-intersection path takes unit level weights");
+#define NBW_ARGS P, c, n_cells, scores, mu64, var64, score64, k, distinct, index_base, oc, st
+#define NBW_ARGS0 P, c, n_cells, scores, mu64, var64, score64, 0, 0, 0, nullptr, st
+    if (n_max == 8 && (compact || !getenv("NBW_SCORE_LANES"))) {
+      if (k > 0) return launch_cell_variant<1, false, true, true>(ctx, 32, NBW_ARGS);
+      return launch_cell_variant<1, false, false, true>(ctx, 33, NBW_ARGS0);
+    }
+    if (n_max == 8) {
+      if (k > 0) return launch_variant<8, 1, false, true, true>(ctx, 34, NBW_ARGS);
+      return launch_variant<8, 1, false, false, true>(ctx, 35, NBW_ARGS0);
+    }
+    if (k > 0) return launch_variant<16, 1, false, true, true>(ctx, 36, NBW_ARGS);
+    return launch_variant<16, 1, false, false, true>(ctx, 37, NBW_ARGS0);
+#undef NBW_ARGS
+#undef NBW_ARGS0
+  }
   if (n_max == 8 && np <= 3 && (compact || !getenv("NBW_SCORE_LANES"))) {
     // 8-node records: one thread per cell (NBW_SCORE_LANES=1 keeps the lane-per-node kernel for comparison)
     const int rc = k > 0 ? launch_cell_parts<true>(ctx, np, weighted, P, c, n_cells, scores, mu64, var64, score64, k, distinct,

@@ -444,7 +444,7 @@ int check_model(nbw_ctx* ctx, const nbw_model* M, bool need_posterior) {
   NBW_REQUIRE(ctx, M->n_features > 0, "model.n_features must be positive");
   NBW_REQUIRE(ctx, M->first_stable == 0 || (M->first_stable >= 3 && M->first_stable <= M->h && M->child != nullptr),
               "model.first_stable must be 0 or in [3, h] with a child table");
-  if (need_posterior && !(M->H != nullptr && !M->oa)) {
+  if (need_posterior && !nbw_packed_applicable(M) && !(M->H != nullptr && !M->oa)) {
     NBW_REQUIRE(ctx, M->G && M->w_mu && M->ld_g >= M->n_features + 1, "model.G / w_mu missing or ld_g < n_features + 1");
   }
   if (need_posterior) NBW_REQUIRE(ctx, M->acq >= NBW_ACQ_EI && M->acq <= NBW_ACQ_MEAN, "unknown acquisition");

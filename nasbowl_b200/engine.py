@@ -443,6 +443,13 @@ class Engine:
         self._check(self.lib.nbw_scale_features(self.ctx, self._p(phi), phi.stride(0), n, k0, k1, self._p(s),
                                                 float(sqrt_w), self._p(out), ldo, self.stream))
 
+    def combine_columns(self, B: torch.Tensor, idx: torch.Tensor, out: torch.Tensor, ldo: int):
+        """out[:, j] = sum_k +-B[:, idx[j, k]] (nbw_combine_columns; ~c subtracts column c, 0x7FFFFFFF skips)."""
+        J, K = idx.shape
+        self._check(self.lib.nbw_combine_columns(self.ctx, self._p(B), B.shape[0], B.stride(0), self._p(idx), J, K,
+                                                 self._p(out), ldo, self.stream))
+        return out
+
     def prefix_features(self, B: torch.Tensor, fit: "WLFit", h: int, out: Optional[torch.Tensor] = None,
                         ldp: Optional[int] = None) -> torch.Tensor:
         """Bp [n, T+1]: features summed over ancestor chains (nbw_prefix_features); the extra
@@ -555,7 +562,9 @@ class Engine:
     def fused_topk_ok(self, model: "_lib.Model", k: int) -> bool:
         """The packed kernel serves this model and k (else: nbw_score_pool + nbw_topk*)."""
         import os
-        if k > 8 or model.oa or not model.H or os.environ.get("NBW_SCORE_LEGACY"):
+        if k > 8 or not model.H or os.environ.get("NBW_SCORE_LEGACY"):
+            return False
+        if model.oa and (not model.oa_exc or model.next):
             return False
         hashed1 = model.h >= 1 and (model.first_stable == 0 or model.first_stable > 1)
         return (not hashed1) or bool(model.bucket_tags[1])

@@ -25,7 +25,8 @@ _SCALARS = ("n_max", "h", "oa", "seed", "masks", "bucket_masks", "col_off", "lab
 class PoolModel:
     """One part of the sum (and, on the first part, the operators of the whole sum: `more` lists the
     further parts)."""
-    TENSOR_FIELDS = ("level0", "thermo_base", "max_count", "G", "w_mu", "H", "w_mu_prefix", "child", "final_label")
+    TENSOR_FIELDS = ("level0", "thermo_base", "max_count", "G", "w_mu", "H", "w_mu_prefix", "child", "final_label",
+                     "oa_exc")
     LIST_FIELDS = ("tables", "id_hash", "bucket_tags", "bucket_entries")
 
     def __init__(self):
@@ -54,6 +55,7 @@ class PoolModel:
         self.w_mu_prefix: Optional[torch.Tensor] = None      # fp64 [T + 1]
         self.child: Optional[torch.Tensor] = None            # int32 [T_part]: label -> its only child label (stable levels)
         self.final_label: Optional[torch.Tensor] = None      # int32 [T_part]: stable label -> global index of its level-h descendant
+        self.oa_exc: Optional[torch.Tensor] = None           # oa item form: int32 [T] (first exception item << 5 | max count)
         self.first_stable = 0                                # first WL level on the stable fast path (0 = none)
         self.use_prefix = True                               # False forces the general G path
         self.general_builder = None                          # builds (G, w_mu) on demand (fitting rank only)
@@ -81,7 +83,7 @@ class PoolModel:
         m.n_features = fit.k_end(h)
         m.n_labels = m.total_labels = fit.label_off[h + 1]
         m._find_stable_suffix(fit, int(h))
-        if packed and not m.oa:
+        if packed:
             last_hashed = h if not m.first_stable else m.first_stable - 1
             m.id_hash, m.bucket_tags, m.bucket_entries, m.bucket_masks = eng.build_packed_tables(fit, last_hashed)
         return m
@@ -182,7 +184,8 @@ class PoolModel:
         d = self._part_descriptor(rec, palettes)
         d.acq = ACQ[acq]
         multi = len(self.more) > 0
-        prefix = self.H is not None and self.use_prefix and not self.oa
+        legacy = bool(os.environ.get("NBW_SCORE_LEGACY"))
+        prefix = self.H is not None and self.use_prefix and (not self.oa or (self.oa_exc is not None and not legacy))
         if multi and not prefix:
             raise NotImplementedError("a sum of kernels is scored in prefix form (linear WL kernels)")
         if self.G is None and not prefix and not (self.H is None and self.general_builder is None):
@@ -196,6 +199,8 @@ class PoolModel:
         if prefix:
             d.H, d.ld_h, d.w_mu_prefix = self.H.data_ptr(), self.H.stride(0), self.w_mu_prefix.data_ptr()
             d.n_labels = self.total_labels or self.n_labels
+            if self.oa:
+                d.oa_exc = self.oa_exc.data_ptr()
         d.rec_stride = self.n_slots * rec
         d.lik, d.y_mean, d.y_std = float(self.lik), float(self.y_mean), float(self.y_std)
         d.incumbent = float(self.incumbent if incumbent is None else incumbent)

@@ -42,12 +42,25 @@ def test_reference_arm_other_ranks_exit_quietly():
 
 @pytest.mark.gpu
 def test_b200_arm_json_line():
-    d = _run(["--gpus", "1", "--steps", "5", "--warmup", "3", "--pool", "200000", "--cpu-sample", "1000"])
-    for k in REQUIRED + ["roofline", "clocks", "parity"]:
+    d = _run(["--gpus", "1", "--steps", "5", "--warmup", "3", "--cpu-sample", "1000",
+              "--configs", "cfg3,cfg5", "--gram-cells", "8192"])
+    for k in REQUIRED + ["roofline", "clocks", "parity", "configs"]:
         assert k in d, k
     assert d["n_gpus"] == 1 and d["steps"] == 5 and d["value"] > 1e7 and d["gpu_launches"] >= 5
     r = d["roofline"]
-    assert r["bound"] in ("hbm", "tensor") and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    if r["bound"] == "issue":
+        # the scoring kernel is bound by instruction issue: warp instructions per candidate come from the committed
+        # ncu counters, the HBM figures of SURVEY 8(d) ride along
+        assert r["unit"] == "Gwarp-inst/s" and r["warp_inst_per_candidate"] > 0 and r["traffic"] > 0
+        assert r["hbm"]["unit"] == "GB/s" and r["hbm"]["bytes_per_unit"] == 36
+    else:
+        assert r["bound"] == "hbm" and r["unit"] == "GB/s"
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
-    assert d["e2e"]["h2d_bytes_per_step"] == 200000 * 16 and d["e2e"]["d2h_bytes_per_step"] >= 200000 * 4
-    assert d["parity"]["max_rel_err_ei_fp64"] < 1e-6 and d["parity"]["h_star_equal"]
+    # NB pools travel as 8-byte wire records; the 16-byte form is measured beside them
+    assert d["e2e"]["h2d_bytes_per_step"] == 1000000 * 8 and d["e2e"]["d2h_bytes_per_step"] >= 1000000 * 4
+    assert d["e2e"]["full_records"]["h2d_bytes_per_step"] == 1000000 * 16
+    assert d["parity"]["max_rel_err_ei_fp64"] < 1e-6 and d["parity"]["h_star_equal"] and d["parity"]["ok"]
+    c3, c5 = d["configs"]["cfg3"], d["configs"]["cfg5"]
+    assert c3["parity"]["ok"] and c3["scaling"] == "strong" and c3["roofline"]["bound"] in ("issue", "hbm")
+    assert c5["parity"]["ok"] and c5["roofline"]["bound"] == "tensor"

@@ -88,6 +88,91 @@ def test_packed_kernel_matches_first_generation_and_oracle(eng, fam, h):
     np.testing.assert_array_equal(eis.reshape(-1), s.cpu().numpy())
 
 
+
+# ---------------------------------------------------------------------------- histogram intersection, item form
+@pytest.mark.parametrize("fam,h", [(0, 0), (0, 2), (0, 3), (1, 1), (1, 5), (2, 1), (2, 3)])
+def test_oa_item_form_matches_general_path_and_oracle(eng, fam, h, monkeypatch):
+    """oa=True on the packed path (rank-1 chains + exception items, nbw_model.oa_exc) against the general G path of
+    the first-generation kernel ((node, level)^2 gathers over thermometer columns) and against the oracle."""
+    from nasbowl_b200.bayesopt import GraphExpectedImprovement
+    monkeypatch.setenv("NBW_OA_FORM", "items")         # also where the default would pick the general path
+    from nasbowl_b200.kernels import WeisfilerLehman
+    n, M = 100, 20_003
+    train = synth.generate_cells_host(fam, 9, 0, n)
+    y = np.random.RandomState(fam * 7 + h).randn(n)
+    gp = _gp(train, y, [WeisfilerLehman(h=h, oa=True)], n_max=train.n_max)
+    gp.fit(wl_subtree_candidates=(h,), optimize_lik=False)
+    pool = eng.generate_cells(fam, 31, 5000, M)
+    acq = GraphExpectedImprovement(gp)
+    pm = gp._score_state()
+    assert pm.oa_exc is not None and pm.total_labels > pm.n_labels
+    assert eng.fused_topk_ok(acq._model(), 5)
+    s, mu, var, s64 = [t.clone() for t in acq.score_pool(pool, want64=True)]
+    s_l, mu_l, var_l, s64_l = _legacy(lambda: [t.clone() for t in acq.score_pool(pool, want64=True)])
+    np.testing.assert_allclose(mu.cpu().numpy(), mu_l.cpu().numpy(), rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(var.cpu().numpy(), var_l.cpu().numpy(), rtol=1e-8, atol=1e-12)
+    if train.n_max == 8:
+        os.environ["NBW_SCORE_LANES"] = "1"
+        try:
+            _, mu_n, var_n, _ = [t.clone() for t in acq.score_pool(pool, want64=True)]
+        finally:
+            os.environ.pop("NBW_SCORE_LANES", None)
+        np.testing.assert_allclose(mu.cpu().numpy(), mu_n.cpu().numpy(), rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(var.cpu().numpy(), var_n.cpu().numpy(), rtol=1e-9, atol=1e-13)
+    sub = CellBatch.from_records(pool[:1200].cpu().numpy(), train.n_max)
+    st = gp_oracle.gp_fit(train, y, h_candidates=(h,), oa=True, optimize_lik=False)
+    mu_o, var_o = gp_oracle.gp_predict_diag(st, train, sub)
+    np.testing.assert_allclose(mu.cpu().numpy()[:1200], mu_o, rtol=RTOL64, atol=1e-9)
+    np.testing.assert_allclose(var.cpu().numpy()[:1200], var_o, rtol=RTOL64, atol=1e-12)
+    for cut in (1, 4097):
+        a = acq.score_pool(pool[:cut].contiguous())[0].clone()
+        b = acq.score_pool(pool[cut:].contiguous())[0].clone()
+        assert torch.equal(torch.cat([a, b]), s)
+    xs, eis, idx = acq.propose_location(pool, top_n=5)
+    ref = gp_oracle.top_n_distinct(s.cpu().numpy(), 5)
+    assert set(int(i) for i in idx) == set(int(i) for i in ref)
+
+
+def test_oa_item_form_on_cells_with_many_twins(eng):
+    """Hand-made cells whose nodes repeat labels at every level (twins keep rank > 1 down the whole chain), counts
+    above the training maximum, labels outside the dictionary."""
+    from nasbowl_b200.kernels import WeisfilerLehman
+    rng = np.random.RandomState(0)
+
+    def cells(N, ops):
+        labels = np.full((N, 8), NO_NODE, dtype=np.uint8)
+        succ = np.zeros((N, 8), dtype=np.uint16)
+        for i in range(N):
+            k = rng.randint(3, 9)
+            labels[i, :k] = rng.choice(ops, size=k)
+            for u in range(k - 1):
+                # many nodes feed the LAST node only: same op + same successors = twins at every level
+                if rng.rand() < 0.7:
+                    succ[i, u] |= 1 << (k - 1)
+                if rng.rand() < 0.3 and u + 1 < k - 1:
+                    succ[i, u] |= 1 << rng.randint(u + 1, k - 1)
+        return CellBatch(8, labels, succ)
+
+    train = cells(60, [1, 2])
+    pool = cells(4000, [1, 2, 3])            # op 3 never seen; pools with up to 7 twins (training max is lower)
+    y = rng.randn(60)
+    for h in (1, 3):
+        gp = _gp(train, y, [WeisfilerLehman(h=h, oa=True)], n_max=8)
+        gp.fit(wl_subtree_candidates=(h,), optimize_lik=False)
+        mu, var = gp.predict_diag(pool)
+        st = gp_oracle.gp_fit(train, y, h_candidates=(h,), oa=True, optimize_lik=False)
+        mu_o, var_o = gp_oracle.gp_predict_diag(st, train, pool)
+        np.testing.assert_allclose(mu.numpy(), mu_o, rtol=RTOL64, atol=1e-9)
+        np.testing.assert_allclose(var.numpy(), var_o, rtol=RTOL64, atol=1e-12)
+        os.environ["NBW_SCORE_LANES"] = "1"
+        try:
+            mu_n, var_n = gp.predict_diag(pool)
+        finally:
+            os.environ.pop("NBW_SCORE_LANES", None)
+        np.testing.assert_allclose(mu.numpy(), mu_n.numpy(), rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(var.numpy(), var_n.numpy(), rtol=1e-9, atol=1e-13)
+
+
 def test_packing_edge_cases(eng):
     """Cells of 1..8 nodes in every order, empty records, isolated nodes, pools of 1..40 cells."""
     from nasbowl_b200.bayesopt import GraphExpectedImprovement

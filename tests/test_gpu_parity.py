@@ -253,7 +253,7 @@ def test_gp_fit_predict_acquisitions(family, oa, opt):
     # the prefix form (H over node pairs, linear kernel) and the general form (G over
     # (node, level) pairs) are two evaluation orders of the same quadratic form
     pm = gp._score_state()
-    assert (pm.H is not None) == (not oa)
+    assert (pm.H is not None) != (oa and pm.oa_exc is None)     # oa: item form (chains + exceptions) or general G
     pm.use_prefix = False
     mu_g, var_g = gp.predict_diag(pool)
     pm.use_prefix = True
