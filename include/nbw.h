@@ -302,7 +302,7 @@ typedef struct {
    * classes inside the cell (needed for k_cc) are refined exactly from the previous classes. */
   const int32_t* child;                  /* stacked [T]: level-(l-1) label -> its only level-l label */
   int32_t first_stable;                  /* levels l >= first_stable (>= 3) take the fast path; 0 = none */
-  int32_t reserved0;
+  int32_t oa_d2_base;                    /* oa item form: first stacked index of the rank-2 chain items (0 = none), see oa_exc */
   double lik, y_mean, y_std, incumbent, xi, beta;
   /* ---- packed scoring path (csrc/score_packed.cu; optional: bucket_tags[1] == NULL keeps the first-generation
    * kernel).  Same dictionaries in a branch-free form:
@@ -341,7 +341,11 @@ typedef struct {
    * H / w_mu_prefix then span n_labels = T + X stacked items: the T chain items (label_off) followed by the
    * exception items, and the posterior is the same sum over item pairs.
    * oa_exc[label_off[l] + id] = (stacked index of e(label, 2)) << 5 | max training count (<= 16); the item of rank r
-   * is that index + min(r, max + 1) - 2.  Single part only. */
+   * is that index + min(r, max + 1) - 2.  Single part only.
+   * Twins — two nodes with the same label at every level — are the common case, and a node whose rank is 2 at level 0
+   * has rank 2 at every level it has an exception at (ranks do not grow): when oa_d2_base != 0 such a node carries ONE
+   * item instead, oa_d2_base + (stacked label at its last exception level) = the sum of e(., 2) along that label's
+   * ancestor chain. */
   const uint32_t* oa_exc;
   const void* next;                      /* const nbw_model* of the next part (host memory) */
 } nbw_model;

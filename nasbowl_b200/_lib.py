@@ -52,7 +52,7 @@ class Model(C.Structure):
         ("G", C.c_void_p), ("w_mu", C.c_void_p),
         ("n_labels", C.c_int32), ("ld_h", C.c_int32),
         ("H", C.c_void_p), ("w_mu_prefix", C.c_void_p),
-        ("child", C.c_void_p), ("first_stable", C.c_int32), ("reserved0", C.c_int32),
+        ("child", C.c_void_p), ("first_stable", C.c_int32), ("oa_d2_base", C.c_int32),
         ("lik", C.c_double), ("y_mean", C.c_double), ("y_std", C.c_double),
         ("incumbent", C.c_double), ("xi", C.c_double), ("beta", C.c_double),
         # packed scoring path (csrc/score_packed.cu)

@@ -698,22 +698,28 @@ class GraphGP:
             lo_a, co_a = np.asarray(lo, dtype=np.int64), np.asarray(co, dtype=np.int64)
             col1 = co_a[level_of] + tb
             X = int(mc.sum())
-            S = Tl + X
-            Kc = max(h + 1, 2)
+            # rank-2 chain items (nbw_model.oa_d2_base): one per label, as long as the operator stays L2-sized
+            twins = (2 * Tl + X + 1) ** 2 * 8 <= 96 << 20 and not os.environ.get("NBW_OA_NO_TWINS")
+            S = Tl + X + (Tl if twins else 0)
+            Kc = 2 * (h + 1)
             SKIP = 0x7FFFFFFF
             idx = np.full((S, Kc), SKIP, dtype=np.int64)
             cur, lev = np.arange(Tl), level_of.copy()
             for k in range(h + 1):
                 alive = lev >= 0
                 idx[:Tl][alive, k] = col1[cur[alive]]
+                if twins:       # sum over the chain of e(a, 2) = column (a, 2) [if seen twice in a training cell] - column (a, 1)
+                    a = cur[alive]
+                    idx[Tl + X:][alive, 2 * k] = np.where(mc[a] >= 2, col1[a] + 1, SKIP)
+                    idx[Tl + X:][alive, 2 * k + 1] = ~col1[a]
                 up = alive & (lev > 0)
                 cur[up] = lo_a[lev[up] - 1] + par[cur[up]]
                 lev = np.where(up, lev - 1, -1)
             first_exc = Tl + np.cumsum(mc) - mc                      # item of e(label, 2)
             lab = np.repeat(np.arange(Tl), mc)                       # label of every exception item
             r = np.arange(X) - (first_exc[lab] - Tl) + 2             # its rank (2 .. max + 1)
-            idx[Tl:, 0] = np.where(r <= mc[lab], col1[lab] + r - 1, SKIP)
-            idx[Tl:, 1] = ~col1[lab]
+            idx[Tl:Tl + X, 0] = np.where(r <= mc[lab], col1[lab] + r - 1, SKIP)
+            idx[Tl:Tl + X, 1] = ~col1[lab]
             Bs = torch.zeros((n, S + 1), dtype=torch.float64, device=eng.device)
             eng.combine_columns(B, torch.from_numpy(idx.astype(np.int32)).to(eng.device), Bs, S + 1)
             Wp = eng.empty((n, S + 1), torch.float64)
@@ -725,6 +731,7 @@ class GraphGP:
             first.H, first.w_mu_prefix, first.total_labels = H, w_mu_p, S
             exc = (first_exc << 5) | np.minimum(mc, 31)
             first.oa_exc = torch.from_numpy(exc.astype(np.uint32).view(np.int32)).to(eng.device)
+            first.oa_d2_base = Tl + X if twins else 0
         else:
             # prefix form (nbw_model.H): the operators summed over ancestor chains of labels, all parts
             # side by side: Bp [n, T + 1], last column zero (landing slot of labels outside the dictionary)

@@ -45,6 +45,7 @@ struct PartParams {
   const int32_t* final_label;
   const uint32_t* oa_exc;           // histogram intersection: (first exception item << 5 | max count) per label
   int32_t h, first_stable, undirected, rec_offset, label_base, compact;
+  int32_t oa_d2_base;               // histogram intersection: first rank-2 chain item (0 = none)
   uint8_t palette[8];
 };
 
@@ -287,12 +288,20 @@ score_packed_kernel(const __grid_constant__ PackedParams P, const uint8_t* __res
       if (present) kss = WEIGHTED ? (KccT)(Q.lw[0] * (OA ? 1 : cnt)) : (KccT)(OA ? 1 : cnt);
       int dp = in_dict ? Q.label_base + Q.loff[0] + (int)d0 : zero_slot;
       int ec = 0;                 // levels 0 .. ec-1 carry an exception item
+      // a node of rank 2 at level 0 keeps rank 2 wherever it has an exception: one chain item (nbw_model.oa_d2_base)
+      bool twin = false;
+      int twin_item = zero_slot;
       if constexpr (OA) {
         const int r0 = __popc(cls & ((1u << node) - 1u));
         int item = zero_slot;
         if (in_dict && r0 > 0) {
-          item = oa_item(__ldg(Q.oa_exc + Q.loff[0] + (int)d0), r0);
-          ec = 1;
+          twin = r0 == 1 && Q.oa_d2_base != 0;
+          if (twin) {
+            twin_item = Q.oa_d2_base + Q.loff[0] + (int)d0;
+          } else {
+            item = oa_item(__ldg(Q.oa_exc + Q.loff[0] + (int)d0), r0);
+            ec = 1;
+          }
         }
         exc_s[0][tid] = item;
       }
@@ -419,20 +428,44 @@ score_packed_kernel(const __grid_constant__ PackedParams P, const uint8_t* __res
           const int r0 = __popc(cls & ((1u << node) - 1u));
           int item = zero_slot;
           if (seen && r0 > 0) {
-            item = oa_item(__ldg(Q.oa_exc + Q.loff[l] + (int)dense), r0);
-            ec = l + 1;
+            if (twin) {
+              twin_item = Q.oa_d2_base + Q.loff[l] + (int)dense;
+            } else {
+              item = oa_item(__ldg(Q.oa_exc + Q.loff[l] + (int)dense), r0);
+              ec = l + 1;
+            }
           }
           exc_s[l][tid] = item;
         }
-        if (!OA && stable && l < h && !__any_sync(FULL, changed)) {
+        if (stable && l < h && !__any_sync(FULL, changed)) {
           // A stable level reproduced (classes, membership) for every cell of this warp: all deeper levels
           // apply the same map, so they reproduce it too; only the labels move down the child chain.
-          if (endpoint) kss += WEIGHTED ? (KccT)(Q.wsuf[l] * cnt) : (KccT)((h - l) * cnt);
+          if (endpoint) kss += WEIGHTED ? (KccT)(Q.wsuf[l] * (OA ? 1 : cnt)) : (KccT)((h - l) * (OA ? 1 : cnt));
+          if constexpr (OA) {
+            // ... and a node that is not the first of its class keeps its rank: one exception item per deeper level
+            const int r0 = __popc(cls & ((1u << node) - 1u));
+            if (seen && r0 > 0) {
+              if (twin) {
+                twin_item = Q.oa_d2_base + __ldg(Q.final_label + Q.loff[l] + (int)dense) - Q.label_base;
+              } else {
+                uint32_t dn = dense;
+                for (int l2 = l + 1; l2 <= h; ++l2) {
+                  dn = (uint32_t)__ldg(Q.child + Q.loff[l2 - 1] + (int)dn);
+                  exc_s[l2][tid] = oa_item(__ldg(Q.oa_exc + Q.loff[l2] + (int)dn), r0);
+                }
+                ec = h + 1;
+              }
+            }
+          }
           if (seen) dp = __ldg(Q.final_label + Q.loff[l] + (int)dense);
           break;
         }
       }
       deep[p] = dp;
+      if (OA && twin) {
+        exc_s[0][tid] = twin_item;
+        ec = 1;
+      }
       n_exc = ec;
       kacc += kss;
     }
@@ -641,7 +674,7 @@ __device__ __forceinline__ uint32_t eq_bits8(uint64_t w, uint32_t byte) {
 }
 
 template <int NP, bool WEIGHTED, bool TOPK, bool OA = false>
-__global__ void __launch_bounds__(kCellThreads)
+__global__ void __launch_bounds__(kCellThreads, OA ? 6 : 0)
 score_cell_kernel(const __grid_constant__ PackedParams P, const uint8_t* __restrict__ cells, int64_t n_cells,
                   float* __restrict__ scores, double* __restrict__ mu64, double* __restrict__ var64,
                   double* __restrict__ score64, NbwCand* __restrict__ block_cands, int k_top, int distinct,
@@ -650,8 +683,9 @@ score_cell_kernel(const __grid_constant__ PackedParams P, const uint8_t* __restr
   using KccT = typename std::conditional<WEIGHTED, double, int>::type;
   static_assert(!OA || NP == 1, "the packed histogram-intersection path takes one kernel");
   // histogram intersection: the exception items of this thread's cell (nbw_model.oa_exc), at most one per node and
-  // level, one column per thread: [8 * (h + 1)][kCellThreads] ints of dynamic shared memory
-  extern __shared__ int exs[];
+  // level.  Dynamically indexed, so the list lives in local memory (L1-resident, interleaved across the warp):
+  // shared memory would cost the resident CTAs these latency-bound gathers need.
+  int exs[OA ? 7 * NBW_MAX_LEVELS : 1];
   __shared__ uint4 ent[8][kCellThreads];     // per node: {ha_lo, ha_hi, hb, class count field}
   __shared__ float sh_tv[TOPK ? kTopMax : 1][kCellThreads];
   __shared__ int sh_ti[TOPK ? kTopMax : 1][kCellThreads];
@@ -737,13 +771,22 @@ score_cell_kernel(const __grid_constant__ PackedParams P, const uint8_t* __restr
       const int cnt0 = OA ? __popc(pm) : __popcll(clsw);
       KccT kss = WEIGHTED ? (KccT)(Q.lw[0] * cnt0) : (KccT)cnt0;
       // exception items of the current level: nodes in the dictionary that are not the first of their class
+      // a node of rank 2 at level 0 keeps rank 2 wherever it has an exception: it carries ONE chain item, named after
+      // its label at the last such level (nbw_model.oa_d2_base)
+      uint32_t twins = 0;
+      int twin_item[8];
       auto emit_exceptions = [&](int l) {
 #pragma unroll
         for (int v = 1; v < 8; ++v) {
           const int r0 = __popc((uint32_t)(clsw >> (8 * v)) & ((1u << v) - 1u));
           if (((im >> v) & 1u) && r0 > 0) {
-            exs[ne * kCellThreads + tid] = oa_item(__ldg(Q.oa_exc + Q.loff[l] + (int)dense[v]), r0);
-            ++ne;
+            if (l == 0 && r0 == 1 && Q.oa_d2_base != 0) twins |= 1u << v;
+            if ((twins >> v) & 1u) {
+              twin_item[v] = Q.oa_d2_base + Q.loff[l] + (int)dense[v];
+            } else {
+              exs[ne] = oa_item(__ldg(Q.oa_exc + Q.loff[l] + (int)dense[v]), r0);
+              ++ne;
+            }
           }
         }
       };
@@ -848,15 +891,42 @@ score_cell_kernel(const __grid_constant__ PackedParams P, const uint8_t* __restr
         const int cnt = OA ? __popc(em) : __popcll(clsw);
         kss += WEIGHTED ? (KccT)(Q.lw[l] * cnt) : (KccT)cnt;
         if constexpr (OA) emit_exceptions(l);
-        if (!OA && stable && l < h && !changed) {
+        if (stable && l < h && !changed) {
           // this cell reproduced (classes, membership) at a stable level: every deeper level will too; only the
           // labels move down the child chain (nbw_model.final_label)
           kss += WEIGHTED ? (KccT)(Q.wsuf[l] * cnt) : (KccT)((h - l) * cnt);
+          if constexpr (OA) {
+            // ... and a node that is not the first of its class keeps its rank: one exception item per deeper level
+#pragma unroll
+            for (int v = 1; v < 8; ++v) {
+              const int r0 = __popc((uint32_t)(clsw >> (8 * v)) & ((1u << v) - 1u));
+              if (((im >> v) & 1u) && r0 > 0) {
+                if ((twins >> v) & 1u) {
+                  twin_item[v] = Q.oa_d2_base + __ldg(Q.final_label + Q.loff[l] + (int)dense[v]) - Q.label_base;
+                } else {
+                  uint32_t dn = dense[v];
+                  for (int l2 = l + 1; l2 <= h; ++l2) {
+                    dn = (uint32_t)__ldg(Q.child + Q.loff[l2 - 1] + (int)dn);
+                    exs[ne] = oa_item(__ldg(Q.oa_exc + Q.loff[l2] + (int)dn), r0);
+                    ++ne;
+                  }
+                }
+              }
+            }
+          }
 #pragma unroll
           for (int v = 0; v < 8; ++v)
             if ((im >> v) & 1u) dp[v] = __ldg(Q.final_label + Q.loff[l] + (int)dense[v]);
           break;
         }
+      }
+      if constexpr (OA) {
+#pragma unroll
+        for (int v = 1; v < 8; ++v)
+          if ((twins >> v) & 1u) {
+            exs[ne] = twin_item[v];
+            ++ne;
+          }
       }
       kacc += kss;
     }
@@ -885,7 +955,7 @@ score_cell_kernel(const __grid_constant__ PackedParams P, const uint8_t* __restr
       }
     if constexpr (OA) {
       for (int a = 0; a < ne; ++a) {
-        const int xa = exs[a * kCellThreads + tid];
+        const int xa = exs[a];
         mu_acc += __ldg(P.w_mu + xa);
         const double* __restrict__ hrow = H + (int64_t)xa * ldh;
         double acc = 0.0;
@@ -894,7 +964,7 @@ score_cell_kernel(const __grid_constant__ PackedParams P, const uint8_t* __restr
           const int du = deep[0][u];
           if (du != zero_slot) acc += __ldg(hrow + du);
         }
-        for (int b = a + 1; b < ne; ++b) acc += __ldg(hrow + exs[b * kCellThreads + tid]);
+        for (int b = a + 1; b < ne; ++b) acc += __ldg(hrow + exs[b]);
         q_acc += 2.0 * acc + __ldg(hrow + xa);
       }
     }
@@ -1058,6 +1128,7 @@ int fill_part(nbw_ctx* ctx, const nbw_model* M, PartParams& Q) {
   Q.child = M->child;
   Q.final_label = M->final_label;
   Q.oa_exc = M->oa_exc;
+  Q.oa_d2_base = M->oa_d2_base;
   double suffix = 0.0;
   for (int l = M->h; l >= 0; --l) {
     Q.lw[l] = M->weighted ? M->level_weight[l] : 1.0;
@@ -1139,17 +1210,7 @@ int launch_cell_variant(nbw_ctx* ctx, int variant, const PackedParams& P, const 
                         double* mu64, double* var64, double* score64, int k, int distinct, int64_t index_base,
                         NbwCand* out_cands, cudaStream_t st) {
   auto kern = score_cell_kernel<NP, WEIGHTED, TOPK, OA>;
-  // histogram intersection: one exception slot per node and level (the occupancy is queried for the deepest model)
-  constexpr size_t kExcMax = OA ? sizeof(int) * 8 * NBW_MAX_LEVELS * kCellThreads : 0;
-  const size_t dyn = OA ? sizeof(int) * 8 * (size_t)(P.part[0].h + 1) * kCellThreads : 0;
-  if (OA) {
-    // the exception columns depend on the model's depth: attribute once, occupancy per launch (a host-side formula)
-    if (!ctx->packed_occ[variant]) NBW_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kExcMax));
-    int occ = 0;
-    NBW_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kCellThreads, dyn));
-    NBW_REQUIRE(ctx, occ >= 1, "score_cell_kernel does not fit this device");
-    ctx->packed_occ[variant] = occ;
-  } else if (!ctx->packed_occ[variant]) {
+  if (!ctx->packed_occ[variant]) {
     int occ = 0;
     NBW_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kCellThreads, 0));
     NBW_REQUIRE(ctx, occ >= 1, "score_cell_kernel does not fit this device");
@@ -1178,7 +1239,7 @@ int launch_cell_variant(nbw_ctx* ctx, int variant, const PackedParams& P, const 
     NBW_REQUIRE(ctx, (size_t)grid * kTopMax * sizeof(NbwCand) <= slot_bytes, "too many CTAs for the top-n block lists");
   }
   if (ctx->prof_ev[0]) NBW_CUDA(ctx, cudaEventRecord(ctx->prof_ev[0], st));
-  kern<<<(unsigned)grid, kCellThreads, dyn, st>>>(P, cells, n, scores, mu64, var64, score64, blocks, k, distinct, index_base);
+  kern<<<(unsigned)grid, kCellThreads, 0, st>>>(P, cells, n, scores, mu64, var64, score64, blocks, k, distinct, index_base);
   NBW_CHECK_LAUNCH(ctx);
   if (ctx->prof_ev[1]) NBW_CUDA(ctx, cudaEventRecord(ctx->prof_ev[1], st));
   if (TOPK) {

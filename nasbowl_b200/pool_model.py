@@ -19,7 +19,7 @@ ACQ = {"EI": 0, "AEI": 1, "UCB": 2, "MEAN": 3}
 
 _SCALARS = ("n_max", "h", "oa", "seed", "masks", "bucket_masks", "col_off", "label_off", "n_features", "n_labels",
             "first_stable", "use_prefix", "lik", "y_mean", "y_std", "incumbent", "incumbent_idx", "slot", "n_slots",
-            "undirected", "level_weight", "label_base", "total_labels")
+            "undirected", "level_weight", "label_base", "total_labels", "oa_d2_base")
 
 
 class PoolModel:
@@ -55,6 +55,7 @@ class PoolModel:
         self.w_mu_prefix: Optional[torch.Tensor] = None      # fp64 [T + 1]
         self.child: Optional[torch.Tensor] = None            # int32 [T_part]: label -> its only child label (stable levels)
         self.final_label: Optional[torch.Tensor] = None      # int32 [T_part]: stable label -> global index of its level-h descendant
+        self.oa_d2_base = 0                                  # oa item form: first rank-2 chain item (0 = none)
         self.oa_exc: Optional[torch.Tensor] = None           # oa item form: int32 [T] (first exception item << 5 | max count)
         self.first_stable = 0                                # first WL level on the stable fast path (0 = none)
         self.use_prefix = True                               # False forces the general G path
@@ -201,6 +202,7 @@ class PoolModel:
             d.n_labels = self.total_labels or self.n_labels
             if self.oa:
                 d.oa_exc = self.oa_exc.data_ptr()
+                d.oa_d2_base = int(self.oa_d2_base)
         d.rec_stride = self.n_slots * rec
         d.lik, d.y_mean, d.y_std = float(self.lik), float(self.y_mean), float(self.y_std)
         d.incumbent = float(self.incumbent if incumbent is None else incumbent)

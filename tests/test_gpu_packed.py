@@ -156,9 +156,16 @@ def test_oa_item_form_on_cells_with_many_twins(eng):
     train = cells(60, [1, 2])
     pool = cells(4000, [1, 2, 3])            # op 3 never seen; pools with up to 7 twins (training max is lower)
     y = rng.randn(60)
-    for h in (1, 3):
-        gp = _gp(train, y, [WeisfilerLehman(h=h, oa=True)], n_max=8)
-        gp.fit(wl_subtree_candidates=(h,), optimize_lik=False)
+    for h, no_twins in ((1, False), (3, False), (3, True)):
+        # rank-2 chain items (nbw_model.oa_d2_base) on and off: two ways of writing the same item sums
+        if no_twins:
+            os.environ["NBW_OA_NO_TWINS"] = "1"
+        try:
+            gp = _gp(train, y, [WeisfilerLehman(h=h, oa=True)], n_max=8)
+            gp.fit(wl_subtree_candidates=(h,), optimize_lik=False)
+            assert (gp._score_state().oa_d2_base == 0) == no_twins
+        finally:
+            os.environ.pop("NBW_OA_NO_TWINS", None)
         mu, var = gp.predict_diag(pool)
         st = gp_oracle.gp_fit(train, y, h_candidates=(h,), oa=True, optimize_lik=False)
         mu_o, var_o = gp_oracle.gp_predict_diag(st, train, pool)
