@@ -171,6 +171,16 @@ int nbw_sym_mirror(nbw_ctx* ctx, void* C, int64_t n, int64_t ldc, int elem_bytes
  *     products of GraphGP.fit / predict (bayesopt/gp.py:173-219, 271-276).
  * All matrices are row-major fp64 with explicit leading dimensions.
  */
+/* The Gram of every single WL level of a SMALL training set in one launch (VertexHistogram._calculate_kernel_matrix,
+ * vertex_histogram.py:243, per level — what the depth grid search of GraphGP.fit, bayesopt/gp.py:493-538, consumes):
+ * out[l][i][j] = sum over the feature columns [col_off[l], col_off[l+1]) of phi[i][k] * phi[j][k], exact int32.
+ * phi: [n x ld_phi] int8 (ld_phi and the column offsets multiples of 128, as nbw_hist_dense_i8 lays them out),
+ * col_off: DEVICE int32 [n_levels + 1], out: n_levels matrices of ld_out columns, level_stride elements apart.
+ * SIMT (dp4a); meant for n up to a few hundred, where one tensor-core launch per level costs more than the arithmetic.
+ * Enqueues only. */
+int nbw_level_grams_i32(nbw_ctx* ctx, const int8_t* phi, int64_t n, int64_t ld_phi, const int32_t* col_off,
+                        int n_levels, int32_t* out, int64_t ld_out, int64_t level_stride, void* stream);
+
 /* out[i,j] = beta*out[i,j] + w * K[i,j] (int32 -> fp64 accumulate): the level sum with
  * layer_weights of weisfeiler_lehman.py:316-327 when the levels are weighted separately */
 int nbw_gram_accumulate(nbw_ctx* ctx, const int32_t* K, int64_t ldk, int64_t m, int64_t n,

@@ -109,6 +109,7 @@ _PROTOTYPES = {
                                          C.POINTER(C.c_double), _vp]),
     "nbw_scale_features": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _f64, _vp, _i64, _vp]),
     "nbw_label_parents": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    "nbw_level_grams_i32": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i32, _vp, _i64, _i64, _vp]),
     "nbw_combine_columns": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i64, _i32, _vp, _i64, _vp]),
     "nbw_prefix_features": (C.c_int, [_vp, _vp, _i64, _i64, _i32, C.POINTER(_i64), C.POINTER(_i64), _vp, _vp,
                                       _i64, _vp]),

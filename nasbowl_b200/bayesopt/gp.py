@@ -445,7 +445,8 @@ class GraphGP:
                     with torch.no_grad():
                         K, inv_sqrt_diag = build_K()
                     factor_cache.clear()
-                _, Linv_i, alpha_i, logdet, yKy, trKinv, alpha_sq = factor(float(likelihood.item()))
+                lam_i = float(likelihood.item())
+                _, Linv_i, alpha_i, logdet, yKy, trKinv, alpha_sq = factor(lam_i)
                 nlml = _nlml_from_stats(logdet, yKy, self.n)
                 if levels is not None:
                     # the gradient form is linear in the raw Gram: one value per (kernel, level) Gram
@@ -486,6 +487,13 @@ class GraphGP:
                         likelihood.clamp_(1e-5, max_lik)
                     if layer_weights is not None:
                         layer_weights.clamp_(0., 1.)
+                # Only the noise is trained and it sits on the clamp: its gradient is negative for every K (Q9), so
+                # Adam's first moment never changes sign, every further step pushes against the same clamp and every
+                # further iteration re-evaluates the same (memoised) factorisation — the loop's result is final.
+                if (light and optimizer.lower() == 'adam' and optimize_lik and levels is None and not self.verbose
+                        and lam_i == float(np.float32(max_lik)) and float(likelihood.item()) == lam_i
+                        and float(likelihood.grad) < 0.0):
+                    break
             weights = weights.detach()
         if layer_weights is not None:
             layer_weights = layer_weights.detach()

@@ -305,6 +305,101 @@ __global__ void assign_ids_kernel(const uint64_t* __restrict__ sk, const uint32_
   }
 }
 
+// Small inputs, all of it in ONE launch: the single-CTA sort above, then head flags, their block-wide exclusive scan,
+// the ids, the dictionary and the credential check, without leaving shared memory (a training set's level used to be
+// sort + heads + three scan launches + assign: six launches of near-empty kernels).
+__global__ void __launch_bounds__(1024)
+small_dict_kernel(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ chks, int n, int n_pad,
+                  const uint8_t* __restrict__ cells, int n_max, const uint32_t* __restrict__ ids_prev,
+                  uint32_t* __restrict__ ids, uint64_t* __restrict__ uniq_keys, uint64_t* __restrict__ uniq_chks, int64_t cap,
+                  DictCounters* __restrict__ counters, uint8_t* __restrict__ first_flag) {
+  extern __shared__ uint64_t sk[];
+  uint32_t* sv = reinterpret_cast<uint32_t*>(sk + n_pad);
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t collided;
+  const int tid = threadIdx.x;
+  if (tid == 0) collided = 0u;
+  for (int i = tid; i < n_pad; i += 1024) {
+    sk[i] = i < n ? keys[i] : ~0ull;
+    sv[i] = (uint32_t)i;
+  }
+  __syncthreads();
+  for (int k = 2; k <= n_pad; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = tid; t < (n_pad >> 1); t += 1024) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int l = i | j;
+        const uint64_t ka = sk[i], kb = sk[l];
+        const uint32_t va = sv[i], vb = sv[l];
+        const bool gt = ka > kb || (ka == kb && va > vb);
+        if (gt == ((i & k) == 0)) {
+          sk[i] = kb; sk[l] = ka;
+          sv[i] = vb; sv[l] = va;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // heads of runs inside this thread's contiguous chunk, then an exclusive scan of the chunk counts over the block
+  const int chunk = (n_pad + 1023) / 1024;
+  const int lo = tid * chunk, hi = min(lo + chunk, n);
+  uint32_t mine = 0;
+  for (int i = lo; i < hi; ++i) {
+    const uint64_t k = sk[i];
+    mine += (k != NBW_INVALID_KEY && (i == 0 || sk[i - 1] != k)) ? 1u : 0u;
+  }
+  uint32_t incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((tid & 31) >= o) incl += t;
+  }
+  if ((tid & 31) == 31) warp_sums[tid >> 5] = incl;
+  __syncthreads();
+  if (tid < 32) {
+    uint32_t w = warp_sums[tid];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, w, o);
+      if (tid >= o) w += t;
+    }
+    warp_sums[tid] = w;       // inclusive over warps
+  }
+  __syncthreads();
+  uint32_t rank = incl - mine + ((tid >> 5) ? warp_sums[(tid >> 5) - 1] : 0u);    // heads before this chunk
+  if (tid == 1023) counters->n_unique = warp_sums[31];
+  bool bad = false;
+  for (int i = lo; i < hi; ++i) {
+    const uint64_t k = sk[i];
+    const uint32_t src = sv[i];
+    if (k == NBW_INVALID_KEY) {
+      ids[src] = NBW_INVALID_ID;
+      if (first_flag) first_flag[src] = 0;
+      continue;
+    }
+    const bool head = i == 0 || sk[i - 1] != k;
+    rank += head ? 1u : 0u;
+    const uint32_t id = rank - 1u;
+    ids[src] = id;
+    if (first_flag) first_flag[src] = head ? 1 : 0;     // (key, index) order: the head of a run is the first occurrence
+    if (head) {
+      if ((int64_t)id < cap) {
+        uniq_keys[id] = k;
+        uniq_chks[id] = chks[src];
+      }
+    } else {
+      const uint32_t prev = sv[i - 1];
+      bool ok = chks[src] == chks[prev];
+      if (ok && cells != nullptr && ids_prev != nullptr)
+        ok = (n_max == 8) ? same_credential<8>(cells, ids_prev, prev, src) : same_credential<16>(cells, ids_prev, prev, src);
+      bad = bad || !ok;
+    }
+  }
+  if (bad) atomicOr(&collided, 1u);
+  __syncthreads();
+  if (tid == 0) counters->collision = collided;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------- hash pre-dedup for large key counts
@@ -568,15 +663,15 @@ int nbw_dict_build_enqueue(nbw_ctx* ctx, const uint64_t* keys, const uint64_t* c
     int n_pad = 2;
     while (n_pad < n_keys) n_pad <<= 1;
     const size_t smem = (size_t)n_pad * (sizeof(uint64_t) + sizeof(uint32_t));
-    if (!(ctx->attr_set & NBW_ATTR_SMALL_SORT)) {
-      NBW_CUDA(ctx, cudaFuncSetAttribute(small_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (!(ctx->attr_set & NBW_ATTR_SMALL_DICT)) {
+      NBW_CUDA(ctx, cudaFuncSetAttribute(small_dict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          kSmallSortMax * (int)(sizeof(uint64_t) + sizeof(uint32_t))));
-      ctx->attr_set |= NBW_ATTR_SMALL_SORT;
+      ctx->attr_set |= NBW_ATTR_SMALL_DICT;
     }
-    small_sort_kernel<<<1, 1024, smem, st>>>(keys, (int)n_keys, n_pad, kbuf[0], vbuf[0]);
+    small_dict_kernel<<<1, 1024, smem, st>>>(keys, chks, (int)n_keys, n_pad, static_cast<const uint8_t*>(cells), n_max, ids_prev,
+                                             ids, uniq_keys, uniq_chks, uniq_cap, counters, first_flag);
     NBW_CHECK_LAUNCH(ctx);
-    kin = kbuf[0];
-    vin = vbuf[0];
+    return NBW_OK;
   }
   for (int shift = 0; !small && shift < key_bits; shift += 8) {
     radix_count_kernel<<<n_tiles, kSortThreads, 0, st>>>(kin, n_keys, shift, n_tiles, counts);

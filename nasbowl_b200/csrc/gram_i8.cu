@@ -808,3 +808,67 @@ extern "C" int nbw_gram_i8(nbw_ctx* ctx, const int8_t* A, int64_t m, int64_t lda
   NBW_CHECK_LAUNCH(ctx);
   return NBW_OK;
 }
+
+// ====================================================================== per-level Grams of a small training set
+// The grid search over the WL depth (bayesopt/gp.py:493-538) needs the Gram of every single level of the training
+// set (vertex_histogram.py:243, one level at a time).  For a few hundred cells that is microseconds of arithmetic:
+// one SIMT launch (dp4a, exact like the tensor-core path) computes all levels — the upper triangle of 32 x 32 tiles,
+// mirrored on store — instead of one TMA descriptor + persistent tensor-core launch per level.
+namespace {
+constexpr int kLgTile = 32;
+__global__ void __launch_bounds__(256)
+level_grams_small_kernel(const int8_t* __restrict__ phi, int64_t ld_phi, int n, const int32_t* __restrict__ col_off,
+                         int32_t* __restrict__ out, int64_t ld_out, int64_t level_stride, int tiles) {
+  __shared__ uint32_t As[kLgTile][36], Bs[kLgTile][36];      // 128 bytes of K per row (+ padding against bank conflicts)
+  const int level = blockIdx.y;
+  // upper-triangle tile index -> (ti, tj), ti <= tj
+  int t = blockIdx.x, ti = 0;
+  while (t >= tiles - ti) { t -= tiles - ti; ++ti; }
+  const int tj = ti + t;
+  const int tid = threadIdx.x;
+  const int row = tid >> 3, cg = tid & 7;                    // this thread: output row `row`, columns 4 cg .. 4 cg + 3
+  const int k0 = col_off[level], k1 = col_off[level + 1];    // multiples of 128
+  int acc[4] = {0, 0, 0, 0};
+  const int lr = tid >> 3, lw = (tid & 7) * 4;               // loader: row lr, words lw .. lw + 3 (16 bytes)
+  for (int k = k0; k < k1; k += 128) {
+    const int ra = ti * kLgTile + lr, rb = tj * kLgTile + lr;
+    uint4 va = make_uint4(0u, 0u, 0u, 0u), vb = va;
+    if (ra < n) va = *reinterpret_cast<const uint4*>(phi + (int64_t)ra * ld_phi + k + 4 * lw);
+    if (rb < n) vb = *reinterpret_cast<const uint4*>(phi + (int64_t)rb * ld_phi + k + 4 * lw);
+    As[lr][lw] = va.x; As[lr][lw + 1] = va.y; As[lr][lw + 2] = va.z; As[lr][lw + 3] = va.w;
+    Bs[lr][lw] = vb.x; Bs[lr][lw + 1] = vb.y; Bs[lr][lw + 2] = vb.z; Bs[lr][lw + 3] = vb.w;
+    __syncthreads();
+#pragma unroll 8
+    for (int w = 0; w < 32; ++w) {
+      const int a = (int)As[row][w];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[c] = __dp4a(a, (int)Bs[4 * cg + c][w], acc[c]);
+    }
+    __syncthreads();
+  }
+  int32_t* o = out + (int64_t)level * level_stride;
+  const int gi = ti * kLgTile + row;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int gj = tj * kLgTile + 4 * cg + c;
+    if (gi < n && gj < n) {
+      o[(int64_t)gi * ld_out + gj] = acc[c];
+      o[(int64_t)gj * ld_out + gi] = acc[c];
+    }
+  }
+}
+}  // namespace
+
+extern "C" int nbw_level_grams_i32(nbw_ctx* ctx, const int8_t* phi, int64_t n, int64_t ld_phi, const int32_t* col_off,
+                                   int n_levels, int32_t* out, int64_t ld_out, int64_t level_stride, void* stream) {
+  if (!ctx) return NBW_ERR_INVALID;
+  NbwRange range("nbw_level_grams_i32");
+  NBW_REQUIRE(ctx, n >= 1 && n <= 4096 && n_levels >= 1 && n_levels <= NBW_MAX_LEVELS, "bad n / n_levels");
+  NBW_REQUIRE(ctx, phi && col_off && out && ld_out >= n && level_stride >= n * ld_out && ld_phi % 16 == 0, "bad argument");
+  const int tiles = (int)((n + kLgTile - 1) / kLgTile);
+  dim3 grid((unsigned)(tiles * (tiles + 1) / 2), (unsigned)n_levels);
+  level_grams_small_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(phi, ld_phi, (int)n, col_off, out, ld_out,
+                                                                              level_stride, tiles);
+  NBW_CHECK_LAUNCH(ctx);
+  return NBW_OK;
+}

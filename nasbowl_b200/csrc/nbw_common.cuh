@@ -37,7 +37,7 @@ struct nbw_ctx {
   size_t topk_blocks_bytes;
   int topk_slot;
 };
-enum { NBW_ATTR_TRSV = 1u << 0, NBW_ATTR_SMALL_SORT = 1u << 1, NBW_ATTR_GRAM_SINGLE = 1u << 2, NBW_ATTR_FACTOR_NP = 1u << 3,
+enum { NBW_ATTR_TRSV = 1u << 0, NBW_ATTR_SMALL_SORT = 1u << 1, NBW_ATTR_GRAM_SINGLE = 1u << 2, NBW_ATTR_FACTOR_NP = 1u << 3, NBW_ATTR_SMALL_DICT = 1u << 4,
        NBW_ATTR_GRAM_PAIR = 1u << 8 /* << output mode: bits 8..11 */ };
 
 // NVTX range around a C-ABI entry point (visible in Nsight Systems / ncu --nvtx); header-only NVTX3,

@@ -7,6 +7,7 @@ behind the C-ABI; nothing in this module computes on the CPU or with torch opera
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence
 
@@ -399,6 +400,12 @@ class Engine:
         n = fit.n_cells
         ld = _round_up(n, 4)
         G = self.empty((hmax + 1, n, ld), torch.int32)
+        if n <= 512 and not os.environ.get("NBW_LEVEL_GRAMS_TC"):
+            # small training sets: all levels in one SIMT launch (nbw_level_grams_i32)
+            co = torch.tensor(fit.col_off[:hmax + 2], dtype=torch.int32).to(self.device, non_blocking=True)
+            self._check(self.lib.nbw_level_grams_i32(self.ctx, self._p(fit.phi), n, fit.phi.stride(0), self._p(co), hmax + 1,
+                                                     self._p(G), ld, n * ld, self.stream))
+            return G
         for l in range(hmax + 1):
             self.gram(fit.phi, fit.phi, fit.col_off[l], fit.col_off[l + 1], out=G[l])
         return G

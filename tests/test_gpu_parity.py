@@ -156,6 +156,22 @@ def test_hash_collision_is_detected_large(eng):
     assert rc == 4
 
 
+
+@pytest.mark.parametrize("fam,n", [(0, 7), (1, 150), (2, 333)])
+def test_level_grams_small_kernel_matches_tensor_core_path(eng, fam, n, monkeypatch):
+    """nbw_level_grams_i32 (one SIMT launch for all WL levels of a small training set) against one tcgen05 Gram per
+    level and against the oracle: exact integers."""
+    from nasbowl_b200 import synth
+    train = synth.generate_cells_host(fam, 4, 0, n)
+    fit = eng.wl_fit(eng.upload_cells(train), train.n_max, 3, False)
+    a = eng.level_grams_i32(fit, 3)[:, :, :n].clone()
+    monkeypatch.setenv("NBW_LEVEL_GRAMS_TC", "1")
+    b = eng.level_grams_i32(fit, 3)[:, :, :n].clone()
+    assert torch.equal(a, b)
+    tot = a.sum(0).cpu().numpy()
+    assert np.array_equal(tot, wl_oracle.gram_raw(train, 3, False))
+
+
 def test_hash_collision_is_detected(eng):
     """Equal keys with different check words must be reported, not merged."""
     import ctypes as C
