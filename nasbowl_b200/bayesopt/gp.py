@@ -130,6 +130,9 @@ class GraphGP:
         self._dev = None           # device state of the last fit (not pickled)
         self._prev = None          # ... of the fit before reset_XY: the next fit may append to it
         self.incremental = True    # False: every fit() starts from scratch
+        # measured (profiles/r02_incremental_bench.json): appending 5 cells beats a from-scratch fit from ~750 cells on
+        # (4.8 vs 5.3 ms at 1000, 18 vs 31 ms at 4000); below that the whole fit is 1.5-3 ms and the bookkeeping loses
+        self.incremental_min_n = 768
         self.last_fit_incremental = False
 
     # ------------------------------------------------------------------ device helpers
@@ -207,7 +210,7 @@ class GraphGP:
             return None
         old = prev['records']
         n_old = old.shape[0]
-        if n_old >= len(slots) or prev['fits'][0].oa:
+        if n_old >= len(slots) or prev['fits'][0].oa or n_old < self.incremental_min_n:
             return None
         h_fit = max([int(c) for c in wl_subtree_candidates] + [k.h])
         if prev['fits'][0].h != h_fit or k._level_weights(k.h) is not None:

@@ -385,6 +385,7 @@ def test_incremental_refit_matches_from_scratch(fam, n0, h_grid):
     y_all = torch.randn(total, generator=torch.Generator().manual_seed(fam)).double()
     pool = synth.generate_cells_host(fam, 9, 5000, 3000)
     gp = GraphGP(cells[:n0], y_all[:n0], [WeisfilerLehman(h=2)], n_max=cells.n_max)
+    gp.incremental_min_n = 0           # (by default only training sets of >= 768 cells are extended: below, refitting is faster)
     gp.fit(wl_subtree_candidates=h_grid, optimize_lik=True, max_lik=0.01)
     assert not gp.last_fit_incremental
     used = 0
