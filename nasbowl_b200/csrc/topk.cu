@@ -25,20 +25,25 @@ __device__ __forceinline__ bool better(float v, int64_t i, float bv, int64_t bi)
   return v > bv || (v == bv && i < bi);
 }
 
-template <bool FROM_CANDS>
-__global__ void __launch_bounds__(kTopThreads)
+// (kWideThreads x kWideItems: one CTA that merges the per-CTA lists of a fused-top-n scoring launch in ONE launch)
+constexpr int kWideThreads = 1024;
+constexpr int kWideItems = 12;
+
+template <bool FROM_CANDS, int THREADS = kTopThreads, int ITEMS = kTopItems>
+__global__ void __launch_bounds__(THREADS)
 topk_round_kernel(const float* __restrict__ scores, const Cand* __restrict__ cands, int64_t n, int k,
                   int distinct, int64_t index_base, Cand* __restrict__ out) {
-  __shared__ float sv[kTopThreads / 32];
-  __shared__ int64_t si[kTopThreads / 32];
+  constexpr int CHUNK = THREADS * ITEMS;
+  __shared__ float sv[THREADS / 32];
+  __shared__ int64_t si[THREADS / 32];
   __shared__ float best_v_s;
   __shared__ int64_t best_i_s;
-  float v[kTopItems];
-  int64_t ix[kTopItems];
-  const int64_t base = (int64_t)blockIdx.x * kTopChunk;
+  float v[ITEMS];
+  int64_t ix[ITEMS];
+  const int64_t base = (int64_t)blockIdx.x * CHUNK;
 #pragma unroll
-  for (int t = 0; t < kTopItems; ++t) {
-    const int64_t p = base + (int64_t)t * kTopThreads + threadIdx.x;
+  for (int t = 0; t < ITEMS; ++t) {
+    const int64_t p = base + (int64_t)t * THREADS + threadIdx.x;
     v[t] = 0.f;
     ix[t] = -1;
     if (p < n) {
@@ -59,7 +64,7 @@ topk_round_kernel(const float* __restrict__ scores, const Cand* __restrict__ can
     float bv = 0.f;
     int64_t bi = -1;
 #pragma unroll
-    for (int t = 0; t < kTopItems; ++t) {
+    for (int t = 0; t < ITEMS; ++t) {
       bool eligible = ix[t] >= 0;
       if (eligible && last_i >= 0)
         eligible = distinct ? (v[t] < last_v) : (v[t] < last_v || (v[t] == last_v && ix[t] > last_i));
@@ -74,8 +79,8 @@ topk_round_kernel(const float* __restrict__ scores, const Cand* __restrict__ can
     if (lane == 0) { sv[warp] = bv; si[warp] = bi; }
     __syncthreads();
     if (warp == 0) {
-      bv = lane < kTopThreads / 32 ? sv[lane] : 0.f;
-      bi = lane < kTopThreads / 32 ? si[lane] : -1;
+      bv = lane < THREADS / 32 ? sv[lane] : 0.f;
+      bi = lane < THREADS / 32 ? si[lane] : -1;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
@@ -95,7 +100,7 @@ topk_round_kernel(const float* __restrict__ scores, const Cand* __restrict__ can
     last_i = best_i_s;
     __syncthreads();
     if (last_i < 0) {   // chunk exhausted: pad the rest of the list with empties
-      for (int r = round + 1 + threadIdx.x; r < k; r += kTopThreads) {
+      for (int r = round + 1 + threadIdx.x; r < k; r += THREADS) {
         Cand c;
         c.v = 0.f; c.pad = 0; c.idx = -1;
         out[(int64_t)blockIdx.x * k + r] = c;
@@ -112,6 +117,13 @@ topk_round_kernel(const float* __restrict__ scores, const Cand* __restrict__ can
 static int topk_enqueue(nbw_ctx* ctx, const float* scores, const Cand* cands, int64_t n, int k, int distinct,
                         int64_t index_base, Cand** result, cudaStream_t st, Cand* direct = nullptr) {
   int64_t blocks = (n + kTopChunk - 1) / kTopChunk;
+  if (cands != nullptr && direct != nullptr && n > kTopChunk && n <= (int64_t)kWideThreads * kWideItems) {
+    // the block lists of one scoring launch (CTAs x k entries): one wide CTA instead of two passes
+    topk_round_kernel<true, kWideThreads, kWideItems><<<1, kWideThreads, 0, st>>>(nullptr, cands, n, k, distinct, 0, direct);
+    NBW_CHECK_LAUNCH(ctx);
+    *result = direct;
+    return NBW_OK;
+  }
   if (blocks == 1 && direct != nullptr) {
     // one chunk: its list IS the result — written straight to the caller's buffer, no scratch involved
     // (which also makes this form safe on a side stream)
