@@ -583,6 +583,7 @@ def run_scoring(name, args, ctx):
         "cpu_baseline": cpu_baseline,
         "e2e": {"value": total * e_steps / (e2e_ms / 1e3), "unit": "candidates/s",
                 "h2d_bytes_per_step": M * wire_bytes, "d2h_bytes_per_step": M * 4 + TOP_N * 16, "steps": e_steps,
+                "numa_node_rank0": ctx.get("numa"),
                 "api": "GraphExpectedImprovement.propose_location on pinned host records (%d-byte %s records per candidate)"
                        % (wire_bytes, "compact wire" if wire_bytes != rec_bytes else "full"),
                 "full_records": {"value": total * e_steps / (e2e_full_ms / 1e3), "h2d_bytes_per_step": M * rec_bytes}},
@@ -668,12 +669,14 @@ def run_b200(args):
     from nasbowl_b200.engine import Engine
     rank, world, local = parallel.init_distributed()
     torch.cuda.set_device(local)
+    # several ranks on one host: keep every rank, and the pinned pools it allocates, on its GPU's NUMA node
+    numa = parallel.bind_to_gpu_numa_node(local) if world > 1 and not os.environ.get("NBW_NO_NUMA_BIND") else None
     eng = Engine.get(local)
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler is not None:
         sampler.start()
     peaks, peak_src = load_peaks()
-    ctx = dict(rank=rank, world=world, eng=eng, sampler=sampler, peaks=peaks, peak_src=peak_src)
+    ctx = dict(rank=rank, world=world, eng=eng, sampler=sampler, peaks=peaks, peak_src=peak_src, numa=numa)
     line = run_scoring(args.workload, args, ctx)
     subs = {}
     for name in [c for c in args.configs.split(",") if c]:

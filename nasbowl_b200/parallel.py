@@ -41,6 +41,48 @@ def init_distributed(backend: Optional[str] = None) -> Tuple[int, int, int]:
     return rank, world, local
 
 
+def parse_cpulist(text: str) -> List[int]:
+    """'0-3,8,10-11' (sysfs cpulist) -> [0, 1, 2, 3, 8, 10, 11]."""
+    cpus: List[int] = []
+    for part in text.strip().split(","):
+        part = part.strip()
+        if not part:
+            continue
+        if "-" in part:
+            a, b = part.split("-", 1)
+            cpus.extend(range(int(a), int(b) + 1))
+        else:
+            cpus.append(int(part))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device_index: int) -> Optional[int]:
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, so that the pinned host pools it allocates
+    afterwards (first touch) and the threads that fill them are local to that GPU's PCIe root: with 8 ranks on one
+    host the pools otherwise land wherever the scheduler started the process.  Best effort: returns the node, or
+    None (and changes nothing) when the topology cannot be read or the node's CPUs are not available to us."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(visible.split(",")[device_index]) if visible and visible.split(",")[device_index].isdigit() else device_index
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(phys)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        path = "/sys/bus/pci/devices/%s:%s" % (dom[-4:].lower(), rest.lower())
+        node = int(open(path + "/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set(parse_cpulist(open("/sys/devices/system/node/node%d/cpulist" % node).read()))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous index range [lo, hi) of `rank` ([r*M/R, (r+1)*M/R))."""
     return (rank * n_items) // world, ((rank + 1) * n_items) // world

@@ -590,3 +590,12 @@ def test_dmu_dphi_closed_form_matches_finite_differences():
             e[c] = 1e-6
             fd = (mu(Y[j] + e) - mu(Y[j] - e)) / 2e-6
             assert abs(fd - g[j, c]) < 1e-7, (j, c, fd, g[j, c])
+
+
+def test_cpulist_parser_and_numa_binding_is_best_effort():
+    from nasbowl_b200 import parallel
+    assert parallel.parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert parallel.parse_cpulist("") == []
+    before = os.sched_getaffinity(0)
+    assert parallel.bind_to_gpu_numa_node(0) is None        # no GPU here: nothing read, nothing changed
+    assert os.sched_getaffinity(0) == before
