@@ -37,6 +37,7 @@ extern "C" int nbw_destroy(nbw_ctx* ctx) {
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->pinned_small) cudaFreeHost(ctx->pinned_small);
   if (ctx->topk_blocks) cudaFree(ctx->topk_blocks);
+  if (ctx->bin_order) cudaFree(ctx->bin_order);
   if (ctx->piece_cands) cudaFree(ctx->piece_cands);
   if (ctx->pipe_ready) {
     cudaStreamDestroy(ctx->s_in);

@@ -35,6 +35,8 @@ struct nbw_ctx {
   void* piece_cands;    // per-piece top-n lists of the host-buffer entry points (score_pool.cu)
   void* topk_blocks;    // per-CTA top-n lists of the fused scoring kernel (score_packed.cu), two alternating slots
   size_t topk_blocks_bytes;
+  void* bin_order;      // cell order of the size-binned scoring pass (score_packed.cu) + its counters
+  size_t bin_order_bytes;
   int topk_slot;
 };
 enum { NBW_ATTR_TRSV = 1u << 0, NBW_ATTR_SMALL_SORT = 1u << 1, NBW_ATTR_GRAM_SINGLE = 1u << 2, NBW_ATTR_FACTOR_NP = 1u << 3, NBW_ATTR_SMALL_DICT = 1u << 4,

@@ -673,12 +673,66 @@ __device__ __forceinline__ uint32_t eq_bits8(uint64_t w, uint32_t byte) {
   return lo | (hi << 4);
 }
 
+// ---------------------------------------------------------------- size-binned order of a pool
+// The thread-per-cell kernel steps over the eight node slots of every cell; a warp skips a slot only if none of its
+// 32 cells has that node.  Cells arrive in arbitrary order (NB cells average ~5 of 8 nodes), so almost every warp pays
+// for eight.  A counting sort of the cell INDICES by node count (largest first) gives every warp cells of one size:
+// two small kernels over the records, then the scoring kernel walks the pool through that order.  Scores, indices and
+// the top-n are those of the original positions.
+constexpr int kBinMax = 8 * NBW_MAX_PARTS + 1;
+constexpr int64_t kBinMinCells = 1 << 16;      // below this the two extra launches cost more than they save
+
+__device__ __forceinline__ int cell_nodes(const uint8_t* __restrict__ rec, bool compact) {
+  if (compact) {
+    const uint2 r = __ldg(reinterpret_cast<const uint2*>(rec));
+    const uint32_t f = r.x & 0xFFFFFFu;                       // eight 3-bit palette indices, 7 = no node
+    const uint32_t all = f & (f >> 1) & (f >> 2) & 0x249249u;  // bit 3v set iff field v == 7
+    return 8 - __popc(all);
+  }
+  const uint2 w = __ldg(reinterpret_cast<const uint2*>(rec));
+  return __popc(present_bits4(w.x) | (present_bits4(w.y) << 4));
+}
+
+template <bool SCATTER>
+__global__ void __launch_bounds__(256)
+cell_bin_kernel(const uint8_t* __restrict__ cells, int64_t n_cells, int64_t stride, int np, int4 offs, int compact,
+                uint32_t* __restrict__ counters /* [kBinMax] counts, then [kBinMax] cursors */, uint32_t* __restrict__ order) {
+  __shared__ uint32_t hist[kBinMax];
+  __shared__ uint32_t base[kBinMax];
+  if (threadIdx.x < kBinMax) hist[threadIdx.x] = 0u;
+  __syncthreads();
+  const int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  int key = -1;
+  uint32_t slot = 0;
+  if (g < n_cells) {
+    const uint8_t* rec = cells + g * stride;
+    key = cell_nodes(rec + offs.x, compact);
+    if (np > 1) key += cell_nodes(rec + offs.y, compact);
+    if (np > 2) key += cell_nodes(rec + offs.z, compact);
+    key = 8 * np - key;                                        // largest cells first
+    slot = atomicAdd(&hist[key], 1u);
+  }
+  __syncthreads();
+  if (!SCATTER) {
+    if (threadIdx.x < kBinMax && hist[threadIdx.x]) atomicAdd(&counters[threadIdx.x], hist[threadIdx.x]);
+    return;
+  }
+  if (threadIdx.x < kBinMax) {
+    // start of my bin = counts of the bins before it (a handful of values: every CTA adds them up itself)
+    uint32_t start = 0;
+    for (int b = 0; b < (int)threadIdx.x; ++b) start += counters[b];
+    base[threadIdx.x] = hist[threadIdx.x] ? start + atomicAdd(&counters[kBinMax + threadIdx.x], hist[threadIdx.x]) : 0u;
+  }
+  __syncthreads();
+  if (key >= 0) order[base[key] + slot] = (uint32_t)g;
+}
+
 template <int NP, bool WEIGHTED, bool TOPK, bool OA = false>
 __global__ void __launch_bounds__(kCellThreads, OA ? 6 : 0)
 score_cell_kernel(const __grid_constant__ PackedParams P, const uint8_t* __restrict__ cells, int64_t n_cells,
                   float* __restrict__ scores, double* __restrict__ mu64, double* __restrict__ var64,
                   double* __restrict__ score64, NbwCand* __restrict__ block_cands, int k_top, int distinct,
-                  int64_t index_base) {
+                  int64_t index_base, const uint32_t* __restrict__ order) {
   constexpr unsigned FULL = 0xffffffffu;
   using KccT = typename std::conditional<WEIGHTED, double, int>::type;
   static_assert(!OA || NP == 1, "the packed histogram-intersection path takes one kernel");
@@ -699,7 +753,8 @@ score_cell_kernel(const __grid_constant__ PackedParams P, const uint8_t* __restr
     for (int j = 0; j < kTopMax; ++j) { sh_tv[j][tid] = 0.f; sh_ti[j][tid] = -1; }
   }
 
-  for (int64_t g = (int64_t)blockIdx.x * kCellThreads + tid; g < n_cells; g += (int64_t)gridDim.x * kCellThreads) {
+  for (int64_t gi = (int64_t)blockIdx.x * kCellThreads + tid; gi < n_cells; gi += (int64_t)gridDim.x * kCellThreads) {
+    const int64_t g = order ? (int64_t)__ldg(order + gi) : gi;      // size-binned walk (cell_bin_kernel) or pool order
     int deep[NP][8];
     int ne = 0;                  // OA: exception items collected so far
     KccT kacc = 0;
@@ -1239,7 +1294,38 @@ int launch_cell_variant(nbw_ctx* ctx, int variant, const PackedParams& P, const 
     NBW_REQUIRE(ctx, (size_t)grid * kTopMax * sizeof(NbwCand) <= slot_bytes, "too many CTAs for the top-n block lists");
   }
   if (ctx->prof_ev[0]) NBW_CUDA(ctx, cudaEventRecord(ctx->prof_ev[0], st));
-  kern<<<(unsigned)grid, kCellThreads, 0, st>>>(P, cells, n, scores, mu64, var64, score64, blocks, k, distinct, index_base);
+  // large device-resident pools are walked in size-binned order (cell_bin_kernel); pools read over PCIe are not
+  // (the pre-pass would fetch every record a second time)
+  const uint32_t* order = nullptr;
+  if (n >= kBinMinCells && !getenv("NBW_NO_BINNING")) {
+    cudaPointerAttributes pa;
+    const bool on_device = cudaPointerGetAttributes(&pa, cells) == cudaSuccess && pa.type == cudaMemoryTypeDevice;
+    if (!on_device) (void)cudaGetLastError();
+    if (on_device) {
+      const size_t need = 512 + sizeof(uint32_t) * (size_t)n;
+      if (ctx->bin_order_bytes < need) {
+        if (ctx->bin_order) {
+          NBW_CUDA(ctx, cudaStreamSynchronize(st));
+          NBW_CUDA(ctx, cudaFree(ctx->bin_order));
+          ctx->bin_order = nullptr;
+          ctx->bin_order_bytes = 0;
+        }
+        NBW_CUDA(ctx, cudaMalloc(&ctx->bin_order, need + need / 4));
+        ctx->bin_order_bytes = need + need / 4;
+      }
+      uint32_t* counters = static_cast<uint32_t*>(ctx->bin_order);
+      uint32_t* ord = counters + 128;
+      NBW_CUDA(ctx, cudaMemsetAsync(counters, 0, 512, st));
+      const int4 offs = make_int4(P.part[0].rec_offset, NP > 1 ? P.part[1].rec_offset : 0, NP > 2 ? P.part[2].rec_offset : 0, 0);
+      const unsigned bgrid = (unsigned)((n + 255) / 256);
+      cell_bin_kernel<false><<<bgrid, 256, 0, st>>>(cells, n, P.rec_stride, NP, offs, P.part[0].compact, counters, ord);
+      NBW_CHECK_LAUNCH(ctx);
+      cell_bin_kernel<true><<<bgrid, 256, 0, st>>>(cells, n, P.rec_stride, NP, offs, P.part[0].compact, counters, ord);
+      NBW_CHECK_LAUNCH(ctx);
+      order = ord;
+    }
+  }
+  kern<<<(unsigned)grid, kCellThreads, 0, st>>>(P, cells, n, scores, mu64, var64, score64, blocks, k, distinct, index_base, order);
   NBW_CHECK_LAUNCH(ctx);
   if (ctx->prof_ev[1]) NBW_CUDA(ctx, cudaEventRecord(ctx->prof_ev[1], st));
   if (TOPK) {
