@@ -180,6 +180,36 @@ def test_oa_item_form_on_cells_with_many_twins(eng):
         np.testing.assert_allclose(var.numpy(), var_n.numpy(), rtol=1e-9, atol=1e-13)
 
 
+
+# ---------------------------------------------------------------------------- size-binned walk of large pools
+@pytest.mark.parametrize("fam", [0, 1])
+def test_size_binned_order_gives_the_same_scores_and_selection(eng, fam, monkeypatch):
+    """Device pools of >= 65536 cells are scored in size-binned order (cell_bin_kernel: counting sort of the cell
+    indices by node count).  Scores are per cell and the top-n is (value desc, index asc), so nothing may change:
+    bitwise equal scores, identical selection, for one kernel and for a sum of two (compact records of that size:
+    test_compact_wire_records_score_identically)."""
+    from nasbowl_b200.bayesopt import GraphExpectedImprovement
+    from nasbowl_b200.kernels import WeisfilerLehman
+    n, M = 80, 150_001
+    train = synth.generate_cells_host(fam, 2, 0, n)
+    y = np.random.RandomState(fam).randn(n)
+    pool = eng.generate_cells(fam, 13, 500, M)
+    for kernels in ([WeisfilerLehman(h=3)], [WeisfilerLehman(h=1), WeisfilerLehman(h=2)]):
+        gp = _gp(train, y, kernels, weights=[1.0 / len(kernels)] * len(kernels))
+        gp.fit(wl_subtree_candidates=(kernels[0].h,) if len(kernels) == 1 else (), optimize_lik=False)
+        acq = GraphExpectedImprovement(gp)
+        s_b = acq.score_pool(pool)[0].clone()
+        _, _, idx_b = acq.propose_location(pool, top_n=5)
+        monkeypatch.setenv("NBW_NO_BINNING", "1")
+        s_p = acq.score_pool(pool)[0].clone()
+        _, _, idx_p = acq.propose_location(pool, top_n=5)
+        monkeypatch.delenv("NBW_NO_BINNING")
+        assert torch.equal(s_b, s_p)
+        assert np.array_equal(np.sort(idx_b), np.sort(idx_p))
+        ref = gp_oracle.top_n_distinct(s_b.cpu().numpy(), 5)
+        assert set(int(i) for i in idx_b) == set(int(i) for i in ref)
+
+
 def test_packing_edge_cases(eng):
     """Cells of 1..8 nodes in every order, empty records, isolated nodes, pools of 1..40 cells."""
     from nasbowl_b200.bayesopt import GraphExpectedImprovement
