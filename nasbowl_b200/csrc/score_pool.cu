@@ -660,8 +660,9 @@ static int score_pool_mapped_impl(nbw_ctx* ctx, const nbw_model* model_h, const 
   for (int c = 0; c < pieces; ++c) {
     const int64_t lo = (int64_t)c * per, hi = (lo + per < n_cells) ? lo + per : n_cells;
     if (lo >= hi) break;
+    // (a single piece writes its list straight into out_cands: no merge launch)
     rc = score_dispatch(ctx, *model_h, src + lo * rec, hi - lo, sink + lo, st, k, distinct, index_base + lo,
-                        lists ? lists + (size_t)c * k : nullptr);
+                        lists ? (pieces == 1 ? static_cast<NbwCand*>(out_cands) : lists + (size_t)c * k) : nullptr);
     if (rc) return rc;
     ++used;
     if (scores_h && !write_through) {
@@ -671,7 +672,7 @@ static int score_pool_mapped_impl(nbw_ctx* ctx, const nbw_model* model_h, const 
                                     cudaMemcpyDeviceToHost, ctx->s_out));
     }
   }
-  if (k > 0) {
+  if (k > 0 && pieces > 1) {
     rc = merge_pieces(ctx, lists, used, k, distinct, out_cands, st);
     if (rc) return rc;
   }
