@@ -644,7 +644,7 @@ def run_gram_stress(args, ctx):
         "metric": "Gram-only stress: int8 tensor-core throughput of the exact WL kernel matrix", "unit": "Tera int8 op/s",
         "value": ops_done / total_ms / 1e9, "n_gpus": world, "steps": 1, "warmup": 1, "ms_per_step": total_ms,
         "higher_is_better": True, "scaling": "strong", "dtype": "s8 x s8 -> s32", "data": "synthetic",
-        "config": {"workload": g["desc"] + " (N=%d), row blocks of %d sharded over the GPUs" % (N, B),
+        "config": {"workload": g["desc"] + " (N=%d), row blocks of %d sharded over the GPUs" % (N, res.get("row_block", B)),
                    "dims": fit_dims(res), "feature_columns_padded": D, "phi_bytes": N * D, "wl_fit_ms": 1e3 * t_fit,
                    "schedule": res["schedule"], "output": res["output"],
                    "dense_equivalent_value": ops_dense / total_ms / 1e9},

@@ -302,8 +302,20 @@ class Engine:
         import time
         N = fit.n_cells
         code, dtype = self.GRAM_OUT[mode]
+        if world > 1 and symmetric:
+            # the symmetric schedule makes row blocks unequal (block r0 holds the tiles right of its diagonal): deal
+            # smaller blocks greedily, largest first, to the least loaded rank (same answer on every rank)
+            block = max(2048, block // 4)
         starts = list(range(0, N, block))
-        mine = [r0 for i, r0 in enumerate(starts) if i % world == rank]
+        if world > 1 and symmetric:
+            load, owner = [0.0] * world, {}
+            for r0 in sorted(starts, key=lambda r: -(min(block, N - r) * (N - r))):
+                r = min(range(world), key=lambda i: (load[i], i))
+                owner[r0] = r
+                load[r] += min(block, N - r0) * (N - r0)
+            mine = [r0 for r0 in starts if owner[r0] == rank]
+        else:
+            mine = [r0 for i, r0 in enumerate(starts) if i % world == rank]
         ld = _round_up(N, 16)
         rows_mine = sum(min(block, N - r0) for r0 in mine)
         out = self.empty((max(rows_mine, 1), ld), dtype)          # this rank's row blocks, stacked
@@ -352,8 +364,11 @@ class Engine:
                 checks["mirrored_corner_equals_transpose"] = bool(torch.equal(low, ref.t().contiguous()))
         return {"ms": ms, "checks": checks, "t_begin": t_begin, "t_end": t_end,
                 "computed_fraction": tiles_done / max(tiles_all, 1), "dims": list(fit.dims),
-                "schedule": ("symmetric: 256x256 tiles strictly below the diagonal skipped, lower triangle filled by a mirror pass"
+                "schedule": (("symmetric: 256x256 tiles strictly below the diagonal skipped, " +
+                              ("lower triangle filled by a mirror pass" if world == 1 else
+                               "row blocks of %d dealt to the ranks by tile count (largest first, least loaded rank)" % block))
                              if symmetric else "all tiles"),
+                "row_block": block,
                 "output": "%s [%d x %d] materialised in HBM (%.1f GB on this rank)" % (mode, rows_mine, N, rows_mine * ld * out.element_size() / 1e9),
                 "output_bytes": rows_mine * N * out.element_size() * world if world > 1 else N * N * out.element_size(),
                 "kernel": "gram_i8_pair_kernel<%s>" % mode, "result": out}

@@ -25,7 +25,14 @@ for pieces in (2, 3, 4):
     t = time.perf_counter()
     for _ in range(100): c, h = eng.propose_host(model, host, 5, True, chunks=pieces); eng.cands_read(c, 5)
     print("propose_host staged %d: %.3f ms" % (pieces, (time.perf_counter() - t) * 10))
+from nasbowl_b200.cells import CellBatch, CompactRecords
+rec, pal = CellBatch.from_records(dev.cpu().numpy(), 8).to_compact()
+wire = CompactRecords(torch.from_numpy(rec).pin_memory(), [pal])
+for _ in range(20): acq.propose_location(wire, top_n=5)
+torch.cuda.synchronize(); t = time.perf_counter()
+for _ in range(100): acq.propose_location(wire, top_n=5)
+torch.cuda.synchronize(); print("propose_location, 8-byte wire records: %.3f ms" % ((time.perf_counter() - t) * 10))
 pr = cProfile.Profile(); pr.enable()
-for _ in range(200): acq.propose_location(host, top_n=5)
+for _ in range(200): acq.propose_location(wire, top_n=5)
 pr.disable()
-s = io.StringIO(); pstats.Stats(pr, stream=s).sort_stats("cumulative").print_stats(22); print(s.getvalue()[:3500])
+s = io.StringIO(); pstats.Stats(pr, stream=s).sort_stats("cumulative").print_stats(30); print(s.getvalue()[:5000])
