@@ -53,7 +53,7 @@ WORKLOADS = {
                  desc="DARTS-shaped normal + reduce cells (<=15 nodes, 11 ops; two records per candidate), summed WL "
                       "kernels h=2 with weights 0.5/0.5, n_train=1000, 10M-candidate pool sharded over the GPUs"),
 }
-GRAM_STRESS = dict(cells=200_000, h=3, block=16384,
+GRAM_STRESS = dict(cells=200_000, h=3, block=4096,      # row block: 4096 measured best (profiles/r02_gram_block_sweep.json)
                    desc="Gram-only stress: 200k x 200k WL h=3 kernel matrix on NB101-shaped cells")
 
 

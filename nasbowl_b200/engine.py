@@ -304,8 +304,8 @@ class Engine:
         code, dtype = self.GRAM_OUT[mode]
         if world > 1 and symmetric:
             # the symmetric schedule makes row blocks unequal (block r0 holds the tiles right of its diagonal): deal
-            # smaller blocks greedily, largest first, to the least loaded rank (same answer on every rank)
-            block = max(2048, block // 4)
+            # blocks of at most 4096 rows greedily, largest first, to the least loaded rank (same answer on every rank)
+            block = min(block, 4096)
         starts = list(range(0, N, block))
         if world > 1 and symmetric:
             load, owner = [0.0] * world, {}
