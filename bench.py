@@ -388,14 +388,12 @@ def run_scoring(name, args, ctx):
     # ---- end to end through the public API with HOST buffers (pinned): H2D pool, score, top-5, D2H scores
     host_pool = torch.empty((M, rec_bytes), dtype=torch.uint8).pin_memory()
     host_pool.copy_(pools[0].cpu())
-    # 8-node cells travel in the 8-byte wire form (cells.CompactRecords, nbw_model.compact): half the PCIe bytes.
-    # The 16 / 48-byte records of the same pool are timed as well and reported beside it.
-    wire_pool, wire_bytes = host_pool, rec_bytes
-    if n_max == 8:
-        from nasbowl_b200.cells import CompactRecords
-        parts = [b.to_compact() for b in records_to_batches(w, host_pool.numpy(), n_max)]
-        data = torch.from_numpy(np.concatenate([r for r, _ in parts], axis=1)).pin_memory()
-        wire_pool, wire_bytes = CompactRecords(data, [p for _, p in parts]), 8 * w["slots"]
+    # Cells travel in the wire form (cells.CompactRecords, nbw_model.compact): 8 bytes per 8-node cell, 24 per 16-node
+    # cell — half the PCIe bytes.  The 16 / 48-byte records of the same pool are timed as well and reported beside it.
+    from nasbowl_b200.cells import CompactRecords
+    parts = [b.to_compact() for b in records_to_batches(w, host_pool.numpy(), n_max)]
+    data = torch.from_numpy(np.concatenate([r for r, _ in parts], axis=1)).pin_memory()
+    wire_pool, wire_bytes = CompactRecords(data, [p for _, p in parts]), (8 if n_max == 8 else 24) * w["slots"]
 
     def time_e2e(pool_obj):
         def e2e_step():

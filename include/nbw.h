@@ -339,9 +339,12 @@ typedef struct {
    * pool that arrives in host memory.  Little-endian u64: bits [3v, 3v+3) = palette index of node v's op code
    * (7 = no node), bits [24, 52) = the strict upper triangle of the adjacency, row by row (edge u -> v, u < v,
    * at bit 24 + u (15 - u) / 2 + (v - u - 1)): cells whose nodes are numbered topologically, at most 7 distinct
-   * ops.  palette[c] = the op code (level-0 key) of index c.  The kernel expands it in its prologue. */
+   * ops.  palette[c] = the op code (level-0 key) of index c.  The kernel expands it in its prologue.
+   * n_max = 16: a 24-byte record of three little-endian u64 words — word 0 = sixteen 4-bit palette indices (15 = no
+   * node, at most 15 distinct ops), words 1-2 = the 120 bits of the strict upper triangle, row by row (edge u -> v,
+   * u < v, at bit u (31 - u) / 2 + (v - u - 1) of the 128-bit field): half the bytes of the 48-byte record. */
   int32_t compact;
-  uint8_t palette[8];
+  uint8_t palette[16];                   /* (n_max = 8 uses the first 8 entries) */
   /* Histogram intersection on the packed path (oa != 0, optional: NULL keeps the general G path).  In thermometer
    * form (vertex_histogram.py:233-249: sum_label min(count, count') = sum_(label, t) [count >= t][count' >= t]) every
    * (node, level) of a candidate activates ONE column: (its label, its rank among the cell's nodes with that label).

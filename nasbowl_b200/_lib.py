@@ -64,7 +64,7 @@ class Model(C.Structure):
         ("level_weight", C.c_double * NBW_MAX_LEVELS),
         ("weighted", C.c_int32), ("undirected", C.c_int32), ("rec_offset", C.c_int32),
         ("rec_stride", C.c_int32), ("label_base", C.c_int32), ("compact", C.c_int32),
-        ("palette", C.c_uint8 * 8),
+        ("palette", C.c_uint8 * 16),
         ("oa_exc", C.c_void_p),
         ("next", C.c_void_p),
     ]

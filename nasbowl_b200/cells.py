@@ -129,9 +129,10 @@ class CellBatch:
     def to_compact(self, palette: Optional[np.ndarray] = None):
         """(records uint8 [N, 8], palette uint8 [8]): the 8-byte wire form (nbw_model.compact).  Needs 8-node
         records, at most seven distinct op codes and topologically numbered nodes (every edge u -> v has u < v);
-        raises ValueError otherwise (such pools travel as full records)."""
-        if self.n_max != 8:
-            raise ValueError("compact records hold 8-node cells")
+        raises ValueError otherwise (such pools travel as full records).  16-node batches give the 24-byte form
+        ([N, 24], palette uint8 [16], at most fifteen distinct op codes)."""
+        if self.n_max == 16:
+            return self._to_compact16(palette)
         present = self.labels != NO_NODE
         if palette is None:
             codes = np.unique(self.labels[present])
@@ -161,6 +162,49 @@ class CellBatch:
             w |= field << np.uint64(off)
             off += 7 - u
         return w.view(np.uint8).reshape(len(self), 8).copy(), palette
+
+    def _to_compact16(self, palette: Optional[np.ndarray] = None):
+        """(records uint8 [N, 24], palette uint8 [16]): the 24-byte wire form of 16-node cells (nbw_model.compact):
+        word 0 = sixteen 4-bit palette indices (15 = no node), words 1-2 = the 120 bits of the strict upper triangle."""
+        present = self.labels != NO_NODE
+        if palette is None:
+            codes = np.unique(self.labels[present])
+            if len(codes) > 15:
+                raise ValueError("24-byte compact records hold at most 15 distinct op codes (got %d)" % len(codes))
+            palette = np.zeros(16, dtype=np.uint8)
+            palette[:len(codes)] = codes
+            n_codes = len(codes)
+        else:
+            palette = np.asarray(palette, dtype=np.uint8)
+            n_codes = 15
+        lut = np.full(256, 255, dtype=np.int64)
+        lut[palette[:n_codes]] = np.arange(n_codes)
+        idx = np.where(present, lut[self.labels], 15)
+        if (idx == 255).any():
+            raise ValueError("an op code is not in the palette")
+        w0 = np.zeros(len(self), dtype=np.uint64)
+        for v in range(16):
+            w0 |= idx[:, v].astype(np.uint64) << np.uint64(4 * v)
+        s = self.succ.astype(np.uint64)
+        lo = np.zeros(len(self), dtype=np.uint64)
+        hi = np.zeros(len(self), dtype=np.uint64)
+        off = 0
+        for u in range(15):
+            if (s[:, u] & np.uint64((1 << (u + 1)) - 1)).any():
+                raise ValueError("compact records need topologically numbered nodes (an edge u -> v with v <= u)")
+            n_bits = 15 - u
+            field = (s[:, u] >> np.uint64(u + 1)) & np.uint64((1 << n_bits) - 1)
+            if off < 64:
+                lo |= field << np.uint64(off)          # (bits beyond 63 fall off: they go to `hi` below)
+                if off + n_bits > 64:
+                    hi |= field >> np.uint64(64 - off)
+            else:
+                hi |= field << np.uint64(off - 64)
+            off += n_bits
+        if s[:, 15].any():
+            raise ValueError("compact records need topologically numbered nodes (an edge u -> v with v <= u)")
+        rec = np.stack([w0, lo, hi], axis=1)
+        return rec.view(np.uint8).reshape(len(self), 24).copy(), palette
 
     def widen(self, n_max: int) -> "CellBatch":
         if n_max == self.n_max:
@@ -200,9 +244,10 @@ class CellBatch:
 
 
 class CompactRecords:
-    """A pool in the 8-byte WIRE form of nbw_model.compact: `data` uint8 [N, 8 * n_slots] (host tensor, pin it for
-    full PCIe speed), `palettes[s][c]` = op code of palette index c in slot s.  Half the bytes of the 16-byte
-    records — what matters when a pool arrives from host memory.  Built by CellBatch.to_compact()."""
+    """A pool in the WIRE form of nbw_model.compact: `data` uint8 [N, 8 * n_slots] for 8-node cells, [N, 24 * n_slots]
+    for 16-node cells (host tensor, pin it for full PCIe speed), `palettes[s][c]` = op code of palette index c in slot
+    s.  Half the bytes of the 16 / 48-byte records — what matters when a pool arrives from host memory.  Built by
+    CellBatch.to_compact()."""
 
     def __init__(self, data, palettes):
         self.data, self.palettes = data, [np.asarray(p, dtype=np.uint8) for p in palettes]

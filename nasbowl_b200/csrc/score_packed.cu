@@ -46,7 +46,7 @@ struct PartParams {
   const uint32_t* oa_exc;           // histogram intersection: (first exception item << 5 | max count) per label
   int32_t h, first_stable, undirected, rec_offset, label_base, compact;
   int32_t oa_d2_base;               // histogram intersection: first rank-2 chain item (0 = none)
-  uint8_t palette[8];
+  uint8_t palette[16];
 };
 
 struct PackedParams {
@@ -208,7 +208,15 @@ score_packed_kernel(const __grid_constant__ PackedParams P, const uint8_t* __res
       uint32_t pm = 0;
 #pragma unroll
       for (int p = 0; p < NP; ++p) {
-        if (NMAX == 8) {
+        if (NMAX == 16 && P.part[p].compact) {
+          // 24-byte wire record: sixteen 4-bit palette indices, 15 = no node
+          const uint2 w = __ldg(reinterpret_cast<const uint2*>(rec + P.part[p].rec_offset));
+#pragma unroll
+          for (int v = 0; v < 8; ++v) {
+            pm |= (((w.x >> (4 * v)) & 15u) != 15u) ? (1u << v) : 0u;
+            pm |= (((w.y >> (4 * v)) & 15u) != 15u) ? (1u << (8 + v)) : 0u;
+          }
+        } else if (NMAX == 8) {
           const uint2 w = __ldg(reinterpret_cast<const uint2*>(rec + P.part[p].rec_offset));
           pm |= present_bits4(w.x) | (present_bits4(w.y) << 4);
         } else {
@@ -244,12 +252,31 @@ score_packed_kernel(const __grid_constant__ PackedParams P, const uint8_t* __res
     for (int p = 0; p < NP; ++p) {
       const PartParams& Q = P.part[p];
       const uint8_t* rec = cells + my_g * stride + Q.rec_offset;
-      const uint32_t label = active ? (uint32_t)__ldg(rec + node) : 0xFFu;
+      uint32_t label = 0xFFu, succ = 0u;
+      if (NMAX == 16 && Q.compact) {
+        if (active) {
+          // 24-byte wire record (nbw_model.compact, n_max = 16): my 4-bit palette index, my row of the upper triangle
+          const uint2 w0 = __ldg(reinterpret_cast<const uint2*>(rec));
+          const uint32_t idx = ((node < 8 ? w0.x : w0.y) >> (4 * (node & 7))) & 15u;
+          if (idx != 15u) {
+            label = Q.palette[idx];
+            if (node < 15) {
+              const uint2 t0 = __ldg(reinterpret_cast<const uint2*>(rec + 8)), t1 = __ldg(reinterpret_cast<const uint2*>(rec + 16));
+              const uint64_t lo = ((uint64_t)t0.y << 32) | t0.x, hi = ((uint64_t)t1.y << 32) | t1.x;
+              const int off = node * (31 - node) / 2, len = 15 - node;
+              uint64_t x = off < 64 ? (lo >> off) : (hi >> (off - 64));
+              if (off > 0 && off < 64) x |= hi << (64 - off);
+              succ = ((uint32_t)x & ((1u << len) - 1u)) << (node + 1);
+            }
+          }
+        }
+      } else {
+        label = active ? (uint32_t)__ldg(rec + node) : 0xFFu;
+        if (label != 0xFFu)
+          succ = NMAX == 8 ? (uint32_t)__ldg(rec + 8 + node) : (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(rec + 16) + node);
+      }
       const bool present = label != 0xFFu;
-      uint32_t succ = 0u;
-      if (present)
-        succ = (NMAX == 8 ? (uint32_t)__ldg(rec + 8 + node) : (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(rec + 16) + node)) &
-               ((1u << my_n) - 1u);     // edges to absent nodes would reach into a neighbouring cell's lanes
+      succ = present ? (succ & ((1u << my_n) - 1u)) : 0u;     // edges to absent nodes would reach into a neighbouring cell's lanes
       if (Q.undirected) {
         // kernels/weisfilerlehman.py:127-128: neighbourhood = successors and predecessors
         uint32_t pred = 0u;
@@ -1179,7 +1206,7 @@ int fill_part(nbw_ctx* ctx, const nbw_model* M, PartParams& Q) {
   Q.rec_offset = M->rec_offset;
   Q.label_base = M->label_base;
   Q.compact = M->compact;
-  memcpy(Q.palette, M->palette, 8);
+  memcpy(Q.palette, M->palette, 16);
   Q.child = M->child;
   Q.final_label = M->final_label;
   Q.oa_exc = M->oa_exc;
@@ -1406,16 +1433,17 @@ int nbw_score_packed(nbw_ctx* ctx, const nbw_model* M, const void* cells, int64_
   NBW_REQUIRE(ctx, P.ld_h >= (int64_t)P.zero_slot + 1, "model.ld_h must be >= n_labels + 1");
   NBW_REQUIRE(ctx, P.rec_stride % (M->compact ? 8 : 16) == 0, "rec_stride must be a multiple of the record size");
   const bool compact = M->compact != 0;
+  const int crec = n_max == 8 ? 8 : 24;      // wire records: 8 bytes (8-node cells) / 24 bytes (16-node cells)
   for (int p = 0; p < np; ++p) {
     NBW_REQUIRE(ctx, (P.part[p].compact != 0) == compact, "all parts of a sum must use the same record form");
     if (compact)
-      NBW_REQUIRE(ctx, n_max == 8 && P.part[p].rec_offset % 8 == 0 && P.part[p].rec_offset + 8 <= P.rec_stride,
-                  "part %d: compact records are 8 bytes, 8-node cells only", p);
+      NBW_REQUIRE(ctx, P.part[p].rec_offset % 8 == 0 && P.part[p].rec_offset + crec <= P.rec_stride,
+                  "part %d: compact records are %d bytes", p, crec);
     else
       NBW_REQUIRE(ctx, P.part[p].rec_offset % 16 == 0 && P.part[p].rec_offset + rec <= P.rec_stride,
                   "part %d: rec_offset outside the candidate record", p);
   }
-  NBW_REQUIRE(ctx, !compact || np <= 3, "compact records are scored by the thread-per-cell kernel (sums of up to 3 kernels)");
+  NBW_REQUIRE(ctx, !compact || n_max == 16 || np <= 3, "8-byte compact records are scored by the thread-per-cell kernel (sums of up to 3 kernels)");
   NBW_REQUIRE(ctx, M->acq >= NBW_ACQ_EI && M->acq <= NBW_ACQ_MEAN, "unknown acquisition");
   P.acq = M->acq;
   P.lik = M->lik; P.y_mean = M->y_mean; P.y_std = M->y_std;

@@ -141,10 +141,8 @@ class PoolModel:
     def _part_descriptor(self, rec: int, palettes=None) -> "_lib.Model":
         d = _lib.Model()
         if palettes is not None:
-            if self.n_max != 8:
-                raise ValueError("compact records hold 8-node cells")
             d.compact = 1
-            for c in range(8):
+            for c in range(8 if self.n_max == 8 else 16):
                 d.palette[c] = int(palettes[self.slot][c])
         d.n_max, d.h, d.oa = self.n_max, self.h, int(self.oa)
         d.seed = self.seed & 0xFFFFFFFFFFFFFFFF
@@ -180,8 +178,9 @@ class PoolModel:
 
     def descriptor(self, acq: str = "MEAN", xi: float = 0.0, beta: float = 0.0,
                    incumbent: Optional[float] = None, palettes=None) -> "_lib.Model":
-        """palettes (one uint8[8] per record slot): the pool arrives as 8-byte compact records (nbw_model.compact)."""
-        rec = (16 if self.n_max == 8 else 48) if palettes is None else 8
+        """palettes (one uint8[8] / uint8[16] per record slot): the pool arrives as 8 / 24-byte compact records
+        (nbw_model.compact)."""
+        rec = (16 if self.n_max == 8 else 48) if palettes is None else (8 if self.n_max == 8 else 24)
         d = self._part_descriptor(rec, palettes)
         d.acq = ACQ[acq]
         multi = len(self.more) > 0

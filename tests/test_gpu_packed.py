@@ -645,9 +645,60 @@ def test_compact_wire_records_score_identically(eng):
     np.testing.assert_array_equal(eis_c, eis_f)
     assert np.array_equal(idx_c, idx_f)
     # what does not fit the wire form is refused on the host
+    many = CellBatch(8, np.arange(8, dtype=np.uint8)[None, :], np.zeros((1, 8), dtype=np.uint16))   # eight distinct ops
     with pytest.raises(ValueError):
-        synth.generate_cells_host(2, 1, 0, 10).to_compact()                 # 16-node records
+        many.to_compact()
     bad = CellBatch(8, np.array([[0, 1, 255, 255, 255, 255, 255, 255]], dtype=np.uint8),
                     np.array([[0, 1, 0, 0, 0, 0, 0, 0]], dtype=np.uint16))  # edge 1 -> 0
     with pytest.raises(ValueError):
         bad.to_compact()
+
+
+def test_compact_24_byte_records_of_16_node_cells(eng):
+    """nbw_model.compact for n_max = 16: sixteen 4-bit palette indices + the 120-bit upper triangle in 24 bytes.  Host
+    round trip of the packing, then bitwise the same scores and selection as the 48-byte records: one kernel and the
+    normal | reduce sum, resident and from pinned host memory."""
+    from nasbowl_b200.bayesopt import GraphExpectedImprovement
+    from nasbowl_b200.cells import CompactRecords
+    from nasbowl_b200.kernels import WeisfilerLehman
+    M = 40_007
+    a, b = synth.generate_cells_host(2, 21, 0, M + 60), synth.generate_cells_host(2, 22, 0, M + 60)
+    rec, pal = a.to_compact()
+    assert rec.shape == (M + 60, 24) and pal.shape == (16,)
+    # decode on the host: labels and successor masks come back exactly
+    w = rec.view(np.uint64).reshape(-1, 3)
+    for v in (0, 3, 9, 14, 15):
+        idx = (w[:, 0] >> np.uint64(4 * v)) & np.uint64(15)
+        lab = np.where(idx == 15, NO_NODE, pal[np.minimum(idx, 14).astype(np.int64)])
+        assert np.array_equal(lab.astype(np.uint8), a.labels[:, v])
+        if v < 15:
+            off, n_bits = v * (31 - v) // 2, 15 - v
+            tri = [int(w[i, 1]) | (int(w[i, 2]) << 64) for i in range(200)]
+            row = np.array([((t >> off) & ((1 << n_bits) - 1)) << (v + 1) for t in tri], dtype=np.uint16)
+            assert np.array_equal(row, a.succ[:200, v])
+    y = np.random.RandomState(8).randn(60)
+    # one kernel
+    gp = _gp(a[:60], y, [WeisfilerLehman(h=2)])
+    gp.fit(wl_subtree_candidates=(2,), optimize_lik=False)
+    acq = GraphExpectedImprovement(gp)
+    pool = a[60:]
+    full = acq.score_pool(pool)[0].clone()
+    _, _, idx_f = acq.propose_location(pool, top_n=5)
+    rec_p, pal_p = pool.to_compact()
+    host = torch.from_numpy(rec_p).pin_memory()
+    for data in (host, host.cuda()):
+        _, eis, idx_c = acq.propose_location(CompactRecords(data, [pal_p]), top_n=5)
+        np.testing.assert_array_equal(eis.reshape(-1), full.cpu().numpy())
+        assert np.array_equal(idx_f, idx_c)
+    # normal | reduce
+    gp2 = _gp(CellSlots([a[:60], b[:60]]), y, [WeisfilerLehman(h=2, slot=0), WeisfilerLehman(h=1, slot=1)], weights=[0.5, 0.5])
+    gp2.fit(wl_subtree_candidates=(), optimize_lik=False)
+    acq2 = GraphExpectedImprovement(gp2)
+    slots = CellSlots([a[60:], b[60:]])
+    _, eis_f, idx_f = acq2.propose_location(slots, top_n=5)
+    ra, pa = a[60:].to_compact()
+    rb, pb = b[60:].to_compact()
+    both = torch.from_numpy(np.concatenate([ra, rb], axis=1)).pin_memory()
+    _, eis_c, idx_c = acq2.propose_location(CompactRecords(both, [pa, pb]), top_n=5)
+    np.testing.assert_array_equal(eis_c, eis_f)
+    assert np.array_equal(idx_f, idx_c)
