@@ -104,7 +104,7 @@ __device__ __forceinline__ int oa_item(uint32_t info, int r0) {
   return (int)(info >> 5) + (r0 < mc ? r0 : mc) - 1;
 }
 
-template <int NMAX, int NP, bool WEIGHTED, bool TOPK, bool OA = false>
+template <int NMAX, int NP, bool WEIGHTED, bool TOPK, bool OA = false, bool WIRE = false>
 __global__ void __launch_bounds__(kPackThreads, NMAX == 8 ? 5 : 4)
 score_packed_kernel(const __grid_constant__ PackedParams P, const uint8_t* __restrict__ cells, int64_t n_cells,
                     int64_t per_warp, float* __restrict__ scores, double* __restrict__ mu64,
@@ -208,7 +208,7 @@ score_packed_kernel(const __grid_constant__ PackedParams P, const uint8_t* __res
       uint32_t pm = 0;
 #pragma unroll
       for (int p = 0; p < NP; ++p) {
-        if (NMAX == 16 && P.part[p].compact) {
+        if (NMAX == 16 && WIRE) {
           // 24-byte wire record: sixteen 4-bit palette indices, 15 = no node
           const uint2 w = __ldg(reinterpret_cast<const uint2*>(rec + P.part[p].rec_offset));
 #pragma unroll
@@ -252,31 +252,30 @@ score_packed_kernel(const __grid_constant__ PackedParams P, const uint8_t* __res
     for (int p = 0; p < NP; ++p) {
       const PartParams& Q = P.part[p];
       const uint8_t* rec = cells + my_g * stride + Q.rec_offset;
-      uint32_t label = 0xFFu, succ = 0u;
-      if (NMAX == 16 && Q.compact) {
-        if (active) {
-          // 24-byte wire record (nbw_model.compact, n_max = 16): my 4-bit palette index, my row of the upper triangle
-          const uint2 w0 = __ldg(reinterpret_cast<const uint2*>(rec));
-          const uint32_t idx = ((node < 8 ? w0.x : w0.y) >> (4 * (node & 7))) & 15u;
-          if (idx != 15u) {
-            label = Q.palette[idx];
-            if (node < 15) {
-              const uint2 t0 = __ldg(reinterpret_cast<const uint2*>(rec + 8)), t1 = __ldg(reinterpret_cast<const uint2*>(rec + 16));
-              const uint64_t lo = ((uint64_t)t0.y << 32) | t0.x, hi = ((uint64_t)t1.y << 32) | t1.x;
-              const int off = node * (31 - node) / 2, len = 15 - node;
-              uint64_t x = off < 64 ? (lo >> off) : (hi >> (off - 64));
-              if (off > 0 && off < 64) x |= hi << (64 - off);
-              succ = ((uint32_t)x & ((1u << len) - 1u)) << (node + 1);
-            }
+      constexpr bool wire16 = NMAX == 16 && WIRE;       // 24-byte wire records are a compile-time variant
+      uint32_t label = (active && !wire16) ? (uint32_t)__ldg(rec + node) : 0xFFu;
+      bool present = label != 0xFFu;
+      uint32_t succ = 0u;
+      if (present)
+        succ = (NMAX == 8 ? (uint32_t)__ldg(rec + 8 + node) : (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(rec + 16) + node)) &
+               ((1u << my_n) - 1u);     // edges to absent nodes would reach into a neighbouring cell's lanes
+      if (wire16 && active) {
+        // 24-byte wire record (nbw_model.compact, n_max = 16): my 4-bit palette index, my row of the upper triangle
+        const uint2 w0 = __ldg(reinterpret_cast<const uint2*>(rec));
+        const uint32_t idx = ((node < 8 ? w0.x : w0.y) >> (4 * (node & 7))) & 15u;
+        if (idx != 15u) {
+          label = Q.palette[idx];
+          present = true;
+          if (node < 15) {
+            const uint2 t0 = __ldg(reinterpret_cast<const uint2*>(rec + 8)), t1 = __ldg(reinterpret_cast<const uint2*>(rec + 16));
+            const uint64_t lo = ((uint64_t)t0.y << 32) | t0.x, hi = ((uint64_t)t1.y << 32) | t1.x;
+            const int off = node * (31 - node) / 2, len = 15 - node;
+            uint64_t x = off < 64 ? (lo >> off) : (hi >> (off - 64));
+            if (off > 0 && off < 64) x |= hi << (64 - off);
+            succ = (((uint32_t)x & ((1u << len) - 1u)) << (node + 1)) & ((1u << my_n) - 1u);
           }
         }
-      } else {
-        label = active ? (uint32_t)__ldg(rec + node) : 0xFFu;
-        if (label != 0xFFu)
-          succ = NMAX == 8 ? (uint32_t)__ldg(rec + 8 + node) : (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(rec + 16) + node);
       }
-      const bool present = label != 0xFFu;
-      succ = present ? (succ & ((1u << my_n) - 1u)) : 0u;     // edges to absent nodes would reach into a neighbouring cell's lanes
       if (Q.undirected) {
         // kernels/weisfilerlehman.py:127-128: neighbourhood = successors and predecessors
         uint32_t pred = 0u;
@@ -1236,11 +1235,11 @@ int fill_part(nbw_ctx* ctx, const nbw_model* M, PartParams& Q) {
   return NBW_OK;
 }
 
-template <int NMAX, int NP, bool WEIGHTED, bool TOPK, bool OA = false>
+template <int NMAX, int NP, bool WEIGHTED, bool TOPK, bool OA = false, bool WIRE = false>
 int launch_variant(nbw_ctx* ctx, int variant, const PackedParams& P, const uint8_t* cells, int64_t n, float* scores,
                    double* mu64, double* var64, double* score64, int k, int distinct, int64_t index_base,
                    NbwCand* out_cands, cudaStream_t st) {
-  auto kern = score_packed_kernel<NMAX, NP, WEIGHTED, TOPK, OA>;
+  auto kern = score_packed_kernel<NMAX, NP, WEIGHTED, TOPK, OA, WIRE>;
   if (!ctx->packed_occ[variant]) {
     int occ = 0;
     NBW_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kPackThreads, 0));
@@ -1378,17 +1377,18 @@ int launch_cell_parts(nbw_ctx* ctx, int np, bool weighted, const PackedParams& P
   return -1;     // four parts: the lane-per-node kernel
 }
 
-template <int NMAX, bool TOPK>
+template <int NMAX, bool TOPK, bool WIRE = false>
 int launch_parts(nbw_ctx* ctx, int np, bool weighted, const PackedParams& P, const uint8_t* cells, int64_t n,
                  float* scores, double* mu64, double* var64, double* score64, int k, int distinct, int64_t index_base,
                  NbwCand* out_cands, cudaStream_t st) {
-  const int base = (NMAX == 16 ? 16 : 0) + (TOPK ? 8 : 0);
+  // occupancy cache slots: 0..15 8-node, 16..31 16-node, 44.. 16-node wire records
+  const int base = (WIRE ? 44 : (NMAX == 16 ? 16 : 0)) + (TOPK ? 8 : 0);
 #define NBW_ARGS P, cells, n, scores, mu64, var64, score64, k, distinct, index_base, out_cands, st
-  if (np == 1 && !weighted) return launch_variant<NMAX, 1, false, TOPK>(ctx, base + 0, NBW_ARGS);
-  if (np == 1) return launch_variant<NMAX, 1, true, TOPK>(ctx, base + 1, NBW_ARGS);
-  if (np == 2) return launch_variant<NMAX, 2, true, TOPK>(ctx, base + 2, NBW_ARGS);
-  if (np == 3) return launch_variant<NMAX, 3, true, TOPK>(ctx, base + 3, NBW_ARGS);
-  if (np == 4) return launch_variant<NMAX, 4, true, TOPK>(ctx, base + 4, NBW_ARGS);
+  if (np == 1 && !weighted) return launch_variant<NMAX, 1, false, TOPK, false, WIRE>(ctx, base + 0, NBW_ARGS);
+  if (np == 1) return launch_variant<NMAX, 1, true, TOPK, false, WIRE>(ctx, base + 1, NBW_ARGS);
+  if (np == 2) return launch_variant<NMAX, 2, true, TOPK, false, WIRE>(ctx, base + 2, NBW_ARGS);
+  if (np == 3) return launch_variant<NMAX, 3, true, TOPK, false, WIRE>(ctx, base + 3, NBW_ARGS);
+  if (np == 4) return launch_variant<NMAX, 4, true, TOPK, false, WIRE>(ctx, base + 4, NBW_ARGS);
 #undef NBW_ARGS
   NBW_FAIL(ctx, NBW_ERR_UNSUPPORTED, "the fused pool path takes sums of up to %d kernels", NBW_MAX_PARTS);
 }
@@ -1455,6 +1455,7 @@ int nbw_score_packed(nbw_ctx* ctx, const nbw_model* M, const void* cells, int64_
     // histogram intersection in item form (nbw_model.oa_exc): single kernel, unit weights; variants 32.. of the
     // occupancy cache
     NBW_REQUIRE(ctx, !weighted, "the packed histogram-intersection path takes unit level weights");
+    NBW_REQUIRE(ctx, !(compact && n_max == 16), "24-byte wire records are not wired to the histogram-intersection kernels");
 #define NBW_ARGS P, c, n_cells, scores, mu64, var64, score64, k, distinct, index_base, oc, st
 #define NBW_ARGS0 P, c, n_cells, scores, mu64, var64, score64, 0, 0, 0, nullptr, st
     if (n_max == 8 && (compact || !getenv("NBW_SCORE_LANES"))) {
@@ -1480,9 +1481,11 @@ int nbw_score_packed(nbw_ctx* ctx, const nbw_model* M, const void* cells, int64_
   }
   if (k > 0) {
     if (n_max == 8) return launch_parts<8, true>(ctx, np, weighted, P, c, n_cells, scores, mu64, var64, score64, k, distinct, index_base, oc, st);
+    if (compact) return launch_parts<16, true, true>(ctx, np, weighted, P, c, n_cells, scores, mu64, var64, score64, k, distinct, index_base, oc, st);
     return launch_parts<16, true>(ctx, np, weighted, P, c, n_cells, scores, mu64, var64, score64, k, distinct, index_base, oc, st);
   }
   if (n_max == 8) return launch_parts<8, false>(ctx, np, weighted, P, c, n_cells, scores, mu64, var64, score64, 0, 0, 0, nullptr, st);
+  if (compact) return launch_parts<16, false, true>(ctx, np, weighted, P, c, n_cells, scores, mu64, var64, score64, 0, 0, 0, nullptr, st);
   return launch_parts<16, false>(ctx, np, weighted, P, c, n_cells, scores, mu64, var64, score64, 0, 0, 0, nullptr, st);
 }
 
