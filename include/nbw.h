@@ -77,8 +77,11 @@ int nbw_wl_signatures(nbw_ctx* ctx, const void* cells, int64_t n_cells, int n_ma
                       uint64_t* keys, uint64_t* chks, void* stream);
 
 /* ---------------------------------------------------------------------------------------
- * (2) Dictionary build: global radix sort + unique that compacts keys into dense label ids —
+ * (2) Dictionary build: sort + unique that compacts keys into dense label ids —
  *     replaces `sorted(list(label_set))` + id assignment, weisfeiler_lehman.py:226-229,271-274.
+ *     Three regimes with the same result: up to 8192 keys one CTA does everything in shared memory (one launch);
+ *     above, a hash pre-dedup finds the distinct keys and only those are sorted (one extra stream sync inside);
+ *     more than 65536 distinct keys take eight LSD radix passes over all keys.
  * ids[i] = rank of keys[i] among the distinct valid keys (NBW_INVALID_ID for invalid keys);
  * uniq_keys/uniq_chks[0..D) = the dictionary in ascending key order (capacity `uniq_cap`).
  * key_bits: number of significant low key bits (8 for level 0, 64 otherwise).
@@ -93,7 +96,8 @@ int nbw_dict_build(nbw_ctx* ctx, const uint64_t* keys, const uint64_t* chks, int
 
 /* (1) + (2) for every WL level of a batch in one call — the whole relabelling loop of
  * WeisfeilerLehman.parse_input (weisfeiler_lehman.py:223-296): levels 0..h are relabelled and their dictionaries
- * built back to back on the stream, with ONE read-back of the dictionary sizes at the end.
+ * built back to back on the stream, with ONE read-back of the dictionary sizes at the end (batches above 8192
+ * node slots add one sync per level, see (2)).
  * ids: [h+1][N * n_max] u32; uniq_keys / uniq_chks: [h+1][N * n_max] u64 (level l's sorted dictionary at offset
  * l * N * n_max); dims_h: [h+1] dictionary sizes.  Syncs once.  NBW_ERR_HASH_COLLISION as for nbw_dict_build. */
 int nbw_wl_fit(nbw_ctx* ctx, const void* cells, int64_t n_cells, int n_max, int h, uint64_t seed,
@@ -335,7 +339,7 @@ typedef struct {
   const int32_t* final_label;
   double level_weight[NBW_MAX_LEVELS];
   int32_t weighted, undirected, rec_offset, rec_stride, label_base;
-  /* compact != 0 (n_max = 8 only): the part's record is the 8-byte WIRE form of a cell — half the PCIe bytes of a
+  /* compact != 0: the part's record is the WIRE form of a cell (n_max = 8: 8 bytes) — half the PCIe bytes of a
    * pool that arrives in host memory.  Little-endian u64: bits [3v, 3v+3) = palette index of node v's op code
    * (7 = no node), bits [24, 52) = the strict upper triangle of the adjacency, row by row (edge u -> v, u < v,
    * at bit 24 + u (15 - u) / 2 + (v - u - 1)): cells whose nodes are numbered topologically, at most 7 distinct
