@@ -599,3 +599,51 @@ def test_cpulist_parser_and_numa_binding_is_best_effort():
     before = os.sched_getaffinity(0)
     assert parallel.bind_to_gpu_numa_node(0) is None        # no GPU here: nothing read, nothing changed
     assert os.sched_getaffinity(0) == before
+
+
+def _decode_wire(rec, pal, n_max):
+    """Decoder of nbw_model.compact exactly as include/nbw.h states it (what the kernel prologues implement)."""
+    import numpy as np
+    from nasbowl_b200.cells import NO_NODE
+    N = rec.shape[0]
+    labels = np.full((N, n_max), NO_NODE, dtype=np.uint8)
+    succ = np.zeros((N, n_max), dtype=np.uint16)
+    words = rec.view(np.uint64).reshape(N, -1)
+    for i in range(N):
+        if n_max == 8:
+            w = int(words[i, 0])
+            idx = [(w >> (3 * v)) & 7 for v in range(8)]
+            none, tri, base = 7, w >> 24, lambda u: u * (15 - u) // 2
+        else:
+            w0 = int(words[i, 0])
+            idx = [(w0 >> (4 * v)) & 15 for v in range(16)]
+            none, tri, base = 15, int(words[i, 1]) | (int(words[i, 2]) << 64), lambda u: u * (31 - u) // 2
+        for v in range(n_max):
+            if idx[v] != none:
+                labels[i, v] = pal[idx[v]]
+            for t in range(v + 1, n_max):
+                if (tri >> (base(v) + (t - v - 1))) & 1:
+                    succ[i, v] |= 1 << t
+    return labels, succ
+
+
+def test_wire_records_round_trip_on_the_host():
+    """CellBatch.to_compact (8 bytes per 8-node cell, 24 per 16-node cell) against the layout written in nbw.h."""
+    import numpy as np
+    from nasbowl_b200 import synth
+    for fam, n_max, width in ((0, 8, 8), (1, 8, 8), (2, 16, 24)):
+        batch = synth.generate_cells_host(fam, 3, 0, 300)
+        rec, pal = batch.to_compact()
+        assert rec.shape == (300, width) and rec.dtype == np.uint8
+        labels, succ = _decode_wire(rec, pal, n_max)
+        assert np.array_equal(labels, batch.labels) and np.array_equal(succ, batch.succ)
+        # a caller-supplied palette (the model's) is honoured; an op outside it is refused
+        rec2, pal2 = batch.to_compact(palette=pal)
+        labels2, succ2 = _decode_wire(rec2, pal2, n_max)        # (unused palette entries may alias an op: still decodes)
+        assert np.array_equal(pal2, pal) and np.array_equal(labels2, batch.labels) and np.array_equal(succ2, batch.succ)
+        short = pal.copy()
+        present_codes = np.unique(batch.labels[batch.labels != 255])
+        short[:] = present_codes[0]
+        if len(present_codes) > 1:
+            with pytest.raises(ValueError):
+                batch.to_compact(palette=short)
