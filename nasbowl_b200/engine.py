@@ -303,19 +303,9 @@ class Engine:
         N = fit.n_cells
         code, dtype = self.GRAM_OUT[mode]
         if world > 1 and symmetric:
-            # the symmetric schedule makes row blocks unequal (block r0 holds the tiles right of its diagonal): deal
-            # blocks of at most 4096 rows greedily, largest first, to the least loaded rank (same answer on every rank)
-            block = min(block, 4096)
-        starts = list(range(0, N, block))
-        if world > 1 and symmetric:
-            load, owner = [0.0] * world, {}
-            for r0 in sorted(starts, key=lambda r: -(min(block, N - r) * (N - r))):
-                r = min(range(world), key=lambda i: (load[i], i))
-                owner[r0] = r
-                load[r] += min(block, N - r0) * (N - r0)
-            mine = [r0 for r0 in starts if owner[r0] == rank]
-        else:
-            mine = [r0 for i, r0 in enumerate(starts) if i % world == rank]
+            block = min(block, 4096)        # smaller blocks deal out more evenly (and 4096 is the fastest on one GPU too)
+        from .parallel import deal_row_blocks
+        mine = deal_row_blocks(N, block, world, symmetric)[rank]
         ld = _round_up(N, 16)
         rows_mine = sum(min(block, N - r0) for r0 in mine)
         out = self.empty((max(rows_mine, 1), ld), dtype)          # this rank's row blocks, stacked

@@ -88,6 +88,25 @@ def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
     return (rank * n_items) // world, ((rank + 1) * n_items) // world
 
 
+def deal_row_blocks(n_rows: int, block: int, world: int, symmetric: bool = True) -> List[List[int]]:
+    """Row blocks of a (symmetric) N x N Gram for every rank: starts[r] = first rows of rank r's blocks, ascending.
+    With the symmetric schedule a block starting at row r0 only computes the tiles right of its diagonal —
+    rows x (N - r0) of work — so equal blocks are unequal work: blocks are dealt largest first to the least loaded
+    rank (ties to the lowest rank: every rank computes the same answer without talking).  Otherwise round-robin."""
+    starts = list(range(0, n_rows, block))
+    if world <= 1:
+        return [starts]
+    if not symmetric:
+        return [[r0 for i, r0 in enumerate(starts) if i % world == r] for r in range(world)]
+    load = [0.0] * world
+    mine: List[List[int]] = [[] for _ in range(world)]
+    for r0 in sorted(starts, key=lambda r: (-(min(block, n_rows - r) * (n_rows - r)), r)):
+        r = min(range(world), key=lambda i: (load[i], i))
+        mine[r].append(r0)
+        load[r] += min(block, n_rows - r0) * (n_rows - r0)
+    return [sorted(m) for m in mine]
+
+
 def merge_topk(vals: np.ndarray, idx: np.ndarray, k: int, distinct: bool = True):
     """Merge candidate (value, global index) pairs into the global top-k: k largest DISTINCT
     values, each with the lowest index at which it occurs (np.unique(return_index=True) +

@@ -647,3 +647,20 @@ def test_wire_records_round_trip_on_the_host():
         if len(present_codes) > 1:
             with pytest.raises(ValueError):
                 batch.to_compact(palette=short)
+
+
+def test_gram_row_blocks_are_dealt_by_work():
+    """parallel.deal_row_blocks: every block exactly once, deterministic, and — for the symmetric schedule, where a
+    block's work is rows x (N - first row) — balanced to within one block of the mean."""
+    from nasbowl_b200 import parallel
+    N, B = 200_000, 4096
+    for world in (1, 2, 3, 8):
+        for symmetric in (True, False):
+            deal = parallel.deal_row_blocks(N, B, world, symmetric)
+            assert len(deal) == world and deal == parallel.deal_row_blocks(N, B, world, symmetric)
+            flat = sorted(r0 for m in deal for r0 in m)
+            assert flat == list(range(0, N, B))
+            if symmetric and world > 1:
+                work = [sum(min(B, N - r0) * (N - r0) for r0 in m) for m in deal]
+                assert max(work) - min(work) <= B * N
+                assert max(work) <= 1.02 * sum(work) / world
