@@ -57,6 +57,21 @@ GRAM_STRESS = dict(cells=200_000, h=3, block=4096,      # row block: 4096 measur
                    desc="Gram-only stress: 200k x 200k WL h=3 kernel matrix on NB101-shaped cells")
 
 
+def pool_sizes(w, world, pool_override=None):
+    """(candidates in total, candidates of rank r as a function) of a workload at `world` GPUs — shared by both arms
+    so that the CPU arm describes exactly the configuration the GPU arm ran."""
+    total = w["pool"] * world if w["scaling"] == "weak" else (pool_override or w["pool"])
+    if w["scaling"] == "weak" and pool_override:
+        total = pool_override * world
+    return total
+
+
+def workload_config(w, per_gpu, total, h_star):
+    """The static part of `config` (identical in the b200 arm and the --impl reference arm)."""
+    return {"workload": w["desc"] + ", %d-candidate EI pool per GPU (%d in total), top-5" % (per_gpu, total),
+            "h_star": h_star, "pool_per_gpu": per_gpu, "pool_total": total}
+
+
 def load_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -240,13 +255,16 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = S * args.steps / dt
     threads = blas_threads()
-    sample_desc = "%d candidates per step (of the pool), n_train=%d, h*=%d" % (S, w["n_train"], h_star)
+    world = max(1, args.gpus)
+    total = pool_sizes(w, world, args.pool)
+    per_gpu = total // world
+    sample_desc = ("%d candidates per step (a bounded sample of the %d-candidate pool; the step time scales linearly "
+                   "in the candidates), n_train=%d, h*=%d, CPU only" % (S, total, w["n_train"], h_star))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "candidates/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": w["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": w["desc"] + ", EI pool scoring",
-                   "h_star": h_star, "sample_per_step": S, "host": "CPU only"},
+        "config": dict(workload_config(w, per_gpu, total, h_star), sample_per_step=S),
         "cpu_baseline": {"value": value, "unit": "candidates/s", "cores": threads, "kind": "port", "sample": sample_desc},
         "e2e": {"value": value, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -274,9 +292,7 @@ def run_scoring(name, args, ctx):
     rank, world, eng, sampler, peaks, peak_src = ctx["rank"], ctx["world"], ctx["eng"], ctx["sampler"], ctx["peaks"], ctx["peak_src"]
     w = WORKLOADS[name]
     steps, warmup = args.steps, args.warmup
-    total = w["pool"] * world if w["scaling"] == "weak" else (args.pool or w["pool"])
-    if w["scaling"] == "weak" and args.pool:
-        total = args.pool * world
+    total = pool_sizes(w, world, args.pool)
     lo, hi = parallel.shard_range(total, rank, world)
     M = hi - lo
     train, y = make_training_set(w)
@@ -563,8 +579,8 @@ def run_scoring(name, args, ctx):
         "metric": METRIC, "value": value, "unit": "candidates/s", "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": elapsed_ms / steps, "higher_is_better": True, "scaling": w["scaling"],
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": w["desc"] + ", %d-candidate EI pool per GPU (%d in total), top-5" % (M, total),
-                   "h_star": h_star, "n_labels": int(pm.total_labels or pm.n_labels), "pool_per_gpu": M, "pool_total": total,
+        "config": dict(workload_config(w, M, total, h_star), **{
+                   "n_labels": int(pm.total_labels or pm.n_labels),
                    "l2": "inputs larger than L2: %d rotating pools x %.0f MB per GPU" % (n_pools, M * rec_bytes / 1e6),
                    "fused_topk": bool(fused), "pipeline": "one pool in flight: exchange of pool i under the scoring of pool i+1",
                    "fit_ms": fit_ms, "score_state_ms": state_ms, "fit_timing": "wall clock, from-scratch fit, best of 3 after 2 warm-ups",
@@ -576,7 +592,7 @@ def run_scoring(name, args, ctx):
                               "bo_iter_ms: the default policy (append path, i.e. rank-k refit, from 768 training cells on; refit below: "
                               "profiles/r02_incremental_bench.json), bo_iter_append_forced_ms: the append path at this size, "
                               "bo_iter_from_scratch_ms: incremental off",
-                   "model_bytes": pm.nbytes()},
+                   "model_bytes": pm.nbytes()}),
         "roofline": roof,
         "cpu_baseline": cpu_baseline,
         "e2e": {"value": total * e_steps / (e2e_ms / 1e3), "unit": "candidates/s",

@@ -206,6 +206,52 @@ def cfg1_case(R, seed=11, n_train=50, n_test=400):
 
 
 
+def baseline_size_case(R, family, seed, n_train, cands, n_pool, n_eval):
+    """A fixture at the TRAINING-SET SIZE of BASELINE.json configs[1] / configs[2] (NB201 n=150 with the
+    h grid 0..5; NB101 n=500 at h=2), from the unmodified reference: the integer Gram at the chosen depth, the
+    marginal-likelihood grid, the fitted noise, the batched posterior over `n_pool` candidates, and the
+    reference's own per-candidate EI (`GraphExpectedImprovement.eval`, acquisitions.py:59-80) and
+    `propose_location` top-5 (acquisitions.py:94-113) over the first `n_eval` of them (the reference needs
+    0.1-1 s per candidate at these sizes, which is what bounds the slice)."""
+    from bayesopt.utils import compute_log_marginal_likelihood, compute_pd_inverse
+    seed_all(seed)
+    graphs = sample_cells(R, family, n_train + n_pool)
+    vocab = OpVocab()
+    batch = pack_networkx(graphs, vocab)
+    train, pool = graphs[:n_train], graphs[n_train:]
+    # a target the cells explain (edges + 3x3 operations) plus noise: with pure noise every pool EI sits 4-5 sigma
+    # in the tail (1e-8 and below), where the reference's fp32 posterior decides the ranking by rounding
+    y = torch.tensor([0.25 * g.number_of_edges() + 0.5 * sum('3x3' in d['op_name'] for _, d in g.nodes(data=True))
+                      for g in train], dtype=torch.float32) + 0.1 * torch.randn(n_train)
+    out = {"records": batch.to_records(), "n_max": np.int64(batch.n_max), "op_names": np.array(vocab.names),
+           "n_train": np.int64(n_train), "y": y.numpy().astype(np.float32),
+           "cands": np.array(cands, dtype=np.int64), "n_eval": np.int64(n_eval)}
+    gp = R.GraphGP(train, y.clone(), [R.WeisfilerLehman(h=2, oa=False)])
+    gp.fit(wl_subtree_candidates=cands, optimize_lik=True, max_lik=0.01)
+    with torch.no_grad():
+        h = int(gp.kernels[0].h)
+        out["gp_h"], out["gp_lik"], out["gp_nlml"] = np.int64(h), np.float64(gp.likelihood), np.float64(gp.nlml)
+        out["gp_logDetK"] = np.float64(gp.logDetK)
+        kk = R.WeisfilerLehman(h=2, oa=False)
+        grid = []
+        for hc in cands:                                   # as _grid_search_wl_kernel does, gp.py:521-527
+            kk.change_kernel_params({'h': hc})
+            Kh = kk.fit_transform(train, rebuild_model=True, save_gram_matrix=True)
+            K_i, ld = compute_pd_inverse(Kh, 1e-3)
+            grid.append(float(-compute_log_marginal_likelihood(K_i, ld, gp.y)))
+            if hc == h:
+                out["Kraw"] = np.rint(Kh.numpy()).astype(np.int32)
+        out["gp_grid"] = np.array(grid)
+        mu, cov = gp.predict(pool)
+        out["gp_mu"], out["gp_var"] = mu.numpy(), np.diag(cov.numpy()).copy()
+        ei = R.GraphExpectedImprovement(gp)
+        out["incumbent"] = np.float64(ei._get_incumbent())
+        out["ei"] = np.array([float(ei.eval(c)) for c in pool[:n_eval]])
+        _, _, idx = R.GraphExpectedImprovement(gp).propose_location(pool[:n_eval], top_n=5)
+        out["top5"] = np.array(sorted(int(i) for i in idx), dtype=np.int64)
+    return out
+
+
 def dmu_case(R, n_train=30, n_pool=20):
     """Interpretability gradients (gp.py:296-476) from the unmodified reference: per family and
     base kernel, GraphGP.dmu_dphi over a pool (raw Jacobian-vector products + the embedding they
@@ -295,6 +341,12 @@ def main():
         return
     if len(sys.argv) > 1 and sys.argv[1] == "dmu":        # only the interpretability fixture
         np.savez_compressed(os.path.join(OUT, "dmu_dphi.npz"), **dmu_case(R))
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "sizes":      # only the BASELINE-size fixtures (minutes of reference time)
+        np.savez_compressed(os.path.join(OUT, "cfg2_nb201_n150.npz"),
+                            **baseline_size_case(R, "nasbench201", 202, 150, tuple(range(6)), 400, 64))
+        np.savez_compressed(os.path.join(OUT, "cfg3_nb101_n500.npz"),
+                            **baseline_size_case(R, "nasbench101", 303, 500, (2,), 400, 32))
         return
     os.makedirs(OUT, exist_ok=True)
     np.savez_compressed(os.path.join(OUT, "appendix_b.npz"), **appendix_b(R))

@@ -30,7 +30,13 @@ def test_reference_arm_json_line():
     assert d["impl"] == "reference" and d["value"] > 0 and d["unit"] == "candidates/s"
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert d["gpu_launches"] == 0 and d["vs_baseline"] is None and "workload" in d["config"]
+    assert d["gpu_launches"] == 0 and d["vs_baseline"] is None
+    # the CPU arm names exactly the configuration the B200 arm runs at this N (the static part of `config`)
+    import bench
+    w = bench.WORKLOADS["cfg2"]
+    want = bench.workload_config(w, w["pool"], w["pool"], d["config"]["h_star"])
+    assert {k: d["config"][k] for k in want} == want
+    assert "1000000-candidate EI pool per GPU (1000000 in total)" in d["config"]["workload"]
 
 
 def test_reference_arm_other_ranks_exit_quietly():

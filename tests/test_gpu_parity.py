@@ -692,6 +692,43 @@ def test_cfg1_regression_case():
         assert max(vals) - min(vals) < 1e-4 * max(1.0, abs(max(vals)))
 
 
+@pytest.mark.parametrize("name", ["cfg2_nb201_n150", "cfg3_nb101_n500"])
+def test_baseline_training_set_sizes_vs_reference_golden(eng, name):
+    """BASELINE configs[1] / configs[2] at their training-set sizes against vectors of the UNMODIFIED reference
+    (tests/golden/cfg2_nb201_n150.npz, cfg3_nb101_n500.npz; make_golden.py::baseline_size_case): chosen depth, fitted
+    noise, integer Gram bit-exact, marginal-likelihood grid; posterior / EI at the reference's fp32 tolerance and at
+    1e-6 against the fp64 oracle; the reference's own propose_location top-5."""
+    from nasbowl_b200.bayesopt import GraphExpectedImprovement, GraphGP
+    from nasbowl_b200.kernels import WeisfilerLehman
+    z, batch = load_golden(name)
+    n = int(z["n_train"])
+    train, pool = batch[:n], batch[n:]
+    cands = tuple(int(c) for c in z["cands"])
+    gp = GraphGP(train, torch.tensor(z["y"]), [WeisfilerLehman(h=2)])
+    gp.fit(wl_subtree_candidates=cands, optimize_lik=True, max_lik=0.01)
+    st = gp_oracle.gp_fit(train, z["y"].astype(np.float64), h_candidates=cands, optimize_lik=True, max_lik=0.01)
+    assert gp.kernels[0].h == st.h == int(z["gp_h"])
+    assert np.float32(gp.likelihood) == np.float32(z["gp_lik"])
+    np.testing.assert_allclose(float(gp.nlml), st.nlml, rtol=1e-9)
+    np.testing.assert_allclose(float(gp.nlml), float(z["gp_nlml"]), rtol=1e-5)
+    fit = eng.wl_fit(eng.upload_cells(train), train.n_max, st.h, False)
+    assert np.array_equal(eng.gram(fit.phi, fit.phi, 0, fit.k_end(st.h)).cpu().numpy(), z["Kraw"])
+    acq = GraphExpectedImprovement(gp)
+    s, mu, var, s64 = acq.score_pool(pool, want64=True)
+    mu, var, s64 = mu.cpu().numpy(), var.cpu().numpy(), s64.cpu().numpy()
+    mu_o, var_o = gp_oracle.gp_predict_diag(st, train, pool)
+    ei_o = gp_oracle.expected_improvement(mu_o, var_o, gp_oracle.incumbent(st))
+    np.testing.assert_allclose(mu, mu_o, rtol=RTOL64, atol=1e-9)
+    np.testing.assert_allclose(var, var_o, rtol=RTOL64, atol=1e-12)
+    np.testing.assert_allclose(s64, ei_o, rtol=RTOL64, atol=1e-12)
+    np.testing.assert_allclose(mu, z["gp_mu"], rtol=2e-3, atol=1e-2)               # fp32 reference
+    np.testing.assert_allclose(var, z["gp_var"], rtol=5e-2, atol=5e-3)
+    ne = int(z["n_eval"])
+    np.testing.assert_allclose(s64[:ne], z["ei"], rtol=5e-2, atol=2e-3)
+    _, eis, idx = acq.propose_location(pool[:ne], top_n=5)
+    assert set(int(i) for i in idx) == set(int(i) for i in z["top5"])
+
+
 @pytest.mark.parametrize("family,h,oa", [(1, 5, False), (1, 5, True), (0, 5, False), (2, 4, False)])
 def test_stable_suffix_fast_path_is_exact(eng, family, h, oa):
     """When the training dictionary stops refining, deeper WL levels inherit membership and take the

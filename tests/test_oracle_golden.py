@@ -151,6 +151,34 @@ def test_cfg1_regression_case():
         assert max(vals) - min(vals) < 1e-4 * max(1.0, abs(max(vals)))
 
 
+@pytest.mark.parametrize("name", ["cfg2_nb201_n150", "cfg3_nb101_n500"])
+def test_baseline_training_set_sizes(name):
+    """BASELINE.json configs[1] / configs[2] at their TRAINING-SET sizes (NB201 n=150 with the h grid 0..5;
+    NB101 n=500 at h=2) — oracle vs the unmodified reference (make_golden.py::baseline_size_case): integer Gram
+    bit-exact, marginal-likelihood grid and chosen depth, fitted noise, batched posterior over 400 candidates, and
+    the reference's own per-candidate EI / propose_location top-5 on a slice.  The reference's posterior is fp32
+    (K_i, K_s: gp.py:271-276), which sets the tolerances on mu / var / EI."""
+    z, batch = load_golden(name)
+    n = int(z["n_train"])
+    train, pool = batch[:n], batch[n:]
+    cands = tuple(int(c) for c in z["cands"])
+    st = gp_oracle.gp_fit(train, z["y"].astype(np.float64), h_candidates=cands, optimize_lik=True, max_lik=0.01)
+    assert st.h == int(z["gp_h"]) and st.lik == float(z["gp_lik"])
+    assert np.array_equal(wl_oracle.gram_raw(train, st.h), z["Kraw"])
+    np.testing.assert_allclose(np.array(st.nlml_grid), z["gp_grid"], rtol=1e-5)
+    np.testing.assert_allclose(st.nlml, z["gp_nlml"], rtol=1e-5)
+    np.testing.assert_allclose(st.logDetK, z["gp_logDetK"], rtol=1e-5)
+    mu, var = gp_oracle.gp_predict_diag(st, train, pool)
+    np.testing.assert_allclose(mu, z["gp_mu"], rtol=2e-3, atol=1e-2)
+    np.testing.assert_allclose(var, z["gp_var"], rtol=5e-2, atol=5e-3)
+    inc = gp_oracle.incumbent(st)
+    assert inc == pytest.approx(float(z["incumbent"]), rel=1e-6)
+    ne = int(z["n_eval"])
+    ei = gp_oracle.expected_improvement(mu[:ne], var[:ne], inc)
+    np.testing.assert_allclose(ei, z["ei"], rtol=5e-2, atol=2e-3)
+    assert set(int(i) for i in gp_oracle.top_n_distinct(ei, 5)) == set(int(i) for i in z["top5"])
+
+
 def _dmu_fixture(family):
     from nasbowl_b200.cells import CellBatch
     z = np.load(os.path.join(os.path.dirname(__file__), "golden", "dmu_dphi.npz"))
