@@ -240,7 +240,9 @@ def baseline_size_case(R, family, seed, n_train, cands, n_pool, n_eval):
             K_i, ld = compute_pd_inverse(Kh, 1e-3)
             grid.append(float(-compute_log_marginal_likelihood(K_i, ld, gp.y)))
             if hc == h:
-                out["Kraw"] = np.rint(Kh.numpy()).astype(np.int32)
+                K = np.rint(Kh.numpy()).astype(np.int64)      # symmetric, entries <= 255 on these sets: the packed
+                assert np.array_equal(K, K.T) and 0 <= K.min() and K.max() < 256       # upper triangle as bytes
+                out["Kraw_triu"] = K[np.triu_indices(n_train)].astype(np.uint8)
         out["gp_grid"] = np.array(grid)
         mu, cov = gp.predict(pool)
         out["gp_mu"], out["gp_var"] = mu.numpy(), np.diag(cov.numpy()).copy()
@@ -347,6 +349,11 @@ def main():
                             **baseline_size_case(R, "nasbench201", 202, 150, tuple(range(6)), 400, 64))
         np.savez_compressed(os.path.join(OUT, "cfg3_nb101_n500.npz"),
                             **baseline_size_case(R, "nasbench101", 303, 500, (2,), 400, 32))
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "sizes-darts":    # configs[3]'s training-set size, one WL kernel (the
+        # reference has no two-cells-per-example form: darts_objectives.py:193 keeps the normal cell's graph only)
+        np.savez_compressed(os.path.join(OUT, "cfg4_darts_n1000.npz"),
+                            **baseline_size_case(R, "darts", 404, 1000, (2,), 200, 16))
         return
     os.makedirs(OUT, exist_ok=True)
     np.savez_compressed(os.path.join(OUT, "appendix_b.npz"), **appendix_b(R))

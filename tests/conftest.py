@@ -23,6 +23,16 @@ def load_golden(name):
     return z, batch
 
 
+def golden_kraw(z):
+    """The integer Gram of a BASELINE-size fixture (stored as the packed upper triangle, u8)."""
+    n = int(z["n_train"])
+    K = np.zeros((n, n), dtype=np.int64)
+    iu = np.triu_indices(n)
+    K[iu] = z["Kraw_triu"]
+    K.T[iu] = z["Kraw_triu"]
+    return K
+
+
 @pytest.fixture(params=FAMILIES)
 def family(request):
     z, batch = load_golden(request.param)

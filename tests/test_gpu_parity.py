@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import load_golden
+from conftest import golden_kraw, load_golden
 from nasbowl_b200 import synth
 from nasbowl_b200.cells import NO_NODE, CellBatch
 from oracle import gp_oracle, wl_oracle
@@ -692,7 +692,7 @@ def test_cfg1_regression_case():
         assert max(vals) - min(vals) < 1e-4 * max(1.0, abs(max(vals)))
 
 
-@pytest.mark.parametrize("name", ["cfg2_nb201_n150", "cfg3_nb101_n500"])
+@pytest.mark.parametrize("name", ["cfg2_nb201_n150", "cfg3_nb101_n500", "cfg4_darts_n1000"])
 def test_baseline_training_set_sizes_vs_reference_golden(eng, name):
     """BASELINE configs[1] / configs[2] at their training-set sizes against vectors of the UNMODIFIED reference
     (tests/golden/cfg2_nb201_n150.npz, cfg3_nb101_n500.npz; make_golden.py::baseline_size_case): chosen depth, fitted
@@ -712,7 +712,7 @@ def test_baseline_training_set_sizes_vs_reference_golden(eng, name):
     np.testing.assert_allclose(float(gp.nlml), st.nlml, rtol=1e-9)
     np.testing.assert_allclose(float(gp.nlml), float(z["gp_nlml"]), rtol=1e-5)
     fit = eng.wl_fit(eng.upload_cells(train), train.n_max, st.h, False)
-    assert np.array_equal(eng.gram(fit.phi, fit.phi, 0, fit.k_end(st.h)).cpu().numpy(), z["Kraw"])
+    assert np.array_equal(eng.gram(fit.phi, fit.phi, 0, fit.k_end(st.h)).cpu().numpy(), golden_kraw(z))
     acq = GraphExpectedImprovement(gp)
     s, mu, var, s64 = acq.score_pool(pool, want64=True)
     mu, var, s64 = mu.cpu().numpy(), var.cpu().numpy(), s64.cpu().numpy()

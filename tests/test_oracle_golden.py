@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import load_golden
+from conftest import golden_kraw, load_golden
 from nasbowl_b200.cells import CellBatch
 from oracle import gp_oracle, wl_oracle
 
@@ -151,7 +151,7 @@ def test_cfg1_regression_case():
         assert max(vals) - min(vals) < 1e-4 * max(1.0, abs(max(vals)))
 
 
-@pytest.mark.parametrize("name", ["cfg2_nb201_n150", "cfg3_nb101_n500"])
+@pytest.mark.parametrize("name", ["cfg2_nb201_n150", "cfg3_nb101_n500", "cfg4_darts_n1000"])
 def test_baseline_training_set_sizes(name):
     """BASELINE.json configs[1] / configs[2] at their TRAINING-SET sizes (NB201 n=150 with the h grid 0..5;
     NB101 n=500 at h=2) — oracle vs the unmodified reference (make_golden.py::baseline_size_case): integer Gram
@@ -164,7 +164,7 @@ def test_baseline_training_set_sizes(name):
     cands = tuple(int(c) for c in z["cands"])
     st = gp_oracle.gp_fit(train, z["y"].astype(np.float64), h_candidates=cands, optimize_lik=True, max_lik=0.01)
     assert st.h == int(z["gp_h"]) and st.lik == float(z["gp_lik"])
-    assert np.array_equal(wl_oracle.gram_raw(train, st.h), z["Kraw"])
+    assert np.array_equal(wl_oracle.gram_raw(train, st.h), golden_kraw(z))
     np.testing.assert_allclose(np.array(st.nlml_grid), z["gp_grid"], rtol=1e-5)
     np.testing.assert_allclose(st.nlml, z["gp_nlml"], rtol=1e-5)
     np.testing.assert_allclose(st.logDetK, z["gp_logDetK"], rtol=1e-5)
