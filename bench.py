@@ -217,6 +217,18 @@ def blas_threads():
         return os.cpu_count() or 1
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm raises the BLAS pools back to the cores this
+    process may run on (the arm is timed "with all the host threads it can use")."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=n)              # not a context manager here: the limit stays
+    except Exception:
+        pass
+    return n
+
+
 def fit_gp(w, gp, train, y):
     if w["slots"] == 1:
         gp.fit(wl_subtree_candidates=w["h_grid"], optimize_lik=True, max_lik=0.01)
@@ -241,6 +253,7 @@ def run_reference(args):
     from nasbowl_b200 import synth
     from nasbowl_b200.cells import CellBatch
     w = WORKLOADS[args.workload]
+    use_all_host_threads()
     train, y = make_training_set(w)
     S = args.ref_sample
     samples = []
