@@ -86,7 +86,7 @@ class _Optim32:
 class GraphGP:
     def __init__(self, train_x, train_y, kernels: list, vectorial_features: list = None, likelihood=1e-3,
                  weights=None, vector_theta_bounds: tuple = (1e-5, 0.1), graph_theta_bounds: tuple = (1e-1, 1.e1),
-                 verbose=False, n_max=None):
+                 verbose=False, n_max=None, out_dtype=None):
         assert len(train_x) == train_y.shape[0], 'mismatch of length between train and test GP'
         if not isinstance(train_x, (CellBatch, CellSlots)):
             # (extension: an example may be a TUPLE of graphs, one per record slot — "normal | reduce" —
@@ -121,6 +121,10 @@ class GraphGP:
         self.graph_theta_bounds = graph_theta_bounds
         self.verbose = verbose
         self.n_max = n_max         # force 16-node records when pools may hold larger cells than train
+        # The GP is evaluated in fp64 and returns fp64 tensors; the reference returns fp32 (K, K_i, mu, cov:
+        # combine_kernels.py:36, utils.py:140).  out_dtype=torch.float32 casts what predict() / K / K_i hand out,
+        # for callers that concatenate them with fp32 tensors.
+        self.out_dtype = out_dtype
         self.theta_vector = None
         self.layer_weights = None
         self.nlml = None
@@ -551,7 +555,7 @@ class GraphGP:
         if not self._fitted or self._dev is None:
             return None
         if self._dev['K_host'] is None:
-            self._dev['K_host'] = self._dev['K'].cpu()
+            self._dev['K_host'] = self._out(self._dev['K'].cpu())
         return self._dev['K_host']
 
     @property
@@ -563,8 +567,12 @@ class GraphGP:
             eng, Linv, n = self._dev['eng'], self._dev['Linv'], self.n
             Ki = eng.empty((n, n), torch.float64)
             eng.gemm(True, False, n, n, n, 1.0, Linv, n, Linv, n, 0.0, Ki, n)
-            self._dev['Ki_host'] = Ki.cpu()
+            self._dev['Ki_host'] = self._out(Ki.cpu())
         return self._dev['Ki_host']
+
+    def _out(self, t):
+        dt = getattr(self, 'out_dtype', None)
+        return t if dt is None else t.to(dt)
 
     def _require_fit(self):
         if not self._fitted or self._dev is None:
@@ -603,7 +611,7 @@ class GraphGP:
         eng.gemm(True, False, M, 1, n, 1.0, K_s, N, d['alpha'], 1, 0.0, mu, 1)
         cov = eng.posterior_cov_finish(K_ss, N, Q, M, self.likelihood, float(self.y_std))
         mu_s = unnormalize_y(mu.cpu(), float(self.y_mean), float(self.y_std))
-        return mu_s, cov.cpu()
+        return self._out(mu_s), self._out(cov.cpu())
 
     # ------------------------------------------------------------------ fused pool path
     def _score_state(self):

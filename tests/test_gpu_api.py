@@ -419,3 +419,23 @@ def test_incremental_refit_matches_from_scratch(fam, n0, h_grid):
     gp.reset_XY(cells[5:n0 + 5], y_all[5:n0 + 5])
     gp.fit(wl_subtree_candidates=h_grid, optimize_lik=True, max_lik=0.01)
     assert not gp.last_fit_incremental
+
+
+def test_reference_output_dtypes():
+    """out_dtype=torch.float32 hands out K, K_i, mu and cov in the reference's dtype (combine_kernels.py:36,
+    utils.py:140, gp.py:271-283) — rounded from the fp64 evaluation, which is what the default returns."""
+    from nasbowl_b200.bayesopt import GraphGP
+    from nasbowl_b200.kernels import WeisfilerLehman
+    z, batch = load_golden("cfg1_nb101")
+    n = int(z["n_train"])
+    train, test = batch[:n], batch[n:n + 64]
+    out = {}
+    for dt in (None, torch.float32):
+        gp = GraphGP(train, torch.tensor(z["y"]), [WeisfilerLehman(h=2)], out_dtype=dt)
+        gp.fit(wl_subtree_candidates=(1, 2), optimize_lik=True, max_lik=0.01)
+        out[dt] = (gp.K, gp.K_i) + tuple(gp.predict(test))
+    for a, b in zip(out[None], out[torch.float32]):
+        assert a.dtype == torch.float64 and b.dtype == torch.float32 and a.shape == b.shape
+        assert torch.equal(a.to(torch.float32), b)
+    # usable next to the reference's own fp32 tensors
+    assert torch.cat([out[torch.float32][2], torch.zeros(3)]).dtype == torch.float32
