@@ -133,6 +133,8 @@ class GraphGP:
         self._fitted = False
         self._dev = None           # device state of the last fit (not pickled)
         self._prev = None          # ... of the fit before reset_XY: the next fit may append to it
+        self.pack_cache = True     # False: every fit() walks all of train_x again (see _pack_train)
+        self._pack_memo = None
         self.incremental = True    # False: every fit() starts from scratch
         # measured (profiles/r02_incremental_bench.json): appending 5 cells beats a from-scratch fit from ~750 cells on
         # (4.8 vs 5.3 ms at 1000, 18 vs 31 ms at 4000); below that the whole fit is 1.5-3 ms and the bookkeeping loses
@@ -163,6 +165,51 @@ class GraphGP:
             return CellSlots([pack_networkx([g[i] for g in gr], k0.vocab, node_label=k0.node_label)
                               for i in range(n_slots)])
         return CellSlots([pack_networkx(gr, k0.vocab, node_label=k0.node_label)])
+
+    @staticmethod
+    def _graph_sig(x):
+        """(nodes, edges) of an example — or of every cell of a multi-cell example — read off the networkx
+        dictionaries directly (number_of_edges() alone costs 3 us per graph, half a pack)."""
+        if isinstance(x, tuple):
+            return tuple((len(g._node), sum(map(len, g._adj.values()))) for g in x)
+        return len(x._node), sum(map(len, x._adj.values()))
+
+    def _pack_train(self) -> CellSlots:
+        """self.x as records, re-using the records packed for the previous fit for the examples both lists share as
+        a prefix.  The reference's BO loops append a batch to x per iteration and refit
+        (nasbench_optimisation.py:209-213, run_darts.py:168-170); walking networkx objects costs ~7 us per cell
+        (~11 for DARTS cells), which from a few hundred examples on is more than the device side of the fit.  An
+        example counts as unchanged if it is the SAME object with the same node and edge counts (graphs edited in
+        place between fits beyond that need `gp.pack_cache = False`)."""
+        x = self.x
+        if isinstance(x, (CellBatch, CellSlots)) or not getattr(self, 'pack_cache', True):
+            return self._pack(x)
+        x = list(x)
+        wl = [k for k in self.kernels if isinstance(k, WeisfilerLehman)]
+        if not wl or not len(x):
+            return self._pack(x)
+        memo = getattr(self, '_pack_memo', None)
+        sig = self._graph_sig
+        keep, sigs = 0, []
+        if memo is not None and memo['vocab'] is wl[0].vocab and memo['label'] == wl[0].node_label:
+            for a, b, sb in zip(x, memo['objs'], memo['sigs']):
+                if a is not b:
+                    break
+                sa = sig(a)
+                if sa != sb:
+                    break
+                sigs.append(sa)
+            keep = len(sigs)
+        if keep == 0:
+            slots = self._pack(x)
+        elif keep == len(x):
+            # (a shorter list: like a fresh pack, 16-node records only if a cell needs them)
+            slots = memo['slots'] if keep == len(memo['objs']) else memo['slots'][:keep].narrow()
+        else:
+            slots = CellSlots.concat([memo['slots'][:keep], self._pack(x[keep:])]).narrow()
+        sigs.extend(sig(g) for g in x[keep:])
+        self._pack_memo = dict(objs=x, sigs=sigs, slots=slots, vocab=wl[0].vocab, label=wl[0].node_label)
+        return slots
 
     @staticmethod
     def _kernel_view(slots: CellSlots, k) -> CellBatch:
@@ -312,7 +359,7 @@ class GraphGP:
 
     def _fit(self, eng, iters, optimizer, wl_subtree_candidates, optimize_lik, max_lik, optimize_wl_layer_weights,
              optimizer_kwargs):
-        slots = self._pack(self.x)
+        slots = self._pack_train()
         if self.n_max is not None:
             slots = slots.widen(self.n_max)
         y_dev = self._y_device(eng)
@@ -873,6 +920,7 @@ class GraphGP:
         st = dict(self.__dict__)
         st['_dev'] = None
         st['_prev'] = None
+        st['_pack_memo'] = None    # (re-derived from x at the next fit)
         st['_fitted'] = False      # device state does not travel; call fit() after unpickling
         return st
 

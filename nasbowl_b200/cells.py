@@ -217,6 +217,15 @@ class CellBatch:
         succ[:, :self.n_max] = self.succ
         return CellBatch(n_max, labels, succ)
 
+    def fits_8(self) -> bool:
+        return self.n_max == 8 or not len(self) or bool((self.labels[:, 8:] == NO_NODE).all())
+
+    def narrow(self) -> "CellBatch":
+        """The 16-byte form of a 16-node batch none of whose cells has more than 8 nodes (else self)."""
+        if self.n_max == 8 or not self.fits_8():
+            return self
+        return CellBatch(8, np.ascontiguousarray(self.labels[:, :8]), np.ascontiguousarray(self.succ[:, :8]))
+
     def to_undirected(self) -> "CellBatch":
         """Symmetrise adjacency (reference kernels/utils.py:511-521 via `undirected=True`)."""
         s = self.succ.astype(np.uint32)
@@ -285,6 +294,12 @@ class CellSlots:
 
     def widen(self, n_max: int) -> "CellSlots":
         return self if n_max == self.n_max else CellSlots([s.widen(n_max) for s in self.slots])
+
+    def narrow(self) -> "CellSlots":
+        """8-node records when no slot holds a larger cell (else self)."""
+        if self.n_max == 8 or not all(s.fits_8() for s in self.slots):
+            return self
+        return CellSlots([s.narrow() for s in self.slots])
 
     def to_records(self) -> np.ndarray:
         return np.concatenate([s.to_records() for s in self.slots], axis=1)

@@ -345,6 +345,18 @@ def test_networkx_entry_points_match_packed(family):
         gp.predict(g_pool)
     gp.fit(wl_subtree_candidates=(0, 1), optimize_lik=True)
     assert gp.K.shape == (20, 20)
+    # growing the list again re-uses the records of the 20 cells already packed (GraphGP._pack_train): same fit as
+    # a GP that sees the list for the first time
+    gp.reset_XY(g_train[:30], y[:30])
+    gp.likelihood = 1e-3                                      # (the grid search starts from the current noise, Q5)
+    gp.fit(wl_subtree_candidates=(0, 1, 2), optimize_lik=True)
+    fresh = GraphGP(g_train[:30], y[:30], [WeisfilerLehman(h=2)])
+    fresh.fit(wl_subtree_candidates=(0, 1, 2), optimize_lik=True)
+    assert gp.kernels[0].h == fresh.kernels[0].h and gp.likelihood == fresh.likelihood
+    np.testing.assert_allclose(gp.K.numpy(), fresh.K.numpy(), rtol=1e-12)
+    mu2, _ = gp.predict(g_pool)
+    mu3, _ = fresh.predict(g_pool)
+    np.testing.assert_allclose(mu2.numpy(), mu3.numpy(), rtol=1e-9, atol=1e-12)
 
 
 def test_appendix_b_known_answer():

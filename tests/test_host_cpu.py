@@ -664,3 +664,67 @@ def test_gram_row_blocks_are_dealt_by_work():
                 work = [sum(min(B, N - r0) * (N - r0) for r0 in m) for m in deal]
                 assert max(work) - min(work) <= B * N
                 assert max(work) <= 1.02 * sum(work) / world
+
+
+def test_training_set_is_packed_incrementally():
+    """GraphGP._pack_train: a refit after reset_XY(x + new_x, ...) walks only the new networkx objects (the BO loops
+    of the reference append a batch per iteration), an edited example invalidates the cache from its position on,
+    and the records always equal those of a full pack."""
+    import pickle
+    from nasbowl_b200.bayesopt import GraphGP
+    from nasbowl_b200.cells import CellSlots
+    from nasbowl_b200.kernels import WeisfilerLehman
+    graphs = synth.generate_cells_host(1, 5, 0, 60).to_networkx(OpVocab(synth.FAMILY_OPS[1]))
+    wide = synth.generate_cells_host(2, 5, 0, 3).to_networkx(OpVocab(synth.FAMILY_OPS[2]))   # DARTS-shaped: 16-node records
+    y = torch.randn(70)
+    gp = GraphGP(graphs[:40], y[:40], [WeisfilerLehman(h=2)])
+    walked = []
+    pack = gp._pack
+    gp._pack = lambda gr: (walked.append(len(list(gr))), pack(gr))[1]
+
+    def full(x):
+        return pack_networkx(x, OpVocab(list(gp.kernels[0].vocab.names))).to_records()
+
+    s = gp._pack_train()
+    assert walked == [40] and np.array_equal(s.to_records(), full(graphs[:40]))
+    gp._pack_train()
+    assert walked == [40]                                                      # nothing new: nothing walked
+    gp.reset_XY(graphs[:45], y[:45])
+    s = gp._pack_train()
+    assert walked == [40, 5] and len(s) == 45 and np.array_equal(s.to_records(), full(graphs[:45]))
+    # wider cells in the tail widen the whole batch
+    x = graphs[:45] + wide
+    gp.reset_XY(x, y[:48])
+    s = gp._pack_train()
+    assert walked == [40, 5, 3] and s.n_max == 16 and np.array_equal(s.to_records(), full(x))
+    # a shorter list that is a prefix of the cached one
+    gp.reset_XY(graphs[:30], y[:30])
+    s = gp._pack_train()
+    assert walked == [40, 5, 3] and np.array_equal(s.to_records(), full(graphs[:30]))
+    # an example edited in place (a node removed) is re-walked together with everything after it
+    g = graphs[10]
+    g.remove_node(max(g.nodes))
+    s = gp._pack_train()
+    assert walked == [40, 5, 3, 20] and np.array_equal(s.to_records(), full(graphs[:30]))
+    # a different object at the same position
+    x = graphs[:29] + [graphs[50]]
+    gp.reset_XY(x, y[:30])
+    s = gp._pack_train()
+    assert walked[-1] == 1 and np.array_equal(s.to_records(), full(x))
+    # switched off: everything is walked; packed inputs pass through
+    gp.pack_cache = False
+    gp._pack_train()
+    assert walked[-1] == 30
+    gp.pack_cache = True
+    gp._pack = pack
+    assert pickle.loads(pickle.dumps(gp))._pack_memo is None
+    # examples made of two cells (record slots)
+    pairs = [(a, b) for a, b in zip(graphs[:20], graphs[20:40])]
+    gp2 = GraphGP(pairs[:15], y[:15], [WeisfilerLehman(h=2, slot=0), WeisfilerLehman(h=2, slot=1)])
+    a = gp2._pack_train()
+    gp2.reset_XY(pairs, y[:20])
+    b = gp2._pack_train()
+    assert isinstance(b, CellSlots) and b.n_slots == 2 and len(b) == 20
+    assert np.array_equal(b.to_records()[:15], a.to_records())
+    ref = CellSlots([pack_networkx([p[i] for p in pairs], OpVocab(list(gp2.kernels[0].vocab.names))) for i in range(2)])
+    assert np.array_equal(b.to_records(), ref.to_records())
