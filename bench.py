@@ -209,6 +209,22 @@ def oracle_score(w, st, inc, train, sample_batches, chunk=2000):
     return ei, gp_oracle.top_n_distinct(ei.astype(np.float32), TOP_N)
 
 
+def oracle_score_per_candidate(w, st, train, sample, count):
+    """The reference's ACTUAL propose_location path (acquisitions.py:94-113): one `eval` per candidate, each a
+    predict on that candidate alone plus `_get_incumbent`'s predict on the whole training set (acquisitions.py:59-92).
+    Restated with the oracle's (cheaper) train-by-pool features; single-kernel workloads only.  Returns seconds."""
+    from oracle import gp_oracle
+    if w["slots"] != 1:
+        return None
+    t0 = time.perf_counter()
+    for i in range(count):
+        mu, var = gp_oracle.gp_predict_diag(st, train, sample[i:i + 1])
+        mu_t, _ = gp_oracle.gp_predict_diag(st, train, train)
+        inc = float(st.y_raw[int(np.argmax(mu_t))])
+        gp_oracle.expected_improvement(mu, var, inc)
+    return time.perf_counter() - t0
+
+
 def blas_threads():
     try:
         from threadpoolctl import threadpool_info
@@ -268,6 +284,8 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = S * args.steps / dt
     threads = blas_threads()
+    P = min(20, S)
+    dt_pc = oracle_score_per_candidate(w, st, train, samples[0][0], P)
     world = max(1, args.gpus)
     total = pool_sizes(w, world, args.pool)
     per_gpu = total // world
@@ -278,7 +296,12 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": w["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": dict(workload_config(w, per_gpu, total, h_star), sample_per_step=S),
-        "cpu_baseline": {"value": value, "unit": "candidates/s", "cores": threads, "kind": "port", "sample": sample_desc},
+        "cpu_baseline": {"value": value, "unit": "candidates/s", "cores": threads, "kind": "port", "sample": sample_desc,
+                         # SURVEY 8(d)'s second CPU number: the loop the reference's propose_location really runs
+                         "propose_location_path": None if dt_pc is None else {
+                             "value": P / dt_pc, "unit": "candidates/s",
+                             "sample": "%d candidates, one eval each: predict(candidate) + _get_incumbent's "
+                                       "predict(train) (acquisitions.py:59-92), oracle port" % P}},
         "e2e": {"value": value, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

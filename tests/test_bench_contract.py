@@ -31,6 +31,9 @@ def test_reference_arm_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0 and d["vs_baseline"] is None
+    # the loop the reference's propose_location really runs (one eval per candidate) is timed beside the batched form
+    pc = d["cpu_baseline"]["propose_location_path"]
+    assert pc["unit"] == "candidates/s" and 0 < pc["value"] < d["value"]
     # the CPU arm names exactly the configuration the B200 arm runs at this N (the static part of `config`)
     import bench
     w = bench.WORKLOADS["cfg2"]
